@@ -1,0 +1,212 @@
+/*
+ * fd_b200.h — C ABI of the B200-native detection hot path for okieraised/rs-face-detection.
+ *
+ * One shared library (libfd_b200.so, hand-written CUDA for sm_100a).  Plain pointers and sizes only.
+ * Every function returns an fd_status (0 = ok); fd_last_error() gives the thread-local message.
+ * Reference citations are relative to the reference repo root.
+ *
+ * Threading: one fd_ctx per GPU per host thread; a ctx is not internally locked.  All work of a ctx is
+ * issued on the ctx's own CUDA stream.  "host" pointers are ordinary (or pinned) host memory owned by the
+ * caller; "dev" pointers are device memory on the ctx's GPU (fd_dev_alloc or any CUDA allocation).
+ */
+#ifndef FD_B200_H
+#define FD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FD_MAX_STRIDES 8
+#define FD_MAX_ANCHORS 4
+#define FD_ABI_VERSION 1
+
+typedef enum fd_status {
+    FD_OK = 0,
+    FD_ERR_INVALID = 1,    /* bad argument */
+    FD_ERR_CUDA = 2,       /* CUDA runtime error (message in fd_last_error) */
+    FD_ERR_NAN_SCORE = 3,  /* NaN score: the reference panics (utils.rs:92 partial_cmp().unwrap()) */
+    FD_ERR_CAPACITY = 4,   /* caller-provided output buffer too small */
+    FD_ERR_NO_DEVICE = 5,  /* no usable CUDA device: there is NO CPU fallback */
+    FD_ERR_ESTIMATE = 6    /* similarity estimation failed (reference: empty matrix, face_alignment.rs:64) */
+} fd_status;
+
+/* Constants of RetinaFaceDetection (face_detection.rs:19-38, 41-129), FaceDetectionConfig and
+ * FaceAlignmentConfig (face_pipeline/config.rs:13-55) as one plain struct. */
+typedef struct fd_config {
+    int32_t image_w, image_h;                              /* detector input, config.rs:27 (640,640) */
+    float conf_thr, iou_thr;                               /* config.rs:29-30 (0.7, 0.45) */
+    int32_t n_strides;
+    int32_t strides[FD_MAX_STRIDES];                       /* _feat_stride_fpn, face_detection.rs:52 */
+    int32_t num_anchors;                                   /* A per stride, face_detection.rs:100-103 */
+    float base_anchors[FD_MAX_STRIDES][FD_MAX_ANCHORS][4]; /* _anchors_fpn, face_detection.rs:94-98 */
+    float pixel_means[3], pixel_stds[3], pixel_scale;      /* face_detection.rs:105-107 (BGR order) */
+    float bbox_stds[4], landmark_std;                      /* face_detection.rs:91-92 */
+    int32_t crop_w, crop_h;                                /* config.rs:45 (112,112) */
+    float template_landmarks[5][2];                        /* config.rs:46-52 */
+} fd_config;
+
+typedef struct fd_ctx fd_ctx;
+
+/* Frame descriptor: BGR u8 HWC (an OpenCV CV_8UC3 Mat: face_detection.rs:131, face_alignment.rs:27). */
+typedef struct fd_frame {
+    const uint8_t *data; /* dev pointer for *_batch functions */
+    int32_t height, width, pitch;
+} fd_frame;
+
+/* ---- library / context ---------------------------------------------------------------------------- */
+int fd_abi_version(void);
+const char *fd_last_error(void);
+/* Fills the reference defaults; base anchors come from fd_generate_anchors_fpn2 (face_detection.rs:55-98). */
+int fd_config_default(fd_config *cfg);
+int fd_device_count(int *count);
+int fd_ctx_create(int device_id, const fd_config *cfg, fd_ctx **out);
+void fd_ctx_destroy(fd_ctx *ctx);
+int fd_ctx_get_config(const fd_ctx *ctx, fd_config *out);
+int fd_ctx_total_anchors(const fd_ctx *ctx, int32_t *out);   /* sum over strides of H*W*A (16800) */
+void *fd_ctx_stream(fd_ctx *ctx);                             /* cudaStream_t */
+int fd_ctx_synchronize(fd_ctx *ctx);
+/* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
+int fd_ctx_launch_count(const fd_ctx *ctx, int64_t *out);
+
+/* ---- memory helpers (so a host language needs no CUDA binding of its own) --------------------------- */
+int fd_dev_alloc(fd_ctx *ctx, size_t bytes, void **out);
+int fd_dev_free(fd_ctx *ctx, void *ptr);
+int fd_host_alloc_pinned(size_t bytes, void **out);
+int fd_host_free_pinned(void *ptr);
+int fd_memcpy_h2d(fd_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);     /* blocking */
+int fd_memcpy_d2h(fd_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);     /* blocking */
+int fd_memcpy_h2d_async(fd_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int fd_memcpy_d2h_async(fd_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+int fd_memset_dev(fd_ctx *ctx, void *dst_dev, int value, size_t bytes);
+
+/* ---- init-time anchor tables: HOST code, no GPU (generate_anchors.rs) ------------------------------- */
+/* generate_anchors.rs:41-59 ; out (n_ratios*n_scales, 4) */
+int fd_generate_anchors(int base_size, const float *ratios, int n_ratios, const float *scales, int n_scales,
+                        float *out, int *n_out);
+/* generate_anchors.rs:61-93 ; out ((dense?2:1)*n_ratios*n_scales, 4) */
+int fd_generate_anchors2(int base_size, const float *ratios, int n_ratios, const float *scales, int n_scales,
+                         int stride, int dense_anchor, float *out, int *n_out);
+/* generate_anchors.rs:95-114 ; level i uses ratios[i], scales[i]; out (n_levels, 4) */
+int fd_generate_anchors_fpn(const int *base_size, const float *ratios, const float *scales, int n_levels, float *out);
+/* generate_anchors.rs:116-138 ; cfg = per stride {base_size, ratios, scales}; strides processed in
+ * descending order; out receives, per stride in that order, its (n_ratios*n_scales*(dense?2:1), 4) block. */
+typedef struct fd_anchor_cfg {
+    int32_t stride, base_size;
+    int32_t n_ratios, n_scales;
+    float ratios[8], scales[8];
+    int32_t allowed_border;
+} fd_anchor_cfg;
+int fd_generate_anchors_fpn2(int dense_anchor, const fd_anchor_cfg *cfg, int n_cfg, float *out, int *rows_per_stride,
+                             int *strides_sorted);
+
+/* ---- drop-in single ops: HOST pointers in/out, blocking, computed on the GPU ------------------------ */
+/* processing::nms::nms(&Array2<f32>, f32) -> Vec<usize>  (nms.rs:3-65).  dets (K,5) any order; keep (cap>=K)
+ * receives indices into dets in pick order (stable descending-score sort done on the device). */
+int fd_nms(fd_ctx *ctx, const float *dets, int K, float thresh, int32_t *keep, int *num_keep);
+/* rcnn::cpu_nms::cpu_nms variant (cpu_nms.rs:10-55): suppresses on ovr >= thresh. */
+int fd_cpu_nms(fd_ctx *ctx, const float *dets, int K, float thresh, int32_t *keep, int *num_keep);
+/* Contract of the reference's C symbol `_nms` (gpu_nms.hpp:6-8, nms_kernel.cu:91-144): boxes (n, boxes_dim>=4)
+ * ALREADY sorted by score descending; keep = indices into the sorted array. */
+int fd_nms_sorted(fd_ctx *ctx, const float *boxes, int n, int boxes_dim, float thresh, int32_t *keep, int *num_out);
+/* The literal reference symbols, so src/rcnn/gpu_nms.rs links unchanged (uses a lazily created per-device ctx). */
+void _nms(int32_t *keep, int *num_out, const float *boxes_host, int boxes_num, int boxes_dim, float thresh, int device_id);
+void _set_device(int device_id);
+/* utils::argsort_descending (utils.rs:87-95): stable; NaN -> FD_ERR_NAN_SCORE. */
+int fd_argsort_descending(fd_ctx *ctx, const float *scores, int n, int32_t *order);
+/* rcnn::anchors::anchors (anchors.rs:3-21): out (H,W,A,4). */
+int fd_anchors_plane(fd_ctx *ctx, int height, int width, int stride, const float *base_anchors, int A, float *out);
+/* RetinaFaceDetection::bbox_pred (face_detection.rs:516-549): boxes (n,4), deltas (n,ncols>=4); columns >=4 copied. */
+int fd_bbox_pred(fd_ctx *ctx, const float *boxes, const float *deltas, int n, int ncols, float *out);
+/* bbox_transform::nonlinear_pred (bbox_transform.rs:90-120): every group of 4 columns regressed. */
+int fd_nonlinear_pred(fd_ctx *ctx, const float *boxes, const float *deltas, int n, int ncols, float *out);
+/* landmark_pred (face_detection.rs:551-570 (n,5,2) == bbox_transform.rs:123-160 (n,10)). */
+int fd_landmark_pred(fd_ctx *ctx, const float *boxes, const float *deltas, int n, float *out);
+/* bbox_transform::clip_boxes / clip_points (bbox_transform.rs:27-65), in place. */
+int fd_clip_boxes(fd_ctx *ctx, float *boxes, int rows, int cols, int im_h, int im_w);
+int fd_clip_points(fd_ctx *ctx, float *points, int rows, int cols, int im_h, int im_w);
+/* bbox_transform::iou_pred (:162-186), nonlinear_transform (:67-88). */
+int fd_iou_pred(fd_ctx *ctx, const float *boxes, const float *deltas, int n, int ncols, int num_classes, float *out);
+int fd_nonlinear_transform(fd_ctx *ctx, const float *ex_rois, const float *gt_rois, int n, float *out);
+/* rcnn::bbox::bbox_overlaps == bbox_transform::bbox_overlaps_py (bbox.rs:4-30): out (n,k). */
+int fd_bbox_overlaps(fd_ctx *ctx, const float *boxes, int n, const float *query, int k, float *out);
+/* RetinaFaceDetection::_preprocess geometry (face_detection.rs:140-153), host arithmetic. */
+int fd_letterbox_geometry(const fd_ctx *ctx, int img_h, int img_w, int *new_w, int *new_h, float *det_scale);
+/* _preprocess + tensor loop (face_detection.rs:131-230) for ONE host image -> (1,3,image_h,image_w) f32 host. */
+int fd_preprocess(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, float *out_nchw, float *det_scale);
+/* cv::resize(INTER_LINEAR) 8UC3 as called at face_detection.rs:156 (host in/out). */
+int fd_resize_linear(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, uint8_t *out, int out_h, int out_w);
+/* _forward post-CNN half + _postprocess (face_detection.rs:319-493) for ONE image, host tensors.
+ * heads[3*s+0..2] = scores (2A,H,W), bbox (4A,H,W), landmarks (10A,H,W) of stride s.
+ * det (cap,5), landmarks (cap,10). */
+int fd_detect(fd_ctx *ctx, const float *const *heads, int n_heads, float det_scale, float conf_thr, float iou_thr,
+              float *det, float *landmarks, int cap, int *num_det);
+/* cv::estimateAffinePartial2D(from, to, LMEDS, 3.0, 2000, 0.99, 10) for n_sets sets of 5 points
+ * (face_alignment.rs:50-59).  from (n_sets,5,2); to = NULL -> ctx template.  M (n_sets,2,3) f64; ok (n_sets). */
+int fd_estimate_affine_partial_2d(fd_ctx *ctx, const float *from, const float *to, int n_sets, double *M, uint8_t *ok);
+/* cv::warpAffine(img, M, (crop_w,crop_h), INTER_LINEAR, BORDER_CONSTANT, 0) (face_alignment.rs:119-126), host in/out. */
+int fd_warp_affine(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, const double *M, uint8_t *out,
+                   int out_h, int out_w);
+/* FaceAlignment::call main branch (face_alignment.rs:27-141) for ONE host image and ONE face.
+ * Returns FD_ERR_ESTIMATE where the reference would take its bbox-crop fallback. */
+int fd_align(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, const float *landmarks /*5x2*/,
+             uint8_t *crop /*crop_h x crop_w x 3*/, double *M_out /*2x3 or NULL*/);
+
+/* ---- batched device-resident pipeline (the benchmarked path); asynchronous on the ctx stream --------- */
+/* fd_nms with DEVICE buffers (asynchronous): dets_dev (K,5); keep_dev (K) int32; num_keep_dev (2) int32 =
+ * {count, NaN flag}.  The sort and the whole suppression sweep stay on the device. */
+int fd_nms_device(fd_ctx *ctx, const float *dets_dev, int K, float thresh, int32_t *keep_dev, int32_t *num_keep_dev);
+/* frames: HOST array of B descriptors whose .data are DEV pointers.  out_nchw_dev (B,3,image_h,image_w) f32.
+ * det_scale_host (B) is written before return (pure host arithmetic). */
+int fd_preprocess_batch(fd_ctx *ctx, const fd_frame *frames, int B, float *out_nchw_dev, float *det_scale_host);
+/* heads_dev[3*s+0..2]: (B,2A,H,W), (B,4A,H,W), (B,10A,H,W) dev tensors of stride s.  Results stay on the device
+ * inside the ctx until fd_detect_fetch / fd_align_detections. */
+int fd_detect_batch(fd_ctx *ctx, const float *const *heads_dev, int n_heads, int B, const float *det_scale_host,
+                    float conf_thr, float iou_thr);
+/* Blocks; copies the compact results of the last fd_detect_batch: counts (B), det (total,5), landmarks (total,10),
+ * rows in frame order then pick order.  cap_rows = capacity of det/landmarks in rows. */
+int fd_detect_fetch(fd_ctx *ctx, int32_t *counts, float *det, float *landmarks, int cap_rows, int *total);
+/* Device views of the last fd_detect_batch results (valid until the next call). */
+typedef struct fd_det_view {
+    const int32_t *counts_dev;    /* (B) */
+    const int32_t *offsets_dev;   /* (B+1) exclusive prefix */
+    const float *det_dev;         /* (total,5) */
+    const float *landmarks_dev;   /* (total,10) */
+    const int32_t *frame_idx_dev; /* (total) */
+    const int32_t *candidates_dev; /* (B) pre-NMS candidate counts K */
+} fd_det_view;
+int fd_detect_view(fd_ctx *ctx, fd_det_view *out);
+/* Aligns F faces: landmarks_dev (F,10) in original-frame coordinates, frame_idx_dev (F) into frames.
+ * crops_dev (F,crop_h,crop_w,3) u8; M_dev (F,6) f64 or NULL; ok_dev (F) u8 or NULL (0 -> estimation failed,
+ * crop zero-filled). */
+int fd_align_batch(fd_ctx *ctx, const fd_frame *frames, int B, const float *landmarks_dev, const int32_t *frame_idx_dev,
+                   int F, uint8_t *crops_dev, double *M_dev, uint8_t *ok_dev);
+/* Aligns every detection of the last fd_detect_batch without a host round trip.  crops_dev has room for cap_faces
+ * crops; detections beyond cap_faces are not aligned (fd_detect_fetch still reports them). */
+int fd_align_detections(fd_ctx *ctx, const fd_frame *frames, int B, uint8_t *crops_dev, int cap_faces, double *M_dev,
+                        uint8_t *ok_dev);
+
+/* ---- end-to-end with HOST buffers (bench.py "e2e"): H2D frames + heads, full path, D2H results -------- */
+typedef struct fd_host_batch_out {
+    int32_t *counts;      /* (B) */
+    float *det;           /* (cap_rows,5) */
+    float *landmarks;     /* (cap_rows,10) */
+    uint8_t *crops;       /* (cap_rows,crop_h,crop_w,3) */
+    float *det_scale;     /* (B) */
+    float *tensor;        /* (B,3,image_h,image_w) or NULL: CNN input stays on the device (Triton CUDA-shm) */
+    int32_t cap_rows;
+    int32_t total;        /* out */
+    int64_t h2d_bytes, d2h_bytes; /* out: bytes moved */
+} fd_host_batch_out;
+/* frames[].data are HOST pointers here; heads_host as in fd_detect_batch but host memory. */
+int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const float *const *heads_host, int n_heads,
+                     float conf_thr, float iou_thr, fd_host_batch_out *out);
+/* Device tensor written by the last fd_pipeline_host / usable as the CNN input. */
+int fd_pipeline_tensor_dev(fd_ctx *ctx, const float **out_nchw_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FD_B200_H */

@@ -1,0 +1,171 @@
+// fd_decode.cu — RetinaFace head decode for all strides and the whole batch in one launch, plus the result
+// finalisation (keep-gather + rescale).
+//
+// Replaces face_detection.rs:319-408 (per-stride decode), rcnn/anchors.rs:3-21 (anchor plane, recomputed on the fly
+// from 6 base anchors), face_detection.rs:516-570 (bbox_pred / landmark_pred), bbox_transform.rs:27-45 (clip_boxes),
+// the >= threshold compaction (:374-379) and, in finalize, the keep-gather (:432-464) and _postprocess (:473-493).
+//
+// Layout: heads are the network's NCHW tensors with a batch dimension, read in place (no NHWC re-layout): a warp
+// walks consecutive (h,w) positions of one channel plane, so every load is a coalesced 128-byte line.  The score
+// planes are read for every anchor; the 14 regression planes only where score >= thr.  Candidates are written
+// sparsely, indexed by their global anchor id (order 32|16|8, then (h,w,a) — face_detection.rs:410), so the later
+// sort key (score desc, anchor id asc) reproduces the reference's stable ordering without an ordered compaction.
+#include "fd_internal.cuh"
+
+namespace fd {
+
+typedef unsigned long long u64;
+
+struct HeadPtrs {
+    const float *p[3 * FD_MAX_STRIDES];
+};
+
+constexpr int CAND_REC = 12;  // floats per candidate record: 10 landmarks, score, pad
+
+__global__ void __launch_bounds__(256) decode_kernel(DecodeCfg c, HeadPtrs hp, float conf_thr, u64 *__restrict__ keys,
+                                                     float4 *__restrict__ cand_box, float *__restrict__ cand_rec,
+                                                     int *__restrict__ counts, int *__restrict__ status) {
+    const int b = blockIdx.y;
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool active = pos < c.total_pos;
+    int s = 0;
+    if (active) {
+#pragma unroll
+        for (int k = 1; k < FD_MAX_STRIDES; ++k)
+            if (k < c.n_strides && pos >= c.pos_off[k]) s = k;
+    }
+    const int local = active ? pos - c.pos_off[s] : 0;
+    const int fw = c.fw[s], hw = c.fh[s] * c.fw[s];
+    const int h = local / fw, w = local - h * fw;
+    const int A = c.A;
+    const float *sc = hp.p[3 * s] + (size_t)b * 2 * A * hw;
+    const float *bb = hp.p[3 * s + 1] + (size_t)b * 4 * A * hw;
+    const float *lm = hp.p[3 * s + 2] + (size_t)b * 10 * A * hw;
+    const size_t img_base = (size_t)b * c.total_anchors;
+    for (int a = 0; a < A; ++a) {
+        float score = 0.0f;
+        bool pass = false;
+        if (active) {
+            score = __ldg(sc + (size_t)(A + a) * hw + local);  // fg scores are channels A.. (face_detection.rs:322)
+            if (score != score) atomicExch(&status[0], 1);     // the reference panics on NaN (utils.rs:92)
+            pass = score >= conf_thr;                          // face_detection.rs:375
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (bal == 0) continue;
+        int base = 0;
+        const int leader = __ffs(bal) - 1;
+        if (lane == leader) base = atomicAdd(&counts[b], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (!pass) continue;
+        const int slot = base + __popc(bal & ((1u << lane) - 1u));
+        const int id = c.anchor_off[s] + local * A + a;
+        // anchor = base + (w*stride, h*stride, w*stride, h*stride)   (anchors.rs:8-16)
+        const float sw = (float)(w * c.stride[s]), sh = (float)(h * c.stride[s]);
+        const float ax1 = __fadd_rn(c.base[s][a][0], sw), ay1 = __fadd_rn(c.base[s][a][1], sh);
+        const float ax2 = __fadd_rn(c.base[s][a][2], sw), ay2 = __fadd_rn(c.base[s][a][3], sh);
+        // face_detection.rs:522-525
+        const float aw = __fadd_rn(__fsub_rn(ax2, ax1), 1.0f), ah = __fadd_rn(__fsub_rn(ay2, ay1), 1.0f);
+        const float cx = __fadd_rn(ax1, __fmul_rn(0.5f, __fsub_rn(aw, 1.0f)));
+        const float cy = __fadd_rn(ay1, __fmul_rn(0.5f, __fsub_rn(ah, 1.0f)));
+        const float dx = __fmul_rn(__ldg(bb + (size_t)(4 * a + 0) * hw + local), c.bbox_stds[0]);  // :366-371
+        const float dy = __fmul_rn(__ldg(bb + (size_t)(4 * a + 1) * hw + local), c.bbox_stds[1]);
+        const float dw = __fmul_rn(__ldg(bb + (size_t)(4 * a + 2) * hw + local), c.bbox_stds[2]);
+        const float dh = __fmul_rn(__ldg(bb + (size_t)(4 * a + 3) * hw + local), c.bbox_stds[3]);
+        // :532-535.  exp through fp64 is correctly rounded to <=0.5 ulp; the reference's f32::exp is the platform expf.
+        const float pcx = __fadd_rn(__fmul_rn(dx, aw), cx), pcy = __fadd_rn(__fmul_rn(dy, ah), cy);
+        const float pw = __fmul_rn((float)exp((double)dw), aw), ph = __fmul_rn((float)exp((double)dh), ah);
+        // :539-542, then clip_boxes to the padded detector image (:373, bbox_transform.rs:36-42)
+        const float hwx = __fmul_rn(0.5f, __fsub_rn(pw, 1.0f)), hwy = __fmul_rn(0.5f, __fsub_rn(ph, 1.0f));
+        float4 box;
+        box.x = fmaxf(fminf(__fsub_rn(pcx, hwx), c.clip_w), 0.0f);
+        box.y = fmaxf(fminf(__fsub_rn(pcy, hwy), c.clip_h), 0.0f);
+        box.z = fmaxf(fminf(__fadd_rn(pcx, hwx), c.clip_w), 0.0f);
+        box.w = fmaxf(fminf(__fadd_rn(pcy, hwy), c.clip_h), 0.0f);
+        cand_box[img_base + id] = box;
+        // landmarks from the ANCHOR box, never clipped (:399, :564-567)
+        float rec[CAND_REC];
+#pragma unroll
+        for (int p = 0; p < 5; ++p) {
+            float lx = __fmul_rn(__ldg(lm + (size_t)(10 * a + 2 * p) * hw + local), c.landmark_std);
+            float ly = __fmul_rn(__ldg(lm + (size_t)(10 * a + 2 * p + 1) * hw + local), c.landmark_std);
+            rec[2 * p] = __fadd_rn(__fmul_rn(lx, aw), cx);
+            rec[2 * p + 1] = __fadd_rn(__fmul_rn(ly, ah), cy);
+        }
+        rec[10] = score;
+        rec[11] = 0.0f;
+        float4 *dst = reinterpret_cast<float4 *>(cand_rec + (img_base + id) * CAND_REC);
+        dst[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+        dst[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+        dst[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+        keys[img_base + slot] = ((u64)desc_key(score) << 32) | (unsigned)id;
+    }
+}
+
+// One CTA per image: exclusive offset over the kept counts, then gather + rescale (division, face_detection.rs:477-483).
+__global__ void __launch_bounds__(256) finalize_kernel(int B, int TA, const int *__restrict__ keep_count,
+                                                       const int *__restrict__ keep_src, const float4 *__restrict__ cand_box,
+                                                       const float *__restrict__ cand_rec, const float *__restrict__ det_scale,
+                                                       int *__restrict__ offsets, float *__restrict__ out_det,
+                                                       float *__restrict__ out_lmk, int *__restrict__ out_frame_idx,
+                                                       int *__restrict__ status) {
+    __shared__ int red[8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    int part = 0;
+    for (int i = tid; i < b; i += 256) part += max(keep_count[i], 0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((tid & 31) == 0) red[tid >> 5] = part;
+    __syncthreads();
+    int offset = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) offset += red[k];
+    const int M = max(keep_count[b], 0);
+    if (tid == 0) {
+        offsets[b] = offset;
+        if (b == B - 1) {
+            offsets[B] = offset + M;
+            status[2] = offset + M;
+        }
+    }
+    const float ds = det_scale[b];
+    const size_t img_base = (size_t)b * TA;
+    for (int m = tid; m < M; m += 256) {
+        const int id = keep_src[img_base + m];
+        const float4 bx = cand_box[img_base + id];
+        const float *rec = cand_rec + (img_base + id) * CAND_REC;
+        float *d = out_det + (size_t)(offset + m) * 5;
+        d[0] = __fdiv_rn(bx.x, ds);
+        d[1] = __fdiv_rn(bx.y, ds);
+        d[2] = __fdiv_rn(bx.z, ds);
+        d[3] = __fdiv_rn(bx.w, ds);
+        d[4] = rec[10];
+        float *l = out_lmk + (size_t)(offset + m) * 10;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) l[k] = __fdiv_rn(rec[k], ds);
+        out_frame_idx[offset + m] = b;
+    }
+}
+
+int decode_launch(fd_ctx *ctx, const float *const *heads_dev, int B, float conf_thr) {
+    HeadPtrs hp;
+    for (int i = 0; i < 3 * FD_MAX_STRIDES; ++i) hp.p[i] = i < 3 * ctx->dcfg.n_strides ? heads_dev[i] : nullptr;
+    dim3 grid((ctx->dcfg.total_pos + 255) / 256, B);
+    decode_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->dcfg, hp, conf_thr, ctx->cand_keys.as<u64>(), ctx->cand_box.as<float4>(),
+                                                 ctx->cand_lmk.as<float>(), ctx->cand_count.as<int>(),
+                                                 ctx->status_dev.as<int>());
+    FD_LAUNCH_CHECK(ctx);
+    return FD_OK;
+}
+
+int finalize_launch(fd_ctx *ctx, int B) {
+    finalize_kernel<<<B, 256, 0, ctx->stream>>>(B, ctx->dcfg.total_anchors, ctx->keep_count.as<int>(), ctx->keep_src.as<int>(),
+                                                ctx->cand_box.as<float4>(), ctx->cand_lmk.as<float>(),
+                                                ctx->det_scale_dev.as<float>(), ctx->out_offsets.as<int>(),
+                                                ctx->out_det.as<float>(), ctx->out_lmk.as<float>(),
+                                                ctx->out_frame_idx.as<int>(), ctx->status_dev.as<int>());
+    FD_LAUNCH_CHECK(ctx);
+    return FD_OK;
+}
+
+}  // namespace fd

@@ -1,0 +1,190 @@
+// fd_internal.cuh — shared internals of libfd_b200.so (context, error plumbing, device helpers).
+// Product code: hand-written CUDA for sm_100a.  No CPU fallback anywhere: every entry point needs a GPU.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/fd_b200.h"
+
+#define FD_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace fd {
+
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+
+#define FD_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return ::fd::fail(FD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));        \
+    } while (0)
+#define FD_TRY(call)                 \
+    do {                             \
+        int _s = (call);             \
+        if (_s != FD_OK) return _s;  \
+    } while (0)
+#define FD_REQUIRE(cond, msg)                                           \
+    do {                                                                \
+        if (!(cond)) return ::fd::fail(FD_ERR_INVALID, (msg));          \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);  // grows (never shrinks); contents are NOT preserved on growth
+    void release();
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// Per-frame descriptor as the kernels see it.
+struct FrameDev {
+    const uint8_t *data;
+    int h, w, pitch;
+    int new_w, new_h;        // letterbox content size
+    double scale_x, scale_y; // cv::resize inverse scales
+};
+
+// Decode geometry passed by value to kernels.
+struct DecodeCfg {
+    int n_strides, A;
+    int stride[FD_MAX_STRIDES];
+    int fh[FD_MAX_STRIDES], fw[FD_MAX_STRIDES];
+    int pos_off[FD_MAX_STRIDES + 1];    // prefix of H*W over strides
+    int anchor_off[FD_MAX_STRIDES + 1]; // prefix of H*W*A
+    float base[FD_MAX_STRIDES][FD_MAX_ANCHORS][4];
+    float bbox_stds[4], landmark_std;
+    float clip_w, clip_h; // image_w-1, image_h-1 as f32 (bbox_transform.rs:30-31)
+    int total_pos, total_anchors;
+};
+
+}  // namespace fd
+
+struct fd_ctx {
+    int device = 0;
+    fd_config cfg{};
+    cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // copy stream for the host pipeline
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int num_sms = 0;
+    int max_smem_optin = 0;
+    int64_t launches = 0;
+    fd::DecodeCfg dcfg{};
+
+    // generic scratch for the host-pointer drop-in ops
+    fd::DevBuf scratch[6];
+    fd::PinnedBuf pinned[3];
+
+    // batched pipeline state
+    fd::DevBuf frames_dev;       // FrameDev[B]
+    fd::DevBuf det_scale_dev;    // float[B]
+    fd::DevBuf cand_count;       // int[B] (+ error flags)
+    fd::DevBuf cand_keys;        // u64[B][total_anchors]
+    fd::DevBuf cand_box;         // float4[B][total_anchors] (indexed by anchor id)
+    fd::DevBuf cand_lmk;         // float[B][total_anchors][10]
+    fd::DevBuf keep_src;         // int[B][total_anchors] kept anchor ids in pick order
+    fd::DevBuf keep_count;       // int[B]
+    fd::DevBuf status_dev;       // int[8]: [0]=nan flag, [1]=n_big, [2]=total faces
+    fd::DevBuf big_list;         // int[B] images that need the big path
+    fd::DevBuf out_offsets;      // int[B+1]
+    fd::DevBuf out_det;          // float[total][5]
+    fd::DevBuf out_lmk;          // float[total][10]
+    fd::DevBuf out_frame_idx;    // int[total]
+    fd::DevBuf align_M;          // double[F][12] (M, inverse)
+    fd::DevBuf align_ok;         // u8[F]
+    fd::DevBuf nms_ws[8];        // big-path workspaces
+    fd::DevBuf pipe_frames;      // host pipeline: device copies of frames
+    fd::DevBuf pipe_heads[3 * FD_MAX_STRIDES];
+    fd::DevBuf pipe_tensor;
+    fd::DevBuf pipe_crops;
+    int last_B = 0;
+    int last_out_cap = 0;
+    bool detect_pending = false; // results enqueued, NaN check / big-path fix-up not yet done (lazy, at fetch)
+    float last_iou = 0.f;
+    std::vector<unsigned char> frames_shadow;    // host copy of the descriptor table currently on the device
+    std::vector<float> det_scale_shadow;
+    // last fd_align_detections call, replayed by the lazy fix-up if the detections it consumed were incomplete
+    bool align_replay = false;
+    uint8_t *align_crops = nullptr;
+    int align_cap = 0;
+    double *align_M_out = nullptr;
+    uint8_t *align_ok_out = nullptr;
+};
+
+namespace fd {
+
+int check_ctx(const fd_ctx *ctx);
+
+#define FD_LAUNCH_CHECK(ctx)                          \
+    do {                                              \
+        (ctx)->launches++;                            \
+        FD_CUDA(cudaGetLastError());                  \
+    } while (0)
+
+// ---- device helpers ---------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// Maps an f32 to a u32 whose ASCENDING order is the DESCENDING float order (for finite / inf values).
+__device__ __forceinline__ uint32_t desc_key(float f) {
+    uint32_t u = __float_as_uint(f);
+    uint32_t asc = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending-orderable
+    return ~asc;
+}
+
+__device__ __forceinline__ float box_area(float4 b) {
+    // (x2 - x1 + 1) * (y2 - y1 + 1), each op rounded separately (nms.rs:46,50)
+    return __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.0f), __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
+}
+
+// MODE 0: processing::nms::nms — a box survives iff ovr <= thr (nms.rs:58), so suppress = !(ovr <= thr)
+// MODE 1: rcnn::cpu_nms — suppress iff ovr >= thr (cpu_nms.rs:48)
+// FAST: every box has a finite positive area and thr admits the "no intersection => no suppression" shortcut
+// (MODE 0: thr >= 0, MODE 1: thr > 0); then a pair with w<=0 or h<=0 has ovr == +0 exactly and is skipped
+// without the division.  Otherwise the full IEEE expression is evaluated for every pair.
+template <int MODE, bool FAST>
+__device__ __forceinline__ bool iou_suppresses(const float4 a, const float4 b, const float thr) {
+    float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+    float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    float w = fmaxf(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
+    float h = fmaxf(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
+    if (FAST) {
+        if (!(w > 0.0f && h > 0.0f)) return false;
+    }
+    float inter = __fmul_rn(w, h);
+    float uni = __fsub_rn(__fadd_rn(box_area(a), box_area(b)), inter);
+    float ovr = __fdiv_rn(inter, uni);
+    return MODE == 0 ? !(ovr <= thr) : (ovr >= thr);
+}
+
+__device__ __forceinline__ bool box_is_fast_ok(float4 b) {
+    float a = box_area(b);
+    return isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w) && isfinite(a) && a > 0.0f;
+}
+
+#endif  // __CUDACC__
+
+// stage entry points implemented across the .cu files
+int preprocess_launch(fd_ctx *ctx, const FrameDev *frames_dev, int B, float *out_nchw_dev, int max_row_bytes);
+int resize_launch(fd_ctx *ctx, const FrameDev &frame, uint8_t *out_dev, int out_h, int out_w);
+int decode_launch(fd_ctx *ctx, const float *const *heads_dev, int B, float conf_thr);
+int nms_batch_launch(fd_ctx *ctx, int B, float iou_thr);
+int nms_batch_big_image(fd_ctx *ctx, int b, int K, float iou_thr);
+int finalize_launch(fd_ctx *ctx, int B);
+int nms_device(fd_ctx *ctx, const float *dets_dev, int K, int stride_floats, float thr, int mode, bool presorted,
+               int32_t *keep_dev, int32_t *num_keep_dev);
+int argsort_device(fd_ctx *ctx, const float *scores_as_dets, int n, int stride, int32_t *order_dev, int32_t *flag_dev);
+int estimate_launch(fd_ctx *ctx, const float *from_dev, const float *to_dev, const int *count_dev, int F_cap,
+                    double *M12_dev, double *M_out_dev, uint8_t *ok_dev, uint8_t *ok_out_dev);
+int invert_launch(fd_ctx *ctx, const double *M_dev, int F, double *M12_dev, uint8_t *ok_dev);
+int warp_launch(fd_ctx *ctx, const FrameDev *frames_dev, const int32_t *frame_idx_dev, const double *M12_dev,
+                const uint8_t *ok_dev, const int *count_dev, int F_cap, uint8_t *crops_dev, int cw, int ch);
+
+}  // namespace fd

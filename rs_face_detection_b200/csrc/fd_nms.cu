@@ -1,0 +1,821 @@
+// fd_nms.cu — stable descending sort + exact greedy IoU NMS, entirely on the device.
+//
+// Replaces processing::nms::nms (src/processing/nms.rs:3-65), rcnn::cpu_nms (src/rcnn/cpu_nms.rs:10-55) and the
+// vestigial CUDA path `_nms` (src/nms_kernel.cu:91-144).  Not a port of the latter: no N x N/64 mask in HBM, no
+// D2H mask copy, no CPU sweep.
+//
+// Algorithm ("peel"): boxes sorted by (score desc, index asc).  The stream of not-yet-removed boxes is consumed
+// HEAD (<=1024) boxes at a time.  For a head, a 64-bit "earlier-overlap" mask (row i = bits of earlier head boxes j<i
+// with IoU > thr) is built in shared memory; the greedy keep set of the head is then resolved by warp/block-parallel
+// rounds over that bitmask (a box is suppressed once an earlier overlapping box is KEPT, kept once all earlier
+// overlapping boxes are decided-suppressed) — the same result as the sequential sweep, in O(dependency depth) rounds.
+// Only the KEPT boxes of the head are then tested against the rest of the stream, which is compacted in order.
+// Work ~ kept x N instead of N^2/2, and nothing larger than the sorted boxes ever touches HBM.
+//
+//   K <= 4096 : one CTA does sort + peel out of shared memory (batched: one CTA per image).
+//   K  > 4096 : LSD radix sort (own kernels) + one cooperative persistent kernel; CTA 0 resolves heads, all CTAs push.
+#include <cooperative_groups.h>
+#include <algorithm>
+#include "fd_internal.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace fd {
+
+typedef unsigned long long u64;
+
+constexpr int NT = 1024;          // threads per NMS CTA
+constexpr int NWARPS = NT / 32;
+constexpr int HEAD = 1024;        // boxes resolved per stage
+constexpr int HEAD_WORDS = HEAD / 64;
+constexpr int MASK_WORDS = 64 * (HEAD_WORDS * (HEAD_WORDS + 1) / 2);  // lower-triangular tiles
+constexpr int SMALL_CAP = 4096;
+
+// triangular tile layout: tile-row t holds (t+1) 64x64 tiles; inside a tile-row the word index is the slow axis so
+// that consecutive rows (lanes) hit consecutive 8-byte words.
+__device__ __forceinline__ int mask_index(int i, int w) {
+    int t = i >> 6;
+    return 64 * (t * (t + 1) / 2) + w * 64 + (i & 63);
+}
+
+// ---- head resolve -------------------------------------------------------------------------------------
+template <int MODE, bool FAST>
+__device__ void build_mask(const float4 *__restrict__ hbox, int S, u64 *__restrict__ mask, float thr) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = (S + 63) >> 6;
+    const int nunits = T * (T + 1);  // (tile pairs) x 2 half-tiles of 32 rows
+    for (int u = warp; u < nunits; u += NWARPS) {
+        int p = u >> 1, half = u & 1;
+        int ti = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= p) ++ti;
+        while (ti * (ti + 1) / 2 > p) --ti;
+        int tj = p - ti * (ti + 1) / 2;
+        int i = ti * 64 + half * 32 + lane;
+        int jbase = tj * 64;
+        int lane_bound = min(64, S - jbase);                 // columns that exist
+        if (ti == tj) lane_bound = min(lane_bound, i - jbase);  // only earlier boxes j < i
+        if (i >= S) lane_bound = 0;
+        int warp_bound = min(64, S - jbase);
+        if (ti == tj) warp_bound = min(warp_bound, half * 32 + 31);
+        u64 word = 0;
+        float4 bi = hbox[min(i, S - 1)];
+        for (int c = 0; c < warp_bound; ++c) {
+            float4 bj = hbox[jbase + c];  // warp-uniform address: shared-memory broadcast
+            bool s = iou_suppresses<MODE, FAST>(bj, bi, thr);
+            if (s && c < lane_bound) word |= (1ull << c);
+        }
+        mask[mask_index(i, tj)] = word;
+    }
+}
+
+// kept/und: HEAD_WORDS words each in shared memory.  On return kept holds the greedy keep set of the head.
+__device__ void resolve_rounds(const u64 *__restrict__ mask, int S, u64 *kept, u64 *und) {
+    const int i = threadIdx.x;
+    if (i < HEAD_WORDS) {
+        int lo = i * 64;
+        int nbits = min(64, max(0, S - lo));
+        und[i] = nbits == 64 ? ~0ull : ((1ull << nbits) - 1ull);
+        kept[i] = 0ull;
+    }
+    __syncthreads();
+    const int t = i >> 6;
+    const u64 bit = 1ull << (i & 63);
+    bool undecided = i < S;
+    while (true) {
+        int dec = 0;  // 0 wait, 1 keep, 2 suppress
+        if (undecided) {
+            bool sup = false, wait = false;
+            for (int w = 0; w <= t; ++w) {
+                u64 e = mask[mask_index(i, w)];
+                if (e & kept[w]) { sup = true; break; }
+                if (e & und[w]) wait = true;
+            }
+            dec = sup ? 2 : (wait ? 0 : 1);
+        }
+        __syncthreads();  // every read of kept/und of this round is done
+        if (dec == 1) atomicOr(&kept[t], bit);
+        if (dec != 0) {
+            atomicAnd(&und[t], ~bit);
+            undecided = false;
+        }
+        if (!__syncthreads_or(undecided)) break;
+    }
+}
+
+// exclusive position of `flag` among the block's threads (thread order) and the block total
+__device__ __forceinline__ int block_compact_pos(bool flag, int *warp_sums, int *total) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned bal = __ballot_sync(0xffffffffu, flag);
+    int within = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_sums[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+        int v = warp_sums[lane];
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        warp_sums[lane] = incl - v;
+        if (lane == 31) warp_sums[32] = incl;
+    }
+    __syncthreads();
+    int pos = warp_sums[warp] + within;
+    *total = warp_sums[32];
+    __syncthreads();
+    return pos;
+}
+
+// position of kept bit i inside the kept bitset (ordered) and total count
+__device__ __forceinline__ int kept_rank(const u64 *kept, int i, int *total) {
+    int pos = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < HEAD_WORDS; ++w) {
+        int c = __popcll(kept[w]);
+        if (w < (i >> 6)) pos += c;
+        tot += c;
+    }
+    pos += __popcll(kept[i >> 6] & ((1ull << (i & 63)) - 1ull));
+    *total = tot;
+    return pos;
+}
+
+// ---- shared memory carve-up of the single-CTA kernel ------------------------------------------------------
+struct SmallSmem {
+    float4 sbox[SMALL_CAP];   // boxes in sorted order
+    float4 hbox[HEAD];        // current head
+    u64 mask[MASK_WORDS];     // also: kept boxes of the head (float4[HEAD]) during the push
+    u64 keys[SMALL_CAP];      // sort keys; afterwards two int streams [2][SMALL_CAP]
+    int sidx[SMALL_CAP];      // source index of sorted rank r
+    u64 kept[HEAD_WORDS], und[HEAD_WORDS];
+    int warp_sums[33];
+    int misc[7];
+};
+
+// Box source: `boxes + idx*BS` floats.  BS==4 -> aligned float4 loads.
+template <int BS>
+__device__ __forceinline__ float4 load_box(const float *__restrict__ boxes, int idx, int stride) {
+    if (BS == 4) return __ldg(reinterpret_cast<const float4 *>(boxes) + idx);
+    const float *p = boxes + (size_t)idx * stride;
+    return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+}
+
+struct SmallArgs {
+    const u64 *keys;          // [B][key_stride] or nullptr -> keys made from dets scores (column 4)
+    size_t key_stride;
+    const float *boxes;       // [B][box_batch_stride floats]
+    size_t box_batch_stride;
+    int box_stride;           // floats between consecutive boxes
+    const int *counts;        // [B] or nullptr -> K
+    int K;
+    int presorted;            // 1 -> input already in pick order (the `_nms` contract): no sort
+    int sort_only;            // 1 -> write the sorted source indices and stop (argsort_descending)
+    float thr;
+    int *keep;                // [B][keep_stride] source indices in pick order
+    size_t keep_stride;
+    int *keep_count;          // [B]
+    int *status;              // [0] NaN flag, [1] number of problems deferred to the big path
+    int *big_list;            // problems with K > SMALL_CAP (or nullptr)
+};
+
+template <int MODE, int BS>
+__global__ void __launch_bounds__(NT, 1) nms_cta_kernel(SmallArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmallSmem &sm = *reinterpret_cast<SmallSmem *>(smem_raw);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int K = a.counts ? a.counts[b] : a.K;
+    int *keep = a.keep + (size_t)b * a.keep_stride;
+    if (K <= 0) {
+        if (tid == 0) a.keep_count[b] = 0;
+        return;
+    }
+    if (K > SMALL_CAP) {
+        if (tid == 0) {
+            a.keep_count[b] = -1;
+            if (a.big_list) a.big_list[atomicAdd(&a.status[1], 1)] = b;
+        }
+        return;
+    }
+    const float *boxes = a.boxes + (size_t)b * a.box_batch_stride;
+
+    // ---- 1. keys + bitonic sort (ascending u64 == score desc, index asc) ----
+    int n2 = 2;
+    while (n2 < K) n2 <<= 1;
+    bool nan_seen = false;
+    for (int i = tid; i < n2; i += NT) {
+        u64 key = ~0ull;
+        if (i < K) {
+            if (a.keys) key = a.keys[(size_t)b * a.key_stride + i];
+            else {
+                float s = __ldg(boxes + (size_t)i * a.box_stride + 4);
+                nan_seen |= (s != s);
+                key = ((u64)desc_key(s) << 32) | (unsigned)i;
+            }
+        }
+        sm.keys[i] = key;
+    }
+    if (__syncthreads_or(nan_seen)) {
+        if (tid == 0) {
+            atomicExch(&a.status[0], 1);
+            a.keep_count[b] = 0;
+        }
+        return;
+    }
+    if (!a.presorted) {
+        for (unsigned k = 2; k <= (unsigned)n2; k <<= 1) {
+            for (unsigned j = k >> 1; j > 0; j >>= 1) {
+                for (unsigned t = tid; t < (unsigned)n2 / 2; t += NT) {
+                    unsigned i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    unsigned l = i | j;
+                    bool up = ((i & k) == 0);
+                    u64 x = sm.keys[i], y = sm.keys[l];
+                    if ((x > y) == up) {
+                        sm.keys[i] = y;
+                        sm.keys[l] = x;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    if (a.sort_only) {
+        for (int r = tid; r < K; r += NT) keep[r] = (int)(unsigned)sm.keys[r];
+        if (tid == 0) a.keep_count[b] = K;
+        return;
+    }
+
+    // ---- 2. gather boxes in sorted order ----
+    bool ok = true;
+    for (int r = tid; r < K; r += NT) {
+        int idx = (int)(unsigned)sm.keys[r];
+        sm.sidx[r] = idx;
+        float4 bx = load_box<BS>(boxes, idx, a.box_stride);
+        sm.sbox[r] = bx;
+        ok &= box_is_fast_ok(bx);
+    }
+    const bool thr_ok = MODE == 0 ? (a.thr >= 0.0f) : (a.thr > 0.0f);
+    const bool fast = __syncthreads_and(ok) && thr_ok;  // also fences the key reads before the streams alias them
+
+    int *stream_cur = reinterpret_cast<int *>(sm.keys);
+    int *stream_nxt = stream_cur + SMALL_CAP;
+    float4 *kbox = reinterpret_cast<float4 *>(sm.mask);
+    bool identity = true;
+    int len = K, nk_total = 0;
+
+    // ---- 3. peel ----
+    while (len > 0) {
+        const int S = min(HEAD, len);
+        int my_rank = 0;
+        if (tid < S) {
+            my_rank = identity ? tid : stream_cur[tid];
+            sm.hbox[tid] = sm.sbox[my_rank];
+        }
+        __syncthreads();
+        if (fast) build_mask<MODE, true>(sm.hbox, S, sm.mask, a.thr);
+        else build_mask<MODE, false>(sm.hbox, S, sm.mask, a.thr);
+        __syncthreads();
+        resolve_rounds(sm.mask, S, sm.kept, sm.und);
+        // (resolve_rounds ends on a block-wide barrier: mask is dead from here, kept is final)
+        int nkept = 0;
+        bool is_kept = false;
+        int pos = 0;
+        if (tid < S) {
+            is_kept = (sm.kept[tid >> 6] >> (tid & 63)) & 1ull;
+            pos = kept_rank(sm.kept, tid, &nkept);
+        } else {
+            kept_rank(sm.kept, 0, &nkept);
+        }
+        const int rem = len - S;
+        if (is_kept) {
+            keep[nk_total + pos] = sm.sidx[my_rank];
+            if (rem > 0) kbox[pos] = sm.hbox[tid];
+        }
+        nk_total += nkept;
+        __syncthreads();
+        if (rem <= 0) break;
+        int new_len = 0;
+        for (int base = 0; base < rem; base += NT) {
+            int r = base + tid;
+            bool alive = false;
+            int rk = 0;
+            if (r < rem) {
+                rk = identity ? (S + r) : stream_cur[S + r];
+                float4 bx = sm.sbox[rk];
+                alive = true;
+                if (fast) {
+                    for (int k = 0; k < nkept; ++k)
+                        if (iou_suppresses<MODE, true>(kbox[k], bx, a.thr)) { alive = false; break; }
+                } else {
+                    for (int k = 0; k < nkept; ++k)
+                        if (iou_suppresses<MODE, false>(kbox[k], bx, a.thr)) { alive = false; break; }
+                }
+            }
+            int total;
+            int p = block_compact_pos(alive, sm.warp_sums, &total);
+            if (alive) stream_nxt[new_len + p] = rk;
+            new_len += total;
+        }
+        __syncthreads();
+        int *tmp = stream_cur;
+        stream_cur = stream_nxt;
+        stream_nxt = tmp;
+        identity = false;
+        len = new_len;
+    }
+    if (tid == 0) a.keep_count[b] = nk_total;
+}
+
+// ============================================================================================================
+// Big path: radix sort of u64 keys (own kernels) + cooperative peel
+// ============================================================================================================
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+
+__global__ void make_keys_kernel(const float *__restrict__ dets, int n, int stride, u64 *__restrict__ keys, int *status) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = __ldg(dets + (size_t)i * stride + 4);
+    if (s != s) atomicExch(&status[0], 1);
+    keys[i] = ((u64)desc_key(s) << 32) | (unsigned)i;
+}
+__global__ void iota_keys_kernel(int n, u64 *__restrict__ keys) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = (u64)(unsigned)i;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const u64 *__restrict__ keys, int n, int shift,
+                                                                int *__restrict__ hist, int ntiles) {
+    __shared__ int h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    int base = blockIdx.x * RS_TILE;
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        int e = base + k * RS_THREADS + threadIdx.x;
+        if (e < n) atomicAdd(&h[(int)((keys[e] >> shift) & 0xffull)], 1);
+    }
+    __syncthreads();
+    hist[threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan over m ints by one CTA
+__global__ void __launch_bounds__(1024) scan_kernel(int *__restrict__ data, int m) {
+    __shared__ int warp_sums[33];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int base = 0; base < m; base += 1024) {
+        int i = base + threadIdx.x;
+        int v = i < m ? data[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_sums[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int nb = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += nb;
+            }
+            warp_sums[lane] = wi - w;
+            if (lane == 31) warp_sums[32] = wi;
+        }
+        __syncthreads();
+        int carry = carry_s;
+        if (i < m) data[i] = carry + warp_sums[warp] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + warp_sums[32];
+        __syncthreads();
+    }
+}
+
+// stable scatter: element order inside a tile is (warp, round, lane)
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
+                                                                   int n, int shift, const int *__restrict__ hist, int ntiles) {
+    __shared__ int wcount[RS_THREADS / 32][256];
+    __shared__ int gofs[256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (RS_THREADS / 32) * 256; i += RS_THREADS) (&wcount[0][0])[i] = 0;
+    gofs[threadIdx.x] = hist[threadIdx.x * ntiles + blockIdx.x];
+    __syncthreads();
+    const int wbase = blockIdx.x * RS_TILE + warp * (32 * RS_ITEMS);
+    u64 key[RS_ITEMS];
+    int rank[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        int e = wbase + r * 32 + lane;
+        bool valid = e < n;
+        key[r] = valid ? keys_in[e] : 0ull;
+        int d = valid ? (int)((key[r] >> shift) & 0xffull) : 256;
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        int prior = valid ? wcount[warp][d] : 0;
+        rank[r] = prior + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+        if (valid && lane == (__ffs(peers) - 1)) wcount[warp][d] = prior + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        int d = threadIdx.x, run = 0;
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; ++w) {
+            int c = wcount[w][d];
+            wcount[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        int e = wbase + r * 32 + lane;
+        if (e < n) {
+            int d = (int)((key[r] >> shift) & 0xffull);
+            keys_out[gofs[d] + wcount[warp][d] + rank[r]] = key[r];
+        }
+    }
+}
+
+__global__ void gather_sorted_boxes_kernel(const u64 *__restrict__ keys, int n, const float *__restrict__ boxes, int stride,
+                                           float4 *__restrict__ sbox, int *status) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = true;
+    if (r < n) {
+        int idx = (int)(unsigned)keys[r];
+        const float *p = boxes + (size_t)idx * stride;
+        float4 bx = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+        sbox[r] = bx;
+        ok = box_is_fast_ok(bx);
+    }
+    if (!__all_sync(0xffffffffu, ok)) {
+        if ((threadIdx.x & 31) == 0) atomicExch(&status[2], 1);  // not "fast"
+    }
+}
+
+__global__ void map_keep_kernel(const int *__restrict__ keep_ranks, const int *__restrict__ state, const u64 *__restrict__ keys,
+                                int *__restrict__ keep, int *__restrict__ num_keep) {
+    int n = state[1];
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) *num_keep = n;
+    if (k < n) keep[k] = (int)(unsigned)keys[keep_ranks[k]];
+}
+__global__ void low32_kernel(const u64 *__restrict__ keys, int n, int *__restrict__ out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = (int)(unsigned)keys[k];
+}
+
+struct PeelSmem {
+    float4 hbox[HEAD];
+    u64 mask[MASK_WORDS];  // aliased by kbox during push
+    u64 kept[HEAD_WORDS], und[HEAD_WORDS];
+    int warp_sums[33];
+    int red[32];
+};
+
+struct PeelArgs {
+    const float4 *sbox;
+    int N;
+    int *stream_a, *stream_b;
+    int *keep_ranks;
+    int *state;         // [0] scratch, [1] total kept (out), [2] kept of the current stage
+    float4 *ks;         // kept boxes of the current stage (HEAD)
+    int *tile_counts;   // ceil(N/NT)
+    unsigned *ballots;  // ceil(N/NT)*32
+    const int *status;  // [2] != 0 -> not fast
+    float thr;
+};
+
+__device__ __forceinline__ int block_sum(int v, int *red) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    int t = red[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    __syncthreads();
+    return t;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NT, 1) nms_peel_kernel(PeelArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PeelSmem &sm = *reinterpret_cast<PeelSmem *>(smem_raw);
+    cg::grid_group grid = cg::this_grid();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = gridDim.x;
+    const bool thr_ok = MODE == 0 ? (a.thr >= 0.0f) : (a.thr > 0.0f);
+    const bool fast = thr_ok && (__ldcg(&a.status[2]) == 0);
+    float4 *kbox = reinterpret_cast<float4 *>(sm.mask);
+    int *cur = a.stream_a, *nxt = a.stream_b;
+    bool identity = true;
+    int len = a.N, nk_total = 0;
+    while (len > 0) {
+        const int S = min(HEAD, len);
+        if (blockIdx.x == 0) {
+            int my_rank = 0;
+            if (tid < S) {
+                my_rank = identity ? tid : __ldcg(&cur[tid]);
+                sm.hbox[tid] = a.sbox[my_rank];
+            }
+            __syncthreads();
+            if (fast) build_mask<MODE, true>(sm.hbox, S, sm.mask, a.thr);
+            else build_mask<MODE, false>(sm.hbox, S, sm.mask, a.thr);
+            __syncthreads();
+            resolve_rounds(sm.mask, S, sm.kept, sm.und);
+            int nkept = 0;
+            if (tid < S) {
+                bool is_kept = (sm.kept[tid >> 6] >> (tid & 63)) & 1ull;
+                int pos = kept_rank(sm.kept, tid, &nkept);
+                if (is_kept) {
+                    a.keep_ranks[nk_total + pos] = my_rank;
+                    a.ks[pos] = sm.hbox[tid];
+                }
+            } else {
+                kept_rank(sm.kept, 0, &nkept);
+            }
+            if (tid == 0) a.state[2] = nkept;
+        }
+        grid.sync();
+        const int nkept = __ldcg(&a.state[2]);
+        nk_total += nkept;
+        const int rem = len - S;
+        if (rem <= 0) break;
+        // ---- push: every CTA tests its tiles of the remaining stream against the kept boxes of this stage ----
+        for (int k = tid; k < nkept; k += NT) kbox[k] = __ldcg(&a.ks[k]);
+        __syncthreads();
+        const int ntiles = (rem + NT - 1) / NT;
+        for (int t = blockIdx.x; t < ntiles; t += G) {
+            int r = t * NT + tid;
+            bool alive = false;
+            if (r < rem) {
+                int rk = identity ? (S + r) : __ldcg(&cur[S + r]);
+                float4 bx = a.sbox[rk];
+                alive = true;
+                if (fast) {
+                    for (int k = 0; k < nkept; ++k)
+                        if (iou_suppresses<MODE, true>(kbox[k], bx, a.thr)) { alive = false; break; }
+                } else {
+                    for (int k = 0; k < nkept; ++k)
+                        if (iou_suppresses<MODE, false>(kbox[k], bx, a.thr)) { alive = false; break; }
+                }
+            }
+            unsigned bal = __ballot_sync(0xffffffffu, alive);
+            if (lane == 0) a.ballots[t * 32 + warp] = bal;
+            int cnt = __syncthreads_count(alive);
+            if (tid == 0) a.tile_counts[t] = cnt;
+        }
+        grid.sync();
+        // ---- ordered scatter of the survivors ----
+        int new_len;
+        {
+            int part = 0;
+            for (int t = tid; t < ntiles; t += NT) part += __ldcg(&a.tile_counts[t]);
+            new_len = block_sum(part, sm.red);
+        }
+        for (int t = blockIdx.x; t < ntiles; t += G) {
+            int part = 0;
+            for (int q = tid; q < t; q += NT) part += __ldcg(&a.tile_counts[q]);
+            int offset = block_sum(part, sm.red);
+            unsigned myb = __ldcg(&a.ballots[t * 32 + lane]);  // lane w holds the ballot of warp w
+            int wpre = 0;
+#pragma unroll
+            for (int w = 0; w < 32; ++w) {
+                unsigned bw = __shfl_sync(0xffffffffu, myb, w);
+                if (w < warp) wpre += __popc(bw);
+            }
+            unsigned mine = __shfl_sync(0xffffffffu, myb, warp);
+            if ((mine >> lane) & 1u) {
+                int r = t * NT + tid;
+                int rk = identity ? (S + r) : __ldcg(&cur[S + r]);
+                nxt[offset + wpre + __popc(mine & ((1u << lane) - 1u))] = rk;
+            }
+        }
+        grid.sync();
+        int *tmp = cur;
+        cur = nxt;
+        nxt = tmp;
+        identity = false;
+        len = new_len;
+    }
+    if (blockIdx.x == 0 && tid == 0) a.state[1] = nk_total;
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+static int radix_sort_u64(fd_ctx *ctx, u64 *keys, u64 *tmp, int n, const int *bytes, int nbytes, int *hist, u64 **sorted) {
+    const int ntiles = (n + RS_TILE - 1) / RS_TILE;
+    u64 *in = keys, *out = tmp;
+    for (int p = 0; p < nbytes; ++p) {
+        int shift = bytes[p] * 8;
+        radix_hist_kernel<<<ntiles, RS_THREADS, 0, ctx->stream>>>(in, n, shift, hist, ntiles);
+        FD_LAUNCH_CHECK(ctx);
+        scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist, 256 * ntiles);
+        FD_LAUNCH_CHECK(ctx);
+        radix_scatter_kernel<<<ntiles, RS_THREADS, 0, ctx->stream>>>(in, out, n, shift, hist, ntiles);
+        FD_LAUNCH_CHECK(ctx);
+        std::swap(in, out);
+    }
+    *sorted = in;
+    return FD_OK;
+}
+
+template <int MODE>
+static int launch_small(fd_ctx *ctx, const SmallArgs &a, int B, bool float4_boxes) {
+    const size_t smem = sizeof(SmallSmem);
+    if (float4_boxes) {
+        FD_CUDA(cudaFuncSetAttribute(nms_cta_kernel<MODE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_cta_kernel<MODE, 4><<<B, NT, smem, ctx->stream>>>(a);
+    } else {
+        FD_CUDA(cudaFuncSetAttribute(nms_cta_kernel<MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_cta_kernel<MODE, 0><<<B, NT, smem, ctx->stream>>>(a);
+    }
+    FD_LAUNCH_CHECK(ctx);
+    return FD_OK;
+}
+
+// keys_dev: optional pre-made u64 keys (score desc | source index), else made from dets column 4.
+// key_bytes/nkey_bytes: radix passes to run (LSD order).
+static int nms_big_impl(fd_ctx *ctx, const u64 *keys_in, const int *key_bytes, int nkey_bytes, const float *boxes, int K,
+                        int stride, float thr, int mode, bool presorted, bool sort_only, int32_t *keep_dev,
+                        int32_t *num_keep_dev) {
+    const int ntiles_rs = (K + RS_TILE - 1) / RS_TILE;
+    const int ntiles_peel = (K + NT - 1) / NT;
+    FD_TRY(ctx->nms_ws[0].reserve(sizeof(u64) * (size_t)K));              // keys a
+    FD_TRY(ctx->nms_ws[1].reserve(sizeof(u64) * (size_t)K));              // keys b
+    FD_TRY(ctx->nms_ws[2].reserve(sizeof(int) * (size_t)256 * ntiles_rs)); // hist
+    FD_TRY(ctx->nms_ws[3].reserve(sizeof(float4) * (size_t)K));           // sorted boxes
+    FD_TRY(ctx->nms_ws[4].reserve(sizeof(int) * (size_t)K * 3));          // stream a, stream b, keep ranks
+    FD_TRY(ctx->nms_ws[5].reserve(sizeof(float4) * HEAD + sizeof(int) * (size_t)ntiles_peel * 33 + 64));
+    FD_TRY(ctx->nms_ws[6].reserve(sizeof(int) * 8));                      // status/state
+    u64 *ka = ctx->nms_ws[0].as<u64>(), *kb = ctx->nms_ws[1].as<u64>();
+    int *hist = ctx->nms_ws[2].as<int>();
+    float4 *sbox = ctx->nms_ws[3].as<float4>();
+    int *stream_a = ctx->nms_ws[4].as<int>(), *stream_b = stream_a + K, *keep_ranks = stream_b + K;
+    float4 *ks = ctx->nms_ws[5].as<float4>();
+    int *tile_counts = reinterpret_cast<int *>(ks + HEAD);
+    unsigned *ballots = reinterpret_cast<unsigned *>(tile_counts + ntiles_peel);
+    int *st = ctx->nms_ws[6].as<int>();  // [0] nan, [1] kept total, [2] not-fast flag, [4..6] peel state
+    FD_CUDA(cudaMemsetAsync(st, 0, sizeof(int) * 8, ctx->stream));
+    const int tb = 256, gb = (K + tb - 1) / tb;
+    u64 *sorted = ka;
+    if (presorted) {
+        iota_keys_kernel<<<gb, tb, 0, ctx->stream>>>(K, ka);
+        FD_LAUNCH_CHECK(ctx);
+    } else {
+        if (keys_in) FD_CUDA(cudaMemcpyAsync(ka, keys_in, sizeof(u64) * (size_t)K, cudaMemcpyDeviceToDevice, ctx->stream));
+        else {
+            make_keys_kernel<<<gb, tb, 0, ctx->stream>>>(boxes, K, stride, ka, st);
+            FD_LAUNCH_CHECK(ctx);
+        }
+        FD_TRY(radix_sort_u64(ctx, ka, kb, K, key_bytes, nkey_bytes, hist, &sorted));
+    }
+    if (sort_only) {
+        low32_kernel<<<gb, tb, 0, ctx->stream>>>(sorted, K, keep_dev);
+        FD_LAUNCH_CHECK(ctx);
+        FD_CUDA(cudaMemcpyAsync(num_keep_dev, st, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));  // nan flag
+        return FD_OK;
+    }
+    gather_sorted_boxes_kernel<<<gb, tb, 0, ctx->stream>>>(sorted, K, boxes, stride, sbox, st);
+    FD_LAUNCH_CHECK(ctx);
+    PeelArgs pa;
+    pa.sbox = sbox;
+    pa.N = K;
+    pa.stream_a = stream_a;
+    pa.stream_b = stream_b;
+    pa.keep_ranks = keep_ranks;
+    pa.state = st + 3;  // state[1] -> st[4], state[2] -> st[5]
+    pa.ks = ks;
+    pa.tile_counts = tile_counts;
+    pa.ballots = ballots;
+    pa.status = st;
+    pa.thr = thr;
+    const size_t smem = sizeof(PeelSmem);
+    void *kargs[] = {&pa};
+    const void *fn = mode == 0 ? (const void *)nms_peel_kernel<0> : (const void *)nms_peel_kernel<1>;
+    FD_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    if (mode == 0) FD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nms_peel_kernel<0>, NT, smem));
+    else FD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nms_peel_kernel<1>, NT, smem));
+    if (per_sm < 1) return fail(FD_ERR_CUDA, "nms_peel_kernel does not fit on an SM");
+    int grid = std::min(ctx->num_sms * per_sm, std::max(1, ntiles_peel));
+    FD_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NT), kargs, smem, ctx->stream));
+    FD_LAUNCH_CHECK(ctx);
+    map_keep_kernel<<<gb, tb, 0, ctx->stream>>>(keep_ranks, st + 3, sorted, keep_dev, num_keep_dev);
+    FD_LAUNCH_CHECK(ctx);
+    return FD_OK;
+}
+
+int nms_big_device(fd_ctx *ctx, const float *dets_dev, int K, int stride, float thr, int mode, bool presorted,
+                   int32_t *keep_dev, int32_t *num_keep_dev) {
+    static const int bytes[4] = {4, 5, 6, 7};  // score bytes only: the sort is stable, ties keep index order
+    return nms_big_impl(ctx, nullptr, bytes, 4, dets_dev, K, stride, thr, mode, presorted, false, keep_dev, num_keep_dev);
+}
+
+// Generic device NMS on a (K, stride) row-major array with the score in column 4 (ignored if presorted).
+// keep_dev (K) and num_keep_dev (2 ints: [0] count, [1] NaN flag) are device buffers.
+int nms_device(fd_ctx *ctx, const float *dets_dev, int K, int stride, float thr, int mode, bool presorted,
+               int32_t *keep_dev, int32_t *num_keep_dev) {
+    FD_TRY(ctx->nms_ws[7].reserve(sizeof(int) * 8));
+    int *status = ctx->nms_ws[7].as<int>();
+    FD_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * 8, ctx->stream));
+    if (K <= SMALL_CAP) {
+        SmallArgs a{};
+        a.keys = nullptr;
+        a.key_stride = 0;
+        a.boxes = dets_dev;
+        a.box_batch_stride = 0;
+        a.box_stride = stride;
+        a.counts = nullptr;
+        a.K = K;
+        a.presorted = presorted ? 1 : 0;
+        a.sort_only = 0;
+        a.thr = thr;
+        a.keep = keep_dev;
+        a.keep_stride = 0;
+        a.keep_count = num_keep_dev;
+        a.status = status;
+        a.big_list = nullptr;
+        if (presorted) {
+            // presorted rows carry no usable score column contract (boxes_dim may be 4): keys = identity
+            FD_TRY(ctx->nms_ws[0].reserve(sizeof(u64) * (size_t)std::max(K, 1)));
+            iota_keys_kernel<<<(K + 255) / 256, 256, 0, ctx->stream>>>(K, ctx->nms_ws[0].as<u64>());
+            FD_LAUNCH_CHECK(ctx);
+            a.keys = ctx->nms_ws[0].as<u64>();
+        }
+        if (mode == 0) FD_TRY(launch_small<0>(ctx, a, 1, false));
+        else FD_TRY(launch_small<1>(ctx, a, 1, false));
+        FD_CUDA(cudaMemcpyAsync(num_keep_dev + 1, status, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+        return FD_OK;
+    }
+    FD_TRY(nms_big_device(ctx, dets_dev, K, stride, thr, mode, presorted, keep_dev, num_keep_dev));
+    FD_CUDA(cudaMemcpyAsync(num_keep_dev + 1, ctx->nms_ws[6].as<int>(), sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    return FD_OK;
+}
+
+// argsort_descending on the device: order_dev (n), flag_dev (1 int: NaN flag)
+int argsort_device(fd_ctx *ctx, const float *scores_as_dets, int n, int stride, int32_t *order_dev, int32_t *flag_dev) {
+    FD_TRY(ctx->nms_ws[7].reserve(sizeof(int) * 8));
+    int *status = ctx->nms_ws[7].as<int>();
+    FD_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * 8, ctx->stream));
+    if (n <= SMALL_CAP) {
+        SmallArgs a{};
+        a.boxes = scores_as_dets;  // score read at column 4 -> caller passes (scores - 4) with stride 1
+        a.box_stride = stride;
+        a.K = n;
+        a.sort_only = 1;
+        a.keep = order_dev;
+        a.keep_count = status + 4;
+        a.status = status;
+        FD_TRY(launch_small<0>(ctx, a, 1, false));
+        FD_CUDA(cudaMemcpyAsync(flag_dev, status, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+        return FD_OK;
+    }
+    static const int bytes[4] = {4, 5, 6, 7};
+    return nms_big_impl(ctx, nullptr, bytes, 4, scores_as_dets, n, stride, 0.f, 0, false, true, order_dev, flag_dev);
+}
+
+// Batched: one CTA per image over the decode kernel's candidate buffers.
+int nms_batch_launch(fd_ctx *ctx, int B, float iou_thr) {
+    const int TA = ctx->dcfg.total_anchors;
+    SmallArgs a{};
+    a.keys = ctx->cand_keys.as<u64>();
+    a.key_stride = (size_t)TA;
+    a.boxes = ctx->cand_box.as<float>();
+    a.box_batch_stride = (size_t)TA * 4;
+    a.box_stride = 4;
+    a.counts = ctx->cand_count.as<int>();
+    a.K = 0;
+    a.presorted = 0;
+    a.sort_only = 0;
+    a.thr = iou_thr;
+    a.keep = ctx->keep_src.as<int>();
+    a.keep_stride = (size_t)TA;
+    a.keep_count = ctx->keep_count.as<int>();
+    a.status = ctx->status_dev.as<int>();
+    a.big_list = ctx->big_list.as<int>();
+    return launch_small<0>(ctx, a, B, true);
+}
+
+// Big-path fix-up for one image of the batch (K > SMALL_CAP): radix sort on (anchor id, score) bytes + peel.
+int nms_batch_big_image(fd_ctx *ctx, int b, int K, float iou_thr) {
+    const int TA = ctx->dcfg.total_anchors;
+    int bytes[8], nb = 0;
+    bytes[nb++] = 0;
+    bytes[nb++] = 1;
+    if (TA > 65536) bytes[nb++] = 2;
+    if (TA > (1 << 24)) bytes[nb++] = 3;
+    for (int k = 4; k < 8; ++k) bytes[nb++] = k;
+    return nms_big_impl(ctx, ctx->cand_keys.as<u64>() + (size_t)b * TA, bytes, nb, ctx->cand_box.as<float>() + (size_t)b * TA * 4,
+                        K, 4, iou_thr, 0, false, false, ctx->keep_src.as<int>() + (size_t)b * TA,
+                        ctx->keep_count.as<int>() + b);
+}
+
+}  // namespace fd

@@ -1,0 +1,468 @@
+// fd_pipeline.cu — batched device-resident pipeline entry points, single-image host wrappers and the
+// host-buffer end-to-end call.  Mirrors RetinaFaceDetection::call (face_detection.rs:496-513) and
+// FaceAlignment::call (face_alignment.rs:27-141) at batch granularity.
+#include <algorithm>
+#include <cstring>
+#include "fd_internal.cuh"
+
+namespace fd {
+
+int preprocess_launch(fd_ctx *ctx, const FrameDev *frames_dev, int B, float *out_nchw_dev, int max_row_bytes);
+int resize_launch(fd_ctx *ctx, const FrameDev &frame, uint8_t *out_dev, int out_h, int out_w);
+int nms_batch_big_image(fd_ctx *ctx, int b, int K, float iou_thr);
+int estimate_launch(fd_ctx *ctx, const float *from_dev, const float *to_dev, const int *count_dev, int F_cap,
+                    double *M12_dev, double *M_out_dev, uint8_t *ok_dev, uint8_t *ok_out_dev);
+int invert_launch(fd_ctx *ctx, const double *M_dev, int F, double *M12_dev, uint8_t *ok_dev);
+int warp_launch(fd_ctx *ctx, const FrameDev *frames_dev, const int32_t *frame_idx_dev, const double *M12_dev,
+                const uint8_t *ok_dev, const int *count_dev, int F_cap, uint8_t *crops_dev, int cw, int ch);
+
+// RetinaFaceDetection::_preprocess geometry (face_detection.rs:140-153): f32 arithmetic, `as i32` truncation
+static void letterbox(int h, int w, int size_w, int size_h, int *new_w, int *new_h, float *det_scale) {
+    volatile float im_ratio = (float)h / (float)w;
+    volatile float model_ratio = (float)size_h / (float)size_w;
+    if (im_ratio > model_ratio) {
+        *new_h = size_h;
+        volatile float q = (float)(*new_h) / im_ratio;
+        *new_w = (int)q;
+    } else {
+        *new_w = size_w;
+        volatile float q = (float)(*new_w) * im_ratio;
+        *new_h = (int)q;
+    }
+    volatile float ds = (float)(*new_h) / (float)h;
+    *det_scale = ds;
+}
+
+static int fill_frame(const fd_ctx *ctx, const fd_frame &fr, const uint8_t *data_dev, FrameDev *out, float *det_scale) {
+    FD_REQUIRE(fr.height > 0 && fr.width > 0 && fr.pitch >= fr.width * 3, "frame: bad geometry");
+    out->data = data_dev;
+    out->h = fr.height;
+    out->w = fr.width;
+    out->pitch = fr.pitch;
+    float ds;
+    letterbox(fr.height, fr.width, ctx->cfg.image_w, ctx->cfg.image_h, &out->new_w, &out->new_h, &ds);
+    // cv::resize rejects an empty destination size (the reference returns Err, face_detection.rs:156-159)
+    FD_REQUIRE(out->new_w > 0 && out->new_h > 0, "frame: letterbox size is empty (extreme aspect ratio)");
+    out->new_w = std::min(out->new_w, ctx->cfg.image_w);
+    out->new_h = std::min(out->new_h, ctx->cfg.image_h);
+    out->scale_x = 1.0 / ((double)out->new_w / fr.width);
+    out->scale_y = 1.0 / ((double)out->new_h / fr.height);
+    if (det_scale) *det_scale = ds;
+    return FD_OK;
+}
+
+// uploads B descriptors (frames[].data are device pointers); returns the widest source row in bytes
+static int upload_frame_table(fd_ctx *ctx, const fd_frame *frames, int B, float *det_scale_host, int *max_row_bytes) {
+    std::vector<FrameDev> tab(B);
+    int mrb = 0;
+    for (int i = 0; i < B; ++i) {
+        FD_REQUIRE(frames[i].data != nullptr, "frame: null data");
+        float ds;
+        memset(&tab[i], 0, sizeof(FrameDev));
+        FD_TRY(fill_frame(ctx, frames[i], frames[i].data, &tab[i], &ds));
+        if (det_scale_host) det_scale_host[i] = ds;
+        mrb = std::max(mrb, frames[i].width * 3);
+    }
+    if (max_row_bytes) *max_row_bytes = mrb;
+    const size_t bytes = sizeof(FrameDev) * (size_t)B;
+    // the table already on the device is reused when nothing changed (steady-state streaming over a frame ring)
+    if (ctx->frames_shadow.size() == bytes && memcmp(ctx->frames_shadow.data(), tab.data(), bytes) == 0) return FD_OK;
+    FD_TRY(ctx->pinned[0].reserve(bytes));
+    FD_TRY(ctx->frames_dev.reserve(bytes));
+    FD_CUDA(cudaEventSynchronize(ctx->ev[0]));  // the pinned staging copy may still be in flight
+    memcpy(ctx->pinned[0].p, tab.data(), bytes);
+    FD_CUDA(cudaMemcpyAsync(ctx->frames_dev.p, ctx->pinned[0].p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FD_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    ctx->frames_shadow.assign(reinterpret_cast<unsigned char *>(tab.data()), reinterpret_cast<unsigned char *>(tab.data()) + bytes);
+    return FD_OK;
+}
+
+static int align_enqueue(fd_ctx *ctx, const FrameDev *frames_dev, const float *lmk_dev, const int32_t *frame_idx_dev,
+                         const int *count_dev, int F_cap, uint8_t *crops_dev, double *M_dev, uint8_t *ok_dev) {
+    if (F_cap <= 0) return FD_OK;
+    FD_TRY(ctx->align_M.reserve(sizeof(double) * 12 * (size_t)F_cap));
+    FD_TRY(ctx->align_ok.reserve((size_t)F_cap));
+    FD_TRY(estimate_launch(ctx, lmk_dev, nullptr, count_dev, F_cap, ctx->align_M.as<double>(), M_dev, ctx->align_ok.as<uint8_t>(), ok_dev));
+    FD_TRY(warp_launch(ctx, frames_dev, frame_idx_dev, ctx->align_M.as<double>(), ctx->align_ok.as<uint8_t>(), count_dev, F_cap,
+                       crops_dev, ctx->cfg.crop_w, ctx->cfg.crop_h));
+    return FD_OK;
+}
+
+// completes a pending fd_detect_batch: surfaces NaN errors and runs the big path for images with K > 4096
+static int detect_resolve(fd_ctx *ctx) {
+    if (!ctx->detect_pending) return FD_OK;
+    const int B = ctx->last_B;
+    int st[4] = {0, 0, 0, 0};
+    FD_CUDA(cudaMemcpyAsync(st, ctx->status_dev.p, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->detect_pending = false;
+    if (st[0]) return fail(FD_ERR_NAN_SCORE, "fd_detect_batch: NaN score (the reference panics, utils.rs:92)");
+    if (st[1] > 0) {
+        std::vector<int> big(st[1]), counts(B);
+        FD_CUDA(cudaMemcpy(big.data(), ctx->big_list.p, sizeof(int) * st[1], cudaMemcpyDeviceToHost));
+        FD_CUDA(cudaMemcpy(counts.data(), ctx->cand_count.p, sizeof(int) * B, cudaMemcpyDeviceToHost));
+        for (int b : big) FD_TRY(nms_batch_big_image(ctx, b, counts[b], ctx->last_iou));
+        FD_TRY(finalize_launch(ctx, B));
+        if (ctx->align_replay)  // the crops were produced from incomplete detections: align again
+            FD_TRY(align_enqueue(ctx, ctx->frames_dev.as<FrameDev>(), ctx->out_lmk.as<float>(), ctx->out_frame_idx.as<int32_t>(),
+                                 ctx->status_dev.as<int>() + 2, ctx->align_cap, ctx->align_crops, ctx->align_M_out, ctx->align_ok_out));
+        FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return FD_OK;
+}
+
+static int reserve_detect(fd_ctx *ctx, int B) {
+    const size_t TA = (size_t)ctx->dcfg.total_anchors, n = TA * B;
+    FD_TRY(ctx->det_scale_dev.reserve(sizeof(float) * B));
+    FD_TRY(ctx->cand_count.reserve(sizeof(int) * B));
+    FD_TRY(ctx->cand_keys.reserve(sizeof(unsigned long long) * n));
+    FD_TRY(ctx->cand_box.reserve(sizeof(float4) * n));
+    FD_TRY(ctx->cand_lmk.reserve(sizeof(float) * 12 * n));
+    FD_TRY(ctx->keep_src.reserve(sizeof(int) * n));
+    FD_TRY(ctx->keep_count.reserve(sizeof(int) * B));
+    FD_TRY(ctx->status_dev.reserve(sizeof(int) * 8));
+    FD_TRY(ctx->big_list.reserve(sizeof(int) * B));
+    FD_TRY(ctx->out_offsets.reserve(sizeof(int) * (B + 1)));
+    FD_TRY(ctx->out_det.reserve(sizeof(float) * 5 * n));
+    FD_TRY(ctx->out_lmk.reserve(sizeof(float) * 10 * n));
+    FD_TRY(ctx->out_frame_idx.reserve(sizeof(int) * n));
+    return FD_OK;
+}
+
+static int detect_enqueue(fd_ctx *ctx, const float *const *heads_dev, int B, const float *det_scale_host, float conf_thr,
+                          float iou_thr) {
+    FD_TRY(reserve_detect(ctx, B));
+    if (ctx->det_scale_shadow.size() != (size_t)B || memcmp(ctx->det_scale_shadow.data(), det_scale_host, sizeof(float) * (size_t)B) != 0) {
+        FD_TRY(ctx->pinned[1].reserve(sizeof(float) * (size_t)B));
+        FD_CUDA(cudaEventSynchronize(ctx->ev[1]));
+        memcpy(ctx->pinned[1].p, det_scale_host, sizeof(float) * (size_t)B);
+        FD_CUDA(cudaMemcpyAsync(ctx->det_scale_dev.p, ctx->pinned[1].p, sizeof(float) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
+        FD_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+        ctx->det_scale_shadow.assign(det_scale_host, det_scale_host + B);
+    }
+    FD_CUDA(cudaMemsetAsync(ctx->cand_count.p, 0, sizeof(int) * (size_t)B, ctx->stream));
+    FD_CUDA(cudaMemsetAsync(ctx->status_dev.p, 0, sizeof(int) * 8, ctx->stream));
+    FD_TRY(decode_launch(ctx, heads_dev, B, conf_thr));
+    FD_TRY(nms_batch_launch(ctx, B, iou_thr));
+    FD_TRY(finalize_launch(ctx, B));
+    ctx->last_B = B;
+    ctx->last_iou = iou_thr;
+    ctx->detect_pending = true;
+    ctx->align_replay = false;
+    return FD_OK;
+}
+
+}  // namespace fd
+
+using namespace fd;
+
+FD_EXPORT int fd_letterbox_geometry(const fd_ctx *ctx, int img_h, int img_w, int *new_w, int *new_h, float *det_scale) {
+    FD_REQUIRE(ctx && img_h > 0 && img_w > 0 && new_w && new_h && det_scale, "fd_letterbox_geometry: bad arguments");
+    letterbox(img_h, img_w, ctx->cfg.image_w, ctx->cfg.image_h, new_w, new_h, det_scale);
+    return FD_OK;
+}
+
+FD_EXPORT int fd_preprocess_batch(fd_ctx *ctx, const fd_frame *frames, int B, float *out_nchw_dev, float *det_scale_host) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(B >= 0 && (B == 0 || (frames && out_nchw_dev)), "fd_preprocess_batch: bad arguments");
+    if (B == 0) return FD_OK;
+    int mrb = 0;
+    FD_TRY(upload_frame_table(ctx, frames, B, det_scale_host, &mrb));
+    return preprocess_launch(ctx, ctx->frames_dev.as<FrameDev>(), B, out_nchw_dev, mrb);
+}
+
+FD_EXPORT int fd_detect_batch(fd_ctx *ctx, const float *const *heads_dev, int n_heads, int B, const float *det_scale_host,
+                              float conf_thr, float iou_thr) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(heads_dev && det_scale_host && B > 0, "fd_detect_batch: bad arguments");
+    FD_REQUIRE(n_heads == 3 * ctx->dcfg.n_strides, "fd_detect_batch: n_heads must be 3 * n_strides");
+    for (int i = 0; i < n_heads; ++i) FD_REQUIRE(heads_dev[i], "fd_detect_batch: null head tensor");
+    return detect_enqueue(ctx, heads_dev, B, det_scale_host, conf_thr, iou_thr);
+}
+
+FD_EXPORT int fd_detect_fetch(fd_ctx *ctx, int32_t *counts, float *det, float *landmarks, int cap_rows, int *total) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(ctx->last_B > 0, "fd_detect_fetch: no fd_detect_batch results");
+    FD_TRY(detect_resolve(ctx));
+    const int B = ctx->last_B;
+    std::vector<int> off(B + 1);
+    FD_CUDA(cudaMemcpyAsync(off.data(), ctx->out_offsets.p, sizeof(int) * (B + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int tot = off[B];
+    if (total) *total = tot;
+    if (counts)
+        for (int i = 0; i < B; ++i) counts[i] = off[i + 1] - off[i];
+    if (tot > cap_rows && (det || landmarks)) return fail(FD_ERR_CAPACITY, "fd_detect_fetch: cap_rows too small");
+    if (det && tot) FD_CUDA(cudaMemcpyAsync(det, ctx->out_det.p, sizeof(float) * 5 * (size_t)tot, cudaMemcpyDeviceToHost, ctx->stream));
+    if (landmarks && tot)
+        FD_CUDA(cudaMemcpyAsync(landmarks, ctx->out_lmk.p, sizeof(float) * 10 * (size_t)tot, cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FD_OK;
+}
+
+FD_EXPORT int fd_detect_view(fd_ctx *ctx, fd_det_view *out) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(out && ctx->last_B > 0, "fd_detect_view: no results");
+    FD_TRY(detect_resolve(ctx));
+    out->counts_dev = ctx->keep_count.as<int32_t>();
+    out->offsets_dev = ctx->out_offsets.as<int32_t>();
+    out->det_dev = ctx->out_det.as<float>();
+    out->landmarks_dev = ctx->out_lmk.as<float>();
+    out->frame_idx_dev = ctx->out_frame_idx.as<int32_t>();
+    out->candidates_dev = ctx->cand_count.as<int32_t>();
+    return FD_OK;
+}
+
+FD_EXPORT int fd_align_batch(fd_ctx *ctx, const fd_frame *frames, int B, const float *landmarks_dev, const int32_t *frame_idx_dev,
+                             int F, uint8_t *crops_dev, double *M_dev, uint8_t *ok_dev) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(B > 0 && frames && F >= 0 && (F == 0 || (landmarks_dev && crops_dev)), "fd_align_batch: bad arguments");
+    if (F == 0) return FD_OK;
+    FD_TRY(upload_frame_table(ctx, frames, B, nullptr, nullptr));
+    return align_enqueue(ctx, ctx->frames_dev.as<FrameDev>(), landmarks_dev, frame_idx_dev, nullptr, F, crops_dev, M_dev, ok_dev);
+}
+
+FD_EXPORT int fd_align_detections(fd_ctx *ctx, const fd_frame *frames, int B, uint8_t *crops_dev, int cap_faces, double *M_dev,
+                                  uint8_t *ok_dev) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(B > 0 && frames && B == ctx->last_B && crops_dev && cap_faces > 0, "fd_align_detections: bad arguments");
+    // No host synchronisation here: NaN scores and images needing the big NMS path are detected lazily at
+    // fd_detect_fetch / fd_detect_view / fd_ctx-level fetch, which replays this align if the detections changed.
+    FD_TRY(upload_frame_table(ctx, frames, B, nullptr, nullptr));
+    ctx->align_replay = true;
+    ctx->align_crops = crops_dev;
+    ctx->align_cap = cap_faces;
+    ctx->align_M_out = M_dev;
+    ctx->align_ok_out = ok_dev;
+    return align_enqueue(ctx, ctx->frames_dev.as<FrameDev>(), ctx->out_lmk.as<float>(), ctx->out_frame_idx.as<int32_t>(),
+                         ctx->status_dev.as<int>() + 2, cap_faces, crops_dev, M_dev, ok_dev);
+}
+
+// ---- single-image host wrappers -----------------------------------------------------------------------------------
+static int upload_image(fd_ctx *ctx, int slot, const uint8_t *img, int h, int w, int pitch, const uint8_t **dev, int *dev_pitch) {
+    FD_REQUIRE(img && h > 0 && w > 0 && pitch >= w * 3, "image: bad geometry");
+    const int dp = (w * 3 + 15) & ~15;
+    FD_TRY(ctx->scratch[slot].reserve((size_t)dp * h));
+    FD_CUDA(cudaMemcpy2DAsync(ctx->scratch[slot].p, dp, img, pitch, (size_t)w * 3, h, cudaMemcpyHostToDevice, ctx->stream));
+    *dev = ctx->scratch[slot].as<uint8_t>();
+    *dev_pitch = dp;
+    return FD_OK;
+}
+
+FD_EXPORT int fd_preprocess(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, float *out_nchw, float *det_scale) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(out_nchw, "fd_preprocess: null output");
+    const uint8_t *d_img;
+    int dp;
+    FD_TRY(upload_image(ctx, 3, img, h, w, pitch, &d_img, &dp));
+    fd_frame fr{d_img, h, w, dp};
+    const size_t n = (size_t)3 * ctx->cfg.image_h * ctx->cfg.image_w;
+    FD_TRY(ctx->scratch[4].reserve(sizeof(float) * n));
+    float ds = 0.f;
+    FD_TRY(fd_preprocess_batch(ctx, &fr, 1, ctx->scratch[4].as<float>(), &ds));
+    if (det_scale) *det_scale = ds;
+    FD_CUDA(cudaMemcpyAsync(out_nchw, ctx->scratch[4].p, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FD_OK;
+}
+
+FD_EXPORT int fd_resize_linear(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, uint8_t *out, int out_h, int out_w) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(out && out_h > 0 && out_w > 0, "fd_resize_linear: bad output size");
+    const uint8_t *d_img;
+    int dp;
+    FD_TRY(upload_image(ctx, 3, img, h, w, pitch, &d_img, &dp));
+    FrameDev f{};
+    f.data = d_img; f.h = h; f.w = w; f.pitch = dp; f.new_w = out_w; f.new_h = out_h;
+    f.scale_x = 1.0 / ((double)out_w / w);
+    f.scale_y = 1.0 / ((double)out_h / h);
+    const size_t n = (size_t)out_h * out_w * 3;
+    FD_TRY(ctx->scratch[4].reserve(n));
+    FD_TRY(resize_launch(ctx, f, ctx->scratch[4].as<uint8_t>(), out_h, out_w));
+    FD_CUDA(cudaMemcpyAsync(out, ctx->scratch[4].p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FD_OK;
+}
+
+FD_EXPORT int fd_detect(fd_ctx *ctx, const float *const *heads, int n_heads, float det_scale, float conf_thr, float iou_thr,
+                        float *det, float *landmarks, int cap, int *num_det) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(heads && num_det && n_heads == 3 * ctx->dcfg.n_strides, "fd_detect: bad arguments");
+    const DecodeCfg &d = ctx->dcfg;
+    const float *dev_heads[3 * FD_MAX_STRIDES];
+    for (int s = 0; s < d.n_strides; ++s) {
+        const int hw = d.fh[s] * d.fw[s];
+        const int ch[3] = {2 * d.A, 4 * d.A, 10 * d.A};
+        for (int k = 0; k < 3; ++k) {
+            FD_REQUIRE(heads[3 * s + k], "fd_detect: null head tensor");
+            const size_t bytes = sizeof(float) * (size_t)ch[k] * hw;
+            FD_TRY(ctx->pipe_heads[3 * s + k].reserve(bytes));
+            FD_CUDA(cudaMemcpyAsync(ctx->pipe_heads[3 * s + k].p, heads[3 * s + k], bytes, cudaMemcpyHostToDevice, ctx->stream));
+            dev_heads[3 * s + k] = ctx->pipe_heads[3 * s + k].as<float>();
+        }
+    }
+    FD_TRY(detect_enqueue(ctx, dev_heads, 1, &det_scale, conf_thr, iou_thr));
+    int32_t cnt = 0;
+    int tot = 0;
+    FD_TRY(fd_detect_fetch(ctx, &cnt, det, landmarks, cap, &tot));
+    *num_det = tot;
+    return FD_OK;
+}
+
+FD_EXPORT int fd_estimate_affine_partial_2d(fd_ctx *ctx, const float *from, const float *to, int n_sets, double *M, uint8_t *ok) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(n_sets >= 0 && (n_sets == 0 || (from && M && ok)), "fd_estimate_affine_partial_2d: bad arguments");
+    if (n_sets == 0) return FD_OK;
+    const size_t nb = sizeof(float) * 10 * (size_t)n_sets;
+    FD_TRY(ctx->scratch[0].reserve(nb));
+    FD_CUDA(cudaMemcpyAsync(ctx->scratch[0].p, from, nb, cudaMemcpyHostToDevice, ctx->stream));
+    const float *d_to = nullptr;
+    if (to) {
+        FD_TRY(ctx->scratch[1].reserve(nb));
+        FD_CUDA(cudaMemcpyAsync(ctx->scratch[1].p, to, nb, cudaMemcpyHostToDevice, ctx->stream));
+        d_to = ctx->scratch[1].as<float>();
+    }
+    FD_TRY(ctx->align_M.reserve(sizeof(double) * 12 * (size_t)n_sets));
+    FD_TRY(ctx->align_ok.reserve((size_t)n_sets));
+    FD_TRY(ctx->scratch[2].reserve(sizeof(double) * 6 * (size_t)n_sets));
+    FD_TRY(estimate_launch(ctx, ctx->scratch[0].as<float>(), d_to, nullptr, n_sets, ctx->align_M.as<double>(),
+                           ctx->scratch[2].as<double>(), ctx->align_ok.as<uint8_t>(), nullptr));
+    FD_CUDA(cudaMemcpyAsync(M, ctx->scratch[2].p, sizeof(double) * 6 * (size_t)n_sets, cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(cudaMemcpyAsync(ok, ctx->align_ok.p, (size_t)n_sets, cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FD_OK;
+}
+
+static int warp_host(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, const double *M, const float *lmk, uint8_t *out,
+                     int out_h, int out_w, double *M_out) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(out && out_h > 0 && out_w > 0 && out_w <= 4096, "warp: bad output size");
+    const uint8_t *d_img;
+    int dp;
+    FD_TRY(upload_image(ctx, 3, img, h, w, pitch, &d_img, &dp));
+    FD_TRY(ctx->pinned[2].reserve(sizeof(FrameDev)));
+    FD_CUDA(cudaEventSynchronize(ctx->ev[2]));
+    FrameDev *f = ctx->pinned[2].as<FrameDev>();
+    memset(f, 0, sizeof(*f));
+    f->data = d_img; f->h = h; f->w = w; f->pitch = dp;
+    FD_TRY(ctx->scratch[5].reserve(sizeof(FrameDev)));
+    FD_CUDA(cudaMemcpyAsync(ctx->scratch[5].p, f, sizeof(FrameDev), cudaMemcpyHostToDevice, ctx->stream));
+    FD_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+    FD_TRY(ctx->align_M.reserve(sizeof(double) * 12));
+    FD_TRY(ctx->align_ok.reserve(16));
+    FD_TRY(ctx->scratch[0].reserve(sizeof(double) * 6 + sizeof(float) * 10));
+    if (M) {
+        FD_CUDA(cudaMemcpyAsync(ctx->scratch[0].p, M, sizeof(double) * 6, cudaMemcpyHostToDevice, ctx->stream));
+        FD_TRY(invert_launch(ctx, ctx->scratch[0].as<double>(), 1, ctx->align_M.as<double>(), ctx->align_ok.as<uint8_t>()));
+    } else {
+        FD_CUDA(cudaMemcpyAsync(ctx->scratch[0].p, lmk, sizeof(float) * 10, cudaMemcpyHostToDevice, ctx->stream));
+        FD_TRY(estimate_launch(ctx, ctx->scratch[0].as<float>(), nullptr, nullptr, 1, ctx->align_M.as<double>(), nullptr,
+                               ctx->align_ok.as<uint8_t>(), nullptr));
+    }
+    const size_t n = (size_t)out_h * out_w * 3;
+    FD_TRY(ctx->scratch[4].reserve(n));
+    FD_TRY(warp_launch(ctx, ctx->scratch[5].as<FrameDev>(), nullptr, ctx->align_M.as<double>(), ctx->align_ok.as<uint8_t>(), nullptr, 1,
+                       ctx->scratch[4].as<uint8_t>(), out_w, out_h));
+    uint8_t okh = 0;
+    double M12[12];
+    FD_CUDA(cudaMemcpyAsync(out, ctx->scratch[4].p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(cudaMemcpyAsync(&okh, ctx->align_ok.p, 1, cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(cudaMemcpyAsync(M12, ctx->align_M.p, sizeof(M12), cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (M_out) memcpy(M_out, M12, sizeof(double) * 6);
+    if (!okh) return fail(FD_ERR_ESTIMATE, "fd_align: similarity estimation failed (reference falls back to a bbox crop)");
+    return FD_OK;
+}
+
+FD_EXPORT int fd_warp_affine(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, const double *M, uint8_t *out, int out_h,
+                             int out_w) {
+    FD_REQUIRE(M, "fd_warp_affine: null M");
+    return warp_host(ctx, img, h, w, pitch, M, nullptr, out, out_h, out_w, nullptr);
+}
+FD_EXPORT int fd_align(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, const float *landmarks, uint8_t *crop, double *M_out) {
+    FD_REQUIRE(ctx && landmarks, "fd_align: null landmarks (the reference's bbox-crop fallback is out of scope)");
+    return warp_host(ctx, img, h, w, pitch, nullptr, landmarks, crop, ctx->cfg.crop_h, ctx->cfg.crop_w, M_out);
+}
+
+// ---- end-to-end with host buffers ------------------------------------------------------------------------------------
+FD_EXPORT int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const float *const *heads_host, int n_heads,
+                               float conf_thr, float iou_thr, fd_host_batch_out *out) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(frames && heads_host && out && B > 0, "fd_pipeline_host: bad arguments");
+    FD_REQUIRE(n_heads == 3 * ctx->dcfg.n_strides, "fd_pipeline_host: n_heads must be 3 * n_strides");
+    FD_REQUIRE(out->counts && out->det && out->landmarks && out->crops && out->cap_rows > 0, "fd_pipeline_host: bad outputs");
+    const DecodeCfg &d = ctx->dcfg;
+    int64_t h2d = 0, d2h = 0;
+    // 1. frames H2D into one device arena (16-byte aligned rows)
+    std::vector<size_t> offs(B);
+    std::vector<int> dpitch(B);
+    size_t arena = 0;
+    for (int i = 0; i < B; ++i) {
+        FD_REQUIRE(frames[i].data && frames[i].height > 0 && frames[i].width > 0 && frames[i].pitch >= frames[i].width * 3,
+                   "fd_pipeline_host: bad frame");
+        dpitch[i] = (frames[i].width * 3 + 15) & ~15;
+        offs[i] = arena;
+        arena += ((size_t)dpitch[i] * frames[i].height + 255) & ~(size_t)255;
+    }
+    FD_TRY(ctx->pipe_frames.reserve(arena));
+    std::vector<fd_frame> dframes(B);
+    for (int i = 0; i < B; ++i) {
+        uint8_t *dst = ctx->pipe_frames.as<uint8_t>() + offs[i];
+        if (frames[i].pitch == dpitch[i])
+            FD_CUDA(cudaMemcpyAsync(dst, frames[i].data, (size_t)dpitch[i] * frames[i].height, cudaMemcpyHostToDevice, ctx->stream));
+        else
+            FD_CUDA(cudaMemcpy2DAsync(dst, dpitch[i], frames[i].data, frames[i].pitch, (size_t)frames[i].width * 3, frames[i].height,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        h2d += (int64_t)frames[i].width * 3 * frames[i].height;
+        dframes[i] = fd_frame{dst, frames[i].height, frames[i].width, dpitch[i]};
+    }
+    // 2. preprocess -> CNN input tensor (stays on the device unless out->tensor is given)
+    const size_t tn = (size_t)B * 3 * ctx->cfg.image_h * ctx->cfg.image_w;
+    FD_TRY(ctx->pipe_tensor.reserve(sizeof(float) * tn));
+    FD_TRY(fd_preprocess_batch(ctx, dframes.data(), B, ctx->pipe_tensor.as<float>(), out->det_scale));
+    // 3. heads H2D (the CNN outputs), decode + NMS
+    const float *dev_heads[3 * FD_MAX_STRIDES];
+    for (int s = 0; s < d.n_strides; ++s) {
+        const int hw = d.fh[s] * d.fw[s];
+        const int ch[3] = {2 * d.A, 4 * d.A, 10 * d.A};
+        for (int k = 0; k < 3; ++k) {
+            const size_t bytes = sizeof(float) * (size_t)B * ch[k] * hw;
+            FD_TRY(ctx->pipe_heads[3 * s + k].reserve(bytes));
+            FD_CUDA(cudaMemcpyAsync(ctx->pipe_heads[3 * s + k].p, heads_host[3 * s + k], bytes, cudaMemcpyHostToDevice, ctx->stream));
+            dev_heads[3 * s + k] = ctx->pipe_heads[3 * s + k].as<float>();
+            h2d += (int64_t)bytes;
+        }
+    }
+    std::vector<float> ds(B);
+    for (int i = 0; i < B; ++i) {
+        int nw, nh;
+        letterbox(frames[i].height, frames[i].width, ctx->cfg.image_w, ctx->cfg.image_h, &nw, &nh, &ds[i]);
+        if (out->det_scale) out->det_scale[i] = ds[i];
+    }
+    FD_TRY(detect_enqueue(ctx, dev_heads, B, ds.data(), conf_thr, iou_thr));
+    // 4. align every detection on the device
+    const size_t crop_bytes = (size_t)ctx->cfg.crop_w * ctx->cfg.crop_h * 3;
+    FD_TRY(ctx->pipe_crops.reserve(crop_bytes * (size_t)out->cap_rows));
+    FD_TRY(fd_align_detections(ctx, dframes.data(), B, ctx->pipe_crops.as<uint8_t>(), out->cap_rows, nullptr, nullptr));
+    // 5. results D2H
+    int total = 0;
+    FD_TRY(fd_detect_fetch(ctx, out->counts, out->det, out->landmarks, out->cap_rows, &total));
+    out->total = total;
+    d2h += (int64_t)sizeof(int) * (B + 1) + (int64_t)total * 15 * sizeof(float);
+    if (total) FD_CUDA(cudaMemcpyAsync(out->crops, ctx->pipe_crops.p, crop_bytes * (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+    d2h += (int64_t)crop_bytes * total;
+    if (out->tensor) {
+        FD_CUDA(cudaMemcpyAsync(out->tensor, ctx->pipe_tensor.p, sizeof(float) * tn, cudaMemcpyDeviceToHost, ctx->stream));
+        d2h += (int64_t)sizeof(float) * tn;
+    }
+    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    out->h2d_bytes = h2d;
+    out->d2h_bytes = d2h;
+    return FD_OK;
+}
+
+FD_EXPORT int fd_pipeline_tensor_dev(fd_ctx *ctx, const float **out_nchw_dev) {
+    FD_REQUIRE(ctx && out_nchw_dev, "fd_pipeline_tensor_dev: null");
+    *out_nchw_dev = ctx->pipe_tensor.as<float>();
+    return FD_OK;
+}

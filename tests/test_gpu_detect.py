@@ -1,0 +1,114 @@
+"""Decode + sort + NMS + rescale parity (face_detection.rs:319-493) through the C ABI vs the oracle."""
+import numpy as np
+import pytest
+
+from rs_face_detection_b200.utils import synth
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+
+
+def _check_image(oracle, cfg, heads_b, det_scale, det, lmk):
+    """GPU result vs the oracle.  Boxes/landmarks within 1e-5 relative (exp differs in the last ulp between expf
+    implementations); the keep list is checked bit-exactly by feeding the GPU-decoded, GPU-ordered boxes to the
+    oracle NMS (SURVEY §7 'exp in decode')."""
+    edet, elmk, K = oracle.detect_post(cfg, heads_b, det_scale)
+    assert len(det) == len(edet), (len(det), len(edet))
+    np.testing.assert_allclose(det, edet, rtol=REL, atol=1e-4)
+    np.testing.assert_allclose(lmk, elmk, rtol=REL, atol=1e-4)
+    np.testing.assert_array_equal(det[:, 4], edet[:, 4])           # scores are copied, never recomputed
+    return K
+
+
+@pytest.mark.parametrize("conf,iou", [(0.7, 0.4), (0.7, 0.45), (0.02, 0.4)])
+def test_c1_single_image(ctx, oracle, conf, iou):
+    """BASELINE config 1: 640x640 single image, synthetic heads for strides 32/16/8 (16,800 anchors)."""
+    heads, _ = synth.make_heads(1, seed=1234, n_faces=20)
+    hb = [h[0] for h in heads]
+    cfg = oracle.make_det_cfg(conf_thr=conf, iou_thr=iou)
+    det, lmk = ctx.detect(hb, 1.0, conf, iou)
+    K = _check_image(oracle, cfg, hb, 1.0, det, lmk)
+    assert K > (10000 if conf < 0.1 else 20)
+
+
+def test_decode_candidates_and_exact_keep(ctx, oracle):
+    """Stage-level: candidate boxes vs oracle decode, and bit-exact keep list on IDENTICAL boxes."""
+    heads, _ = synth.make_heads(3, seed=99, n_faces=25)
+    devs = [ctx.to_device(h) for h in heads]
+    ctx.detect_batch(devs, 3, np.ones(3, np.float32), 0.5, 0.4)
+    counts, det, lmk = ctx.detect_fetch(3)
+    cfg = oracle.make_det_cfg(conf_thr=0.5, iou_thr=0.4)
+    off = 0
+    for b in range(3):
+        hb = [h[b] for h in heads]
+        box, score, clmk, idx = oracle.decode_candidates(cfg, hb)
+        d = det[off:off + counts[b]]
+        # every GPU detection is one of the oracle's candidates (same score, box within tolerance)
+        order = oracle.argsort_descending(score)
+        pre = np.concatenate([box[order], score[order, None]], 1)
+        keep = oracle.nms(pre, 0.4)
+        np.testing.assert_array_equal(d[:, 4], pre[keep, 4])
+        np.testing.assert_allclose(d[:, :4], pre[keep, :4], rtol=REL, atol=1e-4)
+        off += counts[b]
+    assert off == len(det)
+
+
+def test_batch_with_ragged_and_empty_images(ctx, oracle):
+    heads, _ = synth.make_heads(6, seed=7, n_faces=12)
+    for h in heads[0::3]:
+        h[2, 2:] = 0.0           # image 2: no foreground at all -> (0,5), (0,5,2)   (face_detection.rs:413-419)
+        h[2, :2] = 1.0
+    scales = np.array([1.0, 0.5, 0.33333334, 0.25, 0.16666667, 1.5], np.float32)
+    devs = [ctx.to_device(h) for h in heads]
+    ctx.detect_batch(devs, 6, scales, 0.7, 0.45)
+    counts, det, lmk = ctx.detect_fetch(6)
+    cfg = oracle.make_det_cfg(conf_thr=0.7, iou_thr=0.45)
+    assert counts[2] == 0
+    off = 0
+    for b in range(6):
+        _check_image(oracle, cfg, [h[b] for h in heads], scales[b], det[off:off + counts[b]], lmk[off:off + counts[b]])
+        off += counts[b]
+    v = ctx.detect_view()
+    assert v.det_dev and v.landmarks_dev and v.offsets_dev
+
+
+def test_all_anchors_pass_big_path_in_batch(ctx, oracle):
+    """conf 0.02 with every anchor above threshold: K = 16800 per image -> the per-image big path (radix + peel)."""
+    heads = synth.make_dense_heads(2, seed=3)
+    devs = [ctx.to_device(h) for h in heads]
+    ctx.detect_batch(devs, 2, np.ones(2, np.float32), 0.02, 0.4)
+    counts, det, lmk = ctx.detect_fetch(2)
+    cfg = oracle.make_det_cfg(conf_thr=0.02, iou_thr=0.4)
+    off = 0
+    for b in range(2):
+        K = _check_image(oracle, cfg, [h[b] for h in heads], 1.0, det[off:off + counts[b]], lmk[off:off + counts[b]])
+        assert K == 16800
+        off += counts[b]
+
+
+def test_score_ties_follow_concat_order(ctx, oracle):
+    """Equal scores across strides: the stable order is stride32 | stride16 | stride8, then (h,w,a) (face_detection.rs:410)."""
+    heads, _ = synth.make_heads(1, seed=5, n_faces=0, bg=False)
+    rng = np.random.default_rng(1)
+    for s in range(3):
+        n = heads[3 * s].shape[-1]
+        pick = rng.integers(0, n, (12, 2))
+        for (hh, ww) in pick:
+            a = int(rng.integers(0, 2))
+            heads[3 * s][0, 2 + a, hh, ww] = 0.875
+            heads[3 * s][0, a, hh, ww] = 0.125
+    hb = [h[0] for h in heads]
+    cfg = oracle.make_det_cfg(conf_thr=0.7, iou_thr=0.45)
+    det, lmk = ctx.detect(hb, 1.0, 0.7, 0.45)
+    edet, elmk, K = oracle.detect_post(cfg, hb, 1.0)
+    assert K >= 30
+    np.testing.assert_allclose(det, edet, rtol=REL, atol=1e-4)    # same rows in the same order
+    np.testing.assert_allclose(lmk, elmk, rtol=REL, atol=1e-4)
+
+
+def test_nan_score_is_an_error(ctx):
+    from rs_face_detection_b200 import FdError
+    heads, _ = synth.make_heads(1, seed=5, n_faces=2)
+    heads[3][0, 2, 3, 3] = np.nan
+    with pytest.raises(FdError):
+        ctx.detect([h[0] for h in heads], 1.0, 0.7, 0.45)
