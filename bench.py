@@ -329,7 +329,7 @@ def run_ours(args):
         return a.elapsed_time(b) / n * 1e3   # us
 
     ds = ctx.preprocess_batch(frames_l, tensor_t)
-    stages = {
+    stages = None if args.no_stages else {
         "preprocess_us": time_stage(lambda: ctx.preprocess_batch(frames_l, tensor_t)),
         "decode_nms_us": time_stage(lambda: ctx.detect_batch(heads_t, BATCH, ds, CONF_THR, IOU_THR)),
         "align_us": time_stage(lambda: ctx.align_detections(frames_l, crops_t, cap_faces)),
@@ -441,6 +441,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-nms", action="store_true")
+    ap.add_argument("--no-stages", action="store_true", help="skip the per-stage timing loops (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

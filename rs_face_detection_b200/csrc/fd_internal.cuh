@@ -134,7 +134,7 @@ int check_ctx(const fd_ctx *ctx);
 
 // Maps an f32 to a u32 whose ASCENDING order is the DESCENDING float order (for finite / inf values).
 __device__ __forceinline__ uint32_t desc_key(float f) {
-    uint32_t u = __float_as_uint(f);
+    uint32_t u = (f == 0.0f) ? 0u : __float_as_uint(f);  // -0.0 == +0.0 under partial_cmp: one key, stable tie
     uint32_t asc = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending-orderable
     return ~asc;
 }

@@ -28,7 +28,7 @@ def test_c1_single_image(ctx, oracle, conf, iou):
     cfg = oracle.make_det_cfg(conf_thr=conf, iou_thr=iou)
     det, lmk = ctx.detect(hb, 1.0, conf, iou)
     K = _check_image(oracle, cfg, hb, 1.0, det, lmk)
-    assert K > (10000 if conf < 0.1 else 20)
+    assert K > (4096 if conf < 0.1 else 20)   # conf 0.02 exceeds the single-CTA capacity -> big path
 
 
 def test_decode_candidates_and_exact_keep(ctx, oracle):

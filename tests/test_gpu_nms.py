@@ -136,12 +136,19 @@ def test_vs_reference_cuda_nms(ctx, oracle):
     if not os.path.exists(path):
         pytest.skip("oracle/_ref not built")
     ref = C.CDLL(path)
+    # nms_kernel.cu:91 defines _nms(.., const float*, ..) while gpu_nms.hpp:7 declares float*: the definition is a
+    # C++ overload, not the extern "C" symbol, so look the mangled name up.
+    import subprocess
+    names = [l.split()[-1] for l in subprocess.check_output(["nm", "-D", "--defined-only", path], text=True).splitlines()
+             if "_nms" in l and "kernel" not in l]
+    assert names, "no _nms symbol in oracle/_ref"
+    ref_nms = getattr(ref, names[0])
     dets = _random_dets(5000, 99, canvas=1200)
     srt = np.ascontiguousarray(dets[oracle.argsort_descending(dets[:, 4])])
     keep = np.zeros(len(srt), np.int32)
     num = C.c_int(0)
-    ref._nms(keep.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(num), srt.ctypes.data_as(C.POINTER(C.c_float)), len(srt), 5,
-             C.c_float(0.4), 0)
+    ref_nms(keep.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(num), srt.ctypes.data_as(C.POINTER(C.c_float)), len(srt), 5,
+            C.c_float(0.4), 0)
     np.testing.assert_array_equal(ctx.nms_sorted(srt, 0.4), keep[:num.value])
 
 
