@@ -172,7 +172,7 @@ __device__ __forceinline__ bool box_is_fast_ok(float4 b) {
 #endif  // __CUDACC__
 
 // stage entry points implemented across the .cu files
-int preprocess_launch(fd_ctx *ctx, const FrameDev *frames_dev, int B, float *out_nchw_dev, int max_row_bytes);
+int preprocess_launch(fd_ctx *ctx, const FrameDev *frames_dev, int B, float *out_nchw_dev, int max_row_bytes, bool rows_aligned16);
 int resize_launch(fd_ctx *ctx, const FrameDev &frame, uint8_t *out_dev, int out_h, int out_w);
 int decode_launch(fd_ctx *ctx, const float *const *heads_dev, int B, float conf_thr);
 int nms_batch_launch(fd_ctx *ctx, int B, float iou_thr);

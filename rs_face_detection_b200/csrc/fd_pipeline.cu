@@ -7,7 +7,6 @@
 
 namespace fd {
 
-int preprocess_launch(fd_ctx *ctx, const FrameDev *frames_dev, int B, float *out_nchw_dev, int max_row_bytes);
 int resize_launch(fd_ctx *ctx, const FrameDev &frame, uint8_t *out_dev, int out_h, int out_w);
 int nms_batch_big_image(fd_ctx *ctx, int b, int K, float iou_thr);
 int estimate_launch(fd_ctx *ctx, const float *from_dev, const float *to_dev, const int *count_dev, int F_cap,
@@ -168,7 +167,11 @@ FD_EXPORT int fd_preprocess_batch(fd_ctx *ctx, const fd_frame *frames, int B, fl
     if (B == 0) return FD_OK;
     int mrb = 0;
     FD_TRY(upload_frame_table(ctx, frames, B, det_scale_host, &mrb));
-    return preprocess_launch(ctx, ctx->frames_dev.as<FrameDev>(), B, out_nchw_dev, mrb);
+    bool aligned = true;  // bulk-TMA staging needs 16-byte aligned rows that can be over-read to a 16-byte multiple
+    for (int i = 0; i < B; ++i)
+        aligned = aligned && (reinterpret_cast<uintptr_t>(frames[i].data) % 16 == 0) && (frames[i].pitch % 16 == 0) &&
+                  (((frames[i].width * 3 + 15) & ~15) <= frames[i].pitch);
+    return preprocess_launch(ctx, ctx->frames_dev.as<FrameDev>(), B, out_nchw_dev, mrb, aligned);
 }
 
 FD_EXPORT int fd_detect_batch(fd_ctx *ctx, const float *const *heads_dev, int n_heads, int B, const float *det_scale_host,
