@@ -146,22 +146,42 @@ __device__ __forceinline__ float box_area(float4 b) {
 
 // MODE 0: processing::nms::nms — a box survives iff ovr <= thr (nms.rs:58), so suppress = !(ovr <= thr)
 // MODE 1: rcnn::cpu_nms — suppress iff ovr >= thr (cpu_nms.rs:48)
-// FAST: every box has a finite positive area and thr admits the "no intersection => no suppression" shortcut
-// (MODE 0: thr >= 0, MODE 1: thr > 0); then a pair with w<=0 or h<=0 has ovr == +0 exactly and is skipped
-// without the division.  Otherwise the full IEEE expression is evaluated for every pair.
-template <int MODE, bool FAST>
-__device__ __forceinline__ bool iou_suppresses(const float4 a, const float4 b, const float thr) {
+//
+// Full IEEE expression (used when any box is degenerate / non-finite or thr is negative, NaN or huge):
+template <int MODE>
+__device__ __forceinline__ bool iou_suppresses_full(const float4 a, const float4 b, const float thr) {
     float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
     float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
     float w = fmaxf(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
     float h = fmaxf(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
-    if (FAST) {
-        if (!(w > 0.0f && h > 0.0f)) return false;
-    }
     float inter = __fmul_rn(w, h);
     float uni = __fsub_rn(__fadd_rn(box_area(a), box_area(b)), inter);
     float ovr = __fdiv_rn(inter, uni);
     return MODE == 0 ? !(ovr <= thr) : (ovr >= thr);
+}
+
+// Exact test WITHOUT the division, valid when every box has a finite positive area and thr is an ordinary
+// non-negative threshold (the kernels check both):  the float quotient fl(inter/uni) exceeds thr exactly when the real
+// quotient lies beyond the midpoint m between thr and its neighbouring float (ties resolved by round-to-even, `incl`).
+// inter and uni are the same separately-rounded f32 values the reference computes; m has <= 25 significant bits and
+// uni 24, so m*uni is exact in fp64 and the comparison is exact.  Non-intersecting pairs (ovr == +0) exit early.
+struct IouParams {
+    float thr;
+    double m;   // decision boundary
+    int incl;   // boundary itself suppresses
+    int fast;   // thr admits this test (host side); the kernels AND it with the per-problem box check
+};
+__device__ __forceinline__ bool iou_suppresses_exact(const float4 a, const float area_a, const float4 b, const float area_b,
+                                                     const IouParams &p) {
+    float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+    float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    float w = __fadd_rn(__fsub_rn(xx2, xx1), 1.0f);
+    float h = __fadd_rn(__fsub_rn(yy2, yy1), 1.0f);
+    if (!(w > 0.0f && h > 0.0f)) return false;
+    float inter = __fmul_rn(w, h);
+    float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    double lhs = (double)inter, rhs = p.m * (double)uni;
+    return p.incl ? (lhs >= rhs) : (lhs > rhs);
 }
 
 __device__ __forceinline__ bool box_is_fast_ok(float4 b) {

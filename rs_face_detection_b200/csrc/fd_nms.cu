@@ -16,6 +16,8 @@
 //   K  > 4096 : LSD radix sort (own kernels) + one cooperative persistent kernel; CTA 0 resolves heads, all CTAs push.
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <cmath>
+#include <cstring>
 #include "fd_internal.cuh"
 
 namespace cg = cooperative_groups;
@@ -28,6 +30,7 @@ constexpr int NT = 1024;          // threads per NMS CTA
 constexpr int NWARPS = NT / 32;
 constexpr int HEAD = 1024;        // boxes resolved per stage
 constexpr int HEAD_WORDS = HEAD / 64;
+constexpr int HEAD_MIN = 128;      // initial head of the adaptive peel
 constexpr int MASK_WORDS = 64 * (HEAD_WORDS * (HEAD_WORDS + 1) / 2);  // lower-triangular tiles
 constexpr int SMALL_CAP = 4096;
 
@@ -39,32 +42,41 @@ __device__ __forceinline__ int mask_index(int i, int w) {
 }
 
 // ---- head resolve -------------------------------------------------------------------------------------
+// Work unit = (tile pair, 16-column quarter, 32-row half): lanes are consecutive rows, the column box is a warp-uniform
+// shared-memory broadcast, and each lane writes its own 16-bit piece of the 64-bit mask word (no atomics).
 template <int MODE, bool FAST>
-__device__ void build_mask(const float4 *__restrict__ hbox, int S, u64 *__restrict__ mask, float thr) {
+__device__ void build_mask(const float4 *__restrict__ hbox, const float *__restrict__ harea, int S, u64 *__restrict__ mask,
+                           const IouParams P, int nwarps) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = (S + 63) >> 6;
-    const int nunits = T * (T + 1);  // (tile pairs) x 2 half-tiles of 32 rows
-    for (int u = warp; u < nunits; u += NWARPS) {
-        int p = u >> 1, half = u & 1;
+    const int nunits = T * (T + 1) * 4;  // (tile pairs) x 4 quarters x 2 halves
+    unsigned short *mask16 = reinterpret_cast<unsigned short *>(mask);
+    for (int u = warp; u < nunits; u += nwarps) {
+        const int p = u >> 3, q = (u >> 1) & 3, half = u & 1;
         int ti = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
         while ((ti + 1) * (ti + 2) / 2 <= p) ++ti;
         while (ti * (ti + 1) / 2 > p) --ti;
-        int tj = p - ti * (ti + 1) / 2;
-        int i = ti * 64 + half * 32 + lane;
-        int jbase = tj * 64;
-        int lane_bound = min(64, S - jbase);                 // columns that exist
-        if (ti == tj) lane_bound = min(lane_bound, i - jbase);  // only earlier boxes j < i
-        if (i >= S) lane_bound = 0;
-        int warp_bound = min(64, S - jbase);
-        if (ti == tj) warp_bound = min(warp_bound, half * 32 + 31);
-        u64 word = 0;
-        float4 bi = hbox[min(i, S - 1)];
-        for (int c = 0; c < warp_bound; ++c) {
-            float4 bj = hbox[jbase + c];  // warp-uniform address: shared-memory broadcast
-            bool s = iou_suppresses<MODE, FAST>(bj, bi, thr);
-            if (s && c < lane_bound) word |= (1ull << c);
+        const int tj = p - ti * (ti + 1) / 2;
+        const int i = ti * 64 + half * 32 + lane;
+        const int jbase = tj * 64 + q * 16;
+        int lane_bound = min(16, S - jbase);                    // columns that exist
+        int warp_bound = lane_bound;
+        if (ti == tj) {                                         // only earlier boxes j < i
+            lane_bound = min(lane_bound, i - jbase);
+            warp_bound = min(warp_bound, ti * 64 + half * 32 + 31 - jbase);
         }
-        mask[mask_index(i, tj)] = word;
+        if (i >= S) lane_bound = 0;
+        unsigned bits = 0;
+        const float4 bi = hbox[min(i, S - 1)];
+        const float ai = harea[min(i, S - 1)];
+        for (int c = 0; c < warp_bound; ++c) {
+            const float4 bj = hbox[jbase + c];
+            bool s;
+            if (FAST) s = iou_suppresses_exact(bj, harea[jbase + c], bi, ai, P);
+            else s = iou_suppresses_full<MODE>(bj, bi, P.thr);
+            if (s && c < lane_bound) bits |= (1u << c);
+        }
+        mask16[(size_t)mask_index(i, tj) * 4 + q] = (unsigned short)bits;
     }
 }
 
@@ -103,14 +115,14 @@ __device__ void resolve_rounds(const u64 *__restrict__ mask, int S, u64 *kept, u
 }
 
 // exclusive position of `flag` among the block's threads (thread order) and the block total
-__device__ __forceinline__ int block_compact_pos(bool flag, int *warp_sums, int *total) {
+__device__ __forceinline__ int block_compact_pos(bool flag, int *warp_sums, int *total, int nwarps) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned bal = __ballot_sync(0xffffffffu, flag);
     int within = __popc(bal & ((1u << lane) - 1u));
     if (lane == 0) warp_sums[warp] = __popc(bal);
     __syncthreads();
     if (warp == 0) {
-        int v = warp_sums[lane];
+        int v = lane < (int)(blockDim.x >> 5) && lane < nwarps ? warp_sums[lane] : 0;
         int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -145,7 +157,8 @@ __device__ __forceinline__ int kept_rank(const u64 *kept, int i, int *total) {
 struct SmallSmem {
     float4 sbox[SMALL_CAP];   // boxes in sorted order
     float4 hbox[HEAD];        // current head
-    u64 mask[MASK_WORDS];     // also: kept boxes of the head (float4[HEAD]) during the push
+    float harea[HEAD];        // areas of the head boxes
+    u64 mask[MASK_WORDS];     // also: kept boxes of the head (float4[HEAD] + float[HEAD]) during the push
     u64 keys[SMALL_CAP];      // sort keys; afterwards two int streams [2][SMALL_CAP]
     int sidx[SMALL_CAP];      // source index of sorted rank r
     u64 kept[HEAD_WORDS], und[HEAD_WORDS];
@@ -171,7 +184,7 @@ struct SmallArgs {
     int K;
     int presorted;            // 1 -> input already in pick order (the `_nms` contract): no sort
     int sort_only;            // 1 -> write the sorted source indices and stop (argsort_descending)
-    float thr;
+    IouParams iou;
     int *keep;                // [B][keep_stride] source indices in pick order
     size_t keep_stride;
     int *keep_count;          // [B]
@@ -197,13 +210,18 @@ __global__ void __launch_bounds__(NT, 1) nms_cta_kernel(SmallArgs a) {
         }
         return;
     }
+    // Small problems run on 8 warps: whole warps beyond that leave before the first barrier (barriers only count
+    // non-exited warps), which makes every block-wide step of the kernel ~4x cheaper for the typical K of a few hundred.
+    const int nthr = K <= 256 ? 256 : NT;
+    if (tid >= nthr) return;
+    const int nwarps = nthr >> 5;
     const float *boxes = a.boxes + (size_t)b * a.box_batch_stride;
 
-    // ---- 1. keys + bitonic sort (ascending u64 == score desc, index asc) ----
+    // ---- 1. keys + sort (ascending u64 == score desc, index asc) ----
     int n2 = 2;
     while (n2 < K) n2 <<= 1;
     bool nan_seen = false;
-    for (int i = tid; i < n2; i += NT) {
+    for (int i = tid; i < n2; i += nthr) {
         u64 key = ~0ull;
         if (i < K) {
             if (a.keys) key = a.keys[(size_t)b * a.key_stride + i];
@@ -222,58 +240,75 @@ __global__ void __launch_bounds__(NT, 1) nms_cta_kernel(SmallArgs a) {
         }
         return;
     }
+    u64 *sorted = sm.keys;
     if (!a.presorted) {
-        for (unsigned k = 2; k <= (unsigned)n2; k <<= 1) {
-            for (unsigned j = k >> 1; j > 0; j >>= 1) {
-                for (unsigned t = tid; t < (unsigned)n2 / 2; t += NT) {
-                    unsigned i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                    unsigned l = i | j;
-                    bool up = ((i & k) == 0);
-                    u64 x = sm.keys[i], y = sm.keys[l];
-                    if ((x > y) == up) {
-                        sm.keys[i] = y;
-                        sm.keys[l] = x;
+        if (K <= 256) {
+            // rank sort: keys are unique (the index is in the low bits), one key per thread, K broadcast reads
+            u64 mine = tid < K ? sm.keys[tid] : ~0ull;
+            int rank = 0;
+            for (int j = 0; j < K; ++j) rank += (sm.keys[j] < mine) ? 1 : 0;
+            sorted = sm.keys + SMALL_CAP / 2;
+            if (tid < K) sorted[rank] = mine;
+            __syncthreads();
+        } else {
+            for (unsigned k = 2; k <= (unsigned)n2; k <<= 1) {
+                for (unsigned j = k >> 1; j > 0; j >>= 1) {
+                    for (unsigned t = tid; t < (unsigned)n2 / 2; t += nthr) {
+                        unsigned i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                        unsigned l = i | j;
+                        bool up = ((i & k) == 0);
+                        u64 x = sm.keys[i], y = sm.keys[l];
+                        if ((x > y) == up) {
+                            sm.keys[i] = y;
+                            sm.keys[l] = x;
+                        }
                     }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
         }
     }
     if (a.sort_only) {
-        for (int r = tid; r < K; r += NT) keep[r] = (int)(unsigned)sm.keys[r];
+        for (int r = tid; r < K; r += nthr) keep[r] = (int)(unsigned)sorted[r];
         if (tid == 0) a.keep_count[b] = K;
         return;
     }
 
     // ---- 2. gather boxes in sorted order ----
     bool ok = true;
-    for (int r = tid; r < K; r += NT) {
-        int idx = (int)(unsigned)sm.keys[r];
+    for (int r = tid; r < K; r += nthr) {
+        int idx = (int)(unsigned)sorted[r];
         sm.sidx[r] = idx;
         float4 bx = load_box<BS>(boxes, idx, a.box_stride);
         sm.sbox[r] = bx;
         ok &= box_is_fast_ok(bx);
     }
-    const bool thr_ok = MODE == 0 ? (a.thr >= 0.0f) : (a.thr > 0.0f);
-    const bool fast = __syncthreads_and(ok) && thr_ok;  // also fences the key reads before the streams alias them
+    const bool fast = __syncthreads_and(ok) && a.iou.fast;  // also fences the key reads before the streams alias them
 
     int *stream_cur = reinterpret_cast<int *>(sm.keys);
     int *stream_nxt = stream_cur + SMALL_CAP;
     float4 *kbox = reinterpret_cast<float4 *>(sm.mask);
+    float *karea = reinterpret_cast<float *>(kbox + HEAD);
     bool identity = true;
     int len = K, nk_total = 0;
+    // Adaptive head: clustered detections (a few kept boxes suppress everything else) want a small head, because only
+    // the KEPT boxes of a head ever touch the rest of the stream; the head doubles while most of it survives.
+    const int head_max = min(HEAD, nthr);
+    int head_cap = min(HEAD_MIN, head_max);
 
     // ---- 3. peel ----
     while (len > 0) {
-        const int S = min(HEAD, len);
+        const int S = min(head_cap, len);
         int my_rank = 0;
         if (tid < S) {
             my_rank = identity ? tid : stream_cur[tid];
-            sm.hbox[tid] = sm.sbox[my_rank];
+            const float4 bx = sm.sbox[my_rank];
+            sm.hbox[tid] = bx;
+            sm.harea[tid] = box_area(bx);
         }
         __syncthreads();
-        if (fast) build_mask<MODE, true>(sm.hbox, S, sm.mask, a.thr);
-        else build_mask<MODE, false>(sm.hbox, S, sm.mask, a.thr);
+        if (fast) build_mask<MODE, true>(sm.hbox, sm.harea, S, sm.mask, a.iou, nwarps);
+        else build_mask<MODE, false>(sm.hbox, sm.harea, S, sm.mask, a.iou, nwarps);
         __syncthreads();
         resolve_rounds(sm.mask, S, sm.kept, sm.und);
         // (resolve_rounds ends on a block-wide barrier: mask is dead from here, kept is final)
@@ -289,30 +324,35 @@ __global__ void __launch_bounds__(NT, 1) nms_cta_kernel(SmallArgs a) {
         const int rem = len - S;
         if (is_kept) {
             keep[nk_total + pos] = sm.sidx[my_rank];
-            if (rem > 0) kbox[pos] = sm.hbox[tid];
+            if (rem > 0) {
+                kbox[pos] = sm.hbox[tid];
+                karea[pos] = sm.harea[tid];
+            }
         }
         nk_total += nkept;
+        if (2 * nkept > S && head_cap < head_max) head_cap *= 2;
         __syncthreads();
         if (rem <= 0) break;
         int new_len = 0;
-        for (int base = 0; base < rem; base += NT) {
+        for (int base = 0; base < rem; base += nthr) {
             int r = base + tid;
             bool alive = false;
             int rk = 0;
             if (r < rem) {
                 rk = identity ? (S + r) : stream_cur[S + r];
-                float4 bx = sm.sbox[rk];
+                const float4 bx = sm.sbox[rk];
                 alive = true;
                 if (fast) {
+                    const float ab = box_area(bx);
                     for (int k = 0; k < nkept; ++k)
-                        if (iou_suppresses<MODE, true>(kbox[k], bx, a.thr)) { alive = false; break; }
+                        if (iou_suppresses_exact(kbox[k], karea[k], bx, ab, a.iou)) { alive = false; break; }
                 } else {
                     for (int k = 0; k < nkept; ++k)
-                        if (iou_suppresses<MODE, false>(kbox[k], bx, a.thr)) { alive = false; break; }
+                        if (iou_suppresses_full<MODE>(kbox[k], bx, a.iou.thr)) { alive = false; break; }
                 }
             }
             int total;
-            int p = block_compact_pos(alive, sm.warp_sums, &total);
+            int p = block_compact_pos(alive, sm.warp_sums, &total, nwarps);
             if (alive) stream_nxt[new_len + p] = rk;
             new_len += total;
         }
@@ -473,7 +513,8 @@ __global__ void low32_kernel(const u64 *__restrict__ keys, int n, int *__restric
 
 struct PeelSmem {
     float4 hbox[HEAD];
-    u64 mask[MASK_WORDS];  // aliased by kbox during push
+    float harea[HEAD];
+    u64 mask[MASK_WORDS];  // aliased by kbox + karea during push
     u64 kept[HEAD_WORDS], und[HEAD_WORDS];
     int warp_sums[33];
     int red[32];
@@ -489,7 +530,7 @@ struct PeelArgs {
     int *tile_counts;   // ceil(N/NT)
     unsigned *ballots;  // ceil(N/NT)*32
     const int *status;  // [2] != 0 -> not fast
-    float thr;
+    IouParams iou;
 };
 
 __device__ __forceinline__ int block_sum(int v, int *red) {
@@ -512,23 +553,26 @@ __global__ void __launch_bounds__(NT, 1) nms_peel_kernel(PeelArgs a) {
     cg::grid_group grid = cg::this_grid();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x;
-    const bool thr_ok = MODE == 0 ? (a.thr >= 0.0f) : (a.thr > 0.0f);
-    const bool fast = thr_ok && (__ldcg(&a.status[2]) == 0);
+    const bool fast = a.iou.fast && (__ldcg(&a.status[2]) == 0);
     float4 *kbox = reinterpret_cast<float4 *>(sm.mask);
+    float *karea = reinterpret_cast<float *>(kbox + HEAD);
     int *cur = a.stream_a, *nxt = a.stream_b;
     bool identity = true;
     int len = a.N, nk_total = 0;
+    int head_cap = HEAD_MIN;
     while (len > 0) {
-        const int S = min(HEAD, len);
+        const int S = min(head_cap, len);
         if (blockIdx.x == 0) {
             int my_rank = 0;
             if (tid < S) {
                 my_rank = identity ? tid : __ldcg(&cur[tid]);
-                sm.hbox[tid] = a.sbox[my_rank];
+                const float4 bx = a.sbox[my_rank];
+                sm.hbox[tid] = bx;
+                sm.harea[tid] = box_area(bx);
             }
             __syncthreads();
-            if (fast) build_mask<MODE, true>(sm.hbox, S, sm.mask, a.thr);
-            else build_mask<MODE, false>(sm.hbox, S, sm.mask, a.thr);
+            if (fast) build_mask<MODE, true>(sm.hbox, sm.harea, S, sm.mask, a.iou, NWARPS);
+            else build_mask<MODE, false>(sm.hbox, sm.harea, S, sm.mask, a.iou, NWARPS);
             __syncthreads();
             resolve_rounds(sm.mask, S, sm.kept, sm.und);
             int nkept = 0;
@@ -547,10 +591,15 @@ __global__ void __launch_bounds__(NT, 1) nms_peel_kernel(PeelArgs a) {
         grid.sync();
         const int nkept = __ldcg(&a.state[2]);
         nk_total += nkept;
+        if (2 * nkept > S && head_cap < HEAD) head_cap *= 2;
         const int rem = len - S;
         if (rem <= 0) break;
         // ---- push: every CTA tests its tiles of the remaining stream against the kept boxes of this stage ----
-        for (int k = tid; k < nkept; k += NT) kbox[k] = __ldcg(&a.ks[k]);
+        for (int k = tid; k < nkept; k += NT) {
+            const float4 kb = __ldcg(&a.ks[k]);
+            kbox[k] = kb;
+            karea[k] = box_area(kb);
+        }
         __syncthreads();
         const int ntiles = (rem + NT - 1) / NT;
         for (int t = blockIdx.x; t < ntiles; t += G) {
@@ -561,11 +610,12 @@ __global__ void __launch_bounds__(NT, 1) nms_peel_kernel(PeelArgs a) {
                 float4 bx = a.sbox[rk];
                 alive = true;
                 if (fast) {
+                    const float ab = box_area(bx);
                     for (int k = 0; k < nkept; ++k)
-                        if (iou_suppresses<MODE, true>(kbox[k], bx, a.thr)) { alive = false; break; }
+                        if (iou_suppresses_exact(kbox[k], karea[k], bx, ab, a.iou)) { alive = false; break; }
                 } else {
                     for (int k = 0; k < nkept; ++k)
-                        if (iou_suppresses<MODE, false>(kbox[k], bx, a.thr)) { alive = false; break; }
+                        if (iou_suppresses_full<MODE>(kbox[k], bx, a.iou.thr)) { alive = false; break; }
                 }
             }
             unsigned bal = __ballot_sync(0xffffffffu, alive);
@@ -610,6 +660,34 @@ __global__ void __launch_bounds__(NT, 1) nms_peel_kernel(PeelArgs a) {
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
+// Decision boundary of the exact division-free test (see iou_suppresses_exact).
+IouParams make_iou_params(float thr, int mode) {
+    IouParams p;
+    p.thr = thr;
+    p.m = 0.0;
+    p.incl = 0;
+    p.fast = 0;
+    if (!(thr == thr) || std::isinf(thr) || thr > 1e30f) return p;
+    uint32_t bits;
+    memcpy(&bits, &thr, 4);
+    if (mode == 0) {          // suppress iff fl(q) > thr  <=>  fl(q) >= next(thr)
+        if (thr < 0.0f) return p;
+        float nxt = nextafterf(thr, INFINITY);
+        uint32_t nb;
+        memcpy(&nb, &nxt, 4);
+        p.m = ((double)thr + (double)nxt) * 0.5;
+        p.incl = (nb & 1u) == 0;   // a tie rounds to the even neighbour: next(thr) when it is even
+        p.fast = 1;
+    } else {                  // suppress iff fl(q) >= thr
+        if (!(thr > 0.0f)) return p;
+        float prv = nextafterf(thr, -INFINITY);
+        p.m = ((double)prv + (double)thr) * 0.5;
+        p.incl = (bits & 1u) == 0; // tie rounds to thr when thr is even
+        p.fast = 1;
+    }
+    return p;
+}
+
 static int radix_sort_u64(fd_ctx *ctx, u64 *keys, u64 *tmp, int n, const int *bytes, int nbytes, int *hist, u64 **sorted) {
     const int ntiles = (n + RS_TILE - 1) / RS_TILE;
     u64 *in = keys, *out = tmp;
@@ -696,7 +774,7 @@ static int nms_big_impl(fd_ctx *ctx, const u64 *keys_in, const int *key_bytes, i
     pa.tile_counts = tile_counts;
     pa.ballots = ballots;
     pa.status = st;
-    pa.thr = thr;
+    pa.iou = make_iou_params(thr, mode);
     const size_t smem = sizeof(PeelSmem);
     void *kargs[] = {&pa};
     const void *fn = mode == 0 ? (const void *)nms_peel_kernel<0> : (const void *)nms_peel_kernel<1>;
@@ -737,7 +815,7 @@ int nms_device(fd_ctx *ctx, const float *dets_dev, int K, int stride, float thr,
         a.K = K;
         a.presorted = presorted ? 1 : 0;
         a.sort_only = 0;
-        a.thr = thr;
+        a.iou = make_iou_params(thr, mode);
         a.keep = keep_dev;
         a.keep_stride = 0;
         a.keep_count = num_keep_dev;
@@ -795,7 +873,7 @@ int nms_batch_launch(fd_ctx *ctx, int B, float iou_thr) {
     a.K = 0;
     a.presorted = 0;
     a.sort_only = 0;
-    a.thr = iou_thr;
+    a.iou = make_iou_params(iou_thr, 0);
     a.keep = ctx->keep_src.as<int>();
     a.keep_stride = (size_t)TA;
     a.keep_count = ctx->keep_count.as<int>();
