@@ -21,7 +21,8 @@ struct EstArgs {
     float tmpl[10];
     const int *count_dev;  // optional device-side F
     int F;
-    int niters;
+    int niters;            // <= 16
+    int8_t pair0[16], pair1[16];  // LMedS sample pairs per iteration (host-precomputed from OpenCV's RNG)
     double *M12;           // (F,12): M (6) then inverse (6)
     double *M_out;         // optional (F,6)
     uint8_t *ok;           // (F)
@@ -60,46 +61,60 @@ __device__ __forceinline__ void invert_affine(const double *M, double *iM) {
     iM[5] = -iM[3] * M[2] - iM[4] * M[5];
 }
 
+// 16 lanes per face: lane k < niters evaluates LMedS iteration k (the sample pairs depend only on the RNG, which OpenCV
+// reseeds per call, so they are precomputed on the host); a (median, iteration) lexicographic min over the lanes picks
+// the model the sequential loop would have kept (first strictly smaller median wins); lane 0 finishes.
+constexpr int EST_LANES = 16;
 __global__ void estimate_kernel(EstArgs a) {
     const int F = a.count_dev ? min(*a.count_dev, a.F) : a.F;
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= F) return;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = gt / EST_LANES, sub = gt % EST_LANES;
+    const bool live = f < F;
+    const int fc = live ? f : 0;
     float from[10], to[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) {
-        from[k] = a.from[(size_t)f * 10 + k];
-        to[k] = a.to ? a.to[(size_t)f * 10 + k] : a.tmpl[k];
+        from[k] = live ? a.from[(size_t)fc * 10 + k] : 0.0f;
+        to[k] = a.to ? (live ? a.to[(size_t)fc * 10 + k] : 0.0f) : a.tmpl[k];
     }
     const int n = 5;
-    unsigned long long rng = 0xFFFFFFFFFFFFFFFFull;
-    double best[6] = {0, 0, 0, 0, 0, 0};
-    double minMedian = DBL_MAX;
+    double model[6] = {0, 0, 0, 0, 0, 0};
+    double median = DBL_MAX;
     float err[5];
-    for (int iter = 0; iter < a.niters; ++iter) {
-        int i0 = (int)(rng_next(rng) % (unsigned)n), i1;
-        do { i1 = (int)(rng_next(rng) % (unsigned)n); } while (i1 == i0);
-        double model[6];
-        fit2(from, to, i0, i1, model);
+    if (live && sub < a.niters) {
+        fit2(from, to, a.pair0[sub], a.pair1[sub], model);
         bool finite = true;
 #pragma unroll
         for (int k = 0; k < 6; ++k) finite &= isfinite(model[k]);
-        if (!finite) continue;
-        affine_err5(from, to, model, err);
-        float s[5] = {err[0], err[1], err[2], err[3], err[4]};
+        if (finite) {
+            affine_err5(from, to, model, err);
+            float s[5] = {err[0], err[1], err[2], err[3], err[4]};
 #pragma unroll
-        for (int i = 1; i < 5; ++i) {  // insertion sort of 5
-            float v = s[i];
-            int j = i - 1;
-            while (j >= 0 && s[j] > v) { s[j + 1] = s[j]; --j; }
-            s[j + 1] = v;
-        }
-        double median = (double)s[2];
-        if (median < minMedian) {
-            minMedian = median;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) best[k] = model[k];
+            for (int i = 1; i < 5; ++i) {  // insertion sort of 5
+                float v = s[i];
+                int j = i - 1;
+                while (j >= 0 && s[j] > v) { s[j + 1] = s[j]; --j; }
+                s[j + 1] = v;
+            }
+            const double med = (double)s[2];
+            if (med < DBL_MAX) median = med;  // NaN / inf medians never win (median < minMedian is false)
         }
     }
+    // lexicographic (median, lane) min within each group of 16 lanes
+    int win = sub;
+    double best_med = median;
+#pragma unroll
+    for (int o = EST_LANES / 2; o > 0; o >>= 1) {
+        const double om = __shfl_xor_sync(0xffffffffu, best_med, o);
+        const int ow = __shfl_xor_sync(0xffffffffu, win, o);
+        if (om < best_med || (om == best_med && ow < win)) { best_med = om; win = ow; }
+    }
+    const int base_lane = (threadIdx.x & 31) & ~(EST_LANES - 1);
+    double best[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) best[k] = __shfl_sync(0xffffffffu, model[k], base_lane + win);
+    if (!live || sub != 0) return;
+    const double minMedian = best_med;
     bool ok = minMedian < DBL_MAX;
     double M[6] = {0, 0, 0, 0, 0, 0};
     if (ok) {
@@ -158,7 +173,8 @@ __global__ void invert_kernel(const double *M, int F, double *M12, uint8_t *ok) 
 }
 
 constexpr int WARP_BAND = 16;     // output rows per CTA
-constexpr int WARP_THREADS = 256;
+constexpr int WARP_TX = 32, WARP_TY = 8;
+constexpr int WARP_THREADS = WARP_TX * WARP_TY;
 
 struct WarpArgs {
     const FrameDev *frames;
@@ -171,36 +187,58 @@ struct WarpArgs {
     int cw, ch;
 };
 
+// The 6 bytes of two horizontally adjacent BGR pixels starting at p, through at most two aligned 64-bit loads (one
+// when the 6 bytes sit inside one 8-byte word) instead of six byte loads: the warp is L1-wavefront bound.
+__device__ __forceinline__ unsigned long long load6(const uint8_t *p, const uint8_t *lo_lim, const uint8_t *hi_lim) {
+    const uintptr_t ad = reinterpret_cast<uintptr_t>(p);
+    const uint8_t *al = reinterpret_cast<const uint8_t *>(ad & ~(uintptr_t)7);
+    const int sh = (int)(ad & 7);
+    if (al >= lo_lim && al + 16 <= hi_lim) {
+        unsigned long long lo = __ldg(reinterpret_cast<const unsigned long long *>(al));
+        if (sh <= 2) return lo >> (8 * sh);
+        unsigned long long hi = __ldg(reinterpret_cast<const unsigned long long *>(al + 8));
+        return (lo >> (8 * sh)) | (hi << (64 - 8 * sh));
+    }
+    unsigned long long v = 0;  // first / last bytes of the frame buffer: plain byte loads
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v |= (unsigned long long)__ldg(p + k) << (8 * k);
+    return v;
+}
+
 __global__ void __launch_bounds__(WARP_THREADS) warp_kernel(WarpArgs a) {
     extern __shared__ int wsm[];
     int *adelta = wsm;             // [cw]
     int *bdelta = adelta + a.cw;   // [cw]
     int *X0s = bdelta + a.cw;      // [WARP_BAND]
     int *Y0s = X0s + WARP_BAND;    // [WARP_BAND]
+    const int tid = threadIdx.y * WARP_TX + threadIdx.x;
     const int F = a.count_dev ? min(*a.count_dev, a.F) : a.F;
     const int band_y0 = blockIdx.x * WARP_BAND;
     const int rows = min(WARP_BAND, a.ch - band_y0);
+    const int ngroups = (a.cw + 3) >> 2;
     for (int f = blockIdx.y; f < F; f += gridDim.y) {
         uint8_t *crop = a.crops + (size_t)f * a.ch * a.cw * 3;
         if (!a.ok[f]) {
-            for (int p = threadIdx.x; p < rows * a.cw * 3; p += WARP_THREADS) crop[(size_t)band_y0 * a.cw * 3 + p] = 0;
+            for (int p = tid; p < rows * a.cw * 3; p += WARP_THREADS) crop[(size_t)band_y0 * a.cw * 3 + p] = 0;
             continue;
         }
         const FrameDev fr = a.frames[a.frame_idx ? a.frame_idx[f] : 0];
         const double *iM = a.M12 + (size_t)f * 12 + 6;
         const double i0 = iM[0], i1 = iM[1], i2 = iM[2], i3 = iM[3], i4 = iM[4], i5 = iM[5];
         __syncthreads();  // previous face's tables are no longer read
-        for (int x = threadIdx.x; x < a.cw; x += WARP_THREADS) {
+        for (int x = tid; x < a.cw; x += WARP_THREADS) {
             adelta[x] = __double2int_rn(i0 * x * 1024);  // saturate_cast<int>(M[0]*x*AB_SCALE)
             bdelta[x] = __double2int_rn(i3 * x * 1024);
         }
-        if (threadIdx.x < rows) {
-            const int y = band_y0 + threadIdx.x;
-            X0s[threadIdx.x] = __double2int_rn((i1 * y + i2) * 1024) + 16;  // + round_delta
-            Y0s[threadIdx.x] = __double2int_rn((i4 * y + i5) * 1024) + 16;
+        if (tid < rows) {
+            const int y = band_y0 + tid;
+            X0s[tid] = __double2int_rn((i1 * y + i2) * 1024) + 16;  // + round_delta
+            Y0s[tid] = __double2int_rn((i4 * y + i5) * 1024) + 16;
         }
         __syncthreads();
-        for (int p = threadIdx.x; p < rows * a.cw; p += WARP_THREADS) {
+        const uint8_t *lo_lim = fr.data, *hi_lim = fr.data + (size_t)(fr.h - 1) * fr.pitch + (size_t)fr.w * 3;  // end of valid pixel bytes
+        // consecutive lanes = consecutive output pixels, so the lanes of one load instruction share cache lines
+        for (int p = tid; p < rows * a.cw; p += WARP_THREADS) {
             const int ry = p / a.cw, x = p - ry * a.cw;
             const int X = (int)((unsigned)X0s[ry] + (unsigned)adelta[x]) >> 5;
             const int Y = (int)((unsigned)Y0s[ry] + (unsigned)bdelta[x]) >> 5;
@@ -210,15 +248,25 @@ __global__ void __launch_bounds__(WARP_THREADS) warp_kernel(WarpArgs a) {
             const int w10 = ay * (32 - ax) * 32, w11 = ay * ax * 32;
             const bool inx0 = sx >= 0 && sx < fr.w, inx1 = sx + 1 >= 0 && sx + 1 < fr.w;
             const bool iny0 = sy >= 0 && sy < fr.h, iny1 = sy + 1 >= 0 && sy + 1 < fr.h;
-            const uint8_t *p0 = fr.data + (ptrdiff_t)sy * fr.pitch + (ptrdiff_t)sx * 3;
-            const uint8_t *p1 = p0 + fr.pitch;
+            unsigned long long t0 = 0, t1 = 0;  // rows sy, sy+1: bytes [b0 g0 r0 b1 g1 r1]
+            if (inx0 && inx1) {
+                const uint8_t *p0 = fr.data + (ptrdiff_t)sy * fr.pitch + (ptrdiff_t)sx * 3;
+                if (iny0) t0 = load6(p0, lo_lim, hi_lim);
+                if (iny1) t1 = load6(p0 + fr.pitch, lo_lim, hi_lim);
+            } else if (inx0 || inx1) {  // one tap column outside the image (BORDER_CONSTANT 0)
+                const int sxv = inx0 ? sx : sx + 1;
+                const int shl = inx0 ? 0 : 24;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (iny0) t0 |= (unsigned long long)__ldg(fr.data + (ptrdiff_t)sy * fr.pitch + sxv * 3 + c) << (8 * c + shl);
+                    if (iny1) t1 |= (unsigned long long)__ldg(fr.data + (ptrdiff_t)(sy + 1) * fr.pitch + sxv * 3 + c) << (8 * c + shl);
+                }
+            }
             uint8_t *o = crop + ((size_t)(band_y0 + ry) * a.cw + x) * 3;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                int v00 = (iny0 && inx0) ? __ldg(p0 + c) : 0;
-                int v01 = (iny0 && inx1) ? __ldg(p0 + 3 + c) : 0;
-                int v10 = (iny1 && inx0) ? __ldg(p1 + c) : 0;
-                int v11 = (iny1 && inx1) ? __ldg(p1 + 3 + c) : 0;
+                const int v00 = (int)((t0 >> (8 * c)) & 0xff), v01 = (int)((t0 >> (8 * c + 24)) & 0xff);
+                const int v10 = (int)((t1 >> (8 * c)) & 0xff), v11 = (int)((t1 >> (8 * c + 24)) & 0xff);
                 o[c] = (uint8_t)((v00 * w00 + v01 * w01 + v10 * w10 + v11 * w11 + (1 << 14)) >> 15);
             }
         }
@@ -247,11 +295,22 @@ int estimate_launch(fd_ctx *ctx, const float *from_dev, const float *to_dev, con
     a.count_dev = count_dev;
     a.F = F_cap;
     a.niters = std::max(lmeds_niters(0.99, 0.45, 2, 2000), 3);
+    if (a.niters > 16) return fail(FD_ERR_INVALID, "estimate: LMedS iteration count exceeds the lane group");
+    {   // cv::RNG(-1): state = (uint32)state * 4164903690 + (state >> 32); uniform(0,n) = next() % n
+        unsigned long long st = 0xFFFFFFFFFFFFFFFFull;
+        auto next = [&]() { st = (unsigned long long)(unsigned)st * 4164903690ull + (unsigned)(st >> 32); return (unsigned)st; };
+        for (int it = 0; it < 16; ++it) {
+            int i0 = (int)(next() % 5u), i1;
+            do { i1 = (int)(next() % 5u); } while (i1 == i0);
+            a.pair0[it] = (int8_t)i0;
+            a.pair1[it] = (int8_t)i1;
+        }
+    }
     a.M12 = M12_dev;
     a.M_out = M_out_dev;
     a.ok = ok_dev;
     a.ok_out = ok_out_dev;
-    estimate_kernel<<<(F_cap + 127) / 128, 128, 0, ctx->stream>>>(a);
+    estimate_kernel<<<(F_cap * EST_LANES + 127) / 128, 128, 0, ctx->stream>>>(a);
     FD_LAUNCH_CHECK(ctx);
     return FD_OK;
 }
@@ -280,7 +339,7 @@ int warp_launch(fd_ctx *ctx, const FrameDev *frames_dev, const int32_t *frame_id
     // device-side counts: a bounded grid that strides over the faces
     int gy = count_dev ? std::min(F_cap, std::max(1, ctx->num_sms * 8 / bands)) : std::min(F_cap, 65535);
     size_t smem = sizeof(int) * (2 * (size_t)cw + 2 * WARP_BAND);
-    warp_kernel<<<dim3(bands, gy), WARP_THREADS, smem, ctx->stream>>>(a);
+    warp_kernel<<<dim3(bands, gy), dim3(WARP_TX, WARP_TY), smem, ctx->stream>>>(a);
     FD_LAUNCH_CHECK(ctx);
     return FD_OK;
 }
