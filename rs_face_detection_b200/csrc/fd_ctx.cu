@@ -261,6 +261,7 @@ FD_EXPORT void fd_ctx_destroy(fd_ctx *ctx) {
                       &ctx->align_ok, &ctx->pipe_frames, &ctx->pipe_tensor, &ctx->pipe_crops};
     for (auto *b : bufs) b->release();
     for (auto &b : ctx->nms_ws) b.release();
+    for (auto &b : ctx->nms_ws_sp) b.release();
     for (auto &b : ctx->pipe_heads) b.release();
     for (int i = 0; i < 4; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

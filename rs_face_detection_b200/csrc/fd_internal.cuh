@@ -101,6 +101,7 @@ struct fd_ctx {
     fd::DevBuf align_M;          // double[F][12] (M, inverse)
     fd::DevBuf align_ok;         // u8[F]
     fd::DevBuf nms_ws[8];        // big-path workspaces
+    fd::DevBuf nms_ws_sp[4];     // spatial big-path workspaces
     fd::DevBuf pipe_frames;      // host pipeline: device copies of frames
     fd::DevBuf pipe_heads[3 * FD_MAX_STRIDES];
     fd::DevBuf pipe_tensor;

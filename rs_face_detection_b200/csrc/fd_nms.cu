@@ -553,6 +553,7 @@ __global__ void __launch_bounds__(NT, 1) nms_peel_kernel(PeelArgs a) {
     cg::grid_group grid = cg::this_grid();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x;
+    if (__ldcg(&a.status[3]) != 0) return;  // uniform over the grid: the spatial path owns this problem
     const bool fast = a.iou.fast && (__ldcg(&a.status[2]) == 0);
     float4 *kbox = reinterpret_cast<float4 *>(sm.mask);
     float *karea = reinterpret_cast<float *>(kbox + HEAD);
@@ -659,6 +660,272 @@ __global__ void __launch_bounds__(NT, 1) nms_peel_kernel(PeelArgs a) {
     if (blockIdx.x == 0 && tid == 0) a.state[1] = nk_total;
 }
 
+// ============================================================================================================
+// Spatial big path: exact greedy NMS with work proportional to the number of OVERLAPPING pairs.
+//
+// IoU(A,B) > t implies the intersection is at least t x the larger box in each axis, hence the box centres are at
+// most (1-t) x max(w) apart per axis.  Boxes are binned by centre into a uniform grid with that cell size (stable
+// radix sort on the cell id: cells come out with their members in rank order), every box collects the EARLIER-ranked
+// boxes of its 3x3 neighbourhood that suppress it (exact predicate) into a short predecessor list, and the keep set is
+// the unique fixed point of   kept(i) = no predecessor kept,   resolved by monotone parallel sweeps inside one
+// cooperative kernel (a box is suppressed as soon as one predecessor is kept, kept as soon as all are suppressed).
+// Same result as the sequential sweep of nms.rs; used when every box is regular (finite, positive area), the
+// threshold is an ordinary one and the grid is fine enough — otherwise the peel kernel above does the job.
+// ============================================================================================================
+constexpr int ADJ_CAP = 32;
+constexpr int GRID_MAX_CELLS = 65535;
+constexpr int GRID_MAX_DIM = 4096;
+
+struct GridCfg {
+    float minx, miny, cs;
+    int gx, gy, use;
+};
+
+__device__ __forceinline__ unsigned f2ord(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned e) {
+    unsigned u = (e & 0x80000000u) ? (e & 0x7fffffffu) : ~e;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ float box_cx(float4 b) { return __fmul_rn(__fadd_rn(b.x, b.z), 0.5f); }
+__device__ __forceinline__ float box_cy(float4 b) { return __fmul_rn(__fadd_rn(b.y, b.w), 0.5f); }
+__device__ __forceinline__ int cell_coord(float c, float minc, float cs, int g) {
+    int v = (int)floorf(__fdiv_rn(__fsub_rn(c, minc), cs));
+    return min(g - 1, max(0, v));
+}
+
+// gs: [0] min cx, [1] min cy (init 0xFFFFFFFF), [2] max cx, [3] max cy, [4] max dim (init 0); ordered-uint encoding
+__global__ void grid_stats_kernel(const float4 *__restrict__ sbox, int N, unsigned *gs) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned mincx = 0xFFFFFFFFu, mincy = 0xFFFFFFFFu, maxcx = 0, maxcy = 0, maxd = 0;
+    if (r < N) {
+        float4 b = sbox[r];
+        unsigned cx = f2ord(box_cx(b)), cy = f2ord(box_cy(b));
+        mincx = maxcx = cx;
+        mincy = maxcy = cy;
+        float w = __fadd_rn(__fsub_rn(b.z, b.x), 1.0f), h = __fadd_rn(__fsub_rn(b.w, b.y), 1.0f);
+        maxd = f2ord(fmaxf(fabsf(w), fabsf(h)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mincx = min(mincx, __shfl_xor_sync(0xffffffffu, mincx, o));
+        mincy = min(mincy, __shfl_xor_sync(0xffffffffu, mincy, o));
+        maxcx = max(maxcx, __shfl_xor_sync(0xffffffffu, maxcx, o));
+        maxcy = max(maxcy, __shfl_xor_sync(0xffffffffu, maxcy, o));
+        maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&gs[0], mincx);
+        atomicMin(&gs[1], mincy);
+        atomicMax(&gs[2], maxcx);
+        atomicMax(&gs[3], maxcy);
+        atomicMax(&gs[4], maxd);
+    }
+}
+
+__global__ void grid_setup_kernel(const unsigned *gs, int N, IouParams P, GridCfg *cfg, int *st) {
+    GridCfg c;
+    c.minx = ord2f(gs[0]);
+    c.miny = ord2f(gs[1]);
+    const float maxx = ord2f(gs[2]), maxy = ord2f(gs[3]), maxd = ord2f(gs[4]);
+    c.use = 0;
+    c.gx = c.gy = 1;
+    c.cs = 1.0f;
+    if (P.fast && st[2] == 0 && isfinite(maxd) && isfinite(maxx) && isfinite(maxy) && isfinite(c.minx) && isfinite(c.miny)) {
+        const float t = fminf(fmaxf(P.thr, 0.0f), 1.0f);
+        // centre-distance bound per axis, with a 1% + 0.05 px margin for the separately rounded f32 operations
+        double cs = (double)maxd * (1.0 - (double)t) * 1.01 + 0.05;
+        const double ex = (double)maxx - (double)c.minx, ey = (double)maxy - (double)c.miny;
+        for (int it = 0; it < 64; ++it) {
+            double gx = floor(ex / cs) + 1.0, gy = floor(ey / cs) + 1.0;
+            if (gx <= GRID_MAX_DIM && gy <= GRID_MAX_DIM && gx * gy <= GRID_MAX_CELLS) {
+                c.gx = (int)gx;
+                c.gy = (int)gy;
+                c.cs = (float)cs;
+                // fine enough: on average at most ~2k candidates in a box's 3x3 neighbourhood
+                c.use = (9.0 * (double)N / (gx * gy) <= 2048.0) ? 1 : 0;
+                break;
+            }
+            cs *= 1.5;
+        }
+    }
+    *cfg = c;
+    st[3] = c.use;
+}
+
+__global__ void cell_keys_kernel(const float4 *__restrict__ sbox, int N, const GridCfg *cfg, u64 *__restrict__ keys) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    const GridCfg c = *cfg;
+    if (!c.use) { keys[r] = (u64)(unsigned)r; return; }
+    float4 b = sbox[r];
+    int ix = cell_coord(box_cx(b), c.minx, c.cs, c.gx), iy = cell_coord(box_cy(b), c.miny, c.cs, c.gy);
+    keys[r] = ((u64)(unsigned)(iy * c.gx + ix) << 32) | (unsigned)r;
+}
+
+// keys sorted by (cell, rank).  cell_start/cell_end zeroed beforehand.
+__global__ void cell_bounds_kernel(const u64 *__restrict__ keys, int N, const GridCfg *cfg, const float4 *__restrict__ sbox,
+                                   int *__restrict__ cell_start, int *__restrict__ cell_end, float4 *__restrict__ cbox,
+                                   float *__restrict__ carea, int *__restrict__ pos_of_rank) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N || !cfg->use) return;
+    const u64 key = keys[k];
+    const int cell = (int)(key >> 32), rank = (int)(unsigned)key;
+    if (k == 0 || (int)(keys[k - 1] >> 32) != cell) cell_start[cell] = k;
+    if (k == N - 1 || (int)(keys[k + 1] >> 32) != cell) cell_end[cell] = k + 1;
+    const float4 b = sbox[rank];
+    cbox[k] = b;
+    carea[k] = box_area(b);
+    pos_of_rank[rank] = k;
+}
+
+// visits the earlier-ranked members of the 3x3 neighbourhood of cell-ordered box k that suppress it
+template <class F>
+__device__ __forceinline__ void for_each_predecessor(int k, const u64 *__restrict__ keys, const GridCfg &c,
+                                                     const int *__restrict__ cell_start, const int *__restrict__ cell_end,
+                                                     const float4 *__restrict__ cbox, const float *__restrict__ carea,
+                                                     const IouParams &P, F &&visit) {
+    const u64 key = keys[k];
+    const int cell = (int)(key >> 32), rank = (int)(unsigned)key;
+    const int iy = cell / c.gx, ix = cell - iy * c.gx;
+    const float4 bi = cbox[k];
+    const float ai = carea[k];
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int y = iy + dy;
+        if (y < 0 || y >= c.gy) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int x = ix + dx;
+            if (x < 0 || x >= c.gx) continue;
+            const int c2 = y * c.gx + x;
+            const int e = cell_end[c2];
+            for (int j = cell_start[c2]; j < e; ++j) {
+                const int rj = (int)(unsigned)keys[j];
+                if (rj >= rank) break;  // members are in rank order
+                if (iou_suppresses_exact(cbox[j], carea[j], bi, ai, P))
+                    if (!visit(rj)) return;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) adjacency_kernel(const u64 *__restrict__ keys, int N, const GridCfg *cfg,
+                                                        const int *__restrict__ cell_start, const int *__restrict__ cell_end,
+                                                        const float4 *__restrict__ cbox, const float *__restrict__ carea, IouParams P,
+                                                        int *__restrict__ adj, int *__restrict__ adj_cnt) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    const GridCfg c = *cfg;
+    if (!c.use) return;
+    const int rank = (int)(unsigned)keys[k];
+    int cnt = 0;
+    int *mine = adj + (size_t)rank * ADJ_CAP;
+    for_each_predecessor(k, keys, c, cell_start, cell_end, cbox, carea, P, [&](int rj) {
+        if (cnt < ADJ_CAP) mine[cnt] = rj;
+        ++cnt;
+        return true;
+    });
+    adj_cnt[rank] = cnt <= ADJ_CAP ? cnt : -1;  // -1: too many predecessors to list, rescan the neighbourhood instead
+}
+
+struct RoundsArgs {
+    int N;
+    const u64 *keys;
+    const GridCfg *cfg;
+    const int *cell_start, *cell_end;
+    const float4 *cbox;
+    const float *carea;
+    const int *pos_of_rank;
+    const int *adj, *adj_cnt;
+    unsigned char *state;   // by rank: 0 undecided, 1 kept, 2 suppressed (zeroed)
+    int *counters;          // [3] rotating undecided counters (zeroed)
+    int *tile_counts;
+    unsigned *ballots;
+    int *keep_ranks;
+    int *out_state;         // [1] = total kept
+    IouParams iou;
+};
+
+__global__ void __launch_bounds__(NT, 1) nms_rounds_kernel(RoundsArgs a) {
+    __shared__ int red[32];
+    const GridCfg c = *a.cfg;
+    if (!c.use) return;  // uniform over the grid: the peel kernel handles this problem
+    cg::grid_group grid = cg::this_grid();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = gridDim.x;
+    const int gtid = blockIdx.x * NT + tid, gstride = G * NT;
+    volatile unsigned char *state = a.state;
+    for (int epoch = 0;; ++epoch) {
+        int undecided = 0;
+        for (int sweep = 0; sweep < 4; ++sweep) {
+            undecided = 0;
+            for (int r = gtid; r < a.N; r += gstride) {
+                if (state[r] != 0) continue;
+                bool any_kept = false, all_sup = true;
+                const int cnt = a.adj_cnt[r];
+                if (cnt >= 0) {
+                    const int *mine = a.adj + (size_t)r * ADJ_CAP;
+                    for (int e = 0; e < cnt; ++e) {
+                        const unsigned char sj = state[mine[e]];
+                        if (sj == 1) { any_kept = true; break; }
+                        if (sj == 0) all_sup = false;
+                    }
+                } else {
+                    for_each_predecessor(a.pos_of_rank[r], a.keys, c, a.cell_start, a.cell_end, a.cbox, a.carea, a.iou, [&](int rj) {
+                        const unsigned char sj = state[rj];
+                        if (sj == 1) { any_kept = true; return false; }
+                        if (sj == 0) all_sup = false;
+                        return true;
+                    });
+                }
+                if (any_kept) state[r] = 2;
+                else if (all_sup) state[r] = 1;
+                else ++undecided;
+            }
+        }
+        int tot = block_sum(undecided, red);
+        if (tid == 0 && tot) atomicAdd(&a.counters[epoch % 3], tot);
+        __threadfence();
+        grid.sync();
+        const int left = __ldcg(&a.counters[epoch % 3]);
+        if (gtid == 0) a.counters[(epoch + 2) % 3] = 0;
+        if (left == 0) break;
+    }
+    // ordered output of the kept ranks
+    const int ntiles = (a.N + NT - 1) / NT;
+    for (int t = blockIdx.x; t < ntiles; t += G) {
+        const int r = t * NT + tid;
+        const bool flag = r < a.N && state[r] == 1;
+        unsigned bal = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) a.ballots[t * 32 + warp] = bal;
+        int cnt = __syncthreads_count(flag);
+        if (tid == 0) a.tile_counts[t] = cnt;
+    }
+    __threadfence();
+    grid.sync();
+    for (int t = blockIdx.x; t < ntiles; t += G) {
+        int part = 0;
+        for (int q = tid; q < t; q += NT) part += __ldcg(&a.tile_counts[q]);
+        const int offset = block_sum(part, red);
+        const unsigned myb = __ldcg(&a.ballots[t * 32 + lane]);
+        int wpre = 0;
+#pragma unroll
+        for (int w = 0; w < 32; ++w) {
+            const unsigned bw = __shfl_sync(0xffffffffu, myb, w);
+            if (w < warp) wpre += __popc(bw);
+        }
+        const unsigned mine = __shfl_sync(0xffffffffu, myb, warp);
+        if ((mine >> lane) & 1u) a.keep_ranks[offset + wpre + __popc(mine & ((1u << lane) - 1u))] = t * NT + tid;
+    }
+    if (blockIdx.x == 0) {
+        int part = 0;
+        for (int q = tid; q < ntiles; q += NT) part += __ldcg(&a.tile_counts[q]);
+        const int total = block_sum(part, red);
+        if (tid == 0) a.out_state[1] = total;
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------
 // Decision boundary of the exact division-free test (see iou_suppresses_exact).
 IouParams make_iou_params(float thr, int mode) {
@@ -732,7 +999,7 @@ static int nms_big_impl(fd_ctx *ctx, const u64 *keys_in, const int *key_bytes, i
     FD_TRY(ctx->nms_ws[3].reserve(sizeof(float4) * (size_t)K));           // sorted boxes
     FD_TRY(ctx->nms_ws[4].reserve(sizeof(int) * (size_t)K * 3));          // stream a, stream b, keep ranks
     FD_TRY(ctx->nms_ws[5].reserve(sizeof(float4) * HEAD + sizeof(int) * (size_t)ntiles_peel * 33 + 64));
-    FD_TRY(ctx->nms_ws[6].reserve(sizeof(int) * 8));                      // status/state
+    FD_TRY(ctx->nms_ws[6].reserve(sizeof(int) * 32));                     // status/state + grid stats + counters + cfg
     u64 *ka = ctx->nms_ws[0].as<u64>(), *kb = ctx->nms_ws[1].as<u64>();
     int *hist = ctx->nms_ws[2].as<int>();
     float4 *sbox = ctx->nms_ws[3].as<float4>();
@@ -740,8 +1007,10 @@ static int nms_big_impl(fd_ctx *ctx, const u64 *keys_in, const int *key_bytes, i
     float4 *ks = ctx->nms_ws[5].as<float4>();
     int *tile_counts = reinterpret_cast<int *>(ks + HEAD);
     unsigned *ballots = reinterpret_cast<unsigned *>(tile_counts + ntiles_peel);
-    int *st = ctx->nms_ws[6].as<int>();  // [0] nan, [1] kept total, [2] not-fast flag, [4..6] peel state
-    FD_CUDA(cudaMemsetAsync(st, 0, sizeof(int) * 8, ctx->stream));
+    int *st = ctx->nms_ws[6].as<int>();  // [0] nan, [2] not-fast flag, [3] spatial path active, [4] kept total, [5] stage kept,
+                                         // [8..12] grid stats, [13..15] round counters, [16..21] GridCfg
+    FD_CUDA(cudaMemsetAsync(st, 0, sizeof(int) * 32, ctx->stream));
+    FD_CUDA(cudaMemsetAsync(st + 8, 0xFF, sizeof(int) * 2, ctx->stream));   // min cx / min cy
     const int tb = 256, gb = (K + tb - 1) / tb;
     u64 *sorted = ka;
     if (presorted) {
@@ -763,6 +1032,64 @@ static int nms_big_impl(fd_ctx *ctx, const u64 *keys_in, const int *key_bytes, i
     }
     gather_sorted_boxes_kernel<<<gb, tb, 0, ctx->stream>>>(sorted, K, boxes, stride, sbox, st);
     FD_LAUNCH_CHECK(ctx);
+    const IouParams iou = make_iou_params(thr, mode);
+    // ---- spatial path (decides on the device whether it applies; the peel kernel below is its complement) ----
+    {
+        FD_TRY(ctx->nms_ws_sp[0].reserve(sizeof(u64) * (size_t)K * 2));                        // cell keys a/b
+        FD_TRY(ctx->nms_ws_sp[1].reserve(sizeof(int) * (size_t)(GRID_MAX_CELLS + 1) * 2));     // cell start / end
+        FD_TRY(ctx->nms_ws_sp[2].reserve((sizeof(float4) + sizeof(float) + sizeof(int) * 2) * (size_t)K + (size_t)K)); // cbox, carea, pos, cnt, state
+        FD_TRY(ctx->nms_ws_sp[3].reserve(sizeof(int) * (size_t)K * ADJ_CAP));                  // predecessor lists
+        u64 *cka = ctx->nms_ws_sp[0].as<u64>(), *ckb = cka + K;
+        int *cell_start = ctx->nms_ws_sp[1].as<int>(), *cell_end = cell_start + (GRID_MAX_CELLS + 1);
+        float4 *cbox = ctx->nms_ws_sp[2].as<float4>();
+        float *carea = reinterpret_cast<float *>(cbox + K);
+        int *pos_of_rank = reinterpret_cast<int *>(carea + K);
+        int *adj_cnt = pos_of_rank + K;
+        unsigned char *state = reinterpret_cast<unsigned char *>(adj_cnt + K);
+        int *adj = ctx->nms_ws_sp[3].as<int>();
+        unsigned *gs = reinterpret_cast<unsigned *>(st + 8);
+        GridCfg *cfg = reinterpret_cast<GridCfg *>(st + 16);
+        grid_stats_kernel<<<gb, tb, 0, ctx->stream>>>(sbox, K, gs);
+        FD_LAUNCH_CHECK(ctx);
+        grid_setup_kernel<<<1, 1, 0, ctx->stream>>>(gs, K, iou, cfg, st);
+        FD_LAUNCH_CHECK(ctx);
+        cell_keys_kernel<<<gb, tb, 0, ctx->stream>>>(sbox, K, cfg, cka);
+        FD_LAUNCH_CHECK(ctx);
+        static const int cell_bytes[2] = {4, 5};
+        u64 *csorted = cka;
+        FD_TRY(radix_sort_u64(ctx, cka, ckb, K, cell_bytes, 2, hist, &csorted));
+        FD_CUDA(cudaMemsetAsync(cell_start, 0, sizeof(int) * (size_t)(GRID_MAX_CELLS + 1) * 2, ctx->stream));
+        FD_CUDA(cudaMemsetAsync(state, 0, (size_t)K, ctx->stream));
+        cell_bounds_kernel<<<gb, tb, 0, ctx->stream>>>(csorted, K, cfg, sbox, cell_start, cell_end, cbox, carea, pos_of_rank);
+        FD_LAUNCH_CHECK(ctx);
+        adjacency_kernel<<<gb, 256, 0, ctx->stream>>>(csorted, K, cfg, cell_start, cell_end, cbox, carea, iou, adj, adj_cnt);
+        FD_LAUNCH_CHECK(ctx);
+        RoundsArgs ra;
+        ra.N = K;
+        ra.keys = csorted;
+        ra.cfg = cfg;
+        ra.cell_start = cell_start;
+        ra.cell_end = cell_end;
+        ra.cbox = cbox;
+        ra.carea = carea;
+        ra.pos_of_rank = pos_of_rank;
+        ra.adj = adj;
+        ra.adj_cnt = adj_cnt;
+        ra.state = state;
+        ra.counters = st + 13;
+        ra.tile_counts = tile_counts;
+        ra.ballots = ballots;
+        ra.keep_ranks = keep_ranks;
+        ra.out_state = st + 3;
+        ra.iou = iou;
+        void *rargs[] = {&ra};
+        int per_sm_r = 0;
+        FD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_r, nms_rounds_kernel, NT, 0));
+        if (per_sm_r < 1) return fail(FD_ERR_CUDA, "nms_rounds_kernel does not fit on an SM");
+        int grid_r = std::min(ctx->num_sms * per_sm_r, std::max(1, ntiles_peel));
+        FD_CUDA(cudaLaunchCooperativeKernel((const void *)nms_rounds_kernel, dim3(grid_r), dim3(NT), rargs, 0, ctx->stream));
+        FD_LAUNCH_CHECK(ctx);
+    }
     PeelArgs pa;
     pa.sbox = sbox;
     pa.N = K;
@@ -774,7 +1101,7 @@ static int nms_big_impl(fd_ctx *ctx, const u64 *keys_in, const int *key_bytes, i
     pa.tile_counts = tile_counts;
     pa.ballots = ballots;
     pa.status = st;
-    pa.iou = make_iou_params(thr, mode);
+    pa.iou = iou;
     const size_t smem = sizeof(PeelSmem);
     void *kargs[] = {&pa};
     const void *fn = mode == 0 ? (const void *)nms_peel_kernel<0> : (const void *)nms_peel_kernel<1>;
