@@ -106,6 +106,9 @@ int fd_generate_anchors_fpn2(int dense_anchor, const fd_anchor_cfg *cfg, int n_c
 /* processing::nms::nms(&Array2<f32>, f32) -> Vec<usize>  (nms.rs:3-65).  dets (K,5) any order; keep (cap>=K)
  * receives indices into dets in pick order (stable descending-score sort done on the device). */
 int fd_nms(fd_ctx *ctx, const float *dets, int K, float thresh, int32_t *keep, int *num_keep);
+/* Diagnostics of the last NMS with K > 4096 on this ctx (blocks): out[8] = {spatial path used, kept, decision
+ * epochs, grid width, grid height, cell size (f32 bits), 0, 0}. */
+int fd_nms_last_stats(fd_ctx *ctx, int32_t *out);
 /* rcnn::cpu_nms::cpu_nms variant (cpu_nms.rs:10-55): suppresses on ovr >= thresh. */
 int fd_cpu_nms(fd_ctx *ctx, const float *dets, int K, float thresh, int32_t *keep, int *num_keep);
 /* Contract of the reference's C symbol `_nms` (gpu_nms.hpp:6-8, nms_kernel.cu:91-144): boxes (n, boxes_dim>=4)

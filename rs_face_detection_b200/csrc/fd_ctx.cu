@@ -1,6 +1,8 @@
 // fd_ctx.cu — context, error plumbing, memory helpers, config defaults and the init-time anchor tables.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include "fd_internal.cuh"
@@ -48,6 +50,25 @@ void PinnedBuf::release() {
     if (p) cudaFreeHost(p);
     p = nullptr;
     cap = 0;
+}
+
+void trace_mark(fd_ctx *ctx, const char *file, int line) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, ctx->stream);
+    const char *base = strrchr(file, '/');
+    ctx->trace.emplace_back(std::string(base ? base + 1 : file) + ":" + std::to_string(line), e);
+}
+static void trace_dump(fd_ctx *ctx) {
+    if (ctx->trace.size() < 2) return;
+    fprintf(stderr, "[fd trace] %zu marks\n", ctx->trace.size());
+    for (size_t i = 1; i < ctx->trace.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->trace[i - 1].second, ctx->trace[i].second);
+        fprintf(stderr, "[fd trace] %-28s +%8.1f us\n", ctx->trace[i].first.c_str(), ms * 1e3f);
+    }
+    for (auto &t : ctx->trace) cudaEventDestroy(t.second);
+    ctx->trace.clear();
 }
 
 int check_ctx(const fd_ctx *ctx) {
@@ -217,6 +238,7 @@ FD_EXPORT int fd_ctx_create(int device_id, const fd_config *cfg, fd_ctx **out) {
     fd_ctx *ctx = new fd_ctx();
     ctx->device = device_id;
     ctx->cfg = c;
+    ctx->trace_on = getenv("FD_TRACE") != nullptr && getenv("FD_TRACE")[0] == '1';
     cudaDeviceProp prop;
     FD_CUDA(cudaGetDeviceProperties(&prop, device_id));
     ctx->num_sms = prop.multiProcessorCount;
@@ -285,6 +307,7 @@ FD_EXPORT int fd_ctx_synchronize(fd_ctx *ctx) {
     FD_TRY(check_ctx(ctx));
     FD_CUDA(cudaStreamSynchronize(ctx->stream));
     FD_CUDA(cudaStreamSynchronize(ctx->stream2));
+    if (ctx->trace_on) trace_dump(ctx);
     return FD_OK;
 }
 FD_EXPORT int fd_ctx_launch_count(const fd_ctx *ctx, int64_t *out) {

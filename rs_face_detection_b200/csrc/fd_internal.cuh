@@ -77,6 +77,8 @@ struct fd_ctx {
     int num_sms = 0;
     int max_smem_optin = 0;
     int64_t launches = 0;
+    bool trace_on = false;       // FD_TRACE=1: an event after every launch, dumped by fd_ctx_synchronize
+    std::vector<std::pair<std::string, cudaEvent_t>> trace;
     fd::DecodeCfg dcfg{};
 
     // generic scratch for the host-pointer drop-in ops
@@ -124,10 +126,12 @@ namespace fd {
 
 int check_ctx(const fd_ctx *ctx);
 
-#define FD_LAUNCH_CHECK(ctx)                          \
-    do {                                              \
-        (ctx)->launches++;                            \
-        FD_CUDA(cudaGetLastError());                  \
+void trace_mark(fd_ctx *ctx, const char *file, int line);
+#define FD_LAUNCH_CHECK(ctx)                                          \
+    do {                                                              \
+        (ctx)->launches++;                                            \
+        FD_CUDA(cudaGetLastError());                                  \
+        if ((ctx)->trace_on) ::fd::trace_mark((ctx), __FILE__, __LINE__); \
     } while (0)
 
 // ---- device helpers ---------------------------------------------------------------------------------
@@ -201,6 +205,7 @@ int nms_batch_big_image(fd_ctx *ctx, int b, int K, float iou_thr);
 int finalize_launch(fd_ctx *ctx, int B);
 int nms_device(fd_ctx *ctx, const float *dets_dev, int K, int stride_floats, float thr, int mode, bool presorted,
                int32_t *keep_dev, int32_t *num_keep_dev);
+int nms_last_stats(fd_ctx *ctx, int32_t out[8]);
 int argsort_device(fd_ctx *ctx, const float *scores_as_dets, int n, int stride, int32_t *order_dev, int32_t *flag_dev);
 int estimate_launch(fd_ctx *ctx, const float *from_dev, const float *to_dev, const int *count_dev, int F_cap,
                     double *M12_dev, double *M_out_dev, uint8_t *ok_dev, uint8_t *ok_out_dev);

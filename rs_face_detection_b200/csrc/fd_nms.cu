@@ -437,14 +437,40 @@ __global__ void __launch_bounds__(1024) scan_kernel(int *__restrict__ data, int 
     }
 }
 
-// stable scatter: element order inside a tile is (warp, round, lane)
-__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out,
-                                                                   int n, int shift, const int *__restrict__ hist, int ntiles) {
+// One kernel per radix pass.  hist_cur[d*ntiles + t] = number of keys with digit d in tile t (for this pass's digit and
+// the CURRENT key order).  Every CTA derives its own scatter bases from it (no separate scan launch): for digit d,
+// base = sum over smaller digits of their totals + sum over earlier tiles of digit d.  While scattering, the kernel
+// accumulates the NEXT pass's per-tile histogram (the destination tile of every key is known here), so only the first
+// pass needs a histogram launch.  Stable: element order inside a tile is (warp, round, lane).
+__global__ void __launch_bounds__(RS_THREADS) radix_pass_kernel(const u64 *__restrict__ keys_in, u64 *__restrict__ keys_out, int n,
+                                                                int shift, const int *__restrict__ hist_cur, int *__restrict__ hist_next,
+                                                                int next_shift, int ntiles) {
     __shared__ int wcount[RS_THREADS / 32][256];
     __shared__ int gofs[256];
+    __shared__ int wsum[RS_THREADS / 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < (RS_THREADS / 32) * 256; i += RS_THREADS) (&wcount[0][0])[i] = 0;
-    gofs[threadIdx.x] = hist[threadIdx.x * ntiles + blockIdx.x];
+    {   // scatter base of digit d = threadIdx.x for this tile
+        const int d = threadIdx.x;
+        const int *row = hist_cur + (size_t)d * ntiles;
+        int before = 0, total = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            const int v = __ldcg(row + t);
+            total += v;
+            if (t < (int)blockIdx.x) before += v;
+        }
+        int incl = total;  // exclusive scan of the digit totals over the 256 threads
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += wsum[w];
+        gofs[d] = wbase + incl - total + before;
+    }
     __syncthreads();
     const int wbase = blockIdx.x * RS_TILE + warp * (32 * RS_ITEMS);
     u64 key[RS_ITEMS];
@@ -478,7 +504,18 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u64 *__
         int e = wbase + r * 32 + lane;
         if (e < n) {
             int d = (int)((key[r] >> shift) & 0xffull);
-            keys_out[gofs[d] + wcount[warp][d] + rank[r]] = key[r];
+            const int pos = gofs[d] + wcount[warp][d] + rank[r];
+            keys_out[pos] = key[r];
+        }
+        if (hist_next) {  // warp-aggregated: skewed digits (e.g. the exponent byte of scores in [0,1)) would serialise
+            int slot = -1;
+            if (e < n) {
+                int d = (int)((key[r] >> shift) & 0xffull);
+                const int pos = gofs[d] + wcount[warp][d] + rank[r];
+                slot = (int)((key[r] >> next_shift) & 0xffull) * ntiles + pos / RS_TILE;
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, slot);
+            if (slot >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(&hist_next[slot], __popc(peers));
         }
     }
 }
@@ -672,7 +709,8 @@ __global__ void __launch_bounds__(NT, 1) nms_peel_kernel(PeelArgs a) {
 // Same result as the sequential sweep of nms.rs; used when every box is regular (finite, positive area), the
 // threshold is an ordinary one and the grid is fine enough — otherwise the peel kernel above does the job.
 // ============================================================================================================
-constexpr int ADJ_CAP = 32;
+constexpr int ADJ_CAP = 96;      // listed predecessors per box (global memory)
+constexpr int ADJ_SMEM = 32;     // of which the first are cached in shared memory across sweeps
 constexpr int GRID_MAX_CELLS = 65535;
 constexpr int GRID_MAX_DIM = 4096;
 
@@ -716,7 +754,18 @@ __global__ void grid_stats_kernel(const float4 *__restrict__ sbox, int N, unsign
         maxcy = max(maxcy, __shfl_xor_sync(0xffffffffu, maxcy, o));
         maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
     }
+    __shared__ unsigned red[5][8];
+    const int w = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) {
+        red[0][w] = mincx; red[1][w] = mincy; red[2][w] = maxcx; red[3][w] = maxcy; red[4][w] = maxd;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = blockDim.x >> 5;
+        for (int k = 1; k < nw; ++k) {
+            mincx = min(mincx, red[0][k]); mincy = min(mincy, red[1][k]);
+            maxcx = max(maxcx, red[2][k]); maxcy = max(maxcy, red[3][k]); maxd = max(maxd, red[4][k]);
+        }
         atomicMin(&gs[0], mincx);
         atomicMin(&gs[1], mincy);
         atomicMax(&gs[2], maxcx);
@@ -800,9 +849,28 @@ __device__ __forceinline__ void for_each_predecessor(int k, const u64 *__restric
             if (x < 0 || x >= c.gx) continue;
             const int c2 = y * c.gx + x;
             const int e = cell_end[c2];
-            for (int j = cell_start[c2]; j < e; ++j) {
+            int j = cell_start[c2];
+            // members are in rank order: 4 candidates per step so their loads are in flight together
+            for (; j + 3 < e; j += 4) {
+                int rj[4];
+                float4 bj[4];
+                float aj[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    rj[u] = (int)(unsigned)keys[j + u];
+                    bj[u] = cbox[j + u];
+                    aj[u] = carea[j + u];
+                }
+                if (rj[0] >= rank) break;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (rj[u] < rank && iou_suppresses_exact(bj[u], aj[u], bi, ai, P))
+                        if (!visit(rj[u])) return;
+                if (rj[3] >= rank) { j = e; break; }
+            }
+            for (; j < e; ++j) {
                 const int rj = (int)(unsigned)keys[j];
-                if (rj >= rank) break;  // members are in rank order
+                if (rj >= rank) break;
                 if (iou_suppresses_exact(cbox[j], carea[j], bi, ai, P))
                     if (!visit(rj)) return;
             }
@@ -829,6 +897,13 @@ __global__ void __launch_bounds__(256) adjacency_kernel(const u64 *__restrict__ 
     adj_cnt[rank] = cnt <= ADJ_CAP ? cnt : -1;  // -1: too many predecessors to list, rescan the neighbourhood instead
 }
 
+// L2 (cache-global) byte load the compiler may neither cache nor drop: other CTAs update the states concurrently
+__device__ __forceinline__ unsigned ld_state(const unsigned char *p) {
+    unsigned v;
+    asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 struct RoundsArgs {
     int N;
     const u64 *keys;
@@ -847,7 +922,27 @@ struct RoundsArgs {
     IouParams iou;
 };
 
+constexpr int ROUND_SWEEPS = 8;
+
+// decides box r if possible; idx(e) yields its e-th listed predecessor
+template <class IdxFn>
+__device__ __forceinline__ int try_decide_listed(int cnt, IdxFn idx, const unsigned char *state) {
+    bool any_kept = false, all_sup = true;
+    for (int e = 0; e < cnt; e += 8) {
+        unsigned sj[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sj[u] = (e + u < cnt) ? ld_state(state + idx(e + u)) : 2u;  // loads in flight together
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            any_kept |= (sj[u] == 1u);
+            all_sup &= (sj[u] == 2u);
+        }
+    }
+    return any_kept ? 2 : (all_sup ? 1 : 0);
+}
+
 __global__ void __launch_bounds__(NT, 1) nms_rounds_kernel(RoundsArgs a) {
+    extern __shared__ int sadj[];  // [ADJ_SMEM][NT]: head of the predecessor list of each thread's first box, kept across sweeps
     __shared__ int red[32];
     const GridCfg c = *a.cfg;
     if (!c.use) return;  // uniform over the grid: the peel kernel handles this problem
@@ -856,40 +951,73 @@ __global__ void __launch_bounds__(NT, 1) nms_rounds_kernel(RoundsArgs a) {
     const int G = gridDim.x;
     const int gtid = blockIdx.x * NT + tid, gstride = G * NT;
     volatile unsigned char *state = a.state;
+    int cnt0 = 0;
+    if (gtid < a.N) {
+        cnt0 = a.adj_cnt[gtid];
+        const int4 *mine4 = reinterpret_cast<const int4 *>(a.adj + (size_t)gtid * ADJ_CAP);
+        for (int e = 0; e < min(cnt0, ADJ_SMEM); e += 4) {
+            const int4 p = __ldg(mine4 + (e >> 2));
+            sadj[(e + 0) * NT + tid] = p.x;
+            sadj[(e + 1) * NT + tid] = p.y;
+            sadj[(e + 2) * NT + tid] = p.z;
+            sadj[(e + 3) * NT + tid] = p.w;
+        }
+    }
+    bool first_done = gtid >= a.N;
     for (int epoch = 0;; ++epoch) {
         int undecided = 0;
-        for (int sweep = 0; sweep < 4; ++sweep) {
+        for (int sweep = 0; sweep < ROUND_SWEEPS; ++sweep) {
             undecided = 0;
-            for (int r = gtid; r < a.N; r += gstride) {
-                if (state[r] != 0) continue;
-                bool any_kept = false, all_sup = true;
-                const int cnt = a.adj_cnt[r];
-                if (cnt >= 0) {
-                    const int *mine = a.adj + (size_t)r * ADJ_CAP;
-                    for (int e = 0; e < cnt; ++e) {
-                        const unsigned char sj = state[mine[e]];
-                        if (sj == 1) { any_kept = true; break; }
-                        if (sj == 0) all_sup = false;
-                    }
-                } else {
-                    for_each_predecessor(a.pos_of_rank[r], a.keys, c, a.cell_start, a.cell_end, a.cbox, a.carea, a.iou, [&](int rj) {
-                        const unsigned char sj = state[rj];
-                        if (sj == 1) { any_kept = true; return false; }
-                        if (sj == 0) all_sup = false;
+            if (!first_done) {
+                int d;
+                if (cnt0 >= 0) {
+                    const int *mine = a.adj + (size_t)gtid * ADJ_CAP;
+                    d = try_decide_listed(cnt0, [&](int e) { return e < ADJ_SMEM ? sadj[e * NT + tid] : __ldg(mine + e); }, a.state);
+                }
+                else {
+                    bool any_kept = false, all_sup = true;
+                    for_each_predecessor(a.pos_of_rank[gtid], a.keys, c, a.cell_start, a.cell_end, a.cbox, a.carea, a.iou, [&](int rj) {
+                        const unsigned sj = ld_state(a.state + rj);
+                        if (sj == 1u) { any_kept = true; return false; }
+                        if (sj == 0u) all_sup = false;
                         return true;
                     });
+                    d = any_kept ? 2 : (all_sup ? 1 : 0);
                 }
-                if (any_kept) state[r] = 2;
-                else if (all_sup) state[r] = 1;
+                if (d) { state[gtid] = (unsigned char)d; first_done = true; }
                 else ++undecided;
             }
+            for (int r = gtid + gstride; r < a.N; r += gstride) {  // only when N exceeds the resident thread count
+                if (state[r] != 0) continue;
+                const int cnt = a.adj_cnt[r];
+                int d;
+                if (cnt >= 0) {
+                    const int *mine = a.adj + (size_t)r * ADJ_CAP;
+                    d = try_decide_listed(cnt, [&](int e) { return __ldg(mine + e); }, a.state);
+                } else {
+                    bool any_kept = false, all_sup = true;
+                    for_each_predecessor(a.pos_of_rank[r], a.keys, c, a.cell_start, a.cell_end, a.cbox, a.carea, a.iou, [&](int rj) {
+                        const unsigned sj = ld_state(a.state + rj);
+                        if (sj == 1u) { any_kept = true; return false; }
+                        if (sj == 0u) all_sup = false;
+                        return true;
+                    });
+                    d = any_kept ? 2 : (all_sup ? 1 : 0);
+                }
+                if (d) state[r] = (unsigned char)d;
+                else ++undecided;
+            }
+            if (__syncthreads_count(undecided) == 0) break;  // this CTA is finished
         }
         int tot = block_sum(undecided, red);
         if (tid == 0 && tot) atomicAdd(&a.counters[epoch % 3], tot);
         __threadfence();
         grid.sync();
         const int left = __ldcg(&a.counters[epoch % 3]);
-        if (gtid == 0) a.counters[(epoch + 2) % 3] = 0;
+        if (gtid == 0) {
+            a.counters[(epoch + 2) % 3] = 0;
+            a.out_state[3] = epoch + 1;  // statistics: grid-wide epochs used
+        }
         if (left == 0) break;
     }
     // ordered output of the kept ranks
@@ -955,16 +1083,19 @@ IouParams make_iou_params(float thr, int mode) {
     return p;
 }
 
+// hist: (nbytes + 1) x 256 x ntiles ints.
 static int radix_sort_u64(fd_ctx *ctx, u64 *keys, u64 *tmp, int n, const int *bytes, int nbytes, int *hist, u64 **sorted) {
     const int ntiles = (n + RS_TILE - 1) / RS_TILE;
+    const size_t hsz = (size_t)256 * ntiles;
+    FD_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * hsz * (size_t)nbytes, ctx->stream));
     u64 *in = keys, *out = tmp;
+    radix_hist_kernel<<<ntiles, RS_THREADS, 0, ctx->stream>>>(in, n, bytes[0] * 8, hist, ntiles);
+    FD_LAUNCH_CHECK(ctx);
     for (int p = 0; p < nbytes; ++p) {
-        int shift = bytes[p] * 8;
-        radix_hist_kernel<<<ntiles, RS_THREADS, 0, ctx->stream>>>(in, n, shift, hist, ntiles);
-        FD_LAUNCH_CHECK(ctx);
-        scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist, 256 * ntiles);
-        FD_LAUNCH_CHECK(ctx);
-        radix_scatter_kernel<<<ntiles, RS_THREADS, 0, ctx->stream>>>(in, out, n, shift, hist, ntiles);
+        int *hcur = hist + hsz * p;
+        int *hnext = p + 1 < nbytes ? hist + hsz * (p + 1) : nullptr;
+        radix_pass_kernel<<<ntiles, RS_THREADS, 0, ctx->stream>>>(in, out, n, bytes[p] * 8, hcur, hnext,
+                                                                 p + 1 < nbytes ? bytes[p + 1] * 8 : 0, ntiles);
         FD_LAUNCH_CHECK(ctx);
         std::swap(in, out);
     }
@@ -995,7 +1126,7 @@ static int nms_big_impl(fd_ctx *ctx, const u64 *keys_in, const int *key_bytes, i
     const int ntiles_peel = (K + NT - 1) / NT;
     FD_TRY(ctx->nms_ws[0].reserve(sizeof(u64) * (size_t)K));              // keys a
     FD_TRY(ctx->nms_ws[1].reserve(sizeof(u64) * (size_t)K));              // keys b
-    FD_TRY(ctx->nms_ws[2].reserve(sizeof(int) * (size_t)256 * ntiles_rs)); // hist
+    FD_TRY(ctx->nms_ws[2].reserve(sizeof(int) * (size_t)256 * ntiles_rs * 8)); // per-pass histograms
     FD_TRY(ctx->nms_ws[3].reserve(sizeof(float4) * (size_t)K));           // sorted boxes
     FD_TRY(ctx->nms_ws[4].reserve(sizeof(int) * (size_t)K * 3));          // stream a, stream b, keep ranks
     FD_TRY(ctx->nms_ws[5].reserve(sizeof(float4) * HEAD + sizeof(int) * (size_t)ntiles_peel * 33 + 64));
@@ -1084,10 +1215,12 @@ static int nms_big_impl(fd_ctx *ctx, const u64 *keys_in, const int *key_bytes, i
         ra.iou = iou;
         void *rargs[] = {&ra};
         int per_sm_r = 0;
-        FD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_r, nms_rounds_kernel, NT, 0));
+        const size_t smem_r = sizeof(int) * (size_t)ADJ_SMEM * NT;
+        FD_CUDA(cudaFuncSetAttribute(nms_rounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+        FD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_r, nms_rounds_kernel, NT, smem_r));
         if (per_sm_r < 1) return fail(FD_ERR_CUDA, "nms_rounds_kernel does not fit on an SM");
         int grid_r = std::min(ctx->num_sms * per_sm_r, std::max(1, ntiles_peel));
-        FD_CUDA(cudaLaunchCooperativeKernel((const void *)nms_rounds_kernel, dim3(grid_r), dim3(NT), rargs, 0, ctx->stream));
+        FD_CUDA(cudaLaunchCooperativeKernel((const void *)nms_rounds_kernel, dim3(grid_r), dim3(NT), rargs, smem_r, ctx->stream));
         FD_LAUNCH_CHECK(ctx);
     }
     PeelArgs pa;
@@ -1122,6 +1255,18 @@ int nms_big_device(fd_ctx *ctx, const float *dets_dev, int K, int stride, float 
                    int32_t *keep_dev, int32_t *num_keep_dev) {
     static const int bytes[4] = {4, 5, 6, 7};  // score bytes only: the sort is stable, ties keep index order
     return nms_big_impl(ctx, nullptr, bytes, 4, dets_dev, K, stride, thr, mode, presorted, false, keep_dev, num_keep_dev);
+}
+
+// Statistics of the last big-path NMS: [0] spatial path used, [1] kept, [2] decision epochs, [3] grid w, [4] grid h,
+// [5] cell size (float bits)
+int nms_last_stats(fd_ctx *ctx, int32_t out[8]) {
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    if (!ctx->nms_ws[6].p) return FD_OK;
+    int st[32];
+    FD_CUDA(cudaMemcpyAsync(st, ctx->nms_ws[6].p, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    out[0] = st[3]; out[1] = st[4]; out[2] = st[6]; out[3] = st[19]; out[4] = st[20]; out[5] = st[18];
+    return FD_OK;
 }
 
 // Generic device NMS on a (K, stride) row-major array with the score in column 4 (ignored if presorted).

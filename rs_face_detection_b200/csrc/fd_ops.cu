@@ -167,6 +167,11 @@ FD_EXPORT int fd_nms_device(fd_ctx *ctx, const float *dets_dev, int K, float thr
     }
     return nms_device(ctx, dets_dev, K, 5, thresh, 0, false, keep_dev, num_keep_dev);
 }
+FD_EXPORT int fd_nms_last_stats(fd_ctx *ctx, int32_t *out) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(out, "fd_nms_last_stats: null");
+    return nms_last_stats(ctx, out);
+}
 FD_EXPORT int fd_cpu_nms(fd_ctx *ctx, const float *dets, int K, float thresh, int32_t *keep, int *num_keep) {
     return nms_host(ctx, dets, K, 5, thresh, 1, false, keep, num_keep);
 }

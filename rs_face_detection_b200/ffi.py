@@ -68,7 +68,7 @@ SYMBOLS = [
     "fd_dev_alloc", "fd_dev_free", "fd_host_alloc_pinned", "fd_host_free_pinned", "fd_memcpy_h2d", "fd_memcpy_d2h",
     "fd_memcpy_h2d_async", "fd_memcpy_d2h_async", "fd_memset_dev",
     "fd_generate_anchors", "fd_generate_anchors2", "fd_generate_anchors_fpn", "fd_generate_anchors_fpn2",
-    "fd_nms", "fd_cpu_nms", "fd_nms_sorted", "_nms", "_set_device", "fd_argsort_descending", "fd_anchors_plane",
+    "fd_nms", "fd_nms_last_stats", "fd_cpu_nms", "fd_nms_sorted", "_nms", "_set_device", "fd_argsort_descending", "fd_anchors_plane",
     "fd_bbox_pred", "fd_nonlinear_pred", "fd_landmark_pred", "fd_clip_boxes", "fd_clip_points", "fd_iou_pred",
     "fd_nonlinear_transform", "fd_bbox_overlaps", "fd_letterbox_geometry", "fd_preprocess", "fd_resize_linear",
     "fd_detect", "fd_estimate_affine_partial_2d", "fd_warp_affine", "fd_align",
@@ -268,6 +268,12 @@ class Context:
 
     def nms(self, dets, thresh):
         return self._nms(self.lib.fd_nms, dets, thresh)
+
+    def nms_last_stats(self):
+        out = np.zeros(8, np.int32)
+        _chk(self.lib.fd_nms_last_stats(self.handle, _ptr(out, c_i32p)))
+        return dict(spatial=int(out[0]), kept=int(out[1]), epochs=int(out[2]), grid=(int(out[3]), int(out[4])),
+                    cell=float(out[5:6].view(np.float32)[0]))
 
     def cpu_nms(self, dets, thresh):
         return self._nms(self.lib.fd_cpu_nms, dets, thresh)
