@@ -173,7 +173,7 @@ __global__ void invert_kernel(const double *M, int F, double *M12, uint8_t *ok) 
 }
 
 constexpr int WARP_BAND = 16;     // output rows per CTA
-constexpr int WARP_TX = 32, WARP_TY = 8;
+constexpr int WARP_TX = 128, WARP_TY = 2;
 constexpr int WARP_THREADS = WARP_TX * WARP_TY;
 
 struct WarpArgs {
@@ -187,22 +187,65 @@ struct WarpArgs {
     int cw, ch;
 };
 
-// The 6 bytes of two horizontally adjacent BGR pixels starting at p, through at most two aligned 64-bit loads (one
-// when the 6 bytes sit inside one 8-byte word) instead of six byte loads: the warp is L1-wavefront bound.
-__device__ __forceinline__ unsigned long long load6(const uint8_t *p, const uint8_t *lo_lim, const uint8_t *hi_lim) {
+// The 6 bytes of two horizontally adjacent BGR pixels starting at p, through two aligned 64-bit loads and 32-bit
+// funnel shifts (lo = bytes 0..3, hi = bytes 4..5 in its low half) instead of six byte loads.  Caller guarantees
+// that [p & ~7, (p & ~7) + 16) is readable.
+__device__ __forceinline__ void load6_fast(const uint8_t *p, unsigned &lo, unsigned &hi) {
+    const uintptr_t ad = reinterpret_cast<uintptr_t>(p);
+    const uint2 *al = reinterpret_cast<const uint2 *>(ad & ~(uintptr_t)7);
+    const uint2 q0 = __ldg(al), q1 = __ldg(al + 1);
+    const unsigned sh = (unsigned)(ad & 7);
+    const bool up = sh >= 4;
+    const unsigned a = up ? q0.y : q0.x, b = up ? q1.x : q0.y, c = up ? q1.y : q1.x;
+    const unsigned sft = (sh & 3) * 8;
+    lo = __funnelshift_r(a, b, sft);
+    hi = __funnelshift_r(b, c, sft);
+}
+// same, from an 8-byte aligned base and a 32-bit byte offset (interior path: one 64-bit add per load pair)
+__device__ __forceinline__ void load6_off(const uint8_t *base8, unsigned off, unsigned &lo, unsigned &hi) {
+    const uint2 *al = reinterpret_cast<const uint2 *>(base8 + (off & ~7u));
+    const uint2 q0 = __ldg(al), q1 = __ldg(al + 1);
+    const bool up = (off & 4u) != 0;
+    const unsigned a = up ? q0.y : q0.x, b = up ? q1.x : q0.y, c = up ? q1.y : q1.x;
+    const unsigned sft = (off & 3u) * 8;
+    lo = __funnelshift_r(a, b, sft);
+    hi = __funnelshift_r(b, c, sft);
+}
+__device__ __forceinline__ void extract6(uint2 q0, uint2 q1, unsigned off, unsigned &lo, unsigned &hi) {
+    const bool up = (off & 4u) != 0;
+    const unsigned a = up ? q0.y : q0.x, b = up ? q1.x : q0.y, c = up ? q1.y : q1.x;
+    const unsigned sft = (off & 3u) * 8;
+    lo = __funnelshift_r(a, b, sft);
+    hi = __funnelshift_r(b, c, sft);
+}
+// guarded variant for the frame's first/last bytes and for single-column border taps
+__device__ __forceinline__ void load6_safe(const uint8_t *p, const uint8_t *lo_lim, const uint8_t *hi_lim, unsigned &lo, unsigned &hi) {
     const uintptr_t ad = reinterpret_cast<uintptr_t>(p);
     const uint8_t *al = reinterpret_cast<const uint8_t *>(ad & ~(uintptr_t)7);
-    const int sh = (int)(ad & 7);
     if (al >= lo_lim && al + 16 <= hi_lim) {
-        unsigned long long lo = __ldg(reinterpret_cast<const unsigned long long *>(al));
-        if (sh <= 2) return lo >> (8 * sh);
-        unsigned long long hi = __ldg(reinterpret_cast<const unsigned long long *>(al + 8));
-        return (lo >> (8 * sh)) | (hi << (64 - 8 * sh));
+        load6_fast(p, lo, hi);
+        return;
     }
-    unsigned long long v = 0;  // first / last bytes of the frame buffer: plain byte loads
+    lo = hi = 0;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) v |= (unsigned long long)__ldg(p + k) << (8 * k);
-    return v;
+    for (int k = 0; k < 4; ++k) lo |= (unsigned)__ldg(p + k) << (8 * k);
+    hi = (unsigned)__ldg(p + 4) | ((unsigned)__ldg(p + 5) << 8);
+}
+
+// OpenCV: out = (sum_ij v_ij * W_ij + 2^14) >> 15 with W_ij = a_i * b_j * 32 (a = {32-ay, ay}, b = {32-ax, ax}; the
+// 15-bit table entries are exact multiples of 32).  Integer arithmetic is exact, so the sum is evaluated separably:
+// horizontal 2-tap dot products with 6-bit weights (dp4a on the packed byte pair), then the vertical pair; and
+// (32*S + 2^14) >> 15 == (S + 512) >> 10.
+__device__ __forceinline__ void blend_store(unsigned lo0, unsigned hi0, unsigned lo1, unsigned hi1, int ax, int ay, uint8_t *o) {
+    const unsigned wx = (unsigned)(32 - ax) | ((unsigned)ax << 8);   // bytes: [32-ax, ax, 0, 0]
+    const int wy0 = 32 - ay, wy1 = ay;
+    // byte pairs (tap0, tap1) per channel: b = bytes (0,3), g = (1,4), r = (2,5) of [lo | hi]
+    const int hb0 = (int)__dp4a(__byte_perm(lo0, hi0, 0x7730), wx, 0u), hb1 = (int)__dp4a(__byte_perm(lo1, hi1, 0x7730), wx, 0u);
+    const int hg0 = (int)__dp4a(__byte_perm(lo0, hi0, 0x7741), wx, 0u), hg1 = (int)__dp4a(__byte_perm(lo1, hi1, 0x7741), wx, 0u);
+    const int hr0 = (int)__dp4a(__byte_perm(lo0, hi0, 0x7752), wx, 0u), hr1 = (int)__dp4a(__byte_perm(lo1, hi1, 0x7752), wx, 0u);
+    o[0] = (uint8_t)((hb0 * wy0 + hb1 * wy1 + 512) >> 10);
+    o[1] = (uint8_t)((hg0 * wy0 + hg1 * wy1 + 512) >> 10);
+    o[2] = (uint8_t)((hr0 * wy0 + hr1 * wy1 + 512) >> 10);
 }
 
 __global__ void __launch_bounds__(WARP_THREADS) warp_kernel(WarpArgs a) {
@@ -215,7 +258,6 @@ __global__ void __launch_bounds__(WARP_THREADS) warp_kernel(WarpArgs a) {
     const int F = a.count_dev ? min(*a.count_dev, a.F) : a.F;
     const int band_y0 = blockIdx.x * WARP_BAND;
     const int rows = min(WARP_BAND, a.ch - band_y0);
-    const int ngroups = (a.cw + 3) >> 2;
     for (int f = blockIdx.y; f < F; f += gridDim.y) {
         uint8_t *crop = a.crops + (size_t)f * a.ch * a.cw * 3;
         if (!a.ok[f]) {
@@ -236,38 +278,78 @@ __global__ void __launch_bounds__(WARP_THREADS) warp_kernel(WarpArgs a) {
             Y0s[tid] = __double2int_rn((i4 * y + i5) * 1024) + 16;
         }
         __syncthreads();
-        const uint8_t *lo_lim = fr.data, *hi_lim = fr.data + (size_t)(fr.h - 1) * fr.pitch + (size_t)fr.w * 3;  // end of valid pixel bytes
-        // consecutive lanes = consecutive output pixels, so the lanes of one load instruction share cache lines
-        for (int p = tid; p < rows * a.cw; p += WARP_THREADS) {
-            const int ry = p / a.cw, x = p - ry * a.cw;
-            const int X = (int)((unsigned)X0s[ry] + (unsigned)adelta[x]) >> 5;
-            const int Y = (int)((unsigned)Y0s[ry] + (unsigned)bdelta[x]) >> 5;
-            const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
-            const int ax = X & 31, ay = Y & 31;
-            const int w00 = (32 - ay) * (32 - ax) * 32, w01 = (32 - ay) * ax * 32;
-            const int w10 = ay * (32 - ax) * 32, w11 = ay * ax * 32;
-            const bool inx0 = sx >= 0 && sx < fr.w, inx1 = sx + 1 >= 0 && sx + 1 < fr.w;
-            const bool iny0 = sy >= 0 && sy < fr.h, iny1 = sy + 1 >= 0 && sy + 1 < fr.h;
-            unsigned long long t0 = 0, t1 = 0;  // rows sy, sy+1: bytes [b0 g0 r0 b1 g1 r1]
-            if (inx0 && inx1) {
-                const uint8_t *p0 = fr.data + (ptrdiff_t)sy * fr.pitch + (ptrdiff_t)sx * 3;
-                if (iny0) t0 = load6(p0, lo_lim, hi_lim);
-                if (iny1) t1 = load6(p0 + fr.pitch, lo_lim, hi_lim);
-            } else if (inx0 || inx1) {  // one tap column outside the image (BORDER_CONSTANT 0)
-                const int sxv = inx0 ? sx : sx + 1;
-                const int shl = inx0 ? 0 : 24;
+        // The map is affine, so the tap coordinates of the band are extremal at its 4 corners: if all 4 corner taps
+        // (and their +1 neighbours) are interior, no pixel of the band needs a border test.
+        bool interior = (reinterpret_cast<uintptr_t>(fr.data) & 7) == 0 && (fr.pitch & 7) == 0 && fr.pitch >= 16;
+        {
+            const int xs[2] = {0, a.cw - 1}, ys[2] = {0, rows - 1};
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    if (iny0) t0 |= (unsigned long long)__ldg(fr.data + (ptrdiff_t)sy * fr.pitch + sxv * 3 + c) << (8 * c + shl);
-                    if (iny1) t1 |= (unsigned long long)__ldg(fr.data + (ptrdiff_t)(sy + 1) * fr.pitch + sxv * 3 + c) << (8 * c + shl);
+            for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+                for (int cx = 0; cx < 2; ++cx) {
+                    const long long Xl = (long long)X0s[ys[cy]] + adelta[xs[cx]], Yl = (long long)Y0s[ys[cy]] + bdelta[xs[cx]];
+                    const long long sx = Xl >> 10, sy = Yl >> 10;
+                    interior = interior && sx >= 0 && sx + 1 < fr.w && sy >= 0 && sy + 1 < fr.h - 1;  // not the last row: 16-byte over-read
                 }
+        }
+        const uint8_t *lo_lim = fr.data, *hi_lim = fr.data + (size_t)(fr.h - 1) * fr.pitch + (size_t)fr.w * 3;  // end of valid pixel bytes
+        // lanes = consecutive output pixels of one row, so the lanes of one load instruction share cache lines
+        const bool small_frame = (size_t)fr.h * fr.pitch < 0x7fffffffull;
+        for (int x = threadIdx.x; x < a.cw; x += WARP_TX) {
+            const unsigned adx = (unsigned)adelta[x], bdx = (unsigned)bdelta[x];
+            uint8_t *o = crop + ((size_t)(band_y0 + threadIdx.y) * a.cw + x) * 3;
+            const size_t ostep = (size_t)WARP_TY * a.cw * 3;
+            if (interior && small_frame) {
+                const unsigned pitch = (unsigned)fr.pitch;
+                // two output rows per step: their 8 aligned 64-bit loads are issued before any is consumed
+                for (int ry = threadIdx.y; ry < rows; ry += 2 * WARP_TY, o += 2 * ostep) {
+                    const int ryb = min(ry + WARP_TY, rows - 1);
+                    const bool two = ry + WARP_TY < rows;
+                    const int Xa = (int)((unsigned)X0s[ry] + adx) >> 5, Ya = (int)((unsigned)Y0s[ry] + bdx) >> 5;
+                    const int Xb = (int)((unsigned)X0s[ryb] + adx) >> 5, Yb = (int)((unsigned)Y0s[ryb] + bdx) >> 5;
+                    const unsigned offa = (unsigned)(Ya >> 5) * pitch + (unsigned)(Xa >> 5) * 3u;
+                    const unsigned offb = (unsigned)(Yb >> 5) * pitch + (unsigned)(Xb >> 5) * 3u;
+                    const uint2 *pa0 = reinterpret_cast<const uint2 *>(fr.data + (offa & ~7u));
+                    const uint2 *pa1 = reinterpret_cast<const uint2 *>(fr.data + ((offa + pitch) & ~7u));
+                    const uint2 *pb0 = reinterpret_cast<const uint2 *>(fr.data + (offb & ~7u));
+                    const uint2 *pb1 = reinterpret_cast<const uint2 *>(fr.data + ((offb + pitch) & ~7u));
+                    const uint2 qa0 = __ldg(pa0), qa1 = __ldg(pa0 + 1), qa2 = __ldg(pa1), qa3 = __ldg(pa1 + 1);
+                    const uint2 qb0 = __ldg(pb0), qb1 = __ldg(pb0 + 1), qb2 = __ldg(pb1), qb3 = __ldg(pb1 + 1);
+                    unsigned lo0, hi0, lo1, hi1;
+                    extract6(qa0, qa1, offa, lo0, hi0);
+                    extract6(qa2, qa3, offa + pitch, lo1, hi1);
+                    blend_store(lo0, hi0, lo1, hi1, Xa & 31, Ya & 31, o);
+                    if (two) {
+                        extract6(qb0, qb1, offb, lo0, hi0);
+                        extract6(qb2, qb3, offb + pitch, lo1, hi1);
+                        blend_store(lo0, hi0, lo1, hi1, Xb & 31, Yb & 31, o + ostep);
+                    }
+                }
+                continue;
             }
-            uint8_t *o = crop + ((size_t)(band_y0 + ry) * a.cw + x) * 3;
+            for (int ry = threadIdx.y; ry < rows; ry += WARP_TY, o += ostep) {
+                const int X = (int)((unsigned)X0s[ry] + adx) >> 5, Y = (int)((unsigned)Y0s[ry] + bdx) >> 5;
+                const int ax = X & 31, ay = Y & 31;
+                unsigned lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+                const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
+                const bool inx0 = sx >= 0 && sx < fr.w, inx1 = sx + 1 >= 0 && sx + 1 < fr.w;
+                const bool iny0 = sy >= 0 && sy < fr.h, iny1 = sy + 1 >= 0 && sy + 1 < fr.h;
+                if (inx0 && inx1) {
+                    const uint8_t *p0 = fr.data + (ptrdiff_t)sy * fr.pitch + (ptrdiff_t)sx * 3;
+                    if (iny0) load6_safe(p0, lo_lim, hi_lim, lo0, hi0);
+                    if (iny1) load6_safe(p0 + fr.pitch, lo_lim, hi_lim, lo1, hi1);
+                } else if (inx0 || inx1) {  // one tap column outside the image (BORDER_CONSTANT 0)
+                    const int sxv = inx0 ? sx : sx + 1;
+                    unsigned t0 = 0, t1 = 0;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const int v00 = (int)((t0 >> (8 * c)) & 0xff), v01 = (int)((t0 >> (8 * c + 24)) & 0xff);
-                const int v10 = (int)((t1 >> (8 * c)) & 0xff), v11 = (int)((t1 >> (8 * c + 24)) & 0xff);
-                o[c] = (uint8_t)((v00 * w00 + v01 * w01 + v10 * w10 + v11 * w11 + (1 << 14)) >> 15);
+                    for (int c = 0; c < 3; ++c) {
+                        if (iny0) t0 |= (unsigned)__ldg(fr.data + (ptrdiff_t)sy * fr.pitch + sxv * 3 + c) << (8 * c);
+                        if (iny1) t1 |= (unsigned)__ldg(fr.data + (ptrdiff_t)(sy + 1) * fr.pitch + sxv * 3 + c) << (8 * c);
+                    }
+                    if (inx0) { lo0 = t0; lo1 = t1; }              // tap 0 valid, tap 1 (bytes 3..5) zero
+                    else { lo0 = t0 << 24; hi0 = t0 >> 8; lo1 = t1 << 24; hi1 = t1 >> 8; }  // tap 1 valid
+                }
+                blend_store(lo0, hi0, lo1, hi1, ax, ay, o);
             }
         }
     }
