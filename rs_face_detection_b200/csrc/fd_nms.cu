@@ -80,8 +80,14 @@ __device__ void build_mask(const float4 *__restrict__ hbox, const float *__restr
     }
 }
 
-// kept/und: HEAD_WORDS words each in shared memory.  On return kept holds the greedy keep set of the head.
-__device__ void resolve_rounds(const u64 *__restrict__ mask, int S, u64 *kept, u64 *und) {
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// kept/und: HEAD_WORDS words each in shared memory; flags: 2 ints.  On return kept holds the greedy keep set of the head.
+// Only the warps that own head rows take part in the rounds (named barrier 1); the rest of the CTA waits at the final
+// block-wide barrier, so a round costs a barrier over S threads instead of the whole block.
+__device__ void resolve_rounds(const u64 *__restrict__ mask, int S, u64 *kept, u64 *und, int *flags) {
     const int i = threadIdx.x;
     if (i < HEAD_WORDS) {
         int lo = i * 64;
@@ -89,29 +95,37 @@ __device__ void resolve_rounds(const u64 *__restrict__ mask, int S, u64 *kept, u
         und[i] = nbits == 64 ? ~0ull : ((1ull << nbits) - 1ull);
         kept[i] = 0ull;
     }
+    if (i == 0) flags[0] = flags[1] = 0;
     __syncthreads();
-    const int t = i >> 6;
-    const u64 bit = 1ull << (i & 63);
-    bool undecided = i < S;
-    while (true) {
-        int dec = 0;  // 0 wait, 1 keep, 2 suppress
-        if (undecided) {
-            bool sup = false, wait = false;
-            for (int w = 0; w <= t; ++w) {
-                u64 e = mask[mask_index(i, w)];
-                if (e & kept[w]) { sup = true; break; }
-                if (e & und[w]) wait = true;
+    const int P = (S + 31) & ~31;  // participating threads (whole warps)
+    if (i < P) {
+        const int t = i >> 6;
+        const u64 bit = 1ull << (i & 63);
+        bool undecided = i < S;
+        for (int round = 0;; ++round) {
+            int dec = 0;  // 0 wait, 1 keep, 2 suppress
+            if (undecided) {
+                bool sup = false, wait = false;
+                for (int w = 0; w <= t; ++w) {
+                    u64 e = mask[mask_index(i, w)];
+                    if (e & kept[w]) { sup = true; break; }
+                    if (e & und[w]) wait = true;
+                }
+                dec = sup ? 2 : (wait ? 0 : 1);
             }
-            dec = sup ? 2 : (wait ? 0 : 1);
+            named_bar_sync(1, P);  // every read of kept/und of this round (and of last round's flag) is done
+            if (i == 0) flags[(round + 1) & 1] = 0;  // next round's flag: last read before the barrier above
+            if (dec == 1) atomicOr(&kept[t], bit);
+            if (dec != 0) {
+                atomicAnd(&und[t], ~bit);
+                undecided = false;
+            }
+            if (undecided) flags[round & 1] = 1;
+            named_bar_sync(1, P);
+            if (flags[round & 1] == 0) break;
         }
-        __syncthreads();  // every read of kept/und of this round is done
-        if (dec == 1) atomicOr(&kept[t], bit);
-        if (dec != 0) {
-            atomicAnd(&und[t], ~bit);
-            undecided = false;
-        }
-        if (!__syncthreads_or(undecided)) break;
     }
+    __syncthreads();
 }
 
 // exclusive position of `flag` among the block's threads (thread order) and the block total
@@ -243,10 +257,17 @@ __global__ void __launch_bounds__(NT, 1) nms_cta_kernel(SmallArgs a) {
     u64 *sorted = sm.keys;
     if (!a.presorted) {
         if (K <= 256) {
-            // rank sort: keys are unique (the index is in the low bits), one key per thread, K broadcast reads
-            u64 mine = tid < K ? sm.keys[tid] : ~0ull;
+            // rank sort (tiny problems only: beyond ~256 keys the bitonic network is cheaper): keys are unique (the index is in the low bits); one key per thread, every thread streams the K
+            // keys from shared memory as warp-uniform (broadcast) 128-bit reads and counts the smaller ones
+            const u64 mine = tid < K ? sm.keys[tid] : ~0ull;
             int rank = 0;
-            for (int j = 0; j < K; ++j) rank += (sm.keys[j] < mine) ? 1 : 0;
+            const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(sm.keys);
+            const int pairs = n2 >> 1;  // padding keys are ~0: never smaller than a real key
+            for (int j = 0; j < pairs; ++j) {
+                const ulonglong2 q = k2[j];
+                rank += (q.x < mine) ? 1 : 0;
+                rank += (q.y < mine) ? 1 : 0;
+            }
             sorted = sm.keys + SMALL_CAP / 2;
             if (tid < K) sorted[rank] = mine;
             __syncthreads();
@@ -310,7 +331,7 @@ __global__ void __launch_bounds__(NT, 1) nms_cta_kernel(SmallArgs a) {
         if (fast) build_mask<MODE, true>(sm.hbox, sm.harea, S, sm.mask, a.iou, nwarps);
         else build_mask<MODE, false>(sm.hbox, sm.harea, S, sm.mask, a.iou, nwarps);
         __syncthreads();
-        resolve_rounds(sm.mask, S, sm.kept, sm.und);
+        resolve_rounds(sm.mask, S, sm.kept, sm.und, sm.misc);
         // (resolve_rounds ends on a block-wide barrier: mask is dead from here, kept is final)
         int nkept = 0;
         bool is_kept = false;
@@ -612,7 +633,7 @@ __global__ void __launch_bounds__(NT, 1) nms_peel_kernel(PeelArgs a) {
             if (fast) build_mask<MODE, true>(sm.hbox, sm.harea, S, sm.mask, a.iou, NWARPS);
             else build_mask<MODE, false>(sm.hbox, sm.harea, S, sm.mask, a.iou, NWARPS);
             __syncthreads();
-            resolve_rounds(sm.mask, S, sm.kept, sm.und);
+            resolve_rounds(sm.mask, S, sm.kept, sm.und, sm.red);
             int nkept = 0;
             if (tid < S) {
                 bool is_kept = (sm.kept[tid >> 6] >> (tid & 63)) & 1ull;
