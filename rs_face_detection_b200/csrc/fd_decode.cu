@@ -22,11 +22,67 @@ struct HeadPtrs {
 
 constexpr int CAND_REC = 12;  // floats per candidate record: 10 landmarks, score, pad
 
+// decodes anchor (s, local, a) of image b and writes its candidate record; returns nothing
+__device__ __forceinline__ void decode_one(const DecodeCfg &c, const HeadPtrs &hp, int b, int s, int local, int a, float score,
+                                           int slot, u64 *__restrict__ keys, float4 *__restrict__ cand_box,
+                                           float *__restrict__ cand_rec) {
+    const int fw = c.fw[s], hw = c.fh[s] * c.fw[s];
+    const int h = local / fw, w = local - h * fw;
+    const int A = c.A;
+    const float *bb = hp.p[3 * s + 1] + (size_t)b * 4 * A * hw;
+    const float *lm = hp.p[3 * s + 2] + (size_t)b * 10 * A * hw;
+    const size_t img_base = (size_t)b * c.total_anchors;
+    const int id = c.anchor_off[s] + local * A + a;
+    // anchor = base + (w*stride, h*stride, w*stride, h*stride)   (anchors.rs:8-16)
+    const float sw = (float)(w * c.stride[s]), sh = (float)(h * c.stride[s]);
+    const float ax1 = __fadd_rn(c.base[s][a][0], sw), ay1 = __fadd_rn(c.base[s][a][1], sh);
+    const float ax2 = __fadd_rn(c.base[s][a][2], sw), ay2 = __fadd_rn(c.base[s][a][3], sh);
+    // face_detection.rs:522-525
+    const float aw = __fadd_rn(__fsub_rn(ax2, ax1), 1.0f), ah = __fadd_rn(__fsub_rn(ay2, ay1), 1.0f);
+    const float cx = __fadd_rn(ax1, __fmul_rn(0.5f, __fsub_rn(aw, 1.0f)));
+    const float cy = __fadd_rn(ay1, __fmul_rn(0.5f, __fsub_rn(ah, 1.0f)));
+    const float dx = __fmul_rn(__ldg(bb + (size_t)(4 * a + 0) * hw + local), c.bbox_stds[0]);  // :366-371
+    const float dy = __fmul_rn(__ldg(bb + (size_t)(4 * a + 1) * hw + local), c.bbox_stds[1]);
+    const float dw = __fmul_rn(__ldg(bb + (size_t)(4 * a + 2) * hw + local), c.bbox_stds[2]);
+    const float dh = __fmul_rn(__ldg(bb + (size_t)(4 * a + 3) * hw + local), c.bbox_stds[3]);
+    float lraw[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) lraw[k] = __ldg(lm + (size_t)(10 * a + k) * hw + local);
+    // :532-535.  exp through fp64 is correctly rounded to <=0.5 ulp; the reference's f32::exp is the platform expf.
+    const float pcx = __fadd_rn(__fmul_rn(dx, aw), cx), pcy = __fadd_rn(__fmul_rn(dy, ah), cy);
+    const float pw = __fmul_rn((float)exp((double)dw), aw), ph = __fmul_rn((float)exp((double)dh), ah);
+    // :539-542, then clip_boxes to the padded detector image (:373, bbox_transform.rs:36-42)
+    const float hwx = __fmul_rn(0.5f, __fsub_rn(pw, 1.0f)), hwy = __fmul_rn(0.5f, __fsub_rn(ph, 1.0f));
+    float4 box;
+    box.x = fmaxf(fminf(__fsub_rn(pcx, hwx), c.clip_w), 0.0f);
+    box.y = fmaxf(fminf(__fsub_rn(pcy, hwy), c.clip_h), 0.0f);
+    box.z = fmaxf(fminf(__fadd_rn(pcx, hwx), c.clip_w), 0.0f);
+    box.w = fmaxf(fminf(__fadd_rn(pcy, hwy), c.clip_h), 0.0f);
+    cand_box[img_base + id] = box;
+    // landmarks from the ANCHOR box, never clipped (:399, :564-567)
+    float rec[CAND_REC];
+#pragma unroll
+    for (int p = 0; p < 5; ++p) {
+        rec[2 * p] = __fadd_rn(__fmul_rn(__fmul_rn(lraw[2 * p], c.landmark_std), aw), cx);
+        rec[2 * p + 1] = __fadd_rn(__fmul_rn(__fmul_rn(lraw[2 * p + 1], c.landmark_std), ah), cy);
+    }
+    rec[10] = score;
+    rec[11] = 0.0f;
+    float4 *dst = reinterpret_cast<float4 *>(cand_rec + (img_base + id) * CAND_REC);
+    dst[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+    dst[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+    dst[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+    keys[img_base + slot] = ((u64)desc_key(score) << 32) | (unsigned)id;
+}
+
+// VEC consecutive positions of one stride per thread (VEC == 4: 128-bit loads of the score planes; needs every H*W to be
+// a multiple of 4 and 16-byte aligned tensors, else VEC == 1).  One atomicAdd per warp reserves the key slots.
+template <int VEC>
 __global__ void __launch_bounds__(256) decode_kernel(DecodeCfg c, HeadPtrs hp, float conf_thr, u64 *__restrict__ keys,
                                                      float4 *__restrict__ cand_box, float *__restrict__ cand_rec,
                                                      int *__restrict__ counts, int *__restrict__ status) {
     const int b = blockIdx.y;
-    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pos = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     const int lane = threadIdx.x & 31;
     const bool active = pos < c.total_pos;
     int s = 0;
@@ -36,69 +92,55 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeCfg c, HeadPtrs hp, f
             if (k < c.n_strides && pos >= c.pos_off[k]) s = k;
     }
     const int local = active ? pos - c.pos_off[s] : 0;
-    const int fw = c.fw[s], hw = c.fh[s] * c.fw[s];
-    const int h = local / fw, w = local - h * fw;
+    const int hw = c.fh[s] * c.fw[s];
     const int A = c.A;
     const float *sc = hp.p[3 * s] + (size_t)b * 2 * A * hw;
-    const float *bb = hp.p[3 * s + 1] + (size_t)b * 4 * A * hw;
-    const float *lm = hp.p[3 * s + 2] + (size_t)b * 10 * A * hw;
-    const size_t img_base = (size_t)b * c.total_anchors;
-    for (int a = 0; a < A; ++a) {
-        float score = 0.0f;
-        bool pass = false;
-        if (active) {
-            score = __ldg(sc + (size_t)(A + a) * hw + local);  // fg scores are channels A.. (face_detection.rs:322)
-            if (score != score) atomicExch(&status[0], 1);     // the reference panics on NaN (utils.rs:92)
-            pass = score >= conf_thr;                          // face_detection.rs:375
-        }
-        unsigned bal = __ballot_sync(0xffffffffu, pass);
-        if (bal == 0) continue;
-        int base = 0;
-        const int leader = __ffs(bal) - 1;
-        if (lane == leader) base = atomicAdd(&counts[b], __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (!pass) continue;
-        const int slot = base + __popc(bal & ((1u << lane) - 1u));
-        const int id = c.anchor_off[s] + local * A + a;
-        // anchor = base + (w*stride, h*stride, w*stride, h*stride)   (anchors.rs:8-16)
-        const float sw = (float)(w * c.stride[s]), sh = (float)(h * c.stride[s]);
-        const float ax1 = __fadd_rn(c.base[s][a][0], sw), ay1 = __fadd_rn(c.base[s][a][1], sh);
-        const float ax2 = __fadd_rn(c.base[s][a][2], sw), ay2 = __fadd_rn(c.base[s][a][3], sh);
-        // face_detection.rs:522-525
-        const float aw = __fadd_rn(__fsub_rn(ax2, ax1), 1.0f), ah = __fadd_rn(__fsub_rn(ay2, ay1), 1.0f);
-        const float cx = __fadd_rn(ax1, __fmul_rn(0.5f, __fsub_rn(aw, 1.0f)));
-        const float cy = __fadd_rn(ay1, __fmul_rn(0.5f, __fsub_rn(ah, 1.0f)));
-        const float dx = __fmul_rn(__ldg(bb + (size_t)(4 * a + 0) * hw + local), c.bbox_stds[0]);  // :366-371
-        const float dy = __fmul_rn(__ldg(bb + (size_t)(4 * a + 1) * hw + local), c.bbox_stds[1]);
-        const float dw = __fmul_rn(__ldg(bb + (size_t)(4 * a + 2) * hw + local), c.bbox_stds[2]);
-        const float dh = __fmul_rn(__ldg(bb + (size_t)(4 * a + 3) * hw + local), c.bbox_stds[3]);
-        // :532-535.  exp through fp64 is correctly rounded to <=0.5 ulp; the reference's f32::exp is the platform expf.
-        const float pcx = __fadd_rn(__fmul_rn(dx, aw), cx), pcy = __fadd_rn(__fmul_rn(dy, ah), cy);
-        const float pw = __fmul_rn((float)exp((double)dw), aw), ph = __fmul_rn((float)exp((double)dh), ah);
-        // :539-542, then clip_boxes to the padded detector image (:373, bbox_transform.rs:36-42)
-        const float hwx = __fmul_rn(0.5f, __fsub_rn(pw, 1.0f)), hwy = __fmul_rn(0.5f, __fsub_rn(ph, 1.0f));
-        float4 box;
-        box.x = fmaxf(fminf(__fsub_rn(pcx, hwx), c.clip_w), 0.0f);
-        box.y = fmaxf(fminf(__fsub_rn(pcy, hwy), c.clip_h), 0.0f);
-        box.z = fmaxf(fminf(__fadd_rn(pcx, hwx), c.clip_w), 0.0f);
-        box.w = fmaxf(fminf(__fadd_rn(pcy, hwy), c.clip_h), 0.0f);
-        cand_box[img_base + id] = box;
-        // landmarks from the ANCHOR box, never clipped (:399, :564-567)
-        float rec[CAND_REC];
+    float score[FD_MAX_ANCHORS][VEC];
+    unsigned pass = 0;  // bit a*VEC+v
+    bool nan_seen = false;
+    if (active) {
 #pragma unroll
-        for (int p = 0; p < 5; ++p) {
-            float lx = __fmul_rn(__ldg(lm + (size_t)(10 * a + 2 * p) * hw + local), c.landmark_std);
-            float ly = __fmul_rn(__ldg(lm + (size_t)(10 * a + 2 * p + 1) * hw + local), c.landmark_std);
-            rec[2 * p] = __fadd_rn(__fmul_rn(lx, aw), cx);
-            rec[2 * p + 1] = __fadd_rn(__fmul_rn(ly, ah), cy);
+        for (int a = 0; a < FD_MAX_ANCHORS; ++a) {
+            if (a >= A) break;
+            const float *p = sc + (size_t)(A + a) * hw + local;  // fg scores are channels A.. (face_detection.rs:322)
+            if (VEC == 4) {
+                const float4 q = __ldg(reinterpret_cast<const float4 *>(p));
+                score[a][0] = q.x; score[a][1 % VEC] = q.y; score[a][2 % VEC] = q.z; score[a][3 % VEC] = q.w;
+            } else {
+                score[a][0] = __ldg(p);
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const float sv = score[a][v];
+                nan_seen |= (sv != sv);                                  // the reference panics on NaN (utils.rs:92)
+                if (sv >= conf_thr) pass |= 1u << (a * VEC + v);         // face_detection.rs:375
+            }
         }
-        rec[10] = score;
-        rec[11] = 0.0f;
-        float4 *dst = reinterpret_cast<float4 *>(cand_rec + (img_base + id) * CAND_REC);
-        dst[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
-        dst[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
-        dst[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
-        keys[img_base + slot] = ((u64)desc_key(score) << 32) | (unsigned)id;
+    }
+    if (nan_seen) atomicExch(&status[0], 1);
+    const int cnt = __popc(pass);
+    if (__ballot_sync(0xffffffffu, cnt != 0) == 0) return;  // common case: nothing above the threshold in this warp
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += nb;
+    }
+    int base = 0;
+    if (lane == 31) base = atomicAdd(&counts[b], incl);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    int slot = base + incl - cnt;
+    while (pass) {
+        const int bit = __ffs(pass) - 1;
+        pass &= pass - 1;
+        const int a = bit / VEC, v = bit - a * VEC;
+        float sv = 0.0f;
+#pragma unroll
+        for (int aa = 0; aa < FD_MAX_ANCHORS; ++aa)
+#pragma unroll
+            for (int vv = 0; vv < VEC; ++vv)
+                if (aa == a && vv == v) sv = score[aa][vv];
+        decode_one(c, hp, b, s, local + v, a, sv, slot++, keys, cand_box, cand_rec);
     }
 }
 
@@ -150,10 +192,18 @@ __global__ void __launch_bounds__(256) finalize_kernel(int B, int TA, const int 
 int decode_launch(fd_ctx *ctx, const float *const *heads_dev, int B, float conf_thr) {
     HeadPtrs hp;
     for (int i = 0; i < 3 * FD_MAX_STRIDES; ++i) hp.p[i] = i < 3 * ctx->dcfg.n_strides ? heads_dev[i] : nullptr;
-    dim3 grid((ctx->dcfg.total_pos + 255) / 256, B);
-    decode_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->dcfg, hp, conf_thr, ctx->cand_keys.as<u64>(), ctx->cand_box.as<float4>(),
-                                                 ctx->cand_lmk.as<float>(), ctx->cand_count.as<int>(),
-                                                 ctx->status_dev.as<int>());
+    bool vec4 = true;  // 128-bit score loads need H*W % 4 == 0 for every stride and 16-byte aligned score tensors
+    for (int st = 0; st < ctx->dcfg.n_strides; ++st)
+        vec4 = vec4 && ((ctx->dcfg.fh[st] * ctx->dcfg.fw[st]) % 4 == 0) && (reinterpret_cast<uintptr_t>(heads_dev[3 * st]) % 16 == 0);
+    if (vec4) {
+        dim3 grid((ctx->dcfg.total_pos / 4 + 255) / 256, B);
+        decode_kernel<4><<<grid, 256, 0, ctx->stream>>>(ctx->dcfg, hp, conf_thr, ctx->cand_keys.as<u64>(), ctx->cand_box.as<float4>(),
+                                                       ctx->cand_lmk.as<float>(), ctx->cand_count.as<int>(), ctx->status_dev.as<int>());
+    } else {
+        dim3 grid((ctx->dcfg.total_pos + 255) / 256, B);
+        decode_kernel<1><<<grid, 256, 0, ctx->stream>>>(ctx->dcfg, hp, conf_thr, ctx->cand_keys.as<u64>(), ctx->cand_box.as<float4>(),
+                                                       ctx->cand_lmk.as<float>(), ctx->cand_count.as<int>(), ctx->status_dev.as<int>());
+    }
     FD_LAUNCH_CHECK(ctx);
     return FD_OK;
 }
