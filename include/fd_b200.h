@@ -191,6 +191,19 @@ int fd_align_batch(fd_ctx *ctx, const fd_frame *frames, int B, const float *land
 int fd_align_detections(fd_ctx *ctx, const fd_frame *frames, int B, uint8_t *crops_dev, int cap_faces, double *M_dev,
                         uint8_t *ok_dev);
 
+/* ---- post-align model preprocessors, fused onto the aligned crops ----------------------- */
+/* FaceExtraction::_preprocess (face_extraction.rs:38-77: mean 127.5, mul 0.0078125), FaceQuality::call
+ * (face_quality.rs:43-101: mean {123.675,116.28,103.53}, mul {0.01712475,0.017507,0.01742919}),
+ * FaceQualityAssessment::call (face_quality_assessment.rs:48-88: mean 127.5, mul 0.00784313725):
+ * cv::resize INTER_LINEAR to (out_w,out_h) -> BGR2RGB -> (p - mean[i]) * mul[i] (i in RGB order) -> NCHW f32.
+ * crops_dev (F,in_h,in_w,3) u8 (e.g. the fd_align_* output) -> out_nchw_dev (F,3,out_h,out_w).  Asynchronous.
+ * use_detect_count != 0: process min(F, faces of the last fd_detect_batch), counted on the device. */
+int fd_crops_to_tensor(fd_ctx *ctx, const uint8_t *crops_dev, int F, int in_h, int in_w, int out_h, int out_w,
+                       const float *mean_rgb, const float *mul_rgb, float *out_nchw_dev, int use_detect_count);
+/* the same for ONE host image (the reference processes `&[Mat]` one Mat at a time), blocking */
+int fd_model_preprocess(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, int out_h, int out_w,
+                        const float *mean_rgb, const float *mul_rgb, float *out_nchw);
+
 /* ---- end-to-end with HOST buffers (bench.py "e2e"): H2D frames + heads, full path, D2H results -------- */
 typedef struct fd_host_batch_out {
     int32_t *counts;      /* (B) */

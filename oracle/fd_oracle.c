@@ -786,6 +786,26 @@ FDO_API int fdo_align_face(const uint8_t *img, int h, int w, int pitch, const fl
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* N1: post-align model preprocessors.  FaceExtraction::_preprocess                  */
+/* (face_extraction.rs:38-77: mean 127.5, mul 0.0078125), FaceQuality::call (face_quality.rs:43-101: */
+/* mean {123.675,116.28,103.53}, mul {0.01712475,0.017507,0.01742919}), FaceQualityAssessment::call  */
+/* (face_quality_assessment.rs:48-88: mean 127.5, mul 0.00784313725):                               */
+/* cv::resize INTER_LINEAR -> cvtColor BGR2RGB -> (p as f32 - mean[i]) * mul[i] -> NCHW.            */
+/* ------------------------------------------------------------------------------------------ */
+FDO_API void fdo_model_preprocess(const uint8_t *img, int h, int w, int pitch, int out_h, int out_w,
+                                  const float mean_rgb[3], const float mul_rgb[3], float *out) {
+    uint8_t *rs = (uint8_t *)malloc((size_t)out_h * out_w * 3);
+    fdo_resize_linear_u8c3(img, h, w, pitch, rs, out_h, out_w, out_w * 3);
+    for (int i = 0; i < 3; ++i)
+        for (int y = 0; y < out_h; ++y)
+            for (int x = 0; x < out_w; ++x) {
+                uint8_t p = rs[((size_t)y * out_w + x) * 3 + (2 - i)];   /* RGB channel i = BGR channel 2-i */
+                out[((size_t)i * out_h + y) * out_w + x] = ((float)p - mean_rgb[i]) * mul_rgb[i];
+            }
+    free(rs);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* Whole-frame CPU path (bench.py cpu_baseline / --impl reference):                             */
 /* preprocess -> tensor -> decode -> sort -> NMS -> rescale -> align every detection.           */
 /* ------------------------------------------------------------------------------------------ */

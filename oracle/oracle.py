@@ -342,6 +342,24 @@ def align_face(img, lmk, template=ARCFACE_TEMPLATE, dsize=(112, 112)):
     return (out, M.reshape(2, 3)) if ok else (None, None)
 
 
+MODEL_NORMS = {  # (mean_rgb, mul_rgb) of the three post-align models
+    "face_extraction": ((127.5, 127.5, 127.5), (0.0078125,) * 3),                                   # face_extraction.rs:69
+    "face_quality": ((123.675, 116.28, 103.53), (0.01712475, 0.017507, 0.01742919)),               # face_quality.rs:43-44,93
+    "face_quality_assessment": ((127.5, 127.5, 127.5), (0.00784313725,) * 3),                       # face_quality_assessment.rs:78
+}
+
+
+def model_preprocess(img, out_size, mean_rgb, mul_rgb):
+    """resize -> BGR2RGB -> (p - mean) * mul -> (3, out_h, out_w)"""
+    img = np.ascontiguousarray(img, np.uint8)
+    mean_rgb, mul_rgb = _f32(mean_rgb), _f32(mul_rgb)
+    ow, oh = out_size
+    out = np.empty((3, oh, ow), np.float32)
+    lib().fdo_model_preprocess(_p(img, c_u8p), img.shape[0], img.shape[1], img.strides[0], oh, ow, _p(mean_rgb, c_f32p),
+                               _p(mul_rgb, c_f32p), _p(out, c_f32p))
+    return out
+
+
 def pipeline_frame(cfg, img, heads, template=ARCFACE_TEMPLATE, crop=(112, 112), pixel_scale=1.0,
                    means=(0, 0, 0), stds=(1, 1, 1), bufs=None):
     """Whole reference CPU path for one frame.  Returns tensor, det, landmarks, crops."""

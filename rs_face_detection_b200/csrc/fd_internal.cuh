@@ -199,6 +199,8 @@ __device__ __forceinline__ bool box_is_fast_ok(float4 b) {
 // stage entry points implemented across the .cu files
 int preprocess_launch(fd_ctx *ctx, const FrameDev *frames_dev, int B, float *out_nchw_dev, int max_row_bytes, bool rows_aligned16);
 int resize_launch(fd_ctx *ctx, const FrameDev &frame, uint8_t *out_dev, int out_h, int out_w);
+int crops_to_tensor_launch(fd_ctx *ctx, const uint8_t *crops_dev, const int *count_dev, int F, int in_h, int in_w, int out_h,
+                           int out_w, const float *mean_rgb, const float *mul_rgb, float *out_dev);
 int decode_launch(fd_ctx *ctx, const float *const *heads_dev, int B, float conf_thr);
 int nms_batch_launch(fd_ctx *ctx, int B, float iou_thr);
 int nms_batch_big_image(fd_ctx *ctx, int b, int K, float iou_thr);

@@ -387,6 +387,33 @@ FD_EXPORT int fd_align(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch,
     return warp_host(ctx, img, h, w, pitch, nullptr, landmarks, crop, ctx->cfg.crop_h, ctx->cfg.crop_w, M_out);
 }
 
+// ---- N1: post-align model preprocessors ------------------------------------------------------------------------------
+FD_EXPORT int fd_crops_to_tensor(fd_ctx *ctx, const uint8_t *crops_dev, int F, int in_h, int in_w, int out_h, int out_w,
+                                 const float *mean_rgb, const float *mul_rgb, float *out_nchw_dev, int use_detect_count) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(F >= 0 && in_h > 0 && in_w > 0 && out_h > 0 && out_w > 0 && mean_rgb && mul_rgb, "fd_crops_to_tensor: bad arguments");
+    FD_REQUIRE(F == 0 || (crops_dev && out_nchw_dev), "fd_crops_to_tensor: null buffers");
+    FD_REQUIRE(!use_detect_count || ctx->last_B > 0, "fd_crops_to_tensor: no fd_detect_batch results to take the face count from");
+    return crops_to_tensor_launch(ctx, crops_dev, use_detect_count ? ctx->status_dev.as<int>() + 2 : nullptr, F, in_h, in_w, out_h, out_w,
+                                  mean_rgb, mul_rgb, out_nchw_dev);
+}
+
+FD_EXPORT int fd_model_preprocess(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, int out_h, int out_w,
+                                  const float *mean_rgb, const float *mul_rgb, float *out_nchw) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(img && out_nchw && h > 0 && w > 0 && pitch >= w * 3 && out_h > 0 && out_w > 0 && mean_rgb && mul_rgb,
+               "fd_model_preprocess: bad arguments");
+    FD_TRY(ctx->scratch[3].reserve((size_t)h * w * 3));
+    FD_CUDA(cudaMemcpy2DAsync(ctx->scratch[3].p, (size_t)w * 3, img, pitch, (size_t)w * 3, h, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t n = (size_t)3 * out_h * out_w;
+    FD_TRY(ctx->scratch[4].reserve(sizeof(float) * n));
+    FD_TRY(crops_to_tensor_launch(ctx, ctx->scratch[3].as<uint8_t>(), nullptr, 1, h, w, out_h, out_w, mean_rgb, mul_rgb,
+                                  ctx->scratch[4].as<float>()));
+    FD_CUDA(cudaMemcpyAsync(out_nchw, ctx->scratch[4].p, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FD_OK;
+}
+
 // ---- end-to-end with host buffers ------------------------------------------------------------------------------------
 FD_EXPORT int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const float *const *heads_host, int n_heads,
                                float conf_thr, float iou_thr, fd_host_batch_out *out) {

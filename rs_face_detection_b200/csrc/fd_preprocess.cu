@@ -324,6 +324,78 @@ __global__ void resize_u8_kernel(FrameDev f, uint8_t *__restrict__ out, int out_
     }
 }
 
+// N1: post-align model preprocessors fused onto the warp output — FaceExtraction::_preprocess
+// (face_extraction.rs:38-77), FaceQuality::call (face_quality.rs:43-101), FaceQualityAssessment::call
+// (face_quality_assessment.rs:48-88): cv::resize INTER_LINEAR to the model input, BGR->RGB, (p - mean[i]) * mul[i], NCHW.
+// crops (F, in_h, in_w, 3) u8 dense; out (F, 3, out_h, out_w).  4 pixels per thread, 128-bit stores per plane.
+struct CropArgs {
+    const uint8_t *crops;
+    const int *count_dev;
+    int F, in_h, in_w, out_h, out_w;
+    float mean[3], mul[3];  // RGB order
+    float *out;
+};
+__global__ void __launch_bounds__(256) crops_to_tensor_kernel(CropArgs a) {
+    const int F = a.count_dev ? min(*a.count_dev, a.F) : a.F;
+    const int groups_per_row = (a.out_w + 3) >> 2;
+    const int groups = a.out_h * groups_per_row;
+    const bool same = a.in_h == a.out_h && a.in_w == a.out_w;   // cv::resize copies when the size is unchanged
+    const double scale_x = 1.0 / ((double)a.out_w / a.in_w), scale_y = 1.0 / ((double)a.out_h / a.in_h);
+    const size_t plane = (size_t)a.out_h * a.out_w;
+    for (int f = blockIdx.y; f < F; f += gridDim.y) {
+        const uint8_t *src = a.crops + (size_t)f * a.in_h * a.in_w * 3;
+        float *o = a.out + (size_t)f * 3 * plane;
+        for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+            const int y = g / groups_per_row, x4 = (g - y * groups_per_row) * 4;
+            float v[3][4];
+            int y0 = y, y1 = y, b0 = 2048, b1 = 0;
+            if (!same) y_taps(y, scale_y, a.in_h, &y0, &y1, &b0, &b1);
+            const uint8_t *r0 = src + (size_t)y0 * a.in_w * 3, *r1 = src + (size_t)y1 * a.in_w * 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int x = min(x4 + j, a.out_w - 1);
+                int bgr[3];
+                if (same) {
+                    bgr[0] = r0[x * 3]; bgr[1] = r0[x * 3 + 1]; bgr[2] = r0[x * 3 + 2];
+                } else {
+                    int o0, o1;
+                    short q0, q1;
+                    x_taps(x, scale_x, a.in_w, &o0, &o1, &q0, &q1);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) bgr[c] = resize_px(r0, r1, o0 + c, o1 + c, q0, q1, b0, b1);
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) v[i][j] = __fmul_rn(__fsub_rn((float)bgr[2 - i], a.mean[i]), a.mul[i]);
+            }
+            float *dst = o + (size_t)y * a.out_w + x4;
+            if (x4 + 3 < a.out_w && (a.out_w & 3) == 0) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) __stcs(reinterpret_cast<float4 *>(dst + i * plane), make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
+            } else {
+                for (int j = 0; j < 4 && x4 + j < a.out_w; ++j)
+                    for (int i = 0; i < 3; ++i) dst[i * plane + j] = v[i][j];
+            }
+        }
+    }
+}
+
+int crops_to_tensor_launch(fd_ctx *ctx, const uint8_t *crops_dev, const int *count_dev, int F, int in_h, int in_w, int out_h,
+                           int out_w, const float *mean_rgb, const float *mul_rgb, float *out_dev) {
+    if (F <= 0) return FD_OK;
+    CropArgs a;
+    a.crops = crops_dev;
+    a.count_dev = count_dev;
+    a.F = F; a.in_h = in_h; a.in_w = in_w; a.out_h = out_h; a.out_w = out_w;
+    for (int i = 0; i < 3; ++i) { a.mean[i] = mean_rgb[i]; a.mul[i] = mul_rgb[i]; }
+    a.out = out_dev;
+    const int groups = out_h * ((out_w + 3) / 4);
+    dim3 grid(std::max(1, std::min(16, (groups + 255) / 256)), std::min(F, 65535));
+    if (count_dev) grid.y = std::min(F, std::max(1, ctx->num_sms * 8 / (int)grid.x));
+    crops_to_tensor_kernel<<<grid, 256, 0, ctx->stream>>>(a);
+    FD_LAUNCH_CHECK(ctx);
+    return FD_OK;
+}
+
 int preprocess_launch(fd_ctx *ctx, const FrameDev *frames_dev, int B, float *out_nchw_dev, int max_row_bytes, bool rows_aligned16) {
     PreArgs a;
     a.frames = frames_dev;

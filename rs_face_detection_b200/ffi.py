@@ -73,7 +73,7 @@ SYMBOLS = [
     "fd_nonlinear_transform", "fd_bbox_overlaps", "fd_letterbox_geometry", "fd_preprocess", "fd_resize_linear",
     "fd_detect", "fd_estimate_affine_partial_2d", "fd_warp_affine", "fd_align",
     "fd_nms_device", "fd_preprocess_batch", "fd_detect_batch", "fd_detect_fetch", "fd_detect_view", "fd_align_batch",
-    "fd_align_detections", "fd_pipeline_host", "fd_pipeline_tensor_dev",
+    "fd_align_detections", "fd_crops_to_tensor", "fd_model_preprocess", "fd_pipeline_host", "fd_pipeline_tensor_dev",
 ]
 
 _lib = None
@@ -466,6 +466,20 @@ class Context:
         arr = self._frames(frames)
         _chk(self.lib.fd_align_detections(self.handle, arr, len(frames), C.c_void_p(_devptr(crops_dev)), cap_faces,
                                           C.c_void_p(_devptr(M_dev)), C.c_void_p(_devptr(ok_dev))))
+
+    def crops_to_tensor(self, crops_dev, F, in_hw, out_hw, mean_rgb, mul_rgb, out_dev, use_detect_count=False):
+        mean, mul = _f32(mean_rgb), _f32(mul_rgb)
+        _chk(self.lib.fd_crops_to_tensor(self.handle, C.c_void_p(_devptr(crops_dev)), int(F), in_hw[0], in_hw[1], out_hw[0], out_hw[1],
+                                         _ptr(mean, c_f32p), _ptr(mul, c_f32p), C.c_void_p(_devptr(out_dev)), int(use_detect_count)))
+
+    def model_preprocess(self, img, out_size, mean_rgb, mul_rgb):
+        img = np.ascontiguousarray(img, np.uint8)
+        mean, mul = _f32(mean_rgb), _f32(mul_rgb)
+        ow, oh = out_size
+        out = np.empty((3, oh, ow), np.float32)
+        _chk(self.lib.fd_model_preprocess(self.handle, _ptr(img, c_u8p), img.shape[0], img.shape[1], img.strides[0], oh, ow,
+                                          _ptr(mean, c_f32p), _ptr(mul, c_f32p), _ptr(out, c_f32p)))
+        return out
 
     def pipeline_host(self, frames_host, heads_host, cap_rows, conf_thr=None, iou_thr=None, want_tensor=False, bufs=None):
         """frames_host: list of HxWx3 u8 arrays (host, ideally pinned); heads_host: 9 host arrays (B,C,H,W)."""

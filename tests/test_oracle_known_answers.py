@@ -127,3 +127,13 @@ def test_detect_post_empty_and_order(oracle):
     # every planted face is recovered by a detection with IoU > 0.5 (boxes were divided by det_scale 0.5)
     ov = oracle.bbox_overlaps(faces[0] / 0.5, det[:, :4])
     assert (ov.max(1) > 0.5).mean() > 0.8
+
+
+def test_model_preprocess_known_values(oracle):
+    # face_extraction.rs:69: (p - 127.5) * 0.0078125, RGB order, NCHW
+    img = np.zeros((2, 2, 3), np.uint8)
+    img[0, 0] = (10, 20, 30)          # B, G, R
+    out = oracle.model_preprocess(img, (2, 2), *oracle.MODEL_NORMS["face_extraction"])
+    assert out.shape == (3, 2, 2)
+    np.testing.assert_array_equal(out[:, 0, 0], np.float32([(30 - 127.5) * 0.0078125, (20 - 127.5) * 0.0078125, (10 - 127.5) * 0.0078125]))
+    np.testing.assert_array_equal(out[:, 1, 1], np.float32([-127.5 * 0.0078125] * 3))
