@@ -172,9 +172,8 @@ __global__ void invert_kernel(const double *M, int F, double *M12, uint8_t *ok) 
     ok[f] = 1;
 }
 
-constexpr int WARP_BAND = 16;     // output rows per CTA
-constexpr int WARP_TX = 128, WARP_TY = 2;
-constexpr int WARP_THREADS = WARP_TX * WARP_TY;
+constexpr int WARP_BAND = 16;      // output rows per work item
+constexpr int WARP_THREADS = 256;
 
 struct WarpArgs {
     const FrameDev *frames;
@@ -185,38 +184,24 @@ struct WarpArgs {
     int F;
     uint8_t *crops;        // (F, ch, cw, 3)
     int cw, ch;
+    int bands;             // ceil(ch / WARP_BAND)
+    unsigned cw_magic;     // floor(2^32 / cw) + 1: p / cw == umulhi(p, cw_magic) for p < 2^20 (cw <= 4096)
+    int *ticket;           // [0] next work item, [1] CTAs finished (both return to 0 when the launch ends)
 };
 
-// The 6 bytes of two horizontally adjacent BGR pixels starting at p, through two aligned 64-bit loads and 32-bit
-// funnel shifts (lo = bytes 0..3, hi = bytes 4..5 in its low half) instead of six byte loads.  Caller guarantees
-// that [p & ~7, (p & ~7) + 16) is readable.
-__device__ __forceinline__ void load6_fast(const uint8_t *p, unsigned &lo, unsigned &hi) {
-    const uintptr_t ad = reinterpret_cast<uintptr_t>(p);
-    const uint2 *al = reinterpret_cast<const uint2 *>(ad & ~(uintptr_t)7);
-    const uint2 q0 = __ldg(al), q1 = __ldg(al + 1);
-    const unsigned sh = (unsigned)(ad & 7);
-    const bool up = sh >= 4;
-    const unsigned a = up ? q0.y : q0.x, b = up ? q1.x : q0.y, c = up ? q1.y : q1.x;
-    const unsigned sft = (sh & 3) * 8;
-    lo = __funnelshift_r(a, b, sft);
-    hi = __funnelshift_r(b, c, sft);
-}
-// same, from an 8-byte aligned base and a 32-bit byte offset (interior path: one 64-bit add per load pair)
-__device__ __forceinline__ void load6_off(const uint8_t *base8, unsigned off, unsigned &lo, unsigned &hi) {
-    const uint2 *al = reinterpret_cast<const uint2 *>(base8 + (off & ~7u));
-    const uint2 q0 = __ldg(al), q1 = __ldg(al + 1);
-    const bool up = (off & 4u) != 0;
-    const unsigned a = up ? q0.y : q0.x, b = up ? q1.x : q0.y, c = up ? q1.y : q1.x;
-    const unsigned sft = (off & 3u) * 8;
-    lo = __funnelshift_r(a, b, sft);
-    hi = __funnelshift_r(b, c, sft);
-}
+// The 6 bytes of two horizontally adjacent BGR pixels at byte offset `off` of an 8-byte aligned base, extracted from the
+// two aligned 64-bit words that cover them (lo = bytes 0..3, hi = bytes 4..5 in its low half).
 __device__ __forceinline__ void extract6(uint2 q0, uint2 q1, unsigned off, unsigned &lo, unsigned &hi) {
     const bool up = (off & 4u) != 0;
     const unsigned a = up ? q0.y : q0.x, b = up ? q1.x : q0.y, c = up ? q1.y : q1.x;
     const unsigned sft = (off & 3u) * 8;
     lo = __funnelshift_r(a, b, sft);
     hi = __funnelshift_r(b, c, sft);
+}
+__device__ __forceinline__ void load6_fast(const uint8_t *p, unsigned &lo, unsigned &hi) {
+    const uintptr_t ad = reinterpret_cast<uintptr_t>(p);
+    const uint2 *al = reinterpret_cast<const uint2 *>(ad & ~(uintptr_t)7);
+    extract6(__ldg(al), __ldg(al + 1), (unsigned)(ad & 7), lo, hi);
 }
 // guarded variant for the frame's first/last bytes and for single-column border taps
 __device__ __forceinline__ void load6_safe(const uint8_t *p, const uint8_t *lo_lim, const uint8_t *hi_lim, unsigned &lo, unsigned &hi) {
@@ -235,122 +220,188 @@ __device__ __forceinline__ void load6_safe(const uint8_t *p, const uint8_t *lo_l
 // OpenCV: out = (sum_ij v_ij * W_ij + 2^14) >> 15 with W_ij = a_i * b_j * 32 (a = {32-ay, ay}, b = {32-ax, ax}; the
 // 15-bit table entries are exact multiples of 32).  Integer arithmetic is exact, so the sum is evaluated separably:
 // horizontal 2-tap dot products with 6-bit weights (dp4a on the packed byte pair), then the vertical pair; and
-// (32*S + 2^14) >> 15 == (S + 512) >> 10.
-__device__ __forceinline__ void blend_store(unsigned lo0, unsigned hi0, unsigned lo1, unsigned hi1, int ax, int ay, uint8_t *o) {
+// (32*S + 2^14) >> 15 == (S + 512) >> 10.  Returns the pixel as b | g << 8 | r << 16.
+__device__ __forceinline__ unsigned blend24(unsigned lo0, unsigned hi0, unsigned lo1, unsigned hi1, int ax, int ay) {
     const unsigned wx = (unsigned)(32 - ax) | ((unsigned)ax << 8);   // bytes: [32-ax, ax, 0, 0]
     const int wy0 = 32 - ay, wy1 = ay;
     // byte pairs (tap0, tap1) per channel: b = bytes (0,3), g = (1,4), r = (2,5) of [lo | hi]
     const int hb0 = (int)__dp4a(__byte_perm(lo0, hi0, 0x7730), wx, 0u), hb1 = (int)__dp4a(__byte_perm(lo1, hi1, 0x7730), wx, 0u);
     const int hg0 = (int)__dp4a(__byte_perm(lo0, hi0, 0x7741), wx, 0u), hg1 = (int)__dp4a(__byte_perm(lo1, hi1, 0x7741), wx, 0u);
     const int hr0 = (int)__dp4a(__byte_perm(lo0, hi0, 0x7752), wx, 0u), hr1 = (int)__dp4a(__byte_perm(lo1, hi1, 0x7752), wx, 0u);
-    o[0] = (uint8_t)((hb0 * wy0 + hb1 * wy1 + 512) >> 10);
-    o[1] = (uint8_t)((hg0 * wy0 + hg1 * wy1 + 512) >> 10);
-    o[2] = (uint8_t)((hr0 * wy0 + hr1 * wy1 + 512) >> 10);
+    const unsigned ob = (unsigned)(hb0 * wy0 + hb1 * wy1 + 512) >> 10;
+    const unsigned og = (unsigned)(hg0 * wy0 + hg1 * wy1 + 512) >> 10;
+    const unsigned orr = (unsigned)(hr0 * wy0 + hr1 * wy1 + 512) >> 10;
+    return ob | (og << 8) | (orr << 16);
 }
 
-__global__ void __launch_bounds__(WARP_THREADS) warp_kernel(WarpArgs a) {
-    extern __shared__ int wsm[];
-    int *adelta = wsm;             // [cw]
-    int *bdelta = adelta + a.cw;   // [cw]
-    int *X0s = bdelta + a.cw;      // [WARP_BAND]
-    int *Y0s = X0s + WARP_BAND;    // [WARP_BAND]
-    const int tid = threadIdx.y * WARP_TX + threadIdx.x;
+// One output pixel with per-tap BORDER_CONSTANT(0) tests; X, Y are the 5-bit sub-pixel fixed-point source coordinates.
+__device__ __forceinline__ unsigned border_tap_blend(const uint8_t *data, int w, int h, int pitch, const uint8_t *lo_lim,
+                                                     const uint8_t *hi_lim, int X, int Y) {
+    unsigned lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+    const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));   // saturate_cast<short>
+    const bool inx0 = sx >= 0 && sx < w, inx1 = sx + 1 >= 0 && sx + 1 < w;
+    const bool iny0 = sy >= 0 && sy < h, iny1 = sy + 1 >= 0 && sy + 1 < h;
+    if (inx0 && inx1) {
+        const uint8_t *t0 = data + (ptrdiff_t)sy * pitch + (ptrdiff_t)sx * 3;
+        if (iny0) load6_safe(t0, lo_lim, hi_lim, lo0, hi0);
+        if (iny1) load6_safe(t0 + pitch, lo_lim, hi_lim, lo1, hi1);
+    } else if (inx0 || inx1) {  // one tap column outside the image
+        const int sxv = inx0 ? sx : sx + 1;
+        unsigned t0 = 0, t1 = 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (iny0) t0 |= (unsigned)__ldg(data + (ptrdiff_t)sy * pitch + sxv * 3 + c) << (8 * c);
+            if (iny1) t1 |= (unsigned)__ldg(data + (ptrdiff_t)(sy + 1) * pitch + sxv * 3 + c) << (8 * c);
+        }
+        if (inx0) { lo0 = t0; lo1 = t1; }              // tap 0 valid, tap 1 (bytes 3..5) zero
+        else { lo0 = t0 << 24; hi0 = t0 >> 8; lo1 = t1 << 24; hi1 = t1 >> 8; }  // tap 1 valid
+    }
+    return blend24(lo0, hi0, lo1, hi1, X & 31, Y & 31);
+}
+
+// Stores the 24-bit pixels of a warp's 32 consecutive output pixels.  packed: the 4 pixels of a lane quad (12 bytes) leave
+// as three aligned 32-bit words (one shuffle to fetch the neighbour's pixel), i.e. 96 contiguous bytes per warp
+// instruction instead of 96 single-byte stores.  Every lane of the warp must call this (shuffle), valid or not.
+__device__ __forceinline__ void store_px(uint8_t *band_out, int p, unsigned v, bool valid, bool packed) {
+    const unsigned nv = __shfl_down_sync(0xffffffffu, v, 1);
+    if (packed) {
+        const unsigned q = (unsigned)p & 3u;
+        const unsigned lo = __byte_perm(v, nv, 0x4210), hi = nv >> 8;     // 48-bit concat v | nv << 24
+        const unsigned word = __funnelshift_r(lo, hi, 8 * q);
+        if (valid && q < 3u) reinterpret_cast<unsigned *>(band_out)[3 * (p >> 2) + q] = word;
+    } else if (valid) {
+        uint8_t *o = band_out + (size_t)p * 3;
+        o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); o[2] = (uint8_t)(v >> 16);
+    }
+}
+
+struct WarpItem {
+    const uint8_t *data;
+    int w, h, pitch;
+    const uint8_t *lo_lim, *hi_lim;
+};
+
+// N rounds of WARP_THREADS consecutive output pixels starting at p0: all 4N aligned 64-bit loads of a thread are issued
+// before any is consumed (interior items: no border test anywhere in the band).
+template <int N>
+__device__ __forceinline__ void warp_rounds_interior(const WarpItem &it, const int2 *__restrict__ dxy, const int2 *__restrict__ xy0,
+                                                     int cw, unsigned cw_magic, int p0, int npix, uint8_t *band_out, bool packed) {
+    uint2 q[N][4];
+    unsigned off[N];
+    int axy[N];
+    const unsigned pitch = (unsigned)it.pitch;
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        const int p = min(p0 + u * WARP_THREADS, npix - 1);
+        const int row = cw_magic ? (int)__umulhi((unsigned)p, cw_magic) : p, x = p - row * cw;
+        const int2 d = dxy[x], r0 = xy0[row];
+        const int X = (int)((unsigned)r0.x + (unsigned)d.x) >> 5, Y = (int)((unsigned)r0.y + (unsigned)d.y) >> 5;
+        axy[u] = (X & 31) | ((Y & 31) << 8);
+        off[u] = (unsigned)(Y >> 5) * pitch + (unsigned)(X >> 5) * 3u;
+        const uint2 *r0p = reinterpret_cast<const uint2 *>(it.data + (off[u] & ~7u));
+        const uint2 *r1p = reinterpret_cast<const uint2 *>(it.data + ((off[u] + pitch) & ~7u));
+        q[u][0] = __ldg(r0p); q[u][1] = __ldg(r0p + 1);
+        q[u][2] = __ldg(r1p); q[u][3] = __ldg(r1p + 1);
+    }
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        const int p = p0 + u * WARP_THREADS;
+        unsigned lo0, hi0, lo1, hi1;
+        extract6(q[u][0], q[u][1], off[u], lo0, hi0);
+        extract6(q[u][2], q[u][3], off[u] + pitch, lo1, hi1);
+        const unsigned v = blend24(lo0, hi0, lo1, hi1, axy[u] & 31, axy[u] >> 8);
+        store_px(band_out, p, v, p < npix, packed);
+    }
+}
+
+// one round with per-tap BORDER_CONSTANT tests (items that touch the frame border, unaligned or > 2 GB frames)
+__device__ __forceinline__ void warp_round_border(const WarpItem &it, const int2 *__restrict__ dxy, const int2 *__restrict__ xy0, int cw,
+                                                  unsigned cw_magic, int p0, int npix, uint8_t *band_out, bool packed) {
+    const int p = min(p0, npix - 1);
+    const int row = cw_magic ? (int)__umulhi((unsigned)p, cw_magic) : p, x = p - row * cw;
+    const int2 d = dxy[x], r0 = xy0[row];
+    const int X = (int)((unsigned)r0.x + (unsigned)d.x) >> 5, Y = (int)((unsigned)r0.y + (unsigned)d.y) >> 5;
+    const unsigned v = border_tap_blend(it.data, it.w, it.h, it.pitch, it.lo_lim, it.hi_lim, X, Y);
+    store_px(band_out, p0, v, p0 < npix, packed);
+}
+
+// Persistent kernel: the grid fills the GPU once; work items (face, band of 16 output rows) are handed out through an
+// atomic ticket so big faces (more DRAM per item) do not leave a tail.  The next ticket is fetched while the current
+// item is being processed.  Lanes = consecutive output pixels of the band (row-major), so one load instruction's lanes
+// share cache lines and one store instruction writes 96 contiguous bytes.
+__global__ void __launch_bounds__(WARP_THREADS, 4) warp_kernel(WarpArgs a) {
+    extern __shared__ int2 wsm[];
+    int2 *dxy = wsm;             // [cw]  (adelta, bdelta)
+    int2 *xy0 = dxy + a.cw;      // [WARP_BAND]  (X0, Y0) per row
+    __shared__ int s_item[2];
+    const int tid = threadIdx.x;
     const int F = a.count_dev ? min(*a.count_dev, a.F) : a.F;
-    const int band_y0 = blockIdx.x * WARP_BAND;
-    const int rows = min(WARP_BAND, a.ch - band_y0);
-    for (int f = blockIdx.y; f < F; f += gridDim.y) {
-        uint8_t *crop = a.crops + (size_t)f * a.ch * a.cw * 3;
-        if (!a.ok[f]) {
-            for (int p = tid; p < rows * a.cw * 3; p += WARP_THREADS) crop[(size_t)band_y0 * a.cw * 3 + p] = 0;
+    const int n_items = F * a.bands;
+    if (tid == 0) s_item[0] = atomicAdd(a.ticket, 1);
+    __syncthreads();
+    for (int par = 0;; par ^= 1) {
+        const int item = s_item[par];
+        if (item >= n_items) break;
+        if (tid == 0) s_item[par ^ 1] = atomicAdd(a.ticket, 1);
+        const int f = item / a.bands, band_y0 = (item - f * a.bands) * WARP_BAND;
+        const int rows = min(WARP_BAND, a.ch - band_y0);
+        const int npix = rows * a.cw;
+        uint8_t *band_out = a.crops + ((size_t)f * a.ch + band_y0) * a.cw * 3;
+        const bool packed = (reinterpret_cast<uintptr_t>(band_out) & 3) == 0 && (npix & 3) == 0;
+        if (!a.ok[f]) {   // estimation failed: zero crop (uniform over the CTA)
+            for (int p = tid; p < npix * 3; p += WARP_THREADS) band_out[p] = 0;
+            __syncthreads();
             continue;
         }
         const FrameDev fr = a.frames[a.frame_idx ? a.frame_idx[f] : 0];
         const double *iM = a.M12 + (size_t)f * 12 + 6;
         const double i0 = iM[0], i1 = iM[1], i2 = iM[2], i3 = iM[3], i4 = iM[4], i5 = iM[5];
-        __syncthreads();  // previous face's tables are no longer read
-        for (int x = tid; x < a.cw; x += WARP_THREADS) {
-            adelta[x] = __double2int_rn(i0 * x * 1024);  // saturate_cast<int>(M[0]*x*AB_SCALE)
-            bdelta[x] = __double2int_rn(i3 * x * 1024);
-        }
-        if (tid < rows) {
-            const int y = band_y0 + tid;
-            X0s[tid] = __double2int_rn((i1 * y + i2) * 1024) + 16;  // + round_delta
-            Y0s[tid] = __double2int_rn((i4 * y + i5) * 1024) + 16;
+        for (int x = tid; x < a.cw; x += WARP_THREADS)   // saturate_cast<int>(M[0]*x*AB_SCALE), AB_SCALE = 1024
+            dxy[x] = make_int2(__double2int_rn(i0 * x * 1024), __double2int_rn(i3 * x * 1024));
+        if (tid >= WARP_THREADS - WARP_BAND) {
+            const int r = tid - (WARP_THREADS - WARP_BAND), y = band_y0 + min(r, rows - 1);
+            xy0[r] = make_int2(__double2int_rn((i1 * y + i2) * 1024) + 16, __double2int_rn((i4 * y + i5) * 1024) + 16);  // + round_delta
         }
         __syncthreads();
         // The map is affine, so the tap coordinates of the band are extremal at its 4 corners: if all 4 corner taps
         // (and their +1 neighbours) are interior, no pixel of the band needs a border test.
-        bool interior = (reinterpret_cast<uintptr_t>(fr.data) & 7) == 0 && (fr.pitch & 7) == 0 && fr.pitch >= 16;
+        bool interior = (reinterpret_cast<uintptr_t>(fr.data) & 7) == 0 && (fr.pitch & 7) == 0 && fr.pitch >= 16 &&
+                        (size_t)fr.h * fr.pitch < 0x7fffffffull;
         {
             const int xs[2] = {0, a.cw - 1}, ys[2] = {0, rows - 1};
 #pragma unroll
             for (int cy = 0; cy < 2; ++cy)
 #pragma unroll
                 for (int cx = 0; cx < 2; ++cx) {
-                    const long long Xl = (long long)X0s[ys[cy]] + adelta[xs[cx]], Yl = (long long)Y0s[ys[cy]] + bdelta[xs[cx]];
+                    const long long Xl = (long long)xy0[ys[cy]].x + dxy[xs[cx]].x, Yl = (long long)xy0[ys[cy]].y + dxy[xs[cx]].y;
                     const long long sx = Xl >> 10, sy = Yl >> 10;
                     interior = interior && sx >= 0 && sx + 1 < fr.w && sy >= 0 && sy + 1 < fr.h - 1;  // not the last row: 16-byte over-read
                 }
         }
-        const uint8_t *lo_lim = fr.data, *hi_lim = fr.data + (size_t)(fr.h - 1) * fr.pitch + (size_t)fr.w * 3;  // end of valid pixel bytes
-        // lanes = consecutive output pixels of one row, so the lanes of one load instruction share cache lines
-        const bool small_frame = (size_t)fr.h * fr.pitch < 0x7fffffffull;
-        for (int x = threadIdx.x; x < a.cw; x += WARP_TX) {
-            const unsigned adx = (unsigned)adelta[x], bdx = (unsigned)bdelta[x];
-            uint8_t *o = crop + ((size_t)(band_y0 + threadIdx.y) * a.cw + x) * 3;
-            const size_t ostep = (size_t)WARP_TY * a.cw * 3;
-            if (interior && small_frame) {
-                const unsigned pitch = (unsigned)fr.pitch;
-                // two output rows per step: their 8 aligned 64-bit loads are issued before any is consumed
-                for (int ry = threadIdx.y; ry < rows; ry += 2 * WARP_TY, o += 2 * ostep) {
-                    const int ryb = min(ry + WARP_TY, rows - 1);
-                    const bool two = ry + WARP_TY < rows;
-                    const int Xa = (int)((unsigned)X0s[ry] + adx) >> 5, Ya = (int)((unsigned)Y0s[ry] + bdx) >> 5;
-                    const int Xb = (int)((unsigned)X0s[ryb] + adx) >> 5, Yb = (int)((unsigned)Y0s[ryb] + bdx) >> 5;
-                    const unsigned offa = (unsigned)(Ya >> 5) * pitch + (unsigned)(Xa >> 5) * 3u;
-                    const unsigned offb = (unsigned)(Yb >> 5) * pitch + (unsigned)(Xb >> 5) * 3u;
-                    const uint2 *pa0 = reinterpret_cast<const uint2 *>(fr.data + (offa & ~7u));
-                    const uint2 *pa1 = reinterpret_cast<const uint2 *>(fr.data + ((offa + pitch) & ~7u));
-                    const uint2 *pb0 = reinterpret_cast<const uint2 *>(fr.data + (offb & ~7u));
-                    const uint2 *pb1 = reinterpret_cast<const uint2 *>(fr.data + ((offb + pitch) & ~7u));
-                    const uint2 qa0 = __ldg(pa0), qa1 = __ldg(pa0 + 1), qa2 = __ldg(pa1), qa3 = __ldg(pa1 + 1);
-                    const uint2 qb0 = __ldg(pb0), qb1 = __ldg(pb0 + 1), qb2 = __ldg(pb1), qb3 = __ldg(pb1 + 1);
-                    unsigned lo0, hi0, lo1, hi1;
-                    extract6(qa0, qa1, offa, lo0, hi0);
-                    extract6(qa2, qa3, offa + pitch, lo1, hi1);
-                    blend_store(lo0, hi0, lo1, hi1, Xa & 31, Ya & 31, o);
-                    if (two) {
-                        extract6(qb0, qb1, offb, lo0, hi0);
-                        extract6(qb2, qb3, offb + pitch, lo1, hi1);
-                        blend_store(lo0, hi0, lo1, hi1, Xb & 31, Yb & 31, o + ostep);
-                    }
-                }
-                continue;
+        WarpItem it;
+        it.data = fr.data; it.w = fr.w; it.h = fr.h; it.pitch = fr.pitch;
+        it.lo_lim = fr.data;
+        it.hi_lim = fr.data + (size_t)(fr.h - 1) * fr.pitch + (size_t)fr.w * 3;  // end of valid pixel bytes
+        int p0 = tid;
+        if (interior) {
+            int rounds = (npix + WARP_THREADS - 1) / WARP_THREADS;
+            while (rounds > 0) {
+                if (rounds >= 4) { warp_rounds_interior<4>(it, dxy, xy0, a.cw, a.cw_magic, p0, npix, band_out, packed); rounds -= 4; p0 += 4 * WARP_THREADS; }
+                else if (rounds == 3) { warp_rounds_interior<3>(it, dxy, xy0, a.cw, a.cw_magic, p0, npix, band_out, packed); rounds = 0; }
+                else if (rounds == 2) { warp_rounds_interior<2>(it, dxy, xy0, a.cw, a.cw_magic, p0, npix, band_out, packed); rounds = 0; }
+                else { warp_rounds_interior<1>(it, dxy, xy0, a.cw, a.cw_magic, p0, npix, band_out, packed); rounds = 0; }
             }
-            for (int ry = threadIdx.y; ry < rows; ry += WARP_TY, o += ostep) {
-                const int X = (int)((unsigned)X0s[ry] + adx) >> 5, Y = (int)((unsigned)Y0s[ry] + bdx) >> 5;
-                const int ax = X & 31, ay = Y & 31;
-                unsigned lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
-                const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
-                const bool inx0 = sx >= 0 && sx < fr.w, inx1 = sx + 1 >= 0 && sx + 1 < fr.w;
-                const bool iny0 = sy >= 0 && sy < fr.h, iny1 = sy + 1 >= 0 && sy + 1 < fr.h;
-                if (inx0 && inx1) {
-                    const uint8_t *p0 = fr.data + (ptrdiff_t)sy * fr.pitch + (ptrdiff_t)sx * 3;
-                    if (iny0) load6_safe(p0, lo_lim, hi_lim, lo0, hi0);
-                    if (iny1) load6_safe(p0 + fr.pitch, lo_lim, hi_lim, lo1, hi1);
-                } else if (inx0 || inx1) {  // one tap column outside the image (BORDER_CONSTANT 0)
-                    const int sxv = inx0 ? sx : sx + 1;
-                    unsigned t0 = 0, t1 = 0;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        if (iny0) t0 |= (unsigned)__ldg(fr.data + (ptrdiff_t)sy * fr.pitch + sxv * 3 + c) << (8 * c);
-                        if (iny1) t1 |= (unsigned)__ldg(fr.data + (ptrdiff_t)(sy + 1) * fr.pitch + sxv * 3 + c) << (8 * c);
-                    }
-                    if (inx0) { lo0 = t0; lo1 = t1; }              // tap 0 valid, tap 1 (bytes 3..5) zero
-                    else { lo0 = t0 << 24; hi0 = t0 >> 8; lo1 = t1 << 24; hi1 = t1 >> 8; }  // tap 1 valid
-                }
-                blend_store(lo0, hi0, lo1, hi1, ax, ay, o);
-            }
+        } else {
+            for (; p0 - tid < npix; p0 += WARP_THREADS) warp_round_border(it, dxy, xy0, a.cw, a.cw_magic, p0, npix, band_out, packed);
+        }
+        __syncthreads();  // tables and s_item[par] are free again
+    }
+    if (tid == 0) {  // the last CTA to leave re-arms the ticket for the next launch on this ctx
+        __threadfence();
+        if (atomicAdd(a.ticket + 1, 1) == (int)gridDim.x - 1) {
+            a.ticket[0] = 0;
+            a.ticket[1] = 0;
+            __threadfence();
         }
     }
 }
@@ -364,6 +415,131 @@ static int lmeds_niters(double p, double ep, int modelPoints, int maxIters) {  /
     num = std::log(num);
     denom = std::log(denom);
     return denom >= 0 || -num >= maxIters * (-denom) ? maxIters : (int)std::lrint(num / denom);
+}
+
+// ---- fixed-size fast path (the reference's 112x112 ArcFace crop, config.rs:45) --------------------------------------
+// Same persistent/ticket structure; a CTA is 2 output rows x CW columns, so a thread keeps ONE column for the whole item:
+// its (adelta, bdelta) live in registers, no index division, and the packed-store word address advances by a constant.
+// An item is IR output rows (IR/2 rounds per thread); the per-row (X0, Y0) table is double-buffered so one barrier per
+// item is enough, and that barrier also carries the band's interior vote (4 threads evaluate the 4 corners).
+template <int CW, int N>
+__device__ __forceinline__ void fixed_rounds_interior(const uint8_t *__restrict__ data, unsigned pitch, int2 d, const int2 *__restrict__ xy,
+                                                      unsigned *__restrict__ outw, bool store) {
+    uint2 q[N][4];
+    unsigned off[N];
+    int axy[N];
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        const int2 r0 = xy[2 * u];
+        const int X = (int)((unsigned)r0.x + (unsigned)d.x) >> 5, Y = (int)((unsigned)r0.y + (unsigned)d.y) >> 5;
+        axy[u] = (X & 31) | ((Y & 31) << 8);
+        off[u] = (unsigned)(Y >> 5) * pitch + (unsigned)(X >> 5) * 3u;
+        const uint2 *r0p = reinterpret_cast<const uint2 *>(data + (off[u] & ~7u));
+        const uint2 *r1p = reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(r0p) + pitch);   // pitch % 8 == 0
+        q[u][0] = __ldg(r0p); q[u][1] = __ldg(r0p + 1);
+        q[u][2] = __ldg(r1p); q[u][3] = __ldg(r1p + 1);
+    }
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        // both rows share the byte phase (pitch % 8 == 0)
+        const bool up = (off[u] & 4u) != 0;
+        const unsigned sft = (off[u] & 3u) * 8;
+        const unsigned a0 = up ? q[u][0].y : q[u][0].x, b0 = up ? q[u][1].x : q[u][0].y, c0 = up ? q[u][1].y : q[u][1].x;
+        const unsigned a1 = up ? q[u][2].y : q[u][2].x, b1 = up ? q[u][3].x : q[u][2].y, c1 = up ? q[u][3].y : q[u][3].x;
+        const unsigned v = blend24(__funnelshift_r(a0, b0, sft), __funnelshift_r(b0, c0, sft), __funnelshift_r(a1, b1, sft),
+                                   __funnelshift_r(b1, c1, sft), axy[u] & 31, axy[u] >> 8);
+        const unsigned nv = __shfl_down_sync(0xffffffffu, v, 1);
+        const unsigned word = __funnelshift_r(__byte_perm(v, nv, 0x4210), nv >> 8, 8 * (threadIdx.x & 3u));
+        if (store) outw[u * (2 * CW * 3 / 4)] = word;
+    }
+}
+
+template <int CW, int CH, int IR, int UN>
+__global__ void __launch_bounds__(2 * CW) warp_fixed_kernel(WarpArgs a) {
+    constexpr int T = 2 * CW, ITEMS = CH / IR, ROUNDS = IR / 2;
+    static_assert(CH % IR == 0 && IR % 2 == 0 && T % 32 == 0 && (2 * CW * 3) % 4 == 0 && (IR * CW * 3) % 4 == 0, "fixed warp geometry");
+    __shared__ int2 xy0[2][IR];
+    __shared__ int s_item[2];
+    const int tid = threadIdx.x;
+    const int r = tid / CW, x = tid - r * CW;
+    const int F = a.count_dev ? min(*a.count_dev, a.F) : a.F;
+    const int n_items = F * ITEMS;
+    if (tid == 0) s_item[0] = atomicAdd(a.ticket, 1);
+    __syncthreads();
+    for (int par = 0;; par ^= 1) {
+        const int item = s_item[par];
+        if (item >= n_items) break;
+        if (tid == 0) s_item[par ^ 1] = atomicAdd(a.ticket, 1);
+        const int f = item / ITEMS, y0 = (item - f * ITEMS) * IR;
+        uint8_t *band_out = a.crops + ((size_t)f * CH + y0) * CW * 3;
+        const bool okf = a.ok[f] != 0;
+        const FrameDev *frp = a.frames + (a.frame_idx ? a.frame_idx[f] : 0);
+        const uint8_t *data = frp->data;
+        const int fw = frp->w, fh = frp->h, pitch = frp->pitch;
+        int2 d = make_int2(0, 0);
+        bool vote = true;
+        if (okf) {
+            const double *iM = a.M12 + (size_t)f * 12 + 6;
+            const double i0 = iM[0], i3 = iM[3];
+            d = make_int2(__double2int_rn(i0 * x * 1024), __double2int_rn(i3 * x * 1024));   // adelta[x], bdelta[x]
+            if (tid < IR || tid >= T - 4) {
+                const double i1 = iM[1], i2 = iM[2], i4 = iM[4], i5 = iM[5];
+                if (tid < IR) {
+                    const int y = y0 + tid;
+                    xy0[par][tid] = make_int2(__double2int_rn((i1 * y + i2) * 1024) + 16, __double2int_rn((i4 * y + i5) * 1024) + 16);
+                } else {   // one corner of the item each: the affine map's tap coordinates are extremal there
+                    const int c = tid - (T - 4), cx = (c & 1) ? CW - 1 : 0, y = y0 + ((c & 2) ? IR - 1 : 0);
+                    const long long Xl = (long long)(__double2int_rn((i1 * y + i2) * 1024) + 16) + __double2int_rn(i0 * cx * 1024);
+                    const long long Yl = (long long)(__double2int_rn((i4 * y + i5) * 1024) + 16) + __double2int_rn(i3 * cx * 1024);
+                    const long long sx = Xl >> 10, sy = Yl >> 10;
+                    vote = sx >= 0 && sx + 1 < fw && sy >= 0 && sy + 1 < fh - 1;   // not the last row: 16-byte over-read
+                }
+            }
+        }
+        const bool interior = __syncthreads_and(vote) && (reinterpret_cast<uintptr_t>(data) & 7) == 0 && (pitch & 7) == 0 && pitch >= 16 &&
+                              (size_t)fh * pitch < 0x7fffffffull;
+        if (!okf) {   // estimation failed: zero crop
+            for (int p = tid; p < IR * CW * 3 / 4; p += T) reinterpret_cast<unsigned *>(band_out)[p] = 0u;
+            continue;
+        }
+        const int2 *xy = &xy0[par][r];
+        const bool store = (tid & 3) != 3;
+        unsigned *outw = reinterpret_cast<unsigned *>(band_out) + 3 * (tid >> 2) + (tid & 3);
+        if (interior) {
+            int u = 0;
+#pragma unroll 1
+            for (; u + UN <= ROUNDS; u += UN)
+                fixed_rounds_interior<CW, UN>(data, (unsigned)pitch, d, xy + 2 * u, outw + u * (T * 3 / 4), store);
+            constexpr int REM = ROUNDS % UN;
+            if (REM) fixed_rounds_interior<CW, REM ? REM : 1>(data, (unsigned)pitch, d, xy + 2 * (ROUNDS - REM), outw + (ROUNDS - REM) * (T * 3 / 4), store);
+        } else {
+            const uint8_t *lo_lim = data, *hi_lim = data + (size_t)(fh - 1) * pitch + (size_t)fw * 3;  // end of valid pixel bytes
+            for (int u = 0; u < ROUNDS; ++u) {
+                const int2 r0 = xy[2 * u];
+                const int X = (int)((unsigned)r0.x + (unsigned)d.x) >> 5, Y = (int)((unsigned)r0.y + (unsigned)d.y) >> 5;
+                const unsigned v = border_tap_blend(data, fw, fh, pitch, lo_lim, hi_lim, X, Y);
+                const unsigned nv = __shfl_down_sync(0xffffffffu, v, 1);
+                const unsigned word = __funnelshift_r(__byte_perm(v, nv, 0x4210), nv >> 8, 8 * (tid & 3u));
+                if (store) outw[u * (T * 3 / 4)] = word;
+            }
+        }
+    }
+    if (tid == 0) {  // the last CTA to leave re-arms the ticket for the next launch on this ctx
+        __threadfence();
+        if (atomicAdd(a.ticket + 1, 1) == (int)gridDim.x - 1) {
+            a.ticket[0] = 0;
+            a.ticket[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+// zero-initialised work tickets of the persistent kernels (each launch leaves them at zero again)
+static int ticket_buffer(fd_ctx *ctx) {
+    if (ctx->tickets.p) return FD_OK;
+    FD_TRY(ctx->tickets.reserve(sizeof(int) * 16));
+    FD_CUDA(cudaMemsetAsync(ctx->tickets.p, 0, sizeof(int) * 16, ctx->stream));
+    return FD_OK;
 }
 
 // from_dev (F,10); to_dev (F,10) or nullptr (ctx template).  count_dev optional device-side face count (<= F_cap).
@@ -417,11 +593,29 @@ int warp_launch(fd_ctx *ctx, const FrameDev *frames_dev, const int32_t *frame_id
     a.crops = crops_dev;
     a.cw = cw;
     a.ch = ch;
-    const int bands = (ch + WARP_BAND - 1) / WARP_BAND;
-    // device-side counts: a bounded grid that strides over the faces
-    int gy = count_dev ? std::min(F_cap, std::max(1, ctx->num_sms * 8 / bands)) : std::min(F_cap, 65535);
-    size_t smem = sizeof(int) * (2 * (size_t)cw + 2 * WARP_BAND);
-    warp_kernel<<<dim3(bands, gy), dim3(WARP_TX, WARP_TY), smem, ctx->stream>>>(a);
+    a.bands = (ch + WARP_BAND - 1) / WARP_BAND;
+    a.cw_magic = cw > 1 ? (unsigned)((1ull << 32) / (unsigned)cw + 1ull) : 0u;
+    FD_TRY(ticket_buffer(ctx));
+    a.ticket = ctx->tickets.as<int>();
+    if (cw == 112 && ch == 112 && (reinterpret_cast<uintptr_t>(crops_dev) & 3) == 0) {
+        // 14-row items (8 per face, 7 rounds per thread as 4 + 3): small enough that the last items of a launch leave
+        // no long tail (28 rows: +10 % time), large enough to amortise the per-item setup (8 rows: same time, 4: +8 %).
+        constexpr int IR = 14;
+        void (*kern)(WarpArgs) = warp_fixed_kernel<112, 112, IR, 4>;
+        static int per_sm_fixed = 0;
+        if (!per_sm_fixed) FD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fixed, kern, 224, 0));
+        const long long items = (long long)F_cap * (112 / IR);
+        const int grid = (int)std::min<long long>(items, (long long)ctx->num_sms * std::max(per_sm_fixed, 1));
+        kern<<<grid, 224, 0, ctx->stream>>>(a);
+        FD_LAUNCH_CHECK(ctx);
+        return FD_OK;
+    }
+    const size_t smem = sizeof(int2) * ((size_t)cw + WARP_BAND);
+    int per_sm = 0;
+    FD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, warp_kernel, WARP_THREADS, smem));
+    const long long items = (long long)F_cap * a.bands;
+    const int grid = (int)std::min<long long>(items, (long long)ctx->num_sms * std::max(per_sm, 1));
+    warp_kernel<<<grid, WARP_THREADS, smem, ctx->stream>>>(a);
     FD_LAUNCH_CHECK(ctx);
     return FD_OK;
 }

@@ -102,6 +102,7 @@ struct fd_ctx {
     fd::DevBuf out_frame_idx;    // int[total]
     fd::DevBuf align_M;          // double[F][12] (M, inverse)
     fd::DevBuf align_ok;         // u8[F]
+    fd::DevBuf tickets;          // int[16] work tickets of the persistent kernels (zero between launches)
     fd::DevBuf nms_ws[8];        // big-path workspaces
     fd::DevBuf nms_ws_sp[4];     // spatial big-path workspaces
     fd::DevBuf pipe_frames;      // host pipeline: device copies of frames

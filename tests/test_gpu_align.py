@@ -56,6 +56,19 @@ def test_warp_bit_exact_vs_oracle(ctx, oracle, h, w):
         np.testing.assert_array_equal(ctx.warp_affine(img, M, (112, 112)), oracle.warp_affine(img, M, (112, 112)))
 
 
+@pytest.mark.parametrize("dsize", [(96, 80), (1, 5), (7, 1), (200, 131), (113, 112), (256, 256), (1024, 3)])
+def test_warp_other_crop_sizes(ctx, oracle, dsize):
+    """crop sizes other than the reference's 112x112 take the generic kernel (flattened bands, byte or packed stores)"""
+    rng = np.random.default_rng(dsize[0] * 1000 + dsize[1])
+    img = rng.integers(0, 256, (360, 500, 3), dtype=np.uint8)
+    for t in range(3):
+        s, th = rng.uniform(0.3, 2.5), rng.uniform(-0.7, 0.7)
+        a, b = s * np.cos(th), s * np.sin(th)
+        cx, cy = rng.uniform(-20, 520), rng.uniform(-20, 380)
+        M = np.array([[a, -b, dsize[0] / 2 - (a * cx - b * cy)], [b, a, dsize[1] / 2 - (b * cx + a * cy)]], np.float64)
+        np.testing.assert_array_equal(ctx.warp_affine(img, M, dsize), oracle.warp_affine(img, M, dsize))
+
+
 def test_align_single_call(ctx, oracle):
     from rs_face_detection_b200.pipeline import FaceAlignment
     img = synth.make_frame(720, 1280, 5)
