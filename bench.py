@@ -380,6 +380,46 @@ def run_ours(args):
         ctx.synchronize()
         return a.elapsed_time(b) / n * 1e3   # us
 
+    # ---- per-kernel device times (the ABI's per-launch CUDA events on the ctx stream, separate untimed loop) and their
+    #      algorithmic bytes: preprocess 7,680,000 B/frame; decode 1,008,000 B/image + 64 B/candidate;
+    #      warp min(frame, 3*112^2/|det M|) + 37,632 B/face ----
+    kernels = None
+    if not args.no_stages:
+        import ctypes as C
+        peak_k, _ = measured_peak_gbs()
+        Md = ctx.alloc(cap_faces * 48)
+        okd = ctx.alloc(cap_faces)
+        ctx.align_detections(frames_l, crops_t, cap_faces, Md, okd)
+        ctx.synchronize()
+        Mh = Md.download((cap_faces, 2, 3), np.float64)[:faces_per_step]
+        okh = okd.download((cap_faces,), np.uint8)[:faces_per_step]
+        detM = np.abs(Mh[:, 0, 0] * Mh[:, 1, 1] - Mh[:, 0, 1] * Mh[:, 1, 0])
+        foot = np.where(okh > 0, np.minimum(FRAME_H * FRAME_W * 3.0, 3.0 * 112 * 112 / np.maximum(detM, 1e-12)), 0.0)
+        warp_bytes = float(foot.sum() + 37632.0 * faces_per_step)
+        view = ctx.detect_view()
+        Kc = np.empty(BATCH, np.int32)
+        ctx.lib.fd_memcpy_d2h(ctx.handle, Kc.ctypes.data_as(C.c_void_p), C.c_void_p(view.candidates_dev), C.c_size_t(4 * BATCH))
+        decode_bytes = 1008000.0 * BATCH + 64.0 * float(Kc.sum())
+        nprof = 20
+        ctx.profile(True)
+        for _ in range(nprof):
+            step()
+        prof = ctx.profile_fetch()
+        ctx.profile(False)
+        alg = {"preprocess_tma_kernel": PRE_BYTES_PER_FRAME * BATCH, "preprocess_kernel": PRE_BYTES_PER_FRAME * BATCH,
+               "decode_kernel": decode_bytes, "warp_fixed_kernel": warp_bytes, "warp_kernel": warp_bytes}
+        kernels = {}
+        for name, (n, us) in prof.items():
+            ent = {"launches_per_step": n / nprof, "us_per_launch": us / max(n, 1)}
+            if name in alg:
+                gbs = alg[name] / (us / max(n, 1) * 1e-6) / 1e9
+                ent.update({"algorithmic_bytes": alg[name], "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak_k, "bound": "hbm"})
+            else:
+                ent["bound"] = "latency / SM issue"
+            kernels[name] = ent
+        kernels["_note"] = ("us_per_launch = gap between consecutive per-launch CUDA events on the ctx stream (kernel + launch gap) over %d serial steps; "
+                            "candidates/step=%d, faces/step=%d" % (nprof, int(Kc.sum()), faces_per_step))
+
     ds = ctx.preprocess_batch(frames_l, tensor_t)
     stages = None if args.no_stages else {
         "preprocess_us": time_stage(lambda: ctx.preprocess_batch(frames_l, tensor_t)),
@@ -496,6 +536,7 @@ def run_ours(args):
                          "share_of_step": pre_ms * args.steps / (secs * 1e3)},
             "cpu_baseline": cpu_baseline,
             "stages": stages,
+            "kernels": kernels,
             "pipelined": pipelined,
         }
         extra.update(nms_extra)

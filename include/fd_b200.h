@@ -71,6 +71,12 @@ int fd_ctx_synchronize(fd_ctx *ctx);
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 int fd_ctx_launch_count(const fd_ctx *ctx, int64_t *out);
 
+/* Per-kernel device timing for the bench harness: while enabled, every kernel launch of this ctx is followed by a CUDA
+ * event on the ctx stream; fd_ctx_profile_fetch synchronises and writes one line per kernel, "name launches total_us",
+ * where a launch's time is the gap since the previous launch's event (kernel + launch gap).  Not for production use. */
+int fd_ctx_profile(fd_ctx *ctx, int enable);
+int fd_ctx_profile_fetch(fd_ctx *ctx, char *buf, size_t cap);
+
 /* ---- memory helpers (so a host language needs no CUDA binding of its own) --------------------------- */
 int fd_dev_alloc(fd_ctx *ctx, size_t bytes, void **out);
 int fd_dev_free(fd_ctx *ctx, void *ptr);

@@ -569,7 +569,7 @@ int estimate_launch(fd_ctx *ctx, const float *from_dev, const float *to_dev, con
     a.ok = ok_dev;
     a.ok_out = ok_out_dev;
     estimate_kernel<<<(F_cap * EST_LANES + 127) / 128, 128, 0, ctx->stream>>>(a);
-    FD_LAUNCH_CHECK(ctx);
+    FD_LAUNCH_CHECK_NAMED(ctx, "estimate_kernel");
     return FD_OK;
 }
 
@@ -607,7 +607,7 @@ int warp_launch(fd_ctx *ctx, const FrameDev *frames_dev, const int32_t *frame_id
         const long long items = (long long)F_cap * (112 / IR);
         const int grid = (int)std::min<long long>(items, (long long)ctx->num_sms * std::max(per_sm_fixed, 1));
         kern<<<grid, 224, 0, ctx->stream>>>(a);
-        FD_LAUNCH_CHECK(ctx);
+        FD_LAUNCH_CHECK_NAMED(ctx, "warp_fixed_kernel");
         return FD_OK;
     }
     const size_t smem = sizeof(int2) * ((size_t)cw + WARP_BAND);
@@ -616,7 +616,7 @@ int warp_launch(fd_ctx *ctx, const FrameDev *frames_dev, const int32_t *frame_id
     const long long items = (long long)F_cap * a.bands;
     const int grid = (int)std::min<long long>(items, (long long)ctx->num_sms * std::max(per_sm, 1));
     warp_kernel<<<grid, WARP_THREADS, smem, ctx->stream>>>(a);
-    FD_LAUNCH_CHECK(ctx);
+    FD_LAUNCH_CHECK_NAMED(ctx, "warp_kernel");
     return FD_OK;
 }
 

@@ -52,12 +52,23 @@ void PinnedBuf::release() {
     cap = 0;
 }
 
-void trace_mark(fd_ctx *ctx, const char *file, int line) {
+// A mark = event recorded right after a launch; the time attributed to the launch is the gap since the previous
+// mark on the same stream (kernel + its launch gap), which is what a serial step pays for it.
+void trace_mark(fd_ctx *ctx, const char *file, int line, const char *name) {
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return;
     cudaEventRecord(e, ctx->stream);
-    const char *base = strrchr(file, '/');
-    ctx->trace.emplace_back(std::string(base ? base + 1 : file) + ":" + std::to_string(line), e);
+    std::string key;
+    if (name) key = name;
+    else {
+        const char *base = strrchr(file, '/');
+        key = std::string(base ? base + 1 : file) + ":" + std::to_string(line);
+    }
+    ctx->trace.emplace_back(key, e);
+}
+static void trace_clear(fd_ctx *ctx) {
+    for (auto &t : ctx->trace) cudaEventDestroy(t.second);
+    ctx->trace.clear();
 }
 static void trace_dump(fd_ctx *ctx) {
     if (ctx->trace.size() < 2) return;
@@ -67,8 +78,7 @@ static void trace_dump(fd_ctx *ctx) {
         cudaEventElapsedTime(&ms, ctx->trace[i - 1].second, ctx->trace[i].second);
         fprintf(stderr, "[fd trace] %-28s +%8.1f us\n", ctx->trace[i].first.c_str(), ms * 1e3f);
     }
-    for (auto &t : ctx->trace) cudaEventDestroy(t.second);
-    ctx->trace.clear();
+    trace_clear(ctx);
 }
 
 int check_ctx(const fd_ctx *ctx) {
@@ -307,7 +317,48 @@ FD_EXPORT int fd_ctx_synchronize(fd_ctx *ctx) {
     FD_TRY(check_ctx(ctx));
     FD_CUDA(cudaStreamSynchronize(ctx->stream));
     FD_CUDA(cudaStreamSynchronize(ctx->stream2));
-    if (ctx->trace_on) trace_dump(ctx);
+    if (ctx->trace_on && !ctx->profile_on) trace_dump(ctx);
+    return FD_OK;
+}
+
+// ---- per-kernel profile through the ABI (bench.py's per-kernel roofline lines) -----------------------------------------
+FD_EXPORT int fd_ctx_profile(fd_ctx *ctx, int enable) {
+    FD_TRY(check_ctx(ctx));
+    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    trace_clear(ctx);
+    ctx->profile_on = enable != 0;
+    ctx->trace_on = ctx->profile_on || (getenv("FD_TRACE") != nullptr && getenv("FD_TRACE")[0] == '1');
+    if (ctx->profile_on) trace_mark(ctx, __FILE__, __LINE__, "(begin)");
+    return FD_OK;
+}
+FD_EXPORT int fd_ctx_profile_fetch(fd_ctx *ctx, char *buf, size_t cap) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(buf && cap > 0, "fd_ctx_profile_fetch: bad buffer");
+    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<std::string> names;
+    std::vector<double> tot;
+    std::vector<int> cnt;
+    for (size_t i = 1; i < ctx->trace.size(); ++i) {
+        float ms = 0.f;
+        FD_CUDA(cudaEventElapsedTime(&ms, ctx->trace[i - 1].second, ctx->trace[i].second));
+        const std::string &k = ctx->trace[i].first;
+        if (k == "(begin)") continue;
+        size_t j = 0;
+        while (j < names.size() && names[j] != k) ++j;
+        if (j == names.size()) { names.push_back(k); tot.push_back(0); cnt.push_back(0); }
+        tot[j] += ms * 1e3;
+        cnt[j] += 1;
+    }
+    std::string out;
+    for (size_t j = 0; j < names.size(); ++j) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s %d %.3f\n", names[j].c_str(), cnt[j], tot[j]);
+        out += line;
+    }
+    trace_clear(ctx);
+    if (ctx->profile_on) trace_mark(ctx, __FILE__, __LINE__, "(begin)");
+    FD_REQUIRE(out.size() + 1 <= cap, "fd_ctx_profile_fetch: buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
     return FD_OK;
 }
 FD_EXPORT int fd_ctx_launch_count(const fd_ctx *ctx, int64_t *out) {

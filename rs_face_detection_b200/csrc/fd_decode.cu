@@ -204,7 +204,7 @@ int decode_launch(fd_ctx *ctx, const float *const *heads_dev, int B, float conf_
         decode_kernel<1><<<grid, 256, 0, ctx->stream>>>(ctx->dcfg, hp, conf_thr, ctx->cand_keys.as<u64>(), ctx->cand_box.as<float4>(),
                                                        ctx->cand_lmk.as<float>(), ctx->cand_count.as<int>(), ctx->status_dev.as<int>());
     }
-    FD_LAUNCH_CHECK(ctx);
+    FD_LAUNCH_CHECK_NAMED(ctx, "decode_kernel");
     return FD_OK;
 }
 
@@ -214,7 +214,7 @@ int finalize_launch(fd_ctx *ctx, int B) {
                                                 ctx->det_scale_dev.as<float>(), ctx->out_offsets.as<int>(),
                                                 ctx->out_det.as<float>(), ctx->out_lmk.as<float>(),
                                                 ctx->out_frame_idx.as<int>(), ctx->status_dev.as<int>());
-    FD_LAUNCH_CHECK(ctx);
+    FD_LAUNCH_CHECK_NAMED(ctx, "finalize_kernel");
     return FD_OK;
 }
 

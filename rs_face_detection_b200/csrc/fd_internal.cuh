@@ -78,6 +78,7 @@ struct fd_ctx {
     int max_smem_optin = 0;
     int64_t launches = 0;
     bool trace_on = false;       // FD_TRACE=1: an event after every launch, dumped by fd_ctx_synchronize
+    bool profile_on = false;     // fd_ctx_profile: same marks, aggregated by fd_ctx_profile_fetch
     std::vector<std::pair<std::string, cudaEvent_t>> trace;
     fd::DecodeCfg dcfg{};
 
@@ -127,13 +128,15 @@ namespace fd {
 
 int check_ctx(const fd_ctx *ctx);
 
-void trace_mark(fd_ctx *ctx, const char *file, int line);
-#define FD_LAUNCH_CHECK(ctx)                                          \
-    do {                                                              \
-        (ctx)->launches++;                                            \
-        FD_CUDA(cudaGetLastError());                                  \
-        if ((ctx)->trace_on) ::fd::trace_mark((ctx), __FILE__, __LINE__); \
+void trace_mark(fd_ctx *ctx, const char *file, int line, const char *name);
+// Per-launch timing (FD_TRACE=1 or fd_ctx_profile): an event before and after the launch on the ctx stream.
+#define FD_LAUNCH_CHECK_NAMED(ctx, name)                                          \
+    do {                                                                          \
+        (ctx)->launches++;                                                        \
+        FD_CUDA(cudaGetLastError());                                              \
+        if ((ctx)->trace_on) ::fd::trace_mark((ctx), __FILE__, __LINE__, (name)); \
     } while (0)
+#define FD_LAUNCH_CHECK(ctx) FD_LAUNCH_CHECK_NAMED(ctx, nullptr)
 
 // ---- device helpers ---------------------------------------------------------------------------------
 #ifdef __CUDACC__

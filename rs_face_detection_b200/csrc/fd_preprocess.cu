@@ -392,7 +392,7 @@ int crops_to_tensor_launch(fd_ctx *ctx, const uint8_t *crops_dev, const int *cou
     dim3 grid(std::max(1, std::min(16, (groups + 255) / 256)), std::min(F, 65535));
     if (count_dev) grid.y = std::min(F, std::max(1, ctx->num_sms * 8 / (int)grid.x));
     crops_to_tensor_kernel<<<grid, 256, 0, ctx->stream>>>(a);
-    FD_LAUNCH_CHECK(ctx);
+    FD_LAUNCH_CHECK_NAMED(ctx, "crops_to_tensor_kernel");
     return FD_OK;
 }
 
@@ -426,7 +426,7 @@ int preprocess_launch(fd_ctx *ctx, const FrameDev *frames_dev, int B, float *out
                 FD_CUDA(cudaFuncSetAttribute(preprocess_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 preprocess_tma_kernel<false><<<grid, threads, smem, ctx->stream>>>(a);
             }
-            FD_LAUNCH_CHECK(ctx);
+            FD_LAUNCH_CHECK_NAMED(ctx, "preprocess_tma_kernel");
             return FD_OK;
         }
     }
@@ -438,7 +438,7 @@ int preprocess_launch(fd_ctx *ctx, const FrameDev *frames_dev, int B, float *out
     int threads = std::min(1024, std::max(64, ((ngroups + 31) / 32) * 32));
     dim3 grid((a.out_h + PRE_ROWS - 1) / PRE_ROWS, B);
     preprocess_kernel<<<grid, threads, smem, ctx->stream>>>(a);
-    FD_LAUNCH_CHECK(ctx);
+    FD_LAUNCH_CHECK_NAMED(ctx, "preprocess_kernel");
     return FD_OK;
 }
 
