@@ -12,59 +12,22 @@
 #include <cmath>
 #include <cfloat>
 #include "fd_internal.cuh"
+#include "fd_estimate.cuh"
 
 namespace fd {
 
 struct EstArgs {
     const float *from;     // (F,5,2)
-    const float *to;       // (F,5,2) or nullptr -> tmpl
-    float tmpl[10];
+    const float *to;       // (F,5,2) or nullptr -> template
     const int *count_dev;  // optional device-side F
     int F;
-    int niters;            // <= 16
-    int8_t pair0[16], pair1[16];  // LMedS sample pairs per iteration (host-precomputed from OpenCV's RNG)
+    EstConst ec;
     double *M12;           // (F,12): M (6) then inverse (6)
     double *M_out;         // optional (F,6)
     uint8_t *ok;           // (F)
     uint8_t *ok_out;       // optional (F)
 };
 
-__device__ __forceinline__ unsigned rng_next(unsigned long long &state) {
-    state = (unsigned long long)(unsigned)state * 4164903690ull + (unsigned)(state >> 32);
-    return (unsigned)state;
-}
-
-__device__ __forceinline__ void fit2(const float *f, const float *t, int i0, int i1, double *M) {
-    double x1 = f[2 * i0], y1 = f[2 * i0 + 1], x2 = f[2 * i1], y2 = f[2 * i1 + 1];
-    double X1 = t[2 * i0], Y1 = t[2 * i0 + 1], X2 = t[2 * i1], Y2 = t[2 * i1 + 1];
-    double d = 1. / ((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2));
-    double S0 = d * ((X1 - X2) * (x1 - x2) + (Y1 - Y2) * (y1 - y2));
-    double S1 = d * ((Y1 - Y2) * (x1 - x2) - (X1 - X2) * (y1 - y2));
-    double S2 = d * ((Y1 - Y2) * (x1 * y2 - x2 * y1) - (X1 * y2 - X2 * y1) * (y1 - y2) - (X1 * x2 - X2 * x1) * (x1 - x2));
-    double S3 = d * (-(X1 - X2) * (x1 * y2 - x2 * y1) - (Y1 * x2 - Y2 * x1) * (x1 - x2) - (Y1 * y2 - Y2 * y1) * (y1 - y2));
-    M[0] = S0; M[1] = -S1; M[2] = S2; M[3] = S1; M[4] = S0; M[5] = S3;
-}
-__device__ __forceinline__ void affine_err5(const float *f, const float *t, const double *M, float *err) {
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        double a = M[0] * f[2 * i] + M[1] * f[2 * i + 1] + M[2] - t[2 * i];
-        double b = M[3] * f[2 * i] + M[4] * f[2 * i + 1] + M[5] - t[2 * i + 1];
-        err[i] = (float)(a * a + b * b);
-    }
-}
-__device__ __forceinline__ void invert_affine(const double *M, double *iM) {
-    double D = M[0] * M[4] - M[1] * M[3];
-    D = D != 0 ? 1. / D : 0;
-    double A11 = M[4] * D, A22 = M[0] * D;
-    iM[0] = A11; iM[1] = M[1] * (-D); iM[3] = M[3] * (-D); iM[4] = A22;
-    iM[2] = -iM[0] * M[2] - iM[1] * M[5];
-    iM[5] = -iM[3] * M[2] - iM[4] * M[5];
-}
-
-// 16 lanes per face: lane k < niters evaluates LMedS iteration k (the sample pairs depend only on the RNG, which OpenCV
-// reseeds per call, so they are precomputed on the host); a (median, iteration) lexicographic min over the lanes picks
-// the model the sequential loop would have kept (first strictly smaller median wins); lane 0 finishes.
-constexpr int EST_LANES = 16;
 __global__ void estimate_kernel(EstArgs a) {
     const int F = a.count_dev ? min(*a.count_dev, a.F) : a.F;
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
@@ -75,79 +38,12 @@ __global__ void estimate_kernel(EstArgs a) {
 #pragma unroll
     for (int k = 0; k < 10; ++k) {
         from[k] = live ? a.from[(size_t)fc * 10 + k] : 0.0f;
-        to[k] = a.to ? (live ? a.to[(size_t)fc * 10 + k] : 0.0f) : a.tmpl[k];
+        to[k] = a.to ? (live ? a.to[(size_t)fc * 10 + k] : 0.0f) : a.ec.tmpl[k];
     }
-    const int n = 5;
-    double model[6] = {0, 0, 0, 0, 0, 0};
-    double median = DBL_MAX;
-    float err[5];
-    if (live && sub < a.niters) {
-        fit2(from, to, a.pair0[sub], a.pair1[sub], model);
-        bool finite = true;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) finite &= isfinite(model[k]);
-        if (finite) {
-            affine_err5(from, to, model, err);
-            float s[5] = {err[0], err[1], err[2], err[3], err[4]};
-#pragma unroll
-            for (int i = 1; i < 5; ++i) {  // insertion sort of 5
-                float v = s[i];
-                int j = i - 1;
-                while (j >= 0 && s[j] > v) { s[j + 1] = s[j]; --j; }
-                s[j + 1] = v;
-            }
-            const double med = (double)s[2];
-            if (med < DBL_MAX) median = med;  // NaN / inf medians never win (median < minMedian is false)
-        }
-    }
-    // lexicographic (median, lane) min within each group of 16 lanes
-    int win = sub;
-    double best_med = median;
-#pragma unroll
-    for (int o = EST_LANES / 2; o > 0; o >>= 1) {
-        const double om = __shfl_xor_sync(0xffffffffu, best_med, o);
-        const int ow = __shfl_xor_sync(0xffffffffu, win, o);
-        if (om < best_med || (om == best_med && ow < win)) { best_med = om; win = ow; }
-    }
-    const int base_lane = (threadIdx.x & 31) & ~(EST_LANES - 1);
-    double best[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) best[k] = __shfl_sync(0xffffffffu, model[k], base_lane + win);
+    double M[6], iM[6];
+    bool ok;
+    estimate_group(a.ec, from, to, live, sub, M, iM, ok);
     if (!live || sub != 0) return;
-    const double minMedian = best_med;
-    bool ok = minMedian < DBL_MAX;
-    double M[6] = {0, 0, 0, 0, 0, 0};
-    if (ok) {
-        double sigma = 2.5 * 1.4826 * (1 + 5. / (n - 2)) * sqrt(minMedian);
-        if (sigma < 0.001) sigma = 0.001;
-        affine_err5(from, to, best, err);
-        const float thr = (float)(sigma * sigma);
-        bool mask[5];
-        int good = 0;
-#pragma unroll
-        for (int i = 0; i < 5; ++i) { mask[i] = err[i] <= thr; good += mask[i]; }
-        ok = good >= 2;
-        if (ok) {
-            // least squares over the inliers (fixed operation order; the test oracle performs the identical sequence)
-            double sx = 0, sy = 0, sX = 0, sY = 0;
-#pragma unroll
-            for (int i = 0; i < 5; ++i) if (mask[i]) { sx += from[2 * i]; sy += from[2 * i + 1]; sX += to[2 * i]; sY += to[2 * i + 1]; }
-            double mx = sx / good, my = sy / good, mX = sX / good, mY = sY / good;
-            double num_a = 0, num_b = 0, den = 0;
-#pragma unroll
-            for (int i = 0; i < 5; ++i) if (mask[i]) {
-                double dx = from[2 * i] - mx, dy = from[2 * i + 1] - my, dX = to[2 * i] - mX, dY = to[2 * i + 1] - mY;
-                num_a += dx * dX + dy * dY;
-                num_b += dx * dY - dy * dX;
-                den += dx * dx + dy * dy;
-            }
-            double sa = num_a / den, sb = num_b / den;
-            M[0] = sa; M[1] = -sb; M[2] = mX - (sa * mx - sb * my);
-            M[3] = sb; M[4] = sa;  M[5] = mY - (sb * mx + sa * my);
-        }
-    }
-    double iM[6];
-    invert_affine(M, iM);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         a.M12[(size_t)f * 12 + k] = M[k];
@@ -406,17 +302,6 @@ __global__ void __launch_bounds__(WARP_THREADS, 4) warp_kernel(WarpArgs a) {
     }
 }
 
-static int lmeds_niters(double p, double ep, int modelPoints, int maxIters) {  // RANSACUpdateNumIters
-    p = std::max(p, 0.); p = std::min(p, 1.);
-    ep = std::max(ep, 0.); ep = std::min(ep, 1.);
-    double num = std::max(1. - p, DBL_MIN);
-    double denom = 1. - std::pow(1. - ep, modelPoints);
-    if (denom < DBL_MIN) return 0;
-    num = std::log(num);
-    denom = std::log(denom);
-    return denom >= 0 || -num >= maxIters * (-denom) ? maxIters : (int)std::lrint(num / denom);
-}
-
 // ---- fixed-size fast path (the reference's 112x112 ArcFace crop, config.rs:45) --------------------------------------
 // Same persistent/ticket structure; a CTA is 2 output rows x CW columns, so a thread keeps ONE column for the whole item:
 // its (adelta, bdelta) live in registers, no index division, and the packed-store word address advances by a constant.
@@ -534,8 +419,35 @@ __global__ void __launch_bounds__(2 * CW) warp_fixed_kernel(WarpArgs a) {
     }
 }
 
+static int lmeds_niters(double p, double ep, int modelPoints, int maxIters) {  // RANSACUpdateNumIters
+    p = std::max(p, 0.); p = std::min(p, 1.);
+    ep = std::max(ep, 0.); ep = std::min(ep, 1.);
+    double num = std::max(1. - p, DBL_MIN);
+    double denom = 1. - std::pow(1. - ep, modelPoints);
+    if (denom < DBL_MIN) return 0;
+    num = std::log(num);
+    denom = std::log(denom);
+    return denom >= 0 || -num >= maxIters * (-denom) ? maxIters : (int)std::lrint(num / denom);
+}
+
+int make_est_const(const fd_ctx *ctx, EstConst *out) {
+    for (int i = 0; i < 10; ++i) out->tmpl[i] = (&ctx->cfg.template_landmarks[0][0])[i];
+    out->niters = std::max(lmeds_niters(0.99, 0.45, 2, 2000), 3);
+    if (out->niters > EST_LANES) return fail(FD_ERR_INVALID, "estimate: LMedS iteration count exceeds the lane group");
+    // cv::RNG(-1): state = (uint32)state * 4164903690 + (state >> 32); uniform(0,n) = next() % n
+    unsigned long long st = 0xFFFFFFFFFFFFFFFFull;
+    auto next = [&]() { st = (unsigned long long)(unsigned)st * 4164903690ull + (unsigned)(st >> 32); return (unsigned)st; };
+    for (int it = 0; it < 16; ++it) {
+        int i0 = (int)(next() % 5u), i1;
+        do { i1 = (int)(next() % 5u); } while (i1 == i0);
+        out->pair0[it] = (int8_t)i0;
+        out->pair1[it] = (int8_t)i1;
+    }
+    return FD_OK;
+}
+
 // zero-initialised work tickets of the persistent kernels (each launch leaves them at zero again)
-static int ticket_buffer(fd_ctx *ctx) {
+int ticket_buffer(fd_ctx *ctx) {
     if (ctx->tickets.p) return FD_OK;
     FD_TRY(ctx->tickets.reserve(sizeof(int) * 16));
     FD_CUDA(cudaMemsetAsync(ctx->tickets.p, 0, sizeof(int) * 16, ctx->stream));
@@ -549,21 +461,9 @@ int estimate_launch(fd_ctx *ctx, const float *from_dev, const float *to_dev, con
     EstArgs a;
     a.from = from_dev;
     a.to = to_dev;
-    for (int i = 0; i < 10; ++i) a.tmpl[i] = (&ctx->cfg.template_landmarks[0][0])[i];
     a.count_dev = count_dev;
     a.F = F_cap;
-    a.niters = std::max(lmeds_niters(0.99, 0.45, 2, 2000), 3);
-    if (a.niters > 16) return fail(FD_ERR_INVALID, "estimate: LMedS iteration count exceeds the lane group");
-    {   // cv::RNG(-1): state = (uint32)state * 4164903690 + (state >> 32); uniform(0,n) = next() % n
-        unsigned long long st = 0xFFFFFFFFFFFFFFFFull;
-        auto next = [&]() { st = (unsigned long long)(unsigned)st * 4164903690ull + (unsigned)(st >> 32); return (unsigned)st; };
-        for (int it = 0; it < 16; ++it) {
-            int i0 = (int)(next() % 5u), i1;
-            do { i1 = (int)(next() % 5u); } while (i1 == i0);
-            a.pair0[it] = (int8_t)i0;
-            a.pair1[it] = (int8_t)i1;
-        }
-    }
+    FD_TRY(make_est_const(ctx, &a.ec));
     a.M12 = M12_dev;
     a.M_out = M_out_dev;
     a.ok = ok_dev;

@@ -11,61 +11,20 @@
 // sparsely, indexed by their global anchor id (order 32|16|8, then (h,w,a) — face_detection.rs:410), so the later
 // sort key (score desc, anchor id asc) reproduces the reference's stable ordering without an ordered compaction.
 #include "fd_internal.cuh"
+#include "fd_decode.cuh"
 
 namespace fd {
 
-typedef unsigned long long u64;
-
-struct HeadPtrs {
-    const float *p[3 * FD_MAX_STRIDES];
-};
-
-constexpr int CAND_REC = 12;  // floats per candidate record: 10 landmarks, score, pad
-
-// decodes anchor (s, local, a) of image b and writes its candidate record; returns nothing
+// decodes anchor (s, local, a) of image b and writes its candidate record
 __device__ __forceinline__ void decode_one(const DecodeCfg &c, const HeadPtrs &hp, int b, int s, int local, int a, float score,
                                            int slot, u64 *__restrict__ keys, float4 *__restrict__ cand_box,
                                            float *__restrict__ cand_rec) {
-    const int fw = c.fw[s], hw = c.fh[s] * c.fw[s];
-    const int h = local / fw, w = local - h * fw;
-    const int A = c.A;
-    const float *bb = hp.p[3 * s + 1] + (size_t)b * 4 * A * hw;
-    const float *lm = hp.p[3 * s + 2] + (size_t)b * 10 * A * hw;
     const size_t img_base = (size_t)b * c.total_anchors;
-    const int id = c.anchor_off[s] + local * A + a;
-    // anchor = base + (w*stride, h*stride, w*stride, h*stride)   (anchors.rs:8-16)
-    const float sw = (float)(w * c.stride[s]), sh = (float)(h * c.stride[s]);
-    const float ax1 = __fadd_rn(c.base[s][a][0], sw), ay1 = __fadd_rn(c.base[s][a][1], sh);
-    const float ax2 = __fadd_rn(c.base[s][a][2], sw), ay2 = __fadd_rn(c.base[s][a][3], sh);
-    // face_detection.rs:522-525
-    const float aw = __fadd_rn(__fsub_rn(ax2, ax1), 1.0f), ah = __fadd_rn(__fsub_rn(ay2, ay1), 1.0f);
-    const float cx = __fadd_rn(ax1, __fmul_rn(0.5f, __fsub_rn(aw, 1.0f)));
-    const float cy = __fadd_rn(ay1, __fmul_rn(0.5f, __fsub_rn(ah, 1.0f)));
-    const float dx = __fmul_rn(__ldg(bb + (size_t)(4 * a + 0) * hw + local), c.bbox_stds[0]);  // :366-371
-    const float dy = __fmul_rn(__ldg(bb + (size_t)(4 * a + 1) * hw + local), c.bbox_stds[1]);
-    const float dw = __fmul_rn(__ldg(bb + (size_t)(4 * a + 2) * hw + local), c.bbox_stds[2]);
-    const float dh = __fmul_rn(__ldg(bb + (size_t)(4 * a + 3) * hw + local), c.bbox_stds[3]);
-    float lraw[10];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) lraw[k] = __ldg(lm + (size_t)(10 * a + k) * hw + local);
-    // :532-535.  exp through fp64 is correctly rounded to <=0.5 ulp; the reference's f32::exp is the platform expf.
-    const float pcx = __fadd_rn(__fmul_rn(dx, aw), cx), pcy = __fadd_rn(__fmul_rn(dy, ah), cy);
-    const float pw = __fmul_rn((float)exp((double)dw), aw), ph = __fmul_rn((float)exp((double)dh), ah);
-    // :539-542, then clip_boxes to the padded detector image (:373, bbox_transform.rs:36-42)
-    const float hwx = __fmul_rn(0.5f, __fsub_rn(pw, 1.0f)), hwy = __fmul_rn(0.5f, __fsub_rn(ph, 1.0f));
-    float4 box;
-    box.x = fmaxf(fminf(__fsub_rn(pcx, hwx), c.clip_w), 0.0f);
-    box.y = fmaxf(fminf(__fsub_rn(pcy, hwy), c.clip_h), 0.0f);
-    box.z = fmaxf(fminf(__fadd_rn(pcx, hwx), c.clip_w), 0.0f);
-    box.w = fmaxf(fminf(__fadd_rn(pcy, hwy), c.clip_h), 0.0f);
-    cand_box[img_base + id] = box;
-    // landmarks from the ANCHOR box, never clipped (:399, :564-567)
+    const int id = c.anchor_off[s] + local * c.A + a;
+    const AnchorGeo g = anchor_geo(c, s, local, a);
+    cand_box[img_base + id] = decode_box(c, hp, b, s, local, a, g);
     float rec[CAND_REC];
-#pragma unroll
-    for (int p = 0; p < 5; ++p) {
-        rec[2 * p] = __fadd_rn(__fmul_rn(__fmul_rn(lraw[2 * p], c.landmark_std), aw), cx);
-        rec[2 * p + 1] = __fadd_rn(__fmul_rn(__fmul_rn(lraw[2 * p + 1], c.landmark_std), ah), cy);
-    }
+    decode_landmarks(c, hp, b, s, local, a, g, rec);
     rec[10] = score;
     rec[11] = 0.0f;
     float4 *dst = reinterpret_cast<float4 *>(cand_rec + (img_base + id) * CAND_REC);
@@ -85,12 +44,7 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeCfg c, HeadPtrs hp, f
     const int pos = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     const int lane = threadIdx.x & 31;
     const bool active = pos < c.total_pos;
-    int s = 0;
-    if (active) {
-#pragma unroll
-        for (int k = 1; k < FD_MAX_STRIDES; ++k)
-            if (k < c.n_strides && pos >= c.pos_off[k]) s = k;
-    }
+    const int s = active ? stride_of_pos(c, pos) : 0;
     const int local = active ? pos - c.pos_off[s] : 0;
     const int hw = c.fh[s] * c.fw[s];
     const int A = c.A;

@@ -104,6 +104,11 @@ struct fd_ctx {
     fd::DevBuf align_M;          // double[F][12] (M, inverse)
     fd::DevBuf align_ok;         // u8[F]
     fd::DevBuf tickets;          // int[16] work tickets of the persistent kernels (zero between launches)
+    fd::DevBuf scan_agg;         // u64[B] epoch-tagged kept counts of the fused detect kernel
+    unsigned scan_epoch = 0;
+    int est_cap = 0;             // faces align_M / align_ok have room for at detect time
+    int align_cap_hint = 0;      // largest crop capacity an align call has asked for
+    bool est_valid = false;      // align_M / align_ok hold the estimates of the last fd_detect_batch (fused kernel)
     fd::DevBuf nms_ws[8];        // big-path workspaces
     fd::DevBuf nms_ws_sp[4];     // spatial big-path workspaces
     fd::DevBuf pipe_frames;      // host pipeline: device copies of frames
@@ -205,6 +210,9 @@ int preprocess_launch(fd_ctx *ctx, const FrameDev *frames_dev, int B, float *out
 int resize_launch(fd_ctx *ctx, const FrameDev &frame, uint8_t *out_dev, int out_h, int out_w);
 int crops_to_tensor_launch(fd_ctx *ctx, const uint8_t *crops_dev, const int *count_dev, int F, int in_h, int in_w, int out_h,
                            int out_w, const float *mean_rgb, const float *mul_rgb, float *out_dev);
+struct IouParams make_iou_params(float thr, int mode);
+int detect_fused_launch(fd_ctx *ctx, const float *const *heads_dev, int B, float conf_thr, float iou_thr, int est_cap, bool *launched);
+int nms_batch_small_image(fd_ctx *ctx, int b, int K, float iou_thr);
 int decode_launch(fd_ctx *ctx, const float *const *heads_dev, int B, float conf_thr);
 int nms_batch_launch(fd_ctx *ctx, int B, float iou_thr);
 int nms_batch_big_image(fd_ctx *ctx, int b, int K, float iou_thr);
@@ -215,6 +223,7 @@ int nms_last_stats(fd_ctx *ctx, int32_t out[8]);
 int argsort_device(fd_ctx *ctx, const float *scores_as_dets, int n, int stride, int32_t *order_dev, int32_t *flag_dev);
 int estimate_launch(fd_ctx *ctx, const float *from_dev, const float *to_dev, const int *count_dev, int F_cap,
                     double *M12_dev, double *M_out_dev, uint8_t *ok_dev, uint8_t *ok_out_dev);
+int ticket_buffer(fd_ctx *ctx);
 int invert_launch(fd_ctx *ctx, const double *M_dev, int F, double *M12_dev, uint8_t *ok_dev);
 int warp_launch(fd_ctx *ctx, const FrameDev *frames_dev, const int32_t *frame_idx_dev, const double *M12_dev,
                 const uint8_t *ok_dev, const int *count_dev, int F_cap, uint8_t *crops_dev, int cw, int ch);

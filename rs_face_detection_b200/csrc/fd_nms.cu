@@ -20,15 +20,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <cstdio>
-#include <unistd.h>
 #include <vector>
 #include "fd_internal.cuh"
+#include "fd_nms_tiny.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace fd {
 
-typedef unsigned long long u64;
 
 constexpr int NT = 1024;          // threads per NMS CTA
 constexpr int NWARPS = NT / 32;
@@ -84,9 +83,6 @@ __device__ void build_mask(const float4 *__restrict__ hbox, const float *__restr
     }
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // kept/und: HEAD_WORDS words each in shared memory; flags: 2 ints.  On return kept holds the greedy keep set of the head.
 // Only the warps that own head rows take part in the rounds (named barrier 1); the rest of the CTA waits at the final
@@ -213,161 +209,11 @@ struct SmallArgs {
 };
 
 
-// ---- K <= 1024: barrier-light path inside the same kernel --------------------------------------------------------------
-// The pipeline's problems are a few hundred candidates of which a few dozen survive; at that size the cost of the general
-// path is its ~200 block-wide barriers, not its arithmetic.  Here one thread owns one box:
-//   sort     bitonic network on registers: partner distance < 32 by warp shuffle, >= 32 through a double-buffered
-//            shared-memory exchange (15 barriers for 1024 keys instead of 55);
-//   greedy   the first <= 32 undecided boxes in rank order form a mini-head that ONE warp resolves in registers (pairwise
-//            tests by shuffle, then the sequential keep decisions over a 32-bit mask); every other thread then tests its
-//            own box against the mini-head's kept boxes.  Two barriers per mini-head, no mask in memory, no compaction.
-// Same greedy result: a box is kept iff no earlier-ranked kept box suppresses it.
-constexpr int TINY_CAP = 1024;
-struct TinySmem {
-    u64 xch[2][TINY_CAP];
-    float4 sbox[TINY_CAP];   // boxes in rank order
-    float sarea[TINY_CAP];
-    int sidx[TINY_CAP];      // source index of rank r
-    int selw[32][32];        // per-warp scratch: ranks of the current mini-head
-    unsigned alive[2][32];
-    unsigned mrow[32];
-};
 __device__ __forceinline__ void dbg_stamp(const SmallArgs &a, int slot) {
     if (a.dbg && threadIdx.x == 0) {
         long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         a.dbg[blockIdx.x * 16 + slot] = t;
-    }
-}
-__device__ __forceinline__ void dbg_mark(const SmallArgs &a, int id, long long v) {
-    if (a.dbg && (threadIdx.x & 31) == 0 && blockIdx.x == 0) {
-        volatile long long *d = a.dbg;
-        d[32 + (threadIdx.x >> 5) * 2] = id;
-        d[32 + (threadIdx.x >> 5) * 2 + 1] = v;
-        __threadfence_system();
-    }
-}
-__device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
-    int r;
-    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %3, 0;\n\tbar.red.or.pred q, %1, %2, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
-                 : "=r"(r) : "r"(id), "r"(nthreads), "r"((int)pred) : "memory");
-    return r != 0;
-}
-template <int MODE, bool FAST>
-__device__ __forceinline__ bool tiny_suppresses(const float4 earlier, const float area_e, const float4 later, const float area_l,
-                                                const IouParams &P) {
-    if (FAST) return iou_suppresses_exact(earlier, area_e, later, area_l, P);
-    return iou_suppresses_full<MODE>(earlier, later, P.thr);
-}
-
-template <int MODE, bool FAST>
-__device__ void tiny_greedy(TinySmem &sm, const SmallArgs &a, int K, int nthr, int *keep, int *keep_count_out, float4 my) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
-    const float my_area = box_area(my);
-    bool alive = tid < K;
-    // the mini-head of the previous round, replicated in every warp: lane j <-> its j-th box
-    unsigned keptmask = 0;
-    int selj = 0;
-    int nk_total = 0, iters = 0;
-    for (;; ++iters) {
-        // A. my box against the boxes the previous mini-head kept (uniform loop: the shuffles need every lane)
-        bool sup = false;
-        for (unsigned km = keptmask; km; km &= km - 1) {
-            const int ks = __shfl_sync(0xffffffffu, selj, __ffs(km) - 1);
-            if (alive && !sup) sup = tiny_suppresses<MODE, FAST>(sm.sbox[ks], sm.sarea[ks], my, my_area, a.iou);
-        }
-        alive = alive && !sup;
-        const unsigned bal = __ballot_sync(0xffffffffu, alive);
-        if (lane == 0) sm.alive[iters & 1][warp] = bal;
-        dbg_mark(a, 100 + iters * 10, bal);
-        named_bar_sync(2, nthr);
-        dbg_mark(a, 101 + iters * 10, bal);
-        // B. every warp selects the same mini-head: the first <= 32 undecided boxes in rank order
-        const unsigned w = lane < nwarps ? sm.alive[iters & 1][lane] : 0u;
-        const int c = __popc(w);
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += n;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        dbg_mark(a, 102 + iters * 10, total);
-        if (total == 0) break;
-        const int n_sel = min(total, 32);
-        int *mysel = sm.selw[warp];
-        {
-            unsigned ww = w;
-            int pos = incl - c;
-            while (ww && pos < 32) {
-                mysel[pos++] = lane * 32 + __ffs(ww) - 1;
-                ww &= ww - 1;
-            }
-        }
-        __syncwarp();
-        selj = lane < n_sel ? mysel[lane] : 0;
-        __syncwarp();
-        const float4 bj = sm.sbox[selj];
-        const float aj = sm.sarea[selj];
-        const int warp_excl = __shfl_sync(0xffffffffu, incl - c, warp);   // (not inside the && below: every lane must shuffle)
-        const bool selected = alive && (warp_excl + __popc(bal & ((1u << lane) - 1u))) < 32;
-        // C. pairwise tests inside the mini-head, one row per warp: bit j of row r = earlier box j suppresses box r
-        for (int r = warp; r < n_sel; r += nwarps) {
-            const int rs = __shfl_sync(0xffffffffu, selj, r);
-            const bool sp = lane < r && tiny_suppresses<MODE, FAST>(bj, aj, sm.sbox[rs], sm.sarea[rs], a.iou);
-            const unsigned row = __ballot_sync(0xffffffffu, sp);
-            if (lane == 0) sm.mrow[r] = row;
-        }
-        dbg_mark(a, 103 + iters * 10, n_sel);
-        named_bar_sync(2, nthr);
-        dbg_mark(a, 104 + iters * 10, n_sel);
-        // D. every warp resolves the mini-head by parallel rounds over the 32-bit rows: a box is suppressed as soon as an
-        //    earlier overlapping box is kept, kept as soon as every earlier overlapping box is decided (the lowest undecided
-        //    box always qualifies, so each round decides at least one; typical dependency depth is 2-3)
-        const unsigned m = lane < n_sel ? sm.mrow[lane] : 0u;
-        keptmask = __ballot_sync(0xffffffffu, lane < n_sel && m == 0);
-        unsigned und = __ballot_sync(0xffffffffu, m != 0);
-        bool undecided = m != 0;
-        while (und) {
-            bool k = false;
-            if (undecided) {
-                if (m & keptmask) undecided = false;
-                else if ((m & und) == 0) { undecided = false; k = true; }
-            }
-            keptmask |= __ballot_sync(0xffffffffu, k);
-            und = __ballot_sync(0xffffffffu, undecided);
-        }
-        if (warp == 0 && ((keptmask >> lane) & 1u)) keep[nk_total + __popc(keptmask & ((1u << lane) - 1u))] = sm.sidx[selj];
-        nk_total += __popc(keptmask);
-        if (selected) alive = false;   // decided, one way or the other
-        dbg_mark(a, 105 + iters * 10, keptmask);
-    }
-    if (tid == 0) *keep_count_out = nk_total;
-    dbg_stamp(a, 4);
-    if (a.dbg && tid == 0) { a.dbg[blockIdx.x * 16 + 5] = iters; a.dbg[blockIdx.x * 16 + 6] = K; a.dbg[blockIdx.x * 16 + 7] = nk_total; }
-}
-
-// Bitonic network over N2 keys, one per thread, fully unrolled: partner distance < 32 by shuffle, otherwise through the
-// double-buffered exchange array (one barrier per such stage).
-template <int N2>
-__device__ __forceinline__ void tiny_sort(u64 &key, TinySmem &sm, int tid) {
-    int pbuf = 0;
-#pragma unroll
-    for (int k = 2; k <= N2; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            u64 other;
-            if (j >= 32) {
-                sm.xch[pbuf][tid] = key;
-                named_bar_sync(2, N2);
-                other = sm.xch[pbuf][tid ^ j];
-                pbuf ^= 1;
-            } else {
-                other = __shfl_xor_sync(0xffffffffu, key, j);
-            }
-            const bool take_min = ((tid & j) == 0) == ((tid & k) == 0);
-            key = (take_min == (other < key)) ? other : key;
-        }
     }
 }
 
@@ -401,7 +247,6 @@ __device__ void nms_tiny(const SmallArgs &a, unsigned char *smem_raw, int b, int
     }
     if (a.dbg && key == 1) a.dbg[0] = 0;   // (debug) wait for the key load before the stamp
     dbg_stamp(a, 1);
-    dbg_mark(a, 1, n2);
     if (!a.presorted) {
         switch (n2) {
             case 32: tiny_sort<32>(key, sm, tid); break;
@@ -414,7 +259,6 @@ __device__ void nms_tiny(const SmallArgs &a, unsigned char *smem_raw, int b, int
     }
     const int idx = (int)(unsigned)key;
     dbg_stamp(a, 2);
-    dbg_mark(a, 2, idx);
     if (a.sort_only) {
         if (tid < K) keep[tid] = idx;
         if (tid == 0) a.keep_count[b] = K;
@@ -431,9 +275,11 @@ __device__ void nms_tiny(const SmallArgs &a, unsigned char *smem_raw, int b, int
     }
     const bool fast = !named_bar_or(2, nthr, !ok) && a.iou.fast;   // also publishes sbox / sidx
     dbg_stamp(a, 3);
-    dbg_mark(a, 3, fast);
-    if (fast) tiny_greedy<MODE, true>(sm, a, K, nthr, keep, a.keep_count + b, my);
-    else tiny_greedy<MODE, false>(sm, a, K, nthr, keep, a.keep_count + b, my);
+    int iters = 0;
+    const int nk = fast ? tiny_greedy<MODE, true>(sm, a.iou, K, nthr, keep, my, &iters) : tiny_greedy<MODE, false>(sm, a.iou, K, nthr, keep, my, &iters);
+    if (tid == 0) a.keep_count[b] = nk;
+    dbg_stamp(a, 4);
+    if (a.dbg && tid == 0) { a.dbg[blockIdx.x * 16 + 5] = iters; a.dbg[blockIdx.x * 16 + 6] = K; a.dbg[blockIdx.x * 16 + 7] = nk; }
 }
 
 template <int MODE, int BS>
@@ -1366,10 +1212,7 @@ static int launch_small(fd_ctx *ctx, const SmallArgs &a_in, int B, bool float4_b
     static const int dbg_on = getenv("FD_NMS_DBG") != nullptr;
     static long long *dbg_dev = nullptr;
     if (dbg_on) {
-        if (!dbg_dev) {
-            if (getenv("FD_NMS_DBG")[0] == '2') cudaHostAlloc(&dbg_dev, sizeof(long long) * 16 * 4096, cudaHostAllocMapped);
-            else cudaMalloc(&dbg_dev, sizeof(long long) * 16 * 4096);
-        }
+        if (!dbg_dev) cudaMalloc(&dbg_dev, sizeof(long long) * 16 * 4096);
         cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 16 * 4096, ctx->stream);
         a.dbg = dbg_dev;
     }
@@ -1383,14 +1226,6 @@ static int launch_small(fd_ctx *ctx, const SmallArgs &a_in, int B, bool float4_b
         nms_cta_kernel<MODE, 0><<<B, NT, smem, ctx->stream>>>(a);
     }
     FD_LAUNCH_CHECK_NAMED(ctx, "nms_cta_kernel");
-    if (dbg_on && getenv("FD_NMS_DBG")[0] == '2') {   // hang hunt: poll the stream, dump the per-warp progress markers of CTA 0
-        for (int ms = 0; ms < 3000 && cudaStreamQuery(ctx->stream) == cudaErrorNotReady; ++ms) usleep(1000);
-        if (cudaStreamQuery(ctx->stream) == cudaErrorNotReady) {
-            volatile long long *d = dbg_dev;
-            for (int w = 0; w < 32; ++w) fprintf(stderr, "[nms hang] warp %2d marker %lld value 0x%llx\n", w, d[32 + 2 * w], (unsigned long long)d[33 + 2 * w]);
-            _exit(3);
-        }
-    }
     if (dbg_on) {
         std::vector<long long> h(16 * (size_t)std::min(B, 4096));
         cudaStreamSynchronize(ctx->stream);
@@ -1641,6 +1476,26 @@ int nms_batch_launch(fd_ctx *ctx, int B, float iou_thr) {
     a.status = ctx->status_dev.as<int>();
     a.big_list = ctx->big_list.as<int>();
     return launch_small<0>(ctx, a, B, true);
+}
+
+// General single-CTA path for ONE image of the batch (1024 < K <= SMALL_CAP after the fused kernel deferred it).
+int nms_batch_small_image(fd_ctx *ctx, int b, int K, float iou_thr) {
+    const int TA = ctx->dcfg.total_anchors;
+    SmallArgs a{};
+    a.keys = ctx->cand_keys.as<u64>() + (size_t)b * TA;
+    a.key_stride = (size_t)TA;
+    a.boxes = ctx->cand_box.as<float>() + (size_t)b * TA * 4;
+    a.box_batch_stride = (size_t)TA * 4;
+    a.box_stride = 4;
+    a.counts = nullptr;
+    a.K = K;
+    a.iou = make_iou_params(iou_thr, 0);
+    a.keep = ctx->keep_src.as<int>() + (size_t)b * TA;
+    a.keep_stride = (size_t)TA;
+    a.keep_count = ctx->keep_count.as<int>() + b;
+    a.status = ctx->status_dev.as<int>() + 4;   // scratch flags: the batch's own flags were already read
+    a.big_list = nullptr;
+    return launch_small<0>(ctx, a, 1, true);
 }
 
 // Big-path fix-up for one image of the batch (K > SMALL_CAP): radix sort on (anchor id, score) bytes + peel.

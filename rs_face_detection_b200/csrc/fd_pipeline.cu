@@ -2,6 +2,7 @@
 // host-buffer end-to-end call.  Mirrors RetinaFaceDetection::call (face_detection.rs:496-513) and
 // FaceAlignment::call (face_alignment.rs:27-141) at batch granularity.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include "fd_internal.cuh"
 
@@ -76,12 +77,19 @@ static int upload_frame_table(fd_ctx *ctx, const fd_frame *frames, int B, float 
     return FD_OK;
 }
 
+// from_detect: the faces are the detections of the last fd_detect_batch; when the fused detect kernel already estimated
+// their transforms (ctx->est_valid) and they all fit, the estimate launch is skipped.
 static int align_enqueue(fd_ctx *ctx, const FrameDev *frames_dev, const float *lmk_dev, const int32_t *frame_idx_dev,
-                         const int *count_dev, int F_cap, uint8_t *crops_dev, double *M_dev, uint8_t *ok_dev) {
+                         const int *count_dev, int F_cap, uint8_t *crops_dev, double *M_dev, uint8_t *ok_dev, bool from_detect) {
     if (F_cap <= 0) return FD_OK;
-    FD_TRY(ctx->align_M.reserve(sizeof(double) * 12 * (size_t)F_cap));
-    FD_TRY(ctx->align_ok.reserve((size_t)F_cap));
-    FD_TRY(estimate_launch(ctx, lmk_dev, nullptr, count_dev, F_cap, ctx->align_M.as<double>(), M_dev, ctx->align_ok.as<uint8_t>(), ok_dev));
+    ctx->align_cap_hint = std::max(ctx->align_cap_hint, F_cap);
+    const bool reuse = from_detect && ctx->est_valid && F_cap <= ctx->est_cap && !M_dev && !ok_dev;
+    if (!reuse) {
+        ctx->est_valid = false;
+        FD_TRY(ctx->align_M.reserve(sizeof(double) * 12 * (size_t)F_cap));
+        FD_TRY(ctx->align_ok.reserve((size_t)F_cap));
+        FD_TRY(estimate_launch(ctx, lmk_dev, nullptr, count_dev, F_cap, ctx->align_M.as<double>(), M_dev, ctx->align_ok.as<uint8_t>(), ok_dev));
+    }
     FD_TRY(warp_launch(ctx, frames_dev, frame_idx_dev, ctx->align_M.as<double>(), ctx->align_ok.as<uint8_t>(), count_dev, F_cap,
                        crops_dev, ctx->cfg.crop_w, ctx->cfg.crop_h));
     return FD_OK;
@@ -100,11 +108,15 @@ static int detect_resolve(fd_ctx *ctx) {
         std::vector<int> big(st[1]), counts(B);
         FD_CUDA(cudaMemcpy(big.data(), ctx->big_list.p, sizeof(int) * st[1], cudaMemcpyDeviceToHost));
         FD_CUDA(cudaMemcpy(counts.data(), ctx->cand_count.p, sizeof(int) * B, cudaMemcpyDeviceToHost));
-        for (int b : big) FD_TRY(nms_batch_big_image(ctx, b, counts[b], ctx->last_iou));
+        for (int b : big) {
+            if (counts[b] <= 4096) FD_TRY(nms_batch_small_image(ctx, b, counts[b], ctx->last_iou));
+            else FD_TRY(nms_batch_big_image(ctx, b, counts[b], ctx->last_iou));
+        }
         FD_TRY(finalize_launch(ctx, B));
+        ctx->est_valid = false;
         if (ctx->align_replay)  // the crops were produced from incomplete detections: align again
             FD_TRY(align_enqueue(ctx, ctx->frames_dev.as<FrameDev>(), ctx->out_lmk.as<float>(), ctx->out_frame_idx.as<int32_t>(),
-                                 ctx->status_dev.as<int>() + 2, ctx->align_cap, ctx->align_crops, ctx->align_M_out, ctx->align_ok_out));
+                                 ctx->status_dev.as<int>() + 2, ctx->align_cap, ctx->align_crops, ctx->align_M_out, ctx->align_ok_out, true));
         FD_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     return FD_OK;
@@ -125,6 +137,10 @@ static int reserve_detect(fd_ctx *ctx, int B) {
     FD_TRY(ctx->out_det.reserve(sizeof(float) * 5 * n));
     FD_TRY(ctx->out_lmk.reserve(sizeof(float) * 10 * n));
     FD_TRY(ctx->out_frame_idx.reserve(sizeof(int) * n));
+    // transforms of the detections, estimated inside the fused detect kernel for the align call that usually follows
+    ctx->est_cap = (int)std::min<size_t>(n, (size_t)std::max(ctx->align_cap_hint, B * 64));
+    FD_TRY(ctx->align_M.reserve(sizeof(double) * 12 * (size_t)ctx->est_cap));
+    FD_TRY(ctx->align_ok.reserve((size_t)ctx->est_cap));
     return FD_OK;
 }
 
@@ -139,11 +155,16 @@ static int detect_enqueue(fd_ctx *ctx, const float *const *heads_dev, int B, con
         FD_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
         ctx->det_scale_shadow.assign(det_scale_host, det_scale_host + B);
     }
-    FD_CUDA(cudaMemsetAsync(ctx->cand_count.p, 0, sizeof(int) * (size_t)B, ctx->stream));
     FD_CUDA(cudaMemsetAsync(ctx->status_dev.p, 0, sizeof(int) * 8, ctx->stream));
-    FD_TRY(decode_launch(ctx, heads_dev, B, conf_thr));
-    FD_TRY(nms_batch_launch(ctx, B, iou_thr));
-    FD_TRY(finalize_launch(ctx, B));
+    bool fused = false;
+    FD_TRY(detect_fused_launch(ctx, heads_dev, B, conf_thr, iou_thr, ctx->est_cap, &fused));
+    if (!fused) {
+        FD_CUDA(cudaMemsetAsync(ctx->cand_count.p, 0, sizeof(int) * (size_t)B, ctx->stream));
+        FD_TRY(decode_launch(ctx, heads_dev, B, conf_thr));
+        FD_TRY(nms_batch_launch(ctx, B, iou_thr));
+        FD_TRY(finalize_launch(ctx, B));
+    }
+    ctx->est_valid = fused;
     ctx->last_B = B;
     ctx->last_iou = iou_thr;
     ctx->detect_pending = true;
@@ -222,7 +243,7 @@ FD_EXPORT int fd_align_batch(fd_ctx *ctx, const fd_frame *frames, int B, const f
     FD_REQUIRE(B > 0 && frames && F >= 0 && (F == 0 || (landmarks_dev && crops_dev)), "fd_align_batch: bad arguments");
     if (F == 0) return FD_OK;
     FD_TRY(upload_frame_table(ctx, frames, B, nullptr, nullptr));
-    return align_enqueue(ctx, ctx->frames_dev.as<FrameDev>(), landmarks_dev, frame_idx_dev, nullptr, F, crops_dev, M_dev, ok_dev);
+    return align_enqueue(ctx, ctx->frames_dev.as<FrameDev>(), landmarks_dev, frame_idx_dev, nullptr, F, crops_dev, M_dev, ok_dev, false);
 }
 
 FD_EXPORT int fd_align_detections(fd_ctx *ctx, const fd_frame *frames, int B, uint8_t *crops_dev, int cap_faces, double *M_dev,
@@ -238,7 +259,7 @@ FD_EXPORT int fd_align_detections(fd_ctx *ctx, const fd_frame *frames, int B, ui
     ctx->align_M_out = M_dev;
     ctx->align_ok_out = ok_dev;
     return align_enqueue(ctx, ctx->frames_dev.as<FrameDev>(), ctx->out_lmk.as<float>(), ctx->out_frame_idx.as<int32_t>(),
-                         ctx->status_dev.as<int>() + 2, cap_faces, crops_dev, M_dev, ok_dev);
+                         ctx->status_dev.as<int>() + 2, cap_faces, crops_dev, M_dev, ok_dev, true);
 }
 
 // ---- single-image host wrappers -----------------------------------------------------------------------------------
@@ -325,6 +346,7 @@ FD_EXPORT int fd_estimate_affine_partial_2d(fd_ctx *ctx, const float *from, cons
         FD_CUDA(cudaMemcpyAsync(ctx->scratch[1].p, to, nb, cudaMemcpyHostToDevice, ctx->stream));
         d_to = ctx->scratch[1].as<float>();
     }
+    ctx->est_valid = false;   // align_M / align_ok are reused as scratch here
     FD_TRY(ctx->align_M.reserve(sizeof(double) * 12 * (size_t)n_sets));
     FD_TRY(ctx->align_ok.reserve((size_t)n_sets));
     FD_TRY(ctx->scratch[2].reserve(sizeof(double) * 6 * (size_t)n_sets));
@@ -351,6 +373,7 @@ static int warp_host(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, c
     FD_TRY(ctx->scratch[5].reserve(sizeof(FrameDev)));
     FD_CUDA(cudaMemcpyAsync(ctx->scratch[5].p, f, sizeof(FrameDev), cudaMemcpyHostToDevice, ctx->stream));
     FD_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+    ctx->est_valid = false;
     FD_TRY(ctx->align_M.reserve(sizeof(double) * 12));
     FD_TRY(ctx->align_ok.reserve(16));
     FD_TRY(ctx->scratch[0].reserve(sizeof(double) * 6 + sizeof(float) * 10));

@@ -86,6 +86,26 @@ def test_all_anchors_pass_big_path_in_batch(ctx, oracle):
         off += counts[b]
 
 
+@pytest.mark.parametrize("conf", [0.7, 0.2, 0.05])
+def test_mixed_candidate_counts_in_one_batch(ctx, oracle, conf):
+    """A batch mixing images with few candidates (fused single-launch path, K <= 1024) and crowded ones that the fused
+    kernel defers (1024 < K <= 4096: general single-CTA NMS; K > 4096: radix + spatial path); results in frame order."""
+    crowded, _ = synth.make_heads(2, seed=21, n_faces=60)      # K ~ 1150 / 2250 / 5000 at conf 0.7 / 0.2 / 0.05
+    sparse, _ = synth.make_heads(2, seed=22, n_faces=5)
+    heads = [np.ascontiguousarray(np.stack([c[0], s_[0], c[1], s_[1]])) for c, s_ in zip(crowded, sparse)]
+    scales = np.array([1.0, 0.5, 0.33333334, 2.0], np.float32)
+    devs = [ctx.to_device(h) for h in heads]
+    ctx.detect_batch(devs, 4, scales, conf, 0.4)
+    counts, det, lmk = ctx.detect_fetch(4)
+    cfg = oracle.make_det_cfg(conf_thr=conf, iou_thr=0.4)
+    off, Ks = 0, []
+    for b in range(4):
+        Ks.append(_check_image(oracle, cfg, [h[b] for h in heads], scales[b], det[off:off + counts[b]], lmk[off:off + counts[b]]))
+        off += counts[b]
+    assert off == len(det)
+    assert max(Ks) > 1024 and (conf < 0.7 or min(Ks) <= 1024)
+
+
 def test_score_ties_follow_concat_order(ctx, oracle):
     """Equal scores across strides: the stable order is stride32 | stride16 | stride8, then (h,w,a) (face_detection.rs:410)."""
     heads, _ = synth.make_heads(1, seed=5, n_faces=0, bg=False)
