@@ -382,7 +382,9 @@ def run_ours(args):
 
     # ---- per-kernel device times (the ABI's per-launch CUDA events on the ctx stream, separate untimed loop) and their
     #      algorithmic bytes: preprocess 7,680,000 B/frame; decode 1,008,000 B/image + 64 B/candidate;
-    #      warp min(frame, 3*112^2/|det M|) + 37,632 B/face ----
+    #      warp min(source footprint 3*112^2/|det M|, 112*112 px * 4 taps * 3 B) + 37,632 B/face (the same "footprint or
+    #      taps, whichever is smaller" rule SURVEY 8d applies to the resize: a decimating warp reads 4 taps per output
+    #      pixel, not the whole footprint) ----
     kernels = None
     if not args.no_stages:
         import ctypes as C
@@ -394,7 +396,7 @@ def run_ours(args):
         Mh = Md.download((cap_faces, 2, 3), np.float64)[:faces_per_step]
         okh = okd.download((cap_faces,), np.uint8)[:faces_per_step]
         detM = np.abs(Mh[:, 0, 0] * Mh[:, 1, 1] - Mh[:, 0, 1] * Mh[:, 1, 0])
-        foot = np.where(okh > 0, np.minimum(FRAME_H * FRAME_W * 3.0, 3.0 * 112 * 112 / np.maximum(detM, 1e-12)), 0.0)
+        foot = np.where(okh > 0, np.minimum(112 * 112 * 12.0, 3.0 * 112 * 112 / np.maximum(detM, 1e-12)), 0.0)
         warp_bytes = float(foot.sum() + 37632.0 * faces_per_step)
         view = ctx.detect_view()
         Kc = np.empty(BATCH, np.int32)

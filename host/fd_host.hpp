@@ -150,4 +150,21 @@ private:
     fd_config cfg_{};
 };
 
+// pipeline::module::face_selection::FaceSelection (src/pipeline/module/face_selection.rs:5-189)
+class FaceSelection {
+public:
+    FaceSelection(Context &c, float margin_center_left_ratio = 0.3f, float margin_center_right_ratio = 0.3f, float margin_edge_ratio = 0.1f,
+                  float minimum_face_ratio = 0.0075f)
+        : c_(c), p_{margin_center_left_ratio, margin_center_right_ratio, margin_edge_ratio, minimum_face_ratio} {}
+    // call(&Mat, face_boxes (M,5), key_points (M,5,2) or nullptr, is_enroll) -> {row of the box, row of the key points}; -1 = None
+    std::pair<int, int> call(const Mat &img, const float *face_boxes, const float *key_points, int M, bool is_enroll = false) {
+        int bi = -1, ki = -1;
+        check(fd_face_selection(c_.get(), img.rows, img.cols, face_boxes, key_points, M, is_enroll ? 1 : 0, &p_, &bi, &ki));
+        return {bi, ki};
+    }
+private:
+    Context &c_;
+    fd_select_params p_;
+};
+
 }  // namespace fd

@@ -210,6 +210,35 @@ int fd_crops_to_tensor(fd_ctx *ctx, const uint8_t *crops_dev, int F, int in_h, i
 int fd_model_preprocess(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, int out_h, int out_w,
                         const float *mean_rgb, const float *mul_rgb, float *out_nchw);
 
+/* ---- the CNN's wire format ---------------------------------------------------------------------- */
+/* Triton ModelInferResponse.raw_output_contents -> decode + NMS without a host-side f32 conversion (face_detection.rs:286-312,
+ * utils.rs:126-132 u8_to_f32_vec): raw[i] = the little-endian f32 bytes of output i (any host alignment), nbytes[i] its
+ * length, shape[i] = its 4 dims (N,C,H,W), outputs ordered like fd_detect_batch (scores, bbox, landmarks per stride).
+ * Like the reference, trailing bytes that do not fill an f32 are ignored and a shape whose product differs from the f32
+ * count is an error (Array4::from_shape_vec).  The bytes are copied once, host -> device, and read in place by the decode
+ * kernel (the GPU is little-endian).  Tensors the server already left in device memory (Triton CUDA shared memory,
+ * client.rs:169-188) go to fd_detect_batch directly.  Results as fd_detect_batch; B = shape[0][0]. */
+int fd_detect_batch_raw(fd_ctx *ctx, const uint8_t *const *raw, const size_t *nbytes, const int64_t (*shape)[4], int n_heads,
+                        const float *det_scale_host, float conf_thr, float iou_thr);
+
+/* ---- FaceSelection (pipeline/module/face_selection.rs), one face per image ------------------- */
+typedef struct fd_select_params {   /* FaceSelectionConfig::new, face_pipeline/config.rs:107-116 */
+    float margin_center_left_ratio, margin_center_right_ratio, margin_edge_ratio, minimum_face_ratio;
+} fd_select_params;
+int fd_select_params_default(fd_select_params *p);   /* 0.3, 0.3, 0.1, 0.0075 */
+/* FaceSelection::call (face_selection.rs:72-189) for ONE image, host in/out, computed on the GPU.  face_boxes (M,5);
+ * key_points (M,5,2) or NULL (None).  box_index / kp_index: row of the selected box and of the row whose key points the
+ * reference returns (the FIRST row within 2 px of the selected box), -1 = None. */
+int fd_face_selection(fd_ctx *ctx, int img_h, int img_w, const float *face_boxes, const float *key_points, int M, int is_enroll,
+                      const fd_select_params *params, int *box_index, int *kp_index);
+/* The same over the detections of the last fd_detect_batch, one warp per image, asynchronous.  sel_host (B,2) or NULL:
+ * {row of the selected detection, row of its key points} as rows of the fd_detect_fetch arrays (-1 = None).  With sel_host
+ * the call blocks (and first completes images the detect kernel deferred); without it nothing leaves the device. */
+int fd_select_detections(fd_ctx *ctx, const fd_frame *frames, int B, int is_enroll, const fd_select_params *params, int32_t *sel_host);
+/* FaceAlignment::call on the selection of the last fd_select_detections (face_pipeline/pipeline.rs:216-232): one crop per
+ * image, crops_dev (B,crop_h,crop_w,3); images without a selection get ok = 0 and a zero crop.  M_dev (B,6) / ok_dev (B) optional. */
+int fd_align_selected(fd_ctx *ctx, const fd_frame *frames, int B, uint8_t *crops_dev, double *M_dev, uint8_t *ok_dev);
+
 /* ---- end-to-end with HOST buffers (bench.py "e2e"): H2D frames + heads, full path, D2H results -------- */
 typedef struct fd_host_batch_out {
     int32_t *counts;      /* (B) */

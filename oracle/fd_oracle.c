@@ -785,6 +785,81 @@ FDO_API int fdo_align_face(const uint8_t *img, int h, int w, int pitch, const fl
     return 1;
 }
 
+/* ---- FaceSelection::call (pipeline/module/face_selection.rs:72-189), SURVEY 8(f) N3 --------------------------------------
+ * face_boxes (M,5) rows [x1,y1,x2,y2,score]; has_kps: key_points is Some.  params = {margin_center_left_ratio,
+ * margin_center_right_ratio, margin_edge_ratio, minimum_face_ratio} (face_pipeline/config.rs:107-116).
+ * Writes the row index of the selected box and of the row whose key points are returned (-1 = None). */
+FDO_API void fdo_face_selection(int img_h, int img_w, const float *face_boxes, int M, int has_kps, int is_enroll,
+                                const float params[4], int *box_index, int *kp_index) {
+    *box_index = -1;
+    *kp_index = -1;
+    if (is_enroll) { /* get_biggest_area_face (:28-53): nothing is selected without key points */
+        if (!has_kps) return;
+        float biggest = 0.0f;
+        for (int i = 0; i < M; ++i) {
+            const float *b = face_boxes + 5 * i;
+            volatile float area = (b[2] - b[0]) * (b[3] - b[1]);
+            if (area > biggest) {
+                biggest = area;
+                *box_index = i;
+                *kp_index = i;
+            }
+        }
+        return; /* is_face_area_big_enough (:55-70) does not change the result (:84-101) */
+    }
+    const float w = (float)img_w, h = (float)img_h;
+    volatile float mcl = params[0] * w, mcr = params[1] * w; /* :103-104 */
+    volatile float me0 = params[2] * w;
+    const float me = fminf(50.0f, me0);                       /* :105-106 */
+    volatile float x_cen = w / 2.0f;                           /* :108 */
+    volatile float hw = h * w;
+    volatile float w_me = w - me, h_me = h - me;
+    int n_valid = 0, n_center = 0;
+    unsigned char *valid = (unsigned char *)calloc((size_t)(M > 0 ? M : 1), 1), *center = (unsigned char *)calloc((size_t)(M > 0 ? M : 1), 1);
+    for (int i = 0; i < M; ++i) { /* :110-127 */
+        const float *b = face_boxes + 5 * i;
+        volatile float dx = b[2] - b[0];
+        volatile float area = dx * dx; /* (x_max - x_min) * (x_max - x_min): the reference squares the width (:115) */
+        volatile float sx = b[0] + b[2], sy = b[1] + b[3];
+        volatile float cx = sx / 2.0f, cy = sy / 2.0f;
+        volatile float ratio = area / hw;
+        if (cx >= me && cx <= w_me && cy >= me && cy <= h_me && ratio >= params[3]) {
+            valid[i] = 1;
+            ++n_valid;
+            volatile float d = cx - x_cen; /* :129-135 */
+            if (-mcl <= d && d <= mcr) {
+                center[i] = 1;
+                ++n_center;
+            }
+        }
+    }
+    const int mode = n_center > 0 ? 2 : (n_valid > 0 ? 1 : 0); /* :137-143: centre boxes, else valid boxes, else every box */
+    float max_size = 0.0f;
+    for (int i = 0; i < M; ++i) { /* :145-153 */
+        if ((mode == 2 && !center[i]) || (mode == 1 && !valid[i])) continue;
+        const float *b = face_boxes + 5 * i;
+        volatile float ww = b[2] - b[0], hh = b[3] - b[1];
+        volatile float tem = ww + hh;
+        if (tem > max_size) {
+            max_size = tem;
+            *box_index = i;
+        }
+    }
+    free(valid);
+    free(center);
+    if (*box_index < 0) return; /* :154-156 */
+    if (has_kps) {            /* :158-181: key points of the FIRST row within 2 px of the selected box */
+        const float *o = face_boxes + 5 * (*box_index);
+        for (int i = 0; i < M; ++i) {
+            const float *b = face_boxes + 5 * i;
+            if (fabsf(o[0] - b[0]) <= 2.0f && fabsf(o[1] - b[1]) <= 2.0f && fabsf(o[2] - b[2]) <= 2.0f && fabsf(o[3] - b[3]) <= 2.0f) {
+                *kp_index = i;
+                break;
+            }
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* N1: post-align model preprocessors.  FaceExtraction::_preprocess                  */
 /* (face_extraction.rs:38-77: mean 127.5, mul 0.0078125), FaceQuality::call (face_quality.rs:43-101: */

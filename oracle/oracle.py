@@ -360,6 +360,19 @@ def model_preprocess(img, out_size, mean_rgb, mul_rgb):
     return out
 
 
+SELECT_DEFAULTS = (0.3, 0.3, 0.1, 0.0075)   # FaceSelectionConfig::new (face_pipeline/config.rs:107-116)
+
+
+def face_selection(img_hw, face_boxes, key_points=None, is_enroll=False, params=SELECT_DEFAULTS):
+    """FaceSelection::call (face_selection.rs:72-189) -> (box row index or -1, key-point row index or -1)."""
+    fb = _f32(face_boxes).reshape(-1, 5)
+    prm = _f32(params)
+    bi, ki = C.c_int(-1), C.c_int(-1)
+    lib().fdo_face_selection(int(img_hw[0]), int(img_hw[1]), _p(fb, c_f32p), len(fb), int(key_points is not None), int(bool(is_enroll)),
+                             _p(prm, c_f32p), C.byref(bi), C.byref(ki))
+    return bi.value, ki.value
+
+
 def pipeline_frame(cfg, img, heads, template=ARCFACE_TEMPLATE, crop=(112, 112), pixel_scale=1.0,
                    means=(0, 0, 0), stds=(1, 1, 1), bufs=None):
     """Whole reference CPU path for one frame.  Returns tensor, det, landmarks, crops."""

@@ -104,6 +104,8 @@ struct fd_ctx {
     fd::DevBuf align_M;          // double[F][12] (M, inverse)
     fd::DevBuf align_ok;         // u8[F]
     fd::DevBuf tickets;          // int[16] work tickets of the persistent kernels (zero between launches)
+    fd::DevBuf select_sel, select_lmk, select_fidx;   // fd_select_detections results: int[B][2], float[B][10], int[B]
+    int select_B = 0;
     fd::DevBuf scan_agg;         // u64[B] epoch-tagged kept counts of the fused detect kernel
     unsigned scan_epoch = 0;
     int est_cap = 0;             // faces align_M / align_ok have room for at detect time
@@ -224,6 +226,8 @@ int argsort_device(fd_ctx *ctx, const float *scores_as_dets, int n, int stride, 
 int estimate_launch(fd_ctx *ctx, const float *from_dev, const float *to_dev, const int *count_dev, int F_cap,
                     double *M12_dev, double *M_out_dev, uint8_t *ok_dev, uint8_t *ok_out_dev);
 int ticket_buffer(fd_ctx *ctx);
+int select_launch(fd_ctx *ctx, const int *offsets_dev, const float *det_dev, const float *lmk_dev, const FrameDev *frames_dev, int B,
+                  const fd_select_params *p, int is_enroll, int *sel_dev, float *sel_lmk_dev, int *sel_frame_idx_dev);
 int invert_launch(fd_ctx *ctx, const double *M_dev, int F, double *M12_dev, uint8_t *ok_dev);
 int warp_launch(fd_ctx *ctx, const FrameDev *frames_dev, const int32_t *frame_idx_dev, const double *M12_dev,
                 const uint8_t *ok_dev, const int *count_dev, int F_cap, uint8_t *crops_dev, int cw, int ch);

@@ -3,6 +3,7 @@
 // FaceAlignment::call (face_alignment.rs:27-141) at batch granularity.
 #include <algorithm>
 #include <cstdlib>
+#include <cstddef>
 #include <cstring>
 #include "fd_internal.cuh"
 
@@ -435,6 +436,107 @@ FD_EXPORT int fd_model_preprocess(fd_ctx *ctx, const uint8_t *img, int h, int w,
     FD_CUDA(cudaMemcpyAsync(out_nchw, ctx->scratch[4].p, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
     FD_CUDA(cudaStreamSynchronize(ctx->stream));
     return FD_OK;
+}
+
+// ---- N2: raw_output_contents -> decode --------------------------------------------------------------------------------
+FD_EXPORT int fd_detect_batch_raw(fd_ctx *ctx, const uint8_t *const *raw, const size_t *nbytes, const int64_t (*shape)[4], int n_heads,
+                                  const float *det_scale_host, float conf_thr, float iou_thr) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(raw && nbytes && shape && det_scale_host, "fd_detect_batch_raw: bad arguments");
+    const DecodeCfg &d = ctx->dcfg;
+    FD_REQUIRE(n_heads == 3 * d.n_strides, "fd_detect_batch_raw: n_heads must be 3 * n_strides");
+    const int64_t B = shape[0][0];
+    FD_REQUIRE(B > 0 && B <= (1 << 20), "fd_detect_batch_raw: bad batch dimension");
+    const float *dev_heads[3 * FD_MAX_STRIDES];
+    for (int s = 0; s < d.n_strides; ++s) {
+        const int ch[3] = {2 * d.A, 4 * d.A, 10 * d.A};
+        for (int k = 0; k < 3; ++k) {
+            const int i = 3 * s + k;
+            FD_REQUIRE(raw[i], "fd_detect_batch_raw: null output");
+            const int64_t *sh = shape[i];
+            const int64_t n = sh[0] * sh[1] * sh[2] * sh[3];
+            // Array4::from_shape_vec(dims, u8_to_f32_vec(bytes)): chunks_exact(4) drops a trailing partial element
+            FD_REQUIRE(sh[0] > 0 && sh[1] > 0 && sh[2] > 0 && sh[3] > 0 && (int64_t)(nbytes[i] / 4) == n,
+                       "fd_detect_batch_raw: shape does not match the byte length (ShapeError in the reference)");
+            FD_REQUIRE(sh[0] == B && sh[1] == ch[k] && sh[2] == d.fh[s] && sh[3] == d.fw[s],
+                       "fd_detect_batch_raw: output shape does not match the detector geometry");
+            const size_t bytes = sizeof(float) * (size_t)n;
+            FD_TRY(ctx->pipe_heads[i].reserve(bytes));
+            FD_CUDA(cudaMemcpyAsync(ctx->pipe_heads[i].p, raw[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
+            dev_heads[i] = ctx->pipe_heads[i].as<float>();
+        }
+    }
+    return detect_enqueue(ctx, dev_heads, (int)B, det_scale_host, conf_thr, iou_thr);
+}
+
+// ---- N3: FaceSelection -----------------------------------------------------------------------------------------------
+FD_EXPORT int fd_select_params_default(fd_select_params *p) {
+    FD_REQUIRE(p, "fd_select_params_default: null");
+    p->margin_center_left_ratio = 0.3f;    // face_pipeline/config.rs:110-113
+    p->margin_center_right_ratio = 0.3f;
+    p->margin_edge_ratio = 0.1f;
+    p->minimum_face_ratio = 0.0075f;
+    return FD_OK;
+}
+
+FD_EXPORT int fd_face_selection(fd_ctx *ctx, int img_h, int img_w, const float *face_boxes, const float *key_points, int M, int is_enroll,
+                                const fd_select_params *params, int *box_index, int *kp_index) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(img_h > 0 && img_w > 0 && M >= 0 && (M == 0 || face_boxes) && box_index && kp_index, "fd_face_selection: bad arguments");
+    fd_select_params p;
+    if (params) p = *params;
+    else FD_TRY(fd_select_params_default(&p));
+    const size_t nb = sizeof(float) * 5 * (size_t)std::max(M, 1), nl = sizeof(float) * 10 * (size_t)std::max(M, 1);
+    FD_TRY(ctx->scratch[0].reserve(nb));
+    FD_TRY(ctx->scratch[1].reserve(nl));
+    FD_TRY(ctx->scratch[2].reserve(sizeof(FrameDev) + 4 * sizeof(int)));
+    if (M) FD_CUDA(cudaMemcpyAsync(ctx->scratch[0].p, face_boxes, sizeof(float) * 5 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+    if (M && key_points) FD_CUDA(cudaMemcpyAsync(ctx->scratch[1].p, key_points, sizeof(float) * 10 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+    struct { FrameDev f; int off[2]; int sel[2]; } h;
+    memset(&h, 0, sizeof(h));
+    h.f.h = img_h; h.f.w = img_w;
+    h.off[0] = 0; h.off[1] = M;
+    FD_CUDA(cudaMemcpyAsync(ctx->scratch[2].p, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+    unsigned char *base = ctx->scratch[2].as<unsigned char>();
+    FD_TRY(select_launch(ctx, reinterpret_cast<int *>(base + offsetof(decltype(h), off)), ctx->scratch[0].as<float>(),
+                         key_points ? ctx->scratch[1].as<float>() : nullptr, reinterpret_cast<FrameDev *>(base), 1, &p, is_enroll,
+                         reinterpret_cast<int *>(base + offsetof(decltype(h), sel)), nullptr, nullptr));
+    int sel[2];
+    FD_CUDA(cudaMemcpyAsync(sel, base + offsetof(decltype(h), sel), sizeof(sel), cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    *box_index = sel[0];
+    *kp_index = sel[1];
+    return FD_OK;
+}
+
+FD_EXPORT int fd_select_detections(fd_ctx *ctx, const fd_frame *frames, int B, int is_enroll, const fd_select_params *params, int32_t *sel_host) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(frames && B > 0 && B == ctx->last_B, "fd_select_detections: needs the frames of the last fd_detect_batch");
+    if (sel_host) FD_TRY(detect_resolve(ctx));
+    fd_select_params p;
+    if (params) p = *params;
+    else FD_TRY(fd_select_params_default(&p));
+    FD_TRY(upload_frame_table(ctx, frames, B, nullptr, nullptr));
+    FD_TRY(ctx->select_sel.reserve(sizeof(int) * 2 * (size_t)B));
+    FD_TRY(ctx->select_lmk.reserve(sizeof(float) * 10 * (size_t)B));
+    FD_TRY(ctx->select_fidx.reserve(sizeof(int) * (size_t)B));
+    FD_TRY(select_launch(ctx, ctx->out_offsets.as<int>(), ctx->out_det.as<float>(), ctx->out_lmk.as<float>(), ctx->frames_dev.as<FrameDev>(), B,
+                         &p, is_enroll, ctx->select_sel.as<int>(), ctx->select_lmk.as<float>(), ctx->select_fidx.as<int>()));
+    ctx->select_B = B;
+    if (sel_host) {
+        FD_CUDA(cudaMemcpyAsync(sel_host, ctx->select_sel.p, sizeof(int) * 2 * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+        FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return FD_OK;
+}
+
+FD_EXPORT int fd_align_selected(fd_ctx *ctx, const fd_frame *frames, int B, uint8_t *crops_dev, double *M_dev, uint8_t *ok_dev) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(frames && B > 0 && B == ctx->select_B && crops_dev, "fd_align_selected: needs the frames of the last fd_select_detections");
+    FD_TRY(upload_frame_table(ctx, frames, B, nullptr, nullptr));
+    // images without a selection carry NaN key points: the estimate fails there (ok = 0) and the crop is zero-filled
+    return align_enqueue(ctx, ctx->frames_dev.as<FrameDev>(), ctx->select_lmk.as<float>(), ctx->select_fidx.as<int32_t>(), nullptr, B, crops_dev,
+                         M_dev, ok_dev, false);
 }
 
 // ---- end-to-end with host buffers ------------------------------------------------------------------------------------

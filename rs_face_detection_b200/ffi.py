@@ -74,7 +74,8 @@ SYMBOLS = [
     "fd_nonlinear_transform", "fd_bbox_overlaps", "fd_letterbox_geometry", "fd_preprocess", "fd_resize_linear",
     "fd_detect", "fd_estimate_affine_partial_2d", "fd_warp_affine", "fd_align",
     "fd_nms_device", "fd_preprocess_batch", "fd_detect_batch", "fd_detect_fetch", "fd_detect_view", "fd_align_batch",
-    "fd_align_detections", "fd_crops_to_tensor", "fd_model_preprocess", "fd_pipeline_host", "fd_pipeline_tensor_dev",
+    "fd_align_detections", "fd_crops_to_tensor", "fd_model_preprocess", "fd_detect_batch_raw", "fd_select_params_default", "fd_face_selection",
+    "fd_select_detections", "fd_align_selected", "fd_pipeline_host", "fd_pipeline_tensor_dev",
 ]
 
 _lib = None
@@ -481,6 +482,39 @@ class Context:
         arr = self._frames(frames)
         _chk(self.lib.fd_align_detections(self.handle, arr, len(frames), C.c_void_p(_devptr(crops_dev)), cap_faces,
                                           C.c_void_p(_devptr(M_dev)), C.c_void_p(_devptr(ok_dev))))
+
+    # ---- N2: Triton raw_output_contents
+    def detect_batch_raw(self, raw, shapes, det_scale, conf_thr, iou_thr):
+        """raw: list of bytes-like objects (little-endian f32), shapes: list of 4-tuples (N,C,H,W)"""
+        n = len(raw)
+        keep = [np.frombuffer(r, np.uint8) if not isinstance(r, np.ndarray) else r for r in raw]
+        ptrs = (C.c_void_p * n)(*[k.ctypes.data for k in keep])
+        nb = (C.c_size_t * n)(*[k.nbytes for k in keep])
+        sh = ((C.c_int64 * 4) * n)(*[(C.c_int64 * 4)(*s_) for s_ in shapes])
+        ds = _f32(det_scale)
+        _chk(self.lib.fd_detect_batch_raw(self.handle, ptrs, nb, sh, n, _ptr(ds, c_f32p), C.c_float(conf_thr), C.c_float(iou_thr)))
+
+    # ---- N3: FaceSelection
+    def face_selection(self, img_hw, face_boxes, key_points=None, is_enroll=False, params=None):
+        fb = _f32(face_boxes).reshape(-1, 5)
+        kp = None if key_points is None else _f32(key_points).reshape(-1, 10)
+        prm = None if params is None else (C.c_float * 4)(*params)
+        bi, ki = C.c_int(-1), C.c_int(-1)
+        _chk(self.lib.fd_face_selection(self.handle, int(img_hw[0]), int(img_hw[1]), _ptr(fb, c_f32p), None if kp is None else _ptr(kp, c_f32p),
+                                        len(fb), int(bool(is_enroll)), prm, C.byref(bi), C.byref(ki)))
+        return bi.value, ki.value
+
+    def select_detections(self, frames, is_enroll=False, params=None, fetch=True):
+        arr = self._frames(frames)
+        prm = None if params is None else (C.c_float * 4)(*params)
+        sel = np.empty((len(frames), 2), np.int32) if fetch else None
+        _chk(self.lib.fd_select_detections(self.handle, arr, len(frames), int(bool(is_enroll)), prm, None if sel is None else _ptr(sel, c_i32p)))
+        return sel
+
+    def align_selected(self, frames, crops_dev, M_dev=None, ok_dev=None):
+        arr = self._frames(frames)
+        _chk(self.lib.fd_align_selected(self.handle, arr, len(frames), C.c_void_p(_devptr(crops_dev)), C.c_void_p(_devptr(M_dev)),
+                                        C.c_void_p(_devptr(ok_dev))))
 
     def crops_to_tensor(self, crops_dev, F, in_hw, out_hw, mean_rgb, mul_rgb, out_dev, use_detect_count=False):
         mean, mul = _f32(mean_rgb), _f32(mul_rgb)

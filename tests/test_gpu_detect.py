@@ -132,3 +132,43 @@ def test_nan_score_is_an_error(ctx):
     heads[3][0, 2, 3, 3] = np.nan
     with pytest.raises(FdError):
         ctx.detect([h[0] for h in heads], 1.0, 0.7, 0.45)
+
+
+def test_detect_from_raw_output_contents(ctx, oracle):
+    """Triton raw_output_contents (little-endian f32 bytes at arbitrary host alignment) straight into the
+    decode kernel; same results as the f32 path, the reference's shape check reproduced (face_detection.rs:286-312)."""
+    from rs_face_detection_b200 import FdError
+    B = 3
+    heads, _ = synth.make_heads(B, seed=31, n_faces=10)
+    ds = np.array([1.0, 0.5, 0.25], np.float32)
+    raw, shapes = [], []
+    for i, h in enumerate(heads):
+        buf = np.empty(h.nbytes + 7, np.uint8)
+        view = buf[1 + (i % 3):1 + (i % 3) + h.nbytes]          # deliberately unaligned
+        view[:] = np.frombuffer(h.astype("<f4").tobytes(), np.uint8)
+        raw.append(view)
+        shapes.append(h.shape)
+    ctx.detect_batch_raw(raw, shapes, ds, 0.7, 0.45)
+    counts, det, lmk = ctx.detect_fetch(B)
+    devs = [ctx.to_device(h) for h in heads]
+    ctx.detect_batch(devs, B, ds, 0.7, 0.45)
+    counts2, det2, lmk2 = ctx.detect_fetch(B)
+    np.testing.assert_array_equal(counts, counts2)
+    np.testing.assert_array_equal(det, det2)
+    np.testing.assert_array_equal(lmk, lmk2)
+    cfg = oracle.make_det_cfg(conf_thr=0.7, iou_thr=0.45)
+    off = 0
+    for b in range(B):
+        _check_image(oracle, cfg, [h[b] for h in heads], ds[b], det[off:off + counts[b]], lmk[off:off + counts[b]])
+        off += counts[b]
+    # trailing bytes that do not fill an f32 are ignored (chunks_exact) ...
+    longer = [np.concatenate([r, np.zeros(3, np.uint8)]) for r in raw]
+    ctx.detect_batch_raw(longer, shapes, ds, 0.7, 0.45)
+    np.testing.assert_array_equal(ctx.detect_fetch(B)[1], det)
+    # ... a shape whose product differs from the f32 count is an error, as is a foreign geometry
+    bad = list(shapes)
+    bad[0] = (B, 4, 20, 21)
+    with pytest.raises(FdError):
+        ctx.detect_batch_raw(raw, bad, ds, 0.7, 0.45)
+    with pytest.raises(FdError):
+        ctx.detect_batch_raw([r[:-4] for r in raw], shapes, ds, 0.7, 0.45)

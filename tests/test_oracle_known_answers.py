@@ -137,3 +137,29 @@ def test_model_preprocess_known_values(oracle):
     assert out.shape == (3, 2, 2)
     np.testing.assert_array_equal(out[:, 0, 0], np.float32([(30 - 127.5) * 0.0078125, (20 - 127.5) * 0.0078125, (10 - 127.5) * 0.0078125]))
     np.testing.assert_array_equal(out[:, 1, 1], np.float32([-127.5 * 0.0078125] * 3))
+
+
+def test_face_selection_hand_derived(oracle):
+    """FaceSelection::call (face_selection.rs:72-189) on hand-derived cases (the reference has no test for it)."""
+    fb = np.array([[100, 100, 200, 220, .9],      # left of the centre band (|cx - 960| > 0.3 * 1920)
+                   [900, 400, 1100, 640, .8],     # central, size 200 + 240 = 440  -> selected
+                   [10, 10, 60, 70, .99],         # centre inside the 50 px edge margin -> invalid
+                   [902, 401, 1099, 641, .7]], np.float32)   # central, size 437
+    kps = np.zeros((4, 5, 2), np.float32)
+    assert oracle.face_selection((1080, 1920), fb, kps) == (1, 1)
+    assert oracle.face_selection((1080, 1920), fb, None) == (1, -1)                 # key_points = None
+    assert oracle.face_selection((1080, 1920), fb[:0], kps[:0]) == (-1, -1)         # no detections -> (None, None)
+    # key points come from the FIRST row within 2 px of the selected box (:160-176), not necessarily the box itself
+    fb2 = np.array([[899, 399, 1099, 639, .5], [900, 400, 1101, 640.5, .8]], np.float32)
+    assert oracle.face_selection((1080, 1920), fb2, kps[:2]) == (1, 0)
+    # no central box -> the valid boxes compete; none valid -> every box competes (:137-143)
+    assert oracle.face_selection((1080, 1920), fb[[0, 2]], kps[:2]) == (0, 0)
+    assert oracle.face_selection((1080, 1920), fb[[2]], kps[:1]) == (0, 0)
+    # the minimum-size test squares the WIDTH (:115): a 300 x 20 sliver is "big enough", a 20 x 300 one is not
+    sl = np.array([[800, 500, 1100, 520, .9], [950, 300, 970, 600, .9]], np.float32)
+    assert oracle.face_selection((1080, 1920), sl, kps[:2]) == (0, 0)
+    # enroll: biggest (x2-x1)*(y2-y1), first maximum wins, nothing without key points (:28-53)
+    assert oracle.face_selection((1080, 1920), fb, kps, is_enroll=True) == (1, 1)
+    assert oracle.face_selection((1080, 1920), fb, None, is_enroll=True) == (-1, -1)
+    eq = np.array([[0, 0, 10, 10, .1], [5, 5, 15, 15, .2]], np.float32)
+    assert oracle.face_selection((100, 100), eq, kps[:2], is_enroll=True) == (0, 0)
