@@ -500,6 +500,7 @@ int warp_launch(fd_ctx *ctx, const FrameDev *frames_dev, const int32_t *frame_id
     if (cw == 112 && ch == 112 && (reinterpret_cast<uintptr_t>(crops_dev) & 3) == 0) {
         // 14-row items (8 per face, 7 rounds per thread as 4 + 3): small enough that the last items of a launch leave
         // no long tail (28 rows: +10 % time), large enough to amortise the per-item setup (8 rows: same time, 4: +8 %).
+        // 4 rounds in flight per thread (72 registers, 4 CTAs/SM); 2, 3 measure the same, 7 (104 registers) is 35 % slower.
         constexpr int IR = 14;
         void (*kern)(WarpArgs) = warp_fixed_kernel<112, 112, IR, 4>;
         static int per_sm_fixed = 0;

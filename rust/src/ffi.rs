@@ -27,6 +27,11 @@ pub struct fd_host_batch_out {
     pub counts: *mut i32, pub det: *mut f32, pub landmarks: *mut f32, pub crops: *mut u8, pub det_scale: *mut f32,
     pub tensor: *mut f32, pub cap_rows: i32, pub total: i32, pub h2d_bytes: i64, pub d2h_bytes: i64,
 }
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct fd_select_params {
+    pub margin_center_left_ratio: f32, pub margin_center_right_ratio: f32, pub margin_edge_ratio: f32, pub minimum_face_ratio: f32,
+}
 pub enum fd_ctx {}
 
 extern "C" {
@@ -61,6 +66,19 @@ extern "C" {
     pub fn fd_detect_batch(ctx: *mut fd_ctx, heads_dev: *const *const f32, n_heads: c_int, b: c_int, det_scale_host: *const f32, conf_thr: f32, iou_thr: f32) -> c_int;
     pub fn fd_detect_fetch(ctx: *mut fd_ctx, counts: *mut i32, det: *mut f32, landmarks: *mut f32, cap_rows: c_int, total: *mut c_int) -> c_int;
     pub fn fd_align_detections(ctx: *mut fd_ctx, frames: *const fd_frame, b: c_int, crops_dev: *mut u8, cap_faces: c_int, m_dev: *mut f64, ok_dev: *mut u8) -> c_int;
+    // SURVEY 8(f) "next" rows: model preprocessors on the crops, Triton raw_output_contents, FaceSelection
+    pub fn fd_crops_to_tensor(ctx: *mut fd_ctx, crops_dev: *const u8, f: c_int, in_h: c_int, in_w: c_int, out_h: c_int, out_w: c_int,
+                              mean_rgb: *const f32, mul_rgb: *const f32, out_nchw_dev: *mut f32, use_detect_count: c_int) -> c_int;
+    pub fn fd_model_preprocess(ctx: *mut fd_ctx, img: *const u8, h: c_int, w: c_int, pitch: c_int, out_h: c_int, out_w: c_int,
+                               mean_rgb: *const f32, mul_rgb: *const f32, out_nchw: *mut f32) -> c_int;
+    pub fn fd_detect_batch_raw(ctx: *mut fd_ctx, raw: *const *const u8, nbytes: *const usize, shape: *const [i64; 4], n_heads: c_int,
+                               det_scale_host: *const f32, conf_thr: f32, iou_thr: f32) -> c_int;
+    pub fn fd_select_params_default(p: *mut fd_select_params) -> c_int;
+    pub fn fd_face_selection(ctx: *mut fd_ctx, img_h: c_int, img_w: c_int, face_boxes: *const f32, key_points: *const f32, m: c_int,
+                             is_enroll: c_int, params: *const fd_select_params, box_index: *mut c_int, kp_index: *mut c_int) -> c_int;
+    pub fn fd_select_detections(ctx: *mut fd_ctx, frames: *const fd_frame, b: c_int, is_enroll: c_int, params: *const fd_select_params,
+                                sel_host: *mut i32) -> c_int;
+    pub fn fd_align_selected(ctx: *mut fd_ctx, frames: *const fd_frame, b: c_int, crops_dev: *mut u8, m_dev: *mut f64, ok_dev: *mut u8) -> c_int;
     pub fn fd_pipeline_host(ctx: *mut fd_ctx, frames: *const fd_frame, b: c_int, heads_host: *const *const f32, n_heads: c_int,
                             conf_thr: f32, iou_thr: f32, out: *mut fd_host_batch_out) -> c_int;
 }
