@@ -337,6 +337,8 @@ def run_ours(args):
     pipelined = None
     if not args.no_pipelined:
         ctx2 = Context(local_rank)
+        ctx.set_sharing(2)
+        ctx2.set_sharing(2)
         ext2 = torch.cuda.ExternalStream(ctx2.stream(), device=local_rank)
         tensor2_t = torch.empty_like(tensor_t)
         crops2_t = torch.empty_like(crops_t)
@@ -364,9 +366,10 @@ def run_ours(args):
         barrier()
         span = max(a.elapsed_time(b) for a in s0 for b in s1) / 1e3
         span = dist_max(span)
+        ctx.set_sharing(1)
         pipelined = {"value": BATCH * args.steps * world / span, "unit": "frames/s", "batches_in_flight": 2,
                      "ms_per_step": 1e3 * span / args.steps,
-                     "note": "same steps alternated over two fd_ctx (two streams, two workspaces) on each GPU"}
+                     "note": "same steps alternated over two fd_ctx (two streams, two workspaces, fd_ctx_set_sharing(2)) on each GPU"}
 
     # ---- per-stage device times (CUDA events on the launching stream, separate untimed loop) ----
     def time_stage(fn, n=20):
@@ -446,6 +449,8 @@ def run_ours(args):
         e2e_steps = max(4, min(args.steps, 20)) // 2 * 2
         # two host threads, one fd_ctx each, alternate batches: the H2D of one batch overlaps the compute + D2H of the other
         e2e_ctx = [ctx, Context(local_rank)]
+        for c_ in e2e_ctx:
+            c_.set_sharing(2)
         e2e_bufs = [bufs, dict(counts=pin((BATCH,), torch.int32), det=pin((cap_rows, 5), torch.float32), lmk=pin((cap_rows, 10), torch.float32),
                                crops=pin((cap_rows, 112, 112, 3), torch.uint8), det_scale=pin((BATCH,), torch.float32), tensor=None)]
         res = [None, None]
@@ -469,6 +474,7 @@ def run_ours(args):
         e2e_secs = dist_max(e2e_run(e2e_steps // 2))
         _, total, h2d, d2h = res[0]
         # strictly serial variant (one context, one batch at a time) for reference
+        ctx.set_sharing(1)
         t0 = time.perf_counter()
         for _ in range(4):
             ctx.pipeline_host(host_frames, host_heads, cap_rows, CONF_THR, IOU_THR, bufs=bufs)

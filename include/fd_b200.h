@@ -68,6 +68,10 @@ int fd_ctx_get_config(const fd_ctx *ctx, fd_config *out);
 int fd_ctx_total_anchors(const fd_ctx *ctx, int32_t *out);   /* sum over strides of H*W*A (16800) */
 void *fd_ctx_stream(fd_ctx *ctx);                             /* cudaStream_t */
 int fd_ctx_synchronize(fd_ctx *ctx);
+/* Tuning knob: tell the ctx how many contexts keep batches in flight on this GPU at the same time (default 1).  With
+ * more than one, the per-image detect kernel is launched in its 32-register build so that it shares its SMs with the
+ * other batch's bandwidth-bound kernels (slower alone, faster in aggregate).  Results are identical. */
+int fd_ctx_set_sharing(fd_ctx *ctx, int contexts_in_flight);
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 int fd_ctx_launch_count(const fd_ctx *ctx, int64_t *out);
 

@@ -361,6 +361,11 @@ FD_EXPORT int fd_ctx_profile_fetch(fd_ctx *ctx, char *buf, size_t cap) {
     memcpy(buf, out.c_str(), out.size() + 1);
     return FD_OK;
 }
+FD_EXPORT int fd_ctx_set_sharing(fd_ctx *ctx, int contexts_in_flight) {
+    FD_TRY(check_ctx(ctx));
+    ctx->share_sms = contexts_in_flight > 1;
+    return FD_OK;
+}
 FD_EXPORT int fd_ctx_launch_count(const fd_ctx *ctx, int64_t *out) {
     FD_REQUIRE(ctx && out, "fd_ctx_launch_count: null");
     *out = ctx->launches;

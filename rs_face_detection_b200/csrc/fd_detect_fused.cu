@@ -163,7 +163,7 @@ __device__ __forceinline__ void fused_stamp(const FusedArgs &a, int b, int slot)
     }
 }
 
-__global__ void __launch_bounds__(FT, 1) detect_fused_kernel(const __grid_constant__ FusedArgs a) {
+__device__ __forceinline__ void detect_fused_body(const FusedArgs &a) {
     extern __shared__ __align__(16) unsigned char fused_raw[];
     FusedSmem &sm = *reinterpret_cast<FusedSmem *>(fused_raw);
     const DecodeCfg &c = a.c;
@@ -354,6 +354,13 @@ __global__ void __launch_bounds__(FT, 1) detect_fused_kernel(const __grid_consta
     }
 }
 
+// Two builds of the same body.  "latency": up to 64 registers, the whole register file of the SM for the one resident CTA —
+// the fastest single launch.  "shared": capped at 32 registers (spills go to L1) so the image's CTA leaves half of the SM's
+// registers, threads and shared memory to the bandwidth-bound kernels of another in-flight batch (preprocess / warp CTAs
+// co-reside): measured -4 % on a strictly serial stream, +13 % with two batches in flight (fd_ctx_set_sharing).
+__global__ void __launch_bounds__(FT, 1) detect_fused_kernel(const __grid_constant__ FusedArgs a) { detect_fused_body(a); }
+__global__ void __maxnreg__(32) detect_fused_shared_kernel(const __grid_constant__ FusedArgs a) { detect_fused_body(a); }
+
 // Returns FD_OK and sets *launched; *launched == false means the geometry is not eligible and the caller runs the
 // three-kernel path.  est_cap: capacity (faces) of ctx->align_M / ctx->align_ok.
 int detect_fused_launch(fd_ctx *ctx, const float *const *heads_dev, int B, float conf_thr, float iou_thr, int est_cap, bool *launched) {
@@ -406,8 +413,9 @@ int detect_fused_launch(fd_ctx *ctx, const float *const *heads_dev, int B, float
         cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 16 * 4096, ctx->stream);
         a.dbg = dbg_dev;
     }
-    FD_CUDA(cudaFuncSetAttribute(detect_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    detect_fused_kernel<<<B, FT, smem, ctx->stream>>>(a);
+    void (*kern)(const FusedArgs) = ctx->share_sms ? detect_fused_shared_kernel : detect_fused_kernel;
+    FD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B, FT, smem, ctx->stream>>>(a);
     FD_LAUNCH_CHECK_NAMED(ctx, "detect_fused_kernel");
     if (dbg_on) {
         std::vector<long long> h(16 * (size_t)std::min(B, 4096));

@@ -65,7 +65,7 @@ class FdHostBatchOut(C.Structure):
 SYMBOLS = [
     "fd_abi_version", "fd_last_error", "fd_config_default", "fd_device_count", "fd_ctx_create", "fd_ctx_destroy",
     "fd_ctx_get_config", "fd_ctx_total_anchors", "fd_ctx_stream", "fd_ctx_synchronize", "fd_ctx_launch_count",
-    "fd_ctx_profile", "fd_ctx_profile_fetch",
+    "fd_ctx_profile", "fd_ctx_profile_fetch", "fd_ctx_set_sharing",
     "fd_dev_alloc", "fd_dev_free", "fd_host_alloc_pinned", "fd_host_free_pinned", "fd_memcpy_h2d", "fd_memcpy_d2h",
     "fd_memcpy_h2d_async", "fd_memcpy_d2h_async", "fd_memset_dev",
     "fd_generate_anchors", "fd_generate_anchors2", "fd_generate_anchors_fpn", "fd_generate_anchors_fpn2",
@@ -247,6 +247,9 @@ class Context:
         n = C.c_int64()
         _chk(self.lib.fd_ctx_launch_count(self.handle, C.byref(n)))
         return n.value
+
+    def set_sharing(self, contexts_in_flight):
+        _chk(self.lib.fd_ctx_set_sharing(self.handle, int(contexts_in_flight)))
 
     def profile(self, enable=True):
         """per-kernel CUDA-event marks on the ctx stream (bench.py's per-kernel lines)"""

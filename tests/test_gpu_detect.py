@@ -172,3 +172,20 @@ def test_detect_from_raw_output_contents(ctx, oracle):
         ctx.detect_batch_raw(raw, bad, ds, 0.7, 0.45)
     with pytest.raises(FdError):
         ctx.detect_batch_raw([r[:-4] for r in raw], shapes, ds, 0.7, 0.45)
+
+
+def test_shared_sm_build_gives_identical_results(ctx):
+    """fd_ctx_set_sharing(2) launches the 32-register build of the fused detect kernel: same bits out."""
+    heads, _ = synth.make_heads(5, seed=41, n_faces=15)
+    devs = [ctx.to_device(h) for h in heads]
+    ds = np.array([1.0, 0.5, 0.25, 1 / 3, 2.0], np.float32)
+    ctx.detect_batch(devs, 5, ds, 0.7, 0.4)
+    ref = ctx.detect_fetch(5)
+    ctx.set_sharing(2)
+    try:
+        ctx.detect_batch(devs, 5, ds, 0.7, 0.4)
+        got = ctx.detect_fetch(5)
+    finally:
+        ctx.set_sharing(1)
+    for a, b in zip(ref, got):
+        np.testing.assert_array_equal(a, b)
