@@ -152,11 +152,11 @@ int decode_launch(fd_ctx *ctx, const float *const *heads_dev, int B, float conf_
     if (vec4) {
         dim3 grid((ctx->dcfg.total_pos / 4 + 255) / 256, B);
         decode_kernel<4><<<grid, 256, 0, ctx->stream>>>(ctx->dcfg, hp, conf_thr, ctx->cand_keys.as<u64>(), ctx->cand_box.as<float4>(),
-                                                       ctx->cand_lmk.as<float>(), ctx->cand_count.as<int>(), ctx->status_dev.as<int>());
+                                                       ctx->cand_lmk.as<float>(), ctx->cand_count.as<int>(), ctx->status());
     } else {
         dim3 grid((ctx->dcfg.total_pos + 255) / 256, B);
         decode_kernel<1><<<grid, 256, 0, ctx->stream>>>(ctx->dcfg, hp, conf_thr, ctx->cand_keys.as<u64>(), ctx->cand_box.as<float4>(),
-                                                       ctx->cand_lmk.as<float>(), ctx->cand_count.as<int>(), ctx->status_dev.as<int>());
+                                                       ctx->cand_lmk.as<float>(), ctx->cand_count.as<int>(), ctx->status());
     }
     FD_LAUNCH_CHECK_NAMED(ctx, "decode_kernel");
     return FD_OK;
@@ -167,7 +167,7 @@ int finalize_launch(fd_ctx *ctx, int B) {
                                                 ctx->cand_box.as<float4>(), ctx->cand_lmk.as<float>(),
                                                 ctx->det_scale_dev.as<float>(), ctx->out_offsets.as<int>(),
                                                 ctx->out_det.as<float>(), ctx->out_lmk.as<float>(),
-                                                ctx->out_frame_idx.as<int>(), ctx->status_dev.as<int>());
+                                                ctx->out_frame_idx.as<int>(), ctx->status());
     FD_LAUNCH_CHECK_NAMED(ctx, "finalize_kernel");
     return FD_OK;
 }

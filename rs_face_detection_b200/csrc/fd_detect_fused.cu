@@ -40,6 +40,7 @@ struct FusedArgs {
     int *keep;            // [B][TA] kept anchor ids in pick order
     int *keep_count;      // [B]  (-1: deferred)
     int *status;          // [0] NaN flag, [1] deferred images, [2] total faces
+    int *status_next;     // the other half of the ping-pong: zeroed by the last CTA for the next call
     int *big_list;
     const float *det_scale;
     int *offsets;         // [B+1]
@@ -349,6 +350,8 @@ __device__ __forceinline__ void detect_fused_body(const FusedArgs &a) {
         if (atomicAdd(a.ticket + 1, 1) == (int)gridDim.x - 1) {
             a.ticket[0] = 0;
             a.ticket[1] = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a.status_next[k] = 0;
             __threadfence();
         }
     }
@@ -389,7 +392,8 @@ int detect_fused_launch(fd_ctx *ctx, const float *const *heads_dev, int B, float
     a.counts = ctx->cand_count.as<int>();
     a.keep = ctx->keep_src.as<int>();
     a.keep_count = ctx->keep_count.as<int>();
-    a.status = ctx->status_dev.as<int>();
+    a.status = ctx->status();
+    a.status_next = reinterpret_cast<int *>(ctx->status_dev.p) + (ctx->status_cur ^ 8);
     a.big_list = ctx->big_list.as<int>();
     a.det_scale = ctx->det_scale_dev.as<float>();
     a.offsets = ctx->out_offsets.as<int>();

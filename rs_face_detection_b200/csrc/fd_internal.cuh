@@ -95,7 +95,9 @@ struct fd_ctx {
     fd::DevBuf cand_lmk;         // float[B][total_anchors][10]
     fd::DevBuf keep_src;         // int[B][total_anchors] kept anchor ids in pick order
     fd::DevBuf keep_count;       // int[B]
-    fd::DevBuf status_dev;       // int[8]: [0]=nan flag, [1]=n_big, [2]=total faces
+    fd::DevBuf status_dev;       // int[2][8], ping-pong per detect call: [0]=nan flag, [1]=n_big, [2]=total faces, [4..7] scratch
+    int status_cur = 0;          // half (0 or 8) the last fd_detect_batch used
+    int *status() const { return reinterpret_cast<int *>(status_dev.p) + status_cur; }
     fd::DevBuf big_list;         // int[B] images that need the big path
     fd::DevBuf out_offsets;      // int[B+1]
     fd::DevBuf out_det;          // float[total][5]

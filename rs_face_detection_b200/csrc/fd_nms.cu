@@ -1473,7 +1473,7 @@ int nms_batch_launch(fd_ctx *ctx, int B, float iou_thr) {
     a.keep = ctx->keep_src.as<int>();
     a.keep_stride = (size_t)TA;
     a.keep_count = ctx->keep_count.as<int>();
-    a.status = ctx->status_dev.as<int>();
+    a.status = ctx->status();
     a.big_list = ctx->big_list.as<int>();
     return launch_small<0>(ctx, a, B, true);
 }
@@ -1493,7 +1493,7 @@ int nms_batch_small_image(fd_ctx *ctx, int b, int K, float iou_thr) {
     a.keep = ctx->keep_src.as<int>() + (size_t)b * TA;
     a.keep_stride = (size_t)TA;
     a.keep_count = ctx->keep_count.as<int>() + b;
-    a.status = ctx->status_dev.as<int>() + 4;   // scratch flags: the batch's own flags were already read
+    a.status = ctx->status() + 4;   // scratch flags: the batch's own flags were already read
     a.big_list = nullptr;
     return launch_small<0>(ctx, a, 1, true);
 }

@@ -101,7 +101,7 @@ static int detect_resolve(fd_ctx *ctx) {
     if (!ctx->detect_pending) return FD_OK;
     const int B = ctx->last_B;
     int st[4] = {0, 0, 0, 0};
-    FD_CUDA(cudaMemcpyAsync(st, ctx->status_dev.p, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(cudaMemcpyAsync(st, ctx->status(), sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
     FD_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->detect_pending = false;
     if (st[0]) return fail(FD_ERR_NAN_SCORE, "fd_detect_batch: NaN score (the reference panics, utils.rs:92)");
@@ -117,7 +117,7 @@ static int detect_resolve(fd_ctx *ctx) {
         ctx->est_valid = false;
         if (ctx->align_replay)  // the crops were produced from incomplete detections: align again
             FD_TRY(align_enqueue(ctx, ctx->frames_dev.as<FrameDev>(), ctx->out_lmk.as<float>(), ctx->out_frame_idx.as<int32_t>(),
-                                 ctx->status_dev.as<int>() + 2, ctx->align_cap, ctx->align_crops, ctx->align_M_out, ctx->align_ok_out, true));
+                                 ctx->status() + 2, ctx->align_cap, ctx->align_crops, ctx->align_M_out, ctx->align_ok_out, true));
         FD_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     return FD_OK;
@@ -132,7 +132,10 @@ static int reserve_detect(fd_ctx *ctx, int B) {
     FD_TRY(ctx->cand_lmk.reserve(sizeof(float) * 12 * n));
     FD_TRY(ctx->keep_src.reserve(sizeof(int) * n));
     FD_TRY(ctx->keep_count.reserve(sizeof(int) * B));
-    FD_TRY(ctx->status_dev.reserve(sizeof(int) * 8));
+    if (!ctx->status_dev.p) {   // both halves start at zero; afterwards every detect call leaves the OTHER half zeroed
+        FD_TRY(ctx->status_dev.reserve(sizeof(int) * 16));
+        FD_CUDA(cudaMemsetAsync(ctx->status_dev.p, 0, sizeof(int) * 16, ctx->stream));
+    }
     FD_TRY(ctx->big_list.reserve(sizeof(int) * B));
     FD_TRY(ctx->out_offsets.reserve(sizeof(int) * (B + 1)));
     FD_TRY(ctx->out_det.reserve(sizeof(float) * 5 * n));
@@ -156,10 +159,12 @@ static int detect_enqueue(fd_ctx *ctx, const float *const *heads_dev, int B, con
         FD_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
         ctx->det_scale_shadow.assign(det_scale_host, det_scale_host + B);
     }
-    FD_CUDA(cudaMemsetAsync(ctx->status_dev.p, 0, sizeof(int) * 8, ctx->stream));
+    // status flags: the half the previous call did not use was zeroed by that call's kernel (no memset node on the stream)
+    ctx->status_cur ^= 8;
     bool fused = false;
     FD_TRY(detect_fused_launch(ctx, heads_dev, B, conf_thr, iou_thr, ctx->est_cap, &fused));
     if (!fused) {
+        FD_CUDA(cudaMemsetAsync(ctx->status_dev.p, 0, sizeof(int) * 16, ctx->stream));
         FD_CUDA(cudaMemsetAsync(ctx->cand_count.p, 0, sizeof(int) * (size_t)B, ctx->stream));
         FD_TRY(decode_launch(ctx, heads_dev, B, conf_thr));
         FD_TRY(nms_batch_launch(ctx, B, iou_thr));
@@ -260,7 +265,7 @@ FD_EXPORT int fd_align_detections(fd_ctx *ctx, const fd_frame *frames, int B, ui
     ctx->align_M_out = M_dev;
     ctx->align_ok_out = ok_dev;
     return align_enqueue(ctx, ctx->frames_dev.as<FrameDev>(), ctx->out_lmk.as<float>(), ctx->out_frame_idx.as<int32_t>(),
-                         ctx->status_dev.as<int>() + 2, cap_faces, crops_dev, M_dev, ok_dev, true);
+                         ctx->status() + 2, cap_faces, crops_dev, M_dev, ok_dev, true);
 }
 
 // ---- single-image host wrappers -----------------------------------------------------------------------------------
@@ -418,7 +423,7 @@ FD_EXPORT int fd_crops_to_tensor(fd_ctx *ctx, const uint8_t *crops_dev, int F, i
     FD_REQUIRE(F >= 0 && in_h > 0 && in_w > 0 && out_h > 0 && out_w > 0 && mean_rgb && mul_rgb, "fd_crops_to_tensor: bad arguments");
     FD_REQUIRE(F == 0 || (crops_dev && out_nchw_dev), "fd_crops_to_tensor: null buffers");
     FD_REQUIRE(!use_detect_count || ctx->last_B > 0, "fd_crops_to_tensor: no fd_detect_batch results to take the face count from");
-    return crops_to_tensor_launch(ctx, crops_dev, use_detect_count ? ctx->status_dev.as<int>() + 2 : nullptr, F, in_h, in_w, out_h, out_w,
+    return crops_to_tensor_launch(ctx, crops_dev, use_detect_count ? ctx->status() + 2 : nullptr, F, in_h, in_w, out_h, out_w,
                                   mean_rgb, mul_rgb, out_nchw_dev);
 }
 
