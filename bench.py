@@ -538,7 +538,7 @@ def run_ours(args):
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "preprocess_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "preprocess_tma_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": PRE_BYTES_PER_FRAME * BATCH, "avg_launch_us": pre_ms * 1e3,
                          "share_of_step": pre_ms * args.steps / (secs * 1e3)},

@@ -63,15 +63,17 @@ __device__ __forceinline__ void estimate_group(const EstConst &ec, const float *
         for (int k = 0; k < 6; ++k) finite &= isfinite(model[k]);
         if (finite) {
             affine_err5(from, to, model, err);
-            float s[5] = {err[0], err[1], err[2], err[3], err[4]};
-#pragma unroll
-            for (int i = 1; i < 5; ++i) {  // insertion sort of 5
-                float v = s[i];
-                int j = i - 1;
-                while (j >= 0 && s[j] > v) { s[j + 1] = s[j]; --j; }
-                s[j + 1] = v;
-            }
-            const double med = (double)s[2];
+            // median of 5 by a min/max network (registers only; the errors are never NaN for a finite model)
+            float e0 = err[0], e1 = err[1], e2 = err[2], e3 = err[3], e4 = err[4], t;
+            t = fminf(e0, e1); e1 = fmaxf(e0, e1); e0 = t;
+            t = fminf(e3, e4); e4 = fmaxf(e3, e4); e3 = t;
+            t = fmaxf(e0, e3); e3 = fminf(e0, e3); e0 = t;          // e3 = overall min of the two pairs' minima: discard
+            t = fminf(e1, e4); e4 = fmaxf(e1, e4); e1 = t;          // e4 = overall max of the two pairs' maxima: discard
+            // median of {e0, e1, e2}
+            t = fminf(e0, e1); e1 = fmaxf(e0, e1); e0 = t;
+            const float med3 = fmaxf(e0, fminf(e1, e2));
+            (void)e3; (void)e4;
+            const double med = (double)med3;
             if (med < DBL_MAX) median = med;  // NaN / inf medians never win (median < minMedian is false)
         }
     }
