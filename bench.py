@@ -528,12 +528,18 @@ def run_ours(args):
         peak, peak_src = measured_peak_gbs()
         achieved = PRE_BYTES_PER_FRAME * BATCH / (pre_ms * 1e-3) / 1e9
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "preprocess_traffic.json")
-        if os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")   # ncu --set full capture of this workload (c2), per launch
+        ktraffic = {}
+        if os.path.exists(tp) and args.workload == "c2":
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                ktraffic = json.load(open(tp))
+                traffic = ktraffic.get("preprocess_tma_kernel", {}).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        if kernels:
+            for name, ent in kernels.items():
+                if isinstance(ent, dict) and name in ktraffic:
+                    ent["traffic"] = ktraffic[name]["dram_bytes_per_launch"]
         extra = {
             "e2e": e2e,
             "gpu_launches": int(launches),
