@@ -189,3 +189,64 @@ def test_shared_sm_build_gives_identical_results(ctx):
         ctx.set_sharing(1)
     for a, b in zip(ref, got):
         np.testing.assert_array_equal(a, b)
+
+
+def _random_heads(rng, B, A, fhw, hot=0.02):
+    """head tensors for an arbitrary geometry: a few percent of the anchors above 0.7, plausible regression deltas"""
+    heads = []
+    for (fh, fw) in fhw:
+        fg = rng.uniform(0, 0.6, (B, A, fh, fw)).astype(np.float32)
+        hotm = rng.uniform(0, 1, fg.shape) < hot
+        fg[hotm] = rng.uniform(0.7, 0.999, int(hotm.sum())).astype(np.float32)
+        sc = np.concatenate([1 - fg, fg], 1)
+        bb = rng.normal(0, 0.3, (B, 4 * A, fh, fw)).astype(np.float32)
+        lm = rng.normal(0, 0.3, (B, 10 * A, fh, fw)).astype(np.float32)
+        heads += [np.ascontiguousarray(sc), bb, lm]
+    return heads
+
+
+@pytest.mark.parametrize("image_wh,strides,A", [
+    ((480, 320), (16, 8), 1),        # non-square, two strides, one anchor per position (runtime-A score scan)
+    ((640, 640), (32, 16, 8), 3),    # three anchors per position
+    ((328, 328), (8,), 2),           # 41 x 41 positions: no 128-bit score rows -> three-kernel path
+])
+def test_other_detector_geometries(oracle, image_wh, strides, A):
+    """fd_config other than the reference's RetinaFace-640: anchors, strides and image size are configuration, not code."""
+    from rs_face_detection_b200 import Context, default_config
+    rng = np.random.default_rng(image_wh[0] + A)
+    base = np.zeros((len(strides), A, 4), np.float32)
+    for i, st in enumerate(strides):
+        for a in range(A):
+            half = st * (a + 1) * 1.5
+            base[i, a] = [-half + st / 2, -half + st / 2, half + st / 2 - 1, half + st / 2 - 1]
+    cfg = default_config()
+    cfg.image_w, cfg.image_h = image_wh
+    cfg.n_strides = len(strides)
+    for i, st in enumerate(strides):
+        cfg.strides[i] = st
+    cfg.num_anchors = A
+    for i in range(len(strides)):
+        for a in range(A):
+            for k in range(4):
+                cfg.base_anchors[(i * 4 + a) * 4 + k] = float(base[i, a, k])     # [FD_MAX_STRIDES][FD_MAX_ANCHORS][4], flat
+    cfg.bbox_stds[0], cfg.bbox_stds[1], cfg.bbox_stds[2], cfg.bbox_stds[3] = 0.1, 0.1, 0.2, 0.2
+    cfg.landmark_std = 0.5
+    c = Context(0, cfg)
+    try:
+        fhw = [((image_wh[1] + st - 1) // st, (image_wh[0] + st - 1) // st) for st in strides]
+        B = 3
+        heads = _random_heads(rng, B, A, fhw)
+        ocfg = oracle.make_det_cfg(conf_thr=0.7, iou_thr=0.4, image_size=image_wh, strides=strides, base_anchors=base,
+                                   bbox_stds=(0.1, 0.1, 0.2, 0.2), landmark_std=0.5)
+        devs = [c.to_device(h) for h in heads]
+        ds = np.array([1.0, 0.5, 0.75], np.float32)
+        c.detect_batch(devs, B, ds, 0.7, 0.4)
+        counts, det, lmk = c.detect_fetch(B)
+        off = 0
+        for b in range(B):
+            K = _check_image(oracle, ocfg, [h[b] for h in heads], ds[b], det[off:off + counts[b]], lmk[off:off + counts[b]])
+            assert K > 5
+            off += counts[b]
+        assert off == len(det) and off > 0
+    finally:
+        c.close()
