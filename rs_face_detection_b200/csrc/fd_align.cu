@@ -307,6 +307,11 @@ __global__ void __launch_bounds__(WARP_THREADS, 4) warp_kernel(WarpArgs a) {
 // its (adelta, bdelta) live in registers, no index division, and the packed-store word address advances by a constant.
 // An item is IR output rows (IR/2 rounds per thread); the per-row (X0, Y0) table is double-buffered so one barrier per
 // item is enough, and that barrier also carries the band's interior vote (4 threads evaluate the 4 corners).
+#ifdef WARP_LDCG
+#define WARP_LD(p) __ldcg(p)
+#else
+#define WARP_LD(p) __ldg(p)
+#endif
 template <int CW, int N>
 __device__ __forceinline__ void fixed_rounds_interior(const uint8_t *__restrict__ data, unsigned pitch, int2 d, const int2 *__restrict__ xy,
                                                       unsigned *__restrict__ outw, bool store) {
@@ -321,8 +326,8 @@ __device__ __forceinline__ void fixed_rounds_interior(const uint8_t *__restrict_
         off[u] = (unsigned)(Y >> 5) * pitch + (unsigned)(X >> 5) * 3u;
         const uint2 *r0p = reinterpret_cast<const uint2 *>(data + (off[u] & ~7u));
         const uint2 *r1p = reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(r0p) + pitch);   // pitch % 8 == 0
-        q[u][0] = __ldg(r0p); q[u][1] = __ldg(r0p + 1);
-        q[u][2] = __ldg(r1p); q[u][3] = __ldg(r1p + 1);
+        q[u][0] = WARP_LD(r0p); q[u][1] = WARP_LD(r0p + 1);
+        q[u][2] = WARP_LD(r1p); q[u][3] = WARP_LD(r1p + 1);
     }
 #pragma unroll
     for (int u = 0; u < N; ++u) {
