@@ -250,3 +250,21 @@ def test_other_detector_geometries(oracle, image_wh, strides, A):
         assert off == len(det) and off > 0
     finally:
         c.close()
+
+
+def test_large_batch_more_images_than_sms(ctx, oracle):
+    """B = 200 > 148 SMs: the fused kernel's CTAs run in more than one wave, so the epoch-tagged counts of later images wait
+    for earlier tickets; rows must still come out in frame order, twice in a row (the tickets re-arm themselves)."""
+    B = 200
+    heads, _ = synth.make_heads(B, seed=123, n_faces=6)
+    devs = [ctx.to_device(h) for h in heads]
+    ds = (1.0 / (1 + np.arange(B) % 4)).astype(np.float32)
+    cfg = oracle.make_det_cfg(conf_thr=0.7, iou_thr=0.45)
+    for rep in range(2):
+        ctx.detect_batch(devs, B, ds, 0.7, 0.45)
+        counts, det, lmk = ctx.detect_fetch(B)
+        assert counts.sum() == len(det)
+        off = 0
+        for b in range(B):
+            _check_image(oracle, cfg, [h[b] for h in heads], ds[b], det[off:off + counts[b]], lmk[off:off + counts[b]])
+            off += counts[b]
