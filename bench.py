@@ -319,11 +319,12 @@ def run_ours(args):
     cap_faces = BATCH * max(64, FACES_PER_FRAME * 2)
     crops_t = torch.empty((cap_faces, 112, 112, 3), dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
-    frames_l = [(t.data_ptr(), FRAME_H, FRAME_W, FRAME_W * 3) for t in frames_t]
+    frames_l = ctx.frame_table([(t.data_ptr(), FRAME_H, FRAME_W, FRAME_W * 3) for t in frames_t])   # fd_frame[B], built once
+    heads_c = ctx.head_table(heads_t)
 
     def step():
         ds = ctx.preprocess_batch(frames_l, tensor_t)
-        ctx.detect_batch(heads_t, BATCH, ds, CONF_THR, IOU_THR)
+        ctx.detect_batch(heads_c, BATCH, ds, CONF_THR, IOU_THR)
         ctx.align_detections(frames_l, crops_t, cap_faces)
 
     def barrier():
@@ -350,7 +351,7 @@ def run_ours(args):
         pre_ev[k][0].record(ext)
         ds = ctx.preprocess_batch(frames_l, tensor_t)
         pre_ev[k][1].record(ext)
-        ctx.detect_batch(heads_t, BATCH, ds, CONF_THR, IOU_THR)
+        ctx.detect_batch(heads_c, BATCH, ds, CONF_THR, IOU_THR)
         ctx.align_detections(frames_l, crops_t, cap_faces)
     ev1.record(ext)
     barrier()
@@ -374,7 +375,7 @@ def run_ours(args):
         def lane_step(k):
             c, _, tt, cc = lanes[k & 1]
             ds_ = c.preprocess_batch(frames_l, tt)
-            c.detect_batch(heads_t, BATCH, ds_, CONF_THR, IOU_THR)
+            c.detect_batch(heads_c, BATCH, ds_, CONF_THR, IOU_THR)
             c.align_detections(frames_l, cc, cap_faces)
 
         for k in range(6):
@@ -457,7 +458,7 @@ def run_ours(args):
     ds = ctx.preprocess_batch(frames_l, tensor_t)
     stages = None if args.no_stages else {
         "preprocess_us": time_stage(lambda: ctx.preprocess_batch(frames_l, tensor_t)),
-        "decode_nms_us": time_stage(lambda: ctx.detect_batch(heads_t, BATCH, ds, CONF_THR, IOU_THR)),
+        "decode_nms_us": time_stage(lambda: ctx.detect_batch(heads_c, BATCH, ds, CONF_THR, IOU_THR)),
         "align_us": time_stage(lambda: ctx.align_detections(frames_l, crops_t, cap_faces)),
         "faces_per_step": faces_per_step,
     }

@@ -435,11 +435,22 @@ class Context:
     # ---- batched, device-resident
     @staticmethod
     def _frames(frames):
-        """frames: list of (dev_ptr, h, w, pitch)"""
+        """frames: list of (dev_ptr, h, w, pitch), or the fd_frame array a previous frame_table() call built"""
+        if isinstance(frames, C.Array):
+            return frames
         arr = (FdFrame * len(frames))()
         for i, (p, h, w, pitch) in enumerate(frames):
             arr[i].data, arr[i].height, arr[i].width, arr[i].pitch = _devptr(p), h, w, pitch
         return arr
+
+    def frame_table(self, frames):
+        """Builds the fd_frame array once (a streaming caller reuses it: filling 64 ctypes structs per call costs more
+        host time than the kernels they describe)."""
+        return self._frames(frames)
+
+    @staticmethod
+    def head_table(heads_dev):
+        return (C.c_void_p * len(heads_dev))(*[_devptr(h) for h in heads_dev])
 
     def nms_device(self, dets_dev, K, thresh, keep_dev, num_keep_dev):
         _chk(self.lib.fd_nms_device(self.handle, C.c_void_p(_devptr(dets_dev)), int(K), C.c_float(thresh),
@@ -452,7 +463,7 @@ class Context:
         return ds
 
     def detect_batch(self, heads_dev, B, det_scale, conf_thr=None, iou_thr=None):
-        ptrs = (C.c_void_p * len(heads_dev))(*[_devptr(h) for h in heads_dev])
+        ptrs = heads_dev if isinstance(heads_dev, C.Array) else self.head_table(heads_dev)
         ds = _f32(det_scale)
         _chk(self.lib.fd_detect_batch(self.handle, ptrs, len(heads_dev), B, _ptr(ds, c_f32p),
                                       C.c_float(self.cfg.conf_thr if conf_thr is None else conf_thr),
