@@ -588,9 +588,17 @@ FD_EXPORT int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const
         for (int k = 0; k < 3; ++k) {
             const size_t bytes = sizeof(float) * (size_t)B * ch[k] * hw;
             FD_TRY(ctx->pipe_heads[3 * s + k].reserve(bytes));
-            FD_CUDA(cudaMemcpyAsync(ctx->pipe_heads[3 * s + k].p, heads_host[3 * s + k], bytes, cudaMemcpyHostToDevice, ctx->stream));
+            if (k == 0) {   // scores: only the A foreground channels of each image are ever read (face_detection.rs:322)
+                const size_t img = sizeof(float) * (size_t)ch[0] * hw, fg = img / 2;
+                FD_CUDA(cudaMemcpy2DAsync(ctx->pipe_heads[3 * s].as<unsigned char>() + fg, img,
+                                          reinterpret_cast<const unsigned char *>(heads_host[3 * s]) + fg, img, fg, (size_t)B,
+                                          cudaMemcpyHostToDevice, ctx->stream));
+                h2d += (int64_t)(fg * (size_t)B);
+            } else {
+                FD_CUDA(cudaMemcpyAsync(ctx->pipe_heads[3 * s + k].p, heads_host[3 * s + k], bytes, cudaMemcpyHostToDevice, ctx->stream));
+                h2d += (int64_t)bytes;
+            }
             dev_heads[3 * s + k] = ctx->pipe_heads[3 * s + k].as<float>();
-            h2d += (int64_t)bytes;
         }
     }
     std::vector<float> ds(B);
