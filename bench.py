@@ -476,14 +476,16 @@ def run_ours(args):
         pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
         bufs = dict(counts=pin((BATCH,), torch.int32), det=pin((cap_rows, 5), torch.float32), lmk=pin((cap_rows, 10), torch.float32),
                     crops=pin((cap_rows, 112, 112, 3), torch.uint8), det_scale=pin((BATCH,), torch.float32), tensor=None)
-        e2e_steps = max(4, min(args.steps, 20)) // 2 * 2
-        # two host threads, one fd_ctx each, alternate batches: the H2D of one batch overlaps the compute + D2H of the other
-        e2e_ctx = [ctx, Context(local_rank)]
+        L = max(1, args.e2e_lanes)
+        e2e_steps = max(2 * L, min(args.steps, 24)) // L * L
+        # L host threads, one fd_ctx each, alternate batches: the H2D of one batch overlaps the compute + D2H of the others
+        e2e_ctx = [ctx] + [Context(local_rank) for _ in range(L - 1)]
         for c_ in e2e_ctx:
-            c_.set_sharing(2)
-        e2e_bufs = [bufs, dict(counts=pin((BATCH,), torch.int32), det=pin((cap_rows, 5), torch.float32), lmk=pin((cap_rows, 10), torch.float32),
-                               crops=pin((cap_rows, 112, 112, 3), torch.uint8), det_scale=pin((BATCH,), torch.float32), tensor=None)]
-        res = [None, None]
+            c_.set_sharing(L)
+        e2e_bufs = [bufs] + [dict(counts=pin((BATCH,), torch.int32), det=pin((cap_rows, 5), torch.float32), lmk=pin((cap_rows, 10), torch.float32),
+                                  crops=pin((cap_rows, 112, 112, 3), torch.uint8), det_scale=pin((BATCH,), torch.float32), tensor=None)
+                             for _ in range(L - 1)]
+        res = [None] * L
 
         def e2e_worker(i, n):
             torch.cuda.set_device(local_rank)
@@ -491,7 +493,7 @@ def run_ours(args):
                 res[i] = e2e_ctx[i].pipeline_host(host_frames, host_heads, cap_rows, CONF_THR, IOU_THR, bufs=e2e_bufs[i])
 
         def e2e_run(n_each):
-            th = [threading.Thread(target=e2e_worker, args=(i, n_each)) for i in range(2)]
+            th = [threading.Thread(target=e2e_worker, args=(i, n_each)) for i in range(L)]
             t0 = time.perf_counter()
             for t in th:
                 t.start()
@@ -501,7 +503,7 @@ def run_ours(args):
 
         e2e_run(2)
         barrier()
-        e2e_secs = dist_max(e2e_run(e2e_steps // 2))
+        e2e_secs = dist_max(e2e_run(e2e_steps // L))
         _, total, h2d, d2h = res[0]
         # strictly serial variant (one context, one batch at a time) for reference
         ctx.set_sharing(1)
@@ -511,9 +513,9 @@ def run_ours(args):
         serial_secs = (time.perf_counter() - t0) / 4
         e2e = {"value": BATCH * e2e_steps * world / e2e_secs, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_secs / e2e_steps,
-               "batches_in_flight": 2, "serial_ms_per_step": 1e3 * serial_secs,
+               "batches_in_flight": L, "serial_ms_per_step": 1e3 * serial_secs,
                "note": "fd_pipeline_host per batch: pinned host frames+heads -> H2D -> preprocess/decode/NMS/align -> D2H dets+landmarks+crops; "
-                       "two host threads / two fd_ctx alternate batches; the CNN input tensor stays on the device (Triton CUDA-shm boundary)"}
+                       "%d host threads / fd_ctx alternate batches; the CNN input tensor stays on the device (Triton CUDA-shm boundary)" % L}
 
     # ---- NMS stress (BASELINE config 3), secondary number ----
     nms_extra = {}
@@ -608,6 +610,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-lanes", type=int, default=3, help="host threads / contexts keeping batches in flight in the e2e leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-nms", action="store_true")
     ap.add_argument("--no-pipelined", action="store_true")
