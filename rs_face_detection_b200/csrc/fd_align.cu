@@ -3,11 +3,13 @@
 // Replaces FaceAlignment::call (face_alignment.rs:27-141): cv::estimateAffinePartial2D(landmarks, template, LMEDS,
 // 3.0, 2000, 0.99, 10) (:50-59) and cv::warpAffine(img, M, (112,112), INTER_LINEAR, BORDER_CONSTANT, 0) (:119-126).
 //
-// estimate_kernel: one thread per face, fp64, the operation order of OpenCV's calib3d/ptsetreg.cpp (RNG reseeded
-// per call, 2-point exact similarity per LMedS iteration, float32 squared errors, median, inlier threshold) followed
-// by the least-squares similarity over the inliers that OpenCV's LM refinement converges to.
-// warp_kernel: OpenCV's imgwarp.cpp fixed-point scheme (inverse matrix in fp64, 10-bit coordinates, 5-bit sub-pixel
-// position, 15-bit weights, per-tap BORDER_CONSTANT) so crops are bit-identical, not "within a few grey levels".
+// estimate_kernel: 16 lanes per face, fp64 (device code in fd_estimate.cuh; the batched pipeline runs it inside the fused
+// detect kernel instead): the operation order of OpenCV's calib3d/ptsetreg.cpp (RNG reseeded per call, 2-point exact
+// similarity per LMedS iteration, float32 squared errors, median, inlier threshold) followed by the least-squares
+// similarity over the inliers that OpenCV's LM refinement converges to.
+// warp_fixed_kernel (112x112) / warp_kernel (any size): persistent, ticket-scheduled kernels evaluating OpenCV's
+// imgwarp.cpp fixed-point scheme (inverse matrix in fp64, 10-bit coordinates, 5-bit sub-pixel position, 15-bit weights,
+// per-tap BORDER_CONSTANT) so crops are bit-identical, not "within a few grey levels".
 #include <algorithm>
 #include <cmath>
 #include <cfloat>

@@ -1,5 +1,7 @@
 // fd_decode.cu — RetinaFace head decode for all strides and the whole batch in one launch, plus the result
-// finalisation (keep-gather + rescale).
+// finalisation (keep-gather + rescale): the three-kernel path (decode_kernel -> nms_cta_kernel -> finalize_kernel) that
+// the fused kernel (fd_detect_fused.cu) replaces in the batched pipeline; kept for geometries without 128-bit score rows,
+// for images the fused kernel defers, and as the A/B reference (FD_NO_FUSED=1).  Arithmetic in fd_decode.cuh.
 //
 // Replaces face_detection.rs:319-408 (per-stride decode), rcnn/anchors.rs:3-21 (anchor plane, recomputed on the fly
 // from 6 base anchors), face_detection.rs:516-570 (bbox_pred / landmark_pred), bbox_transform.rs:27-45 (clip_boxes),

@@ -12,8 +12,11 @@
 // Only the KEPT boxes of the head are then tested against the rest of the stream, which is compacted in order.
 // Work ~ kept x N instead of N^2/2, and nothing larger than the sorted boxes ever touches HBM.
 //
-//   K <= 4096 : one CTA does sort + peel out of shared memory (batched: one CTA per image).
-//   K  > 4096 : LSD radix sort (own kernels) + one cooperative persistent kernel; CTA 0 resolves heads, all CTAs push.
+//   K <= 1024 : barrier-light single-CTA path (fd_nms_tiny.cuh: register bitonic sort, warp-resolved mini-heads of 32);
+//               the batched pipeline runs the same code inside the fused detect kernel (fd_detect_fused.cu).
+//   K <= 4096 : one CTA does sort + peel out of shared memory.
+//   K  > 4096 : LSD radix sort (own kernels) + spatially binned exact NMS (predecessor lists + decision sweeps in one
+//               cooperative kernel), or the cooperative multi-CTA peel for degenerate inputs.
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
