@@ -380,6 +380,9 @@ def run_ours(args):
 
         for k in range(6):
             lane_step(k)
+        ctx2.detect_fetch(BATCH)   # like ctx above: completes (and makes the ctx remember) images with > 1024 candidates
+        for k in range(2):
+            lane_step(k)
         ctx2.synchronize()
         barrier()
         s0 = [torch.cuda.Event(enable_timing=True) for _ in lanes]

@@ -22,6 +22,7 @@
 #include "fd_internal.cuh"
 #include "fd_decode.cuh"
 #include "fd_nms_tiny.cuh"
+#include "fd_nms_small.cuh"
 #include "fd_estimate.cuh"
 
 namespace fd {
@@ -55,16 +56,25 @@ struct FusedArgs {
     u64 *agg;             // [B] (epoch << 32) | kept count
     unsigned epoch;
     int B;
+    int general_ok;       // the dynamic shared memory has room for the general single-CTA NMS (1024 < K <= 4096 on the device)
     long long *dbg;       // FD_FUSED_DBG=1: per-CTA stage timestamps
 };
 
+// Shared memory of one image's CTA: a small control block, then a work area that is either the K <= 1024 state below or,
+// for an image with 1024 < K <= 4096 candidates, the general path's SmallSmem (fd_nms_small.cuh) — the launch reserves room
+// for that only when the ctx has seen such images (`general_ok`); the rows of the kept faces (flmk / fdet) are written after
+// the NMS, when either state is dead.
+struct FusedCtrl {
+    int red[33];
+    int b, cnt, kept, off, general;
+};
+constexpr int FUSED_CTRL_BYTES = 256;
+static_assert(sizeof(FusedCtrl) <= FUSED_CTRL_BYTES, "control block");
 struct FusedSmem {
     TinySmem t;
     u64 ckey[TINY_CAP];          // candidate keys in arrival order
     float flmk[TINY_CAP * 10];   // rescaled landmarks of the kept faces (output rows, input of the estimate)
     float fdet[TINY_CAP * 5];    // rescaled boxes + score of the kept faces (output rows)
-    int red[33];
-    int b, cnt, kept, off;
 };
 
 __device__ __forceinline__ u64 ld_acquire_u64(const u64 *p) {
@@ -79,7 +89,7 @@ __device__ __forceinline__ void st_release_u64(u64 *p, u64 v) {
 // Score scan of image b: UN items (4 consecutive positions of one stride each) per thread are loaded before any is
 // processed, so the image's 2A score planes (134 KB for 640x640) cost about one memory latency.  AT: compile-time A (0 = runtime).
 template <int AT, int UN>
-__device__ __forceinline__ bool fused_score_scan(const FusedArgs &a, FusedSmem &sm, int b) {
+__device__ __forceinline__ bool fused_score_scan(const FusedArgs &a, FusedSmem &sm, FusedCtrl &ctl, int b) {
     const DecodeCfg &c = a.c;
     constexpr int AMAX = AT ? AT : FD_MAX_ANCHORS;
     const int A = AT ? AT : c.A;
@@ -130,7 +140,7 @@ __device__ __forceinline__ bool fused_score_scan(const FusedArgs &a, FusedSmem &
                 if (lane >= o) incl += nb;
             }
             int base = 0;
-            if (lane == 31) base = atomicAdd(&sm.cnt, incl);
+            if (lane == 31) base = atomicAdd(&ctl.cnt, incl);
             base = __shfl_sync(0xffffffffu, base, 31);
             int slot = base + incl - cnt;
             while (pass) {
@@ -166,27 +176,29 @@ __device__ __forceinline__ void fused_stamp(const FusedArgs &a, int b, int slot)
 
 __device__ __forceinline__ void detect_fused_body(const FusedArgs &a) {
     extern __shared__ __align__(16) unsigned char fused_raw[];
-    FusedSmem &sm = *reinterpret_cast<FusedSmem *>(fused_raw);
+    FusedCtrl &ctl = *reinterpret_cast<FusedCtrl *>(fused_raw);
+    FusedSmem &sm = *reinterpret_cast<FusedSmem *>(fused_raw + FUSED_CTRL_BYTES);
     const DecodeCfg &c = a.c;
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) {
-        sm.b = atomicAdd(a.ticket, 1);   // images in ticket order: every predecessor of this image is already running
-        sm.cnt = 0;
-        sm.kept = 0;
+        ctl.b = atomicAdd(a.ticket, 1);   // images in ticket order: every predecessor of this image is already running
+        ctl.cnt = 0;
+        ctl.kept = 0;
+        ctl.general = 0;
     }
     __syncthreads();
-    const int b = sm.b;
+    const int b = ctl.b;
     fused_stamp(a, b, 0);
     const int A = c.A, TA = c.total_anchors;
     const size_t img_base = (size_t)b * TA;
 
     // ---- 1. score scan + key compaction ----
-    const bool nan_seen = c.A == 2 ? fused_score_scan<2, 3>(a, sm, b) : fused_score_scan<0, 1>(a, sm, b);
+    const bool nan_seen = c.A == 2 ? fused_score_scan<2, 3>(a, sm, ctl, b) : fused_score_scan<0, 1>(a, sm, ctl, b);
     const bool nan_any = __syncthreads_or(nan_seen);
     fused_stamp(a, b, 1);
-    const int K = nan_any ? 0 : sm.cnt;
+    const int K = nan_any ? 0 : ctl.cnt;
     if (tid == 0) {
-        a.counts[b] = sm.cnt;
+        a.counts[b] = ctl.cnt;
         if (nan_any) atomicExch(&a.status[0], 1);
     }
 
@@ -209,7 +221,33 @@ __device__ __forceinline__ void detect_fused_body(const FusedArgs &a) {
             dst[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
             dst[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
         }
-        if (tid == 0) {
+        bool handled = false;
+        if (a.general_ok && K <= SMALL_CAP) {   // the general single-CTA path, in place of the K <= 1024 one
+            __syncthreads();                     // keys and boxes of this image are in global memory: visible to the block
+            SmallArgs sa{};
+            sa.keys = a.keys;
+            sa.key_stride = (size_t)TA;
+            sa.boxes = reinterpret_cast<const float *>(a.cand_box);
+            sa.box_batch_stride = (size_t)TA * 4;
+            sa.box_stride = 4;
+            sa.K = K;
+            sa.iou = a.iou;
+            sa.keep = a.keep;
+            sa.keep_stride = (size_t)TA;
+            sa.keep_count = a.keep_count;
+            sa.status = a.status;
+            nms_general_cta<0, 4>(sa, *reinterpret_cast<SmallSmem *>(fused_raw + FUSED_CTRL_BYTES), b, K);
+            __syncthreads();
+            const int nk = a.keep_count[b];      // written by thread 0 of this CTA before the barrier
+            if (nk >= 0 && nk <= TINY_CAP) {     // (more kept faces than the row staging holds: leave it to the host path)
+                handled = true;
+                if (tid == 0) {
+                    ctl.kept = nk;
+                    ctl.general = 1;
+                }
+            }
+        }
+        if (!handled && tid == 0) {
             a.keep_count[b] = -1;
             a.big_list[atomicAdd(&a.status[1], 1)] = b;
         }
@@ -244,7 +282,7 @@ __device__ __forceinline__ void detect_fused_body(const FusedArgs &a) {
             const int nk = fast ? tiny_greedy<0, true>(sm.t, a.iou, K, n2, keep, my, nullptr)
                                 : tiny_greedy<0, false>(sm.t, a.iou, K, n2, keep, my, nullptr);
             if (tid == 0) {
-                sm.kept = nk;
+                ctl.kept = nk;
                 a.keep_count[b] = nk;
             }
         }
@@ -252,7 +290,8 @@ __device__ __forceinline__ void detect_fused_body(const FusedArgs &a) {
         a.keep_count[b] = 0;
     }
     __syncthreads();
-    const int M = sm.kept;
+    const int M = ctl.kept;
+    const bool general = ctl.general != 0;
     fused_stamp(a, b, 4);
 
     // ---- 3. publish this image's kept count (epoch-tagged); the predecessors' counts are summed in step 5 ----
@@ -261,21 +300,31 @@ __device__ __forceinline__ void detect_fused_body(const FusedArgs &a) {
     // ---- 4. gather + rescale (division, face_detection.rs:477-483) into shared memory: needs no offset yet ----
     const float ds = a.det_scale[b];
     for (int m = tid; m < M; m += FT) {
-        const int rank = sm.t.krank[m];
-        const int id = sm.t.sidx[rank];
-        const float4 bx = sm.t.sbox[rank];
-        int s, local, aa;
-        split_anchor_id(c, id, s, local, aa);
+        float4 bx;
         float rec[CAND_REC];
-        decode_landmarks(c, a.hp, b, s, local, aa, anchor_geo(c, s, local, aa), rec);
-        const int hw = c.fh[s] * c.fw[s];
-        rec[10] = __ldg(a.hp.p[3 * s] + (size_t)b * 2 * A * hw + (size_t)(A + aa) * hw + local);
-        rec[11] = 0.0f;
-        a.cand_box[img_base + id] = bx;   // the lazily-run general finalize reads these for every image of the batch
-        float4 *dst = reinterpret_cast<float4 *>(a.cand_rec + (img_base + id) * CAND_REC);
-        dst[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
-        dst[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
-        dst[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+        if (general) {   // kept anchor ids from the general path; boxes / landmarks / score were decoded to global memory
+            const int id = keep[m];
+            bx = a.cand_box[img_base + id];
+            const float4 *src = reinterpret_cast<const float4 *>(a.cand_rec + (img_base + id) * CAND_REC);
+            const float4 r0 = src[0], r1 = src[1], r2 = src[2];
+            rec[0] = r0.x; rec[1] = r0.y; rec[2] = r0.z; rec[3] = r0.w; rec[4] = r1.x; rec[5] = r1.y; rec[6] = r1.z; rec[7] = r1.w;
+            rec[8] = r2.x; rec[9] = r2.y; rec[10] = r2.z; rec[11] = r2.w;
+        } else {
+            const int rank = sm.t.krank[m];
+            const int id = sm.t.sidx[rank];
+            bx = sm.t.sbox[rank];
+            int s, local, aa;
+            split_anchor_id(c, id, s, local, aa);
+            decode_landmarks(c, a.hp, b, s, local, aa, anchor_geo(c, s, local, aa), rec);
+            const int hw = c.fh[s] * c.fw[s];
+            rec[10] = __ldg(a.hp.p[3 * s] + (size_t)b * 2 * A * hw + (size_t)(A + aa) * hw + local);
+            rec[11] = 0.0f;
+            a.cand_box[img_base + id] = bx;   // the lazily-run general finalize reads these for every image of the batch
+            float4 *dst = reinterpret_cast<float4 *>(a.cand_rec + (img_base + id) * CAND_REC);
+            dst[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+            dst[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+            dst[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+        }
         float *d = sm.fdet + m * 5;
         d[0] = __fdiv_rn(bx.x, ds);
         d[1] = __fdiv_rn(bx.y, ds);
@@ -317,10 +366,10 @@ __device__ __forceinline__ void detect_fused_body(const FusedArgs &a) {
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-            if (lane == 0) sm.red[tid >> 5] = part;
+            if (lane == 0) ctl.red[tid >> 5] = part;
             __syncthreads();
 #pragma unroll
-            for (int k = 0; k < FT / 32; ++k) off += sm.red[k];
+            for (int k = 0; k < FT / 32; ++k) off += ctl.red[k];
             if (tid == 0) {
                 a.offsets[b] = off;
                 if (b == a.B - 1) {
@@ -373,7 +422,12 @@ int detect_fused_launch(fd_ctx *ctx, const float *const *heads_dev, int B, float
     const DecodeCfg &d = ctx->dcfg;
     for (int st = 0; st < d.n_strides; ++st)   // 128-bit score loads: H*W % 4 == 0 for every stride, 16-byte aligned score tensors
         if ((d.fh[st] * d.fw[st]) % 4 != 0 || reinterpret_cast<uintptr_t>(heads_dev[3 * st]) % 16 != 0) return FD_OK;
-    const size_t smem = sizeof(FusedSmem);
+    // images with 1024 < K <= 4096 candidates stay on the device once the ctx has met one (fd_detect_fetch saw a deferred
+    // image): from then on the launch reserves the general path's shared memory as well
+    static const char *force = getenv("FD_FUSED_GENERAL");
+    const bool general_ok = (force ? force[0] == '1' : ctx->crowded) &&
+                            FUSED_CTRL_BYTES + sizeof(SmallSmem) <= (size_t)ctx->max_smem_optin;
+    const size_t smem = FUSED_CTRL_BYTES + (general_ok ? std::max(sizeof(FusedSmem), sizeof(SmallSmem)) : sizeof(FusedSmem));
     if (smem > (size_t)ctx->max_smem_optin) return FD_OK;
     FD_TRY(ticket_buffer(ctx));
     {   // a fresh allocation must not hold a stale tag that could match a future epoch
@@ -409,6 +463,7 @@ int detect_fused_launch(fd_ctx *ctx, const float *const *heads_dev, int B, float
     a.epoch = ++ctx->scan_epoch;
     if (a.epoch == 0) a.epoch = ++ctx->scan_epoch;   // 0 is the "never written" tag
     a.B = B;
+    a.general_ok = general_ok ? 1 : 0;
     static const bool dbg_on = getenv("FD_FUSED_DBG") != nullptr;
     static long long *dbg_dev = nullptr;
     a.dbg = nullptr;

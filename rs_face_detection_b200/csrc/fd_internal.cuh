@@ -112,6 +112,7 @@ struct fd_ctx {
     unsigned scan_epoch = 0;
     int est_cap = 0;             // faces align_M / align_ok have room for at detect time
     int align_cap_hint = 0;      // largest crop capacity an align call has asked for
+    bool crowded = false;        // a detect call met an image with more than 1024 candidates: keep room for the general NMS
     bool share_sms = false;      // fd_ctx_set_sharing: prefer kernels that leave room for another batch's kernels on the SMs
     bool est_valid = false;      // align_M / align_ok hold the estimates of the last fd_detect_batch (fused kernel)
     fd::DevBuf nms_ws[8];        // big-path workspaces

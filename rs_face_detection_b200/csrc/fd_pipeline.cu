@@ -106,6 +106,7 @@ static int detect_resolve(fd_ctx *ctx) {
     ctx->detect_pending = false;
     if (st[0]) return fail(FD_ERR_NAN_SCORE, "fd_detect_batch: NaN score (the reference panics, utils.rs:92)");
     if (st[1] > 0) {
+        ctx->crowded = true;   // later fused launches keep images with up to 4096 candidates on the device
         std::vector<int> big(st[1]), counts(B);
         FD_CUDA(cudaMemcpy(big.data(), ctx->big_list.p, sizeof(int) * st[1], cudaMemcpyDeviceToHost));
         FD_CUDA(cudaMemcpy(counts.data(), ctx->cand_count.p, sizeof(int) * B, cudaMemcpyDeviceToHost));
