@@ -11,8 +11,10 @@
 //   gather          kept boxes / landmark_pred / `÷ det_scale` (face_detection.rs:432-493) straight to the compact outputs;
 //   estimate        LMedS similarity per kept face, 16 lanes each (fd_estimate.cuh), for the warp kernel that follows.
 //
-// Per-image candidate lists longer than 1024 (conf_thr far below the reference's 0.7) are decoded to the global candidate
-// buffers and deferred to the general NMS paths (fd_nms.cu) exactly like K > 4096 was before; fd_detect_fetch resolves them.
+// Per-image candidate lists longer than 1024 (conf_thr far below the reference's 0.7, or ~50 faces per frame) are decoded to
+// the global candidate buffers; up to 4096 candidates the same CTA runs the general single-CTA NMS (fd_nms_small.cuh) in
+// place once the ctx has met such an image (the launch then reserves that path's shared memory); otherwise, and always
+// beyond 4096, the image is deferred and fd_detect_fetch completes it with the general NMS paths of fd_nms.cu.
 // The three-kernel path (decode_kernel, nms_cta_kernel, finalize_kernel) remains for geometries without 128-bit score rows
 // and as the A/B reference (FD_NO_FUSED=1).
 #include <algorithm>
