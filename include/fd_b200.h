@@ -177,7 +177,8 @@ int fd_preprocess_batch(fd_ctx *ctx, const fd_frame *frames, int B, float *out_n
 /* heads_dev[3*s+0..2]: (B,2A,H,W), (B,4A,H,W), (B,10A,H,W) dev tensors of stride s.  Results stay on the device
  * inside the ctx until fd_detect_fetch / fd_align_detections.  Asynchronous.  Images with more than 4096 candidates
  * (and, the first time a ctx meets one, images with more than 1024) are completed by fd_detect_fetch / fd_detect_view;
- * consumers enqueued before that (fd_align_detections, fd_select_detections) are re-run there. */
+ * an fd_align_detections enqueued before that is re-run there (call fd_detect_fetch first when other consumers, e.g.
+ * fd_select_detections without sel_host, must see such images). */
 int fd_detect_batch(fd_ctx *ctx, const float *const *heads_dev, int n_heads, int B, const float *det_scale_host,
                     float conf_thr, float iou_thr);
 /* Blocks; copies the compact results of the last fd_detect_batch: counts (B), det (total,5), landmarks (total,10),
