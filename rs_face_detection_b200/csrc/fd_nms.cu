@@ -1059,12 +1059,16 @@ int nms_last_stats(fd_ctx *ctx, int32_t out[8]) {
 
 // Generic device NMS on a (K, stride) row-major array with the score in column 4 (ignored if presorted).
 // keep_dev (K) and num_keep_dev (2 ints: [0] count, [1] NaN flag) are device buffers.
+constexpr int SINGLE_PROBLEM_CROSSOVER = 2560;
 int nms_device(fd_ctx *ctx, const float *dets_dev, int K, int stride, float thr, int mode, bool presorted,
                int32_t *keep_dev, int32_t *num_keep_dev) {
     FD_TRY(ctx->nms_ws[7].reserve(sizeof(int) * 8));
     int *status = ctx->nms_ws[7].as<int>();
     FD_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * 8, ctx->stream));
-    if (K <= SMALL_CAP) {
+    // ONE problem: a single SM is the faster home up to a few thousand boxes, the multi-kernel path beyond (measured
+    // crossover, profiles/r1_nms_sizes.json); batched callers keep one CTA per image up to SMALL_CAP
+    static const int single_cross = getenv("FD_NMS_CROSS") ? atoi(getenv("FD_NMS_CROSS")) : SINGLE_PROBLEM_CROSSOVER;
+    if (K <= std::min(SMALL_CAP, single_cross)) {
         SmallArgs a{};
         a.keys = nullptr;
         a.key_stride = 0;
