@@ -294,3 +294,38 @@ def test_large_batch_more_images_than_sms(ctx, oracle):
         for b in range(B):
             _check_image(oracle, cfg, [h[b] for h in heads], ds[b], det[off:off + counts[b]], lmk[off:off + counts[b]])
             off += counts[b]
+
+
+def test_property_random_heads(ctx, oracle):
+    """Random head tensors through the fused kernel: quantised scores (many exact ties across strides and anchors), hot
+    fractions from nothing to crowded, random batch sizes and det_scales; rows and order must match the oracle."""
+    hypothesis = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    fhw = [(20, 20), (40, 40), (80, 80)]
+
+    @settings(max_examples=25, deadline=None, derandomize=True)
+    @given(st.integers(0, 10 ** 6), st.integers(1, 4), st.sampled_from([0.0, 0.001, 0.01, 0.04, 0.1]), st.sampled_from([None, 64, 8]),
+           st.sampled_from([0.3, 0.4, 0.45, 0.6]))
+    def prop(seed, B, hot, levels, iou):
+        rng = np.random.default_rng(seed)
+        heads = _random_heads(rng, B, 2, fhw, hot=hot)
+        if levels:                                   # quantise the fg scores: exact ties, bg = 1 - fg stays consistent
+            for s in range(3):
+                fg = np.round(heads[3 * s][:, 2:] * levels) / levels
+                heads[3 * s][:, 2:] = fg
+                heads[3 * s][:, :2] = 1 - fg
+        ds = rng.choice(np.float32([1.0, 0.5, 0.33333334, 0.25, 1.5]), B).astype(np.float32)
+        cfg = oracle.make_det_cfg(conf_thr=0.7, iou_thr=iou)
+        devs = [ctx.to_device(h) for h in heads]
+        ctx.detect_batch(devs, B, ds, 0.7, iou)
+        counts, det, lmk = ctx.detect_fetch(B)
+        off = 0
+        for b in range(B):
+            _check_image(oracle, cfg, [h[b] for h in heads], ds[b], det[off:off + counts[b]], lmk[off:off + counts[b]])
+            off += counts[b]
+        assert off == len(det)
+        for d in devs:
+            d.free()
+
+    prop()
