@@ -873,6 +873,8 @@ static int launch_small(fd_ctx *ctx, const SmallArgs &a_in, int B, bool float4_b
     static const int no_tiny = getenv("FD_NMS_NO_TINY") != nullptr && getenv("FD_NMS_NO_TINY")[0] == '1';
     SmallArgs a = a_in;
     a.no_tiny = no_tiny;
+    static const int use_peel = getenv("FD_NMS_PEEL") != nullptr && getenv("FD_NMS_PEEL")[0] == '1';
+    a.use_peel = use_peel;
     static const int dbg_on = getenv("FD_NMS_DBG") != nullptr;
     static long long *dbg_dev = nullptr;
     if (dbg_on) {

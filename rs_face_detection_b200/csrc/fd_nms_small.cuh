@@ -182,6 +182,7 @@ struct SmallArgs {
     int *status;              // [0] NaN flag, [1] number of problems deferred to the big path
     int *big_list;            // problems with K > SMALL_CAP (or nullptr)
     long long *dbg;           // FD_NMS_DBG=1: per-CTA stage timestamps (globaltimer), 16 slots per CTA
+    int use_peel;             // FD_NMS_PEEL=1: the peel instead of the mini-head greedy for 1024 < K <= 4096 (A/B reference)
     int no_tiny;              // FD_NMS_NO_TINY=1: force the general single-CTA path for K <= 1024 too (tests, A/B timing)
 };
 
@@ -275,6 +276,24 @@ __device__ void nms_general_cta(const SmallArgs &a, SmallSmem &sm, int b, int K)
     }
     const bool fast = __syncthreads_and(ok) && a.iou.fast;  // also fences the key reads before the streams alias them
 
+    if (nthr == NT && !a.use_peel) {
+        // ---- 3'. mini-head greedy over up to 4 boxes per thread (fd_nms_tiny.cuh); the peel below stays as the A/B reference ----
+        GreedyBufs g;
+        float *sarea = reinterpret_cast<float *>(sm.mask);          // the mask region is free on this path
+        g.selw = reinterpret_cast<int *>(sarea + SMALL_CAP);
+        g.alive = reinterpret_cast<unsigned *>(g.selw + 32 * 32);
+        g.mrow = g.alive + 2 * 4 * 32;
+        for (int r = tid; r < K; r += nthr) sarea[r] = box_area(sm.sbox[r]);
+        __syncthreads();
+        g.sbox = sm.sbox;
+        g.sarea = sarea;
+        g.sidx = sm.sidx;
+        int nk;
+        if (K <= 2 * NT) nk = fast ? multi_greedy<MODE, true, 2>(g, a.iou, K, keep) : multi_greedy<MODE, false, 2>(g, a.iou, K, keep);
+        else nk = fast ? multi_greedy<MODE, true, 4>(g, a.iou, K, keep) : multi_greedy<MODE, false, 4>(g, a.iou, K, keep);
+        if (tid == 0) a.keep_count[b] = nk;
+        return;
+    }
     int *stream_cur = reinterpret_cast<int *>(sm.keys);
     int *stream_nxt = stream_cur + SMALL_CAP;
     float4 *kbox = reinterpret_cast<float4 *>(sm.mask);

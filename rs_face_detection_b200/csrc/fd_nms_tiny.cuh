@@ -160,4 +160,102 @@ __device__ __forceinline__ void tiny_sort(u64 &key, TinySmem &sm, int tid) {
 }
 
 
+// ---- the same greedy for up to R x 1024 boxes in one CTA of 1024 threads ------------------------------------------------
+// Thread t owns the boxes of rank t, t + 1024, ... (so the alive word of its i-th box is word (t >> 5) + 32 i: words are in
+// rank order); everything else is tiny_greedy: mini-heads of the first <= 32 undecided boxes, one pairwise row per warp,
+// every warp resolving the rows redundantly, every thread testing its R boxes against the mini-head's kept boxes.
+// Work ~ K x kept / 1024 tests per thread instead of the peel's mask builds; two block-wide barriers per mini-head.
+struct GreedyBufs {
+    const float4 *sbox;   // [K] boxes in rank order
+    const float *sarea;   // [K]
+    const int *sidx;      // [K] source index of rank r
+    int *selw;            // [32][32] per-warp scratch
+    unsigned *alive;      // [2][R * 32]
+    unsigned *mrow;       // [32]
+};
+template <int MODE, bool FAST, int R>
+__device__ int multi_greedy(const GreedyBufs &g, const IouParams iou, int K, int *keep) {
+    constexpr int NTH = 1024, NWORDS = R * 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float4 my[R];
+    float marea[R];
+    bool alive[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int r = tid + i * NTH;
+        alive[i] = r < K;
+        my[i] = alive[i] ? g.sbox[r] : make_float4(0.f, 0.f, 0.f, 0.f);
+        marea[i] = alive[i] ? g.sarea[r] : 0.f;
+    }
+    unsigned keptmask = 0;
+    int selj = 0, nk_total = 0;
+    for (int iters = 0;; ++iters) {
+        // A. my boxes against the boxes the previous mini-head kept
+        for (unsigned km = keptmask; km; km &= km - 1) {
+            const int ks = __shfl_sync(0xffffffffu, selj, __ffs(km) - 1);
+            const float4 kb = g.sbox[ks];
+            const float ka = g.sarea[ks];
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+                if (alive[i] && tiny_suppresses<MODE, FAST>(kb, ka, my[i], marea[i], iou)) alive[i] = false;
+        }
+        unsigned *aw = g.alive + (iters & 1) * NWORDS;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const unsigned bal = __ballot_sync(0xffffffffu, alive[i]);
+            if (lane == 0) aw[warp + 32 * i] = bal;
+        }
+        __syncthreads();
+        // B. every warp selects the same mini-head: the first <= 32 undecided boxes in rank order
+        int total = 0;
+#pragma unroll
+        for (int i = 0; i < R; ++i) total += __popc(aw[lane + 32 * i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        if (total == 0) break;
+        const int n_sel = min(total, 32);
+        int *mysel = g.selw + warp * 32;
+        for (int q = 0, basep = 0; q < NWORDS && basep < 32; ++q) {
+            const unsigned wq = aw[q];
+            const int p = basep + __popc(wq & ((1u << lane) - 1u));
+            if (((wq >> lane) & 1u) && p < 32) mysel[p] = q * 32 + lane;
+            basep += __popc(wq);
+        }
+        __syncwarp();
+        selj = lane < n_sel ? mysel[lane] : 0;
+        const int sel_last = mysel[n_sel - 1];   // every undecided box up to this rank is in the mini-head
+        __syncwarp();
+        const float4 bj = g.sbox[selj];
+        const float aj = g.sarea[selj];
+        // C. pairwise tests inside the mini-head, one row per warp: bit j of row r = earlier box j suppresses box r
+        if (warp < n_sel) {
+            const int rs = __shfl_sync(0xffffffffu, selj, warp);
+            const bool sp = lane < warp && tiny_suppresses<MODE, FAST>(bj, aj, g.sbox[rs], g.sarea[rs], iou);
+            const unsigned row = __ballot_sync(0xffffffffu, sp);
+            if (lane == 0) g.mrow[warp] = row;
+        }
+        __syncthreads();
+        // D. every warp resolves the mini-head (parallel decision rounds over the 32-bit rows)
+        const unsigned m = lane < n_sel ? g.mrow[lane] : 0u;
+        keptmask = __ballot_sync(0xffffffffu, lane < n_sel && m == 0);
+        unsigned und = __ballot_sync(0xffffffffu, m != 0);
+        bool undecided = m != 0;
+        while (und) {
+            bool k = false;
+            if (undecided) {
+                if (m & keptmask) undecided = false;
+                else if ((m & und) == 0) { undecided = false; k = true; }
+            }
+            keptmask |= __ballot_sync(0xffffffffu, k);
+            und = __ballot_sync(0xffffffffu, undecided);
+        }
+        if (warp == 0 && ((keptmask >> lane) & 1u)) keep[nk_total + __popc(keptmask & ((1u << lane) - 1u))] = g.sidx[selj];
+        nk_total += __popc(keptmask);
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+            if (tid + i * NTH <= sel_last) alive[i] = false;   // decided, one way or the other
+    }
+    return nk_total;   // identical in every thread
+}
+
 }  // namespace fd
