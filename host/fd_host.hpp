@@ -138,11 +138,11 @@ private:
 class FaceAlignment {
 public:
     explicit FaceAlignment(Context &c) : c_(c) { check(fd_ctx_get_config(c.get(), &cfg_)); }
-    // call(&Mat, bbox, landmarks) -> crop (crop_h x crop_w x 3 u8).  Throws Error(FD_ERR_ESTIMATE) where the reference
-    // would take its bbox-crop fallback (:64-116).
-    std::vector<uint8_t> call(const Mat &img, const float *landmarks_5x2) {
+    // call(&Mat, bbox (4, or nullptr = None), landmarks (5x2, or nullptr = None)) -> crop (crop_h x crop_w x 3 u8): the
+    // similarity warp, or the bbox-crop fallback (:64-116) when the estimate is empty.  Throws where the reference returns Err.
+    std::vector<uint8_t> call(const Mat &img, const float *bbox, const float *landmarks_5x2) {
         std::vector<uint8_t> crop((size_t)cfg_.crop_h * cfg_.crop_w * 3);
-        check(fd_align(c_.get(), img.data, img.rows, img.cols, img.step, landmarks_5x2, crop.data(), nullptr));
+        check(fd_align(c_.get(), img.data, img.rows, img.cols, img.step, bbox, landmarks_5x2, crop.data(), nullptr, nullptr));
         return crop;
     }
 private:

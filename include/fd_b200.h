@@ -21,16 +21,19 @@ extern "C" {
 
 #define FD_MAX_STRIDES 8
 #define FD_MAX_ANCHORS 4
-#define FD_ABI_VERSION 1
+#define FD_ABI_VERSION 2
 
 typedef enum fd_status {
     FD_OK = 0,
     FD_ERR_INVALID = 1,    /* bad argument */
     FD_ERR_CUDA = 2,       /* CUDA runtime error (message in fd_last_error) */
-    FD_ERR_NAN_SCORE = 3,  /* NaN score: the reference panics (utils.rs:92 partial_cmp().unwrap()) */
+    FD_ERR_NAN_SCORE = 3,  /* NaN key in fd_argsort_descending / fd_nms*: utils.rs:92 unwraps partial_cmp (panic); nms.rs:6
+                              sorts with an inconsistent comparator (unspecified order).  The detect path never raises it:
+                              `score >= thr` (face_detection.rs:375) drops a NaN score before any sort. */
     FD_ERR_CAPACITY = 4,   /* caller-provided output buffer too small */
     FD_ERR_NO_DEVICE = 5,  /* no usable CUDA device: there is NO CPU fallback */
-    FD_ERR_ESTIMATE = 6    /* similarity estimation failed (reference: empty matrix, face_alignment.rs:64) */
+    FD_ERR_ESTIMATE = 6    /* FaceAlignment: empty transform AND the bbox-crop fallback's ROI is outside the image (the reference
+                              returns Err from Mat::roi, face_alignment.rs:92-95) */
 } fd_status;
 
 /* Constants of RetinaFaceDetection (face_detection.rs:19-38, 41-129), FaceDetectionConfig and
@@ -162,10 +165,14 @@ int fd_estimate_affine_partial_2d(fd_ctx *ctx, const float *from, const float *t
 /* cv::warpAffine(img, M, (crop_w,crop_h), INTER_LINEAR, BORDER_CONSTANT, 0) (face_alignment.rs:119-126), host in/out. */
 int fd_warp_affine(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, const double *M, uint8_t *out,
                    int out_h, int out_w);
-/* FaceAlignment::call main branch (face_alignment.rs:27-141) for ONE host image and ONE face.
- * Returns FD_ERR_ESTIMATE where the reference would take its bbox-crop fallback. */
-int fd_align(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, const float *landmarks /*5x2*/,
-             uint8_t *crop /*crop_h x crop_w x 3*/, double *M_out /*2x3 or NULL*/);
+/* FaceAlignment::call (face_alignment.rs:27-141) for ONE host image and ONE face: the similarity warp, or — when
+ * estimateAffinePartial2D returns an empty matrix (degenerate / non-finite landmarks) — the bbox-crop fallback (:64-116):
+ * det = bbox (NULL = None: the image inset by 1/16), ROI (max(x1-22,0), max(y1-22,0)) .. (max(x2+22,W), max(y1+22,H)) exactly
+ * as written there (`max`, det[1]), cv::resize to the crop size.  mode_out (optional): 1 = warp, 2 = fallback crop.
+ * Errors like the reference: landmarks NULL (None: OpenCV asserts on the empty Mat) -> FD_ERR_INVALID; fallback ROI not
+ * inside the image (Mat::roi) -> FD_ERR_ESTIMATE.  M_out is written only in mode 1. */
+int fd_align(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, const float *bbox /*4 or NULL*/,
+             const float *landmarks /*5x2*/, uint8_t *crop /*crop_h x crop_w x 3*/, double *M_out /*2x3 or NULL*/, int *mode_out);
 
 /* ---- batched device-resident pipeline (the benchmarked path); asynchronous on the ctx stream --------- */
 /* fd_nms with DEVICE buffers (asynchronous): dets_dev (K,5); keep_dev (K) int32; num_keep_dev (2) int32 =
@@ -194,13 +201,13 @@ typedef struct fd_det_view {
     const int32_t *candidates_dev; /* (B) pre-NMS candidate counts K */
 } fd_det_view;
 int fd_detect_view(fd_ctx *ctx, fd_det_view *out);
-/* Aligns F faces: landmarks_dev (F,10) in original-frame coordinates, frame_idx_dev (F) into frames.
- * crops_dev (F,crop_h,crop_w,3) u8; M_dev (F,6) f64 or NULL; ok_dev (F) u8 or NULL (0 -> estimation failed,
- * crop zero-filled). */
+/* Aligns F faces: landmarks_dev (F,10) in original-frame coordinates, frame_idx_dev (F) into frames, bbox_dev (F,4) or
+ * NULL (bbox == None) for the fallback.  crops_dev (F,crop_h,crop_w,3) u8; M_dev (F,6) f64 or NULL; ok_dev (F) u8 or NULL:
+ * 1 = similarity warp, 2 = bbox-crop fallback (face_alignment.rs:64-116), 0 = the reference returns Err (crop zero-filled). */
 int fd_align_batch(fd_ctx *ctx, const fd_frame *frames, int B, const float *landmarks_dev, const int32_t *frame_idx_dev,
-                   int F, uint8_t *crops_dev, double *M_dev, uint8_t *ok_dev);
-/* Aligns every detection of the last fd_detect_batch without a host round trip.  crops_dev has room for cap_faces
- * crops; detections beyond cap_faces are not aligned (fd_detect_fetch still reports them). */
+                   const float *bbox_dev, int F, uint8_t *crops_dev, double *M_dev, uint8_t *ok_dev);
+/* Aligns every detection of the last fd_detect_batch without a host round trip (fallback box = the detection's own box).
+ * crops_dev has room for cap_faces crops; detections beyond cap_faces are not aligned (fd_detect_fetch still reports them). */
 int fd_align_detections(fd_ctx *ctx, const fd_frame *frames, int B, uint8_t *crops_dev, int cap_faces, double *M_dev,
                         uint8_t *ok_dev);
 
@@ -243,24 +250,40 @@ int fd_face_selection(fd_ctx *ctx, int img_h, int img_w, const float *face_boxes
  * the call blocks (and first completes images the detect kernel deferred); without it nothing leaves the device. */
 int fd_select_detections(fd_ctx *ctx, const fd_frame *frames, int B, int is_enroll, const fd_select_params *params, int32_t *sel_host);
 /* FaceAlignment::call on the selection of the last fd_select_detections (face_pipeline/pipeline.rs:216-232): one crop per
- * image, crops_dev (B,crop_h,crop_w,3); images without a selection get ok = 0 and a zero crop.  M_dev (B,6) / ok_dev (B) optional. */
+ * image, crops_dev (B,crop_h,crop_w,3); images without a selection or without key points (the reference's call(.., None)
+ * returns Err) get ok = 0 and a zero crop; ok = 2 marks the bbox-crop fallback on the selected box.  M_dev (B,6) / ok_dev (B) optional. */
 int fd_align_selected(fd_ctx *ctx, const fd_frame *frames, int B, uint8_t *crops_dev, double *M_dev, uint8_t *ok_dev);
 
 /* ---- end-to-end with HOST buffers (bench.py "e2e"): H2D frames + heads, full path, D2H results -------- */
 typedef struct fd_host_batch_out {
-    int32_t *counts;      /* (B) */
+    int32_t *counts;      /* (B) detections per image */
     float *det;           /* (cap_rows,5) */
     float *landmarks;     /* (cap_rows,10) */
-    uint8_t *crops;       /* (cap_rows,crop_h,crop_w,3) */
+    uint8_t *crops;       /* (cap_rows,crop_h,crop_w,3): one per detection, or (select) one per image */
     float *det_scale;     /* (B) */
     float *tensor;        /* (B,3,image_h,image_w) or NULL: CNN input stays on the device (Triton CUDA-shm) */
+    uint8_t *align_mode;  /* (cap_rows) or NULL: per crop 1 = similarity warp, 2 = bbox-crop fallback, 0 = the reference errs (zero crop) */
+    int32_t *sel;         /* (B,2) or NULL, select mode: {row of the selected detection, row of its key points}, -1 = None */
     int32_t cap_rows;
-    int32_t total;        /* out */
+    int32_t total;        /* out: detections */
+    int32_t n_crops;      /* out: crops written (total, or B in select mode) */
     int64_t h2d_bytes, d2h_bytes; /* out: bytes moved */
 } fd_host_batch_out;
-/* frames[].data are HOST pointers here; heads_host as in fd_detect_batch but host memory. */
+enum { FD_UPLOAD_FULL = 0, FD_UPLOAD_ON_DEMAND = 1 };
+typedef struct fd_pipeline_opts {
+    int32_t select;     /* 0: align every detection (BASELINE config 4).  1: FacePipeline::extract's flow (face_pipeline/pipeline.rs:
+                           196-232): FaceSelection::call picks one face per image and only that face is aligned (crop b = image b) */
+    int32_t is_enroll;  /* FaceSelection::call is_enroll */
+    int32_t upload;     /* FD_UPLOAD_FULL: every frame crosses PCIe whole.  FD_UPLOAD_ON_DEMAND: first only the source rows the
+                           letterbox resize reads (1080p -> 640x360: one row in three), then, once the detections are known, only the
+                           pixel rectangles the warps read (or the rest of the frame when that is cheaper).  Same results. */
+    fd_select_params select_params;
+} fd_pipeline_opts;
+int fd_pipeline_opts_default(fd_pipeline_opts *opts);   /* select 0, FD_UPLOAD_FULL, fd_select_params_default */
+/* frames[].data are HOST pointers here (pinned for full PCIe rate); heads_host as in fd_detect_batch but host memory.
+ * opts NULL = defaults.  Blocks until the outputs are in host memory. */
 int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const float *const *heads_host, int n_heads,
-                     float conf_thr, float iou_thr, fd_host_batch_out *out);
+                     float conf_thr, float iou_thr, const fd_pipeline_opts *opts, fd_host_batch_out *out);
 /* Device tensor written by the last fd_pipeline_host / usable as the CNN input. */
 int fd_pipeline_tensor_dev(fd_ctx *ctx, const float **out_nchw_dev);
 

@@ -774,12 +774,52 @@ FDO_API void fdo_warp_affine_u8c3(const uint8_t *src, int sh, int sw, int spitch
     }
 }
 
-/* a14. FaceAlignment::call main branch (face_alignment.rs:50-59,119-126). Returns 1, or 0 when the
- * estimate is empty (the reference then takes the bbox-crop fallback :64-116, which is out of scope). */
-FDO_API int fdo_align_face(const uint8_t *img, int h, int w, int pitch, const float lmk[10], const float tmpl[10],
+/* Rust `f32::max` (returns the other operand when one is NaN) and `as i32` (truncates, saturates, NaN -> 0). */
+static inline float rs_f32_max(float a, float b) { return a != a ? b : (b != b ? a : (a > b ? a : b)); }
+static inline int rs_f32_as_i32(float v) {
+    if (v != v) return 0;
+    if (v >= 2147483648.0f) return 2147483647;
+    if (v <= -2147483648.0f) return (-2147483647 - 1);
+    return (int)v;
+}
+
+/* a14 fallback. FaceAlignment::call when the transformation matrix is empty (face_alignment.rs:64-116).
+ * bbox = Option<Array1<f32>> (NULL = None, :66-72).  Returns 1 and the resized crop, or 0 where the reference returns Err:
+ * Mat::roi (:92-95) rejects a rectangle that is not inside the image, cv::resize (:98) an empty one. */
+FDO_API int fdo_align_fallback(const uint8_t *img, int h, int w, int pitch, const float *bbox, int crop_w, int crop_h, uint8_t *crop) {
+    float det[4];
+    if (!bbox) {                                     /* :67-72 */
+        det[0] = (float)w * 0.0625f;
+        det[1] = (float)h * 0.0625f;
+        det[2] = (float)w - det[0];
+        det[3] = (float)h - det[1];
+    } else {
+        memcpy(det, bbox, sizeof(det));              /* :74 */
+    }
+    const float margin = 44.0f;                      /* :77 */
+    float bb[4];
+    bb[0] = rs_f32_max(det[0] - margin / 2.0f, 0.0f);            /* :79 */
+    bb[1] = rs_f32_max(det[1] - margin / 2.0f, 0.0f);            /* :80 */
+    bb[2] = rs_f32_max(det[2] + margin / 2.0f, (float)w);        /* :81 — `max`, as written */
+    bb[3] = rs_f32_max(det[1] + margin / 2.0f, (float)h);        /* :82 — det[1] and `max`, as written */
+    const int x0 = rs_f32_as_i32(bb[0]), y0 = rs_f32_as_i32(bb[1]), x1 = rs_f32_as_i32(bb[2]), y1 = rs_f32_as_i32(bb[3]);
+    const int width = x1 - x0, height = y1 - y0;     /* :88-89 */
+    /* Mat::roi: 0 <= x, 0 <= width, x + width <= cols (same for y); cv::resize: !src.empty() */
+    if (x0 < 0 || width < 0 || (long long)x0 + width > w || y0 < 0 || height < 0 || (long long)y0 + height > h) return 0;
+    if (width == 0 || height == 0) return 0;
+    fdo_resize_linear_u8c3(img + (size_t)y0 * pitch + (size_t)x0 * 3, height, width, pitch, crop, crop_h, crop_w, crop_w * 3);
+    return 1;
+}
+
+/* a14. FaceAlignment::call (face_alignment.rs:27-141): similarity warp (:50-59, :119-126), or the bbox-crop fallback
+ * (:64-116) when the estimate is empty.  Returns the mode: 1 = warp (M_out written), 2 = fallback crop, 0 = the reference
+ * returns Err (fallback ROI outside the image).  bbox NULL = None.  (landmarks = None never reaches here: the reference
+ * returns Err from estimateAffinePartial2D's assertion on the empty Mat.) */
+FDO_API int fdo_align_face(const uint8_t *img, int h, int w, int pitch, const float *bbox, const float lmk[10], const float tmpl[10],
                            int crop_w, int crop_h, uint8_t *crop, double M_out[6]) {
     double M[6];
-    if (!fdo_estimate_affine_partial_2d_lmeds(lmk, tmpl, 5, M, NULL)) return 0;
+    if (!fdo_estimate_affine_partial_2d_lmeds(lmk, tmpl, 5, M, NULL))
+        return fdo_align_fallback(img, h, w, pitch, bbox, crop_w, crop_h, crop) ? 2 : 0;
     if (M_out) memcpy(M_out, M, sizeof(M));
     fdo_warp_affine_u8c3(img, h, w, pitch, M, crop, crop_h, crop_w, crop_w * 3);
     return 1;
@@ -897,7 +937,8 @@ FDO_API int fdo_pipeline_frame(const fdo_det_cfg *cfg, const uint8_t *img, int h
     if (M < 0) return M;
     for (int i = 0; i < M; ++i) {
         uint8_t *crop = crops_out + (size_t)i * crop_w * crop_h * 3;
-        if (!fdo_align_face(img, h, w, pitch, lmk_out + (size_t)i * 10, tmpl, crop_w, crop_h, crop, NULL))
+        /* FacePipeline::extract passes the face's own box as the fallback bbox (face_pipeline/pipeline.rs:216) */
+        if (!fdo_align_face(img, h, w, pitch, det_out + (size_t)i * 5, lmk_out + (size_t)i * 10, tmpl, crop_w, crop_h, crop, NULL))
             memset(crop, 0, (size_t)crop_w * crop_h * 3);
     }
     return M;

@@ -331,15 +331,30 @@ def warp_affine(img, M, dsize=(112, 112)):
     return out
 
 
-def align_face(img, lmk, template=ARCFACE_TEMPLATE, dsize=(112, 112)):
+def align_face(img, lmk, template=ARCFACE_TEMPLATE, dsize=(112, 112), bbox=None, with_mode=False):
+    """FaceAlignment::call (face_alignment.rs:27-141).  -> (crop, M) — M is None when the bbox-crop fallback (:64-116) was
+    taken, both are None where the reference returns Err; with_mode appends the mode (1 warp, 2 fallback, 0 Err)."""
     img = np.ascontiguousarray(img, np.uint8)
     lmk, template = _f32(lmk).reshape(10), _f32(template).reshape(10)
+    bb = _f32(bbox).reshape(-1)[:4].copy() if bbox is not None else None
     dw, dh = dsize
     out = np.empty((dh, dw, 3), np.uint8)
     M = np.empty(6, np.float64)
-    ok = lib().fdo_align_face(_p(img, c_u8p), img.shape[0], img.shape[1], img.strides[0], _p(lmk, c_f32p),
-                              _p(template, c_f32p), dw, dh, _p(out, c_u8p), _p(M, c_f64p))
-    return (out, M.reshape(2, 3)) if ok else (None, None)
+    mode = lib().fdo_align_face(_p(img, c_u8p), img.shape[0], img.shape[1], img.strides[0], _p(bb, c_f32p) if bb is not None else None,
+                                _p(lmk, c_f32p), _p(template, c_f32p), dw, dh, _p(out, c_u8p), _p(M, c_f64p))
+    res = (out, M.reshape(2, 3)) if mode == 1 else ((out, None) if mode == 2 else (None, None))
+    return res + (mode,) if with_mode else res
+
+
+def align_fallback(img, bbox=None, dsize=(112, 112)):
+    """The empty-transform branch of FaceAlignment::call on its own (face_alignment.rs:64-116); None where it errs."""
+    img = np.ascontiguousarray(img, np.uint8)
+    bb = _f32(bbox).reshape(-1)[:4].copy() if bbox is not None else None
+    dw, dh = dsize
+    out = np.empty((dh, dw, 3), np.uint8)
+    ok = lib().fdo_align_fallback(_p(img, c_u8p), img.shape[0], img.shape[1], img.strides[0], _p(bb, c_f32p) if bb is not None else None,
+                                  dw, dh, _p(out, c_u8p))
+    return out if ok else None
 
 
 MODEL_NORMS = {  # (mean_rgb, mul_rgb) of the three post-align models

@@ -15,6 +15,7 @@
 #include <cfloat>
 #include "fd_internal.cuh"
 #include "fd_estimate.cuh"
+#include "fd_resize.cuh"
 
 namespace fd {
 
@@ -85,7 +86,26 @@ struct WarpArgs {
     int bands;             // ceil(ch / WARP_BAND)
     unsigned cw_magic;     // floor(2^32 / cw) + 1: p / cw == umulhi(p, cw_magic) for p < 2^20 (cw <= 4096)
     int *ticket;           // [0] next work item, [1] CTAs finished (both return to 0 when the launch ends)
+    // FaceAlignment::call's bbox-crop fallback (face_alignment.rs:64-116) for faces whose estimate is empty (ok == 0)
+    const float *bbox;     // rows of x1,y1,x2,y2,... (bbox_stride floats apart) or nullptr (bbox == None)
+    int bbox_stride;
+    const int *sel;        // optional (F,2) = {bbox row, key-point row} (fd_select_detections); key-point row < 0: landmarks == None
+    uint8_t *mode_out;     // optional (F): 1 = similarity warp, 2 = bbox-crop fallback, 0 = the reference returns Err (zero crop)
 };
+
+// Resolves the fallback of face f: returns true and the ROI origin when the reference would crop + resize, false when it
+// returns Err (landmarks == None: cv::estimateAffinePartial2D asserts on the empty Mat; ROI outside the image: Mat::roi).
+__device__ __forceinline__ bool warp_fallback_roi(const WarpArgs &a, int f, int fw, int fh, int *rx0, int *ry0) {
+    const float *bb = nullptr;
+    if (a.sel) {
+        if (a.sel[2 * f + 1] < 0) return false;
+        const int br = a.sel[2 * f];
+        if (br >= 0 && a.bbox) bb = a.bbox + (size_t)br * a.bbox_stride;
+    } else if (a.bbox) {
+        bb = a.bbox + (size_t)f * a.bbox_stride;
+    }
+    return fallback_roi(bb, fw, fh, rx0, ry0);
+}
 
 // The 6 bytes of two horizontally adjacent BGR pixels at byte offset `off` of an 8-byte aligned base, extracted from the
 // two aligned 64-bit words that cover them (lo = bytes 0..3, hi = bytes 4..5 in its low half).
@@ -246,12 +266,25 @@ __global__ void __launch_bounds__(WARP_THREADS, 4) warp_kernel(WarpArgs a) {
         const int npix = rows * a.cw;
         uint8_t *band_out = a.crops + ((size_t)f * a.ch + band_y0) * a.cw * 3;
         const bool packed = (reinterpret_cast<uintptr_t>(band_out) & 3) == 0 && (npix & 3) == 0;
-        if (!a.ok[f]) {   // estimation failed: zero crop (uniform over the CTA)
-            for (int p = tid; p < npix * 3; p += WARP_THREADS) band_out[p] = 0;
+        const FrameDev fr = a.frames[a.frame_idx ? a.frame_idx[f] : 0];
+        if (!a.ok[f]) {   // estimation failed (uniform over the CTA): bbox-crop fallback, or a zero crop where the reference errs
+            int rx0 = 0, ry0 = 0;
+            const bool valid = warp_fallback_roi(a, f, fr.w, fr.h, &rx0, &ry0);
+            if (tid == 0 && band_y0 == 0 && a.mode_out) a.mode_out[f] = valid ? 2 : 0;
+            if (valid) {
+                const uint8_t *roi = fr.data + (size_t)ry0 * fr.pitch + (size_t)rx0 * 3;
+                for (int p = tid; p < npix; p += WARP_THREADS) {
+                    const int row = p / a.cw, x = p - row * a.cw;
+                    const unsigned v = resize_pixel24(roi, fr.pitch, fr.w - rx0, fr.h - ry0, a.cw, a.ch, x, band_y0 + row);
+                    band_out[3 * p] = (uint8_t)v; band_out[3 * p + 1] = (uint8_t)(v >> 8); band_out[3 * p + 2] = (uint8_t)(v >> 16);
+                }
+            } else {
+                for (int p = tid; p < npix * 3; p += WARP_THREADS) band_out[p] = 0;
+            }
             __syncthreads();
             continue;
         }
-        const FrameDev fr = a.frames[a.frame_idx ? a.frame_idx[f] : 0];
+        if (tid == 0 && band_y0 == 0 && a.mode_out) a.mode_out[f] = 1;
         const double *iM = a.M12 + (size_t)f * 12 + 6;
         const double i0 = iM[0], i1 = iM[1], i2 = iM[2], i3 = iM[3], i4 = iM[4], i5 = iM[5];
         for (int x = tid; x < a.cw; x += WARP_THREADS)   // saturate_cast<int>(M[0]*x*AB_SCALE), AB_SCALE = 1024
@@ -390,13 +423,27 @@ __global__ void __launch_bounds__(2 * CW) warp_fixed_kernel(WarpArgs a) {
         }
         const bool interior = __syncthreads_and(vote) && (reinterpret_cast<uintptr_t>(data) & 7) == 0 && (pitch & 7) == 0 && pitch >= 16 &&
                               (size_t)fh * pitch < 0x7fffffffull;
-        if (!okf) {   // estimation failed: zero crop
-            for (int p = tid; p < IR * CW * 3 / 4; p += T) reinterpret_cast<unsigned *>(band_out)[p] = 0u;
-            continue;
-        }
-        const int2 *xy = &xy0[par][r];
         const bool store = (tid & 3) != 3;
         unsigned *outw = reinterpret_cast<unsigned *>(band_out) + 3 * (tid >> 2) + (tid & 3);
+        if (!okf) {   // estimation failed: bbox-crop fallback (face_alignment.rs:64-116), or a zero crop where the reference errs
+            int rx0 = 0, ry0 = 0;
+            const bool valid = warp_fallback_roi(a, f, fw, fh, &rx0, &ry0);
+            if (tid == 0 && y0 == 0 && a.mode_out) a.mode_out[f] = valid ? 2 : 0;
+            if (valid) {
+                const uint8_t *roi = data + (size_t)ry0 * pitch + (size_t)rx0 * 3;
+                for (int u = 0; u < ROUNDS; ++u) {
+                    const unsigned v = resize_pixel24(roi, pitch, fw - rx0, fh - ry0, CW, CH, x, y0 + r + 2 * u);
+                    const unsigned nv = __shfl_down_sync(0xffffffffu, v, 1);
+                    const unsigned word = __funnelshift_r(__byte_perm(v, nv, 0x4210), nv >> 8, 8 * (tid & 3u));
+                    if (store) outw[u * (T * 3 / 4)] = word;
+                }
+            } else {
+                for (int p = tid; p < IR * CW * 3 / 4; p += T) reinterpret_cast<unsigned *>(band_out)[p] = 0u;
+            }
+            continue;
+        }
+        if (tid == 0 && y0 == 0 && a.mode_out) a.mode_out[f] = 1;
+        const int2 *xy = &xy0[par][r];
         if (interior) {
             int u = 0;
 #pragma unroll 1
@@ -488,9 +535,13 @@ int invert_launch(fd_ctx *ctx, const double *M_dev, int F, double *M12_dev, uint
 }
 
 int warp_launch(fd_ctx *ctx, const FrameDev *frames_dev, const int32_t *frame_idx_dev, const double *M12_dev,
-                const uint8_t *ok_dev, const int *count_dev, int F_cap, uint8_t *crops_dev, int cw, int ch) {
+                const uint8_t *ok_dev, const int *count_dev, int F_cap, uint8_t *crops_dev, int cw, int ch, const WarpFallback &fb) {
     if (F_cap <= 0) return FD_OK;
     WarpArgs a;
+    a.bbox = fb.bbox;
+    a.bbox_stride = fb.bbox_stride;
+    a.sel = fb.sel;
+    a.mode_out = fb.mode_out;
     a.frames = frames_dev;
     a.frame_idx = frame_idx_dev;
     a.M12 = M12_dev;

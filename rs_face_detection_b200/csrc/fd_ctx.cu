@@ -244,8 +244,14 @@ FD_EXPORT int fd_ctx_create(int device_id, const fd_config *cfg, fd_ctx **out) {
     FD_REQUIRE(c.image_w > 0 && c.image_h > 0 && c.n_strides > 0 && c.n_strides <= FD_MAX_STRIDES, "fd_ctx_create: bad geometry");
     FD_REQUIRE(c.num_anchors > 0 && c.num_anchors <= FD_MAX_ANCHORS, "fd_ctx_create: bad num_anchors");
     FD_REQUIRE(c.crop_w > 0 && c.crop_h > 0 && c.crop_w <= 1024 && c.crop_h <= 1024, "fd_ctx_create: bad crop size");
+    for (int s = 0; s < c.n_strides; ++s) FD_REQUIRE(c.strides[s] > 0, "fd_ctx_create: bad stride");
     FD_CUDA(cudaSetDevice(device_id));
-    fd_ctx *ctx = new fd_ctx();
+    // every failure below goes through the guard, so a half-built ctx (streams, events) is released, not leaked
+    struct Guard {
+        fd_ctx *p;
+        ~Guard() { if (p) fd_ctx_destroy(p); }
+    } guard{new fd_ctx()};
+    fd_ctx *ctx = guard.p;
     ctx->device = device_id;
     ctx->cfg = c;
     ctx->trace_on = getenv("FD_TRACE") != nullptr && getenv("FD_TRACE")[0] == '1';
@@ -261,7 +267,6 @@ FD_EXPORT int fd_ctx_create(int device_id, const fd_config *cfg, fd_ctx **out) {
     d.n_strides = c.n_strides;
     d.A = c.num_anchors;
     for (int s = 0; s < c.n_strides; ++s) {
-        FD_REQUIRE(c.strides[s] > 0, "fd_ctx_create: bad stride");
         d.stride[s] = c.strides[s];
         d.fh[s] = (c.image_h + c.strides[s] - 1) / c.strides[s];
         d.fw[s] = (c.image_w + c.strides[s] - 1) / c.strides[s];
@@ -276,6 +281,7 @@ FD_EXPORT int fd_ctx_create(int device_id, const fd_config *cfg, fd_ctx **out) {
     d.landmark_std = c.landmark_std;
     d.clip_w = (float)c.image_w - 1.0f;
     d.clip_h = (float)c.image_h - 1.0f;
+    guard.p = nullptr;
     *out = ctx;
     return FD_OK;
 }
@@ -290,7 +296,7 @@ FD_EXPORT void fd_ctx_destroy(fd_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->frames_dev, &ctx->det_scale_dev, &ctx->cand_count, &ctx->cand_keys, &ctx->cand_box,
                       &ctx->cand_lmk, &ctx->keep_src, &ctx->keep_count, &ctx->status_dev, &ctx->big_list,
                       &ctx->out_offsets, &ctx->out_det, &ctx->out_lmk, &ctx->out_frame_idx, &ctx->align_M,
-                      &ctx->align_ok, &ctx->tickets, &ctx->scan_agg, &ctx->select_sel, &ctx->select_lmk, &ctx->select_fidx, &ctx->pipe_frames, &ctx->pipe_tensor, &ctx->pipe_crops};
+                      &ctx->align_ok, &ctx->tickets, &ctx->scan_agg, &ctx->select_sel, &ctx->select_lmk, &ctx->select_fidx, &ctx->pipe_frames, &ctx->pipe_tensor, &ctx->pipe_crops, &ctx->pipe_mode};
     for (auto *b : bufs) b->release();
     for (auto &b : ctx->nms_ws) b.release();
     for (auto &b : ctx->nms_ws_sp) b.release();

@@ -53,7 +53,6 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeCfg c, HeadPtrs hp, f
     const float *sc = hp.p[3 * s] + (size_t)b * 2 * A * hw;
     float score[FD_MAX_ANCHORS][VEC];
     unsigned pass = 0;  // bit a*VEC+v
-    bool nan_seen = false;
     if (active) {
 #pragma unroll
         for (int a = 0; a < FD_MAX_ANCHORS; ++a) {
@@ -68,12 +67,10 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeCfg c, HeadPtrs hp, f
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 const float sv = score[a][v];
-                nan_seen |= (sv != sv);                                  // the reference panics on NaN (utils.rs:92)
-                if (sv >= conf_thr) pass |= 1u << (a * VEC + v);         // face_detection.rs:375
+                if (sv >= conf_thr) pass |= 1u << (a * VEC + v);         // face_detection.rs:375 (a NaN score fails `>=`: dropped)
             }
         }
     }
-    if (nan_seen) atomicExch(&status[0], 1);
     const int cnt = __popc(pass);
     if (__ballot_sync(0xffffffffu, cnt != 0) == 0) return;  // common case: nothing above the threshold in this warp
     int incl = cnt;

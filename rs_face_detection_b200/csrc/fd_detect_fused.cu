@@ -30,6 +30,7 @@
 namespace fd {
 
 constexpr int FT = 1024;
+constexpr int FUSED_DBG_IMAGES = 4096;   // FD_FUSED_DBG=1 timestamps are kept for the first 4096 images of a launch
 
 struct FusedArgs {
     DecodeCfg c;
@@ -42,7 +43,7 @@ struct FusedArgs {
     int *counts;          // [B] candidates per image
     int *keep;            // [B][TA] kept anchor ids in pick order
     int *keep_count;      // [B]  (-1: deferred)
-    int *status;          // [0] NaN flag, [1] deferred images, [2] total faces
+    int *status;          // [0] unused, [1] deferred images, [2] total faces
     int *status_next;     // the other half of the ping-pong: zeroed by the last CTA for the next call
     int *big_list;
     const float *det_scale;
@@ -91,14 +92,13 @@ __device__ __forceinline__ void st_release_u64(u64 *p, u64 v) {
 // Score scan of image b: UN items (4 consecutive positions of one stride each) per thread are loaded before any is
 // processed, so the image's 2A score planes (134 KB for 640x640) cost about one memory latency.  AT: compile-time A (0 = runtime).
 template <int AT, int UN>
-__device__ __forceinline__ bool fused_score_scan(const FusedArgs &a, FusedSmem &sm, FusedCtrl &ctl, int b) {
+__device__ __forceinline__ void fused_score_scan(const FusedArgs &a, FusedSmem &sm, FusedCtrl &ctl, int b) {
     const DecodeCfg &c = a.c;
     constexpr int AMAX = AT ? AT : FD_MAX_ANCHORS;
     const int A = AT ? AT : c.A;
     const int tid = threadIdx.x, lane = tid & 31;
     const size_t img_base = (size_t)b * c.total_anchors;
     const int nq = c.total_pos >> 2;   // every H*W is a multiple of 4 (checked by the host)
-    bool nan_seen = false;
     for (int q0 = 0; q0 < nq; q0 += UN * FT) {
         float4 v[UN][AMAX];
         int s_[UN], local_[UN];
@@ -127,10 +127,8 @@ __device__ __forceinline__ bool fused_score_scan(const FusedArgs &a, FusedSmem &
                     if (aa >= A) break;
                     const float sv4[4] = {v[u][aa].x, v[u][aa].y, v[u][aa].z, v[u][aa].w};
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        nan_seen |= (sv4[k] != sv4[k]);                       // the reference panics on NaN (utils.rs:92)
-                        if (sv4[k] >= a.conf_thr) pass |= 1u << (aa * 4 + k);   // face_detection.rs:375
-                    }
+                    for (int k = 0; k < 4; ++k)   // face_detection.rs:375; a NaN score fails `>=` and is dropped like any low score
+                        if (sv4[k] >= a.conf_thr) pass |= 1u << (aa * 4 + k);
                 }
             }
             const int cnt = __popc(pass);
@@ -165,11 +163,10 @@ __device__ __forceinline__ bool fused_score_scan(const FusedArgs &a, FusedSmem &
             }
         }
     }
-    return nan_seen;
 }
 
 __device__ __forceinline__ void fused_stamp(const FusedArgs &a, int b, int slot) {
-    if (a.dbg && threadIdx.x == 0) {
+    if (a.dbg && threadIdx.x == 0 && b < FUSED_DBG_IMAGES) {
         long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         a.dbg[b * 16 + slot] = t;
@@ -195,14 +192,12 @@ __device__ __forceinline__ void detect_fused_body(const FusedArgs &a) {
     const size_t img_base = (size_t)b * TA;
 
     // ---- 1. score scan + key compaction ----
-    const bool nan_seen = c.A == 2 ? fused_score_scan<2, 3>(a, sm, ctl, b) : fused_score_scan<0, 1>(a, sm, ctl, b);
-    const bool nan_any = __syncthreads_or(nan_seen);
+    if (c.A == 2) fused_score_scan<2, 3>(a, sm, ctl, b);
+    else fused_score_scan<0, 1>(a, sm, ctl, b);
+    __syncthreads();
     fused_stamp(a, b, 1);
-    const int K = nan_any ? 0 : ctl.cnt;
-    if (tid == 0) {
-        a.counts[b] = ctl.cnt;
-        if (nan_any) atomicExch(&a.status[0], 1);
-    }
+    const int K = ctl.cnt;
+    if (tid == 0) a.counts[b] = K;
 
     // ---- 2. sort + decode + NMS (K <= 1024), or decode everything and defer ----
     int *keep = a.keep + img_base;
@@ -395,7 +390,7 @@ __device__ __forceinline__ void detect_fused_body(const FusedArgs &a) {
 
     __syncthreads();
     fused_stamp(a, b, 7);
-    if (a.dbg && tid == 0) { a.dbg[b * 16 + 8] = K; a.dbg[b * 16 + 9] = M; }
+    if (a.dbg && tid == 0 && b < FUSED_DBG_IMAGES) { a.dbg[b * 16 + 8] = K; a.dbg[b * 16 + 9] = M; }
     if (tid == 0) {   // the last CTA to leave re-arms the ticket for the next launch on this ctx
         __threadfence();
         if (atomicAdd(a.ticket + 1, 1) == (int)gridDim.x - 1) {
@@ -470,8 +465,8 @@ int detect_fused_launch(fd_ctx *ctx, const float *const *heads_dev, int B, float
     static long long *dbg_dev = nullptr;
     a.dbg = nullptr;
     if (dbg_on) {
-        if (!dbg_dev) cudaMalloc(&dbg_dev, sizeof(long long) * 16 * 4096);
-        cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 16 * 4096, ctx->stream);
+        if (!dbg_dev) FD_CUDA(cudaMalloc(&dbg_dev, sizeof(long long) * 16 * FUSED_DBG_IMAGES));
+        FD_CUDA(cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 16 * FUSED_DBG_IMAGES, ctx->stream));
         a.dbg = dbg_dev;
     }
     void (*kern)(const FusedArgs) = ctx->share_sms ? detect_fused_shared_kernel : detect_fused_kernel;
@@ -479,12 +474,12 @@ int detect_fused_launch(fd_ctx *ctx, const float *const *heads_dev, int B, float
     kern<<<B, FT, smem, ctx->stream>>>(a);
     FD_LAUNCH_CHECK_NAMED(ctx, "detect_fused_kernel");
     if (dbg_on) {
-        std::vector<long long> h(16 * (size_t)std::min(B, 4096));
+        std::vector<long long> h(16 * (size_t)std::min(B, FUSED_DBG_IMAGES));
         cudaStreamSynchronize(ctx->stream);
         cudaMemcpy(h.data(), dbg_dev, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
         long long t0 = h[0];
-        for (int b = 0; b < std::min(B, 4096); ++b) t0 = std::min(t0, h[16 * b]);
-        for (int b = 0; b < std::min(B, 4096); ++b) {
+        for (int b = 0; b < std::min(B, FUSED_DBG_IMAGES); ++b) t0 = std::min(t0, h[16 * b]);
+        for (int b = 0; b < std::min(B, FUSED_DBG_IMAGES); ++b) {
             const long long *d = &h[16 * b];
             fprintf(stderr, "[fused dbg] img %3d K=%4lld M=%3lld start+%5.2f scan %5.2f sort %5.2f decode %5.2f nms %6.2f gather %5.2f est %5.2f offs+out %5.2f total %6.2f us\n",
                     b, d[8], d[9], (d[0] - t0) * 1e-3, (d[1] - d[0]) * 1e-3, (d[2] - d[1]) * 1e-3, (d[3] - d[2]) * 1e-3, (d[4] - d[3]) * 1e-3,

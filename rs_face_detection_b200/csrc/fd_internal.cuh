@@ -121,6 +121,7 @@ struct fd_ctx {
     fd::DevBuf pipe_heads[3 * FD_MAX_STRIDES];
     fd::DevBuf pipe_tensor;
     fd::DevBuf pipe_crops;
+    fd::DevBuf pipe_mode;        // u8[cap_rows] per-crop align mode of the host pipeline
     int last_B = 0;
     int last_out_cap = 0;
     bool detect_pending = false; // results enqueued, NaN check / big-path fix-up not yet done (lazy, at fetch)
@@ -233,7 +234,14 @@ int ticket_buffer(fd_ctx *ctx);
 int select_launch(fd_ctx *ctx, const int *offsets_dev, const float *det_dev, const float *lmk_dev, const FrameDev *frames_dev, int B,
                   const fd_select_params *p, int is_enroll, int *sel_dev, float *sel_lmk_dev, int *sel_frame_idx_dev);
 int invert_launch(fd_ctx *ctx, const double *M_dev, int F, double *M12_dev, uint8_t *ok_dev);
+// inputs of FaceAlignment::call's bbox-crop fallback (face_alignment.rs:64-116), taken by faces whose estimate is empty
+struct WarpFallback {
+    const float *bbox = nullptr;   // device rows x1,y1,x2,y2,... bbox_stride floats apart; nullptr: bbox == None
+    int bbox_stride = 4;
+    const int *sel = nullptr;      // optional device (F,2) {bbox row, key-point row}; key-point row < 0: landmarks == None -> Err
+    uint8_t *mode_out = nullptr;   // optional device (F): 1 warp, 2 fallback crop, 0 the reference returns Err (zero crop)
+};
 int warp_launch(fd_ctx *ctx, const FrameDev *frames_dev, const int32_t *frame_idx_dev, const double *M12_dev,
-                const uint8_t *ok_dev, const int *count_dev, int F_cap, uint8_t *crops_dev, int cw, int ch);
+                const uint8_t *ok_dev, const int *count_dev, int F_cap, uint8_t *crops_dev, int cw, int ch, const WarpFallback &fb);
 
 }  // namespace fd

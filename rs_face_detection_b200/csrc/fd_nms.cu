@@ -34,7 +34,7 @@ namespace fd {
 
 
 __device__ __forceinline__ void dbg_stamp(const SmallArgs &a, int slot) {
-    if (a.dbg && threadIdx.x == 0) {
+    if (a.dbg && threadIdx.x == 0 && blockIdx.x < 4096) {   // FD_NMS_DBG=1 keeps the first 4096 problems
         long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         a.dbg[blockIdx.x * 16 + slot] = t;
@@ -103,7 +103,7 @@ __device__ void nms_tiny(const SmallArgs &a, unsigned char *smem_raw, int b, int
     const int nk = fast ? tiny_greedy<MODE, true>(sm, a.iou, K, nthr, keep, my, &iters) : tiny_greedy<MODE, false>(sm, a.iou, K, nthr, keep, my, &iters);
     if (tid == 0) a.keep_count[b] = nk;
     dbg_stamp(a, 4);
-    if (a.dbg && tid == 0) { a.dbg[blockIdx.x * 16 + 5] = iters; a.dbg[blockIdx.x * 16 + 6] = K; a.dbg[blockIdx.x * 16 + 7] = nk; }
+    if (a.dbg && tid == 0 && blockIdx.x < 4096) { a.dbg[blockIdx.x * 16 + 5] = iters; a.dbg[blockIdx.x * 16 + 6] = K; a.dbg[blockIdx.x * 16 + 7] = nk; }
 }
 
 template <int MODE, int BS>
@@ -878,8 +878,8 @@ static int launch_small(fd_ctx *ctx, const SmallArgs &a_in, int B, bool float4_b
     static const int dbg_on = getenv("FD_NMS_DBG") != nullptr;
     static long long *dbg_dev = nullptr;
     if (dbg_on) {
-        if (!dbg_dev) cudaMalloc(&dbg_dev, sizeof(long long) * 16 * 4096);
-        cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 16 * 4096, ctx->stream);
+        if (!dbg_dev) FD_CUDA(cudaMalloc(&dbg_dev, sizeof(long long) * 16 * 4096));
+        FD_CUDA(cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 16 * 4096, ctx->stream));
         a.dbg = dbg_dev;
     }
     static_assert(sizeof(TinySmem) <= sizeof(SmallSmem), "tiny path lives in the general path's shared memory");

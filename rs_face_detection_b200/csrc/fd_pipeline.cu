@@ -2,20 +2,14 @@
 // host-buffer end-to-end call.  Mirrors RetinaFaceDetection::call (face_detection.rs:496-513) and
 // FaceAlignment::call (face_alignment.rs:27-141) at batch granularity.
 #include <algorithm>
+#include <cmath>
+#include <climits>
 #include <cstdlib>
 #include <cstddef>
 #include <cstring>
 #include "fd_internal.cuh"
 
 namespace fd {
-
-int resize_launch(fd_ctx *ctx, const FrameDev &frame, uint8_t *out_dev, int out_h, int out_w);
-int nms_batch_big_image(fd_ctx *ctx, int b, int K, float iou_thr);
-int estimate_launch(fd_ctx *ctx, const float *from_dev, const float *to_dev, const int *count_dev, int F_cap,
-                    double *M12_dev, double *M_out_dev, uint8_t *ok_dev, uint8_t *ok_out_dev);
-int invert_launch(fd_ctx *ctx, const double *M_dev, int F, double *M12_dev, uint8_t *ok_dev);
-int warp_launch(fd_ctx *ctx, const FrameDev *frames_dev, const int32_t *frame_idx_dev, const double *M12_dev,
-                const uint8_t *ok_dev, const int *count_dev, int F_cap, uint8_t *crops_dev, int cw, int ch);
 
 // RetinaFaceDetection::_preprocess geometry (face_detection.rs:140-153): f32 arithmetic, `as i32` truncation
 static void letterbox(int h, int w, int size_w, int size_h, int *new_w, int *new_h, float *det_scale) {
@@ -80,23 +74,34 @@ static int upload_frame_table(fd_ctx *ctx, const fd_frame *frames, int B, float 
 
 // from_detect: the faces are the detections of the last fd_detect_batch; when the fused detect kernel already estimated
 // their transforms (ctx->est_valid) and they all fit, the estimate launch is skipped.
+// fb: the bbox rows / selection of the fallback (face_alignment.rs:64-116); ok_dev receives the per-face mode (0/1/2).
 static int align_enqueue(fd_ctx *ctx, const FrameDev *frames_dev, const float *lmk_dev, const int32_t *frame_idx_dev,
-                         const int *count_dev, int F_cap, uint8_t *crops_dev, double *M_dev, uint8_t *ok_dev, bool from_detect) {
+                         const int *count_dev, int F_cap, uint8_t *crops_dev, double *M_dev, uint8_t *ok_dev, bool from_detect,
+                         WarpFallback fb) {
     if (F_cap <= 0) return FD_OK;
     ctx->align_cap_hint = std::max(ctx->align_cap_hint, F_cap);
-    const bool reuse = from_detect && ctx->est_valid && F_cap <= ctx->est_cap && !M_dev && !ok_dev;
+    const bool reuse = from_detect && ctx->est_valid && F_cap <= ctx->est_cap && !M_dev;
     if (!reuse) {
         ctx->est_valid = false;
         FD_TRY(ctx->align_M.reserve(sizeof(double) * 12 * (size_t)F_cap));
         FD_TRY(ctx->align_ok.reserve((size_t)F_cap));
-        FD_TRY(estimate_launch(ctx, lmk_dev, nullptr, count_dev, F_cap, ctx->align_M.as<double>(), M_dev, ctx->align_ok.as<uint8_t>(), ok_dev));
+        FD_TRY(estimate_launch(ctx, lmk_dev, nullptr, count_dev, F_cap, ctx->align_M.as<double>(), M_dev, ctx->align_ok.as<uint8_t>(), nullptr));
     }
+    fb.mode_out = ok_dev;
     FD_TRY(warp_launch(ctx, frames_dev, frame_idx_dev, ctx->align_M.as<double>(), ctx->align_ok.as<uint8_t>(), count_dev, F_cap,
-                       crops_dev, ctx->cfg.crop_w, ctx->cfg.crop_h));
+                       crops_dev, ctx->cfg.crop_w, ctx->cfg.crop_h, fb));
     return FD_OK;
 }
 
-// completes a pending fd_detect_batch: surfaces NaN errors and runs the big path for images with K > 4096
+// the detections of the last fd_detect_batch as fallback boxes: row f of out_det = x1,y1,x2,y2,score
+static WarpFallback detect_fallback(fd_ctx *ctx) {
+    WarpFallback fb;
+    fb.bbox = ctx->out_det.as<float>();
+    fb.bbox_stride = 5;
+    return fb;
+}
+
+// completes a pending fd_detect_batch: runs the big path for images the detect kernel deferred (K > 4096)
 static int detect_resolve(fd_ctx *ctx) {
     if (!ctx->detect_pending) return FD_OK;
     const int B = ctx->last_B;
@@ -104,7 +109,6 @@ static int detect_resolve(fd_ctx *ctx) {
     FD_CUDA(cudaMemcpyAsync(st, ctx->status(), sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
     FD_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->detect_pending = false;
-    if (st[0]) return fail(FD_ERR_NAN_SCORE, "fd_detect_batch: NaN score (the reference panics, utils.rs:92)");
     if (st[1] > 0) {
         ctx->crowded = true;   // later fused launches keep images with up to 4096 candidates on the device
         std::vector<int> big(st[1]), counts(B);
@@ -118,7 +122,8 @@ static int detect_resolve(fd_ctx *ctx) {
         ctx->est_valid = false;
         if (ctx->align_replay)  // the crops were produced from incomplete detections: align again
             FD_TRY(align_enqueue(ctx, ctx->frames_dev.as<FrameDev>(), ctx->out_lmk.as<float>(), ctx->out_frame_idx.as<int32_t>(),
-                                 ctx->status() + 2, ctx->align_cap, ctx->align_crops, ctx->align_M_out, ctx->align_ok_out, true));
+                                 ctx->status() + 2, ctx->align_cap, ctx->align_crops, ctx->align_M_out, ctx->align_ok_out, true,
+                                 detect_fallback(ctx)));
         FD_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     return FD_OK;
@@ -245,19 +250,22 @@ FD_EXPORT int fd_detect_view(fd_ctx *ctx, fd_det_view *out) {
 }
 
 FD_EXPORT int fd_align_batch(fd_ctx *ctx, const fd_frame *frames, int B, const float *landmarks_dev, const int32_t *frame_idx_dev,
-                             int F, uint8_t *crops_dev, double *M_dev, uint8_t *ok_dev) {
+                             const float *bbox_dev, int F, uint8_t *crops_dev, double *M_dev, uint8_t *ok_dev) {
     FD_TRY(check_ctx(ctx));
     FD_REQUIRE(B > 0 && frames && F >= 0 && (F == 0 || (landmarks_dev && crops_dev)), "fd_align_batch: bad arguments");
     if (F == 0) return FD_OK;
     FD_TRY(upload_frame_table(ctx, frames, B, nullptr, nullptr));
-    return align_enqueue(ctx, ctx->frames_dev.as<FrameDev>(), landmarks_dev, frame_idx_dev, nullptr, F, crops_dev, M_dev, ok_dev, false);
+    WarpFallback fb;
+    fb.bbox = bbox_dev;
+    fb.bbox_stride = 4;
+    return align_enqueue(ctx, ctx->frames_dev.as<FrameDev>(), landmarks_dev, frame_idx_dev, nullptr, F, crops_dev, M_dev, ok_dev, false, fb);
 }
 
 FD_EXPORT int fd_align_detections(fd_ctx *ctx, const fd_frame *frames, int B, uint8_t *crops_dev, int cap_faces, double *M_dev,
                                   uint8_t *ok_dev) {
     FD_TRY(check_ctx(ctx));
     FD_REQUIRE(B > 0 && frames && B == ctx->last_B && crops_dev && cap_faces > 0, "fd_align_detections: bad arguments");
-    // No host synchronisation here: NaN scores and images needing the big NMS path are detected lazily at
+    // No host synchronisation here: images needing the big NMS path are detected lazily at
     // fd_detect_fetch / fd_detect_view / fd_ctx-level fetch, which replays this align if the detections changed.
     FD_TRY(upload_frame_table(ctx, frames, B, nullptr, nullptr));
     ctx->align_replay = true;
@@ -266,7 +274,7 @@ FD_EXPORT int fd_align_detections(fd_ctx *ctx, const fd_frame *frames, int B, ui
     ctx->align_M_out = M_dev;
     ctx->align_ok_out = ok_dev;
     return align_enqueue(ctx, ctx->frames_dev.as<FrameDev>(), ctx->out_lmk.as<float>(), ctx->out_frame_idx.as<int32_t>(),
-                         ctx->status() + 2, cap_faces, crops_dev, M_dev, ok_dev, true);
+                         ctx->status() + 2, cap_faces, crops_dev, M_dev, ok_dev, true, detect_fallback(ctx));
 }
 
 // ---- single-image host wrappers -----------------------------------------------------------------------------------
@@ -365,8 +373,9 @@ FD_EXPORT int fd_estimate_affine_partial_2d(fd_ctx *ctx, const float *from, cons
     return FD_OK;
 }
 
-static int warp_host(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, const double *M, const float *lmk, uint8_t *out,
-                     int out_h, int out_w, double *M_out) {
+// M given (fd_warp_affine) or estimated from lmk (fd_align; bbox = the fallback's box, face_alignment.rs:64-116)
+static int warp_host(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, const double *M, const float *lmk, const float *bbox,
+                     uint8_t *out, int out_h, int out_w, double *M_out, int *mode_out) {
     FD_TRY(check_ctx(ctx));
     FD_REQUIRE(out && out_h > 0 && out_w > 0 && out_w <= 4096, "warp: bad output size");
     const uint8_t *d_img;
@@ -383,38 +392,50 @@ static int warp_host(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, c
     ctx->est_valid = false;
     FD_TRY(ctx->align_M.reserve(sizeof(double) * 12));
     FD_TRY(ctx->align_ok.reserve(16));
-    FD_TRY(ctx->scratch[0].reserve(sizeof(double) * 6 + sizeof(float) * 10));
+    FD_TRY(ctx->scratch[0].reserve(64 + sizeof(float) * 10 + sizeof(float) * 4 + 16));   // M or landmarks | bbox | mode
+    unsigned char *sc0 = ctx->scratch[0].as<unsigned char>();
     if (M) {
-        FD_CUDA(cudaMemcpyAsync(ctx->scratch[0].p, M, sizeof(double) * 6, cudaMemcpyHostToDevice, ctx->stream));
-        FD_TRY(invert_launch(ctx, ctx->scratch[0].as<double>(), 1, ctx->align_M.as<double>(), ctx->align_ok.as<uint8_t>()));
+        FD_CUDA(cudaMemcpyAsync(sc0, M, sizeof(double) * 6, cudaMemcpyHostToDevice, ctx->stream));
+        FD_TRY(invert_launch(ctx, reinterpret_cast<double *>(sc0), 1, ctx->align_M.as<double>(), ctx->align_ok.as<uint8_t>()));
     } else {
-        FD_CUDA(cudaMemcpyAsync(ctx->scratch[0].p, lmk, sizeof(float) * 10, cudaMemcpyHostToDevice, ctx->stream));
-        FD_TRY(estimate_launch(ctx, ctx->scratch[0].as<float>(), nullptr, nullptr, 1, ctx->align_M.as<double>(), nullptr,
+        FD_CUDA(cudaMemcpyAsync(sc0, lmk, sizeof(float) * 10, cudaMemcpyHostToDevice, ctx->stream));
+        FD_TRY(estimate_launch(ctx, reinterpret_cast<float *>(sc0), nullptr, nullptr, 1, ctx->align_M.as<double>(), nullptr,
                                ctx->align_ok.as<uint8_t>(), nullptr));
     }
+    WarpFallback fb;
+    if (bbox) {
+        FD_CUDA(cudaMemcpyAsync(sc0 + 64, bbox, sizeof(float) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        fb.bbox = reinterpret_cast<float *>(sc0 + 64);
+    }
+    fb.mode_out = sc0 + 64 + 16;
     const size_t n = (size_t)out_h * out_w * 3;
     FD_TRY(ctx->scratch[4].reserve(n));
     FD_TRY(warp_launch(ctx, ctx->scratch[5].as<FrameDev>(), nullptr, ctx->align_M.as<double>(), ctx->align_ok.as<uint8_t>(), nullptr, 1,
-                       ctx->scratch[4].as<uint8_t>(), out_w, out_h));
-    uint8_t okh = 0;
+                       ctx->scratch[4].as<uint8_t>(), out_w, out_h, fb));
+    uint8_t mode = 0;
     double M12[12];
     FD_CUDA(cudaMemcpyAsync(out, ctx->scratch[4].p, n, cudaMemcpyDeviceToHost, ctx->stream));
-    FD_CUDA(cudaMemcpyAsync(&okh, ctx->align_ok.p, 1, cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(cudaMemcpyAsync(&mode, fb.mode_out, 1, cudaMemcpyDeviceToHost, ctx->stream));
     FD_CUDA(cudaMemcpyAsync(M12, ctx->align_M.p, sizeof(M12), cudaMemcpyDeviceToHost, ctx->stream));
     FD_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (M_out) memcpy(M_out, M12, sizeof(double) * 6);
-    if (!okh) return fail(FD_ERR_ESTIMATE, "fd_align: similarity estimation failed (reference falls back to a bbox crop)");
+    if (M_out && mode == 1) memcpy(M_out, M12, sizeof(double) * 6);
+    if (mode_out) *mode_out = mode;
+    if (!mode)
+        return fail(FD_ERR_ESTIMATE, "fd_align: empty transform and the fallback crop (x0,y0)..(max(x2+22,W), max(y1+22,H)) is not inside "
+                                     "the image (the reference returns Err from Mat::roi, face_alignment.rs:92-95)");
     return FD_OK;
 }
 
 FD_EXPORT int fd_warp_affine(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, const double *M, uint8_t *out, int out_h,
                              int out_w) {
     FD_REQUIRE(M, "fd_warp_affine: null M");
-    return warp_host(ctx, img, h, w, pitch, M, nullptr, out, out_h, out_w, nullptr);
+    return warp_host(ctx, img, h, w, pitch, M, nullptr, nullptr, out, out_h, out_w, nullptr, nullptr);
 }
-FD_EXPORT int fd_align(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, const float *landmarks, uint8_t *crop, double *M_out) {
-    FD_REQUIRE(ctx && landmarks, "fd_align: null landmarks (the reference's bbox-crop fallback is out of scope)");
-    return warp_host(ctx, img, h, w, pitch, nullptr, landmarks, crop, ctx->cfg.crop_h, ctx->cfg.crop_w, M_out);
+FD_EXPORT int fd_align(fd_ctx *ctx, const uint8_t *img, int h, int w, int pitch, const float *bbox, const float *landmarks, uint8_t *crop,
+                       double *M_out, int *mode_out) {
+    // landmarks == None: array2_to_mat is skipped, cv::estimateAffinePartial2D asserts on the empty Mat and call() returns Err
+    FD_REQUIRE(ctx && landmarks, "fd_align: landmarks == None (the reference returns Err: estimateAffinePartial2D on an empty Mat)");
+    return warp_host(ctx, img, h, w, pitch, nullptr, landmarks, bbox, crop, ctx->cfg.crop_h, ctx->cfg.crop_w, M_out, mode_out);
 }
 
 // ---- N1: post-align model preprocessors ------------------------------------------------------------------------------
@@ -540,57 +561,201 @@ FD_EXPORT int fd_align_selected(fd_ctx *ctx, const fd_frame *frames, int B, uint
     FD_TRY(check_ctx(ctx));
     FD_REQUIRE(frames && B > 0 && B == ctx->select_B && crops_dev, "fd_align_selected: needs the frames of the last fd_select_detections");
     FD_TRY(upload_frame_table(ctx, frames, B, nullptr, nullptr));
-    // images without a selection carry NaN key points: the estimate fails there (ok = 0) and the crop is zero-filled
+    // Images without a selection (or whose selection has no key points) carry NaN key points: the estimate fails there and,
+    // as the reference's call(&image, box, None) errs on the empty landmark Mat, the crop is zero-filled with ok = 0; a
+    // selection whose key points are degenerate takes the bbox-crop fallback on its selected box (ok = 2).
+    WarpFallback fb = detect_fallback(ctx);
+    fb.sel = ctx->select_sel.as<int>();
     return align_enqueue(ctx, ctx->frames_dev.as<FrameDev>(), ctx->select_lmk.as<float>(), ctx->select_fidx.as<int32_t>(), nullptr, B, crops_dev,
-                         M_dev, ok_dev, false);
+                         M_dev, ok_dev, false, fb);
 }
 
 // ---- end-to-end with host buffers ------------------------------------------------------------------------------------
+namespace fd {
+
+// Host replica of y_taps (fd_resize.cuh): the one or two source rows destination row dy of cv::resize reads.
+static void host_y_rows(int dy, double scale_y, int sh, int *y0, int *y1, bool *two) {
+    volatile float fy = (float)(((double)dy + 0.5) * scale_y - 0.5);
+    const int sy = (int)floorf(fy);
+    volatile float fr = fy - (float)sy;
+    volatile float w1 = fr * 2048.0f;
+    const long b1 = lrintf(w1);   // cvRound: round-half-even in the default rounding mode
+    *y0 = std::min(std::max(sy, 0), sh - 1);
+    *y1 = std::min(std::max(sy + 1, 0), sh - 1);
+    *two = b1 != 0;
+}
+
+static int sat_int_rn(double v) {   // __double2int_rn: round-half-even, saturating, NaN -> 0
+    if (!(v == v)) return 0;
+    const double r = nearbyint(v);
+    if (r >= 2147483647.0) return 2147483647;
+    if (r <= -2147483648.0) return (-2147483647 - 1);
+    return (int)r;
+}
+
+// Source pixel rectangle [x0,x1] x [y0,y1] (inclusive, clipped to the frame) the fixed-point warp of one face reads:
+// the tap coordinates of warp_fixed_kernel / warp_kernel are monotone in x and in y, so their extremes are at the crop's
+// corners; +1 for the second tap of each axis.  Returns false when the crop reads nothing inside the frame.
+static bool warp_source_rect(const double *iM, int cw, int ch, int fw, int fh, int *x0, int *y0, int *x1, int *y1) {
+    long long lx = (1ll << 40), ly = (1ll << 40), hx = -(1ll << 40), hy = -(1ll << 40);
+    const int xs[2] = {0, cw - 1}, ys[2] = {0, ch - 1};
+    for (int cy = 0; cy < 2; ++cy)
+        for (int cx = 0; cx < 2; ++cx) {
+            const int X0 = sat_int_rn((iM[1] * ys[cy] + iM[2]) * 1024) + 16, Y0 = sat_int_rn((iM[4] * ys[cy] + iM[5]) * 1024) + 16;
+            const int dx = sat_int_rn(iM[0] * xs[cx] * 1024), dy = sat_int_rn(iM[3] * xs[cx] * 1024);
+            const int X = (int)((unsigned)X0 + (unsigned)dx) >> 5, Y = (int)((unsigned)Y0 + (unsigned)dy) >> 5;
+            const long long sx = X >> 5, sy = Y >> 5;
+            lx = std::min(lx, sx); hx = std::max(hx, sx + 1);
+            ly = std::min(ly, sy); hy = std::max(hy, sy + 1);
+        }
+    lx = std::max<long long>(lx, 0); ly = std::max<long long>(ly, 0);
+    hx = std::min<long long>(hx, fw - 1); hy = std::min<long long>(hy, fh - 1);
+    if (lx > hx || ly > hy) return false;
+    *x0 = (int)lx; *y0 = (int)ly; *x1 = (int)hx; *y1 = (int)hy;
+    return true;
+}
+
+struct HostFrame {
+    size_t off;     // offset of the frame in the device arena
+    int dpitch;     // device pitch (16-byte multiple)
+    bool full;      // every row is on the device
+    // rows already uploaded for the preprocess when !full: a0 + k*j (and a1 + k*j when two), j < n
+    int a0, a1, k, n;
+    bool two;
+};
+
+// whole frame, one copy
+static int upload_full(fd_ctx *ctx, const fd_frame &fr, uint8_t *dst, int dpitch, int64_t *h2d) {
+    const size_t row = (size_t)fr.width * 3;
+    if (fr.pitch == dpitch)
+        FD_CUDA(cudaMemcpyAsync(dst, fr.data, (size_t)dpitch * (fr.height - 1) + row, cudaMemcpyHostToDevice, ctx->stream));
+    else
+        FD_CUDA(cudaMemcpy2DAsync(dst, dpitch, fr.data, fr.pitch, row, fr.height, cudaMemcpyHostToDevice, ctx->stream));
+    *h2d += (int64_t)row * fr.height;
+    return FD_OK;
+}
+
+// Only the source rows the letterbox resize reads (face_detection.rs:156): for an integer down-scale k they form at most two
+// arithmetic progressions of stride k (1080p -> 640x360: rows 3y+1; 4K: rows 6y+2 and 6y+3), each ONE strided 2-D copy.
+// Returns *done = false when the pattern is not worth it (most rows needed, or no short description): caller uploads the frame.
+static int upload_preprocess_rows(fd_ctx *ctx, const fd_frame &fr, int new_h, double scale_y, uint8_t *dst, int dpitch, int64_t *h2d,
+                                  HostFrame *hfr, bool *done) {
+    *done = false;
+    const int h = fr.height;
+    const long long k = llround(scale_y);
+    if (k < 2 || fabs(scale_y - (double)k) > 1e-12 || new_h < 2) return FD_OK;
+    // rows of dy = 0 and their stride-k continuation must reproduce every dy's rows
+    int a0, a1, c0, c1;
+    bool two0, two;
+    host_y_rows(0, scale_y, h, &a0, &a1, &two0);
+    for (int dy = 1; dy < new_h; ++dy) {
+        host_y_rows(dy, scale_y, h, &c0, &c1, &two);
+        if (two != two0 || c0 != a0 + (int)k * dy || (two && c1 != a1 + (int)k * dy)) return FD_OK;
+    }
+    if (two0 && k < 3) return FD_OK;
+    const size_t row = (size_t)fr.width * 3;
+    FD_CUDA(cudaMemcpy2DAsync(dst + (size_t)a0 * dpitch, (size_t)k * dpitch, fr.data + (size_t)a0 * fr.pitch, (size_t)k * fr.pitch, row, new_h,
+                              cudaMemcpyHostToDevice, ctx->stream));
+    *h2d += (int64_t)row * new_h;
+    if (two0) {
+        FD_CUDA(cudaMemcpy2DAsync(dst + (size_t)a1 * dpitch, (size_t)k * dpitch, fr.data + (size_t)a1 * fr.pitch, (size_t)k * fr.pitch, row, new_h,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+        *h2d += (int64_t)row * new_h;
+    }
+    hfr->a0 = a0; hfr->a1 = a1; hfr->k = (int)k; hfr->n = new_h; hfr->two = two0;
+    *done = true;
+    return FD_OK;
+}
+
+// the rows upload_preprocess_rows left out: the other residues mod k, and the tail of the uploaded residues
+static int upload_complement_rows(fd_ctx *ctx, const fd_frame &fr, const HostFrame &hfr, uint8_t *dst, int64_t *h2d) {
+    const size_t row = (size_t)fr.width * 3;
+    const int k = hfr.k, h = fr.height;
+    auto strided = [&](int first, int step, int count) -> int {
+        if (count <= 0) return FD_OK;
+        FD_CUDA(cudaMemcpy2DAsync(dst + (size_t)first * hfr.dpitch, (size_t)step * hfr.dpitch, fr.data + (size_t)first * fr.pitch,
+                                  (size_t)step * fr.pitch, row, count, cudaMemcpyHostToDevice, ctx->stream));
+        *h2d += (int64_t)row * count;
+        return FD_OK;
+    };
+    for (int r = 0; r < k; ++r) {
+        if (r == hfr.a0 % k || (hfr.two && r == hfr.a1 % k)) continue;
+        FD_TRY(strided(r, k, (h - r + k - 1) / k));
+    }
+    const int firsts[2] = {hfr.a0, hfr.a1};
+    for (int t = 0; t < (hfr.two ? 2 : 1); ++t) {
+        const int r = firsts[t] % k;
+        if (firsts[t] > r) FD_TRY(strided(r, k, (firsts[t] - r) / k));                   // rows of this residue before the first one
+        const int next = firsts[t] + k * hfr.n;
+        if (next < h) FD_TRY(strided(next, k, (h - next + k - 1) / k));                   // ... and after the last one
+    }
+    return FD_OK;
+}
+
+}  // namespace fd
+
+FD_EXPORT int fd_pipeline_opts_default(fd_pipeline_opts *o) {
+    FD_REQUIRE(o, "fd_pipeline_opts_default: null");
+    memset(o, 0, sizeof(*o));
+    return fd_select_params_default(&o->select_params);
+}
+
 FD_EXPORT int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const float *const *heads_host, int n_heads,
-                               float conf_thr, float iou_thr, fd_host_batch_out *out) {
+                               float conf_thr, float iou_thr, const fd_pipeline_opts *opts, fd_host_batch_out *out) {
     FD_TRY(check_ctx(ctx));
     FD_REQUIRE(frames && heads_host && out && B > 0, "fd_pipeline_host: bad arguments");
     FD_REQUIRE(n_heads == 3 * ctx->dcfg.n_strides, "fd_pipeline_host: n_heads must be 3 * n_strides");
     FD_REQUIRE(out->counts && out->det && out->landmarks && out->crops && out->cap_rows > 0, "fd_pipeline_host: bad outputs");
+    fd_pipeline_opts o;
+    if (opts) o = *opts;
+    else FD_TRY(fd_pipeline_opts_default(&o));
+    const bool select = o.select != 0, demand = o.upload == FD_UPLOAD_ON_DEMAND;
+    FD_REQUIRE(!select || out->cap_rows >= B, "fd_pipeline_host: select mode writes one crop per image (cap_rows >= B)");
     const DecodeCfg &d = ctx->dcfg;
+    const int cw = ctx->cfg.crop_w, ch = ctx->cfg.crop_h;
     int64_t h2d = 0, d2h = 0;
-    // 1. frames H2D into one device arena (16-byte aligned rows)
-    std::vector<size_t> offs(B);
-    std::vector<int> dpitch(B);
+    // 1. frames H2D into one device arena (16-byte aligned rows).  FD_UPLOAD_ON_DEMAND: only the rows the letterbox resize
+    //    reads now; the pixels the warps read follow after detection (step 4).
+    std::vector<HostFrame> hf(B);
     size_t arena = 0;
     for (int i = 0; i < B; ++i) {
         FD_REQUIRE(frames[i].data && frames[i].height > 0 && frames[i].width > 0 && frames[i].pitch >= frames[i].width * 3,
                    "fd_pipeline_host: bad frame");
-        dpitch[i] = (frames[i].width * 3 + 15) & ~15;
-        offs[i] = arena;
-        arena += ((size_t)dpitch[i] * frames[i].height + 255) & ~(size_t)255;
+        hf[i].dpitch = (frames[i].width * 3 + 15) & ~15;
+        hf[i].off = arena;
+        hf[i].full = false;
+        arena += ((size_t)hf[i].dpitch * frames[i].height + 255) & ~(size_t)255;
     }
-    FD_TRY(ctx->pipe_frames.reserve(arena));
+    FD_TRY(ctx->pipe_frames.reserve(arena + 256));
     std::vector<fd_frame> dframes(B);
+    std::vector<float> ds(B);
     for (int i = 0; i < B; ++i) {
-        uint8_t *dst = ctx->pipe_frames.as<uint8_t>() + offs[i];
-        if (frames[i].pitch == dpitch[i])
-            FD_CUDA(cudaMemcpyAsync(dst, frames[i].data, (size_t)dpitch[i] * frames[i].height, cudaMemcpyHostToDevice, ctx->stream));
-        else
-            FD_CUDA(cudaMemcpy2DAsync(dst, dpitch[i], frames[i].data, frames[i].pitch, (size_t)frames[i].width * 3, frames[i].height,
-                                      cudaMemcpyHostToDevice, ctx->stream));
-        h2d += (int64_t)frames[i].width * 3 * frames[i].height;
-        dframes[i] = fd_frame{dst, frames[i].height, frames[i].width, dpitch[i]};
+        uint8_t *dst = ctx->pipe_frames.as<uint8_t>() + hf[i].off;
+        dframes[i] = fd_frame{dst, frames[i].height, frames[i].width, hf[i].dpitch};
+        FrameDev geo;
+        FD_TRY(fill_frame(ctx, dframes[i], dst, &geo, &ds[i]));
+        if (out->det_scale) out->det_scale[i] = ds[i];
+        bool sparse = false;
+        if (demand) FD_TRY(upload_preprocess_rows(ctx, frames[i], geo.new_h, geo.scale_y, dst, hf[i].dpitch, &h2d, &hf[i], &sparse));
+        if (!sparse) {
+            FD_TRY(upload_full(ctx, frames[i], dst, hf[i].dpitch, &h2d));
+            hf[i].full = true;
+        }
     }
     // 2. preprocess -> CNN input tensor (stays on the device unless out->tensor is given)
     const size_t tn = (size_t)B * 3 * ctx->cfg.image_h * ctx->cfg.image_w;
     FD_TRY(ctx->pipe_tensor.reserve(sizeof(float) * tn));
-    FD_TRY(fd_preprocess_batch(ctx, dframes.data(), B, ctx->pipe_tensor.as<float>(), out->det_scale));
+    FD_TRY(fd_preprocess_batch(ctx, dframes.data(), B, ctx->pipe_tensor.as<float>(), nullptr));
     // 3. heads H2D (the CNN outputs), decode + NMS
     const float *dev_heads[3 * FD_MAX_STRIDES];
     for (int s = 0; s < d.n_strides; ++s) {
         const int hw = d.fh[s] * d.fw[s];
-        const int ch[3] = {2 * d.A, 4 * d.A, 10 * d.A};
+        const int chn[3] = {2 * d.A, 4 * d.A, 10 * d.A};
         for (int k = 0; k < 3; ++k) {
-            const size_t bytes = sizeof(float) * (size_t)B * ch[k] * hw;
+            const size_t bytes = sizeof(float) * (size_t)B * chn[k] * hw;
             FD_TRY(ctx->pipe_heads[3 * s + k].reserve(bytes));
             if (k == 0) {   // scores: only the A foreground channels of each image are ever read (face_detection.rs:322)
-                const size_t img = sizeof(float) * (size_t)ch[0] * hw, fg = img / 2;
+                const size_t img = sizeof(float) * (size_t)chn[0] * hw, fg = img / 2;
                 FD_CUDA(cudaMemcpy2DAsync(ctx->pipe_heads[3 * s].as<unsigned char>() + fg, img,
                                           reinterpret_cast<const unsigned char *>(heads_host[3 * s]) + fg, img, fg, (size_t)B,
                                           cudaMemcpyHostToDevice, ctx->stream));
@@ -602,24 +767,110 @@ FD_EXPORT int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const
             dev_heads[3 * s + k] = ctx->pipe_heads[3 * s + k].as<float>();
         }
     }
-    std::vector<float> ds(B);
-    for (int i = 0; i < B; ++i) {
-        int nw, nh;
-        letterbox(frames[i].height, frames[i].width, ctx->cfg.image_w, ctx->cfg.image_h, &nw, &nh, &ds[i]);
-        if (out->det_scale) out->det_scale[i] = ds[i];
-    }
     FD_TRY(detect_enqueue(ctx, dev_heads, B, ds.data(), conf_thr, iou_thr));
-    // 4. align every detection on the device
-    const size_t crop_bytes = (size_t)ctx->cfg.crop_w * ctx->cfg.crop_h * 3;
+    const size_t crop_bytes = (size_t)cw * ch * 3;
     FD_TRY(ctx->pipe_crops.reserve(crop_bytes * (size_t)out->cap_rows));
-    FD_TRY(fd_align_detections(ctx, dframes.data(), B, ctx->pipe_crops.as<uint8_t>(), out->cap_rows, nullptr, nullptr));
+    FD_TRY(ctx->pipe_mode.reserve((size_t)out->cap_rows));
+    uint8_t *crops_dev = ctx->pipe_crops.as<uint8_t>(), *mode_dev = ctx->pipe_mode.as<uint8_t>();
+    int total = 0, n_crops = 0;
+    if (!demand && !select) {
+        // 4a. whole frames are on the device: align every detection without a host round trip, then fetch
+        FD_TRY(fd_align_detections(ctx, dframes.data(), B, crops_dev, out->cap_rows, nullptr, mode_dev));
+        FD_TRY(fd_detect_fetch(ctx, out->counts, out->det, out->landmarks, out->cap_rows, &total));
+        n_crops = total;
+    } else {
+        // 4b. fetch the detections first (the reference has a host round trip here too: gRPC response, face_detection.rs:279,
+        //     then FaceSelection / FaceAlignment on the host, face_pipeline/pipeline.rs:208-216)
+        FD_TRY(fd_detect_fetch(ctx, out->counts, out->det, out->landmarks, out->cap_rows, &total));
+        const FrameDev *frames_dev = ctx->frames_dev.as<FrameDev>();
+        const int F = select ? B : total;
+        n_crops = F;
+        WarpFallback fb = detect_fallback(ctx);
+        const int32_t *fidx_dev = ctx->out_frame_idx.as<int32_t>();
+        if (select) {   // FaceSelection::call per image on the device, then the estimate of the B selected faces
+            FD_TRY(fd_select_detections(ctx, dframes.data(), B, o.is_enroll, &o.select_params, nullptr));
+            fb.sel = ctx->select_sel.as<int>();
+            fidx_dev = ctx->select_fidx.as<int32_t>();
+            ctx->est_valid = false;
+        }
+        if (F > 0) {
+            if (select || !ctx->est_valid || F > ctx->est_cap) {
+                ctx->est_valid = false;
+                FD_TRY(ctx->align_M.reserve(sizeof(double) * 12 * (size_t)F));
+                FD_TRY(ctx->align_ok.reserve((size_t)F));
+                FD_TRY(estimate_launch(ctx, select ? ctx->select_lmk.as<float>() : ctx->out_lmk.as<float>(), nullptr, nullptr, F,
+                                       ctx->align_M.as<double>(), nullptr, ctx->align_ok.as<uint8_t>(), nullptr));
+            }
+            if (demand) {
+                // the transforms come back (96 B per face); the host turns them into the pixel rectangles the warps read
+                std::vector<double> M12((size_t)F * 12);
+                std::vector<uint8_t> okh(F);
+                std::vector<int> selh(select ? 2 * (size_t)B : 0);
+                FD_CUDA(cudaMemcpyAsync(M12.data(), ctx->align_M.p, sizeof(double) * 12 * (size_t)F, cudaMemcpyDeviceToHost, ctx->stream));
+                FD_CUDA(cudaMemcpyAsync(okh.data(), ctx->align_ok.p, (size_t)F, cudaMemcpyDeviceToHost, ctx->stream));
+                if (select) FD_CUDA(cudaMemcpyAsync(selh.data(), ctx->select_sel.p, sizeof(int) * 2 * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+                FD_CUDA(cudaStreamSynchronize(ctx->stream));
+                d2h += (int64_t)F * 97 + (int64_t)selh.size() * 4;
+                struct Rect { int x0, y0, x1, y1; };
+                std::vector<std::vector<Rect>> rects(B);
+                std::vector<int64_t> rect_bytes(B, 0);
+                int f = 0;
+                for (int b = 0; b < B; ++b) {
+                    const int nf = select ? 1 : out->counts[b];
+                    for (int j = 0; j < nf; ++j, ++f) {
+                        if (hf[b].full) continue;
+                        if (select && (selh[2 * b] < 0 || selh[2 * b + 1] < 0)) continue;   // nothing to align: zero crop
+                        Rect r;
+                        if (!okh[f]) {   // bbox-crop fallback reads (x0,y0)..(W,H): rare, take the whole frame
+                            rect_bytes[b] = INT64_MAX / 4;
+                            continue;
+                        }
+                        if (!warp_source_rect(&M12[(size_t)f * 12 + 6], cw, ch, frames[b].width, frames[b].height, &r.x0, &r.y0, &r.x1, &r.y1))
+                            continue;
+                        rects[b].push_back(r);
+                        rect_bytes[b] += (int64_t)(r.x1 - r.x0 + 1) * 3 * (r.y1 - r.y0 + 1);
+                    }
+                }
+                for (int b = 0; b < B; ++b) {
+                    if (hf[b].full || rect_bytes[b] == 0) continue;
+                    uint8_t *dst = ctx->pipe_frames.as<uint8_t>() + hf[b].off;
+                    const int64_t frame_bytes = (int64_t)frames[b].width * 3 * frames[b].height;
+                    const int64_t sent = (int64_t)frames[b].width * 3 * hf[b].n * (hf[b].two ? 2 : 1);
+                    if (rect_bytes[b] >= frame_bytes - sent) {   // many overlapping faces: the rest of the frame is cheaper
+                        FD_TRY(upload_complement_rows(ctx, frames[b], hf[b], dst, &h2d));
+                        hf[b].full = true;
+                        continue;
+                    }
+                    for (const Rect &r : rects[b]) {
+                        const size_t wbytes = (size_t)(r.x1 - r.x0 + 1) * 3, rows = (size_t)(r.y1 - r.y0 + 1);
+                        FD_CUDA(cudaMemcpy2DAsync(dst + (size_t)r.y0 * hf[b].dpitch + (size_t)r.x0 * 3, hf[b].dpitch,
+                                                  frames[b].data + (size_t)r.y0 * frames[b].pitch + (size_t)r.x0 * 3, frames[b].pitch, wbytes, rows,
+                                                  cudaMemcpyHostToDevice, ctx->stream));
+                        h2d += (int64_t)(wbytes * rows);
+                    }
+                }
+            }
+            FD_TRY(upload_frame_table(ctx, dframes.data(), B, nullptr, nullptr));
+            fb.mode_out = mode_dev;
+            FD_TRY(warp_launch(ctx, frames_dev, fidx_dev, ctx->align_M.as<double>(), ctx->align_ok.as<uint8_t>(), nullptr,
+                               std::min(F, (int)out->cap_rows), crops_dev, cw, ch, fb));
+            ctx->align_replay = false;
+        }
+        if (select && out->sel) {
+            FD_CUDA(cudaMemcpyAsync(out->sel, ctx->select_sel.p, sizeof(int) * 2 * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+            d2h += (int64_t)sizeof(int) * 2 * B;
+        }
+    }
     // 5. results D2H
-    int total = 0;
-    FD_TRY(fd_detect_fetch(ctx, out->counts, out->det, out->landmarks, out->cap_rows, &total));
     out->total = total;
+    out->n_crops = n_crops;
     d2h += (int64_t)sizeof(int) * (B + 1) + (int64_t)total * 15 * sizeof(float);
-    if (total) FD_CUDA(cudaMemcpyAsync(out->crops, ctx->pipe_crops.p, crop_bytes * (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
-    d2h += (int64_t)crop_bytes * total;
+    if (n_crops) FD_CUDA(cudaMemcpyAsync(out->crops, crops_dev, crop_bytes * (size_t)n_crops, cudaMemcpyDeviceToHost, ctx->stream));
+    d2h += (int64_t)crop_bytes * n_crops;
+    if (out->align_mode && n_crops) {
+        FD_CUDA(cudaMemcpyAsync(out->align_mode, mode_dev, (size_t)n_crops, cudaMemcpyDeviceToHost, ctx->stream));
+        d2h += n_crops;
+    }
     if (out->tensor) {
         FD_CUDA(cudaMemcpyAsync(out->tensor, ctx->pipe_tensor.p, sizeof(float) * tn, cudaMemcpyDeviceToHost, ctx->stream));
         d2h += (int64_t)sizeof(float) * tn;

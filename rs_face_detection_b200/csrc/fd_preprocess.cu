@@ -13,6 +13,7 @@
 // entry instead of per pixel).
 #include <algorithm>
 #include "fd_internal.cuh"
+#include "fd_resize.cuh"
 
 namespace fd {
 
@@ -40,44 +41,6 @@ __device__ __forceinline__ const uint8_t *stage_row(uint8_t *buf, const uint8_t 
     const int done = head + (nvec << 4);
     for (int i = done + threadIdx.x; i < nbytes; i += blockDim.x) dst[i] = __ldg(src + i);
     return dst;
-}
-
-// horizontal + vertical fixed-point taps for one channel
-__device__ __forceinline__ int resize_px(const uint8_t *r0, const uint8_t *r1, int x0, int x1, int a0, int a1, int b0, int b1) {
-    int t0 = r0[x0] * a0 + r0[x1] * a1;
-    int v = (b0 * (t0 >> 4)) >> 16;
-    if (b1 != 0) {
-        int t1 = r1[x0] * a0 + r1[x1] * a1;
-        v += (b1 * (t1 >> 4)) >> 16;
-    }
-    return (v + 2) >> 2;
-}
-
-__device__ __forceinline__ short sat_short_rn(float v) {
-    int r = __float2int_rn(v);  // round-half-even, as cvRound
-    return (short)max(-32768, min(32767, r));
-}
-
-// x tap table for one destination column (cv::resize, INTER_LINEAR): byte offsets of the two taps and their weights
-__device__ __forceinline__ void x_taps(int dx, double scale_x, int sw, int *o0, int *o1, short *a0, short *a1) {
-    float fx = (float)(((double)dx + 0.5) * scale_x - 0.5);
-    int sx = (int)floorf(fx);
-    fx = __fsub_rn(fx, (float)sx);
-    if (sx < 0) { fx = 0.0f; sx = 0; }
-    if (sx >= sw - 1) { fx = 0.0f; sx = sw - 1; }
-    *o0 = sx * 3;
-    *o1 = min(sx + 1, sw - 1) * 3;
-    *a0 = sat_short_rn(__fmul_rn(__fsub_rn(1.0f, fx), 2048.0f));
-    *a1 = sat_short_rn(__fmul_rn(fx, 2048.0f));
-}
-__device__ __forceinline__ void y_taps(int dy, double scale_y, int sh, int *y0, int *y1, int *b0, int *b1) {
-    float fy = (float)(((double)dy + 0.5) * scale_y - 0.5);
-    int sy = (int)floorf(fy);
-    fy = __fsub_rn(fy, (float)sy);
-    *b0 = sat_short_rn(__fmul_rn(__fsub_rn(1.0f, fy), 2048.0f));
-    *b1 = sat_short_rn(__fmul_rn(fy, 2048.0f));
-    *y0 = min(max(sy, 0), sh - 1);
-    *y1 = min(max(sy + 1, 0), sh - 1);
 }
 
 __global__ void preprocess_kernel(PreArgs a) {

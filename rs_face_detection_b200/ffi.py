@@ -55,10 +55,22 @@ class FdDetView(C.Structure):
                 ("landmarks_dev", C.c_void_p), ("frame_idx_dev", C.c_void_p), ("candidates_dev", C.c_void_p)]
 
 
+class FdSelectParams(C.Structure):
+    _fields_ = [("margin_center_left_ratio", C.c_float), ("margin_center_right_ratio", C.c_float),
+                ("margin_edge_ratio", C.c_float), ("minimum_face_ratio", C.c_float)]
+
+
 class FdHostBatchOut(C.Structure):
     _fields_ = [("counts", c_i32p), ("det", c_f32p), ("landmarks", c_f32p), ("crops", c_u8p), ("det_scale", c_f32p),
-                ("tensor", c_f32p), ("cap_rows", C.c_int32), ("total", C.c_int32), ("h2d_bytes", C.c_int64),
-                ("d2h_bytes", C.c_int64)]
+                ("tensor", c_f32p), ("align_mode", c_u8p), ("sel", c_i32p), ("cap_rows", C.c_int32), ("total", C.c_int32),
+                ("n_crops", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+
+FD_UPLOAD_FULL, FD_UPLOAD_ON_DEMAND = 0, 1
+
+
+class FdPipelineOpts(C.Structure):
+    _fields_ = [("select", C.c_int32), ("is_enroll", C.c_int32), ("upload", C.c_int32), ("select_params", FdSelectParams)]
 
 
 # every symbol include/fd_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
@@ -75,7 +87,7 @@ SYMBOLS = [
     "fd_detect", "fd_estimate_affine_partial_2d", "fd_warp_affine", "fd_align",
     "fd_nms_device", "fd_preprocess_batch", "fd_detect_batch", "fd_detect_fetch", "fd_detect_view", "fd_align_batch",
     "fd_align_detections", "fd_crops_to_tensor", "fd_model_preprocess", "fd_detect_batch_raw", "fd_select_params_default", "fd_face_selection",
-    "fd_select_detections", "fd_align_selected", "fd_pipeline_host", "fd_pipeline_tensor_dev",
+    "fd_select_detections", "fd_align_selected", "fd_pipeline_opts_default", "fd_pipeline_host", "fd_pipeline_tensor_dev",
 ]
 
 _lib = None
@@ -423,14 +435,21 @@ class Context:
                                      _ptr(out, c_u8p), dh, dw))
         return out
 
-    def align(self, img, landmarks):
+    def align(self, img, landmarks, bbox=None, with_mode=False):
+        """FaceAlignment::call: -> (crop, M) or, with_mode, (crop, M, mode): mode 1 = similarity warp, 2 = bbox-crop
+        fallback (face_alignment.rs:64-116; M is None then).  Raises FdError where the reference returns Err."""
         img = np.ascontiguousarray(img, np.uint8)
-        lmk = _f32(landmarks).reshape(10)
+        lmk = _f32(landmarks).reshape(10) if landmarks is not None else None
+        bb = _f32(bbox).reshape(-1)[:4].copy() if bbox is not None else None
         out = np.empty((self.cfg.crop_h, self.cfg.crop_w, 3), np.uint8)
         M = np.empty((2, 3), np.float64)
-        _chk(self.lib.fd_align(self.handle, _ptr(img, c_u8p), img.shape[0], img.shape[1], img.strides[0], _ptr(lmk, c_f32p),
-                               _ptr(out, c_u8p), _ptr(M, c_f64p)))
-        return out, M
+        mode = C.c_int(0)
+        _chk(self.lib.fd_align(self.handle, _ptr(img, c_u8p), img.shape[0], img.shape[1], img.strides[0],
+                               _ptr(bb, c_f32p) if bb is not None else None, _ptr(lmk, c_f32p) if lmk is not None else None,
+                               _ptr(out, c_u8p), _ptr(M, c_f64p), C.byref(mode)))
+        if mode.value != 1:
+            M = None
+        return (out, M, mode.value) if with_mode else (out, M)
 
     # ---- batched, device-resident
     @staticmethod
@@ -486,11 +505,11 @@ class Context:
         _chk(self.lib.fd_detect_view(self.handle, C.byref(v)))
         return v
 
-    def align_batch(self, frames, landmarks_dev, frame_idx_dev, F, crops_dev, M_dev=None, ok_dev=None):
+    def align_batch(self, frames, landmarks_dev, frame_idx_dev, F, crops_dev, M_dev=None, ok_dev=None, bbox_dev=None):
         arr = self._frames(frames)
         _chk(self.lib.fd_align_batch(self.handle, arr, len(frames), C.c_void_p(_devptr(landmarks_dev)),
-                                     C.c_void_p(_devptr(frame_idx_dev)), F, C.c_void_p(_devptr(crops_dev)),
-                                     C.c_void_p(_devptr(M_dev)), C.c_void_p(_devptr(ok_dev))))
+                                     C.c_void_p(_devptr(frame_idx_dev)), C.c_void_p(_devptr(bbox_dev)), F,
+                                     C.c_void_p(_devptr(crops_dev)), C.c_void_p(_devptr(M_dev)), C.c_void_p(_devptr(ok_dev))))
 
     def align_detections(self, frames, crops_dev, cap_faces, M_dev=None, ok_dev=None):
         arr = self._frames(frames)
@@ -544,8 +563,12 @@ class Context:
                                           _ptr(mean, c_f32p), _ptr(mul, c_f32p), _ptr(out, c_f32p)))
         return out
 
-    def pipeline_host(self, frames_host, heads_host, cap_rows, conf_thr=None, iou_thr=None, want_tensor=False, bufs=None):
-        """frames_host: list of HxWx3 u8 arrays (host, ideally pinned); heads_host: 9 host arrays (B,C,H,W)."""
+    def pipeline_host(self, frames_host, heads_host, cap_rows, conf_thr=None, iou_thr=None, want_tensor=False, bufs=None,
+                      select=False, is_enroll=False, upload=FD_UPLOAD_FULL, select_params=None):
+        """frames_host: list of HxWx3 u8 arrays (host, ideally pinned); heads_host: 9 host arrays (B,C,H,W).
+        select: FacePipeline::extract's flow (one selected face per image is aligned; crop b belongs to image b).
+        upload: FD_UPLOAD_FULL | FD_UPLOAD_ON_DEMAND.  -> (bufs, total detections, h2d bytes, d2h bytes); bufs also
+        holds "n_crops"."""
         B = len(frames_host)
         arr = (FdFrame * B)()
         for i, f in enumerate(frames_host):
@@ -555,14 +578,23 @@ class Context:
             bufs = dict(counts=np.empty(B, np.int32), det=np.empty((cap_rows, 5), np.float32),
                         lmk=np.empty((cap_rows, 10), np.float32),
                         crops=np.empty((cap_rows, self.cfg.crop_h, self.cfg.crop_w, 3), np.uint8),
-                        det_scale=np.empty(B, np.float32),
+                        det_scale=np.empty(B, np.float32), align_mode=np.zeros(cap_rows, np.uint8),
+                        sel=np.full((B, 2), -1, np.int32),
                         tensor=np.empty((B, 3, self.cfg.image_h, self.cfg.image_w), np.float32) if want_tensor else None)
         out = FdHostBatchOut()
         out.counts, out.det, out.landmarks = _ptr(bufs["counts"], c_i32p), _ptr(bufs["det"], c_f32p), _ptr(bufs["lmk"], c_f32p)
         out.crops, out.det_scale = _ptr(bufs["crops"], c_u8p), _ptr(bufs["det_scale"], c_f32p)
         out.tensor = _ptr(bufs["tensor"], c_f32p) if bufs.get("tensor") is not None else None
+        out.align_mode = _ptr(bufs["align_mode"], c_u8p) if bufs.get("align_mode") is not None else None
+        out.sel = _ptr(bufs["sel"], c_i32p) if bufs.get("sel") is not None else None
         out.cap_rows = cap_rows
+        opts = FdPipelineOpts()
+        _chk(self.lib.fd_pipeline_opts_default(C.byref(opts)))
+        opts.select, opts.is_enroll, opts.upload = int(bool(select)), int(bool(is_enroll)), int(upload)
+        if select_params is not None:
+            opts.select_params = FdSelectParams(*select_params)
         _chk(self.lib.fd_pipeline_host(self.handle, arr, B, hp, len(heads_host),
                                        C.c_float(self.cfg.conf_thr if conf_thr is None else conf_thr),
-                                       C.c_float(self.cfg.iou_thr if iou_thr is None else iou_thr), C.byref(out)))
+                                       C.c_float(self.cfg.iou_thr if iou_thr is None else iou_thr), C.byref(opts), C.byref(out)))
+        bufs["n_crops"] = out.n_crops
         return bufs, out.total, out.h2d_bytes, out.d2h_bytes

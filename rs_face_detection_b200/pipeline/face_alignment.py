@@ -1,8 +1,8 @@
 """pipeline::module::face_alignment::FaceAlignment (src/pipeline/module/face_alignment.rs:14-141)."""
 import numpy as np
 
-from .. import Context, FdError
-from ..ffi import FD_ERR_ESTIMATE, default_config
+from .. import Context
+from ..ffi import default_config
 
 
 class FaceAlignment:
@@ -15,9 +15,8 @@ class FaceAlignment:
         self.ctx = ctx or Context(device, cfg)
 
     def call(self, img, bbox=None, landmarks=None):
-        """Main branch (:50-59, :119-126).  Where the reference would take its bbox-crop fallback (:64-116, reachable
-        only when the estimate is empty) this raises FdError(FD_ERR_ESTIMATE): that branch is out of scope."""
-        if landmarks is None:
-            raise FdError(FD_ERR_ESTIMATE, "landmarks=None: the reference's bbox-crop fallback is out of scope")
-        crop, _ = self.ctx.align(img, landmarks)
+        """face_alignment.rs:27-141: the similarity warp (:50-59, :119-126) or, when estimateAffinePartial2D returns an
+        empty matrix, the margin-44 bbox crop + resize (:64-116).  Raises FdError where the reference returns Err
+        (landmarks=None: OpenCV asserts on the empty Mat; fallback ROI outside the image: Mat::roi)."""
+        crop, _ = self.ctx.align(img, landmarks, bbox)
         return crop

@@ -97,13 +97,100 @@ def test_align_batch_c4_shape(ctx, oracle):
     ok = okd.download((F,), np.uint8)
     outside = 0
     for f in range(F):
-        crop, Mo = oracle.align_face(frames[fidx[f]], pts[f])
-        assert bool(ok[f]) == (crop is not None)
-        if crop is not None:
-            np.testing.assert_array_equal(M[f], Mo)
-            np.testing.assert_array_equal(got[f], crop)
-            outside += int((crop == 0).all(-1).mean() > 0.2)
+        crop, Mo, mode = oracle.align_face(frames[fidx[f]], pts[f], with_mode=True)
+        assert int(ok[f]) == mode == 1
+        np.testing.assert_array_equal(M[f], Mo)
+        np.testing.assert_array_equal(got[f], crop)
+        outside += int((crop == 0).all(-1).mean() > 0.2)
     assert outside > 0        # some crops hang off the frame border (BORDER_CONSTANT taps)
+
+
+# ---- FaceAlignment::call's bbox-crop fallback (face_alignment.rs:64-116): taken when the estimate is empty ----------------
+DEGENERATE = np.tile(np.array([[300.0, 200.0]], np.float32), (5, 1))          # five equal points: no 2-point sample is valid
+
+
+def _fallback_cases(h, w):
+    """(bbox, expected mode): 2 = the reference crops (x0,y0)..(W,H) and resizes, 0 = Mat::roi rejects the rectangle -> Err"""
+    return [
+        (None, 2),                                                           # bbox None -> the image inset by 1/16 (:67-72)
+        (np.array([100.5, 60.25, 180.0, 140.0], np.float32), 2),
+        (np.array([10.0, 5.0, 60.0, 70.0, 0.93], np.float32), 2),            # a (5,) detection row: x1-22 and y1-22 clamp to 0
+        (np.array([w - 150.0, 30.0, w - 22.0, 90.0], np.float32), 2),        # x2 + 22 == W exactly: still inside
+        (np.array([w - 150.0, 30.0, w - 21.5, 90.0], np.float32), 0),        # x2 + 22 > W: `max` keeps it, roi is out of range
+        (np.array([50.0, h - 21.0, 120.0, h - 5.0], np.float32), 0),         # det[1] + 22 > H (the :82 quirk uses det[1])
+        (np.array([np.nan, 40.0, np.nan, 90.0], np.float32), 2),             # f32::max drops NaN; `as i32` maps NaN to 0
+        (np.array([w + 40.0, 40.0, w - 100.0, 90.0], np.float32), 0),        # x0 >= W: negative width
+    ]
+
+
+@pytest.mark.parametrize("h,w", [(480, 640), (1080, 1920), (113, 131)])
+def test_align_fallback_single(ctx, oracle, h, w):
+    from rs_face_detection_b200 import FdError
+    from rs_face_detection_b200.ffi import FD_ERR_ESTIMATE
+    img = synth.make_frame(h, w, 3)
+    seen = set()
+    for bbox, mode in _fallback_cases(h, w):
+        ecrop, eM, emode = oracle.align_face(img, DEGENERATE, bbox=bbox, with_mode=True)
+        assert emode == mode or (h, w) == (113, 131)      # the expectations are written for frames wider than the boxes
+        mode = emode
+        seen.add(mode)
+        if mode == 0:
+            with pytest.raises(FdError) as e:
+                ctx.align(img, DEGENERATE, bbox)
+            assert e.value.code == FD_ERR_ESTIMATE
+        else:
+            crop, M, got_mode = ctx.align(img, DEGENERATE, bbox, with_mode=True)
+            assert got_mode == 2 and M is None
+            np.testing.assert_array_equal(crop, ecrop)
+    assert seen == {0, 2}
+
+
+def test_align_none_landmarks_is_an_error_like_the_reference(ctx):
+    """landmarks == None: the reference hands an empty Mat to cv::estimateAffinePartial2D, which asserts -> Err"""
+    from rs_face_detection_b200 import FdError
+    with pytest.raises(FdError):
+        ctx.align(synth.make_frame(100, 100, 1), None, np.array([1, 2, 30, 40], np.float32))
+
+
+@pytest.mark.parametrize("crop", [(112, 112), (96, 128)])
+def test_align_batch_mixed_fallback(oracle, crop):
+    """one batch mixing warps, fallback crops and reference errors, on both warp kernels (112x112 and generic)"""
+    from rs_face_detection_b200 import Context
+    from rs_face_detection_b200.ffi import default_config
+    cfg = default_config()
+    cfg.crop_w, cfg.crop_h = crop
+    c = Context(0, cfg)
+    try:
+        sizes = [(480, 640), (1080, 1920)]
+        frames = [synth.make_frame(h, w, 40 + i) for i, (h, w) in enumerate(sizes)]
+        devs = [c.to_device(f) for f in frames]
+        good = synth.make_landmarks(6, seed=5, frame_hw=(480, 640))
+        lmk, fidx, bbs = [], [], []
+        for b, (h, w) in enumerate(sizes):
+            for bbox, _ in _fallback_cases(h, w)[1:]:
+                lmk.append(DEGENERATE); fidx.append(b); bbs.append(bbox[:4])
+            for t in range(3):
+                lmk.append(good[3 * b + t]); fidx.append(b); bbs.append(np.array([10, 10, 50, 50], np.float32))
+        lmk = np.stack(lmk).reshape(-1, 10).astype(np.float32)
+        fidx = np.array(fidx, np.int32)
+        bbs = np.stack(bbs).astype(np.float32)
+        F = len(lmk)
+        nb = crop[0] * crop[1] * 3
+        crops, okd = c.alloc(F * nb), c.alloc(F)
+        c.align_batch([(d.ptr, f.shape[0], f.shape[1], f.strides[0]) for d, f in zip(devs, frames)], c.to_device(lmk), c.to_device(fidx),
+                      F, crops, None, okd, bbox_dev=c.to_device(bbs))
+        c.synchronize()
+        got = crops.download((F, crop[1], crop[0], 3), np.uint8)
+        mode = okd.download((F,), np.uint8)
+        seen = set()
+        for f in range(F):
+            ecrop, _, emode = oracle.align_face(frames[fidx[f]], lmk[f], bbox=bbs[f], dsize=crop, with_mode=True)
+            assert int(mode[f]) == emode
+            seen.add(emode)
+            np.testing.assert_array_equal(got[f], ecrop if ecrop is not None else np.zeros_like(got[f]))
+        assert seen == {0, 1, 2}
+    finally:
+        c.close()
 
 
 def test_round_trip_property(ctx):

@@ -152,12 +152,21 @@ def test_score_ties_follow_concat_order(ctx, oracle):
     np.testing.assert_allclose(lmk, elmk, rtol=REL, atol=1e-4)
 
 
-def test_nan_score_is_an_error(ctx):
-    from rs_face_detection_b200 import FdError
-    heads, _ = synth.make_heads(1, seed=5, n_faces=2)
-    heads[3][0, 2, 3, 3] = np.nan
-    with pytest.raises(FdError):
-        ctx.detect([h[0] for h in heads], 1.0, 0.7, 0.45)
+def test_nan_score_is_dropped_like_the_reference(ctx, oracle):
+    """face_detection.rs:375 keeps `s >= confidence_threshold`; NaN fails the comparison, so a NaN foreground score is
+    dropped before argsort_descending could ever see it (no panic, no error) — same rows as the oracle."""
+    heads, _ = synth.make_heads(3, seed=5, n_faces=4)
+    heads[3][0, 2, 3, 3] = np.nan          # fg channel of stride 16, image 0
+    heads[0][1, 3, 7, 2] = np.nan          # fg channel of stride 32, image 1
+    heads[6][2, 2, 40, 41] = -np.nan
+    cfg = oracle.make_det_cfg(conf_thr=0.7, iou_thr=0.45)
+    for b in range(3):
+        hb = [h[b] for h in heads]
+        det, lmk = ctx.detect(hb, 1.0, 0.7, 0.45)
+        edet, elmk, _ = oracle.detect_post(cfg, hb, 1.0)
+        assert len(det) == len(edet) > 0
+        np.testing.assert_allclose(det, edet, rtol=REL, atol=1e-4)
+        np.testing.assert_allclose(lmk, elmk, rtol=REL, atol=1e-4)
 
 
 def test_detect_from_raw_output_contents(ctx, oracle):

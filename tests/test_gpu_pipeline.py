@@ -43,6 +43,77 @@ def test_pipeline_host_matches_oracle(ctx, oracle):
     assert mism_crops <= max(2, total // 10)
 
 
+def _check_all_faces(oracle, frames, heads, bufs, total, conf, iou):
+    cfg = oracle.make_det_cfg(conf_thr=conf, iou_thr=iou)
+    off = 0
+    for b in range(len(frames)):
+        tensor, det, lmk, _ = _oracle_frame(oracle, cfg, frames[b], [h[b] for h in heads])
+        n = bufs["counts"][b]
+        assert n == len(det)
+        np.testing.assert_allclose(bufs["det"][off:off + n], det, rtol=REL, atol=1e-3)
+        for i in range(n):
+            crop, _, mode = oracle.align_face(frames[b], bufs["lmk"][off + i], bbox=bufs["det"][off + i], with_mode=True)
+            assert bufs["align_mode"][off + i] == mode
+            np.testing.assert_array_equal(bufs["crops"][off + i], crop if crop is not None else np.zeros((112, 112, 3), np.uint8))
+        off += n
+    assert off == total == bufs["n_crops"]
+
+
+@pytest.mark.parametrize("shapes", [[(1080, 1920)] * 3 + [(2160, 3840)], [(720, 1280), (1080, 1920), (600, 800), (1081, 1923)]])
+def test_pipeline_host_on_demand_upload(ctx, oracle, shapes):
+    """FD_UPLOAD_ON_DEMAND (preprocess rows first, then only the pixels the warps read) gives the same bytes out as whole-frame
+    upload — over exact 3x / 6x decimations (strided row copies), a non-integer scale and an odd pitch (whole-frame path)."""
+    from rs_face_detection_b200.ffi import FD_UPLOAD_ON_DEMAND
+    B = len(shapes)
+    frames = [synth.make_frame(h, w, 2300 + i) for i, (h, w) in enumerate(shapes)]
+    heads, _ = synth.make_heads(B, seed=3100, n_faces=6, content_hw=(360, 640))
+    full, total_f, h2d_f, _ = ctx.pipeline_host(frames, heads, cap_rows=B * 64, conf_thr=0.7, iou_thr=0.4, want_tensor=True)
+    dem, total_d, h2d_d, _ = ctx.pipeline_host(frames, heads, cap_rows=B * 64, conf_thr=0.7, iou_thr=0.4, want_tensor=True,
+                                               upload=FD_UPLOAD_ON_DEMAND)
+    assert total_f == total_d > 0
+    for k in ("counts", "det", "lmk", "tensor", "det_scale"):
+        np.testing.assert_array_equal(full[k], dem[k])
+    np.testing.assert_array_equal(full["crops"][:total_f], dem["crops"][:total_d])
+    np.testing.assert_array_equal(full["align_mode"][:total_f], dem["align_mode"][:total_d])
+    _check_all_faces(oracle, frames, heads, dem, total_d, 0.7, 0.4)
+    assert h2d_d <= h2d_f * 1.02      # never (noticeably) more than whole frames
+
+
+@pytest.mark.parametrize("upload", [0, 1])
+@pytest.mark.parametrize("is_enroll", [False, True])
+def test_pipeline_host_select_flow(ctx, oracle, upload, is_enroll):
+    """FacePipeline::extract's flow (face_pipeline/pipeline.rs:196-232): detect -> FaceSelection::call -> align the ONE selected
+    face.  Crop b belongs to image b; an image without a selection gets a zero crop with mode 0 (the reference returns Err)."""
+    B = 5
+    frames = [synth.make_frame(1080, 1920, 2400 + i) for i in range(B)]
+    heads, _ = synth.make_heads(B, seed=3200, n_faces=5, content_hw=(360, 640))
+    for h in heads[0::3]:
+        h[B - 1, 2:] = 0.0            # last image: no foreground score passes -> no detection -> nothing selected
+    cfg = oracle.make_det_cfg(conf_thr=0.7, iou_thr=0.4)
+    bufs, total, h2d, d2h = ctx.pipeline_host(frames, heads, cap_rows=B * 64, conf_thr=0.7, iou_thr=0.4, select=True, is_enroll=is_enroll,
+                                              upload=upload)
+    assert bufs["n_crops"] == B and bufs["counts"][B - 1] == 0
+    off = 0
+    picked = 0
+    for b in range(B):
+        n = bufs["counts"][b]
+        det, lmk = bufs["det"][off:off + n], bufs["lmk"][off:off + n].reshape(-1, 5, 2)
+        bi, ki = oracle.face_selection((1080, 1920), det, lmk, is_enroll) if n else (-1, -1)
+        want = (off + bi if bi >= 0 else -1, off + ki if ki >= 0 else -1)
+        assert tuple(bufs["sel"][b]) == want
+        if bi >= 0 and ki >= 0:
+            crop, _, mode = oracle.align_face(frames[b], lmk[ki], bbox=det[bi], with_mode=True)
+            picked += 1
+        else:
+            crop, mode = None, 0
+        assert bufs["align_mode"][b] == mode
+        np.testing.assert_array_equal(bufs["crops"][b], crop if crop is not None else np.zeros((112, 112, 3), np.uint8))
+        off += n
+    assert picked >= B - 2
+    if upload:
+        assert h2d < 0.75 * sum(f.nbytes for f in frames)   # preprocess rows + one face rectangle per image
+
+
 def test_device_resident_sequence(ctx, oracle):
     """The benchmarked call sequence: preprocess_batch -> detect_batch -> align_detections, inputs resident in HBM."""
     B = 3

@@ -72,3 +72,48 @@ def test_live_estimate(oracle):
         if Mc is not None:
             np.testing.assert_array_equal(inl.ravel() != 0, mask != 0)
             np.testing.assert_allclose(Mo, Mc, rtol=0, atol=1e-7)
+
+
+@pytest.mark.skipif(cv2 is None, reason="cv2 not importable")
+def test_align_fallback_vs_cv2(oracle):
+    """FaceAlignment::call's empty-transform branch (face_alignment.rs:64-116) restated with numpy f32 + cv2.resize on the
+    ROI, against the oracle: same crops, same Err cases (Mat::roi range check, empty ROI)."""
+    f32 = np.float32
+    rng = np.random.default_rng(8)
+
+    def reference(img, bbox):
+        H, W = img.shape[:2]
+        if bbox is None:
+            d0, d1 = f32(W) * f32(0.0625), f32(H) * f32(0.0625)
+            det = [d0, d1, f32(W) - d0, f32(H) - d1]
+        else:
+            det = [f32(v) for v in bbox[:4]]
+        fmax = lambda a, b: b if np.isnan(a) else (a if np.isnan(b) else max(a, b))            # Rust f32::max
+        as_i32 = lambda v: 0 if np.isnan(v) else int(np.clip(np.trunc(v), -2**31, 2**31 - 1))   # Rust `as i32`
+        bb = [fmax(det[0] - f32(22), f32(0)), fmax(det[1] - f32(22), f32(0)), fmax(det[2] + f32(22), f32(W)), fmax(det[1] + f32(22), f32(H))]
+        x0, y0, x1, y1 = (as_i32(v) for v in bb)
+        wd, ht = x1 - x0, y1 - y0
+        if not (0 <= x0 and 0 <= wd and x0 + wd <= W and 0 <= y0 and 0 <= ht and y0 + ht <= H) or wd == 0 or ht == 0:
+            return None                                                                         # Mat::roi / cv::resize -> Err
+        return cv2.resize(np.ascontiguousarray(img[y0:y0 + ht, x0:x0 + wd]), (112, 112), interpolation=cv2.INTER_LINEAR)
+
+    n_ok = n_err = 0
+    for (h, w) in [(480, 640), (1080, 1920), (113, 131), (112, 134), (60, 45)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        cases = [None, [100.5, 60.25, 180.0, 140.0], [10, 5, 60, 70, 0.9], [w - 150.0, 30, w - 22.0, 90], [w - 150.0, 30, w - 21.5, 90],
+                 [50, h - 21.0, 120, h - 5.0], [np.nan, 40, np.nan, 90], [w + 40.0, 40, w - 100.0, 90], [22.0 + w - 112, 22.0 + h - 112, 5, 5]]
+        for bbox in cases:
+            want = reference(img, bbox)
+            got = oracle.align_fallback(img, None if bbox is None else np.array(bbox, np.float32))
+            assert (want is None) == (got is None), (h, w, bbox)
+            if want is not None:
+                np.testing.assert_array_equal(got, want)
+                n_ok += 1
+            else:
+                n_err += 1
+    assert n_ok >= 15 and n_err >= 8
+    # and the estimate really is empty for the landmark sets the fallback tests use (cv2 returns None)
+    same = np.tile(np.array([[300.0, 200.0]], np.float32), (5, 1))
+    M, _ = cv2.estimateAffinePartial2D(same, oracle.ARCFACE_TEMPLATE, method=cv2.LMEDS, ransacReprojThreshold=3.0, maxIters=2000,
+                                       confidence=0.99, refineIters=10)
+    assert M is None and oracle.estimate_affine_partial_2d(same, oracle.ARCFACE_TEMPLATE)[0] is None
