@@ -6,13 +6,18 @@
 
 A "step" is one pass of the hot path over one batch of 64 synthetic 1920x1080 BGR frames per GPU (BASELINE.json
 configs[1]) with synthetic RetinaFace head tensors of the exact output shapes (no CNN / model server offline):
-fd_preprocess_batch -> fd_detect_batch (decode + sort + NMS + rescale) -> fd_align_detections (every detection).
+fd_preprocess_batch -> fd_detect_batch (decode + sort + NMS + rescale + estimate) -> fd_align_detections (every detection).
 `value` times that with inputs resident in HBM; `e2e` times fd_pipeline_host with pinned HOST buffers (H2D of frames and
-head tensors, D2H of detections, landmarks and crops inside the timed region).
+head tensors, D2H of detections, landmarks and crops inside the timed region).  Before anything is timed, the step's own
+outputs are checked against the CPU oracle (`parity`), and after the timed loop the line reports how many images the detect
+kernel deferred to the host-completed NMS path (`deferred_images`, 0 unless an image has more than 4096 candidates).
+The same line carries BASELINE configs 4 and 5 (`extra_workloads`: batch-256 / ~50 faces per frame, 4K frames) at a
+reduced step count, each with its own parity sample and per-kernel roofline table.
 """
 import argparse
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -22,27 +27,23 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BATCH = 64
-FRAME_H, FRAME_W = 1080, 1920
-FACES_PER_FRAME = 20
 CONF_THR, IOU_THR = 0.7, 0.4
-PRE_BYTES_PER_FRAME = 640 * 360 * 12 + 3 * 640 * 640 * 4      # 2,764,800 in + 4,915,200 out = 7,680,000
-WORKLOAD = "batch-64 1920x1080: preprocess+decode+NMS@0.4+align(112x112), ~%d faces/frame" % FACES_PER_FRAME
+PRE_OUT_BYTES = 3 * 640 * 640 * 4
 
-# BASELINE.json configs: c2 is the one the metric is quoted on (default); c4 / c5 are optional extra workloads
+# BASELINE.json configs: c2 is the one the metric is quoted on (the bench line); c4 / c5 ride along as `extra_workloads`
 WORKLOADS = {
-    "c2": dict(batch=64, h=1080, w=1920, faces=20, name=WORKLOAD),
-    "c4": dict(batch=256, h=1080, w=1920, faces=50,
+    "c2": dict(batch=64, h=1080, w=1920, faces=20, distinct=64,
+               name="batch-64 1920x1080: preprocess+decode+NMS@0.4+align(112x112), ~20 faces/frame"),
+    "c4": dict(batch=256, h=1080, w=1920, faces=50, distinct=32,
                name="batch-256 1920x1080: full detect+align, ~50 faces/frame -> 112x112 ArcFace crops (BASELINE config 4)"),
-    "c5": dict(batch=128, h=2160, w=3840, faces=50,
+    "c5": dict(batch=128, h=2160, w=3840, faces=50, distinct=32,
                name="4K stream: 128 frames of 3840x2160 per GPU per step, image-sharded, ~50 faces/frame (BASELINE config 5)"),
 }
 
 
-def set_workload(key):
-    global BATCH, FRAME_H, FRAME_W, FACES_PER_FRAME, WORKLOAD
-    wl = WORKLOADS[key]
-    BATCH, FRAME_H, FRAME_W, FACES_PER_FRAME, WORKLOAD = wl["batch"], wl["h"], wl["w"], wl["faces"], wl["name"]
+def pre_bytes_per_frame(h, w, new_h=360, new_w=640):
+    """min(H*W*3, new_h*new_w*4 taps*3 B) in + 3*640*640*4 out (1080p and 4K: 2,764,800 + 4,915,200 = 7,680,000)."""
+    return min(h * w * 3, new_h * new_w * 12) + PRE_OUT_BYTES
 
 
 # ---- helpers shared with tests/test_host_logic.py and tests/test_multi_rank_gloo.py ---------------------------------
@@ -51,37 +52,32 @@ def shard_range(n_items, rank, world):
     return (rank * n_items) // world, ((rank + 1) * n_items) // world
 
 
-def dist_max(value):
-    """max over ranks of a python float (gloo or nccl), identity without torch.distributed."""
+def _dist_reduce(value, op_name):
     try:
         import torch
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
             dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
             t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=getattr(dist.ReduceOp, op_name))
             return float(t.item())
     except ImportError:
         pass
     return float(value)
+
+
+def dist_max(value):
+    """max over ranks of a python float (gloo or nccl), identity without torch.distributed."""
+    return _dist_reduce(value, "MAX")
 
 
 def dist_sum(value):
-    try:
-        import torch
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-            t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            return float(t.item())
-    except ImportError:
-        pass
-    return float(value)
+    return _dist_reduce(value, "SUM")
 
 
-def result_line(frames, seconds, n_gpus, steps, warmup, extra):
+def result_line(frames, seconds, n_gpus, steps, warmup, extra, wl="c2"):
     """frames = frames ONE rank processed in the timed region (weak scaling: every rank does the same)."""
+    w = WORKLOADS[wl]
     line = {
         "metric": "frames/s preproc+decode+NMS+align",
         "value": frames * n_gpus / seconds,
@@ -95,10 +91,10 @@ def result_line(frames, seconds, n_gpus, steps, warmup, extra):
         "vs_baseline": None,          # BASELINE.md holds no published number for this metric
         "dtype": "u8/f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": BATCH, "frame": "%dx%d BGR u8" % (FRAME_W, FRAME_H),
+        "config": {"workload": w["name"], "frames_per_gpu_per_step": w["batch"], "frame": "%dx%d BGR u8" % (w["w"], w["h"]),
                    "detector_input": "640x640", "anchors": 16800, "conf_thr": CONF_THR, "iou_thr": IOU_THR,
                    "l2": "inputs larger than L2 (%d MB of frames + %d MB tensor per step vs 126 MB L2)"
-                         % (BATCH * FRAME_H * FRAME_W * 3 // 1000000, BATCH * 3 * 640 * 640 * 4 // 1000000),
+                         % (w["batch"] * w["h"] * w["w"] * 3 // 1000000, w["batch"] * PRE_OUT_BYTES // 1000000),
                    "parallelism": "image-sharded, no collective"},
     }
     line.update(extra)
@@ -196,21 +192,9 @@ class CpuPath:
                                                maxIters=2000, confidence=0.99, refineIters=10)
             if M is not None:
                 cv2.warpAffine(img, M, (112, 112), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+            else:
+                O.align_fallback(img, det[i])                                                    # :64-116
         return len(det)
-
-    def run(self, frames, heads, n_frames, threads):
-        """Processes n_frames (cycling over the given frames) on `threads` host threads; returns seconds."""
-        from concurrent.futures import ThreadPoolExecutor
-        B = len(frames)
-        per_image = [[np.ascontiguousarray(h[b]) for h in heads] for b in range(B)]
-        t0 = time.perf_counter()
-        if threads <= 1:
-            for i in range(n_frames):
-                self.frame(frames[i % B], per_image[i % B])
-        else:
-            with ThreadPoolExecutor(threads) as ex:
-                list(ex.map(lambda i: self.frame(frames[i % B], per_image[i % B]), range(n_frames)))
-        return time.perf_counter() - t0
 
 
 def host_cores():
@@ -220,45 +204,115 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def make_host_inputs(n_frames, seed0=2000):
+def make_host_frames(wl, indices, seed0=2000):
     from rs_face_detection_b200.utils import synth
-    frames = [synth.make_frame(FRAME_H, FRAME_W, seed0 + i) for i in range(n_frames)]
-    heads, _ = synth.make_heads(n_frames, seed=3000, n_faces=FACES_PER_FRAME, content_hw=(360, 640))
-    return frames, heads
+    w = WORKLOADS[wl]
+    return [synth.make_frame(w["h"], w["w"], seed0 + i) for i in indices]
+
+
+def make_host_heads(wl, seed=3000):
+    """Head tensors of the workload's batch: `distinct` different images, tiled to the batch size (host generation time)."""
+    from rs_face_detection_b200.utils import synth
+    w = WORKLOADS[wl]
+    heads, _ = synth.make_heads(w["distinct"], seed=seed, n_faces=w["faces"], content_hw=(360, 640))
+    reps = w["batch"] // w["distinct"]
+    return [np.ascontiguousarray(np.tile(h, (reps, 1, 1, 1))) for h in heads] if reps > 1 else heads
+
+
+# One process per core (SURVEY §8(d), BASELINE.md §3.3): the reference is single-threaded per image, so the all-core number
+# shards the batch's images over worker PROCESSES (fork, before any CUDA initialisation in this process).  Every worker
+# builds its own shard of the step's frames and head tensors, then all of them run one step per barrier release.
+def _ref_worker(wl, rank, nproc, frames_per_step, n_steps, barrier, out_q):
+    cpu = CpuPath()
+    batch = WORKLOADS[wl]["batch"]
+    lo, hi = shard_range(frames_per_step, rank, nproc)
+    idx = [i % batch for i in range(lo, hi)]
+    uniq = sorted(set(idx))
+    frames = dict(zip(uniq, make_host_frames(wl, uniq)))
+    heads = make_host_heads(wl)
+    per_image = {i: [np.ascontiguousarray(h[i]) for h in heads] for i in uniq}
+    del heads
+    faces = 0
+    for _ in range(n_steps):
+        barrier.wait()
+        for i in idx:
+            faces += cpu.frame(frames[i], per_image[i])
+        barrier.wait()
+    out_q.put((rank, faces))
+
+
+def run_cpu_processes(wl, nproc, frames_per_step, warmup, steps):
+    """-> (seconds over `steps` steps, faces per step).  Step time = barrier to barrier in the parent (max over workers)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    barrier = ctx.Barrier(nproc + 1)
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ref_worker, args=(wl, r, nproc, frames_per_step, warmup + steps, barrier, q), daemon=True) for r in range(nproc)]
+    for p in procs:
+        p.start()
+    secs = 0.0
+    for s in range(warmup + steps):
+        barrier.wait()
+        t0 = time.perf_counter()
+        barrier.wait()
+        if s >= warmup:
+            secs += time.perf_counter() - t0
+    faces = sum(q.get()[1] for _ in procs)
+    for p in procs:
+        p.join()
+    return secs, faces // max(warmup + steps, 1)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    wl = args.workload
     cores = host_cores()
-    cpu = CpuPath()
-    sample = 8                                   # distinct synthetic frames cycled through
-    frames, heads = make_host_inputs(sample)
-    per_step = max(cores, 8)                     # frames per step: a bounded sample of the 64-frame batch per core
-    for _ in range(args.warmup):
-        cpu.run(frames, heads, min(per_step, cores), cores)
-    secs = 0.0
-    for _ in range(args.steps):
-        secs += cpu.run(frames, heads, per_step, cores)
+    nproc = max(1, min(cores, args.ref_procs or cores))
+    batch = WORKLOADS[wl]["batch"]
+    rounds = max(1, -(-nproc * 4 // batch))       # keep >= 4 frames per worker per step: 64 frames/step up to 16 cores
+    per_step = batch * rounds
+    warm = max(1, min(args.warmup, 2))
+    secs, faces = run_cpu_processes(wl, nproc, per_step, warm, args.steps)
     n = per_step * args.steps
     v = n / secs
-    line = result_line(frames=n / max(args.gpus, 1), seconds=secs, n_gpus=max(args.gpus, 1), steps=args.steps, warmup=args.warmup, extra={})
+    # single process on a bounded sample, for the parallel efficiency
+    s1, _ = run_cpu_processes(wl, 1, 8, 1, 1)
+    single = 8 / s1
+    cpu = CpuPath()
+    line = result_line(frames=n / max(args.gpus, 1), seconds=secs, n_gpus=max(args.gpus, 1), steps=args.steps, warmup=args.warmup, extra={}, wl=wl)
     line["value"] = v
     line["ms_per_step"] = 1e3 * secs / max(args.steps, 1)
     line["impl"] = "reference"
     line["n_gpus"] = args.gpus
-    line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": cpu.kind,
-                            "sample": "%d frames/step x %d steps on %d threads (%d distinct 1080p frames); %s" % (per_step, args.steps, cores, sample, cpu.desc)}
+    line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": nproc, "kind": cpu.kind,
+                            "single_process_value": single, "parallel_efficiency": v / (single * nproc), "host_cores": cores,
+                            "faces_per_step": faces,
+                            "sample": "%d frames/step (the %d-frame batch x %d) x %d steps, one forked process per core (%d), image-sharded, "
+                                      "step = barrier to barrier; %s" % (per_step, batch, rounds, args.steps, nproc, cpu.desc)}
     line["e2e"] = {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     line["gpu_launches"] = 0
     print(json.dumps(line))
     return 0
 
 
+def cpu_baseline_subprocess(wl, steps=3):
+    """Runs the reference arm in a fresh interpreter (fork-per-core must not happen inside a process that holds a CUDA
+    context) and returns its cpu_baseline object."""
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", "1",
+                          "--workload", wl], env=env, capture_output=True, text=True, timeout=900)
+    for ln in reversed(out.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)["cpu_baseline"]
+    raise RuntimeError("reference arm printed no JSON line: %s" % out.stderr[-400:])
+
+
 def time_reference_cuda_nms(ctx, dets):
     import ctypes as C
-    import subprocess
     path = os.path.join(ROOT, "oracle", "_ref", "libref_gpu_nms.so")
     ref = C.CDLL(path)
     # nms_kernel.cu:91 defines `_nms(.., const float*, ..)` while gpu_nms.hpp:7 declares `float*`: a C++ overload, mangled
@@ -283,6 +337,198 @@ def time_reference_cuda_nms(ctx, dets):
             "nms_100k_ref_cuda_note": "wall time of the host-pointer calls: reference `_nms` (sorted boxes in, keep out) vs fd_nms_sorted, same contract"}
 
 
+# ---- one workload on this rank's GPU ---------------------------------------------------------------------------------------
+class Workload:
+    """Device-resident inputs of one BASELINE config and the three-call step over them."""
+
+    def __init__(self, ctx, wl, rank, local_rank):
+        import torch
+        self.torch, self.ctx, self.wl = torch, ctx, wl
+        w = WORKLOADS[wl]
+        self.B, self.H, self.W, self.faces = w["batch"], w["h"], w["w"], w["faces"]
+        dev = torch.device("cuda", local_rank)
+        g = torch.Generator(device=dev)
+        g.manual_seed(2000 + rank)
+        yy = torch.arange(self.H, device=dev, dtype=torch.float32)[:, None, None]
+        xx = torch.arange(self.W, device=dev, dtype=torch.float32)[None, :, None]
+        cc = torch.arange(3, device=dev, dtype=torch.float32)[None, None, :]
+        base = 127 + 100 * torch.sin(xx / (0.13 * self.W) + cc) * torch.cos(yy / (0.21 * self.H) - cc)
+        self.frames_t = []
+        for _ in range(self.B):
+            noise = torch.randint(0, 256, (self.H, self.W, 3), generator=g, device=dev, dtype=torch.int32).float()
+            self.frames_t.append((0.6 * base + 0.4 * noise).clamp(0, 255).to(torch.uint8).contiguous())
+        del base
+        self.heads_np = make_host_heads(wl, seed=3000 + rank)
+        self.heads_t = [torch.from_numpy(h).to(dev) for h in self.heads_np]
+        self.tensor_t = torch.empty((self.B, 3, 640, 640), dtype=torch.float32, device=dev)
+        self.cap_faces = self.B * max(64, self.faces * 2)
+        self.crops_t = torch.empty((self.cap_faces, 112, 112, 3), dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        self.frames_l = ctx.frame_table([(t.data_ptr(), self.H, self.W, self.W * 3) for t in self.frames_t])   # fd_frame[B], built once
+        self.heads_c = ctx.head_table(self.heads_t)
+        self.pre_bytes = pre_bytes_per_frame(self.H, self.W) * self.B
+
+    def step(self, ctx=None, tensor=None, crops=None):
+        c = ctx or self.ctx
+        ds = c.preprocess_batch(self.frames_l, self.tensor_t if tensor is None else tensor)
+        c.detect_batch(self.heads_c, self.B, ds, CONF_THR, IOU_THR)
+        c.align_detections(self.frames_l, self.crops_t if crops is None else crops, self.cap_faces)
+        return ds
+
+    def parity(self, n_images=4, max_crops=200):
+        """Checks the step's own outputs for the first n_images images against the CPU oracle: CNN input tensor bit-exact, detection
+        rows within 1e-5 relative, aligned crops bit-exact.  Raises on any mismatch (a fast wrong step is not a result)."""
+        from oracle import oracle as O            # checker only, outside every timed region
+        O.build()
+        ctx = self.ctx
+        self.step()
+        counts, det, lmk = ctx.detect_fetch(self.B)
+        ctx.synchronize()
+        cfg = O.make_det_cfg(conf_thr=CONF_THR, iou_thr=IOU_THR)
+        off, n_crops, max_rel = 0, 0, 0.0
+        total = int(counts.sum())
+        crops = self.crops_t[:total].cpu().numpy()
+        for b in range(n_images):
+            frame = self.frames_t[b].cpu().numpy()
+            hb = [h[b] for h in self.heads_np]
+            etensor, edet, elmk, _ = O.pipeline_frame(cfg, frame, hb)
+            got_tensor = self.tensor_t[b].cpu().numpy()
+            if not np.array_equal(got_tensor, etensor[0]):
+                raise AssertionError("bench parity: CNN input tensor of image %d differs from the oracle" % b)
+            n = int(counts[b])
+            if n != len(edet):
+                raise AssertionError("bench parity: image %d has %d detections, oracle %d" % (b, n, len(edet)))
+            if n:
+                d, e = det[off:off + n], edet
+                rel = np.abs(d - e) / np.maximum(np.abs(e), 1.0)
+                max_rel = max(max_rel, float(rel.max()), float((np.abs(lmk[off:off + n].reshape(-1, 5, 2) - elmk) / np.maximum(np.abs(elmk), 1.0)).max()))
+                if max_rel > 1e-5:
+                    raise AssertionError("bench parity: detection rows of image %d off by %.3g relative" % (b, max_rel))
+            for i in range(n):
+                if n_crops >= max_crops:
+                    break
+                crop, _, mode = O.align_face(frame, lmk[off + i], bbox=det[off + i], with_mode=True)
+                want = crop if crop is not None else np.zeros((112, 112, 3), np.uint8)
+                if not np.array_equal(crops[off + i], want):
+                    raise AssertionError("bench parity: crop %d of image %d differs from the oracle" % (i, b))
+                n_crops += 1
+            off += n
+        return {"images": n_images, "detections": off, "crops": n_crops, "tensor": "bit-exact", "crops_result": "bit-exact",
+                "rows_max_rel_err": max_rel, "tolerance": "tensor/crops bit-exact, rows 1e-5 relative (BASELINE north_star)"}, counts
+
+
+def measure(ctx, ext, wk, steps, warmup, world, barrier, sample_every=1, profile_steps=20):
+    """Times `steps` serial steps of workload `wk` with CUDA events on the ctx stream; per-kernel events on every
+    `sample_every`-th step of the timed region.  Returns a dict (rank-local values already max-reduced over ranks)."""
+    import ctypes as C
+    import torch
+    for _ in range(max(warmup, 3)):
+        wk.step()
+    parity, counts = wk.parity(n_images=4)
+    faces_per_step = int(counts.sum())
+    for _ in range(2):
+        wk.step()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = {k: [torch.cuda.Event(enable_timing=True) for _ in range(4)] for k in range(0, steps, sample_every)}
+    barrier()
+    l0 = ctx.launch_count()
+    ev0.record(ext)
+    for k in range(steps):
+        m = marks.get(k)
+        if m:
+            m[0].record(ext)
+        ds = ctx.preprocess_batch(wk.frames_l, wk.tensor_t)
+        if m:
+            m[1].record(ext)
+        ctx.detect_batch(wk.heads_c, wk.B, ds, CONF_THR, IOU_THR)
+        if m:
+            m[2].record(ext)
+        ctx.align_detections(wk.frames_l, wk.crops_t, wk.cap_faces)
+        if m:
+            m[3].record(ext)
+    ev1.record(ext)
+    barrier()
+    launches = ctx.launch_count() - l0
+    stats = ctx.detect_last_stats()           # of the LAST timed step, before anything completes deferred images
+    secs = dist_max(ev0.elapsed_time(ev1) / 1e3)
+    live_us = {name: 1e3 * float(np.mean([m[i].elapsed_time(m[i + 1]) for m in marks.values()]))
+               for i, name in enumerate(("preprocess", "detect", "align"))}
+
+    # ---- per-kernel device times through the ABI's per-launch events (separate untimed loop) + algorithmic bytes (SURVEY 8d):
+    #      preprocess min(H*W*3, 640*360*12) + 4,915,200 B/frame; decode 1,008,000 B/image + 64 B/candidate; warp
+    #      min(source footprint 3*112^2/|det M|, 112*112 px * 4 taps * 3 B) + 37,632 B/face ----
+    peak, _ = measured_peak_gbs()
+    Md, okd = ctx.alloc(wk.cap_faces * 48), ctx.alloc(wk.cap_faces)
+    ctx.align_detections(wk.frames_l, wk.crops_t, wk.cap_faces, Md, okd)
+    ctx.synchronize()
+    Mh = Md.download((wk.cap_faces, 2, 3), np.float64)[:faces_per_step]
+    okh = okd.download((wk.cap_faces,), np.uint8)[:faces_per_step]
+    detM = np.abs(Mh[:, 0, 0] * Mh[:, 1, 1] - Mh[:, 0, 1] * Mh[:, 1, 0])
+    foot = np.where(okh == 1, np.minimum(112 * 112 * 12.0, 3.0 * 112 * 112 / np.maximum(detM, 1e-12)), 0.0)
+    warp_bytes = float(foot.sum() + 37632.0 * faces_per_step)
+    decode_bytes = 1008000.0 * wk.B + 64.0 * float(stats["total_candidates"])
+    ctx.profile(True)
+    for _ in range(profile_steps):
+        wk.step()
+    prof = ctx.profile_fetch()
+    ctx.profile(False)
+    alg = {"preprocess_tma_kernel": wk.pre_bytes, "preprocess_kernel": wk.pre_bytes, "decode_kernel": decode_bytes,
+           "detect_fused_kernel": decode_bytes, "warp_fixed_kernel": warp_bytes, "warp_kernel": warp_bytes}
+    kernels = {}
+    for name, (n, us) in prof.items():
+        ent = {"launches_per_step": n / profile_steps, "us_per_launch": us / max(n, 1)}
+        if name in alg:
+            gbs = alg[name] / (us / max(n, 1) * 1e-6) / 1e9
+            ent.update({"algorithmic_bytes": alg[name], "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak, "bound": "hbm"})
+            if name == "detect_fused_kernel":   # decode + sort + NMS + gather + estimate in one launch
+                ent["bound"] = "latency (sort/NMS dependency chains per image); bytes = the decode stage's algorithmic bytes, for reference"
+        else:
+            ent["bound"] = "latency / SM issue"
+        kernels[name] = ent
+    kernels["_note"] = ("us_per_launch = gap between consecutive per-launch CUDA events on the ctx stream (kernel + launch gap) over %d serial "
+                        "steps; candidates/step=%d, faces/step=%d" % (profile_steps, stats["total_candidates"], faces_per_step))
+    Md.free()
+    okd.free()
+    return dict(secs=secs, launches=launches, stats=stats, live_us=live_us, kernels=kernels, parity=parity, faces_per_step=faces_per_step,
+                alg_bytes={"preprocess": wk.pre_bytes, "detect": decode_bytes, "align": warp_bytes})
+
+
+def roofline_of(res, steps, wl):
+    """The roofline object: the LONGEST kernel of the step, timed live inside the timed region; plus the step-level fraction."""
+    peak, peak_src = measured_peak_gbs()
+    kname = {"preprocess": "preprocess_tma_kernel", "detect": "detect_fused_kernel", "align": "warp_fixed_kernel"}
+    hbm_stages = {k: v for k, v in res["live_us"].items() if k != "detect"}          # the detect kernel is latency-bound, not byte-bound
+    longest = max(hbm_stages, key=hbm_stages.get)
+    us = res["live_us"][longest]
+    achieved = res["alg_bytes"][longest] / (us * 1e-6) / 1e9
+    traffic = None
+    ktraffic = {}
+    tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")   # ncu --set full capture of the c2 workload, per launch
+    if os.path.exists(tp) and wl == "c2":
+        try:
+            ktraffic = json.load(open(tp))
+            traffic = ktraffic.get(kname[longest], {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    for name, ent in res["kernels"].items():
+        if isinstance(ent, dict) and name in ktraffic:
+            ent["traffic"] = ktraffic[name]["dram_bytes_per_launch"]
+    step_us = 1e6 * res["secs"] / steps
+    step_bytes = sum(res["alg_bytes"].values())
+    per_stage = {k: {"kernel": kname[k], "avg_launch_us": res["live_us"][k], "algorithmic_bytes": res["alg_bytes"][k],
+                     "achieved_gbs": res["alg_bytes"][k] / (res["live_us"][k] * 1e-6) / 1e9,
+                     "frac": res["alg_bytes"][k] / (res["live_us"][k] * 1e-6) / 1e9 / peak,
+                     "share_of_step": res["live_us"][k] / step_us} for k in res["live_us"]}
+    return {"bound": "hbm", "kernel": kname[longest], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": res["alg_bytes"][longest], "avg_launch_us": us,
+            "share_of_step": us / step_us,
+            "selection": "longest HBM-bound kernel of the step by its live CUDA-event time inside the timed region (events on the ctx stream around each "
+                         "of the three launches)",
+            "stages": per_stage,
+            "step": {"algorithmic_bytes": step_bytes, "us": step_us, "achieved_gbs": step_bytes / (step_us * 1e-6) / 1e9,
+                     "frac": step_bytes / (step_us * 1e-6) / 1e9 / peak}}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -296,36 +542,12 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from rs_face_detection_b200 import Context
+    from rs_face_detection_b200.ffi import FD_UPLOAD_ON_DEMAND
     from rs_face_detection_b200.utils import synth
 
+    wl = args.workload
     ctx = Context(local_rank)
     ext = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)   # events must be recorded on the launching stream
-    dev = torch.device("cuda", local_rank)
-
-    # ---- synthetic inputs, resident in HBM (frames generated on the device: 398 MB per GPU) ----
-    g = torch.Generator(device=dev)
-    g.manual_seed(2000 + rank)
-    yy = torch.arange(FRAME_H, device=dev, dtype=torch.float32)[:, None, None]
-    xx = torch.arange(FRAME_W, device=dev, dtype=torch.float32)[None, :, None]
-    cc = torch.arange(3, device=dev, dtype=torch.float32)[None, None, :]
-    base = 127 + 100 * torch.sin(xx / (0.13 * FRAME_W) + cc) * torch.cos(yy / (0.21 * FRAME_H) - cc)
-    frames_t = []
-    for i in range(BATCH):
-        noise = torch.randint(0, 256, (FRAME_H, FRAME_W, 3), generator=g, device=dev, dtype=torch.int32).float()
-        frames_t.append((0.6 * base + 0.4 * noise).clamp(0, 255).to(torch.uint8).contiguous())
-    heads_np, _ = synth.make_heads(BATCH, seed=3000 + rank, n_faces=FACES_PER_FRAME, content_hw=(360, 640))
-    heads_t = [torch.from_numpy(h).to(dev) for h in heads_np]
-    tensor_t = torch.empty((BATCH, 3, 640, 640), dtype=torch.float32, device=dev)
-    cap_faces = BATCH * max(64, FACES_PER_FRAME * 2)
-    crops_t = torch.empty((cap_faces, 112, 112, 3), dtype=torch.uint8, device=dev)
-    torch.cuda.synchronize()
-    frames_l = ctx.frame_table([(t.data_ptr(), FRAME_H, FRAME_W, FRAME_W * 3) for t in frames_t])   # fd_frame[B], built once
-    heads_c = ctx.head_table(heads_t)
-
-    def step():
-        ds = ctx.preprocess_batch(frames_l, tensor_t)
-        ctx.detect_batch(heads_c, BATCH, ds, CONF_THR, IOU_THR)
-        ctx.align_detections(frames_l, crops_t, cap_faces)
 
     def barrier():
         ctx.synchronize()
@@ -334,34 +556,16 @@ def run_ours(args):
             dist.barrier()
         ctx.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    counts, det, lmk = ctx.detect_fetch(BATCH)         # also validates (NaN / big-path flags) once, untimed
-    faces_per_step = int(counts.sum())
+    wk = Workload(ctx, wl, rank, local_rank)
+    BATCH, FRAME_H, FRAME_W = wk.B, wk.H, wk.W
+    warmup = max(args.warmup, 3)
 
     # ---- timed region: device-resident ----
     sampler = ClockSampler(local_rank)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pre_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    l0 = ctx.launch_count()
     sampler.start()
-    ev0.record(ext)
-    for k in range(args.steps):
-        timed = k % args.roofline_sample == 0     # the events around the roofline kernel, on every n-th step of the timed region
-        if timed:
-            pre_ev[k][0].record(ext)
-        ds = ctx.preprocess_batch(frames_l, tensor_t)
-        if timed:
-            pre_ev[k][1].record(ext)
-        ctx.detect_batch(heads_c, BATCH, ds, CONF_THR, IOU_THR)
-        ctx.align_detections(frames_l, crops_t, cap_faces)
-    ev1.record(ext)
-    barrier()
+    res = measure(ctx, ext, wk, args.steps, warmup, world, barrier, sample_every=args.roofline_sample)
     clocks = sampler.stop()
-    launches = ctx.launch_count() - l0
-    secs = dist_max(ev0.elapsed_time(ev1) / 1e3)
-    pre_ms = float(np.mean([a.elapsed_time(b) for k, (a, b) in enumerate(pre_ev) if k % args.roofline_sample == 0]))
+    secs, launches = res["secs"], res["launches"]
 
     # ---- two batches in flight: a second context (own stream + workspaces) alternates steps with the first, so the
     #      latency-bound kernels of one batch (per-image NMS CTAs, estimate) overlap the bandwidth-bound ones of the other ----
@@ -371,15 +575,13 @@ def run_ours(args):
         ctx.set_sharing(2)
         ctx2.set_sharing(2)
         ext2 = torch.cuda.ExternalStream(ctx2.stream(), device=local_rank)
-        tensor2_t = torch.empty_like(tensor_t)
-        crops2_t = torch.empty_like(crops_t)
-        lanes = [(ctx, ext, tensor_t, crops_t), (ctx2, ext2, tensor2_t, crops2_t)]
+        tensor2_t = torch.empty_like(wk.tensor_t)
+        crops2_t = torch.empty_like(wk.crops_t)
+        lanes = [(ctx, ext, wk.tensor_t, wk.crops_t), (ctx2, ext2, tensor2_t, crops2_t)]
 
         def lane_step(k):
             c, _, tt, cc = lanes[k & 1]
-            ds_ = c.preprocess_batch(frames_l, tt)
-            c.detect_batch(heads_c, BATCH, ds_, CONF_THR, IOU_THR)
-            c.align_detections(frames_l, cc, cap_faces)
+            wk.step(c, tt, cc)
 
         for k in range(6):
             lane_step(k)
@@ -404,102 +606,40 @@ def run_ours(args):
         pipelined = {"value": BATCH * args.steps * world / span, "unit": "frames/s", "batches_in_flight": 2,
                      "ms_per_step": 1e3 * span / args.steps,
                      "note": "same steps alternated over two fd_ctx (two streams, two workspaces, fd_ctx_set_sharing(2)) on each GPU"}
-
-    # ---- per-stage device times (CUDA events on the launching stream, separate untimed loop) ----
-    def time_stage(fn, n=20):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        fn()
-        ctx.synchronize()
-        a.record(ext)
-        for _ in range(n):
-            fn()
-        b.record(ext)
-        ctx.synchronize()
-        return a.elapsed_time(b) / n * 1e3   # us
-
-    # ---- per-kernel device times (the ABI's per-launch CUDA events on the ctx stream, separate untimed loop) and their
-    #      algorithmic bytes: preprocess 7,680,000 B/frame; decode 1,008,000 B/image + 64 B/candidate;
-    #      warp min(source footprint 3*112^2/|det M|, 112*112 px * 4 taps * 3 B) + 37,632 B/face (the same "footprint or
-    #      taps, whichever is smaller" rule SURVEY 8d applies to the resize: a decimating warp reads 4 taps per output
-    #      pixel, not the whole footprint) ----
-    kernels = None
-    if not args.no_stages:
-        import ctypes as C
-        peak_k, _ = measured_peak_gbs()
-        Md = ctx.alloc(cap_faces * 48)
-        okd = ctx.alloc(cap_faces)
-        ctx.align_detections(frames_l, crops_t, cap_faces, Md, okd)
-        ctx.synchronize()
-        Mh = Md.download((cap_faces, 2, 3), np.float64)[:faces_per_step]
-        okh = okd.download((cap_faces,), np.uint8)[:faces_per_step]
-        detM = np.abs(Mh[:, 0, 0] * Mh[:, 1, 1] - Mh[:, 0, 1] * Mh[:, 1, 0])
-        foot = np.where(okh > 0, np.minimum(112 * 112 * 12.0, 3.0 * 112 * 112 / np.maximum(detM, 1e-12)), 0.0)
-        warp_bytes = float(foot.sum() + 37632.0 * faces_per_step)
-        view = ctx.detect_view()
-        Kc = np.empty(BATCH, np.int32)
-        ctx.lib.fd_memcpy_d2h(ctx.handle, Kc.ctypes.data_as(C.c_void_p), C.c_void_p(view.candidates_dev), C.c_size_t(4 * BATCH))
-        decode_bytes = 1008000.0 * BATCH + 64.0 * float(Kc.sum())
-        nprof = 20
-        ctx.profile(True)
-        for _ in range(nprof):
-            step()
-        prof = ctx.profile_fetch()
-        ctx.profile(False)
-        alg = {"preprocess_tma_kernel": PRE_BYTES_PER_FRAME * BATCH, "preprocess_kernel": PRE_BYTES_PER_FRAME * BATCH,
-               "decode_kernel": decode_bytes, "detect_fused_kernel": decode_bytes, "warp_fixed_kernel": warp_bytes, "warp_kernel": warp_bytes}
-        kernels = {}
-        for name, (n, us) in prof.items():
-            ent = {"launches_per_step": n / nprof, "us_per_launch": us / max(n, 1)}
-            if name in alg:
-                gbs = alg[name] / (us / max(n, 1) * 1e-6) / 1e9
-                ent.update({"algorithmic_bytes": alg[name], "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak_k, "bound": "hbm"})
-                if name == "detect_fused_kernel":   # decode + sort + NMS + gather + estimate in one launch, one SM per image
-                    ent["bound"] = "latency (one CTA per image); bytes = the decode stage's algorithmic bytes, for reference"
-            else:
-                ent["bound"] = "latency / SM issue"
-            kernels[name] = ent
-        kernels["_note"] = ("us_per_launch = gap between consecutive per-launch CUDA events on the ctx stream (kernel + launch gap) over %d serial steps; "
-                            "candidates/step=%d, faces/step=%d" % (nprof, int(Kc.sum()), faces_per_step))
-
-    ds = ctx.preprocess_batch(frames_l, tensor_t)
-    stages = None if args.no_stages else {
-        "preprocess_us": time_stage(lambda: ctx.preprocess_batch(frames_l, tensor_t)),
-        "decode_nms_us": time_stage(lambda: ctx.detect_batch(heads_c, BATCH, ds, CONF_THR, IOU_THR)),
-        "align_us": time_stage(lambda: ctx.align_detections(frames_l, crops_t, cap_faces)),
-        "faces_per_step": faces_per_step,
-    }
+        del tensor2_t, crops2_t
+        ctx2.close()
 
     # ---- end to end through the host-buffer call: pinned host frames + heads in, detections + crops out ----
     e2e = None
+    e2e_variants = {}
     if not args.no_e2e:
         host_frames_t = [torch.empty((FRAME_H, FRAME_W, 3), dtype=torch.uint8).pin_memory() for _ in range(BATCH)]
-        for ht, dt in zip(host_frames_t, frames_t):
+        for ht, dt in zip(host_frames_t, wk.frames_t):
             ht.copy_(dt)
         host_frames = [t.numpy() for t in host_frames_t]
-        host_heads_t = [torch.from_numpy(h).pin_memory() for h in heads_np]
+        host_heads_t = [torch.from_numpy(h).pin_memory() for h in wk.heads_np]
         host_heads = [t.numpy() for t in host_heads_t]
-        cap_rows = BATCH * max(64, FACES_PER_FRAME * 2)
+        cap_rows = wk.cap_faces
         pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
-        bufs = dict(counts=pin((BATCH,), torch.int32), det=pin((cap_rows, 5), torch.float32), lmk=pin((cap_rows, 10), torch.float32),
-                    crops=pin((cap_rows, 112, 112, 3), torch.uint8), det_scale=pin((BATCH,), torch.float32), tensor=None)
+        mkbufs = lambda: dict(counts=pin((BATCH,), torch.int32), det=pin((cap_rows, 5), torch.float32), lmk=pin((cap_rows, 10), torch.float32),
+                              crops=pin((cap_rows, 112, 112, 3), torch.uint8), det_scale=pin((BATCH,), torch.float32),
+                              align_mode=pin((cap_rows,), torch.uint8), sel=pin((BATCH, 2), torch.int32), tensor=None)
         L = max(1, args.e2e_lanes)
         e2e_steps = max(2 * L, min(args.steps, 24)) // L * L
         # L host threads, one fd_ctx each, alternate batches: the H2D of one batch overlaps the compute + D2H of the others
         e2e_ctx = [ctx] + [Context(local_rank) for _ in range(L - 1)]
         for c_ in e2e_ctx:
             c_.set_sharing(L)
-        e2e_bufs = [bufs] + [dict(counts=pin((BATCH,), torch.int32), det=pin((cap_rows, 5), torch.float32), lmk=pin((cap_rows, 10), torch.float32),
-                                  crops=pin((cap_rows, 112, 112, 3), torch.uint8), det_scale=pin((BATCH,), torch.float32), tensor=None)
-                             for _ in range(L - 1)]
-        res = [None] * L
+        e2e_bufs = [mkbufs() for _ in range(L)]
+        res_e = [None] * L
 
-        def e2e_worker(i, n):
+        def e2e_worker(i, n, kw):
             torch.cuda.set_device(local_rank)
             for _ in range(n):
-                res[i] = e2e_ctx[i].pipeline_host(host_frames, host_heads, cap_rows, CONF_THR, IOU_THR, bufs=e2e_bufs[i])
+                res_e[i] = e2e_ctx[i].pipeline_host(host_frames, host_heads, cap_rows, CONF_THR, IOU_THR, bufs=e2e_bufs[i], **kw)
 
-        def e2e_run(n_each):
-            th = [threading.Thread(target=e2e_worker, args=(i, n_each)) for i in range(L)]
+        def e2e_run(n_each, kw):
+            th = [threading.Thread(target=e2e_worker, args=(i, n_each, kw)) for i in range(L)]
             t0 = time.perf_counter()
             for t in th:
                 t.start()
@@ -507,21 +647,43 @@ def run_ours(args):
                 t.join()
             return time.perf_counter() - t0
 
-        e2e_run(2)
-        barrier()
-        e2e_secs = dist_max(e2e_run(e2e_steps // L))
-        _, total, h2d, d2h = res[0]
+        def e2e_leg(kw, n_steps, note):
+            e2e_run(2, kw)
+            barrier()
+            s = dist_max(e2e_run(n_steps // L, kw))
+            _, total, h2d, d2h = res_e[0]
+            return {"value": BATCH * n_steps * world / s, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": n_steps, "ms_per_step": 1e3 * s / n_steps, "batches_in_flight": L, "detections_per_step": int(total),
+                    "crops_per_step": int(e2e_bufs[0]["n_crops"]), "note": note}
+
+        e2e = e2e_leg({}, e2e_steps,
+                      "fd_pipeline_host per batch: pinned host frames+heads -> H2D -> preprocess/decode/NMS/align of EVERY detection -> D2H "
+                      "dets+landmarks+crops; %d host threads / fd_ctx alternate batches; the CNN input tensor stays on the device (Triton "
+                      "CUDA-shm boundary)" % L)
         # strictly serial variant (one context, one batch at a time) for reference
         ctx.set_sharing(1)
         t0 = time.perf_counter()
         for _ in range(4):
-            ctx.pipeline_host(host_frames, host_heads, cap_rows, CONF_THR, IOU_THR, bufs=bufs)
-        serial_secs = (time.perf_counter() - t0) / 4
-        e2e = {"value": BATCH * e2e_steps * world / e2e_secs, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_secs / e2e_steps,
-               "batches_in_flight": L, "serial_ms_per_step": 1e3 * serial_secs,
-               "note": "fd_pipeline_host per batch: pinned host frames+heads -> H2D -> preprocess/decode/NMS/align -> D2H dets+landmarks+crops; "
-                       "%d host threads / fd_ctx alternate batches; the CNN input tensor stays on the device (Triton CUDA-shm boundary)" % L}
+            ctx.pipeline_host(host_frames, host_heads, cap_rows, CONF_THR, IOU_THR, bufs=e2e_bufs[0])
+        e2e["serial_ms_per_step"] = 1e3 * (time.perf_counter() - t0) / 4
+        for c_ in e2e_ctx:
+            c_.set_sharing(L)
+        if not args.no_e2e_variants:
+            short = max(2 * L, min(e2e_steps, 12)) // L * L
+            e2e_variants["on_demand_upload"] = e2e_leg(
+                dict(upload=FD_UPLOAD_ON_DEMAND), short,
+                "same work, FD_UPLOAD_ON_DEMAND: rows the letterbox reads first, then only what the warps read — with ~20 large overlapping faces "
+                "per frame the warps read (almost) every row, so the bytes do not drop for THIS workload")
+            e2e_variants["extract_flow"] = e2e_leg(
+                dict(select=True, upload=FD_UPLOAD_ON_DEMAND), short,
+                "FacePipeline::extract's flow (face_pipeline/pipeline.rs:196-232): detect -> FaceSelection -> align the ONE selected face per frame, "
+                "FD_UPLOAD_ON_DEMAND: preprocess rows + one face rectangle per frame cross PCIe")
+            e2e_variants["extract_flow_full_upload"] = e2e_leg(
+                dict(select=True), short, "the extract flow with whole-frame upload, for the byte comparison")
+        ctx.set_sharing(1)
+        for c_ in e2e_ctx[1:]:
+            c_.close()
+        del host_frames_t, host_heads_t, e2e_bufs
 
     # ---- NMS stress (BASELINE config 3), secondary number ----
     nms_extra = {}
@@ -531,17 +693,30 @@ def run_ours(args):
         d_dev = ctx.to_device(dets)
         keep_dev, num_dev = ctx.alloc(4 * len(dets)), ctx.alloc(16)
         times = []
-        for it in range(13):
+        for it in range(110):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(ext)
             ctx.nms_device(d_dev, len(dets), 0.4, keep_dev, num_dev)
             b.record(ext)
             ctx.synchronize()
-            if it >= 3:
+            if it >= 10:
                 times.append(a.elapsed_time(b) * 1e3)
         assert int(num_dev.download((2,), np.int32)[0]) == len(keep)
-        if times:
-            nms_extra = {"nms_100k_us": float(np.median(times)), "nms_100k_kept": int(len(keep)), "nms_100k_note": "device-resident dets, sort included, IoU 0.4"}
+        from oracle import oracle as O                      # checker / work counter only (never timed)
+        O.build()
+        pairs = int(O.nms_pairs(dets, 0.4))                  # IoU pairs the greedy reference loop evaluates (nms.rs:10-62)
+        med = float(np.median(times))
+        nms_extra = {"nms_100k_us": med, "nms_100k_kept": int(len(keep)), "nms_100k_p10_us": float(np.percentile(times, 10)),
+                     "nms_100k_p90_us": float(np.percentile(times, 90)), "nms_100k_samples": len(times),
+                     "nms_100k_pairs_evaluated": pairs, "nms_100k_gpairs_per_s": pairs / (med * 1e-6) / 1e9,
+                     "nms_100k_note": "device-resident dets, sort included, IoU 0.4; median of %d launches after 10 warm-up; pairs = the IoU "
+                                      "evaluations of the reference's greedy loop (sum over kept boxes of the boxes still alive), the algorithmic "
+                                      "work SURVEY 8(d) names; the spatial path evaluates far fewer" % len(times)}
+        try:
+            st = ctx.nms_last_stats()
+            nms_extra["nms_100k_path"] = {"spatial": int(st[0]), "kept": int(st[1]), "decision_epochs": int(st[2]), "grid": [int(st[3]), int(st[4])]}
+        except Exception:
+            pass
         # the reference's own CUDA NMS (src/nms_kernel.cu, never built by the reference) recompiled for sm_100a from the
         # sources where they lie (oracle/_ref, baseline leg): host boxes in, H2D + N x N/64 mask kernel + D2H of the 1.25 GB
         # mask + CPU sweep inside `_nms`; next to it, this repo's fd_nms_sorted through the same host-pointer contract
@@ -551,56 +726,51 @@ def run_ours(args):
             nms_extra["nms_100k_ref_cuda_us"] = None
             nms_extra["nms_100k_ref_cuda_note"] = "oracle/_ref not available: %s" % (e,)
 
-    # ---- CPU baseline: bounded sample on rank 0 at N=1 ----
+    # ---- BASELINE configs 4 and 5 at a reduced step count, same measurement (frees the main workload's buffers first) ----
+    extra_workloads = {}
+    main_roofline = roofline_of(res, args.steps, wl)
+    if not args.no_extra:
+        del wk
+        torch.cuda.empty_cache()
+        for xwl in [k for k in ("c4", "c5") if k != wl]:
+            xk = Workload(ctx, xwl, rank, local_rank)
+            xsteps = max(4, min(args.steps, 10))
+            xr = measure(ctx, ext, xk, xsteps, 3, world, barrier, sample_every=1, profile_steps=8)
+            rl = roofline_of(xr, xsteps, xwl)
+            extra_workloads[xwl] = {"workload": WORKLOADS[xwl]["name"], "value": xk.B * xsteps * world / xr["secs"], "unit": "frames/s",
+                                    "n_gpus": world, "steps": xsteps, "ms_per_step": 1e3 * xr["secs"] / xsteps, "frames_per_gpu_per_step": xk.B,
+                                    "faces_per_step": xr["faces_per_step"], "crops_per_s": xr["faces_per_step"] * xsteps * world / xr["secs"],
+                                    "parity": xr["parity"], "deferred_images": xr["stats"]["deferred_images"],
+                                    "max_candidates_per_image": xr["stats"]["max_candidates"], "roofline": rl, "kernels": xr["kernels"]}
+            del xk
+            torch.cuda.empty_cache()
+
+    # ---- CPU baseline: the reference arm in a fresh interpreter (one forked process per core), rank 0 at N=1 only ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = host_cores()
-        cpu = CpuPath()
-        nsamp = 8
-        hf = [frames_t[i].cpu().numpy() for i in range(nsamp)]
-        hh = [h[:nsamp] for h in heads_np]
-        cpu.run(hf, hh, min(cores, nsamp), cores)                    # warm-up
-        n = max(nsamp, cores) * 2
-        s = cpu.run(hf, hh, n, cores)
-        while s < 4.0 and n < 100000:                                # ~10-30 s of CPU work in total
-            n *= 2
-            s = cpu.run(hf, hh, n, cores)
-        s1 = cpu.run(hf, hh, nsamp, 1)
-        cpu_baseline = {"value": n / s, "unit": "frames/s", "cores": cores, "kind": cpu.kind,
-                        "single_thread_value": nsamp / s1,
-                        "sample": "%d frames cycling %d of the step's 1080p frames + their head tensors on %d threads; %s" % (n, nsamp, cores, cpu.desc)}
+        cpu_baseline = cpu_baseline_subprocess(wl)
 
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        achieved = PRE_BYTES_PER_FRAME * BATCH / (pre_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")   # ncu --set full capture of this workload (c2), per launch
-        ktraffic = {}
-        if os.path.exists(tp) and args.workload == "c2":
-            try:
-                ktraffic = json.load(open(tp))
-                traffic = ktraffic.get("preprocess_tma_kernel", {}).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        if kernels:
-            for name, ent in kernels.items():
-                if isinstance(ent, dict) and name in ktraffic:
-                    ent["traffic"] = ktraffic[name]["dram_bytes_per_launch"]
         extra = {
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "preprocess_tma_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": PRE_BYTES_PER_FRAME * BATCH, "avg_launch_us": pre_ms * 1e3,
-                         "share_of_step": pre_ms * args.steps / (secs * 1e3)},
+            "roofline": main_roofline,
             "cpu_baseline": cpu_baseline,
-            "stages": stages,
-            "kernels": kernels,
+            "parity": res["parity"],
+            "parity_checked": res["parity"]["images"],
+            "deferred_images": res["stats"]["deferred_images"],
+            "max_candidates_per_image": res["stats"]["max_candidates"],
+            "faces_per_step": res["faces_per_step"],
+            "stages": {"preprocess_us": res["live_us"]["preprocess"], "decode_nms_us": res["live_us"]["detect"], "align_us": res["live_us"]["align"],
+                       "note": "live CUDA-event times inside the timed region"},
+            "kernels": res["kernels"],
             "pipelined": pipelined,
+            "e2e_variants": e2e_variants or None,
+            "extra_workloads": extra_workloads or None,
         }
         extra.update(nms_extra)
-        print(json.dumps(result_line(frames=BATCH * args.steps, seconds=secs, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), extra=extra)))
+        print(json.dumps(result_line(frames=BATCH * args.steps, seconds=secs, n_gpus=world, steps=args.steps, warmup=warmup, extra=extra, wl=wl)))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -615,21 +785,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--roofline-sample", type=int, default=1, help="record the roofline kernel's CUDA events on every n-th timed step")
+    ap.add_argument("--roofline-sample", type=int, default=1, help="record the per-kernel CUDA events on every n-th timed step")
+    ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: worker processes (default: one per host core)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-variants", action="store_true")
     ap.add_argument("--e2e-lanes", type=int, default=3, help="host threads / contexts keeping batches in flight in the e2e leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-nms", action="store_true")
     ap.add_argument("--no-pipelined", action="store_true")
-    ap.add_argument("--no-stages", action="store_true", help="skip the per-stage timing loops (profiling runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip BASELINE configs 4 and 5 (extra_workloads)")
     args = ap.parse_args()
-    set_workload(args.workload)
     if args.impl == "reference":
         return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun, one rank per GPU
-        import subprocess
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
                "--master-port", str(29500 + os.getpid() % 500), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)

@@ -201,6 +201,11 @@ typedef struct fd_det_view {
     const int32_t *candidates_dev; /* (B) pre-NMS candidate counts K */
 } fd_det_view;
 int fd_detect_view(fd_ctx *ctx, fd_det_view *out);
+/* Diagnostics of the last fd_detect_batch, read without completing anything (blocks on the ctx stream): out[8] =
+ * {images the detect kernel deferred to fd_detect_fetch's host-driven NMS path, largest per-image candidate count K,
+ *  total candidates, faces the kernel finished itself, 1 if the single fused kernel ran (0: three-kernel path),
+ *  1 if the launch kept 1024 < K <= 4096 images on the device, 0, 0}.  bench.py reports the first two. */
+int fd_detect_last_stats(fd_ctx *ctx, int32_t *out);
 /* Aligns F faces: landmarks_dev (F,10) in original-frame coordinates, frame_idx_dev (F) into frames, bbox_dev (F,4) or
  * NULL (bbox == None) for the fallback.  crops_dev (F,crop_h,crop_w,3) u8; M_dev (F,6) f64 or NULL; ok_dev (F) u8 or NULL:
  * 1 = similarity warp, 2 = bbox-crop fallback (face_alignment.rs:64-116), 0 = the reference returns Err (crop zero-filled). */

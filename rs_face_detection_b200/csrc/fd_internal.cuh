@@ -124,6 +124,7 @@ struct fd_ctx {
     fd::DevBuf pipe_mode;        // u8[cap_rows] per-crop align mode of the host pipeline
     int last_B = 0;
     int last_out_cap = 0;
+    bool last_fused = false;     // the last fd_detect_batch ran the single fused kernel
     bool detect_pending = false; // results enqueued, NaN check / big-path fix-up not yet done (lazy, at fetch)
     float last_iou = 0.f;
     std::vector<unsigned char> frames_shadow;    // host copy of the descriptor table currently on the device

@@ -177,6 +177,7 @@ static int detect_enqueue(fd_ctx *ctx, const float *const *heads_dev, int B, con
         FD_TRY(finalize_launch(ctx, B));
     }
     ctx->est_valid = fused;
+    ctx->last_fused = fused;
     ctx->last_B = B;
     ctx->last_iou = iou_thr;
     ctx->detect_pending = true;
@@ -246,6 +247,28 @@ FD_EXPORT int fd_detect_view(fd_ctx *ctx, fd_det_view *out) {
     out->landmarks_dev = ctx->out_lmk.as<float>();
     out->frame_idx_dev = ctx->out_frame_idx.as<int32_t>();
     out->candidates_dev = ctx->cand_count.as<int32_t>();
+    return FD_OK;
+}
+
+FD_EXPORT int fd_detect_last_stats(fd_ctx *ctx, int32_t *out) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(out && ctx->last_B > 0, "fd_detect_last_stats: no fd_detect_batch results");
+    const int B = ctx->last_B;
+    int st[4] = {0, 0, 0, 0};
+    std::vector<int> counts(B);
+    FD_CUDA(cudaMemcpyAsync(st, ctx->status(), sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(cudaMemcpyAsync(counts.data(), ctx->cand_count.p, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    long long tot = 0;
+    int mx = 0;
+    for (int c : counts) { tot += c; mx = std::max(mx, c); }
+    memset(out, 0, sizeof(int32_t) * 8);
+    out[0] = ctx->detect_pending ? st[1] : 0;   // once resolved, nothing is pending any more
+    out[1] = mx;
+    out[2] = (int32_t)std::min<long long>(tot, INT_MAX);
+    out[3] = st[2];
+    out[4] = ctx->last_fused ? 1 : 0;
+    out[5] = ctx->crowded ? 1 : 0;
     return FD_OK;
 }
 

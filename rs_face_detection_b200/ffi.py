@@ -85,7 +85,7 @@ SYMBOLS = [
     "fd_bbox_pred", "fd_nonlinear_pred", "fd_landmark_pred", "fd_clip_boxes", "fd_clip_points", "fd_iou_pred",
     "fd_nonlinear_transform", "fd_bbox_overlaps", "fd_letterbox_geometry", "fd_preprocess", "fd_resize_linear",
     "fd_detect", "fd_estimate_affine_partial_2d", "fd_warp_affine", "fd_align",
-    "fd_nms_device", "fd_preprocess_batch", "fd_detect_batch", "fd_detect_fetch", "fd_detect_view", "fd_align_batch",
+    "fd_nms_device", "fd_preprocess_batch", "fd_detect_batch", "fd_detect_fetch", "fd_detect_view", "fd_detect_last_stats", "fd_align_batch",
     "fd_align_detections", "fd_crops_to_tensor", "fd_model_preprocess", "fd_detect_batch_raw", "fd_select_params_default", "fd_face_selection",
     "fd_select_detections", "fd_align_selected", "fd_pipeline_opts_default", "fd_pipeline_host", "fd_pipeline_tensor_dev",
 ]
@@ -504,6 +504,13 @@ class Context:
         v = FdDetView()
         _chk(self.lib.fd_detect_view(self.handle, C.byref(v)))
         return v
+
+    def detect_last_stats(self):
+        """{deferred_images, max_candidates, total_candidates, faces_on_device, fused, crowded} of the last detect_batch"""
+        out = np.zeros(8, np.int32)
+        _chk(self.lib.fd_detect_last_stats(self.handle, _ptr(out, c_i32p)))
+        return dict(deferred_images=int(out[0]), max_candidates=int(out[1]), total_candidates=int(out[2]), faces_on_device=int(out[3]),
+                    fused=bool(out[4]), crowded=bool(out[5]))
 
     def align_batch(self, frames, landmarks_dev, frame_idx_dev, F, crops_dev, M_dev=None, ok_dev=None, bbox_dev=None):
         arr = self._frames(frames)

@@ -116,7 +116,8 @@ def _fallback_cases(h, w):
         (np.array([100.5, 60.25, 180.0, 140.0], np.float32), 2),
         (np.array([10.0, 5.0, 60.0, 70.0, 0.93], np.float32), 2),            # a (5,) detection row: x1-22 and y1-22 clamp to 0
         (np.array([w - 150.0, 30.0, w - 22.0, 90.0], np.float32), 2),        # x2 + 22 == W exactly: still inside
-        (np.array([w - 150.0, 30.0, w - 21.5, 90.0], np.float32), 0),        # x2 + 22 > W: `max` keeps it, roi is out of range
+        (np.array([w - 150.0, 30.0, w - 21.5, 90.0], np.float32), 2),        # x2 + 22 = W + 0.5: `as i32` truncates back to W
+        (np.array([w - 150.0, 30.0, w - 20.0, 90.0], np.float32), 0),        # x2 + 22 > W: `max` keeps it, roi is out of range
         (np.array([50.0, h - 21.0, 120.0, h - 5.0], np.float32), 0),         # det[1] + 22 > H (the :82 quirk uses det[1])
         (np.array([np.nan, 40.0, np.nan, 90.0], np.float32), 2),             # f32::max drops NaN; `as i32` maps NaN to 0
         (np.array([w + 40.0, 40.0, w - 100.0, 90.0], np.float32), 0),        # x0 >= W: negative width

@@ -71,8 +71,10 @@ def test_pipeline_host_on_demand_upload(ctx, oracle, shapes):
     dem, total_d, h2d_d, _ = ctx.pipeline_host(frames, heads, cap_rows=B * 64, conf_thr=0.7, iou_thr=0.4, want_tensor=True,
                                                upload=FD_UPLOAD_ON_DEMAND)
     assert total_f == total_d > 0
-    for k in ("counts", "det", "lmk", "tensor", "det_scale"):
+    for k in ("counts", "tensor", "det_scale"):
         np.testing.assert_array_equal(full[k], dem[k])
+    for k in ("det", "lmk"):
+        np.testing.assert_array_equal(full[k][:total_f], dem[k][:total_d])
     np.testing.assert_array_equal(full["crops"][:total_f], dem["crops"][:total_d])
     np.testing.assert_array_equal(full["align_mode"][:total_f], dem["align_mode"][:total_d])
     _check_all_faces(oracle, frames, heads, dem, total_d, 0.7, 0.4)
@@ -110,8 +112,9 @@ def test_pipeline_host_select_flow(ctx, oracle, upload, is_enroll):
         np.testing.assert_array_equal(bufs["crops"][b], crop if crop is not None else np.zeros((112, 112, 3), np.uint8))
         off += n
     assert picked >= B - 2
-    if upload:
-        assert h2d < 0.75 * sum(f.nbytes for f in frames)   # preprocess rows + one face rectangle per image
+    if upload:   # preprocess rows + one face rectangle per image + heads, against whole frames + heads
+        _, _, h2d_full, _ = ctx.pipeline_host(frames, heads, cap_rows=B * 64, conf_thr=0.7, iou_thr=0.4, select=True, is_enroll=is_enroll)
+        assert h2d < 0.75 * h2d_full
 
 
 def test_device_resident_sequence(ctx, oracle):
