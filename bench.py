@@ -688,6 +688,10 @@ def run_ours(args):
             c_.set_sharing(L)
         if not args.no_e2e_variants:
             short = max(2 * L, min(e2e_steps, 12)) // L * L
+            e2e_variants["heads_zero_copy"] = e2e_leg(
+                dict(heads_zero_copy=True), short,
+                "same work, fd_pipeline_opts.heads_zero_copy: the bbox/landmark head tensors are not copied; the detect kernel reads the passing "
+                "anchors' sectors straight from pinned host memory")
             e2e_variants["on_demand_upload"] = e2e_leg(
                 dict(upload=FD_UPLOAD_ON_DEMAND), short,
                 "same work, FD_UPLOAD_ON_DEMAND: rows the letterbox reads first, then only what the warps read — with ~20 large overlapping faces "

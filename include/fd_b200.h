@@ -282,9 +282,11 @@ typedef struct fd_pipeline_opts {
     int32_t upload;     /* FD_UPLOAD_FULL: every frame crosses PCIe whole.  FD_UPLOAD_ON_DEMAND: first only the source rows the
                            letterbox resize reads (1080p -> 640x360: one row in three), then, once the detections are known, only the
                            pixel rectangles the warps read (or the rest of the frame when that is cheaper).  Same results. */
+    int32_t heads_zero_copy; /* 1: bbox / landmark head tensors in PINNED host memory are not copied; the detect kernel reads the few
+                           sectors it needs (anchors above the threshold) straight from host memory.  Pageable buffers are copied. */
     fd_select_params select_params;
 } fd_pipeline_opts;
-int fd_pipeline_opts_default(fd_pipeline_opts *opts);   /* select 0, FD_UPLOAD_FULL, fd_select_params_default */
+int fd_pipeline_opts_default(fd_pipeline_opts *opts);   /* select 0, FD_UPLOAD_FULL, heads_zero_copy 0, fd_select_params_default */
 /* frames[].data are HOST pointers here (pinned for full PCIe rate); heads_host as in fd_detect_batch but host memory.
  * opts NULL = defaults.  Blocks until the outputs are in host memory. */
 int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const float *const *heads_host, int n_heads,

@@ -12,6 +12,9 @@
 // per-tap BORDER_CONSTANT) so crops are bit-identical, not "within a few grey levels".
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 #include <cfloat>
 #include "fd_internal.cuh"
 #include "fd_estimate.cuh"
@@ -91,7 +94,13 @@ struct WarpArgs {
     int bbox_stride;
     const int *sel;        // optional (F,2) = {bbox row, key-point row} (fd_select_detections); key-point row < 0: landmarks == None
     uint8_t *mode_out;     // optional (F): 1 = similarity warp, 2 = bbox-crop fallback, 0 = the reference returns Err (zero crop)
+    long long *dbg;        // FD_WARP_DBG=1: per-CTA timestamps {entry, first item start, first item end, exit, items, sum of item ns}
 };
+__device__ __forceinline__ long long warp_now() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // Resolves the fallback of face f: returns true and the ROI origin when the reference would crop + resize, false when it
 // returns Err (landmarks == None: cv::estimateAffinePartial2D asserts on the empty Mat; ROI outside the image: Mat::roi).
@@ -389,10 +398,16 @@ __global__ void __launch_bounds__(2 * CW) warp_fixed_kernel(WarpArgs a) {
     const int r = tid / CW, x = tid - r * CW;
     const int F = a.count_dev ? min(*a.count_dev, a.F) : a.F;
     const int n_items = F * ITEMS;
+    long long t_entry = 0, t_prev = 0, t_sum = 0;
+    int n_done = 0;
+    if (a.dbg && tid == 0) t_entry = warp_now();
     if (tid == 0) s_item[0] = atomicAdd(a.ticket, 1);
     __syncthreads();
+    if (a.dbg && tid == 0) { t_prev = warp_now(); a.dbg[blockIdx.x * 8 + 1] = t_prev; }
     for (int par = 0;; par ^= 1) {
         const int item = s_item[par];
+        if (a.dbg && tid == 0 && par == 1 && n_done == 1) a.dbg[blockIdx.x * 8 + 2] = warp_now();
+        if (a.dbg && tid == 0) { const long long t = warp_now(); if (n_done) t_sum += t - t_prev; t_prev = t; ++n_done; }
         if (item >= n_items) break;
         if (tid == 0) s_item[par ^ 1] = atomicAdd(a.ticket, 1);
         const int f = item / ITEMS, y0 = (item - f * ITEMS) * IR;
@@ -462,6 +477,12 @@ __global__ void __launch_bounds__(2 * CW) warp_fixed_kernel(WarpArgs a) {
                 if (store) outw[u * (T * 3 / 4)] = word;
             }
         }
+    }
+    if (a.dbg && tid == 0) {
+        a.dbg[blockIdx.x * 8 + 0] = t_entry;
+        a.dbg[blockIdx.x * 8 + 3] = warp_now();
+        a.dbg[blockIdx.x * 8 + 4] = n_done - 1;
+        a.dbg[blockIdx.x * 8 + 5] = t_sum;
     }
     if (tid == 0) {  // the last CTA to leave re-arms the ticket for the next launch on this ctx
         __threadfence();
@@ -555,6 +576,14 @@ int warp_launch(fd_ctx *ctx, const FrameDev *frames_dev, const int32_t *frame_id
     a.cw_magic = cw > 1 ? (unsigned)((1ull << 32) / (unsigned)cw + 1ull) : 0u;
     FD_TRY(ticket_buffer(ctx));
     a.ticket = ctx->tickets.as<int>();
+    a.dbg = nullptr;
+    static const bool dbg_on = getenv("FD_WARP_DBG") != nullptr;
+    static long long *dbg_dev = nullptr;
+    if (dbg_on) {
+        if (!dbg_dev) FD_CUDA(cudaMalloc(&dbg_dev, sizeof(long long) * 8 * 4096));
+        FD_CUDA(cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 8 * 4096, ctx->stream));
+        a.dbg = dbg_dev;
+    }
     if (cw == 112 && ch == 112 && (reinterpret_cast<uintptr_t>(crops_dev) & 3) == 0) {
         // 14-row items (8 per face, 7 rounds per thread as 4 + 3): small enough that the last items of a launch leave
         // no long tail (28 rows: +10 % time), large enough to amortise the per-item setup (8 rows: same time, 4: +8 %).
@@ -567,6 +596,21 @@ int warp_launch(fd_ctx *ctx, const FrameDev *frames_dev, const int32_t *frame_id
         const int grid = (int)std::min<long long>(items, (long long)ctx->num_sms * std::max(per_sm_fixed, 1));
         kern<<<grid, 224, 0, ctx->stream>>>(a);
         FD_LAUNCH_CHECK_NAMED(ctx, "warp_fixed_kernel");
+        if (dbg_on) {   // in-kernel timeline (globaltimer): where a launch's time goes beyond the per-item work
+            std::vector<long long> h(8 * (size_t)std::min(grid, 4096));
+            cudaStreamSynchronize(ctx->stream);
+            cudaMemcpy(h.data(), dbg_dev, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+            long long t0 = h[0], t1 = h[3], first_sum = 0, item_sum = 0, items_n = 0, entry_max = h[0], tick_sum = 0;
+            const int n = (int)h.size() / 8;
+            for (int b = 0; b < n; ++b) {
+                t0 = std::min(t0, h[8 * b]); t1 = std::max(t1, h[8 * b + 3]); entry_max = std::max(entry_max, h[8 * b]);
+                tick_sum += h[8 * b + 1] - h[8 * b];
+                if (h[8 * b + 2]) first_sum += h[8 * b + 2] - h[8 * b + 1];
+                item_sum += h[8 * b + 5]; items_n += h[8 * b + 4];
+            }
+            fprintf(stderr, "[warp dbg] F=%d grid=%d span %.2f us; CTA entry spread %.2f us; first ticket %.2f us; first item %.2f us; mean item %.2f us over %lld items\n",
+                    F_cap, grid, (t1 - t0) * 1e-3, (entry_max - t0) * 1e-3, tick_sum * 1e-3 / n, first_sum * 1e-3 / n, items_n ? item_sum * 1e-3 / items_n : 0.0, items_n);
+        }
         return FD_OK;
     }
     const size_t smem = sizeof(int2) * ((size_t)cw + WARP_BAND);

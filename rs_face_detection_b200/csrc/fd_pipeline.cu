@@ -769,15 +769,30 @@ FD_EXPORT int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const
     const size_t tn = (size_t)B * 3 * ctx->cfg.image_h * ctx->cfg.image_w;
     FD_TRY(ctx->pipe_tensor.reserve(sizeof(float) * tn));
     FD_TRY(fd_preprocess_batch(ctx, dframes.data(), B, ctx->pipe_tensor.as<float>(), nullptr));
-    // 3. heads H2D (the CNN outputs), decode + NMS
+    // 3. heads (the CNN outputs), decode + NMS.  The score planes are dense reads: the A foreground channels of each image go
+    //    to the device by DMA (face_detection.rs:322 never reads the background half).  The bbox / landmark tensors are read
+    //    only at the anchors that pass the threshold (~450 of 16 800 per image): when the caller's buffers are pinned, the
+    //    detect kernel reads those few sectors straight from host memory (zero-copy over PCIe) instead of copying 14 planes.
     const float *dev_heads[3 * FD_MAX_STRIDES];
     for (int s = 0; s < d.n_strides; ++s) {
         const int hw = d.fh[s] * d.fw[s];
         const int chn[3] = {2 * d.A, 4 * d.A, 10 * d.A};
         for (int k = 0; k < 3; ++k) {
             const size_t bytes = sizeof(float) * (size_t)B * chn[k] * hw;
+            const float *mapped = nullptr;
+            if (k != 0 && o.heads_zero_copy) {
+                cudaPointerAttributes at;
+                if (cudaPointerGetAttributes(&at, heads_host[3 * s + k]) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+                    mapped = static_cast<const float *>(at.devicePointer);
+                else
+                    cudaGetLastError();   // pageable memory: not an error, take the copy
+            }
+            if (mapped) {
+                dev_heads[3 * s + k] = mapped;
+                continue;
+            }
             FD_TRY(ctx->pipe_heads[3 * s + k].reserve(bytes));
-            if (k == 0) {   // scores: only the A foreground channels of each image are ever read (face_detection.rs:322)
+            if (k == 0) {
                 const size_t img = sizeof(float) * (size_t)chn[0] * hw, fg = img / 2;
                 FD_CUDA(cudaMemcpy2DAsync(ctx->pipe_heads[3 * s].as<unsigned char>() + fg, img,
                                           reinterpret_cast<const unsigned char *>(heads_host[3 * s]) + fg, img, fg, (size_t)B,
@@ -882,6 +897,14 @@ FD_EXPORT int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const
         if (select && out->sel) {
             FD_CUDA(cudaMemcpyAsync(out->sel, ctx->select_sel.p, sizeof(int) * 2 * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
             d2h += (int64_t)sizeof(int) * 2 * B;
+        }
+    }
+    if (o.heads_zero_copy) {   // sectors the detect kernel pulled from pinned host memory: 4 deltas per candidate, 10 per kept face
+        int32_t st[8];
+        if (fd_detect_last_stats(ctx, st) == FD_OK) {
+            bool any = false;
+            for (int i = 0; i < n_heads; ++i) any = any || (i % 3 != 0 && dev_heads[i] != ctx->pipe_heads[i].as<float>());
+            if (any) h2d += 32ll * (4ll * st[2] + 10ll * total);
         }
     }
     // 5. results D2H

@@ -70,7 +70,8 @@ FD_UPLOAD_FULL, FD_UPLOAD_ON_DEMAND = 0, 1
 
 
 class FdPipelineOpts(C.Structure):
-    _fields_ = [("select", C.c_int32), ("is_enroll", C.c_int32), ("upload", C.c_int32), ("select_params", FdSelectParams)]
+    _fields_ = [("select", C.c_int32), ("is_enroll", C.c_int32), ("upload", C.c_int32), ("heads_zero_copy", C.c_int32),
+                ("select_params", FdSelectParams)]
 
 
 # every symbol include/fd_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
@@ -132,6 +133,38 @@ def _devptr(x):
     if hasattr(x, "ptr"):
         return x.ptr
     raise TypeError("not a device pointer: %r" % (x,))
+
+
+class PinnedArray:
+    """numpy view over page-locked host memory (fd_host_alloc_pinned): full-rate DMA source and, for the head tensors,
+    directly readable by the kernels (fd_pipeline_opts.heads_zero_copy).  Keep the object alive while the array is in use."""
+
+    def __init__(self, shape, dtype):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _chk(load().fd_host_alloc_pinned(C.c_size_t(max(self.nbytes, 1)), C.byref(p)))
+        self.ptr = p.value
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            load().fd_host_free_pinned(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def pinned_like(arr):
+    """-> PinnedArray holding a copy of arr"""
+    pa = PinnedArray(arr.shape, arr.dtype)
+    pa.array[...] = arr
+    return pa
 
 
 def default_config():
@@ -571,7 +604,7 @@ class Context:
         return out
 
     def pipeline_host(self, frames_host, heads_host, cap_rows, conf_thr=None, iou_thr=None, want_tensor=False, bufs=None,
-                      select=False, is_enroll=False, upload=FD_UPLOAD_FULL, select_params=None):
+                      select=False, is_enroll=False, upload=FD_UPLOAD_FULL, select_params=None, heads_zero_copy=False):
         """frames_host: list of HxWx3 u8 arrays (host, ideally pinned); heads_host: 9 host arrays (B,C,H,W).
         select: FacePipeline::extract's flow (one selected face per image is aligned; crop b belongs to image b).
         upload: FD_UPLOAD_FULL | FD_UPLOAD_ON_DEMAND.  -> (bufs, total detections, h2d bytes, d2h bytes); bufs also
@@ -598,6 +631,7 @@ class Context:
         opts = FdPipelineOpts()
         _chk(self.lib.fd_pipeline_opts_default(C.byref(opts)))
         opts.select, opts.is_enroll, opts.upload = int(bool(select)), int(bool(is_enroll)), int(upload)
+        opts.heads_zero_copy = int(bool(heads_zero_copy))
         if select_params is not None:
             opts.select_params = FdSelectParams(*select_params)
         _chk(self.lib.fd_pipeline_host(self.handle, arr, B, hp, len(heads_host),

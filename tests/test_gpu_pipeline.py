@@ -117,6 +117,31 @@ def test_pipeline_host_select_flow(ctx, oracle, upload, is_enroll):
         assert h2d < 0.75 * h2d_full
 
 
+def test_pipeline_host_zero_copy_heads(ctx, oracle):
+    """heads_zero_copy: the bbox / landmark tensors stay in pinned host memory and the detect kernel reads the passing anchors'
+    values from there — same outputs, fewer bytes over PCIe; pageable buffers silently take the copy."""
+    from rs_face_detection_b200.ffi import pinned_like
+    B = 4
+    frames = [synth.make_frame(1080, 1920, 2500 + i) for i in range(B)]
+    heads, _ = synth.make_heads(B, seed=3300, n_faces=12, content_hw=(360, 640))
+    ref, total, h2d_copy, _ = ctx.pipeline_host(frames, heads, cap_rows=B * 64, conf_thr=0.7, iou_thr=0.4)
+    pinned = [pinned_like(h) for h in heads]
+    for mode_heads in ([p.array for p in pinned], heads):
+        got, total2, h2d, _ = ctx.pipeline_host(frames, mode_heads, cap_rows=B * 64, conf_thr=0.7, iou_thr=0.4, heads_zero_copy=True)
+        assert total2 == total > 0
+        np.testing.assert_array_equal(got["counts"], ref["counts"])
+        np.testing.assert_array_equal(got["det"][:total], ref["det"][:total])
+        np.testing.assert_array_equal(got["lmk"][:total], ref["lmk"][:total])
+        np.testing.assert_array_equal(got["crops"][:total], ref["crops"][:total])
+        if mode_heads is not heads:
+            assert h2d < h2d_copy - 0.8 * sum(h.nbytes for i, h in enumerate(heads) if i % 3)
+        else:
+            assert h2d == h2d_copy
+    _check_all_faces(oracle, frames, heads, got, total, 0.7, 0.4)
+    for p in pinned:
+        p.free()
+
+
 def test_device_resident_sequence(ctx, oracle):
     """The benchmarked call sequence: preprocess_batch -> detect_batch -> align_detections, inputs resident in HBM."""
     B = 3
