@@ -674,34 +674,32 @@ def run_ours(args):
                     "steps": n_steps, "ms_per_step": 1e3 * s / n_steps, "batches_in_flight": L, "detections_per_step": int(total),
                     "crops_per_step": int(e2e_bufs[0]["n_crops"]), "note": note}
 
-        e2e = e2e_leg({}, e2e_steps,
+        e2e = e2e_leg(dict(heads_zero_copy=True), e2e_steps,
                       "fd_pipeline_host per batch: pinned host frames+heads -> H2D -> preprocess/decode/NMS/align of EVERY detection -> D2H "
                       "dets+landmarks+crops; %d host threads / fd_ctx alternate batches; the CNN input tensor stays on the device (Triton "
-                      "CUDA-shm boundary)" % L)
+                      "CUDA-shm boundary); heads_zero_copy: the bbox/landmark head tensors are read in place from pinned host memory (only the "
+                      "passing anchors' sectors cross PCIe), the score planes and the frames are copied whole" % L)
         # strictly serial variant (one context, one batch at a time) for reference
         ctx.set_sharing(1)
         t0 = time.perf_counter()
         for _ in range(4):
-            ctx.pipeline_host(host_frames, host_heads, cap_rows, CONF_THR, IOU_THR, bufs=e2e_bufs[0])
+            ctx.pipeline_host(host_frames, host_heads, cap_rows, CONF_THR, IOU_THR, bufs=e2e_bufs[0], heads_zero_copy=True)
         e2e["serial_ms_per_step"] = 1e3 * (time.perf_counter() - t0) / 4
         for c_ in e2e_ctx:
             c_.set_sharing(L)
         if not args.no_e2e_variants:
             short = max(2 * L, min(e2e_steps, 12)) // L * L
-            e2e_variants["heads_zero_copy"] = e2e_leg(
-                dict(heads_zero_copy=True), short,
-                "same work, fd_pipeline_opts.heads_zero_copy: the bbox/landmark head tensors are not copied; the detect kernel reads the passing "
-                "anchors' sectors straight from pinned host memory")
+            e2e_variants["heads_copied"] = e2e_leg({}, short, "same work with every head tensor copied to the device (fd_pipeline_opts defaults)")
             e2e_variants["on_demand_upload"] = e2e_leg(
-                dict(upload=FD_UPLOAD_ON_DEMAND), short,
+                dict(upload=FD_UPLOAD_ON_DEMAND, heads_zero_copy=True), short,
                 "same work, FD_UPLOAD_ON_DEMAND: rows the letterbox reads first, then only what the warps read — with ~20 large overlapping faces "
                 "per frame the warps read (almost) every row, so the bytes do not drop for THIS workload")
             e2e_variants["extract_flow"] = e2e_leg(
-                dict(select=True, upload=FD_UPLOAD_ON_DEMAND), short,
+                dict(select=True, upload=FD_UPLOAD_ON_DEMAND, heads_zero_copy=True), short,
                 "FacePipeline::extract's flow (face_pipeline/pipeline.rs:196-232): detect -> FaceSelection -> align the ONE selected face per frame, "
                 "FD_UPLOAD_ON_DEMAND: preprocess rows + one face rectangle per frame cross PCIe")
             e2e_variants["extract_flow_full_upload"] = e2e_leg(
-                dict(select=True), short, "the extract flow with whole-frame upload, for the byte comparison")
+                dict(select=True, heads_zero_copy=True), short, "the extract flow with whole-frame upload, for the byte comparison")
         ctx.set_sharing(1)
         for c_ in e2e_ctx[1:]:
             c_.close()

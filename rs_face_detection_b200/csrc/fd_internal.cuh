@@ -74,6 +74,8 @@ struct fd_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // copy stream for the host pipeline
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_block = nullptr;  // cudaEventBlockingSync: host waits that sleep instead of spinning (fd_pipeline_host)
+    bool blocking_sync = false;
     int num_sms = 0;
     int max_smem_optin = 0;
     int64_t launches = 0;

@@ -11,6 +11,19 @@
 
 namespace fd {
 
+// Waits for the ctx stream.  In blocking mode (set by fd_pipeline_host: several host threads / processes each drive a ctx and
+// sleep through multi-millisecond PCIe transfers) the wait is an OS-level block on an event created with
+// cudaEventBlockingSync instead of a spin on the CPU, so N ranks x L lanes do not burn N*L host cores.
+static int wait_stream(fd_ctx *ctx) {
+    if (ctx->blocking_sync && ctx->ev_block) {
+        FD_CUDA(cudaEventRecord(ctx->ev_block, ctx->stream));
+        FD_CUDA(cudaEventSynchronize(ctx->ev_block));
+    } else {
+        FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return FD_OK;
+}
+
 // RetinaFaceDetection::_preprocess geometry (face_detection.rs:140-153): f32 arithmetic, `as i32` truncation
 static void letterbox(int h, int w, int size_w, int size_h, int *new_w, int *new_h, float *det_scale) {
     volatile float im_ratio = (float)h / (float)w;
@@ -107,7 +120,7 @@ static int detect_resolve(fd_ctx *ctx) {
     const int B = ctx->last_B;
     int st[4] = {0, 0, 0, 0};
     FD_CUDA(cudaMemcpyAsync(st, ctx->status(), sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
-    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    FD_TRY(wait_stream(ctx));
     ctx->detect_pending = false;
     if (st[1] > 0) {
         ctx->crowded = true;   // later fused launches keep images with up to 4096 candidates on the device
@@ -124,7 +137,7 @@ static int detect_resolve(fd_ctx *ctx) {
             FD_TRY(align_enqueue(ctx, ctx->frames_dev.as<FrameDev>(), ctx->out_lmk.as<float>(), ctx->out_frame_idx.as<int32_t>(),
                                  ctx->status() + 2, ctx->align_cap, ctx->align_crops, ctx->align_M_out, ctx->align_ok_out, true,
                                  detect_fallback(ctx)));
-        FD_CUDA(cudaStreamSynchronize(ctx->stream));
+        FD_TRY(wait_stream(ctx));
     }
     return FD_OK;
 }
@@ -224,7 +237,7 @@ FD_EXPORT int fd_detect_fetch(fd_ctx *ctx, int32_t *counts, float *det, float *l
     const int B = ctx->last_B;
     std::vector<int> off(B + 1);
     FD_CUDA(cudaMemcpyAsync(off.data(), ctx->out_offsets.p, sizeof(int) * (B + 1), cudaMemcpyDeviceToHost, ctx->stream));
-    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    FD_TRY(wait_stream(ctx));
     const int tot = off[B];
     if (total) *total = tot;
     if (counts)
@@ -233,7 +246,7 @@ FD_EXPORT int fd_detect_fetch(fd_ctx *ctx, int32_t *counts, float *det, float *l
     if (det && tot) FD_CUDA(cudaMemcpyAsync(det, ctx->out_det.p, sizeof(float) * 5 * (size_t)tot, cudaMemcpyDeviceToHost, ctx->stream));
     if (landmarks && tot)
         FD_CUDA(cudaMemcpyAsync(landmarks, ctx->out_lmk.p, sizeof(float) * 10 * (size_t)tot, cudaMemcpyDeviceToHost, ctx->stream));
-    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    FD_TRY(wait_stream(ctx));
     return FD_OK;
 }
 
@@ -258,7 +271,7 @@ FD_EXPORT int fd_detect_last_stats(fd_ctx *ctx, int32_t *out) {
     std::vector<int> counts(B);
     FD_CUDA(cudaMemcpyAsync(st, ctx->status(), sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
     FD_CUDA(cudaMemcpyAsync(counts.data(), ctx->cand_count.p, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
-    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    FD_TRY(wait_stream(ctx));
     long long tot = 0;
     int mx = 0;
     for (int c : counts) { tot += c; mx = std::max(mx, c); }
@@ -733,6 +746,11 @@ FD_EXPORT int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const
     if (opts) o = *opts;
     else FD_TRY(fd_pipeline_opts_default(&o));
     const bool select = o.select != 0, demand = o.upload == FD_UPLOAD_ON_DEMAND;
+    struct BlockingScope {   // sleep, do not spin, while this call waits on PCIe
+        fd_ctx *c; bool prev;
+        explicit BlockingScope(fd_ctx *c_) : c(c_), prev(c_->blocking_sync) { c->blocking_sync = true; }
+        ~BlockingScope() { c->blocking_sync = prev; }
+    } blocking_scope(ctx);
     FD_REQUIRE(!select || out->cap_rows >= B, "fd_pipeline_host: select mode writes one crop per image (cap_rows >= B)");
     const DecodeCfg &d = ctx->dcfg;
     const int cw = ctx->cfg.crop_w, ch = ctx->cfg.crop_h;
@@ -847,7 +865,7 @@ FD_EXPORT int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const
                 FD_CUDA(cudaMemcpyAsync(M12.data(), ctx->align_M.p, sizeof(double) * 12 * (size_t)F, cudaMemcpyDeviceToHost, ctx->stream));
                 FD_CUDA(cudaMemcpyAsync(okh.data(), ctx->align_ok.p, (size_t)F, cudaMemcpyDeviceToHost, ctx->stream));
                 if (select) FD_CUDA(cudaMemcpyAsync(selh.data(), ctx->select_sel.p, sizeof(int) * 2 * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
-                FD_CUDA(cudaStreamSynchronize(ctx->stream));
+                FD_TRY(wait_stream(ctx));
                 d2h += (int64_t)F * 97 + (int64_t)selh.size() * 4;
                 struct Rect { int x0, y0, x1, y1; };
                 std::vector<std::vector<Rect>> rects(B);
@@ -921,7 +939,7 @@ FD_EXPORT int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const
         FD_CUDA(cudaMemcpyAsync(out->tensor, ctx->pipe_tensor.p, sizeof(float) * tn, cudaMemcpyDeviceToHost, ctx->stream));
         d2h += (int64_t)sizeof(float) * tn;
     }
-    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    FD_TRY(wait_stream(ctx));
     out->h2d_bytes = h2d;
     out->d2h_bytes = d2h;
     return FD_OK;
