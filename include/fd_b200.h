@@ -259,6 +259,19 @@ int fd_select_detections(fd_ctx *ctx, const fd_frame *frames, int B, int is_enro
  * returns Err) get ok = 0 and a zero crop; ok = 2 marks the bbox-crop fallback on the selected box.  M_dev (B,6) / ok_dev (B) optional. */
 int fd_align_selected(fd_ctx *ctx, const fd_frame *frames, int B, uint8_t *crops_dev, double *M_dev, uint8_t *ok_dev);
 
+/* ---- utils::byte_data_to_opencv (utils.rs:8-52 = cv::imdecode(bytes, IMREAD_UNCHANGED)), baseline JPEG ------- */
+/* Host-only header parse: image size and luma sampling (11 = 4:4:4, 21 = 4:2:2, 22 = 4:2:0).  FD_ERR_INVALID for streams the
+ * decoder does not cover (progressive, arithmetic, grayscale, CMYK, non-interleaved scans): the reference hands those to OpenCV. */
+int fd_jpeg_info(const uint8_t *jpeg, size_t nbytes, int *height, int *width, int *subsampling);
+/* Decodes B JPEG streams (host memory) into DEVICE-resident BGR frames, bit-identical to cv2.imdecode (libjpeg-turbo islow IDCT,
+ * fancy upsampling, 16-bit colour tables).  The Huffman stage is serial per stream by construction and runs on the host on up
+ * to n_threads threads (0 = hardware concurrency), one image per thread; dequantisation + IDCT and upsampling + colour
+ * conversion are CUDA kernels on the ctx stream (asynchronous).  frames_out[i] = {device pointer owned by the ctx and valid
+ * until the next call, h, w, pitch = align16(3w)}: feed it to fd_preprocess_batch / fd_align_detections directly. */
+int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, const size_t *nbytes, int B, int n_threads, fd_frame *frames_out);
+/* One stream to a HOST buffer (the reference's call shape: one Mat out), blocking.  out_bgr: height rows of `pitch` bytes. */
+int fd_imdecode(fd_ctx *ctx, const uint8_t *jpeg, size_t nbytes, uint8_t *out_bgr, int pitch);
+
 /* ---- end-to-end with HOST buffers (bench.py "e2e"): H2D frames + heads, full path, D2H results -------- */
 typedef struct fd_host_batch_out {
     int32_t *counts;      /* (B) detections per image */

@@ -20,8 +20,8 @@ c_f64p = C.POINTER(C.c_double)
 
 def build(force=False):
     """Compile the oracle (and oracle/_ref when /root/reference is present) with oracle/Makefile."""
-    src = os.path.join(_HERE, "fd_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("fd_oracle.c", "fd_jpeg_oracle.c", "Makefile")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "libfd_oracle.so"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
@@ -406,3 +406,25 @@ def pipeline_frame(cfg, img, heads, template=ARCFACE_TEMPLATE, crop=(112, 112), 
     if M < 0:
         raise ValueError("NaN score")
     return tensor, det[:M], lmk[:M].reshape(M, 5, 2), crops[:M]
+
+
+# ---------------------------------------------------------------- N4: JPEG decode (utils.rs:8-52 -> cv::imdecode)
+def jpeg_info(data):
+    """-> (h, w, subsampling) with subsampling 11 (4:4:4), 21 (4:2:2) or 22 (4:2:0); raises ValueError on unsupported streams"""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    h, w, ss = C.c_int(0), C.c_int(0), C.c_int(0)
+    rc = lib().fdo_jpeg_info(_p(buf, c_u8p), C.c_size_t(len(buf)), C.byref(h), C.byref(w), C.byref(ss))
+    if rc != 0:
+        raise ValueError("jpeg oracle: error %d" % rc)
+    return h.value, w.value, ss.value
+
+
+def jpeg_decode(data):
+    """cv::imdecode(bytes, IMREAD_UNCHANGED) for a baseline 3-component JPEG -> (h, w, 3) BGR u8"""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    h, w, _ = jpeg_info(data)
+    out = np.empty((h, w, 3), np.uint8)
+    rc = lib().fdo_jpeg_decode_bgr(_p(buf, c_u8p), C.c_size_t(len(buf)), _p(out, c_u8p), w * 3)
+    if rc != 0:
+        raise ValueError("jpeg oracle: error %d" % rc)
+    return out

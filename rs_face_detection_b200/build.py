@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfd_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["fd_ctx.cu", "fd_ops.cu", "fd_nms.cu", "fd_decode.cu", "fd_detect_fused.cu", "fd_select.cu", "fd_preprocess.cu", "fd_align.cu", "fd_pipeline.cu"]
+SOURCES = ["fd_ctx.cu", "fd_ops.cu", "fd_nms.cu", "fd_decode.cu", "fd_detect_fused.cu", "fd_select.cu", "fd_preprocess.cu", "fd_align.cu", "fd_pipeline.cu", "fd_jpeg.cu"]
 EXTRA = os.environ.get("FD_NVCC_EXTRA", "").split()   # experiments only, e.g. FD_NVCC_EXTRA=-DFUSED_MAXNREG=48
 FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
          "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2", "--shared", "-cudart", "shared"]

@@ -1,0 +1,544 @@
+// fd_jpeg.cu — SURVEY 8(f) row N4: utils::byte_data_to_opencv (reference src/utils/utils.rs:8-52 = cv::imdecode(bytes,
+// IMREAD_UNCHANGED)) for baseline JPEG, producing DEVICE-resident BGR frames for fd_preprocess_batch / fd_align_*.
+//
+// Split of the work:
+//   host   marker parsing and Huffman entropy decoding (ITU-T T.81 Annex F.2.2).  An entropy-coded segment is one serial
+//          bit stream — every symbol's position depends on all earlier ones and a file without restart markers has no
+//          synchronisation point — so this stage runs on the host, one image per worker thread, and emits the quantised
+//          coefficients (int16, natural order, one 64-entry block per DCT block) into pinned memory;
+//   device `jpeg_idct_kernel`: dequantisation + libjpeg's jpeg_idct_islow (jidctint.c: 13-bit constants, PASS1_BITS 2, the
+//          range-limit table with its wrap-around), 8 threads per block;
+//          `jpeg_color_kernel`: chroma upsampling (jdsample.c h2v1 / h2v2 "fancy" triangle filters with jdmainct.c's replicated
+//          context rows; plain replication when downsampled_width <= 2, as jinit_upsampler selects) + YCbCr -> BGR with
+//          jdcolor.c's 16-bit fixed-point constants, 4 pixels per thread, 12-byte packed stores.
+// Every integer operation follows libjpeg-turbo's decompressor with the defaults OpenCV leaves in place (JDCT_ISLOW,
+// do_fancy_upsampling), so the frames are bit-identical to cv2.imdecode (tests/test_gpu_jpeg.py, golden vectors from cv2 4.13).
+// Scope: SOF0 / SOF1 8-bit, one interleaved 3-component scan, 4:4:4 / 4:2:2 / 4:2:0, DRI/RSTn.  Progressive, arithmetic,
+// grayscale, CMYK streams return FD_ERR_INVALID (the reference would hand them to OpenCV).
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <thread>
+#include <vector>
+#include "fd_internal.cuh"
+
+namespace fd {
+
+static const uint8_t JZIGZAG[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                    41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                    30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+constexpr int HUFF_LOOKAHEAD = 10;
+
+struct HuffTable {
+    bool present = false;
+    uint8_t bits[17] = {0}, vals[256] = {0};
+    int maxcode[18], mincode[17], valptr[17];
+    uint16_t look[1 << HUFF_LOOKAHEAD];   // (length << 8) | symbol for codes of <= HUFF_LOOKAHEAD bits, 0 = longer code
+    void build() {
+        int code = 0, k = 0;
+        memset(look, 0, sizeof(look));
+        for (int l = 1; l <= 16; ++l) {
+            valptr[l] = k;
+            mincode[l] = code;
+            for (int i = 0; i < bits[l]; ++i, ++k, ++code) {
+                if (l <= HUFF_LOOKAHEAD) {
+                    const int first = code << (HUFF_LOOKAHEAD - l), n = 1 << (HUFF_LOOKAHEAD - l);
+                    for (int j = 0; j < n; ++j) look[first + j] = (uint16_t)((l << 8) | vals[k]);
+                }
+            }
+            maxcode[l] = bits[l] ? code - 1 : -1;
+            code <<= 1;
+        }
+        maxcode[17] = 0x7fffffff;
+        present = true;
+    }
+};
+
+struct JpegHeader {
+    int h = 0, w = 0, restart = 0;
+    int id[3], hs[3], vs[3], tq[3], td[3], ta[3];
+    uint16_t qt[4][64];
+    bool qt_present[4] = {false, false, false, false};
+    HuffTable dc[4], ac[4];
+    const uint8_t *scan = nullptr;
+    size_t scan_len = 0;
+    // derived geometry
+    int mcux = 0, mcuy = 0;
+    int pw[3], ph[3];          // component plane sizes (multiples of 8 x the MCU grid)
+    size_t blocks[3];          // DCT blocks per component
+};
+
+static const char *parse_jpeg(const uint8_t *p, size_t n, JpegHeader *j) {
+    if (!p || n < 4 || p[0] != 0xFF || p[1] != 0xD8) return "not a JPEG stream (no SOI)";
+    size_t i = 2;
+    bool have_sof = false;
+    while (i + 4 <= n) {
+        if (p[i] != 0xFF) return "marker expected";
+        while (i < n && p[i] == 0xFF) ++i;
+        if (i >= n) break;
+        const int m = p[i++];
+        if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7) || m == 0x01) continue;
+        if (m == 0xD9) return "EOI before SOS";
+        if (i + 2 > n) break;
+        const size_t len = ((size_t)p[i] << 8) | p[i + 1];
+        if (len < 2 || i + len > n) break;
+        const uint8_t *s = p + i + 2;
+        const size_t sl = len - 2;
+        switch (m) {
+            case 0xDB: {
+                size_t k = 0;
+                while (k < sl) {
+                    const int pq = s[k] >> 4, tq = s[k] & 15;
+                    ++k;
+                    if (tq > 3 || k + (pq ? 128u : 64u) > sl) return "bad DQT";
+                    for (int z = 0; z < 64; ++z) {
+                        j->qt[tq][JZIGZAG[z]] = (uint16_t)(pq ? ((s[k] << 8) | s[k + 1]) : s[k]);
+                        k += pq ? 2 : 1;
+                    }
+                    j->qt_present[tq] = true;
+                }
+                break;
+            }
+            case 0xC4: {
+                size_t k = 0;
+                while (k < sl) {
+                    const int tc = s[k] >> 4, th = s[k] & 15;
+                    ++k;
+                    if (tc > 1 || th > 3 || k + 16 > sl) return "bad DHT";
+                    HuffTable &t = tc ? j->ac[th] : j->dc[th];
+                    int total = 0;
+                    for (int l = 1; l <= 16; ++l) { t.bits[l] = s[k++]; total += t.bits[l]; }
+                    if (total > 256 || k + (size_t)total > sl) return "bad DHT";
+                    memcpy(t.vals, s + k, (size_t)total);
+                    k += (size_t)total;
+                    t.build();
+                }
+                break;
+            }
+            case 0xC0:
+            case 0xC1: {
+                if (sl < 15 || s[0] != 8) return "unsupported sample precision";
+                j->h = (s[1] << 8) | s[2];
+                j->w = (s[3] << 8) | s[4];
+                if (s[5] != 3) return "unsupported component count (grayscale / CMYK)";
+                if (j->h == 0 || j->w == 0) return "empty image";
+                for (int c = 0; c < 3; ++c) {
+                    j->id[c] = s[6 + 3 * c];
+                    j->hs[c] = s[7 + 3 * c] >> 4;
+                    j->vs[c] = s[7 + 3 * c] & 15;
+                    j->tq[c] = s[8 + 3 * c];
+                    if (j->tq[c] > 3) return "bad SOF";
+                }
+                if (j->hs[1] != 1 || j->vs[1] != 1 || j->hs[2] != 1 || j->vs[2] != 1) return "unsupported chroma sampling";
+                if (!((j->hs[0] == 1 && j->vs[0] == 1) || (j->hs[0] == 2 && j->vs[0] == 1) || (j->hs[0] == 2 && j->vs[0] == 2)))
+                    return "unsupported luma sampling (4:4:4, 4:2:2 and 4:2:0 are)";
+                have_sof = true;
+                break;
+            }
+            case 0xDD:
+                if (sl < 2) return "bad DRI";
+                j->restart = (s[0] << 8) | s[1];
+                break;
+            case 0xDA: {
+                if (!have_sof) return "SOS before SOF";
+                if (sl < 10 || s[0] != 3) return "unsupported scan (one interleaved 3-component scan is)";
+                for (int c = 0; c < 3; ++c) {
+                    if (s[1 + 2 * c] != j->id[c]) return "unsupported scan component order";
+                    j->td[c] = s[2 + 2 * c] >> 4;
+                    j->ta[c] = s[2 + 2 * c] & 15;
+                    if (j->td[c] > 3 || j->ta[c] > 3 || !j->dc[j->td[c]].present || !j->ac[j->ta[c]].present || !j->qt_present[j->tq[c]])
+                        return "scan refers to a missing table";
+                }
+                if (s[7] != 0 || s[8] != 63) return "unsupported spectral selection";
+                j->scan = p + i + len;
+                j->scan_len = n - (i + len);
+                const int H = j->hs[0], V = j->vs[0];
+                j->mcux = (j->w + 8 * H - 1) / (8 * H);
+                j->mcuy = (j->h + 8 * V - 1) / (8 * V);
+                for (int c = 0; c < 3; ++c) {
+                    j->pw[c] = j->mcux * j->hs[c] * 8;
+                    j->ph[c] = j->mcuy * j->vs[c] * 8;
+                    j->blocks[c] = (size_t)(j->pw[c] / 8) * (j->ph[c] / 8);
+                }
+                return nullptr;
+            }
+            default:
+                if (m >= 0xC2 && m <= 0xCF && m != 0xC8 && m != 0xCC) return "unsupported JPEG process (progressive / lossless / arithmetic)";
+                break;   // APPn, COM, ...
+        }
+        i += len;
+    }
+    return "truncated JPEG stream";
+}
+
+// Entropy-coded segment reader: FF00 -> FF; any other marker stops the feed (zero fill, as libjpeg does).
+struct BitReader {
+    const uint8_t *p;
+    size_t n, i = 0;
+    uint64_t acc = 0;
+    int cnt = 0;
+    bool marker = false;
+    BitReader(const uint8_t *p_, size_t n_) : p(p_), n(n_) {}
+    inline void fill() {
+        while (cnt <= 56) {
+            unsigned byte = 0;
+            if (!marker && i < n) {
+                byte = p[i];
+                if (byte == 0xFF) {
+                    if (i + 1 < n && p[i + 1] == 0x00) i += 2;
+                    else { marker = true; byte = 0; }
+                } else {
+                    ++i;
+                }
+            }
+            acc |= (uint64_t)byte << (56 - cnt);
+            cnt += 8;
+        }
+    }
+    inline unsigned peek(int nb) const { return (unsigned)(acc >> (64 - nb)); }
+    inline void drop(int nb) { acc <<= nb; cnt -= nb; }
+    inline int receive_extend(int s) {   // F.2.2.1 RECEIVE + EXTEND
+        if (cnt < s) fill();
+        const int v = (int)peek(s);
+        drop(s);
+        return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+    }
+    inline int decode(const HuffTable &t) {   // F.2.2.3 DECODE with a 10-bit lookahead table
+        if (cnt < 16) fill();
+        const unsigned e = t.look[peek(HUFF_LOOKAHEAD)];
+        if (e) {
+            drop(e >> 8);
+            return e & 0xFF;
+        }
+        int l = HUFF_LOOKAHEAD + 1;
+        int code = (int)peek(l);
+        while (l <= 16 && code > t.maxcode[l]) {
+            ++l;
+            code = (int)peek(l);
+        }
+        if (l > 16) { drop(16); return 0; }
+        drop(l);
+        return t.vals[t.valptr[l] + code - t.mincode[l]];
+    }
+    void restart() {   // byte-align, step over the RSTn marker
+        acc = 0;
+        cnt = 0;
+        if (marker) {
+            while (i + 1 < n && !(p[i] == 0xFF && p[i + 1] >= 0xD0 && p[i + 1] <= 0xD7)) ++i;
+            i = std::min(n, i + 2);
+            marker = false;
+        } else if (i + 1 < n && p[i] == 0xFF && p[i + 1] >= 0xD0 && p[i + 1] <= 0xD7) {
+            i += 2;
+        }
+    }
+};
+
+// coef: [comp 0 blocks][comp 1 blocks][comp 2 blocks], each block 64 int16 in natural order, block (by,bx) row-major
+static void huffman_decode(const JpegHeader &j, int16_t *coef) {
+    BitReader b(j.scan, j.scan_len);
+    int16_t *base[3] = {coef, coef + j.blocks[0] * 64, coef + (j.blocks[0] + j.blocks[1]) * 64};
+    const int bw[3] = {j.pw[0] / 8, j.pw[1] / 8, j.pw[2] / 8};
+    int pred[3] = {0, 0, 0};
+    int count = 0;
+    for (int my = 0; my < j.mcuy; ++my)
+        for (int mx = 0; mx < j.mcux; ++mx) {
+            if (j.restart && count && count % j.restart == 0) {
+                b.restart();
+                pred[0] = pred[1] = pred[2] = 0;
+            }
+            ++count;
+            for (int c = 0; c < 3; ++c) {
+                const HuffTable &dct = j.dc[j.td[c]], &act = j.ac[j.ta[c]];
+                for (int v = 0; v < j.vs[c]; ++v)
+                    for (int hh = 0; hh < j.hs[c]; ++hh) {
+                        int16_t *blk = base[c] + ((size_t)(my * j.vs[c] + v) * bw[c] + (size_t)(mx * j.hs[c] + hh)) * 64;
+                        int s = b.decode(dct);
+                        if (s) pred[c] += b.receive_extend(s);
+                        blk[0] = (int16_t)pred[c];
+                        for (int k = 1; k < 64;) {
+                            const int rs = b.decode(act);
+                            const int r = rs >> 4;
+                            s = rs & 15;
+                            if (s == 0) {
+                                if (r != 15) break;
+                                k += 16;
+                                continue;
+                            }
+                            k += r;
+                            if (k > 63) break;
+                            blk[JZIGZAG[k]] = (int16_t)b.receive_extend(s);
+                            ++k;
+                        }
+                    }
+            }
+        }
+}
+
+// ---- device side --------------------------------------------------------------------------------------------------------
+struct JpegImageDev {
+    const int16_t *coef;       // this image's coefficient blocks (component-major)
+    uint8_t *plane[3];         // component planes, pw x ph
+    uint8_t *bgr;              // output frame
+    int pw[3], ph[3];
+    int nblk[3];               // blocks per component
+    int w, h, pitch;           // output geometry
+    int H, V;                  // luma sampling factors (chroma is 1x1)
+    uint16_t qt[3][64];        // per COMPONENT quantisation table, natural order
+};
+
+#define JCONST_BITS 13
+#define JPASS1_BITS 2
+#define JDESCALE(x, n) (((x) + (1 << ((n) - 1))) >> (n))
+__device__ __forceinline__ unsigned jpeg_range_limit(int x) {   // sample_range_limit + CENTERJSAMPLE at (x & RANGE_MASK)
+    const int m = x & 1023;
+    return (unsigned)(m < 128 ? m + 128 : (m < 512 ? 255 : (m < 896 ? 0 : m - 896)));
+}
+// one 1-D pass of jpeg_idct_islow over 8 values (already dequantised in pass 1); shift = the pass's descale
+__device__ __forceinline__ void jpeg_idct_1d(const int *v, int shift, int *o) {
+    int z2 = v[2], z3 = v[6];
+    int z1 = (z2 + z3) * 4433;
+    int tmp2 = z1 + z3 * (-15137), tmp3 = z1 + z2 * 6270;
+    int tmp0 = (v[0] + v[4]) << JCONST_BITS, tmp1 = (v[0] - v[4]) << JCONST_BITS;
+    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    tmp0 = v[7]; tmp1 = v[5]; tmp2 = v[3]; tmp3 = v[1];
+    z1 = tmp0 + tmp3;
+    z2 = tmp1 + tmp2;
+    z3 = tmp0 + tmp2;
+    int z4 = tmp1 + tmp3;
+    const int z5 = (z3 + z4) * 9633;
+    tmp0 *= 2446; tmp1 *= 16819; tmp2 *= 25172; tmp3 *= 12299;
+    z1 *= -7373; z2 *= -20995; z3 *= -16069; z4 *= -3196;
+    z3 += z5;
+    z4 += z5;
+    tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+    o[0] = JDESCALE(tmp10 + tmp3, shift); o[7] = JDESCALE(tmp10 - tmp3, shift);
+    o[1] = JDESCALE(tmp11 + tmp2, shift); o[6] = JDESCALE(tmp11 - tmp2, shift);
+    o[2] = JDESCALE(tmp12 + tmp1, shift); o[5] = JDESCALE(tmp12 - tmp1, shift);
+    o[3] = JDESCALE(tmp13 + tmp0, shift); o[4] = JDESCALE(tmp13 - tmp0, shift);
+}
+
+constexpr int IDCT_BLOCKS = 32;   // DCT blocks per CTA (8 threads each)
+
+// grid (ceil(blocks of the image / 32), B): thread = (block, column) in pass 1, (block, row) in pass 2
+__global__ void __launch_bounds__(IDCT_BLOCKS * 8) jpeg_idct_kernel(const JpegImageDev *__restrict__ imgs) {
+    __shared__ int ws[IDCT_BLOCKS][64 + 8];   // +8: the row pass reads 8 consecutive ints per thread, rows of different blocks apart
+    const JpegImageDev &im = imgs[blockIdx.y];
+    const int lb = threadIdx.x >> 3, k = threadIdx.x & 7;
+    const int gb = blockIdx.x * IDCT_BLOCKS + lb;
+    const int total = im.nblk[0] + im.nblk[1] + im.nblk[2];
+    const bool live = gb < total;
+    int c = 0, bi = gb;
+    if (live) {
+        if (bi >= im.nblk[0]) { bi -= im.nblk[0]; c = 1; }
+        if (c == 1 && bi >= im.nblk[1]) { bi -= im.nblk[1]; c = 2; }
+        const int16_t *in = im.coef + (size_t)gb * 64 + k;    // column k of the block
+        const uint16_t *q = im.qt[c] + k;
+        int v[8], o[8];
+        bool ac0 = true;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            v[r] = (int)in[8 * r] * (int)q[8 * r];            // DEQUANTIZE
+            if (r) ac0 = ac0 && in[8 * r] == 0;
+        }
+        if (ac0) {   // jidctint.c's shortcut (identical to the general path for an all-zero AC column)
+            const int dc = v[0] << JPASS1_BITS;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) o[r] = dc;
+        } else {
+            jpeg_idct_1d(v, JCONST_BITS - JPASS1_BITS, o);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) ws[lb][8 * r + k] = o[r];
+    }
+    __syncthreads();
+    if (!live) return;
+    int v[8], o[8];
+#pragma unroll
+    for (int x = 0; x < 8; ++x) v[x] = ws[lb][8 * k + x];     // row k
+    jpeg_idct_1d(v, JCONST_BITS + JPASS1_BITS + 3, o);
+    const int bw = im.pw[c] >> 3;
+    const int by = bi / bw, bx = bi - by * bw;
+    uint8_t *dst = im.plane[c] + (size_t)(by * 8 + k) * im.pw[c] + bx * 8;
+    uint2 out;
+    out.x = jpeg_range_limit(o[0]) | (jpeg_range_limit(o[1]) << 8) | (jpeg_range_limit(o[2]) << 16) | (jpeg_range_limit(o[3]) << 24);
+    out.y = jpeg_range_limit(o[4]) | (jpeg_range_limit(o[5]) << 8) | (jpeg_range_limit(o[6]) << 16) | (jpeg_range_limit(o[7]) << 24);
+    *reinterpret_cast<uint2 *>(dst) = out;                   // planes are 8-byte aligned, pw % 8 == 0
+}
+
+// chroma sample at full resolution (jdsample.c fullsize / h2v1_fancy / h2v2_fancy, jdmainct.c context rows)
+__device__ __forceinline__ int jpeg_chroma_at(const uint8_t *__restrict__ pl, int pitch, int dw, int dh, int H, int V, int x, int y) {
+    if (H == 1) return pl[(size_t)y * pitch + x];
+    const int cx = x >> 1;
+    if (dw <= 2) return pl[(size_t)(V == 2 ? y >> 1 : y) * pitch + cx];   // jinit_upsampler: replication for narrow components
+    if (V == 1) {
+        const uint8_t *r = pl + (size_t)y * pitch;
+        const int v = r[cx];
+        if (!(x & 1)) return cx == 0 ? v : (v * 3 + r[cx - 1] + 1) >> 2;
+        if (cx == 0) return (v * 3 + r[1] + 2) >> 2;
+        return cx == dw - 1 ? v : (v * 3 + r[cx + 1] + 2) >> 2;
+    }
+    const int cy = y >> 1;
+    int ny = (y & 1) ? cy + 1 : cy - 1;
+    ny = max(0, min(dh - 1, ny));
+    const uint8_t *r0 = pl + (size_t)cy * pitch, *r1 = pl + (size_t)ny * pitch;
+    const int t = r0[cx] * 3 + r1[cx];
+    if (cx == 0) return (x & 1) ? (t * 3 + (r0[1] * 3 + r1[1]) + 7) >> 4 : (t * 4 + 8) >> 4;
+    if (!(x & 1)) return (t * 3 + (r0[cx - 1] * 3 + r1[cx - 1]) + 8) >> 4;
+    return cx == dw - 1 ? (t * 4 + 7) >> 4 : (t * 3 + (r0[cx + 1] * 3 + r1[cx + 1]) + 7) >> 4;
+}
+
+// grid (ceil(w/4 / 128), h rows, B): 4 pixels per thread -> 12 bytes = three aligned 32-bit stores (pitch % 16 == 0)
+__global__ void __launch_bounds__(128) jpeg_color_kernel(const JpegImageDev *__restrict__ imgs) {
+    const JpegImageDev &im = imgs[blockIdx.z];
+    const int y = blockIdx.y;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (y >= im.h || x0 >= im.w) return;
+    const int dw = (im.w + im.H - 1) / im.H, dh = (im.h + im.V - 1) / im.V;
+    unsigned px[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = min(x0 + i, im.w - 1);
+        const int Y = im.plane[0][(size_t)y * im.pw[0] + x];
+        const int cb = jpeg_chroma_at(im.plane[1], im.pw[1], dw, dh, im.H, im.V, x, y) - 128;
+        const int cr = jpeg_chroma_at(im.plane[2], im.pw[2], dw, dh, im.H, im.V, x, y) - 128;
+        const int r = Y + ((91881 * cr + 32768) >> 16);                        // FIX(1.40200)
+        const int g = Y + ((-22554 * cb + 32768 + -46802 * cr) >> 16);         // -FIX(0.34414), -FIX(0.71414)
+        const int b = Y + ((116130 * cb + 32768) >> 16);                       // FIX(1.77200)
+        px[i] = (unsigned)max(0, min(255, b)) | ((unsigned)max(0, min(255, g)) << 8) | ((unsigned)max(0, min(255, r)) << 16);
+    }
+    uint8_t *row = im.bgr + (size_t)y * im.pitch;
+    if (x0 + 3 < im.w) {
+        unsigned *o = reinterpret_cast<unsigned *>(row + (size_t)x0 * 3);
+        o[0] = px[0] | (px[1] << 24);
+        o[1] = (px[1] >> 8) | (px[2] << 16);
+        o[2] = (px[2] >> 16) | (px[3] << 8);
+    } else {
+        for (int i = 0; i < 4 && x0 + i < im.w; ++i) {
+            row[(x0 + i) * 3] = (uint8_t)px[i];
+            row[(x0 + i) * 3 + 1] = (uint8_t)(px[i] >> 8);
+            row[(x0 + i) * 3 + 2] = (uint8_t)(px[i] >> 16);
+        }
+    }
+}
+
+}  // namespace fd
+
+using namespace fd;
+
+FD_EXPORT int fd_jpeg_info(const uint8_t *jpeg, size_t nbytes, int *height, int *width, int *subsampling) {
+    FD_REQUIRE(jpeg && height && width, "fd_jpeg_info: null argument");
+    JpegHeader *j = new JpegHeader();
+    const char *err = parse_jpeg(jpeg, nbytes, j);
+    if (!err) {
+        *height = j->h;
+        *width = j->w;
+        if (subsampling) *subsampling = j->hs[0] * 10 + j->vs[0];
+    }
+    delete j;
+    if (err) return fail(FD_ERR_INVALID, std::string("fd_jpeg_info: ") + err);
+    return FD_OK;
+}
+
+FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, const size_t *nbytes, int B, int n_threads, fd_frame *frames_out) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(jpegs && nbytes && frames_out && B > 0, "fd_decode_jpeg_batch: bad arguments");
+    std::vector<JpegHeader> hdr((size_t)B);
+    for (int i = 0; i < B; ++i) {
+        const char *err = parse_jpeg(jpegs[i], nbytes[i], &hdr[i]);
+        if (err) return fail(FD_ERR_INVALID, "fd_decode_jpeg_batch: image " + std::to_string(i) + ": " + err);
+    }
+    // layout: pinned + device coefficient arenas, device plane arena, device frame arena
+    std::vector<size_t> coef_off(B), plane_off(B), frame_off(B);
+    size_t coef_total = 0, plane_total = 0, frame_total = 0;
+    int max_blocks = 0, max_h = 0, max_w = 0;
+    for (int i = 0; i < B; ++i) {
+        const JpegHeader &j = hdr[i];
+        const size_t nblk = j.blocks[0] + j.blocks[1] + j.blocks[2];
+        coef_off[i] = coef_total;
+        coef_total += nblk * 64;                                   // int16 elements
+        plane_off[i] = plane_total;
+        plane_total += (nblk * 64 + 255) & ~(size_t)255;           // u8 elements (a plane byte per coefficient)
+        frame_off[i] = frame_total;
+        const size_t pitch = ((size_t)j.w * 3 + 15) & ~(size_t)15;
+        frame_total += (pitch * j.h + 255) & ~(size_t)255;
+        max_blocks = std::max<int>(max_blocks, (int)nblk);
+        max_h = std::max(max_h, j.h);
+        max_w = std::max(max_w, j.w);
+    }
+    FD_TRY(ctx->jpeg_coef_host.reserve(coef_total * sizeof(int16_t)));
+    FD_TRY(ctx->jpeg_coef.reserve(coef_total * sizeof(int16_t)));
+    FD_TRY(ctx->jpeg_planes.reserve(plane_total));
+    FD_TRY(ctx->jpeg_frames.reserve(frame_total + 256));
+    FD_TRY(ctx->jpeg_desc.reserve(sizeof(JpegImageDev) * (size_t)B));
+    FD_TRY(ctx->jpeg_desc_host.reserve(sizeof(JpegImageDev) * (size_t)B));
+    FD_CUDA(cudaEventSynchronize(ctx->ev[3]));   // the previous call's H2D copies have left the pinned staging buffers
+    int16_t *coef_host = ctx->jpeg_coef_host.as<int16_t>();
+    // 1. entropy decoding on the host: images are independent, one per worker thread
+    {
+        std::atomic<int> next(0);
+        auto work = [&]() {
+            for (int i = next.fetch_add(1); i < B; i = next.fetch_add(1)) {
+                const size_t n = (hdr[i].blocks[0] + hdr[i].blocks[1] + hdr[i].blocks[2]) * 64;
+                memset(coef_host + coef_off[i], 0, n * sizeof(int16_t));
+                huffman_decode(hdr[i], coef_host + coef_off[i]);
+            }
+        };
+        const int nt = std::max(1, std::min(B, n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+    }
+    // 2. descriptors + coefficients to the device
+    JpegImageDev *desc = ctx->jpeg_desc_host.as<JpegImageDev>();
+    for (int i = 0; i < B; ++i) {
+        const JpegHeader &j = hdr[i];
+        JpegImageDev &d = desc[i];
+        d.coef = ctx->jpeg_coef.as<int16_t>() + coef_off[i];
+        uint8_t *pl = ctx->jpeg_planes.as<uint8_t>() + plane_off[i];
+        for (int c = 0; c < 3; ++c) {
+            d.plane[c] = pl;
+            pl += j.blocks[c] * 64;
+            d.pw[c] = j.pw[c];
+            d.ph[c] = j.ph[c];
+            d.nblk[c] = (int)j.blocks[c];
+            memcpy(d.qt[c], j.qt[j.tq[c]], sizeof(d.qt[c]));
+        }
+        d.w = j.w;
+        d.h = j.h;
+        d.pitch = (j.w * 3 + 15) & ~15;
+        d.bgr = ctx->jpeg_frames.as<uint8_t>() + frame_off[i];
+        d.H = j.hs[0];
+        d.V = j.vs[0];
+        frames_out[i].data = d.bgr;
+        frames_out[i].height = j.h;
+        frames_out[i].width = j.w;
+        frames_out[i].pitch = d.pitch;
+    }
+    FD_CUDA(cudaMemcpyAsync(ctx->jpeg_desc.p, desc, sizeof(JpegImageDev) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
+    FD_CUDA(cudaMemcpyAsync(ctx->jpeg_coef.p, coef_host, coef_total * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+    FD_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+    ctx->jpeg_last_h2d = (int64_t)(coef_total * sizeof(int16_t) + sizeof(JpegImageDev) * (size_t)B);
+    // 3. IDCT, then upsampling + colour conversion
+    dim3 g1((max_blocks + IDCT_BLOCKS - 1) / IDCT_BLOCKS, B);
+    jpeg_idct_kernel<<<g1, IDCT_BLOCKS * 8, 0, ctx->stream>>>(ctx->jpeg_desc.as<JpegImageDev>());
+    FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_idct_kernel");
+    FD_REQUIRE(max_h <= 65535 && B <= 65535, "fd_decode_jpeg_batch: image too tall / batch too large for one launch");
+    dim3 g2(((max_w + 3) / 4 + 127) / 128, max_h, B);
+    jpeg_color_kernel<<<g2, 128, 0, ctx->stream>>>(ctx->jpeg_desc.as<JpegImageDev>());
+    FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_color_kernel");
+    return FD_OK;
+}
+
+FD_EXPORT int fd_imdecode(fd_ctx *ctx, const uint8_t *jpeg, size_t nbytes, uint8_t *out_bgr, int pitch) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(jpeg && out_bgr, "fd_imdecode: null argument");
+    fd_frame fr;
+    FD_TRY(fd_decode_jpeg_batch(ctx, &jpeg, &nbytes, 1, 1, &fr));
+    FD_REQUIRE(pitch >= fr.width * 3, "fd_imdecode: pitch smaller than a row");
+    FD_CUDA(cudaMemcpy2DAsync(out_bgr, (size_t)pitch, fr.data, (size_t)fr.pitch, (size_t)fr.width * 3, (size_t)fr.height, cudaMemcpyDeviceToHost,
+                              ctx->stream));
+    FD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FD_OK;
+}

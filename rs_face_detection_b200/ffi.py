@@ -88,7 +88,7 @@ SYMBOLS = [
     "fd_detect", "fd_estimate_affine_partial_2d", "fd_warp_affine", "fd_align",
     "fd_nms_device", "fd_preprocess_batch", "fd_detect_batch", "fd_detect_fetch", "fd_detect_view", "fd_detect_last_stats", "fd_align_batch",
     "fd_align_detections", "fd_crops_to_tensor", "fd_model_preprocess", "fd_detect_batch_raw", "fd_select_params_default", "fd_face_selection",
-    "fd_select_detections", "fd_align_selected", "fd_pipeline_opts_default", "fd_pipeline_host", "fd_pipeline_tensor_dev",
+    "fd_select_detections", "fd_align_selected", "fd_jpeg_info", "fd_decode_jpeg_batch", "fd_imdecode", "fd_pipeline_opts_default", "fd_pipeline_host", "fd_pipeline_tensor_dev",
 ]
 
 _lib = None
@@ -602,6 +602,27 @@ class Context:
         _chk(self.lib.fd_model_preprocess(self.handle, _ptr(img, c_u8p), img.shape[0], img.shape[1], img.strides[0], oh, ow,
                                           _ptr(mean, c_f32p), _ptr(mul, c_f32p), _ptr(out, c_f32p)))
         return out
+
+    # ---- N4: JPEG decode (utils.rs:8-52)
+    def imdecode(self, data):
+        """byte_data_to_opencv / cv::imdecode(bytes, IMREAD_UNCHANGED) for a baseline 3-component JPEG -> (h, w, 3) BGR u8 (host)"""
+        buf = np.frombuffer(bytes(data), np.uint8)
+        h, w = C.c_int(0), C.c_int(0)
+        _chk(self.lib.fd_jpeg_info(_ptr(buf, c_u8p), C.c_size_t(len(buf)), C.byref(h), C.byref(w), None))
+        out = np.empty((h.value, w.value, 3), np.uint8)
+        _chk(self.lib.fd_imdecode(self.handle, _ptr(buf, c_u8p), C.c_size_t(len(buf)), _ptr(out, c_u8p), w.value * 3))
+        return out
+
+    def decode_jpeg_batch(self, jpegs, n_threads=0):
+        """jpegs: list of bytes-like JPEG streams -> fd_frame array of device-resident BGR frames (valid until the next call)"""
+        bufs = [np.frombuffer(bytes(j), np.uint8) if not isinstance(j, np.ndarray) else j for j in jpegs]
+        B = len(bufs)
+        ptrs = (C.c_void_p * B)(*[b.ctypes.data for b in bufs])
+        lens = (C.c_size_t * B)(*[b.size for b in bufs])
+        frames = (FdFrame * B)()
+        _chk(self.lib.fd_decode_jpeg_batch(self.handle, ptrs, lens, B, int(n_threads), frames))
+        self._jpeg_keepalive = bufs
+        return frames
 
     def pipeline_host(self, frames_host, heads_host, cap_rows, conf_thr=None, iou_thr=None, want_tensor=False, bufs=None,
                       select=False, is_enroll=False, upload=FD_UPLOAD_FULL, select_params=None, heads_zero_copy=False):

@@ -1,0 +1,73 @@
+"""SURVEY 8(f) N4 — byte_data_to_opencv (utils.rs:8-52 = cv::imdecode): host Huffman pass + CUDA IDCT / upsampling / colour
+kernels, bit-exact against the cv2-generated golden vectors and the CPU oracle; decoded frames feed the detection path directly."""
+import os
+
+import numpy as np
+import pytest
+
+from rs_face_detection_b200.utils import synth
+
+pytestmark = pytest.mark.gpu
+try:
+    import cv2
+except Exception:  # pragma: no cover
+    cv2 = None
+
+
+def _golden():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jpeg_golden.npz"))
+
+
+def test_imdecode_golden_cv2(ctx):
+    g = _golden()
+    for i in range(int(g["n"])):
+        np.testing.assert_array_equal(ctx.imdecode(g["jpeg_%d" % i].tobytes()), g["bgr_%d" % i])
+
+
+def test_imdecode_unsupported_streams_are_errors(ctx):
+    from rs_face_detection_b200 import FdError
+    g = _golden()
+    for k in ("unsupported_progressive", "unsupported_gray"):
+        with pytest.raises(FdError):
+            ctx.imdecode(g[k].tobytes())
+    with pytest.raises(FdError):
+        ctx.imdecode(b"\x00\x01\x02\x03 not a jpeg")
+    with pytest.raises(FdError):
+        ctx.imdecode(g["jpeg_0"].tobytes()[:40])        # truncated before SOS
+
+
+@pytest.mark.skipif(cv2 is None, reason="cv2 not importable")
+def test_imdecode_vs_oracle_and_cv2_at_frame_size(ctx, oracle):
+    """the bench's 1080p frame and a 4K frame, 4:2:0 and 4:4:4: GPU == oracle == cv2.imdecode"""
+    for (h, w, ss, q) in [(1080, 1920, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, 90), (1080, 1920, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, 75),
+                          (2160, 3840, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, 85), (1081, 1923, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, 95)]:
+        ok, buf = cv2.imencode(".jpg", synth.make_frame(h, w, h + q), [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, ss])
+        want = cv2.imdecode(buf, cv2.IMREAD_UNCHANGED)
+        np.testing.assert_array_equal(oracle.jpeg_decode(buf.tobytes()), want)
+        np.testing.assert_array_equal(ctx.imdecode(buf.tobytes()), want)
+
+
+def test_decode_batch_feeds_the_detection_path(ctx, oracle):
+    """JPEG bytes -> device frames (mixed sizes and samplings in one batch) -> fd_preprocess_batch: same CNN input tensors as the
+    oracle's decode + letterbox + tensor path; and the frames themselves equal the oracle's decode."""
+    g = _golden()
+    idx = [0, 7, 8, 1, 9]
+    jpegs = [g["jpeg_%d" % i] for i in idx]
+    for threads in (1, 3):
+        frames = ctx.decode_jpeg_batch(jpegs, n_threads=threads)
+        B = len(idx)
+        tensor = ctx.alloc(B * 3 * 640 * 640 * 4)
+        ds = ctx.preprocess_batch(frames, tensor)
+        ctx.synchronize()
+        t = tensor.download((B, 3, 640, 640), np.float32)
+        for b, i in enumerate(idx):
+            want = g["bgr_%d" % i]
+            assert (frames[b].height, frames[b].width) == want.shape[:2]
+            row = np.empty((want.shape[0], frames[b].pitch), np.uint8)
+            import ctypes as C
+            ctx.lib.fd_memcpy_d2h(ctx.handle, row.ctypes.data_as(C.c_void_p), C.c_void_p(frames[b].data), C.c_size_t(row.nbytes))
+            np.testing.assert_array_equal(row[:, :want.shape[1] * 3].reshape(want.shape), want)
+            det_img, sc = oracle.preprocess_letterbox(want)
+            np.testing.assert_array_equal(t[b], oracle.to_tensor(det_img)[0])
+            assert ds[b] == sc
+        tensor.free()

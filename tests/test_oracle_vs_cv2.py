@@ -117,3 +117,39 @@ def test_align_fallback_vs_cv2(oracle):
     M, _ = cv2.estimateAffinePartial2D(same, oracle.ARCFACE_TEMPLATE, method=cv2.LMEDS, ransacReprojThreshold=3.0, maxIters=2000,
                                        confidence=0.99, refineIters=10)
     assert M is None and oracle.estimate_affine_partial_2d(same, oracle.ARCFACE_TEMPLATE)[0] is None
+
+
+# ---- N4: byte_data_to_opencv (utils.rs:8-52) = cv::imdecode -> the JPEG restatement of oracle/fd_jpeg_oracle.c -------------
+def _jpeg_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jpeg_golden.npz"))
+
+
+def test_jpeg_golden(oracle):
+    g = _jpeg_golden()
+    for i in range(int(g["n"])):
+        np.testing.assert_array_equal(oracle.jpeg_decode(g["jpeg_%d" % i].tobytes()), g["bgr_%d" % i])
+    for k in ("unsupported_progressive", "unsupported_gray"):
+        with pytest.raises(ValueError):
+            oracle.jpeg_decode(g[k].tobytes())
+
+
+@pytest.mark.skipif(cv2 is None, reason="cv2 not importable")
+def test_jpeg_vs_live_cv2(oracle):
+    """bit-exact against cv2.imdecode over samplings, qualities, odd sizes, restart intervals and optimised Huffman tables"""
+    SS = {"444": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, "422": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, "420": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420}
+    rng = np.random.default_rng(5)
+    n = 0
+    for (h, w) in [(480, 640), (123, 77), (17, 33), (8, 8), (3, 2), (5, 4), (9, 6), (1, 7), (31, 250)]:
+        for ss in SS.values():
+            for q in (20, 75, 92, 100):
+                img = np.clip(rng.normal(128, 50, (h, w, 3)) + np.linspace(0, 60, w)[None, :, None], 0, 255).astype(np.uint8)
+                params = [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, ss]
+                if (h + q) % 3 == 0:
+                    params += [cv2.IMWRITE_JPEG_RST_INTERVAL, 1 + (w % 4)]
+                if q == 92:
+                    params += [cv2.IMWRITE_JPEG_OPTIMIZE, 1]
+                ok, buf = cv2.imencode(".jpg", img, params)
+                np.testing.assert_array_equal(oracle.jpeg_decode(buf.tobytes()), cv2.imdecode(buf, cv2.IMREAD_UNCHANGED))
+                n += 1
+    assert n == 108
