@@ -226,14 +226,30 @@ def make_host_heads(wl, seed=3000):
 _REF_SHARED = {}
 
 
+JPEG_QUALITY = 90      # the jpeg-input variants: cv2.imencode defaults otherwise (baseline, 4:2:0, standard Huffman tables)
+
+
+def encode_jpeg(frame):
+    import cv2
+    ok, buf = cv2.imencode(".jpg", frame, [cv2.IMWRITE_JPEG_QUALITY, JPEG_QUALITY])
+    assert ok
+    return np.ascontiguousarray(np.asarray(buf, np.uint8).ravel())
+
+
 def _ref_make_frame(args):
-    wl, i = args
-    return make_host_frames(wl, [i])[0]
+    wl, i, jpeg = args
+    f = make_host_frames(wl, [i])[0]
+    return encode_jpeg(f) if jpeg else f
 
 
-def _ref_worker(wl, frames_per_step, n_steps, barrier, counter, out_q):
+def _ref_worker(wl, frames_per_step, n_steps, barrier, counter, out_q, jpeg):
     cpu = CpuPath()
     frames, per_image = _REF_SHARED["frames"], _REF_SHARED["per_image"]
+    if jpeg:
+        import cv2
+        decode = lambda b: cv2.imdecode(b, cv2.IMREAD_UNCHANGED)     # byte_data_to_opencv (utils.rs:8-52)
+    else:
+        decode = lambda f: f
     batch = len(frames)
     faces = 0
     for _ in range(n_steps):
@@ -244,27 +260,27 @@ def _ref_worker(wl, frames_per_step, n_steps, barrier, counter, out_q):
                 counter.value = i + 1
             if i >= frames_per_step:
                 break
-            faces += cpu.frame(frames[i % batch], per_image[i % batch])
+            faces += cpu.frame(decode(frames[i % batch]), per_image[i % batch])
         barrier.wait()
     out_q.put(faces)
 
 
-def run_cpu_processes(wl, nproc, frames_per_step, warmup, steps, n_distinct=None):
+def run_cpu_processes(wl, nproc, frames_per_step, warmup, steps, n_distinct=None, jpeg=False):
     """-> (seconds over `steps` steps, faces per step).  Step time = barrier to barrier in the parent."""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
     batch = WORKLOADS[wl]["batch"]
     n_distinct = min(batch, n_distinct or batch)
-    if _REF_SHARED.get("key") != (wl, n_distinct):
-        with ctx.Pool(min(nproc, n_distinct)) as pool:
-            frames = pool.map(_ref_make_frame, [(wl, i) for i in range(n_distinct)])
+    if _REF_SHARED.get("key") != (wl, n_distinct, jpeg):
+        with ctx.Pool(min(max(nproc, 4), n_distinct)) as pool:
+            frames = pool.map(_ref_make_frame, [(wl, i, jpeg) for i in range(n_distinct)])
         heads = make_host_heads(wl)
-        _REF_SHARED.update(key=(wl, n_distinct), frames=frames,
+        _REF_SHARED.update(key=(wl, n_distinct, jpeg), frames=frames,
                            per_image=[[np.ascontiguousarray(h[i]) for h in heads] for i in range(n_distinct)])
     barrier = ctx.Barrier(nproc + 1)
     counter = ctx.Value("i", 0)
     q = ctx.Queue()
-    procs = [ctx.Process(target=_ref_worker, args=(wl, frames_per_step, warmup + steps, barrier, counter, q), daemon=True) for _ in range(nproc)]
+    procs = [ctx.Process(target=_ref_worker, args=(wl, frames_per_step, warmup + steps, barrier, counter, q, jpeg), daemon=True) for _ in range(nproc)]
     for p in procs:
         p.start()
     secs = 0.0
@@ -292,11 +308,12 @@ def run_reference(args):
     rounds = max(1, -(-nproc * 4 // batch))       # keep >= 4 frames per worker per step: 64 frames/step up to 16 cores
     per_step = batch * rounds
     warm = max(1, min(args.warmup, 2))
-    secs, faces = run_cpu_processes(wl, nproc, per_step, warm, args.steps)
+    jpeg = args.input == "jpeg"
+    secs, faces = run_cpu_processes(wl, nproc, per_step, warm, args.steps, jpeg=jpeg)
     n = per_step * args.steps
     v = n / secs
     # single process on a bounded sample, for the parallel efficiency
-    s1, _ = run_cpu_processes(wl, 1, 16, 1, 1)
+    s1, _ = run_cpu_processes(wl, 1, 16, 1, 1, jpeg=jpeg)
     single = 16 / s1
     cpu = CpuPath()
     line = result_line(frames=n / max(args.gpus, 1), seconds=secs, n_gpus=max(args.gpus, 1), steps=args.steps, warmup=args.warmup, extra={}, wl=wl)
@@ -307,6 +324,8 @@ def run_reference(args):
     line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": nproc, "kind": cpu.kind,
                             "single_process_value": single, "parallel_efficiency": v / (single * nproc), "host_cores": cores,
                             "faces_per_step": faces,
+                            "input": "JPEG bytes (q%d 4:2:0): cv2.imdecode per frame first (byte_data_to_opencv, utils.rs:8-52)" % JPEG_QUALITY if jpeg
+                                     else "decoded BGR frames",
                             "sample": "%d frames/step (the %d-frame batch x %d) x %d steps, one forked process per core (%d) pulling images from a "
                                       "shared counter, step = barrier to barrier; %s" % (per_step, batch, rounds, args.steps, nproc, cpu.desc)}
     line["e2e"] = {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
@@ -315,14 +334,14 @@ def run_reference(args):
     return 0
 
 
-def cpu_baseline_subprocess(wl, steps=3):
+def cpu_baseline_subprocess(wl, steps=3, jpeg=False):
     """Runs the reference arm in a fresh interpreter (fork-per-core must not happen inside a process that holds a CUDA
     context) and returns its cpu_baseline object."""
     env = dict(os.environ)
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
     out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", "1",
-                          "--workload", wl], env=env, capture_output=True, text=True, timeout=900)
+                          "--workload", wl] + (["--input", "jpeg"] if jpeg else []), env=env, capture_output=True, text=True, timeout=900)
     for ln in reversed(out.stdout.strip().splitlines()):
         if ln.startswith("{"):
             return json.loads(ln)["cpu_baseline"]
@@ -643,6 +662,7 @@ def run_ours(args):
                               crops=pin((cap_rows, 112, 112, 3), torch.uint8), det_scale=pin((BATCH,), torch.float32),
                               align_mode=pin((cap_rows,), torch.uint8), sel=pin((BATCH, 2), torch.int32), tensor=None)
         L = max(1, args.e2e_lanes)
+        jpeg_streams = None
         e2e_steps = max(2 * L, min(args.steps, 24)) // L * L
         # L host threads, one fd_ctx each, alternate batches: the H2D of one batch overlaps the compute + D2H of the others
         e2e_ctx = [ctx] + [Context(local_rank) for _ in range(L - 1)]
@@ -653,8 +673,9 @@ def run_ours(args):
 
         def e2e_worker(i, n, kw):
             torch.cuda.set_device(local_rank)
+            src = jpeg_streams if kw.get("jpeg") else host_frames
             for _ in range(n):
-                res_e[i] = e2e_ctx[i].pipeline_host(host_frames, host_heads, cap_rows, CONF_THR, IOU_THR, bufs=e2e_bufs[i], **kw)
+                res_e[i] = e2e_ctx[i].pipeline_host(src, host_heads, cap_rows, CONF_THR, IOU_THR, bufs=e2e_bufs[i], **kw)
 
         def e2e_run(n_each, kw):
             th = [threading.Thread(target=e2e_worker, args=(i, n_each, kw)) for i in range(L)]
@@ -698,6 +719,19 @@ def run_ours(args):
                 dict(select=True, upload=FD_UPLOAD_ON_DEMAND, heads_zero_copy=True), short,
                 "FacePipeline::extract's flow (face_pipeline/pipeline.rs:196-232): detect -> FaceSelection -> align the ONE selected face per frame, "
                 "FD_UPLOAD_ON_DEMAND: preprocess rows + one face rectangle per frame cross PCIe")
+            try:       # N4: the frames arrive as JPEG bytes (FacePipeline::extract's real input); needs cv2 only to ENCODE the test streams
+                from rs_face_detection_b200.ffi import pinned_like
+                pinned_jpegs = [pinned_like(encode_jpeg(f)) for f in host_frames]
+                jpeg_streams = [p.array for p in pinned_jpegs]
+                cores = host_cores()
+                e2e_variants["jpeg_input"] = e2e_leg(
+                    dict(jpeg=True, jpeg_threads=max(1, cores // L), heads_zero_copy=True), short,
+                    "fd_pipeline_host_jpeg: q%d 4:2:0 JPEG streams in (%.2f MB/frame) -> Huffman decoding on the host (%d threads per lane; serial per "
+                    "stream by construction) -> CUDA IDCT/upsampling/colour -> the same path; h2d counts the coefficient upload"
+                    % (JPEG_QUALITY, float(np.mean([j.size for j in jpeg_streams])) / 1e6, max(1, cores // L)))
+                e2e_variants["jpeg_input"]["jpeg_bytes_per_step"] = int(sum(j.size for j in jpeg_streams))
+            except ImportError:
+                e2e_variants["jpeg_input"] = None
             e2e_variants["extract_flow_full_upload"] = e2e_leg(
                 dict(select=True, heads_zero_copy=True), short, "the extract flow with whole-frame upload, for the byte comparison")
         ctx.set_sharing(1)
@@ -769,6 +803,12 @@ def run_ours(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu_baseline = cpu_baseline_subprocess(wl)
+        if e2e_variants.get("jpeg_input"):
+            try:
+                cj = cpu_baseline_subprocess(wl, steps=2, jpeg=True)
+                e2e_variants["jpeg_input"]["cpu_reference"] = {k: cj[k] for k in ("value", "unit", "cores", "single_process_value", "input")}
+            except Exception as e:
+                e2e_variants["jpeg_input"]["cpu_reference"] = {"error": str(e)[:200]}
 
     if rank == 0:
         extra = {
@@ -807,6 +847,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--roofline-sample", type=int, default=1, help="record the per-kernel CUDA events on every n-th timed step")
     ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: worker processes (default: one per host core)")
+    ap.add_argument("--input", default="frames", choices=["frames", "jpeg"], help="reference arm: start from decoded frames or from JPEG bytes")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-variants", action="store_true")
     ap.add_argument("--e2e-lanes", type=int, default=3, help="host threads / contexts keeping batches in flight in the e2e leg")

@@ -304,6 +304,12 @@ int fd_pipeline_opts_default(fd_pipeline_opts *opts);   /* select 0, FD_UPLOAD_F
  * opts NULL = defaults.  Blocks until the outputs are in host memory. */
 int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const float *const *heads_host, int n_heads,
                      float conf_thr, float iou_thr, const fd_pipeline_opts *opts, fd_host_batch_out *out);
+/* The same with the frames given as JPEG streams — FacePipeline::extract's real input (face_pipeline/pipeline.rs:188-196,
+ * byte_data_to_opencv): fd_decode_jpeg_batch (host Huffman on n_threads threads, CUDA IDCT / upsampling / colour) on the way in,
+ * then the path above with the frames already on the device.  h2d_bytes counts the coefficient upload.  opts->upload is ignored. */
+int fd_pipeline_host_jpeg(fd_ctx *ctx, const uint8_t *const *jpegs, const size_t *nbytes, int B, int n_threads,
+                          const float *const *heads_host, int n_heads, float conf_thr, float iou_thr, const fd_pipeline_opts *opts,
+                          fd_host_batch_out *out);
 /* Device tensor written by the last fd_pipeline_host / usable as the CNN input. */
 int fd_pipeline_tensor_dev(fd_ctx *ctx, const float **out_nchw_dev);
 

@@ -736,16 +736,16 @@ FD_EXPORT int fd_pipeline_opts_default(fd_pipeline_opts *o) {
     return fd_select_params_default(&o->select_params);
 }
 
-FD_EXPORT int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const float *const *heads_host, int n_heads,
-                               float conf_thr, float iou_thr, const fd_pipeline_opts *opts, fd_host_batch_out *out) {
-    FD_TRY(check_ctx(ctx));
-    FD_REQUIRE(frames && heads_host && out && B > 0, "fd_pipeline_host: bad arguments");
+// frames: HOST pixel frames, or (dev_frames != nullptr) frames already resident on the device (fd_decode_jpeg_batch)
+static int pipeline_host_impl(fd_ctx *ctx, const fd_frame *frames, const fd_frame *dev_frames, int B, const float *const *heads_host, int n_heads,
+                              float conf_thr, float iou_thr, const fd_pipeline_opts *opts, fd_host_batch_out *out, int64_t h2d_so_far) {
+    FD_REQUIRE(heads_host && out && B > 0, "fd_pipeline_host: bad arguments");
     FD_REQUIRE(n_heads == 3 * ctx->dcfg.n_strides, "fd_pipeline_host: n_heads must be 3 * n_strides");
     FD_REQUIRE(out->counts && out->det && out->landmarks && out->crops && out->cap_rows > 0, "fd_pipeline_host: bad outputs");
     fd_pipeline_opts o;
     if (opts) o = *opts;
     else FD_TRY(fd_pipeline_opts_default(&o));
-    const bool select = o.select != 0, demand = o.upload == FD_UPLOAD_ON_DEMAND;
+    const bool select = o.select != 0, demand = o.upload == FD_UPLOAD_ON_DEMAND && !dev_frames;
     struct BlockingScope {   // sleep, do not spin, while this call waits on PCIe
         fd_ctx *c; bool prev;
         explicit BlockingScope(fd_ctx *c_) : c(c_), prev(c_->blocking_sync) { c->blocking_sync = true; }
@@ -754,10 +754,23 @@ FD_EXPORT int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const
     FD_REQUIRE(!select || out->cap_rows >= B, "fd_pipeline_host: select mode writes one crop per image (cap_rows >= B)");
     const DecodeCfg &d = ctx->dcfg;
     const int cw = ctx->cfg.crop_w, ch = ctx->cfg.crop_h;
-    int64_t h2d = 0, d2h = 0;
+    int64_t h2d = h2d_so_far, d2h = 0;
     // 1. frames H2D into one device arena (16-byte aligned rows).  FD_UPLOAD_ON_DEMAND: only the rows the letterbox resize
     //    reads now; the pixels the warps read follow after detection (step 4).
     std::vector<HostFrame> hf(B);
+    std::vector<fd_frame> dframes(B);
+    std::vector<float> ds(B);
+    if (dev_frames) {
+        for (int i = 0; i < B; ++i) {
+            dframes[i] = dev_frames[i];
+            hf[i].full = true;
+            hf[i].dpitch = dev_frames[i].pitch;
+            hf[i].off = 0;
+            FrameDev geo;
+            FD_TRY(fill_frame(ctx, dframes[i], dframes[i].data, &geo, &ds[i]));
+            if (out->det_scale) out->det_scale[i] = ds[i];
+        }
+    } else {
     size_t arena = 0;
     for (int i = 0; i < B; ++i) {
         FD_REQUIRE(frames[i].data && frames[i].height > 0 && frames[i].width > 0 && frames[i].pitch >= frames[i].width * 3,
@@ -768,8 +781,6 @@ FD_EXPORT int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const
         arena += ((size_t)hf[i].dpitch * frames[i].height + 255) & ~(size_t)255;
     }
     FD_TRY(ctx->pipe_frames.reserve(arena + 256));
-    std::vector<fd_frame> dframes(B);
-    std::vector<float> ds(B);
     for (int i = 0; i < B; ++i) {
         uint8_t *dst = ctx->pipe_frames.as<uint8_t>() + hf[i].off;
         dframes[i] = fd_frame{dst, frames[i].height, frames[i].width, hf[i].dpitch};
@@ -782,6 +793,7 @@ FD_EXPORT int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const
             FD_TRY(upload_full(ctx, frames[i], dst, hf[i].dpitch, &h2d));
             hf[i].full = true;
         }
+    }
     }
     // 2. preprocess -> CNN input tensor (stays on the device unless out->tensor is given)
     const size_t tn = (size_t)B * 3 * ctx->cfg.image_h * ctx->cfg.image_w;
@@ -943,6 +955,25 @@ FD_EXPORT int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const
     out->h2d_bytes = h2d;
     out->d2h_bytes = d2h;
     return FD_OK;
+}
+
+FD_EXPORT int fd_pipeline_host(fd_ctx *ctx, const fd_frame *frames, int B, const float *const *heads_host, int n_heads,
+                               float conf_thr, float iou_thr, const fd_pipeline_opts *opts, fd_host_batch_out *out) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(frames, "fd_pipeline_host: null frames");
+    return pipeline_host_impl(ctx, frames, nullptr, B, heads_host, n_heads, conf_thr, iou_thr, opts, out, 0);
+}
+
+// FacePipeline::extract's real input (face_pipeline/pipeline.rs:188-196): encoded image bytes.  byte_data_to_opencv (N4) on the
+// way in, then the same path with the frames already on the device — the compressed stream is all that crosses PCIe for them.
+FD_EXPORT int fd_pipeline_host_jpeg(fd_ctx *ctx, const uint8_t *const *jpegs, const size_t *nbytes, int B, int n_threads,
+                                    const float *const *heads_host, int n_heads, float conf_thr, float iou_thr, const fd_pipeline_opts *opts,
+                                    fd_host_batch_out *out) {
+    FD_TRY(check_ctx(ctx));
+    FD_REQUIRE(jpegs && nbytes && B > 0, "fd_pipeline_host_jpeg: bad arguments");
+    std::vector<fd_frame> dev((size_t)B);
+    FD_TRY(fd_decode_jpeg_batch(ctx, jpegs, nbytes, B, n_threads, dev.data()));
+    return pipeline_host_impl(ctx, nullptr, dev.data(), B, heads_host, n_heads, conf_thr, iou_thr, opts, out, ctx->jpeg_last_h2d);
 }
 
 FD_EXPORT int fd_pipeline_tensor_dev(fd_ctx *ctx, const float **out_nchw_dev) {

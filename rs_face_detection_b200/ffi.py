@@ -88,7 +88,7 @@ SYMBOLS = [
     "fd_detect", "fd_estimate_affine_partial_2d", "fd_warp_affine", "fd_align",
     "fd_nms_device", "fd_preprocess_batch", "fd_detect_batch", "fd_detect_fetch", "fd_detect_view", "fd_detect_last_stats", "fd_align_batch",
     "fd_align_detections", "fd_crops_to_tensor", "fd_model_preprocess", "fd_detect_batch_raw", "fd_select_params_default", "fd_face_selection",
-    "fd_select_detections", "fd_align_selected", "fd_jpeg_info", "fd_decode_jpeg_batch", "fd_imdecode", "fd_pipeline_opts_default", "fd_pipeline_host", "fd_pipeline_tensor_dev",
+    "fd_select_detections", "fd_align_selected", "fd_jpeg_info", "fd_decode_jpeg_batch", "fd_imdecode", "fd_pipeline_opts_default", "fd_pipeline_host", "fd_pipeline_host_jpeg", "fd_pipeline_tensor_dev",
 ]
 
 _lib = None
@@ -625,15 +625,20 @@ class Context:
         return frames
 
     def pipeline_host(self, frames_host, heads_host, cap_rows, conf_thr=None, iou_thr=None, want_tensor=False, bufs=None,
-                      select=False, is_enroll=False, upload=FD_UPLOAD_FULL, select_params=None, heads_zero_copy=False):
+                      select=False, is_enroll=False, upload=FD_UPLOAD_FULL, select_params=None, heads_zero_copy=False, jpeg=False,
+                      jpeg_threads=0):
         """frames_host: list of HxWx3 u8 arrays (host, ideally pinned); heads_host: 9 host arrays (B,C,H,W).
         select: FacePipeline::extract's flow (one selected face per image is aligned; crop b belongs to image b).
         upload: FD_UPLOAD_FULL | FD_UPLOAD_ON_DEMAND.  -> (bufs, total detections, h2d bytes, d2h bytes); bufs also
         holds "n_crops"."""
         B = len(frames_host)
-        arr = (FdFrame * B)()
-        for i, f in enumerate(frames_host):
-            arr[i].data, arr[i].height, arr[i].width, arr[i].pitch = f.ctypes.data, f.shape[0], f.shape[1], f.strides[0]
+        if jpeg:     # frames_host: list of 1-D u8 arrays holding JPEG streams (fd_pipeline_host_jpeg)
+            jp = (C.c_void_p * B)(*[f.ctypes.data for f in frames_host])
+            jl = (C.c_size_t * B)(*[f.size for f in frames_host])
+        else:
+            arr = (FdFrame * B)()
+            for i, f in enumerate(frames_host):
+                arr[i].data, arr[i].height, arr[i].width, arr[i].pitch = f.ctypes.data, f.shape[0], f.shape[1], f.strides[0]
         hp = (C.c_void_p * len(heads_host))(*[h.ctypes.data for h in heads_host])
         if bufs is None:
             bufs = dict(counts=np.empty(B, np.int32), det=np.empty((cap_rows, 5), np.float32),
@@ -655,8 +660,11 @@ class Context:
         opts.heads_zero_copy = int(bool(heads_zero_copy))
         if select_params is not None:
             opts.select_params = FdSelectParams(*select_params)
-        _chk(self.lib.fd_pipeline_host(self.handle, arr, B, hp, len(heads_host),
-                                       C.c_float(self.cfg.conf_thr if conf_thr is None else conf_thr),
-                                       C.c_float(self.cfg.iou_thr if iou_thr is None else iou_thr), C.byref(opts), C.byref(out)))
+        ct = C.c_float(self.cfg.conf_thr if conf_thr is None else conf_thr)
+        it = C.c_float(self.cfg.iou_thr if iou_thr is None else iou_thr)
+        if jpeg:
+            _chk(self.lib.fd_pipeline_host_jpeg(self.handle, jp, jl, B, int(jpeg_threads), hp, len(heads_host), ct, it, C.byref(opts), C.byref(out)))
+        else:
+            _chk(self.lib.fd_pipeline_host(self.handle, arr, B, hp, len(heads_host), ct, it, C.byref(opts), C.byref(out)))
         bufs["n_crops"] = out.n_crops
         return bufs, out.total, out.h2d_bytes, out.d2h_bytes

@@ -71,3 +71,22 @@ def test_decode_batch_feeds_the_detection_path(ctx, oracle):
             np.testing.assert_array_equal(t[b], oracle.to_tensor(det_img)[0])
             assert ds[b] == sc
         tensor.free()
+
+
+@pytest.mark.skipif(cv2 is None, reason="cv2 not importable (only to ENCODE the test streams)")
+def test_pipeline_host_jpeg_equals_pipeline_on_decoded_frames(ctx, oracle):
+    """fd_pipeline_host_jpeg(JPEG bytes) == fd_pipeline_host(cv2.imdecode of the same bytes): detections, landmarks, crops"""
+    B = 3
+    frames = [synth.make_frame(1080, 1920, 2600 + i) for i in range(B - 1)] + [synth.make_frame(720, 1280, 2650)]
+    streams = [np.asarray(cv2.imencode(".jpg", f, [cv2.IMWRITE_JPEG_QUALITY, 88])[1], np.uint8).ravel() for f in frames]
+    decoded = [cv2.imdecode(s, cv2.IMREAD_UNCHANGED) for s in streams]
+    heads, _ = synth.make_heads(B, seed=3400, n_faces=8, content_hw=(360, 640))
+    ref, total, _, _ = ctx.pipeline_host(decoded, heads, cap_rows=B * 64, conf_thr=0.7, iou_thr=0.4, want_tensor=True)
+    got, total2, h2d, _ = ctx.pipeline_host(streams, heads, cap_rows=B * 64, conf_thr=0.7, iou_thr=0.4, want_tensor=True, jpeg=True, jpeg_threads=2)
+    assert total2 == total > 0 and h2d > 0
+    for k in ("counts", "tensor", "det_scale"):
+        np.testing.assert_array_equal(got[k], ref[k])
+    for k in ("det", "lmk", "crops", "align_mode"):
+        np.testing.assert_array_equal(got[k][:total], ref[k][:total])
+    crop, _ = oracle.align_face(oracle.jpeg_decode(streams[0].tobytes()), got["lmk"][0])
+    np.testing.assert_array_equal(got["crops"][0], crop)
