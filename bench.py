@@ -229,9 +229,12 @@ _REF_SHARED = {}
 JPEG_QUALITY = 90      # the jpeg-input variants: cv2.imencode defaults otherwise (baseline, 4:2:0, standard Huffman tables)
 
 
-def encode_jpeg(frame):
+JPEG_RST_INTERVAL = 16  # MCUs per restart interval of the "jpeg-rst" variants (an ENCODER option: ~0.3 % larger files)
+
+
+def encode_jpeg(frame, rst=0):
     import cv2
-    ok, buf = cv2.imencode(".jpg", frame, [cv2.IMWRITE_JPEG_QUALITY, JPEG_QUALITY])
+    ok, buf = cv2.imencode(".jpg", frame, [cv2.IMWRITE_JPEG_QUALITY, JPEG_QUALITY] + ([cv2.IMWRITE_JPEG_RST_INTERVAL, rst] if rst else []))
     assert ok
     return np.ascontiguousarray(np.asarray(buf, np.uint8).ravel())
 
@@ -239,7 +242,7 @@ def encode_jpeg(frame):
 def _ref_make_frame(args):
     wl, i, jpeg = args
     f = make_host_frames(wl, [i])[0]
-    return encode_jpeg(f) if jpeg else f
+    return encode_jpeg(f, JPEG_RST_INTERVAL if jpeg == "jpeg-rst" else 0) if jpeg else f
 
 
 def _ref_worker(wl, frames_per_step, n_steps, barrier, counter, out_q, jpeg):
@@ -308,7 +311,7 @@ def run_reference(args):
     rounds = max(1, -(-nproc * 4 // batch))       # keep >= 4 frames per worker per step: 64 frames/step up to 16 cores
     per_step = batch * rounds
     warm = max(1, min(args.warmup, 2))
-    jpeg = args.input == "jpeg"
+    jpeg = args.input if args.input != "frames" else False
     secs, faces = run_cpu_processes(wl, nproc, per_step, warm, args.steps, jpeg=jpeg)
     n = per_step * args.steps
     v = n / secs
@@ -324,7 +327,8 @@ def run_reference(args):
     line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": nproc, "kind": cpu.kind,
                             "single_process_value": single, "parallel_efficiency": v / (single * nproc), "host_cores": cores,
                             "faces_per_step": faces,
-                            "input": "JPEG bytes (q%d 4:2:0): cv2.imdecode per frame first (byte_data_to_opencv, utils.rs:8-52)" % JPEG_QUALITY if jpeg
+                            "input": "JPEG bytes (q%d 4:2:0%s): cv2.imdecode per frame first (byte_data_to_opencv, utils.rs:8-52)"
+                                     % (JPEG_QUALITY, ", restart interval %d MCUs" % JPEG_RST_INTERVAL if jpeg == "jpeg-rst" else "") if jpeg
                                      else "decoded BGR frames",
                             "sample": "%d frames/step (the %d-frame batch x %d) x %d steps, one forked process per core (%d) pulling images from a "
                                       "shared counter, step = barrier to barrier; %s" % (per_step, batch, rounds, args.steps, nproc, cpu.desc)}
@@ -341,7 +345,7 @@ def cpu_baseline_subprocess(wl, steps=3, jpeg=False):
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
     out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", "1",
-                          "--workload", wl] + (["--input", "jpeg"] if jpeg else []), env=env, capture_output=True, text=True, timeout=900)
+                          "--workload", wl] + (["--input", jpeg] if jpeg else []), env=env, capture_output=True, text=True, timeout=900)
     for ln in reversed(out.stdout.strip().splitlines()):
         if ln.startswith("{"):
             return json.loads(ln)["cpu_baseline"]
@@ -662,7 +666,6 @@ def run_ours(args):
                               crops=pin((cap_rows, 112, 112, 3), torch.uint8), det_scale=pin((BATCH,), torch.float32),
                               align_mode=pin((cap_rows,), torch.uint8), sel=pin((BATCH, 2), torch.int32), tensor=None)
         L = max(1, args.e2e_lanes)
-        jpeg_streams = None
         e2e_steps = max(2 * L, min(args.steps, 24)) // L * L
         # L host threads, one fd_ctx each, alternate batches: the H2D of one batch overlaps the compute + D2H of the others
         e2e_ctx = [ctx] + [Context(local_rank) for _ in range(L - 1)]
@@ -673,7 +676,8 @@ def run_ours(args):
 
         def e2e_worker(i, n, kw):
             torch.cuda.set_device(local_rank)
-            src = jpeg_streams if kw.get("jpeg") else host_frames
+            kw = dict(kw)
+            src = kw.pop("streams", None) or host_frames
             for _ in range(n):
                 res_e[i] = e2e_ctx[i].pipeline_host(src, host_heads, cap_rows, CONF_THR, IOU_THR, bufs=e2e_bufs[i], **kw)
 
@@ -721,15 +725,20 @@ def run_ours(args):
                 "FD_UPLOAD_ON_DEMAND: preprocess rows + one face rectangle per frame cross PCIe")
             try:       # N4: the frames arrive as JPEG bytes (FacePipeline::extract's real input); needs cv2 only to ENCODE the test streams
                 from rs_face_detection_b200.ffi import pinned_like
-                pinned_jpegs = [pinned_like(encode_jpeg(f)) for f in host_frames]
-                jpeg_streams = [p.array for p in pinned_jpegs]
                 cores = host_cores()
-                e2e_variants["jpeg_input"] = e2e_leg(
-                    dict(jpeg=True, jpeg_threads=max(1, cores // L), heads_zero_copy=True), short,
-                    "fd_pipeline_host_jpeg: q%d 4:2:0 JPEG streams in (%.2f MB/frame) -> Huffman decoding on the host (%d threads per lane; serial per "
-                    "stream by construction) -> CUDA IDCT/upsampling/colour -> the same path; h2d counts the coefficient upload"
-                    % (JPEG_QUALITY, float(np.mean([j.size for j in jpeg_streams])) / 1e6, max(1, cores // L)))
-                e2e_variants["jpeg_input"]["jpeg_bytes_per_step"] = int(sum(j.size for j in jpeg_streams))
+                for key, rst in (("jpeg_input_rst", JPEG_RST_INTERVAL), ("jpeg_input", 0)):
+                    pinned_jpegs = [pinned_like(encode_jpeg(f, rst)) for f in host_frames]
+                    streams = [p.array for p in pinned_jpegs]
+                    e2e_variants[key] = e2e_leg(
+                        dict(jpeg=True, jpeg_threads=max(1, cores // L), heads_zero_copy=True, streams=streams), short,
+                        ("fd_pipeline_host_jpeg: q%d 4:2:0 JPEG streams in (%.2f MB/frame), " % (JPEG_QUALITY, float(np.mean([j.size for j in streams])) / 1e6)) +
+                        ("restart interval %d MCUs: the compressed streams cross PCIe and jpeg_huffman_kernel decodes one restart interval per thread"
+                         % rst if rst else
+                         "no restart markers: one serial bit stream per image, Huffman-decoded on the host (%d threads per lane), coefficients copied"
+                         % max(1, cores // L)) + " -> CUDA IDCT/upsampling/colour -> the same path; frames bit-identical to cv2.imdecode")
+                    e2e_variants[key]["jpeg_bytes_per_step"] = int(sum(j.size for j in streams))
+                    e2e_variants[key]["entropy_decode"] = e2e_ctx[0].jpeg_last_stats()
+                    del pinned_jpegs, streams
             except ImportError:
                 e2e_variants["jpeg_input"] = None
             e2e_variants["extract_flow_full_upload"] = e2e_leg(
@@ -803,12 +812,13 @@ def run_ours(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu_baseline = cpu_baseline_subprocess(wl)
-        if e2e_variants.get("jpeg_input"):
-            try:
-                cj = cpu_baseline_subprocess(wl, steps=2, jpeg=True)
-                e2e_variants["jpeg_input"]["cpu_reference"] = {k: cj[k] for k in ("value", "unit", "cores", "single_process_value", "input")}
-            except Exception as e:
-                e2e_variants["jpeg_input"]["cpu_reference"] = {"error": str(e)[:200]}
+        for key, inp in (("jpeg_input_rst", "jpeg-rst"), ("jpeg_input", "jpeg")):
+            if e2e_variants.get(key):
+                try:
+                    cj = cpu_baseline_subprocess(wl, steps=2, jpeg=inp)
+                    e2e_variants[key]["cpu_reference"] = {k: cj[k] for k in ("value", "unit", "cores", "single_process_value", "input")}
+                except Exception as e:
+                    e2e_variants[key]["cpu_reference"] = {"error": str(e)[:200]}
 
     if rank == 0:
         extra = {
@@ -847,7 +857,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--roofline-sample", type=int, default=1, help="record the per-kernel CUDA events on every n-th timed step")
     ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: worker processes (default: one per host core)")
-    ap.add_argument("--input", default="frames", choices=["frames", "jpeg"], help="reference arm: start from decoded frames or from JPEG bytes")
+    ap.add_argument("--input", default="frames", choices=["frames", "jpeg", "jpeg-rst"],
+                    help="reference arm: start from decoded frames or from JPEG bytes (jpeg-rst: streams with restart markers)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-variants", action="store_true")
     ap.add_argument("--e2e-lanes", type=int, default=3, help="host threads / contexts keeping batches in flight in the e2e leg")

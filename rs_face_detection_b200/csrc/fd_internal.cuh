@@ -124,8 +124,11 @@ struct fd_ctx {
     fd::DevBuf pipe_tensor;
     fd::DevBuf pipe_crops;
     fd::DevBuf jpeg_coef, jpeg_planes, jpeg_frames, jpeg_desc;   // fd_decode_jpeg_batch: coefficients, component planes, BGR frames
-    fd::PinnedBuf jpeg_coef_host, jpeg_desc_host;
+    fd::DevBuf jpeg_stream, jpeg_aux;      // compressed streams, Huffman + restart-interval tables (device entropy decoding)
+    fd::PinnedBuf jpeg_coef_host, jpeg_desc_host, jpeg_aux_host;
     int64_t jpeg_last_h2d = 0;
+    int jpeg_last_B = 0;
+    int jpeg_last_gpu_entropy = 0;          // images of the last batch whose Huffman stage ran on the device
     fd::DevBuf pipe_mode;        // u8[cap_rows] per-crop align mode of the host pipeline
     int last_B = 0;
     int last_out_cap = 0;

@@ -2,10 +2,14 @@
 // IMREAD_UNCHANGED)) for baseline JPEG, producing DEVICE-resident BGR frames for fd_preprocess_batch / fd_align_*.
 //
 // Split of the work:
-//   host   marker parsing and Huffman entropy decoding (ITU-T T.81 Annex F.2.2).  An entropy-coded segment is one serial
-//          bit stream — every symbol's position depends on all earlier ones and a file without restart markers has no
-//          synchronisation point — so this stage runs on the host, one image per worker thread, and emits the quantised
-//          coefficients (int16, natural order, one 64-entry block per DCT block) into pinned memory;
+//   entropy decoding (ITU-T T.81 Annex F.2.2).  An entropy-coded segment is a serial bit stream: every symbol's position
+//          depends on all earlier ones, and the only synchronisation points the format has are restart markers (DRI / RSTn).
+//          * streams WITH restart markers: the host only locates the markers (a byte scan); the compressed bytes go to the
+//            device as they are and `jpeg_huffman_kernel` decodes one restart interval per thread (Huffman lookup tables in
+//            shared memory, coefficients written straight into the device coefficient blocks) — the 1.3 MB stream of a 1080p
+//            frame is all that crosses PCIe;
+//          * streams WITHOUT restart markers (what most encoders emit by default) have no parallelism to offer: the Huffman
+//            pass runs on the host, one image per worker thread, into pinned int16 coefficient blocks that are then copied;
 //   device `jpeg_idct_kernel`: dequantisation + libjpeg's jpeg_idct_islow (jidctint.c: 13-bit constants, PASS1_BITS 2, the
 //          range-limit table with its wrap-around), 8 threads per block;
 //          `jpeg_color_kernel`: chroma upsampling (jdsample.c h2v1 / h2v2 "fancy" triangle filters with jdmainct.c's replicated
@@ -17,6 +21,7 @@
 // grayscale, CMYK streams return FD_ERR_INVALID (the reference would hand them to OpenCV).
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -53,6 +58,13 @@ struct HuffTable {
         maxcode[17] = 0x7fffffff;
         present = true;
     }
+};
+
+// Huffman tables of one image as the device decoder wants them (baseline: at most 2 DC + 2 AC tables)
+struct JpegHuffDev {
+    uint16_t look[4][1 << HUFF_LOOKAHEAD];   // [0,1] DC tables 0/1, [2,3] AC tables 0/1
+    int maxcode[4][18], mincode[4][17], valptr[4][17];
+    uint8_t vals[4][256];
 };
 
 struct JpegHeader {
@@ -234,6 +246,60 @@ struct BitReader {
     }
 };
 
+// Locates the restart intervals of an entropy-coded segment: iv = {first data byte, end (exclusive)} per interval, as offsets into
+// j.scan.  Returns false when the markers do not describe exactly ceil(MCUs / restart) intervals (then the host decodes).
+static bool scan_restart_intervals(const JpegHeader &j, std::vector<uint32_t> *iv) {
+    iv->clear();
+    if (j.restart <= 0 || j.scan_len >= 0xFFFFFFF0ull) return false;
+    const size_t want = ((size_t)j.mcux * j.mcuy + j.restart - 1) / j.restart;
+    const uint8_t *p = j.scan;
+    const size_t n = j.scan_len;
+    size_t start = 0, i = 0;
+    int expect = 0;
+    bool closed = false;
+    while (i < n) {
+        const uint8_t *ff = static_cast<const uint8_t *>(memchr(p + i, 0xFF, n - i));
+        if (!ff) break;
+        const size_t at = (size_t)(ff - p);
+        size_t k = at + 1;
+        while (k < n && p[k] == 0xFF) ++k;            // fill bytes before a marker
+        if (k >= n) break;
+        const int m = p[k];
+        if (m == 0x00 && k == at + 1) { i = k + 1; continue; }    // stuffed data byte
+        if (m >= 0xD0 && m <= 0xD7) {
+            if (m - 0xD0 != expect) return false;
+            expect = (expect + 1) & 7;
+            iv->push_back((uint32_t)start);
+            iv->push_back((uint32_t)at);
+            start = k + 1;
+            i = k + 1;
+            continue;
+        }
+        iv->push_back((uint32_t)start);               // EOI (or any other marker) ends the scan
+        iv->push_back((uint32_t)at);
+        closed = true;
+        break;
+    }
+    if (!closed) {
+        iv->push_back((uint32_t)start);
+        iv->push_back((uint32_t)n);
+    }
+    return iv->size() / 2 == want;
+}
+
+static void fill_huff_dev(const JpegHeader &j, JpegHuffDev *d) {
+    memset(d, 0, sizeof(*d));
+    for (int t = 0; t < 4; ++t) {
+        const HuffTable &h = t < 2 ? j.dc[t] : j.ac[t - 2];
+        if (!h.present) continue;
+        memcpy(d->look[t], h.look, sizeof(h.look));
+        memcpy(d->maxcode[t], h.maxcode, sizeof(h.maxcode));
+        memcpy(d->mincode[t], h.mincode, sizeof(h.mincode));
+        memcpy(d->valptr[t], h.valptr, sizeof(h.valptr));
+        memcpy(d->vals[t], h.vals, sizeof(h.vals));
+    }
+}
+
 // coef: [comp 0 blocks][comp 1 blocks][comp 2 blocks], each block 64 int16 in natural order, block (by,bx) row-major
 static void huffman_decode(const JpegHeader &j, int16_t *coef) {
     BitReader b(j.scan, j.scan_len);
@@ -277,7 +343,13 @@ static void huffman_decode(const JpegHeader &j, int16_t *coef) {
 
 // ---- device side --------------------------------------------------------------------------------------------------------
 struct JpegImageDev {
-    const int16_t *coef;       // this image's coefficient blocks (component-major)
+    int16_t *coef;             // this image's coefficient blocks (component-major)
+    // entropy decoding on the device (streams with restart markers); gpu_entropy == 0: the host filled `coef`
+    int gpu_entropy, n_intervals, restart, mcux, mcuy;
+    int td[3], ta[3];
+    const uint8_t *stream;     // entropy-coded segment
+    const uint32_t *iv;        // [n_intervals][2]: first byte / end (exclusive) of each restart interval's data, offsets into stream
+    const JpegHuffDev *huff;
     uint8_t *plane[3];         // component planes, pw x ph
     uint8_t *bgr;              // output frame
     int pw[3], ph[3];
@@ -316,6 +388,108 @@ __device__ __forceinline__ void jpeg_idct_1d(const int *v, int shift, int *o) {
     o[1] = JDESCALE(tmp11 + tmp2, shift); o[6] = JDESCALE(tmp11 - tmp2, shift);
     o[2] = JDESCALE(tmp12 + tmp1, shift); o[5] = JDESCALE(tmp12 - tmp1, shift);
     o[3] = JDESCALE(tmp13 + tmp0, shift); o[4] = JDESCALE(tmp13 - tmp0, shift);
+}
+
+
+__constant__ uint8_t c_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                     41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                     30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+struct DevBits {
+    const uint8_t *p, *end;
+    unsigned long long acc;
+    int cnt;
+    __device__ __forceinline__ void fill() {
+        while (cnt <= 56) {
+            unsigned byte = 0;
+            if (p < end) {
+                byte = *p++;
+                if (byte == 0xFF && p < end) ++p;   // inside an interval a data FF is always followed by the stuffed 00
+            }
+            acc |= (unsigned long long)byte << (56 - cnt);
+            cnt += 8;
+        }
+    }
+    __device__ __forceinline__ unsigned peek(int nb) const { return (unsigned)(acc >> (64 - nb)); }
+    __device__ __forceinline__ void drop(int nb) { acc <<= nb; cnt -= nb; }
+};
+__device__ __forceinline__ int dev_decode(DevBits &b, const JpegHuffDev &t, int slot) {   // F.2.2.3 DECODE
+    if (b.cnt < 16) b.fill();
+    const unsigned e = t.look[slot][b.peek(HUFF_LOOKAHEAD)];
+    if (e) {
+        b.drop(e >> 8);
+        return e & 0xFF;
+    }
+    int l = HUFF_LOOKAHEAD + 1;
+    int code = (int)b.peek(l);
+    while (l <= 16 && code > t.maxcode[slot][l]) {
+        ++l;
+        code = (int)b.peek(l);
+    }
+    if (l > 16) { b.drop(16); return 0; }
+    b.drop(l);
+    return t.vals[slot][t.valptr[slot][l] + code - t.mincode[slot][l]];
+}
+__device__ __forceinline__ int dev_receive_extend(DevBits &b, int s) {   // F.2.2.1 RECEIVE + EXTEND
+    if (b.cnt < s) b.fill();
+    const int v = (int)b.peek(s);
+    b.drop(s);
+    return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+}
+
+constexpr int HUFF_THREADS = 128;
+
+// grid (ceil(max intervals / 128), B): one restart interval per thread.  The coefficient arena is zeroed beforehand.
+__global__ void __launch_bounds__(HUFF_THREADS) jpeg_huffman_kernel(const JpegImageDev *__restrict__ imgs) {
+    __shared__ JpegHuffDev tab;
+    const JpegImageDev &im = imgs[blockIdx.y];
+    if (!im.gpu_entropy || blockIdx.x * HUFF_THREADS >= im.n_intervals) return;   // uniform over the CTA
+    for (int i = threadIdx.x; i < (int)(sizeof(JpegHuffDev) / 4); i += HUFF_THREADS)
+        reinterpret_cast<unsigned *>(&tab)[i] = reinterpret_cast<const unsigned *>(im.huff)[i];
+    __syncthreads();
+    const int iv = blockIdx.x * HUFF_THREADS + threadIdx.x;
+    if (iv >= im.n_intervals) return;
+    DevBits b;
+    b.p = im.stream + im.iv[2 * iv];
+    b.end = im.stream + im.iv[2 * iv + 1];
+    b.acc = 0;
+    b.cnt = 0;
+    int16_t *base[3];
+    base[0] = im.coef;
+    base[1] = base[0] + (size_t)im.nblk[0] * 64;
+    base[2] = base[1] + (size_t)im.nblk[1] * 64;
+    const int bw[3] = {im.pw[0] >> 3, im.pw[1] >> 3, im.pw[2] >> 3};
+    int pred[3] = {0, 0, 0};
+    const int mcu_end = min((iv + 1) * im.restart, im.mcux * im.mcuy);
+    for (int mcu = iv * im.restart; mcu < mcu_end; ++mcu) {
+        const int my = mcu / im.mcux, mx = mcu - my * im.mcux;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int hs = c ? 1 : im.H, vs = c ? 1 : im.V;
+            const int dslot = im.td[c], aslot = 2 + im.ta[c];
+            for (int v = 0; v < vs; ++v)
+                for (int hh = 0; hh < hs; ++hh) {
+                    int16_t *blk = base[c] + ((size_t)(my * vs + v) * bw[c] + (size_t)(mx * hs + hh)) * 64;
+                    int s = dev_decode(b, tab, dslot);
+                    if (s) pred[c] += dev_receive_extend(b, s);
+                    blk[0] = (int16_t)pred[c];
+                    for (int k = 1; k < 64;) {
+                        const int rs = dev_decode(b, tab, aslot);
+                        const int r = rs >> 4;
+                        s = rs & 15;
+                        if (s == 0) {
+                            if (r != 15) break;
+                            k += 16;
+                            continue;
+                        }
+                        k += r;
+                        if (k > 63) break;
+                        blk[c_zigzag[k]] = (int16_t)dev_receive_extend(b, s);
+                        ++k;
+                    }
+                }
+        }
+    }
 }
 
 constexpr int IDCT_BLOCKS = 32;   // DCT blocks per CTA (8 threads each)
@@ -448,10 +622,20 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
         const char *err = parse_jpeg(jpegs[i], nbytes[i], &hdr[i]);
         if (err) return fail(FD_ERR_INVALID, "fd_decode_jpeg_batch: image " + std::to_string(i) + ": " + err);
     }
-    // layout: pinned + device coefficient arenas, device plane arena, device frame arena
-    std::vector<size_t> coef_off(B), plane_off(B), frame_off(B);
-    size_t coef_total = 0, plane_total = 0, frame_total = 0;
-    int max_blocks = 0, max_h = 0, max_w = 0;
+    static const bool no_gpu_entropy = getenv("FD_JPEG_HOST_HUFFMAN") != nullptr;   // A/B switch: force the host Huffman pass
+    // which images can be entropy-decoded on the device: restart markers present and consistent, baseline table ids
+    std::vector<std::vector<uint32_t>> ivs((size_t)B);
+    std::vector<char> on_gpu((size_t)B, 0);
+    for (int i = 0; i < B; ++i) {
+        const JpegHeader &j = hdr[i];
+        bool ok = !no_gpu_entropy && j.restart > 0;
+        for (int c = 0; c < 3 && ok; ++c) ok = j.td[c] <= 1 && j.ta[c] <= 1;
+        on_gpu[i] = ok && scan_restart_intervals(j, &ivs[i]);
+    }
+    // layout: coefficient arena (device; pinned mirror for host-decoded images), plane arena, frame arena, stream / aux arenas
+    std::vector<size_t> coef_off(B), plane_off(B), frame_off(B), stream_off(B), aux_off(B);
+    size_t coef_total = 0, plane_total = 0, frame_total = 0, stream_total = 0, aux_total = 0, host_coef_total = 0;
+    int max_blocks = 0, max_h = 0, max_w = 0, max_iv = 0, n_gpu = 0;
     for (int i = 0; i < B; ++i) {
         const JpegHeader &j = hdr[i];
         const size_t nblk = j.blocks[0] + j.blocks[1] + j.blocks[2];
@@ -465,36 +649,77 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
         max_blocks = std::max<int>(max_blocks, (int)nblk);
         max_h = std::max(max_h, j.h);
         max_w = std::max(max_w, j.w);
+        if (on_gpu[i]) {
+            ++n_gpu;
+            stream_off[i] = stream_total;
+            stream_total += (j.scan_len + 15) & ~(size_t)15;
+            aux_off[i] = aux_total;
+            aux_total += ((sizeof(JpegHuffDev) + ivs[i].size() * sizeof(uint32_t)) + 15) & ~(size_t)15;
+            max_iv = std::max<int>(max_iv, (int)(ivs[i].size() / 2));
+        } else {
+            host_coef_total += nblk * 64;
+        }
     }
-    FD_TRY(ctx->jpeg_coef_host.reserve(coef_total * sizeof(int16_t)));
+    FD_TRY(ctx->jpeg_coef_host.reserve(std::max<size_t>(host_coef_total, 1) * sizeof(int16_t)));
     FD_TRY(ctx->jpeg_coef.reserve(coef_total * sizeof(int16_t)));
     FD_TRY(ctx->jpeg_planes.reserve(plane_total));
     FD_TRY(ctx->jpeg_frames.reserve(frame_total + 256));
     FD_TRY(ctx->jpeg_desc.reserve(sizeof(JpegImageDev) * (size_t)B));
     FD_TRY(ctx->jpeg_desc_host.reserve(sizeof(JpegImageDev) * (size_t)B));
+    FD_TRY(ctx->jpeg_stream.reserve(stream_total + 64));
+    FD_TRY(ctx->jpeg_aux.reserve(aux_total + 64));
+    FD_TRY(ctx->jpeg_aux_host.reserve(aux_total + 64));
     FD_CUDA(cudaEventSynchronize(ctx->ev[3]));   // the previous call's H2D copies have left the pinned staging buffers
-    int16_t *coef_host = ctx->jpeg_coef_host.as<int16_t>();
-    // 1. entropy decoding on the host: images are independent, one per worker thread
-    {
+    int64_t h2d = 0;
+    // 1a. device path: compressed streams + interval tables + Huffman tables go up as they are
+    if (n_gpu) {
+        FD_CUDA(cudaMemsetAsync(ctx->jpeg_coef.p, 0, coef_total * sizeof(int16_t), ctx->stream));   // the decoder writes non-zero coefficients only
+        unsigned char *aux = ctx->jpeg_aux_host.as<unsigned char>();
+        for (int i = 0; i < B; ++i) {
+            if (!on_gpu[i]) continue;
+            fill_huff_dev(hdr[i], reinterpret_cast<JpegHuffDev *>(aux + aux_off[i]));
+            memcpy(aux + aux_off[i] + sizeof(JpegHuffDev), ivs[i].data(), ivs[i].size() * sizeof(uint32_t));
+            FD_CUDA(cudaMemcpyAsync(ctx->jpeg_stream.as<uint8_t>() + stream_off[i], hdr[i].scan, hdr[i].scan_len, cudaMemcpyHostToDevice, ctx->stream));
+            h2d += (int64_t)hdr[i].scan_len;
+        }
+        FD_CUDA(cudaMemcpyAsync(ctx->jpeg_aux.p, aux, aux_total, cudaMemcpyHostToDevice, ctx->stream));
+        h2d += (int64_t)aux_total;
+    }
+    // 1b. host path (no restart markers): entropy decoding on the host, images are independent, one per worker thread
+    std::vector<size_t> host_off(B, 0);
+    if (n_gpu < B) {
+        int16_t *coef_host = ctx->jpeg_coef_host.as<int16_t>();
+        size_t o = 0;
+        for (int i = 0; i < B; ++i)
+            if (!on_gpu[i]) { host_off[i] = o; o += (hdr[i].blocks[0] + hdr[i].blocks[1] + hdr[i].blocks[2]) * 64; }
         std::atomic<int> next(0);
         auto work = [&]() {
             for (int i = next.fetch_add(1); i < B; i = next.fetch_add(1)) {
+                if (on_gpu[i]) continue;
                 const size_t n = (hdr[i].blocks[0] + hdr[i].blocks[1] + hdr[i].blocks[2]) * 64;
-                memset(coef_host + coef_off[i], 0, n * sizeof(int16_t));
-                huffman_decode(hdr[i], coef_host + coef_off[i]);
+                memset(coef_host + host_off[i], 0, n * sizeof(int16_t));
+                huffman_decode(hdr[i], coef_host + host_off[i]);
             }
         };
-        const int nt = std::max(1, std::min(B, n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency()));
+        const int nt = std::max(1, std::min(B - n_gpu, n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency()));
         std::vector<std::thread> pool;
         for (int t = 1; t < nt; ++t) pool.emplace_back(work);
         work();
         for (auto &t : pool) t.join();
+        for (int i = 0; i < B; ++i) {
+            if (on_gpu[i]) continue;
+            const size_t n = (hdr[i].blocks[0] + hdr[i].blocks[1] + hdr[i].blocks[2]) * 64;
+            FD_CUDA(cudaMemcpyAsync(ctx->jpeg_coef.as<int16_t>() + coef_off[i], coef_host + host_off[i], n * sizeof(int16_t), cudaMemcpyHostToDevice,
+                                    ctx->stream));
+            h2d += (int64_t)(n * sizeof(int16_t));
+        }
     }
-    // 2. descriptors + coefficients to the device
+    // 2. descriptors
     JpegImageDev *desc = ctx->jpeg_desc_host.as<JpegImageDev>();
     for (int i = 0; i < B; ++i) {
         const JpegHeader &j = hdr[i];
         JpegImageDev &d = desc[i];
+        memset(&d, 0, sizeof(d));
         d.coef = ctx->jpeg_coef.as<int16_t>() + coef_off[i];
         uint8_t *pl = ctx->jpeg_planes.as<uint8_t>() + plane_off[i];
         for (int c = 0; c < 3; ++c) {
@@ -503,6 +728,8 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
             d.pw[c] = j.pw[c];
             d.ph[c] = j.ph[c];
             d.nblk[c] = (int)j.blocks[c];
+            d.td[c] = j.td[c];
+            d.ta[c] = j.ta[c];
             memcpy(d.qt[c], j.qt[j.tq[c]], sizeof(d.qt[c]));
         }
         d.w = j.w;
@@ -511,16 +738,33 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
         d.bgr = ctx->jpeg_frames.as<uint8_t>() + frame_off[i];
         d.H = j.hs[0];
         d.V = j.vs[0];
+        d.mcux = j.mcux;
+        d.mcuy = j.mcuy;
+        d.restart = j.restart;
+        d.gpu_entropy = on_gpu[i] ? 1 : 0;
+        if (on_gpu[i]) {
+            d.n_intervals = (int)(ivs[i].size() / 2);
+            d.stream = ctx->jpeg_stream.as<uint8_t>() + stream_off[i];
+            d.huff = reinterpret_cast<const JpegHuffDev *>(ctx->jpeg_aux.as<unsigned char>() + aux_off[i]);
+            d.iv = reinterpret_cast<const uint32_t *>(ctx->jpeg_aux.as<unsigned char>() + aux_off[i] + sizeof(JpegHuffDev));
+        }
         frames_out[i].data = d.bgr;
         frames_out[i].height = j.h;
         frames_out[i].width = j.w;
         frames_out[i].pitch = d.pitch;
     }
     FD_CUDA(cudaMemcpyAsync(ctx->jpeg_desc.p, desc, sizeof(JpegImageDev) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
-    FD_CUDA(cudaMemcpyAsync(ctx->jpeg_coef.p, coef_host, coef_total * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
     FD_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
-    ctx->jpeg_last_h2d = (int64_t)(coef_total * sizeof(int16_t) + sizeof(JpegImageDev) * (size_t)B);
-    // 3. IDCT, then upsampling + colour conversion
+    h2d += (int64_t)(sizeof(JpegImageDev) * (size_t)B);
+    ctx->jpeg_last_h2d = h2d;
+    ctx->jpeg_last_gpu_entropy = n_gpu;
+    ctx->jpeg_last_B = B;
+    // 3. entropy decoding on the device (one restart interval per thread), IDCT, upsampling + colour conversion
+    if (n_gpu) {
+        dim3 g0((max_iv + HUFF_THREADS - 1) / HUFF_THREADS, B);
+        jpeg_huffman_kernel<<<g0, HUFF_THREADS, 0, ctx->stream>>>(ctx->jpeg_desc.as<JpegImageDev>());
+        FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_huffman_kernel");
+    }
     dim3 g1((max_blocks + IDCT_BLOCKS - 1) / IDCT_BLOCKS, B);
     jpeg_idct_kernel<<<g1, IDCT_BLOCKS * 8, 0, ctx->stream>>>(ctx->jpeg_desc.as<JpegImageDev>());
     FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_idct_kernel");
@@ -528,6 +772,15 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
     dim3 g2(((max_w + 3) / 4 + 127) / 128, max_h, B);
     jpeg_color_kernel<<<g2, 128, 0, ctx->stream>>>(ctx->jpeg_desc.as<JpegImageDev>());
     FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_color_kernel");
+    return FD_OK;
+}
+
+FD_EXPORT int fd_jpeg_last_stats(const fd_ctx *ctx, int64_t *out) {
+    FD_REQUIRE(ctx && out, "fd_jpeg_last_stats: null");
+    out[0] = ctx->jpeg_last_h2d;
+    out[1] = ctx->jpeg_last_gpu_entropy;
+    out[2] = ctx->jpeg_last_B - ctx->jpeg_last_gpu_entropy;
+    out[3] = 0;
     return FD_OK;
 }
 

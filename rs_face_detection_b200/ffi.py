@@ -88,7 +88,7 @@ SYMBOLS = [
     "fd_detect", "fd_estimate_affine_partial_2d", "fd_warp_affine", "fd_align",
     "fd_nms_device", "fd_preprocess_batch", "fd_detect_batch", "fd_detect_fetch", "fd_detect_view", "fd_detect_last_stats", "fd_align_batch",
     "fd_align_detections", "fd_crops_to_tensor", "fd_model_preprocess", "fd_detect_batch_raw", "fd_select_params_default", "fd_face_selection",
-    "fd_select_detections", "fd_align_selected", "fd_jpeg_info", "fd_decode_jpeg_batch", "fd_imdecode", "fd_pipeline_opts_default", "fd_pipeline_host", "fd_pipeline_host_jpeg", "fd_pipeline_tensor_dev",
+    "fd_select_detections", "fd_align_selected", "fd_jpeg_info", "fd_decode_jpeg_batch", "fd_jpeg_last_stats", "fd_imdecode", "fd_pipeline_opts_default", "fd_pipeline_host", "fd_pipeline_host_jpeg", "fd_pipeline_tensor_dev",
 ]
 
 _lib = None
@@ -612,6 +612,11 @@ class Context:
         out = np.empty((h.value, w.value, 3), np.uint8)
         _chk(self.lib.fd_imdecode(self.handle, _ptr(buf, c_u8p), C.c_size_t(len(buf)), _ptr(out, c_u8p), w.value * 3))
         return out
+
+    def jpeg_last_stats(self):
+        out = (C.c_int64 * 4)()
+        _chk(self.lib.fd_jpeg_last_stats(self.handle, out))
+        return dict(h2d_bytes=int(out[0]), device_entropy_images=int(out[1]), host_entropy_images=int(out[2]))
 
     def decode_jpeg_batch(self, jpegs, n_threads=0):
         """jpegs: list of bytes-like JPEG streams -> fd_frame array of device-resident BGR frames (valid until the next call)"""

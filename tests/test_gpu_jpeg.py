@@ -90,3 +90,34 @@ def test_pipeline_host_jpeg_equals_pipeline_on_decoded_frames(ctx, oracle):
         np.testing.assert_array_equal(got[k][:total], ref[k][:total])
     crop, _ = oracle.align_face(oracle.jpeg_decode(streams[0].tobytes()), got["lmk"][0])
     np.testing.assert_array_equal(got["crops"][0], crop)
+
+
+@pytest.mark.skipif(cv2 is None, reason="cv2 not importable (only to ENCODE the test streams)")
+def test_restart_marker_streams_are_huffman_decoded_on_the_device(ctx):
+    """Streams with DRI/RSTn take jpeg_huffman_kernel (one restart interval per thread; only the compressed bytes cross PCIe);
+    streams without take the host pass.  Both in one batch, every frame bit-identical to cv2.imdecode."""
+    import ctypes as C
+    SS = [cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]
+    cases = [(1080, 1920, 0, 16, 90), (1080, 1920, 0, 0, 90), (720, 1280, 1, 1, 75), (333, 517, 2, 7, 95), (2160, 3840, 0, 240, 85),
+             (64, 48, 0, 1000, 60), (17, 33, 0, 2, 100), (480, 640, 0, 40, 30)]
+    streams, want = [], []
+    for i, (h, w, ss, rst, q) in enumerate(cases):
+        params = [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, SS[ss]]
+        if rst:
+            params += [cv2.IMWRITE_JPEG_RST_INTERVAL, rst]
+        if i == 3:
+            params += [cv2.IMWRITE_JPEG_OPTIMIZE, 1]
+        buf = np.asarray(cv2.imencode(".jpg", synth.make_frame(h, w, 900 + i), params)[1], np.uint8).ravel()
+        streams.append(buf)
+        want.append(cv2.imdecode(buf, cv2.IMREAD_UNCHANGED))
+    frames = ctx.decode_jpeg_batch(streams, n_threads=2)
+    ctx.synchronize()
+    st = ctx.jpeg_last_stats()
+    assert st["device_entropy_images"] == sum(1 for c in cases if c[3]) and st["host_entropy_images"] == 1
+    assert st["h2d_bytes"] < sum(s.size for s in streams) + 6.5e6 + 1e6       # compressed streams + ONE frame's coefficients
+    for b, w_ in enumerate(want):
+        row = np.empty((w_.shape[0], frames[b].pitch), np.uint8)
+        ctx.lib.fd_memcpy_d2h(ctx.handle, row.ctypes.data_as(C.c_void_p), C.c_void_p(frames[b].data), C.c_size_t(row.nbytes))
+        np.testing.assert_array_equal(row[:, :w_.shape[1] * 3].reshape(w_.shape), w_, err_msg="case %d %r" % (b, cases[b]))
+    for s_, w_ in zip(streams[:3], want[:3]):                                  # and through the single-image call
+        np.testing.assert_array_equal(ctx.imdecode(s_.tobytes()), w_)
