@@ -21,8 +21,11 @@
 // grayscale, CMYK streams return FD_ERR_INVALID (the reference would hand them to OpenCV).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <thread>
 #include <vector>
 #include "fd_internal.cuh"
@@ -39,6 +42,7 @@ struct HuffTable {
     bool present = false;
     uint8_t bits[17] = {0}, vals[256] = {0};
     int maxcode[18], mincode[17], valptr[17];
+    unsigned maxleft[17];                 // first 16-bit left-aligned code value that is LONGER than l bits (non-decreasing in l)
     uint16_t look[1 << HUFF_LOOKAHEAD];   // (length << 8) | symbol for codes of <= HUFF_LOOKAHEAD bits, 0 = longer code
     void build() {
         int code = 0, k = 0;
@@ -53,8 +57,10 @@ struct HuffTable {
                 }
             }
             maxcode[l] = bits[l] ? code - 1 : -1;
+            maxleft[l] = (unsigned)code << (16 - l);
             code <<= 1;
         }
+        maxleft[0] = 0;
         maxcode[17] = 0x7fffffff;
         present = true;
     }
@@ -63,7 +69,8 @@ struct HuffTable {
 // Huffman tables of one image as the device decoder wants them (baseline: at most 2 DC + 2 AC tables)
 struct JpegHuffDev {
     uint16_t look[4][1 << HUFF_LOOKAHEAD];   // [0,1] DC tables 0/1, [2,3] AC tables 0/1
-    int maxcode[4][18], mincode[4][17], valptr[4][17];
+    int mincode[4][17], valptr[4][17];
+    unsigned maxleft[4][17];
     uint8_t vals[4][256];
 };
 
@@ -293,7 +300,7 @@ static void fill_huff_dev(const JpegHeader &j, JpegHuffDev *d) {
         const HuffTable &h = t < 2 ? j.dc[t] : j.ac[t - 2];
         if (!h.present) continue;
         memcpy(d->look[t], h.look, sizeof(h.look));
-        memcpy(d->maxcode[t], h.maxcode, sizeof(h.maxcode));
+        memcpy(d->maxleft[t], h.maxleft, sizeof(h.maxleft));
         memcpy(d->mincode[t], h.mincode, sizeof(h.mincode));
         memcpy(d->valptr[t], h.valptr, sizeof(h.valptr));
         memcpy(d->vals[t], h.vals, sizeof(h.vals));
@@ -395,99 +402,144 @@ __constant__ uint8_t c_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32,
                                      41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                                      30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
-struct DevBits {
-    const uint8_t *p, *end;
-    unsigned long long acc;
-    int cnt;
-    __device__ __forceinline__ void fill() {
-        while (cnt <= 56) {
-            unsigned byte = 0;
-            if (p < end) {
-                byte = *p++;
-                if (byte == 0xFF && p < end) ++p;   // inside an interval a data FF is always followed by the stuffed 00
-            }
-            acc |= (unsigned long long)byte << (56 - cnt);
-            cnt += 8;
-        }
-    }
-    __device__ __forceinline__ unsigned peek(int nb) const { return (unsigned)(acc >> (64 - nb)); }
-    __device__ __forceinline__ void drop(int nb) { acc <<= nb; cnt -= nb; }
-};
-__device__ __forceinline__ int dev_decode(DevBits &b, const JpegHuffDev &t, int slot) {   // F.2.2.3 DECODE
-    if (b.cnt < 16) b.fill();
-    const unsigned e = t.look[slot][b.peek(HUFF_LOOKAHEAD)];
-    if (e) {
-        b.drop(e >> 8);
-        return e & 0xFF;
-    }
-    int l = HUFF_LOOKAHEAD + 1;
-    int code = (int)b.peek(l);
-    while (l <= 16 && code > t.maxcode[slot][l]) {
-        ++l;
-        code = (int)b.peek(l);
-    }
-    if (l > 16) { b.drop(16); return 0; }
-    b.drop(l);
-    return t.vals[slot][t.valptr[slot][l] + code - t.mincode[slot][l]];
-}
-__device__ __forceinline__ int dev_receive_extend(DevBits &b, int s) {   // F.2.2.1 RECEIVE + EXTEND
-    if (b.cnt < s) b.fill();
-    const int v = (int)b.peek(s);
-    b.drop(s);
-    return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
-}
+constexpr int HUFF_THREADS = 64;
 
-constexpr int HUFF_THREADS = 128;
-
-// grid (ceil(max intervals / 128), B): one restart interval per thread.  The coefficient arena is zeroed beforehand.
+// grid (ceil(max intervals / 64), B): one restart interval per thread.  The coefficient arena is zeroed beforehand.
+//
+// The decode is ONE flat loop that consumes exactly one Huffman symbol per lane per iteration (DC or AC, decided by the lane's
+// own position k in its block): the 32 lanes of a warp sit at unrelated points of 32 different bit streams, and a nested
+// MCU / block / coefficient loop nest would leave them in different loop levels — i.e. serialised.  In the flat form every lane
+// runs the same instructions with predicated updates of k / block / MCU, so the warp stays converged until its lanes run out
+// of MCUs.  Codes longer than the lookahead are resolved without a loop (count of the left-aligned length boundaries the
+// 16-bit prefix has passed); the refill appends an aligned 32-bit word when none of its bytes is 0xFF (a data FF is followed by
+// a stuffed 00 that must be dropped: ~1.6 % of the words) and goes byte by byte otherwise; block pointers advance by
+// per-image constants.  What is left to diverge: the FF words, the block advance (~1 iteration in 35 per lane) and the tail.
 __global__ void __launch_bounds__(HUFF_THREADS) jpeg_huffman_kernel(const JpegImageDev *__restrict__ imgs) {
     __shared__ JpegHuffDev tab;
+    __shared__ uint8_t zz[64];
     const JpegImageDev &im = imgs[blockIdx.y];
     if (!im.gpu_entropy || blockIdx.x * HUFF_THREADS >= im.n_intervals) return;   // uniform over the CTA
     for (int i = threadIdx.x; i < (int)(sizeof(JpegHuffDev) / 4); i += HUFF_THREADS)
-        reinterpret_cast<unsigned *>(&tab)[i] = reinterpret_cast<const unsigned *>(im.huff)[i];
+        reinterpret_cast<unsigned *>(&tab)[i] = __ldg(reinterpret_cast<const unsigned *>(im.huff) + i);
+    if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
     __syncthreads();
+    const uint16_t *look = &tab.look[0][0];
     const int iv = blockIdx.x * HUFF_THREADS + threadIdx.x;
-    if (iv >= im.n_intervals) return;
-    DevBits b;
-    b.p = im.stream + im.iv[2 * iv];
-    b.end = im.stream + im.iv[2 * iv + 1];
-    b.acc = 0;
-    b.cnt = 0;
-    int16_t *base[3];
-    base[0] = im.coef;
-    base[1] = base[0] + (size_t)im.nblk[0] * 64;
-    base[2] = base[1] + (size_t)im.nblk[1] * 64;
-    const int bw[3] = {im.pw[0] >> 3, im.pw[1] >> 3, im.pw[2] >> 3};
-    int pred[3] = {0, 0, 0};
-    const int mcu_end = min((iv + 1) * im.restart, im.mcux * im.mcuy);
-    for (int mcu = iv * im.restart; mcu < mcu_end; ++mcu) {
-        const int my = mcu / im.mcux, mx = mcu - my * im.mcux;
+    const bool live = iv < im.n_intervals;
+    // The interval's bytes are consumed as ALIGNED 32-bit words, each loaded one refill ahead of its use (`wnext`), so the load's
+    // latency (DRAM: the stream has just arrived over PCIe) overlaps the ~4 symbols decoded in between.  `lo`/`hi`: the first and
+    // one-past-last byte address of the interval; bytes of a word outside [lo, hi) are ignored.
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(im.stream) + (live ? im.iv[2 * iv] : 0u);
+    const uintptr_t hi = reinterpret_cast<uintptr_t>(im.stream) + (live ? im.iv[2 * iv + 1] : 0u);
+    uintptr_t ap = lo & ~(uintptr_t)3;                                  // address of the word in wnext
+    unsigned wnext = ap < hi ? *reinterpret_cast<const unsigned *>(ap) : 0u;
+    bool ffpending = false;                                            // the previous byte was a data FF: the next one is its stuffed 00
+    unsigned long long acc = 0;
+    int cnt = 0;
+    const int H = im.H, V = im.V, HV = H * V, mcux = im.mcux, restart = im.restart;
+    const int bw0 = im.pw[0] >> 3;
+    const int ds0 = im.td[0] << HUFF_LOOKAHEAD, ds1 = im.td[1] << HUFF_LOOKAHEAD, ds2 = im.td[2] << HUFF_LOOKAHEAD;
+    const int as0 = (2 + im.ta[0]) << HUFF_LOOKAHEAD, as1 = (2 + im.ta[1]) << HUFF_LOOKAHEAD, as2 = (2 + im.ta[2]) << HUFF_LOOKAHEAD;
+    int pred0 = 0, pred1 = 0, pred2 = 0;
+    const int mcu_end = live ? min((iv + 1) * restart, mcux * im.mcuy) : 0;
+    int mcu = live ? iv * restart : 0;
+    int mx = mcu % mcux;
+    const int my0 = mcu / mcux;
+    // block pointers of the current MCU: luma top-left block, Cb block, Cr block
+    int16_t *by = im.coef + ((size_t)(my0 * V) * bw0 + (size_t)(mx * H)) * 64;
+    int16_t *bcb = im.coef + ((size_t)im.nblk[0] + (size_t)my0 * (im.pw[1] >> 3) + mx) * 64;
+    int16_t *bcr = bcb + (size_t)im.nblk[1] * 64;
+    const int row_step_y = (V * bw0 - mcux * H) * 64;        // luma pointer: from the end of an MCU row to the start of the next
+    const int luma_row = bw0 * 64;                            // one block row down inside the MCU
+    int q = 0, k = 0;               // block within the MCU (scan order: HV luma blocks, Cb, Cr), next coefficient (0 = DC)
+    bool active = mcu < mcu_end;
+    int16_t *blk = by;
+    int dslot = ds0, aslot = as0, comp = 0;
+    while (__any_sync(0xffffffffu, active)) {
+        if (active) {
+            // ---- refill: >= 33 valid bits afterwards = one code (<= 16) + one value (<= 15) ----
+            while (cnt <= 32) {
+                const unsigned w = wnext;
+                const uintptr_t wa = ap;
+                ap += 4;
+                wnext = ap < hi ? *reinterpret_cast<const unsigned *>(ap) : 0u;      // needed one refill from now
+                const unsigned inv = ~w;                                               // a byte of w is FF  <=>  that byte of ~w is 00
+                if (wa >= lo && wa + 4 <= hi && !ffpending && ((inv - 0x01010101u) & ~inv & 0x80808080u) == 0) {
+                    acc |= (unsigned long long)__byte_perm(w, 0, 0x0123) << (32 - cnt);
+                    cnt += 32;
+                } else if (wa >= hi) {
+                    cnt += 32;                                                         // past the interval: zero bits
+                } else {                                                               // an FF, or the interval's first / last word
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const int hs = c ? 1 : im.H, vs = c ? 1 : im.V;
-            const int dslot = im.td[c], aslot = 2 + im.ta[c];
-            for (int v = 0; v < vs; ++v)
-                for (int hh = 0; hh < hs; ++hh) {
-                    int16_t *blk = base[c] + ((size_t)(my * vs + v) * bw[c] + (size_t)(mx * hs + hh)) * 64;
-                    int s = dev_decode(b, tab, dslot);
-                    if (s) pred[c] += dev_receive_extend(b, s);
-                    blk[0] = (int16_t)pred[c];
-                    for (int k = 1; k < 64;) {
-                        const int rs = dev_decode(b, tab, aslot);
-                        const int r = rs >> 4;
-                        s = rs & 15;
-                        if (s == 0) {
-                            if (r != 15) break;
-                            k += 16;
-                            continue;
-                        }
-                        k += r;
-                        if (k > 63) break;
-                        blk[c_zigzag[k]] = (int16_t)dev_receive_extend(b, s);
-                        ++k;
+                    for (int i = 0; i < 4; ++i) {
+                        const unsigned byte = (w >> (8 * i)) & 0xFFu;
+                        if (wa + i < lo || wa + i >= hi) continue;
+                        if (ffpending) { ffpending = false; continue; }               // the stuffed 00 after a data FF
+                        acc |= (unsigned long long)byte << (56 - cnt);
+                        cnt += 8;
+                        ffpending = byte == 0xFFu;
                     }
                 }
+            }
+            // ---- one symbol ----
+            const bool dc = k == 0;
+            const int slot = dc ? dslot : aslot;
+            const unsigned top16 = (unsigned)(acc >> 48);
+            const unsigned e = look[slot + (top16 >> (16 - HUFF_LOOKAHEAD))];
+            int len = (int)(e >> 8), sym = (int)(e & 0xFF);
+            if (!e) {                                                  // F.2.2.3 DECODE beyond the lookahead, without a loop
+                const int t = slot >> HUFF_LOOKAHEAD;
+                len = HUFF_LOOKAHEAD + 1;
+#pragma unroll
+                for (int l = HUFF_LOOKAHEAD + 1; l <= 16; ++l) len += top16 >= tab.maxleft[t][l] ? 1 : 0;
+                if (len > 16) { len = 16; sym = 0; }
+                else sym = tab.vals[t][tab.valptr[t][len] + (int)(top16 >> (16 - len)) - tab.mincode[t][len]];
+            }
+            acc <<= len;
+            cnt -= len;
+            const int s = dc ? sym : (sym & 15), r = dc ? 0 : (sym >> 4);
+            int val = 0;
+            if (s) {                                                   // F.2.2.1 RECEIVE + EXTEND
+                const int v = (int)(acc >> (64 - s));
+                acc <<= s;
+                cnt -= s;
+                val = v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+            }
+            // ---- where it goes ----
+            int kk = k + r;                                            // AC: position of this coefficient
+            if (dc) {
+                const int pred = (comp == 0 ? pred0 : (comp == 1 ? pred1 : pred2)) + val;
+                pred0 = comp == 0 ? pred : pred0;
+                pred1 = comp == 1 ? pred : pred1;
+                pred2 = comp == 2 ? pred : pred2;
+                val = pred;
+                kk = 0;
+            }
+            if ((dc || s) && kk < 64) blk[dc ? 0 : zz[kk]] = (int16_t)val;
+            k = dc ? 1 : (s ? kk + 1 : (r == 15 ? k + 16 : 64));       // DC / coefficient / ZRL / EOB
+            if (k >= 64) {                                             // next block of the scan
+                k = 0;
+                ++q;
+                if (q == HV + 2) {                                     // next MCU
+                    q = 0;
+                    ++mcu;
+                    by += H * 64;
+                    bcb += 64;
+                    bcr += 64;
+                    if (++mx == mcux) { mx = 0; by += row_step_y; }
+                    active = mcu < mcu_end;
+                }
+                if (q < HV) {
+                    blk = by + (q >= H ? luma_row : 0) + (q & (H - 1)) * 64;     // H, V in {1, 2}: q = v * H + h
+                    dslot = ds0; aslot = as0; comp = 0;
+                } else if (q == HV) {
+                    blk = bcb;
+                    dslot = ds1; aslot = as1; comp = 1;
+                } else {
+                    blk = bcr;
+                    dslot = ds2; aslot = as2; comp = 2;
+                }
+            }
         }
     }
 }
@@ -617,21 +669,41 @@ FD_EXPORT int fd_jpeg_info(const uint8_t *jpeg, size_t nbytes, int *height, int 
 FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, const size_t *nbytes, int B, int n_threads, fd_frame *frames_out) {
     FD_TRY(check_ctx(ctx));
     FD_REQUIRE(jpegs && nbytes && frames_out && B > 0, "fd_decode_jpeg_batch: bad arguments");
-    std::vector<JpegHeader> hdr((size_t)B);
-    for (int i = 0; i < B; ++i) {
-        const char *err = parse_jpeg(jpegs[i], nbytes[i], &hdr[i]);
-        if (err) return fail(FD_ERR_INVALID, "fd_decode_jpeg_batch: image " + std::to_string(i) + ": " + err);
-    }
+    static const bool dbg = getenv("FD_JPEG_DBG") != nullptr;   // host-phase timeline on stderr
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_parse = 0, t_wait = 0, t_copies = 0;
+    const int hw_threads = std::max(1, n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency());
+    // runs fn(i) for i in [0, B) on up to hw_threads threads of the calling process (images are independent)
+    auto parallel_images = [&](int limit, const std::function<void(int)> &fn) {
+        std::atomic<int> next(0);
+        auto work = [&]() {
+            for (int i = next.fetch_add(1); i < B; i = next.fetch_add(1)) fn(i);
+        };
+        const int nt = std::max(1, std::min(limit, hw_threads));
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+    };
     static const bool no_gpu_entropy = getenv("FD_JPEG_HOST_HUFFMAN") != nullptr;   // A/B switch: force the host Huffman pass
-    // which images can be entropy-decoded on the device: restart markers present and consistent, baseline table ids
+    // 0. headers, Huffman tables and (streams with restart markers) the restart-interval table: host parsing, one image per thread.
+    //    An image can be entropy-decoded on the device when its markers are present and consistent and it uses baseline table ids.
+    std::vector<JpegHeader> hdr((size_t)B);
+    std::vector<const char *> errs((size_t)B, nullptr);
     std::vector<std::vector<uint32_t>> ivs((size_t)B);
     std::vector<char> on_gpu((size_t)B, 0);
-    for (int i = 0; i < B; ++i) {
+    parallel_images(B, [&](int i) {
+        errs[i] = parse_jpeg(jpegs[i], nbytes[i], &hdr[i]);
+        if (errs[i]) return;
         const JpegHeader &j = hdr[i];
         bool ok = !no_gpu_entropy && j.restart > 0;
         for (int c = 0; c < 3 && ok; ++c) ok = j.td[c] <= 1 && j.ta[c] <= 1;
         on_gpu[i] = ok && scan_restart_intervals(j, &ivs[i]);
-    }
+    });
+    for (int i = 0; i < B; ++i)
+        if (errs[i]) return fail(FD_ERR_INVALID, "fd_decode_jpeg_batch: image " + std::to_string(i) + ": " + errs[i]);
+    t_parse = now();
     // layout: coefficient arena (device; pinned mirror for host-decoded images), plane arena, frame arena, stream / aux arenas
     std::vector<size_t> coef_off(B), plane_off(B), frame_off(B), stream_off(B), aux_off(B);
     size_t coef_total = 0, plane_total = 0, frame_total = 0, stream_total = 0, aux_total = 0, host_coef_total = 0;
@@ -669,11 +741,14 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
     FD_TRY(ctx->jpeg_stream.reserve(stream_total + 64));
     FD_TRY(ctx->jpeg_aux.reserve(aux_total + 64));
     FD_TRY(ctx->jpeg_aux_host.reserve(aux_total + 64));
+    const double t_layout = now();
     FD_CUDA(cudaEventSynchronize(ctx->ev[3]));   // the previous call's H2D copies have left the pinned staging buffers
+    t_wait = now();
     int64_t h2d = 0;
     // 1a. device path: compressed streams + interval tables + Huffman tables go up as they are
     if (n_gpu) {
         FD_CUDA(cudaMemsetAsync(ctx->jpeg_coef.p, 0, coef_total * sizeof(int16_t), ctx->stream));   // the decoder writes non-zero coefficients only
+        if (ctx->trace_on) trace_mark(ctx, __FILE__, __LINE__, "jpeg_memset_coefficients");
         unsigned char *aux = ctx->jpeg_aux_host.as<unsigned char>();
         for (int i = 0; i < B; ++i) {
             if (!on_gpu[i]) continue;
@@ -692,20 +767,12 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
         size_t o = 0;
         for (int i = 0; i < B; ++i)
             if (!on_gpu[i]) { host_off[i] = o; o += (hdr[i].blocks[0] + hdr[i].blocks[1] + hdr[i].blocks[2]) * 64; }
-        std::atomic<int> next(0);
-        auto work = [&]() {
-            for (int i = next.fetch_add(1); i < B; i = next.fetch_add(1)) {
-                if (on_gpu[i]) continue;
-                const size_t n = (hdr[i].blocks[0] + hdr[i].blocks[1] + hdr[i].blocks[2]) * 64;
-                memset(coef_host + host_off[i], 0, n * sizeof(int16_t));
-                huffman_decode(hdr[i], coef_host + host_off[i]);
-            }
-        };
-        const int nt = std::max(1, std::min(B - n_gpu, n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency()));
-        std::vector<std::thread> pool;
-        for (int t = 1; t < nt; ++t) pool.emplace_back(work);
-        work();
-        for (auto &t : pool) t.join();
+        parallel_images(B - n_gpu, [&](int i) {
+            if (on_gpu[i]) return;
+            const size_t n = (hdr[i].blocks[0] + hdr[i].blocks[1] + hdr[i].blocks[2]) * 64;
+            memset(coef_host + host_off[i], 0, n * sizeof(int16_t));
+            huffman_decode(hdr[i], coef_host + host_off[i]);
+        });
         for (int i = 0; i < B; ++i) {
             if (on_gpu[i]) continue;
             const size_t n = (hdr[i].blocks[0] + hdr[i].blocks[1] + hdr[i].blocks[2]) * 64;
@@ -714,6 +781,8 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
             h2d += (int64_t)(n * sizeof(int16_t));
         }
     }
+    if (ctx->trace_on) trace_mark(ctx, __FILE__, __LINE__, "jpeg_h2d_copies");
+    t_copies = now();
     // 2. descriptors
     JpegImageDev *desc = ctx->jpeg_desc_host.as<JpegImageDev>();
     for (int i = 0; i < B; ++i) {
@@ -772,6 +841,10 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
     dim3 g2(((max_w + 3) / 4 + 127) / 128, max_h, B);
     jpeg_color_kernel<<<g2, 128, 0, ctx->stream>>>(ctx->jpeg_desc.as<JpegImageDev>());
     FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_color_kernel");
+    if (dbg)
+        fprintf(stderr, "[jpeg dbg] B=%d on-device entropy %d: parse+scan %.2f ms, layout %.2f, wait prev copies %.2f, enqueue copies (+host huffman) %.2f, "
+                        "descriptors+launches %.2f, total host %.2f ms\n", B, n_gpu, t_parse - t_begin, t_layout - t_parse, t_wait - t_layout,
+                t_copies - t_wait, now() - t_copies, now() - t_begin);
     return FD_OK;
 }
 
