@@ -13,6 +13,9 @@ pub mod rcnn {
     pub mod cpu_nms;
     pub mod gpu_nms;         // the binding the reference left commented out
 }
+pub mod utils {
+    pub mod utils;           // byte_data_to_opencv (src/utils/utils.rs:8-52); the reference's body stays as utils_opencv
+}
 pub mod pipeline {
     pub mod module {
         pub mod face_detection;

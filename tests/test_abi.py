@@ -183,6 +183,7 @@ REFERENCE_SIGNATURES = {   # file under rust/src -> signatures that must appear 
         "pub fn call(&self, img: &Mat, face_boxes: Array2<f32>, key_points: Option<Array3<f32>>, is_enroll: Option<bool>, _is_debug: Option<bool>) "
         "-> Result<(Option<Array1<f32>>, Option<Array2<f32>>), Error>"],                                                   # :72
     "pipeline/module/face_detection.rs": ["-> Result<(Array2<f32>, Option<Array3<f32>>), Error>"],                         # :496
+    "utils/utils.rs": ["pub fn byte_data_to_opencv(im_bytes: &[u8]) -> Result<Mat, Error>"],                              # utils.rs:8
 }
 
 

@@ -24,6 +24,12 @@ def test_imdecode_golden_cv2(ctx):
         np.testing.assert_array_equal(ctx.imdecode(g["jpeg_%d" % i].tobytes()), g["bgr_%d" % i])
 
 
+def test_byte_data_to_opencv_mirror(ctx):
+    from rs_face_detection_b200.utils.utils import byte_data_to_opencv
+    g = _golden()
+    np.testing.assert_array_equal(byte_data_to_opencv(g["jpeg_7"].tobytes(), ctx), g["bgr_7"])
+
+
 def test_imdecode_unsupported_streams_are_errors(ctx):
     from rs_face_detection_b200 import FdError
     g = _golden()
