@@ -855,7 +855,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--roofline-sample", type=int, default=1, help="record the per-kernel CUDA events on every n-th timed step")
+    ap.add_argument("--roofline-sample", type=int, default=4, help="record the per-kernel CUDA events on every n-th timed step")
     ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: worker processes (default: one per host core)")
     ap.add_argument("--input", default="frames", choices=["frames", "jpeg", "jpeg-rst"],
                     help="reference arm: start from decoded frames or from JPEG bytes (jpeg-rst: streams with restart markers)")
