@@ -10,7 +10,11 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "l1tex__throughput.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct",
            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "launch__registers_per_thread", "launch__grid_size",
            "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
-           "sm__inst_executed_pipe_fp32.sum", "smsp__inst_executed.sum"]
+           "sm__inst_executed_pipe_fp32.sum", "smsp__inst_executed.sum",
+           # SM pipe utilisation (the NMS kernels' roofline is issue rate): fp32 = fma + fmaheavy/lite pipes, alu, fp64
+           "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+           "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+           "smsp__thread_inst_executed_per_inst_executed.ratio"]
 
 
 def main(rep, out):
