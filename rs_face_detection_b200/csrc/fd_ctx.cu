@@ -262,6 +262,7 @@ FD_EXPORT int fd_ctx_create(int device_id, const fd_config *cfg, fd_ctx **out) {
     FD_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     FD_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) FD_CUDA(cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) FD_CUDA(cudaEventCreateWithFlags(&ctx->ev_j[i], cudaEventDisableTiming));
     FD_CUDA(cudaEventCreateWithFlags(&ctx->ev_block, cudaEventDisableTiming | cudaEventBlockingSync));
     DecodeCfg &d = ctx->dcfg;
     memset(&d, 0, sizeof(d));
@@ -307,6 +308,8 @@ FD_EXPORT void fd_ctx_destroy(fd_ctx *ctx) {
     for (auto &b : ctx->pipe_heads) b.release();
     for (int i = 0; i < 4; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 2; ++i)
+        if (ctx->ev_j[i]) cudaEventDestroy(ctx->ev_j[i]);
     if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);

@@ -74,6 +74,7 @@ struct fd_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // copy stream for the host pipeline
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_j[2] = {nullptr, nullptr};   // fd_decode_jpeg_batch: joins of the two copy queues
     cudaEvent_t ev_block = nullptr;  // cudaEventBlockingSync: host waits that sleep instead of spinning (fd_pipeline_host)
     bool blocking_sync = false;
     int num_sms = 0;
