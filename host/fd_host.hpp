@@ -150,6 +150,18 @@ private:
     fd_config cfg_{};
 };
 
+// utils::utils::byte_data_to_opencv (src/utils/utils.rs:8-52) for baseline JPEG: encoded bytes -> BGR pixels (rows * cols * 3),
+// bit-identical to cv::imdecode.  Throws for streams the decoder does not cover (the reference hands those to OpenCV).
+inline std::vector<uint8_t> byte_data_to_opencv(Context &c, const uint8_t *im_bytes, size_t n, int *rows, int *cols) {
+    int h = 0, w = 0, ss = 0;
+    check(fd_jpeg_info(im_bytes, n, &h, &w, &ss));
+    std::vector<uint8_t> img((size_t)h * w * 3);
+    check(fd_imdecode(c.get(), im_bytes, n, img.data(), w * 3));
+    *rows = h;
+    *cols = w;
+    return img;
+}
+
 // pipeline::module::face_selection::FaceSelection (src/pipeline/module/face_selection.rs:5-189)
 class FaceSelection {
 public:

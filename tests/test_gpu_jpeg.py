@@ -127,3 +127,28 @@ def test_restart_marker_streams_are_huffman_decoded_on_the_device(ctx):
         np.testing.assert_array_equal(row[:, :w_.shape[1] * 3].reshape(w_.shape), w_, err_msg="case %d %r" % (b, cases[b]))
     for s_, w_ in zip(streams[:3], want[:3]):                                  # and through the single-image call
         np.testing.assert_array_equal(ctx.imdecode(s_.tobytes()), w_)
+
+
+def test_corrupted_streams_fail_or_decode_but_never_wedge_the_context(ctx):
+    """Bit flips / truncations in the entropy-coded segment (with and without restart markers): the call returns — an error
+    or some image of the right shape — and the context keeps decoding good streams bit-exactly afterwards."""
+    from rs_face_detection_b200 import FdError
+    g = _golden()
+    rng = np.random.default_rng(11)
+    for i in (0, 2, 7, 8):                       # 2 and 8 carry restart markers (device Huffman), 0 and 7 do not (host Huffman)
+        good = g["jpeg_%d" % i]
+        want = g["bgr_%d" % i]
+        for trial in range(6):
+            bad = good.copy()
+            start = len(bad) // 2                # well inside the entropy-coded segment
+            if trial < 4:
+                for pos in rng.integers(start, len(bad) - 2, 12):
+                    bad[pos] ^= np.uint8(1 << int(rng.integers(0, 8)))
+            else:
+                bad = bad[:int(rng.integers(start, len(bad) - 2))]
+            try:
+                out = ctx.imdecode(bad.tobytes())
+                assert out.shape == want.shape
+            except FdError:
+                pass
+        np.testing.assert_array_equal(ctx.imdecode(good.tobytes()), want)
