@@ -264,15 +264,16 @@ int fd_align_selected(fd_ctx *ctx, const fd_frame *frames, int B, uint8_t *crops
  * decoder does not cover (progressive, arithmetic, grayscale, CMYK, non-interleaved scans): the reference hands those to OpenCV. */
 int fd_jpeg_info(const uint8_t *jpeg, size_t nbytes, int *height, int *width, int *subsampling);
 /* Decodes B JPEG streams (host memory) into DEVICE-resident BGR frames, bit-identical to cv2.imdecode (libjpeg-turbo islow IDCT,
- * fancy upsampling, 16-bit colour tables).  Entropy decoding: a stream that carries restart markers (DRI / RSTn) is copied to the
- * device compressed and Huffman-decoded there, one restart interval per thread; a stream without them is one serial bit stream
- * and is Huffman-decoded on the host (up to n_threads threads, 0 = hardware concurrency, one image per thread) into coefficient
- * blocks that are then copied.  Dequantisation + IDCT and upsampling + colour conversion are CUDA kernels on the ctx stream
- * (asynchronous).  frames_out[i] = {device pointer owned by the ctx and valid
+ * fancy upsampling, 16-bit colour tables).  Entropy decoding runs on the device: a stream that carries restart markers (DRI /
+ * RSTn) is copied as it is and decoded one restart interval per thread; a stream without them is unstuffed on the host (a byte
+ * scan, up to n_threads threads, 0 = hardware concurrency, one image per thread), copied, and decoded by self-synchronising
+ * sub-sequences (exact: the rounds run to their fixed point; the call synchronises the ctx stream once per round).  Only a stream
+ * with more than two DC / AC tables or an inconsistent marker sequence is Huffman-decoded on the host.  Dequantisation + IDCT and
+ * upsampling + colour conversion are CUDA kernels on the ctx stream.  frames_out[i] = {device pointer owned by the ctx and valid
  * until the next call, h, w, pitch = align16(3w)}: feed it to fd_preprocess_batch / fd_align_detections directly. */
 int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, const size_t *nbytes, int B, int n_threads, fd_frame *frames_out);
-/* Of the last fd_decode_jpeg_batch: out[4] = {bytes copied host -> device, images whose Huffman stage ran on the device (streams with
- * restart markers), images entropy-decoded on the host, 0}. */
+/* Of the last fd_decode_jpeg_batch: out[4] = {bytes copied host -> device, images whose Huffman stage ran on the device, images
+ * entropy-decoded on the host, (synchronisation rounds << 32) | images decoded by the self-synchronising path}. */
 int fd_jpeg_last_stats(const fd_ctx *ctx, int64_t *out);
 /* One stream to a HOST buffer (the reference's call shape: one Mat out), blocking.  out_bgr: height rows of `pitch` bytes. */
 int fd_imdecode(fd_ctx *ctx, const uint8_t *jpeg, size_t nbytes, uint8_t *out_bgr, int pitch);

@@ -294,6 +294,30 @@ static bool scan_restart_intervals(const JpegHeader &j, std::vector<uint32_t> *i
     return iv->size() / 2 == want;
 }
 
+// Removes the byte stuffing of an entropy-coded segment without restart markers (FF 00 -> FF) and stops at the first marker
+// (EOI).  out must have room for scan_len + 16 bytes; returns the number of data bytes (the 16 bytes after them are zeroed).
+static size_t unstuff_scan(const uint8_t *p, size_t n, uint8_t *out) {
+    size_t i = 0, o = 0;
+    while (i < n) {
+        const uint8_t *ff = static_cast<const uint8_t *>(memchr(p + i, 0xFF, n - i));
+        const size_t run = ff ? (size_t)(ff - p) - i : n - i;
+        memcpy(out + o, p + i, run);
+        o += run;
+        i += run;
+        if (!ff) break;
+        if (i + 1 < n && p[i + 1] == 0x00) {
+            out[o++] = 0xFF;
+            i += 2;
+        } else if (i + 1 < n && p[i + 1] == 0xFF) {
+            i += 1;                                     // fill byte
+        } else {
+            break;                                      // a marker: end of the entropy-coded data
+        }
+    }
+    memset(out + o, 0, 16);
+    return o;
+}
+
 static void fill_huff_dev(const JpegHeader &j, JpegHuffDev *d) {
     memset(d, 0, sizeof(*d));
     for (int t = 0; t < 4; ++t) {
@@ -354,9 +378,15 @@ struct JpegImageDev {
     // entropy decoding on the device (streams with restart markers); gpu_entropy == 0: the host filled `coef`
     int gpu_entropy, n_intervals, restart, mcux, mcuy;
     int td[3], ta[3];
-    const uint8_t *stream;     // entropy-coded segment
+    const uint8_t *stream;     // entropy-coded segment (gpu_entropy 1: as received; 2: with the stuffed zero bytes removed)
     const uint32_t *iv;        // [n_intervals][2]: first byte / end (exclusive) of each restart interval's data, offsets into stream
     const JpegHuffDev *huff;
+    // gpu_entropy == 2: self-synchronising decode of a stream WITHOUT restart markers (sub-sequences of SUBSEQ_BITS bits)
+    int n_sub;                 // number of sub-sequences
+    long long nbits;           // length of the unstuffed stream in bits
+    unsigned *exit_state[2];   // [n_sub] decoder state at the end of each sub-sequence (ping-pong between rounds)
+    int *sub_blocks;           // [n_sub + 1] blocks completed inside each sub-sequence -> (after the scan) first block of each
+    int *changed;              // [1] a round changed some exit state
     uint8_t *plane[3];         // component planes, pw x ph
     uint8_t *bgr;              // output frame
     int pw[3], ph[3];
@@ -541,6 +571,257 @@ __global__ void __launch_bounds__(HUFF_THREADS) jpeg_huffman_kernel(const JpegIm
                 }
             }
         }
+    }
+}
+
+
+// ---- streams WITHOUT restart markers: self-synchronising parallel Huffman decoding ------------------------------------------
+// A Huffman decoder started at an arbitrary bit of the stream, in an arbitrary state, decodes garbage for a while and then
+// (with overwhelming probability) falls into step with the true symbol sequence: prefix codes self-synchronise, and so does
+// the JPEG state around them (position k in the block, block q in the MCU) because a wrong table breaks the alignment again
+// until all three agree.  This is used as follows (Klein & Wiseman's observation, organised for a GPU like Weissenberger &
+// Schmidt's decoder; the stream is unstuffed first so that bit positions are plain offsets):
+//   1. every thread decodes one sub-sequence of SUBSEQ_BITS bits — thread 0 from the true start state, every other thread from
+//      a guessed state at its first bit — and records the state in which it crosses the sub-sequence's end;
+//   2. rounds: thread i decodes its sub-sequence again, now starting from the state thread i-1 recorded in the previous
+//      round, and records its exit state again.  Thread 0's chain is correct by construction, so after round r the first r+1
+//      exit states are final; in practice almost all of them are final after round 1.  The rounds stop when one changes
+//      nothing: the states are then THE fixed point of the chain, i.e. exactly what the serial decoder passes through;
+//   3. the same pass counts the blocks finished inside each sub-sequence; an exclusive scan turns the counts into the index of
+//      the block each sub-sequence starts in;
+//   4. a last pass decodes every sub-sequence from its (now exact) start state and writes the coefficients; DC values are
+//      written as differences and integrated per component afterwards (jpeg_dc_kernel).
+constexpr int SUBSEQ_BITS = 4096;
+constexpr int SYNC_THREADS = 128;
+
+// exit state: bits past the sub-sequence end (< 32) | block-in-MCU q << 5 | coefficient position k << 8
+__device__ __forceinline__ unsigned pack_state(int over, int q, int k) { return (unsigned)over | ((unsigned)q << 5) | ((unsigned)k << 8); }
+
+// Decodes from bit `pos` in state (q, k) until the position reaches `end_bit`.  WRITE: block number n0 of the block the start
+// lies in; coefficients go to their blocks (DC as a difference).  Returns the exit state; *blocks = blocks finished.
+template <bool WRITE>
+__device__ __forceinline__ unsigned decode_subsequence(const JpegImageDev &im, const JpegHuffDev &tab, const uint16_t *look, const uint8_t *zz,
+                                                       long long pos, long long end_bit, int q, int k, int n0, int *blocks) {
+    const int H = im.H, V = im.V, HV = H * V, per_mcu = HV + 2, mcux = im.mcux;
+    const int ds[3] = {im.td[0] << HUFF_LOOKAHEAD, im.td[1] << HUFF_LOOKAHEAD, im.td[2] << HUFF_LOOKAHEAD};
+    const int as[3] = {(2 + im.ta[0]) << HUFF_LOOKAHEAD, (2 + im.ta[1]) << HUFF_LOOKAHEAD, (2 + im.ta[2]) << HUFF_LOOKAHEAD};
+    // bit window over the (clean) stream: 64-bit accumulator, left-aligned; aligned big-endian words
+    const unsigned *wp = reinterpret_cast<const unsigned *>(im.stream) + (pos >> 5);
+    unsigned long long acc = ((unsigned long long)__byte_perm(wp[0], 0, 0x0123) << 32) | __byte_perm(wp[1], 0, 0x0123);
+    wp += 2;
+    int cnt = 64 - (int)(pos & 31);
+    acc <<= (int)(pos & 31);
+    int comp = q < HV ? 0 : q - HV + 1;
+    int dslot = ds[comp], aslot = as[comp];
+    int nblocks = 0;
+    int16_t *blk = nullptr;
+    const int total_blocks = im.mcux * im.mcuy * per_mcu;
+    auto block_ptr = [&](int n) -> int16_t * {   // block number in scan order -> its coefficient block
+        const int mcu = n / per_mcu, qq = n - mcu * per_mcu;
+        const int my = mcu / mcux, mx = mcu - my * mcux;
+        if (qq < HV) return im.coef + ((size_t)(my * V + qq / H) * (im.pw[0] >> 3) + (size_t)(mx * H + (qq & (H - 1)))) * 64;
+        return im.coef + ((size_t)im.nblk[0] + (qq > HV ? (size_t)im.nblk[1] : 0) + (size_t)my * (im.pw[1] >> 3) + mx) * 64;
+    };
+    int n = n0;
+    if (WRITE) blk = block_ptr(min(n, total_blocks - 1));
+    while (pos < end_bit) {
+        if (cnt <= 32) {
+            acc |= (unsigned long long)__byte_perm(*wp++, 0, 0x0123) << (32 - cnt);
+            cnt += 32;
+        }
+        const bool dc = k == 0;
+        const int slot = dc ? dslot : aslot;
+        const unsigned top16 = (unsigned)(acc >> 48);
+        const unsigned e = look[slot + (top16 >> (16 - HUFF_LOOKAHEAD))];
+        int len = (int)(e >> 8), sym = (int)(e & 0xFF);
+        if (!e) {
+            const int t = slot >> HUFF_LOOKAHEAD;
+            len = HUFF_LOOKAHEAD + 1;
+#pragma unroll
+            for (int l = HUFF_LOOKAHEAD + 1; l <= 16; ++l) len += top16 >= tab.maxleft[t][l] ? 1 : 0;
+            if (len > 16) { len = 16; sym = 0; }
+            else sym = tab.vals[t][tab.valptr[t][len] + (int)(top16 >> (16 - len)) - tab.mincode[t][len]];
+        }
+        acc <<= len;
+        const int s = dc ? sym : (sym & 15), r = dc ? 0 : (sym >> 4);
+        int val = 0;
+        if (s) {
+            const int v = (int)(acc >> (64 - s));
+            acc <<= s;
+            val = v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+        }
+        cnt -= len + s;
+        pos += len + s;
+        const int kk = dc ? 0 : k + r;
+        if (WRITE && (dc || s) && kk < 64 && n < total_blocks) blk[dc ? 0 : zz[kk]] = (int16_t)val;    // DC: the difference
+        k = dc ? 1 : (s ? kk + 1 : (r == 15 ? k + 16 : 64));
+        if (k >= 64) {
+            k = 0;
+            ++nblocks;
+            ++n;
+            if (++q == per_mcu) q = 0;
+            comp = q < HV ? 0 : q - HV + 1;
+            dslot = ds[comp];
+            aslot = as[comp];
+            if (WRITE) blk = block_ptr(min(n, total_blocks - 1));
+        }
+    }
+    *blocks = nblocks;
+    return pack_state((int)(pos - end_bit), q, k);
+}
+
+// grid (ceil(max n_sub / 128), B).  round 0: guessed start states; round > 0: the previous round's exit state of the left neighbour.
+__global__ void __launch_bounds__(SYNC_THREADS) jpeg_sync_kernel(const JpegImageDev *__restrict__ imgs, int round) {
+    __shared__ JpegHuffDev tab;
+    __shared__ uint8_t zz[64];
+    const JpegImageDev &im = imgs[blockIdx.y];
+    if (im.gpu_entropy != 2 || blockIdx.x * SYNC_THREADS >= im.n_sub) return;
+    if (round > 1 && *im.changed == 0) return;          // this image's states are already the fixed point
+    for (int i = threadIdx.x; i < (int)(sizeof(JpegHuffDev) / 4); i += SYNC_THREADS)
+        reinterpret_cast<unsigned *>(&tab)[i] = __ldg(reinterpret_cast<const unsigned *>(im.huff) + i);
+    if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
+    __syncthreads();
+    const int i = blockIdx.x * SYNC_THREADS + threadIdx.x;
+    if (i >= im.n_sub) return;
+    const unsigned *prev = im.exit_state[(round + 1) & 1];
+    unsigned *cur = im.exit_state[round & 1];
+    long long pos = (long long)i * SUBSEQ_BITS;
+    int q = 0, k = 0;
+    if (i > 0 && round > 0) {
+        const unsigned st = prev[i - 1];
+        pos += st & 31u;
+        q = (st >> 5) & 7u;
+        k = (int)(st >> 8);
+    }
+    const long long end_bit = min((long long)(i + 1) * SUBSEQ_BITS, im.nbits);
+    int blocks = 0;
+    const unsigned out = decode_subsequence<false>(im, tab, &tab.look[0][0], zz, pos, end_bit, q, k, 0, &blocks);
+    if (round > 0 && out != prev[i] ) atomicOr(im.changed + 1, 1);   // [1] collects this round's changes
+    cur[i] = out;
+    im.sub_blocks[i] = blocks;
+}
+
+// one CTA per image: publishes the round's change flag ([0] <- [1], [1] <- 0); with do_scan, turns the block counts into
+// exclusive prefix sums (sub_blocks[i] = number of the block sub-sequence i starts in)
+__global__ void __launch_bounds__(1024) jpeg_sync_epilogue_kernel(const JpegImageDev *__restrict__ imgs, int do_scan) {
+    const JpegImageDev &im = imgs[blockIdx.x];
+    if (im.gpu_entropy != 2) return;
+    if (!do_scan) {
+        if (threadIdx.x == 0) { im.changed[0] = im.changed[1]; im.changed[1] = 0; }
+        return;
+    }
+    __shared__ int warp_sums[33];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int base = 0; base < im.n_sub; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < im.n_sub ? im.sub_blocks[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = warp_sums[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int nb = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += nb;
+            }
+            warp_sums[lane] = wi - w;
+            if (lane == 31) warp_sums[32] = wi;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        if (i < im.n_sub) im.sub_blocks[i] = carry + warp_sums[warp] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + warp_sums[32];
+        __syncthreads();
+    }
+}
+
+// the write pass: every sub-sequence from its exact start state; `final` = index of the exit-state buffer of the last round
+__global__ void __launch_bounds__(SYNC_THREADS) jpeg_write_kernel(const JpegImageDev *__restrict__ imgs, int final) {
+    __shared__ JpegHuffDev tab;
+    __shared__ uint8_t zz[64];
+    const JpegImageDev &im = imgs[blockIdx.y];
+    if (im.gpu_entropy != 2 || blockIdx.x * SYNC_THREADS >= im.n_sub) return;
+    for (int i = threadIdx.x; i < (int)(sizeof(JpegHuffDev) / 4); i += SYNC_THREADS)
+        reinterpret_cast<unsigned *>(&tab)[i] = __ldg(reinterpret_cast<const unsigned *>(im.huff) + i);
+    if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
+    __syncthreads();
+    const int i = blockIdx.x * SYNC_THREADS + threadIdx.x;
+    if (i >= im.n_sub) return;
+    long long pos = (long long)i * SUBSEQ_BITS;
+    int q = 0, k = 0;
+    if (i > 0) {
+        const unsigned st = im.exit_state[final][i - 1];
+        pos += st & 31u;
+        q = (st >> 5) & 7u;
+        k = (int)(st >> 8);
+    }
+    const long long end_bit = min((long long)(i + 1) * SUBSEQ_BITS, im.nbits);
+    int blocks = 0;
+    decode_subsequence<true>(im, tab, &tab.look[0][0], zz, pos, end_bit, q, k, im.sub_blocks[i], &blocks);
+}
+
+// DC prediction (T.81 F.2.1.3.1: DIFF is relative to the previous block OF THE SAME COMPONENT in scan order; no restart markers
+// here, so one chain per component over the whole image): grid (3 components, B), the write pass left the differences in blk[0].
+__global__ void __launch_bounds__(1024) jpeg_dc_kernel(const JpegImageDev *__restrict__ imgs) {
+    const JpegImageDev &im = imgs[blockIdx.y];
+    if (im.gpu_entropy != 2) return;
+    const int c = blockIdx.x;
+    const int H = im.H, V = im.V, HV = H * V, mcux = im.mcux;
+    const int per = c == 0 ? HV : 1;                       // blocks of this component per MCU
+    const int total = im.mcux * im.mcuy * per;
+    int16_t *base = im.coef + (c == 0 ? 0 : ((size_t)im.nblk[0] + (c == 2 ? (size_t)im.nblk[1] : 0)) * 64);
+    const int bw = im.pw[c] >> 3;
+    __shared__ int warp_sums[33];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int b0 = 0; b0 < total; b0 += 1024) {
+        const int n = b0 + threadIdx.x;                    // index in the component's scan order
+        int16_t *blk = nullptr;
+        int v = 0;
+        if (n < total) {
+            const int mcu = n / per, sub = n - mcu * per;
+            const int my = mcu / mcux, mx = mcu - my * mcux;
+            blk = c == 0 ? base + ((size_t)(my * V + sub / H) * bw + (size_t)(mx * H + (sub & (H - 1)))) * 64 : base + ((size_t)my * bw + mx) * 64;
+            v = blk[0];
+        }
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = warp_sums[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int nb = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += nb;
+            }
+            warp_sums[lane] = wi - w;
+            if (lane == 31) warp_sums[32] = wi;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        if (blk) blk[0] = (int16_t)(carry + warp_sums[warp] + incl);
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + warp_sums[32];
+        __syncthreads();
     }
 }
 
@@ -735,27 +1016,30 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
         for (auto &t : pool) t.join();
     };
     static const bool no_gpu_entropy = getenv("FD_JPEG_HOST_HUFFMAN") != nullptr;   // A/B switch: force the host Huffman pass
+    static const bool no_selfsync = getenv("FD_JPEG_NO_SELFSYNC") != nullptr;        // A/B switch: host pass for streams without RSTn
     // 0. headers, Huffman tables and (streams with restart markers) the restart-interval table: host parsing, one image per thread.
-    //    An image can be entropy-decoded on the device when its markers are present and consistent and it uses baseline table ids.
+    //    Entropy-decoding mode per image: 1 = device, one restart interval per thread; 2 = device, self-synchronising sub-sequences
+    //    (no restart markers); 0 = host (more than two DC / AC tables, or a restart-marker sequence that does not add up).
     std::vector<JpegHeader> hdr((size_t)B);
     std::vector<const char *> errs((size_t)B, nullptr);
     std::vector<std::vector<uint32_t>> ivs((size_t)B);
-    std::vector<char> on_gpu((size_t)B, 0);
+    std::vector<char> mode((size_t)B, 0);
     parallel_images(B, [&](int i) {
         errs[i] = parse_jpeg(jpegs[i], nbytes[i], &hdr[i]);
         if (errs[i]) return;
         const JpegHeader &j = hdr[i];
-        bool ok = !no_gpu_entropy && j.restart > 0;
+        bool ok = !no_gpu_entropy && j.scan_len < 0x7FFFFFF0ull;
         for (int c = 0; c < 3 && ok; ++c) ok = j.td[c] <= 1 && j.ta[c] <= 1;
-        on_gpu[i] = ok && scan_restart_intervals(j, &ivs[i]);
+        if (ok && j.restart > 0) mode[i] = scan_restart_intervals(j, &ivs[i]) ? 1 : 0;
+        else if (ok && !no_selfsync) mode[i] = 2;
     });
     for (int i = 0; i < B; ++i)
         if (errs[i]) return fail(FD_ERR_INVALID, "fd_decode_jpeg_batch: image " + std::to_string(i) + ": " + errs[i]);
     t_parse = now();
     // layout: coefficient arena (device; pinned mirror for host-decoded images), plane arena, frame arena, stream / aux arenas
-    std::vector<size_t> coef_off(B), plane_off(B), frame_off(B), stream_off(B), aux_off(B);
-    size_t coef_total = 0, plane_total = 0, frame_total = 0, stream_total = 0, aux_total = 0, host_coef_total = 0;
-    int max_blocks = 0, max_h = 0, max_w = 0, max_iv = 0, n_gpu = 0;
+    std::vector<size_t> coef_off(B), plane_off(B), frame_off(B), stream_off(B), aux_off(B), ustage_off(B), sync_off(B);
+    size_t coef_total = 0, plane_total = 0, frame_total = 0, stream_total = 0, aux_total = 0, host_coef_total = 0, ustage_total = 0, sync_total = 0;
+    int max_blocks = 0, max_h = 0, max_w = 0, max_iv = 0, max_sub = 0, n_rst = 0, n_sync = 0;
     for (int i = 0; i < B; ++i) {
         const JpegHeader &j = hdr[i];
         const size_t nblk = j.blocks[0] + j.blocks[1] + j.blocks[2];
@@ -769,17 +1053,29 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
         max_blocks = std::max<int>(max_blocks, (int)nblk);
         max_h = std::max(max_h, j.h);
         max_w = std::max(max_w, j.w);
-        if (on_gpu[i]) {
-            ++n_gpu;
+        if (mode[i] == 1) {
+            ++n_rst;
             stream_off[i] = stream_total;
             stream_total += (j.scan_len + 15) & ~(size_t)15;
             aux_off[i] = aux_total;
             aux_total += ((sizeof(JpegHuffDev) + ivs[i].size() * sizeof(uint32_t)) + 15) & ~(size_t)15;
             max_iv = std::max<int>(max_iv, (int)(ivs[i].size() / 2));
+        } else if (mode[i] == 2) {
+            ++n_sync;
+            stream_off[i] = stream_total;
+            stream_total += (j.scan_len + 32 + 15) & ~(size_t)15;
+            ustage_off[i] = ustage_total;
+            ustage_total += (j.scan_len + 32 + 15) & ~(size_t)15;
+            aux_off[i] = aux_total;
+            aux_total += (sizeof(JpegHuffDev) + 15) & ~(size_t)15;
+            const size_t nsub_cap = (j.scan_len * 8 + SUBSEQ_BITS - 1) / SUBSEQ_BITS + 1;
+            sync_off[i] = sync_total;
+            sync_total += (nsub_cap * 3 + 4) * sizeof(int);         // exit states x 2, block counts (+1)
         } else {
             host_coef_total += nblk * 64;
         }
     }
+    const int n_gpu = n_rst + n_sync;
     FD_TRY(ctx->jpeg_coef_host.reserve(std::max<size_t>(host_coef_total, 1) * sizeof(int16_t)));
     FD_TRY(ctx->jpeg_coef.reserve(coef_total * sizeof(int16_t)));
     FD_TRY(ctx->jpeg_planes.reserve(plane_total));
@@ -789,42 +1085,58 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
     FD_TRY(ctx->jpeg_stream.reserve(stream_total + 64));
     FD_TRY(ctx->jpeg_aux.reserve(aux_total + 64));
     FD_TRY(ctx->jpeg_aux_host.reserve(aux_total + 64));
+    FD_TRY(ctx->jpeg_ustage_host.reserve(ustage_total + 64));
+    FD_TRY(ctx->jpeg_sync.reserve(sync_total + 64));
+    FD_TRY(ctx->jpeg_flags.reserve(sizeof(int) * 2 * (size_t)B));
+    FD_TRY(ctx->jpeg_flags_host.reserve(sizeof(int) * 2 * (size_t)B));
     const double t_layout = now();
     FD_CUDA(cudaEventSynchronize(ctx->ev[3]));   // the previous call's H2D copies have left the pinned staging buffers
     t_wait = now();
     int64_t h2d = 0;
-    // 1a. device path: compressed streams + interval tables + Huffman tables go up as they are
+    std::vector<size_t> ulen(B, 0);
+    // 1a. device paths: the streams go up compressed (mode 2: with the stuffed zero bytes removed on the way, one image per thread)
     if (n_gpu) {
-        // the decoder writes non-zero coefficients only (blocks are 128 bytes: the arena is a whole number of uint4)
+        // the decoders write non-zero coefficients only (blocks are 128 bytes: the arena is a whole number of uint4)
         jpeg_zero_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->jpeg_coef.as<uint4>(), coef_total * sizeof(int16_t) / 16);
         FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_zero_kernel");
         unsigned char *aux = ctx->jpeg_aux_host.as<unsigned char>();
+        uint8_t *ustage = ctx->jpeg_ustage_host.as<uint8_t>();
+        if (n_sync)
+            parallel_images(n_sync, [&](int i) {
+                if (mode[i] == 2) ulen[i] = unstuff_scan(hdr[i].scan, hdr[i].scan_len, ustage + ustage_off[i]);
+            });
         // (one copy queue: alternating the copies over two streams was measured 2x SLOWER, 5.0 vs 2.4 ms for 64 x 1.26 MB)
         for (int i = 0; i < B; ++i) {
-            if (!on_gpu[i]) continue;
+            if (!mode[i]) continue;
             fill_huff_dev(hdr[i], reinterpret_cast<JpegHuffDev *>(aux + aux_off[i]));
-            memcpy(aux + aux_off[i] + sizeof(JpegHuffDev), ivs[i].data(), ivs[i].size() * sizeof(uint32_t));
-            FD_CUDA(cudaMemcpyAsync(ctx->jpeg_stream.as<uint8_t>() + stream_off[i], hdr[i].scan, hdr[i].scan_len, cudaMemcpyHostToDevice, ctx->stream));
-            h2d += (int64_t)hdr[i].scan_len;
+            if (mode[i] == 1) {
+                memcpy(aux + aux_off[i] + sizeof(JpegHuffDev), ivs[i].data(), ivs[i].size() * sizeof(uint32_t));
+                FD_CUDA(cudaMemcpyAsync(ctx->jpeg_stream.as<uint8_t>() + stream_off[i], hdr[i].scan, hdr[i].scan_len, cudaMemcpyHostToDevice, ctx->stream));
+                h2d += (int64_t)hdr[i].scan_len;
+            } else {
+                FD_CUDA(cudaMemcpyAsync(ctx->jpeg_stream.as<uint8_t>() + stream_off[i], ustage + ustage_off[i], ulen[i] + 16, cudaMemcpyHostToDevice, ctx->stream));
+                h2d += (int64_t)ulen[i] + 16;
+            }
         }
         FD_CUDA(cudaMemcpyAsync(ctx->jpeg_aux.p, aux, aux_total, cudaMemcpyHostToDevice, ctx->stream));
         h2d += (int64_t)aux_total;
+        if (n_sync) FD_CUDA(cudaMemsetAsync(ctx->jpeg_flags.p, 0, sizeof(int) * 2 * (size_t)B, ctx->stream));
     }
-    // 1b. host path (no restart markers): entropy decoding on the host, images are independent, one per worker thread
+    // 1b. host path: entropy decoding on the host, images are independent, one per worker thread
     std::vector<size_t> host_off(B, 0);
     if (n_gpu < B) {
         int16_t *coef_host = ctx->jpeg_coef_host.as<int16_t>();
         size_t o = 0;
         for (int i = 0; i < B; ++i)
-            if (!on_gpu[i]) { host_off[i] = o; o += (hdr[i].blocks[0] + hdr[i].blocks[1] + hdr[i].blocks[2]) * 64; }
+            if (!mode[i]) { host_off[i] = o; o += (hdr[i].blocks[0] + hdr[i].blocks[1] + hdr[i].blocks[2]) * 64; }
         parallel_images(B - n_gpu, [&](int i) {
-            if (on_gpu[i]) return;
+            if (mode[i]) return;
             const size_t n = (hdr[i].blocks[0] + hdr[i].blocks[1] + hdr[i].blocks[2]) * 64;
             memset(coef_host + host_off[i], 0, n * sizeof(int16_t));
             huffman_decode(hdr[i], coef_host + host_off[i]);
         });
         for (int i = 0; i < B; ++i) {
-            if (on_gpu[i]) continue;
+            if (mode[i]) continue;
             const size_t n = (hdr[i].blocks[0] + hdr[i].blocks[1] + hdr[i].blocks[2]) * 64;
             FD_CUDA(cudaMemcpyAsync(ctx->jpeg_coef.as<int16_t>() + coef_off[i], coef_host + host_off[i], n * sizeof(int16_t), cudaMemcpyHostToDevice,
                                     ctx->stream));
@@ -860,12 +1172,24 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
         d.mcux = j.mcux;
         d.mcuy = j.mcuy;
         d.restart = j.restart;
-        d.gpu_entropy = on_gpu[i] ? 1 : 0;
-        if (on_gpu[i]) {
-            d.n_intervals = (int)(ivs[i].size() / 2);
+        d.gpu_entropy = mode[i];
+        if (mode[i]) {
             d.stream = ctx->jpeg_stream.as<uint8_t>() + stream_off[i];
             d.huff = reinterpret_cast<const JpegHuffDev *>(ctx->jpeg_aux.as<unsigned char>() + aux_off[i]);
+        }
+        if (mode[i] == 1) {
+            d.n_intervals = (int)(ivs[i].size() / 2);
             d.iv = reinterpret_cast<const uint32_t *>(ctx->jpeg_aux.as<unsigned char>() + aux_off[i] + sizeof(JpegHuffDev));
+        } else if (mode[i] == 2) {
+            d.nbits = (long long)ulen[i] * 8;
+            d.n_sub = (int)((d.nbits + SUBSEQ_BITS - 1) / SUBSEQ_BITS);
+            const size_t cap = (j.scan_len * 8 + SUBSEQ_BITS - 1) / SUBSEQ_BITS + 1;
+            unsigned *sy = reinterpret_cast<unsigned *>(ctx->jpeg_sync.as<unsigned char>() + sync_off[i]);
+            d.exit_state[0] = sy;
+            d.exit_state[1] = sy + cap;
+            d.sub_blocks = reinterpret_cast<int *>(sy + 2 * cap);
+            d.changed = ctx->jpeg_flags.as<int>() + 2 * i;
+            max_sub = std::max(max_sub, d.n_sub);
         }
         frames_out[i].data = d.bgr;
         frames_out[i].height = j.h;
@@ -877,19 +1201,51 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
     h2d += (int64_t)(sizeof(JpegImageDev) * (size_t)B);
     ctx->jpeg_last_h2d = h2d;
     ctx->jpeg_last_gpu_entropy = n_gpu;
+    ctx->jpeg_last_selfsync = n_sync;
     ctx->jpeg_last_B = B;
-    // 3. entropy decoding on the device (one restart interval per thread), IDCT, upsampling + colour conversion
-    if (n_gpu) {
+    const JpegImageDev *ddesc = ctx->jpeg_desc.as<JpegImageDev>();
+    // 3a. entropy decoding on the device, streams with restart markers: one restart interval per thread
+    if (n_rst) {
         dim3 g0((max_iv + HUFF_THREADS - 1) / HUFF_THREADS, B);
-        jpeg_huffman_kernel<<<g0, HUFF_THREADS, 0, ctx->stream>>>(ctx->jpeg_desc.as<JpegImageDev>());
+        jpeg_huffman_kernel<<<g0, HUFF_THREADS, 0, ctx->stream>>>(ddesc);
         FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_huffman_kernel");
     }
+    // 3b. streams without restart markers: self-synchronising rounds until a round changes no exit state, then count -> scan -> write
+    ctx->jpeg_last_rounds = 0;
+    if (n_sync && max_sub > 0) {
+        dim3 gs((max_sub + SYNC_THREADS - 1) / SYNC_THREADS, B);
+        jpeg_sync_kernel<<<gs, SYNC_THREADS, 0, ctx->stream>>>(ddesc, 0);
+        FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_sync_kernel");
+        int round = 0;
+        int *flags = ctx->jpeg_flags_host.as<int>();
+        for (;;) {
+            ++round;
+            jpeg_sync_kernel<<<gs, SYNC_THREADS, 0, ctx->stream>>>(ddesc, round);
+            FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_sync_kernel");
+            jpeg_sync_epilogue_kernel<<<B, 1024, 0, ctx->stream>>>(ddesc, 0);
+            FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_sync_epilogue_kernel");
+            FD_CUDA(cudaMemcpyAsync(flags, ctx->jpeg_flags.p, sizeof(int) * 2 * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+            FD_CUDA(cudaStreamSynchronize(ctx->stream));
+            bool any = false;
+            for (int i = 0; i < B; ++i) any = any || (mode[i] == 2 && flags[2 * i] != 0);
+            if (!any) break;
+            FD_REQUIRE(round <= max_sub + 2, "fd_decode_jpeg_batch: the sub-sequence states did not converge (corrupt stream?)");
+        }
+        ctx->jpeg_last_rounds = round;
+        jpeg_sync_epilogue_kernel<<<B, 1024, 0, ctx->stream>>>(ddesc, 1);
+        FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_sync_epilogue_kernel");
+        jpeg_write_kernel<<<gs, SYNC_THREADS, 0, ctx->stream>>>(ddesc, round & 1);
+        FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_write_kernel");
+        jpeg_dc_kernel<<<dim3(3, B), 1024, 0, ctx->stream>>>(ddesc);
+        FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_dc_kernel");
+    }
+    // 4. IDCT, upsampling + colour conversion
     dim3 g1((max_blocks + IDCT_BLOCKS - 1) / IDCT_BLOCKS, B);
-    jpeg_idct_kernel<<<g1, IDCT_BLOCKS * 8, 0, ctx->stream>>>(ctx->jpeg_desc.as<JpegImageDev>());
+    jpeg_idct_kernel<<<g1, IDCT_BLOCKS * 8, 0, ctx->stream>>>(ddesc);
     FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_idct_kernel");
     FD_REQUIRE(max_h <= 65535 && B <= 65535, "fd_decode_jpeg_batch: image too tall / batch too large for one launch");
     dim3 g2(((max_w + 7) / 8 + 127) / 128, max_h, B);
-    jpeg_color_kernel<<<g2, 128, 0, ctx->stream>>>(ctx->jpeg_desc.as<JpegImageDev>());
+    jpeg_color_kernel<<<g2, 128, 0, ctx->stream>>>(ddesc);
     FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_color_kernel");
     if (dbg)
         fprintf(stderr, "[jpeg dbg] B=%d on-device entropy %d: parse+scan %.2f ms, layout %.2f, wait prev copies %.2f, enqueue copies (+host huffman) %.2f, "
@@ -903,7 +1259,7 @@ FD_EXPORT int fd_jpeg_last_stats(const fd_ctx *ctx, int64_t *out) {
     out[0] = ctx->jpeg_last_h2d;
     out[1] = ctx->jpeg_last_gpu_entropy;
     out[2] = ctx->jpeg_last_B - ctx->jpeg_last_gpu_entropy;
-    out[3] = 0;
+    out[3] = ((int64_t)ctx->jpeg_last_rounds << 32) | (unsigned)ctx->jpeg_last_selfsync;
     return FD_OK;
 }
 

@@ -616,7 +616,8 @@ class Context:
     def jpeg_last_stats(self):
         out = (C.c_int64 * 4)()
         _chk(self.lib.fd_jpeg_last_stats(self.handle, out))
-        return dict(h2d_bytes=int(out[0]), device_entropy_images=int(out[1]), host_entropy_images=int(out[2]))
+        return dict(h2d_bytes=int(out[0]), device_entropy_images=int(out[1]), host_entropy_images=int(out[2]),
+                    selfsync_images=int(out[3] & 0xFFFFFFFF), selfsync_rounds=int(out[3] >> 32))
 
     def decode_jpeg_batch(self, jpegs, n_threads=0):
         """jpegs: list of bytes-like JPEG streams -> fd_frame array of device-resident BGR frames (valid until the next call)"""
