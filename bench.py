@@ -666,13 +666,14 @@ def run_ours(args):
                               crops=pin((cap_rows, 112, 112, 3), torch.uint8), det_scale=pin((BATCH,), torch.float32),
                               align_mode=pin((cap_rows,), torch.uint8), sel=pin((BATCH, 2), torch.int32), tensor=None)
         L = max(1, args.e2e_lanes)
+        LJ = max(L, args.e2e_jpeg_lanes)     # the JPEG legs have a host round trip per batch (convergence flags): more lanes hide it
         e2e_steps = max(2 * L, min(args.steps, 24)) // L * L
         # L host threads, one fd_ctx each, alternate batches: the H2D of one batch overlaps the compute + D2H of the others
-        e2e_ctx = [ctx] + [Context(local_rank) for _ in range(L - 1)]
+        e2e_ctx = [ctx] + [Context(local_rank) for _ in range(LJ - 1)]
         for c_ in e2e_ctx:
             c_.set_sharing(L)
-        e2e_bufs = [mkbufs() for _ in range(L)]
-        res_e = [None] * L
+        e2e_bufs = [mkbufs() for _ in range(LJ)]
+        res_e = [None] * LJ
 
         def e2e_worker(i, n, kw):
             torch.cuda.set_device(local_rank)
@@ -681,8 +682,8 @@ def run_ours(args):
             for _ in range(n):
                 res_e[i] = e2e_ctx[i].pipeline_host(src, host_heads, cap_rows, CONF_THR, IOU_THR, bufs=e2e_bufs[i], **kw)
 
-        def e2e_run(n_each, kw):
-            th = [threading.Thread(target=e2e_worker, args=(i, n_each, kw)) for i in range(L)]
+        def e2e_run(n_each, kw, lanes):
+            th = [threading.Thread(target=e2e_worker, args=(i, n_each, kw)) for i in range(lanes)]
             t0 = time.perf_counter()
             for t in th:
                 t.start()
@@ -690,13 +691,17 @@ def run_ours(args):
                 t.join()
             return time.perf_counter() - t0
 
-        def e2e_leg(kw, n_steps, note):
-            e2e_run(2, kw)
+        def e2e_leg(kw, n_steps, note, lanes=None):
+            lanes = lanes or L
+            n_steps = max(2 * lanes, n_steps) // lanes * lanes
+            for c_ in e2e_ctx[:lanes]:
+                c_.set_sharing(lanes)
+            e2e_run(2, kw, lanes)
             barrier()
-            s = dist_max(e2e_run(n_steps // L, kw))
+            s = dist_max(e2e_run(n_steps // lanes, kw, lanes))
             _, total, h2d, d2h = res_e[0]
             return {"value": BATCH * n_steps * world / s, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": n_steps, "ms_per_step": 1e3 * s / n_steps, "batches_in_flight": L, "detections_per_step": int(total),
+                    "steps": n_steps, "ms_per_step": 1e3 * s / n_steps, "batches_in_flight": lanes, "detections_per_step": int(total),
                     "crops_per_step": int(e2e_bufs[0]["n_crops"]), "note": note}
 
         e2e = e2e_leg(dict(heads_zero_copy=True), e2e_steps,
@@ -730,12 +735,13 @@ def run_ours(args):
                     pinned_jpegs = [pinned_like(encode_jpeg(f, rst)) for f in host_frames]
                     streams = [p.array for p in pinned_jpegs]
                     e2e_variants[key] = e2e_leg(
-                        dict(jpeg=True, jpeg_threads=max(1, cores // L), heads_zero_copy=True, streams=streams), short,
+                        dict(jpeg=True, jpeg_threads=max(1, cores // LJ), heads_zero_copy=True, streams=streams), max(short, 2 * LJ),
                         ("fd_pipeline_host_jpeg: q%d 4:2:0 JPEG streams in (%.2f MB/frame), " % (JPEG_QUALITY, float(np.mean([j.size for j in streams])) / 1e6)) +
                         ("restart interval %d MCUs: the compressed streams cross PCIe and jpeg_huffman_kernel decodes one restart interval per thread"
                          % rst if rst else
-                         "no restart markers: one serial bit stream per image, Huffman-decoded on the host (%d threads per lane), coefficients copied"
-                         % max(1, cores // L)) + " -> CUDA IDCT/upsampling/colour -> the same path; frames bit-identical to cv2.imdecode")
+                         "no restart markers (what encoders emit by default): the compressed streams cross PCIe as they are, unstuffed on the device and "
+                         "Huffman-decoded by self-synchronising sub-sequences (jpeg_sync_kernel rounds to the fixed point, jpeg_write_kernel)") +
+                        " -> CUDA IDCT/upsampling/colour -> the same path; frames bit-identical to cv2.imdecode", lanes=LJ)
                     e2e_variants[key]["jpeg_bytes_per_step"] = int(sum(j.size for j in streams))
                     e2e_variants[key]["entropy_decode"] = e2e_ctx[0].jpeg_last_stats()
                     del pinned_jpegs, streams
@@ -862,6 +868,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-variants", action="store_true")
     ap.add_argument("--e2e-lanes", type=int, default=3, help="host threads / contexts keeping batches in flight in the e2e leg")
+    ap.add_argument("--e2e-jpeg-lanes", type=int, default=6, help="the same for the JPEG-input legs of e2e_variants")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-nms", action="store_true")
     ap.add_argument("--no-pipelined", action="store_true")

@@ -298,12 +298,11 @@ FD_EXPORT void fd_ctx_destroy(fd_ctx *ctx) {
     ctx->jpeg_coef_host.release();
     ctx->jpeg_desc_host.release();
     ctx->jpeg_aux_host.release();
-    ctx->jpeg_ustage_host.release();
     ctx->jpeg_flags_host.release();
     DevBuf *bufs[] = {&ctx->frames_dev, &ctx->det_scale_dev, &ctx->cand_count, &ctx->cand_keys, &ctx->cand_box,
                       &ctx->cand_lmk, &ctx->keep_src, &ctx->keep_count, &ctx->status_dev, &ctx->big_list,
                       &ctx->out_offsets, &ctx->out_det, &ctx->out_lmk, &ctx->out_frame_idx, &ctx->align_M,
-                      &ctx->align_ok, &ctx->tickets, &ctx->scan_agg, &ctx->select_sel, &ctx->select_lmk, &ctx->select_fidx, &ctx->pipe_frames, &ctx->pipe_tensor, &ctx->pipe_crops, &ctx->pipe_mode, &ctx->jpeg_coef, &ctx->jpeg_planes, &ctx->jpeg_frames, &ctx->jpeg_desc, &ctx->jpeg_stream, &ctx->jpeg_aux, &ctx->jpeg_sync, &ctx->jpeg_flags};
+                      &ctx->align_ok, &ctx->tickets, &ctx->scan_agg, &ctx->select_sel, &ctx->select_lmk, &ctx->select_fidx, &ctx->pipe_frames, &ctx->pipe_tensor, &ctx->pipe_crops, &ctx->pipe_mode, &ctx->jpeg_coef, &ctx->jpeg_planes, &ctx->jpeg_frames, &ctx->jpeg_desc, &ctx->jpeg_raw, &ctx->jpeg_stream, &ctx->jpeg_aux, &ctx->jpeg_sync, &ctx->jpeg_flags};
     for (auto *b : bufs) b->release();
     for (auto &b : ctx->nms_ws) b.release();
     for (auto &b : ctx->nms_ws_sp) b.release();

@@ -125,9 +125,10 @@ struct fd_ctx {
     fd::DevBuf pipe_tensor;
     fd::DevBuf pipe_crops;
     fd::DevBuf jpeg_coef, jpeg_planes, jpeg_frames, jpeg_desc;   // fd_decode_jpeg_batch: coefficients, component planes, BGR frames
+    fd::DevBuf jpeg_raw;                   // self-synchronising decode: segments as received (jpeg_stream holds them unstuffed)
     fd::DevBuf jpeg_stream, jpeg_aux;      // compressed streams, Huffman + restart-interval tables (device entropy decoding)
     fd::DevBuf jpeg_sync, jpeg_flags;      // self-synchronising decode: exit states / block counts per sub-sequence, change flags
-    fd::PinnedBuf jpeg_coef_host, jpeg_desc_host, jpeg_aux_host, jpeg_ustage_host, jpeg_flags_host;
+    fd::PinnedBuf jpeg_coef_host, jpeg_desc_host, jpeg_aux_host, jpeg_flags_host;
     int jpeg_last_selfsync = 0, jpeg_last_rounds = 0;
     int64_t jpeg_last_h2d = 0;
     int jpeg_last_B = 0;

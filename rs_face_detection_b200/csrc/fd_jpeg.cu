@@ -294,30 +294,6 @@ static bool scan_restart_intervals(const JpegHeader &j, std::vector<uint32_t> *i
     return iv->size() / 2 == want;
 }
 
-// Removes the byte stuffing of an entropy-coded segment without restart markers (FF 00 -> FF) and stops at the first marker
-// (EOI).  out must have room for scan_len + 16 bytes; returns the number of data bytes (the 16 bytes after them are zeroed).
-static size_t unstuff_scan(const uint8_t *p, size_t n, uint8_t *out) {
-    size_t i = 0, o = 0;
-    while (i < n) {
-        const uint8_t *ff = static_cast<const uint8_t *>(memchr(p + i, 0xFF, n - i));
-        const size_t run = ff ? (size_t)(ff - p) - i : n - i;
-        memcpy(out + o, p + i, run);
-        o += run;
-        i += run;
-        if (!ff) break;
-        if (i + 1 < n && p[i + 1] == 0x00) {
-            out[o++] = 0xFF;
-            i += 2;
-        } else if (i + 1 < n && p[i + 1] == 0xFF) {
-            i += 1;                                     // fill byte
-        } else {
-            break;                                      // a marker: end of the entropy-coded data
-        }
-    }
-    memset(out + o, 0, 16);
-    return o;
-}
-
 static void fill_huff_dev(const JpegHeader &j, JpegHuffDev *d) {
     memset(d, 0, sizeof(*d));
     for (int t = 0; t < 4; ++t) {
@@ -331,11 +307,9 @@ static void fill_huff_dev(const JpegHeader &j, JpegHuffDev *d) {
     }
 }
 
-// coef: [comp 0 blocks][comp 1 blocks][comp 2 blocks], each block 64 int16 in natural order, block (by,bx) row-major
+// coef: blocks in SCAN order (MCU by MCU: the H*V luma blocks, Cb, Cr), each block 64 int16 in natural order
 static void huffman_decode(const JpegHeader &j, int16_t *coef) {
     BitReader b(j.scan, j.scan_len);
-    int16_t *base[3] = {coef, coef + j.blocks[0] * 64, coef + (j.blocks[0] + j.blocks[1]) * 64};
-    const int bw[3] = {j.pw[0] / 8, j.pw[1] / 8, j.pw[2] / 8};
     int pred[3] = {0, 0, 0};
     int count = 0;
     for (int my = 0; my < j.mcuy; ++my)
@@ -349,7 +323,8 @@ static void huffman_decode(const JpegHeader &j, int16_t *coef) {
                 const HuffTable &dct = j.dc[j.td[c]], &act = j.ac[j.ta[c]];
                 for (int v = 0; v < j.vs[c]; ++v)
                     for (int hh = 0; hh < j.hs[c]; ++hh) {
-                        int16_t *blk = base[c] + ((size_t)(my * j.vs[c] + v) * bw[c] + (size_t)(mx * j.hs[c] + hh)) * 64;
+                        int16_t *blk = coef;
+                        coef += 64;
                         int s = b.decode(dct);
                         if (s) pred[c] += b.receive_extend(s);
                         blk[0] = (int16_t)pred[c];
@@ -378,15 +353,20 @@ struct JpegImageDev {
     // entropy decoding on the device (streams with restart markers); gpu_entropy == 0: the host filled `coef`
     int gpu_entropy, n_intervals, restart, mcux, mcuy;
     int td[3], ta[3];
-    const uint8_t *stream;     // entropy-coded segment (gpu_entropy 1: as received; 2: with the stuffed zero bytes removed)
+    const uint8_t *stream;     // entropy-coded segment (gpu_entropy 1: as received; 2: with the stuffed zero bytes removed, device-made)
     const uint32_t *iv;        // [n_intervals][2]: first byte / end (exclusive) of each restart interval's data, offsets into stream
     const JpegHuffDev *huff;
     // gpu_entropy == 2: self-synchronising decode of a stream WITHOUT restart markers (sub-sequences of SUBSEQ_BITS bits)
-    int n_sub;                 // number of sub-sequences
-    long long nbits;           // length of the unstuffed stream in bits
-    unsigned *exit_state[2];   // [n_sub] decoder state at the end of each sub-sequence (ping-pong between rounds)
+    const uint8_t *raw;        // the segment as received (FF 00 stuffing, EOI at the end); raw_len bytes
+    uint8_t *clean;            // == stream: jpeg_unstuff_write_kernel fills it
+    int raw_len;
+    int n_sub;                 // number of sub-sequences            } written on the device by jpeg_unstuff_write_kernel
+    long long nbits;           // length of the unstuffed data in bits }
+    int *chunk_drop;           // [raw_len / UNSTUFF_CHUNK + 1] non-data bytes per chunk -> (after the scan) before each chunk
+    unsigned *exit_state;      // [n_sub] decoder state at the end of each sub-sequence
+    unsigned *used_state;      // [n_sub] the start state its last decode began from
     int *sub_blocks;           // [n_sub + 1] blocks completed inside each sub-sequence -> (after the scan) first block of each
-    int *changed;              // [1] a round changed some exit state
+    int *changed;              // [0] the last finished round changed some exit state, [1] collects the running round, [2] raw_len - first marker
     uint8_t *plane[3];         // component planes, pw x ph
     uint8_t *bgr;              // output frame
     int pw[3], ph[3];
@@ -432,9 +412,36 @@ __constant__ uint8_t c_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32,
                                      41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                                      30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
+__constant__ uint8_t c_unzigzag[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30,
+                                       41, 43, 9,  11, 18, 24, 31, 40, 44, 53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38,
+                                       46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+
+// Coefficient staging of the entropy decoders.  The arena holds the blocks in SCAN order (block n of the scan at coef + 64 n;
+// the IDCT and DC kernels map their plane positions to n), each block in natural order.  Every thread assembles its current
+// block in a private row of shared memory (33 words apart: the rows of a warp's lanes start in different banks) and the WARP
+// writes finished blocks out together: one 128-byte store per block instead of ~30 scattered 2-byte stores, and no per-lane
+// pointer bookkeeping in the decode loop.  A block carries its zeros, so nothing pre-clears the arena.
+constexpr int STAGE_PITCH = 33;
+
+// all 32 lanes: writes lane `src`'s staged block to `dst` and clears the row.  [kf, ke) != [0, 64): only the coefficients whose
+// SCAN position lies in that range (a block shared with the neighbouring sub-sequences, jpeg_write_kernel).
+__device__ __forceinline__ void stage_flush(unsigned *stage_warp, int src, int lane, int16_t *dst, int kf, int ke, bool valid) {
+    unsigned *w = stage_warp + src * STAGE_PITCH + lane;
+    const unsigned word = *w;
+    *w = 0u;
+    if (!valid) return;
+    if (kf == 0 && ke == 64) {
+        reinterpret_cast<unsigned *>(dst)[lane] = word;
+    } else {
+        const int e = 2 * lane, k0 = c_unzigzag[e], k1 = c_unzigzag[e + 1];
+        if (k0 >= kf && k0 < ke) dst[e] = (int16_t)(word & 0xFFFFu);
+        if (k1 >= kf && k1 < ke) dst[e + 1] = (int16_t)(word >> 16);
+    }
+}
+
 constexpr int HUFF_THREADS = 64;
 
-// grid (ceil(max intervals / 64), B): one restart interval per thread.  The coefficient arena is zeroed beforehand.
+// grid (ceil(max intervals / 64), B): one restart interval per thread.
 //
 // The decode is ONE flat loop that consumes exactly one Huffman symbol per lane per iteration (DC or AC, decided by the lane's
 // own position k in its block): the 32 lanes of a warp sit at unrelated points of 32 different bit streams, and a nested
@@ -446,13 +453,18 @@ constexpr int HUFF_THREADS = 64;
 // per-image constants.  What is left to diverge: the FF words, the block advance (~1 iteration in 35 per lane) and the tail.
 __global__ void __launch_bounds__(HUFF_THREADS) jpeg_huffman_kernel(const JpegImageDev *__restrict__ imgs) {
     __shared__ JpegHuffDev tab;
+    __shared__ unsigned stage[HUFF_THREADS * STAGE_PITCH];
     __shared__ uint8_t zz[64];
     const JpegImageDev &im = imgs[blockIdx.y];
-    if (!im.gpu_entropy || blockIdx.x * HUFF_THREADS >= im.n_intervals) return;   // uniform over the CTA
+    if (im.gpu_entropy != 1 || blockIdx.x * HUFF_THREADS >= im.n_intervals) return;   // uniform over the CTA
+    if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
     for (int i = threadIdx.x; i < (int)(sizeof(JpegHuffDev) / 4); i += HUFF_THREADS)
         reinterpret_cast<unsigned *>(&tab)[i] = __ldg(reinterpret_cast<const unsigned *>(im.huff) + i);
-    if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
+    for (int i = threadIdx.x; i < HUFF_THREADS * STAGE_PITCH; i += HUFF_THREADS) stage[i] = 0u;
     __syncthreads();
+    const int lane = threadIdx.x & 31;
+    unsigned *stage_warp = stage + (threadIdx.x & ~31) * STAGE_PITCH;
+    int16_t *my_row = reinterpret_cast<int16_t *>(stage + threadIdx.x * STAGE_PITCH);
     const uint16_t *look = &tab.look[0][0];
     const int iv = blockIdx.x * HUFF_THREADS + threadIdx.x;
     const bool live = iv < im.n_intervals;
@@ -466,26 +478,18 @@ __global__ void __launch_bounds__(HUFF_THREADS) jpeg_huffman_kernel(const JpegIm
     bool ffpending = false;                                            // the previous byte was a data FF: the next one is its stuffed 00
     unsigned long long acc = 0;
     int cnt = 0;
-    const int H = im.H, V = im.V, HV = H * V, mcux = im.mcux, restart = im.restart;
-    const int bw0 = im.pw[0] >> 3;
+    const int HV = im.H * im.V, per_mcu = HV + 2, restart = im.restart;
     const int ds0 = im.td[0] << HUFF_LOOKAHEAD, ds1 = im.td[1] << HUFF_LOOKAHEAD, ds2 = im.td[2] << HUFF_LOOKAHEAD;
     const int as0 = (2 + im.ta[0]) << HUFF_LOOKAHEAD, as1 = (2 + im.ta[1]) << HUFF_LOOKAHEAD, as2 = (2 + im.ta[2]) << HUFF_LOOKAHEAD;
     int pred0 = 0, pred1 = 0, pred2 = 0;
-    const int mcu_end = live ? min((iv + 1) * restart, mcux * im.mcuy) : 0;
+    const int mcu_end = live ? min((iv + 1) * restart, im.mcux * im.mcuy) : 0;
     int mcu = live ? iv * restart : 0;
-    int mx = mcu % mcux;
-    const int my0 = mcu / mcux;
-    // block pointers of the current MCU: luma top-left block, Cb block, Cr block
-    int16_t *by = im.coef + ((size_t)(my0 * V) * bw0 + (size_t)(mx * H)) * 64;
-    int16_t *bcb = im.coef + ((size_t)im.nblk[0] + (size_t)my0 * (im.pw[1] >> 3) + mx) * 64;
-    int16_t *bcr = bcb + (size_t)im.nblk[1] * 64;
-    const int row_step_y = (V * bw0 - mcux * H) * 64;        // luma pointer: from the end of an MCU row to the start of the next
-    const int luma_row = bw0 * 64;                            // one block row down inside the MCU
+    int n = mcu * per_mcu;          // block number in scan order
     int q = 0, k = 0;               // block within the MCU (scan order: HV luma blocks, Cb, Cr), next coefficient (0 = DC)
     bool active = mcu < mcu_end;
-    int16_t *blk = by;
     int dslot = ds0, aslot = as0, comp = 0;
     while (__any_sync(0xffffffffu, active)) {
+        bool done = false;                                             // this lane finished a block in this iteration
         if (active) {
             // ---- refill: >= 33 valid bits afterwards = one code (<= 16) + one value (<= 15) ----
             while (cnt <= 32) {
@@ -545,31 +549,32 @@ __global__ void __launch_bounds__(HUFF_THREADS) jpeg_huffman_kernel(const JpegIm
                 val = pred;
                 kk = 0;
             }
-            if ((dc || s) && kk < 64) blk[dc ? 0 : zz[kk]] = (int16_t)val;
+            if ((dc || s) && kk < 64) my_row[dc ? 0 : zz[kk]] = (int16_t)val;
             k = dc ? 1 : (s ? kk + 1 : (r == 15 ? k + 16 : 64));       // DC / coefficient / ZRL / EOB
-            if (k >= 64) {                                             // next block of the scan
-                k = 0;
-                ++q;
-                if (q == HV + 2) {                                     // next MCU
-                    q = 0;
-                    ++mcu;
-                    by += H * 64;
-                    bcb += 64;
-                    bcr += 64;
-                    if (++mx == mcux) { mx = 0; by += row_step_y; }
-                    active = mcu < mcu_end;
-                }
-                if (q < HV) {
-                    blk = by + (q >= H ? luma_row : 0) + (q & (H - 1)) * 64;     // H, V in {1, 2}: q = v * H + h
-                    dslot = ds0; aslot = as0; comp = 0;
-                } else if (q == HV) {
-                    blk = bcb;
-                    dslot = ds1; aslot = as1; comp = 1;
-                } else {
-                    blk = bcr;
-                    dslot = ds2; aslot = as2; comp = 2;
-                }
+            done = k >= 64;
+        }
+        unsigned fm = __ballot_sync(0xffffffffu, done);
+        if (fm) {
+            __syncwarp();
+            do {
+                const int src = __ffs(fm) - 1;
+                fm &= fm - 1;
+                int16_t *dst = im.coef + (size_t)__shfl_sync(0xffffffffu, n, src) * 64;
+                stage_flush(stage_warp, src, lane, dst, 0, 64, true);
+            } while (fm);
+            __syncwarp();
+        }
+        if (done) {                                                    // next block of the scan
+            k = 0;
+            ++n;
+            if (++q == per_mcu) {                                      // next MCU
+                q = 0;
+                ++mcu;
+                active = mcu < mcu_end;
             }
+            comp = q < HV ? 0 : q - HV + 1;
+            dslot = comp == 0 ? ds0 : (comp == 1 ? ds1 : ds2);
+            aslot = comp == 0 ? as0 : (comp == 1 ? as1 : as2);
         }
     }
 }
@@ -580,144 +585,37 @@ __global__ void __launch_bounds__(HUFF_THREADS) jpeg_huffman_kernel(const JpegIm
 // (with overwhelming probability) falls into step with the true symbol sequence: prefix codes self-synchronise, and so does
 // the JPEG state around them (position k in the block, block q in the MCU) because a wrong table breaks the alignment again
 // until all three agree.  This is used as follows (Klein & Wiseman's observation, organised for a GPU like Weissenberger &
-// Schmidt's decoder; the stream is unstuffed first so that bit positions are plain offsets):
+// Schmidt's decoder):
+//   0. the segment crosses PCIe as received; three small kernels remove the byte stuffing (FF 00 -> FF) and find the end of the
+//      data (the first marker), so that bit positions are plain offsets and the host never touches the entropy-coded bytes;
 //   1. every thread decodes one sub-sequence of SUBSEQ_BITS bits — thread 0 from the true start state, every other thread from
 //      a guessed state at its first bit — and records the state in which it crosses the sub-sequence's end;
-//   2. rounds: thread i decodes its sub-sequence again, now starting from the state thread i-1 recorded in the previous
-//      round, and records its exit state again.  Thread 0's chain is correct by construction, so after round r the first r+1
-//      exit states are final; in practice almost all of them are final after round 1.  The rounds stop when one changes
-//      nothing: the states are then THE fixed point of the chain, i.e. exactly what the serial decoder passes through;
+//   2. rounds: thread i looks at the state thread i-1 recorded; if that is not the state its own last decode started from, it
+//      decodes its sub-sequence again from there and records its exit state again.  Thread 0's chain is correct by
+//      construction, so after round r the first r+1 exit states are final; in practice almost all of them are final after
+//      round 1 and later rounds touch only the few sub-sequences whose input still moves.  The rounds stop when one changes
+//      nothing: the states are then THE fixed point of the chain, i.e. exactly what the serial decoder passes through
+//      (the fixed point is unique — induction from thread 0 — so reading a neighbour's state while it is being replaced is
+//      harmless: either value is a guess, and a changed state always forces another round);
 //   3. the same pass counts the blocks finished inside each sub-sequence; an exclusive scan turns the counts into the index of
 //      the block each sub-sequence starts in;
 //   4. a last pass decodes every sub-sequence from its (now exact) start state and writes the coefficients; DC values are
 //      written as differences and integrated per component afterwards (jpeg_dc_kernel).
-constexpr int SUBSEQ_BITS = 4096;
-constexpr int SYNC_THREADS = 128;
+#ifndef FD_SUBSEQ_BITS
+#define FD_SUBSEQ_BITS 4096
+#endif
+constexpr int SUBSEQ_BITS = FD_SUBSEQ_BITS;   // 2048 / 4096 / 8192 / 16384 measured on the bench's frames: profiles/r2_jpeg_selfsync_subseq.txt
 
-// exit state: bits past the sub-sequence end (< 32) | block-in-MCU q << 5 | coefficient position k << 8
-__device__ __forceinline__ unsigned pack_state(int over, int q, int k) { return (unsigned)over | ((unsigned)q << 5) | ((unsigned)k << 8); }
-
-// Decodes from bit `pos` in state (q, k) until the position reaches `end_bit`.  WRITE: block number n0 of the block the start
-// lies in; coefficients go to their blocks (DC as a difference).  Returns the exit state; *blocks = blocks finished.
-template <bool WRITE>
-__device__ __forceinline__ unsigned decode_subsequence(const JpegImageDev &im, const JpegHuffDev &tab, const uint16_t *look, const uint8_t *zz,
-                                                       long long pos, long long end_bit, int q, int k, int n0, int *blocks) {
-    const int H = im.H, V = im.V, HV = H * V, per_mcu = HV + 2, mcux = im.mcux;
-    const int ds[3] = {im.td[0] << HUFF_LOOKAHEAD, im.td[1] << HUFF_LOOKAHEAD, im.td[2] << HUFF_LOOKAHEAD};
-    const int as[3] = {(2 + im.ta[0]) << HUFF_LOOKAHEAD, (2 + im.ta[1]) << HUFF_LOOKAHEAD, (2 + im.ta[2]) << HUFF_LOOKAHEAD};
-    // bit window over the (clean) stream: 64-bit accumulator, left-aligned; aligned big-endian words
-    const unsigned *wp = reinterpret_cast<const unsigned *>(im.stream) + (pos >> 5);
-    unsigned long long acc = ((unsigned long long)__byte_perm(wp[0], 0, 0x0123) << 32) | __byte_perm(wp[1], 0, 0x0123);
-    wp += 2;
-    int cnt = 64 - (int)(pos & 31);
-    acc <<= (int)(pos & 31);
-    int comp = q < HV ? 0 : q - HV + 1;
-    int dslot = ds[comp], aslot = as[comp];
-    int nblocks = 0;
-    int16_t *blk = nullptr;
-    const int total_blocks = im.mcux * im.mcuy * per_mcu;
-    auto block_ptr = [&](int n) -> int16_t * {   // block number in scan order -> its coefficient block
-        const int mcu = n / per_mcu, qq = n - mcu * per_mcu;
-        const int my = mcu / mcux, mx = mcu - my * mcux;
-        if (qq < HV) return im.coef + ((size_t)(my * V + qq / H) * (im.pw[0] >> 3) + (size_t)(mx * H + (qq & (H - 1)))) * 64;
-        return im.coef + ((size_t)im.nblk[0] + (qq > HV ? (size_t)im.nblk[1] : 0) + (size_t)my * (im.pw[1] >> 3) + mx) * 64;
-    };
-    int n = n0;
-    if (WRITE) blk = block_ptr(min(n, total_blocks - 1));
-    while (pos < end_bit) {
-        if (cnt <= 32) {
-            acc |= (unsigned long long)__byte_perm(*wp++, 0, 0x0123) << (32 - cnt);
-            cnt += 32;
-        }
-        const bool dc = k == 0;
-        const int slot = dc ? dslot : aslot;
-        const unsigned top16 = (unsigned)(acc >> 48);
-        const unsigned e = look[slot + (top16 >> (16 - HUFF_LOOKAHEAD))];
-        int len = (int)(e >> 8), sym = (int)(e & 0xFF);
-        if (!e) {
-            const int t = slot >> HUFF_LOOKAHEAD;
-            len = HUFF_LOOKAHEAD + 1;
-#pragma unroll
-            for (int l = HUFF_LOOKAHEAD + 1; l <= 16; ++l) len += top16 >= tab.maxleft[t][l] ? 1 : 0;
-            if (len > 16) { len = 16; sym = 0; }
-            else sym = tab.vals[t][tab.valptr[t][len] + (int)(top16 >> (16 - len)) - tab.mincode[t][len]];
-        }
-        acc <<= len;
-        const int s = dc ? sym : (sym & 15), r = dc ? 0 : (sym >> 4);
-        int val = 0;
-        if (s) {
-            const int v = (int)(acc >> (64 - s));
-            acc <<= s;
-            val = v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
-        }
-        cnt -= len + s;
-        pos += len + s;
-        const int kk = dc ? 0 : k + r;
-        if (WRITE && (dc || s) && kk < 64 && n < total_blocks) blk[dc ? 0 : zz[kk]] = (int16_t)val;    // DC: the difference
-        k = dc ? 1 : (s ? kk + 1 : (r == 15 ? k + 16 : 64));
-        if (k >= 64) {
-            k = 0;
-            ++nblocks;
-            ++n;
-            if (++q == per_mcu) q = 0;
-            comp = q < HV ? 0 : q - HV + 1;
-            dslot = ds[comp];
-            aslot = as[comp];
-            if (WRITE) blk = block_ptr(min(n, total_blocks - 1));
-        }
-    }
-    *blocks = nblocks;
-    return pack_state((int)(pos - end_bit), q, k);
-}
-
-// grid (ceil(max n_sub / 128), B).  round 0: guessed start states; round > 0: the previous round's exit state of the left neighbour.
-__global__ void __launch_bounds__(SYNC_THREADS) jpeg_sync_kernel(const JpegImageDev *__restrict__ imgs, int round) {
-    __shared__ JpegHuffDev tab;
-    __shared__ uint8_t zz[64];
-    const JpegImageDev &im = imgs[blockIdx.y];
-    if (im.gpu_entropy != 2 || blockIdx.x * SYNC_THREADS >= im.n_sub) return;
-    if (round > 1 && *im.changed == 0) return;          // this image's states are already the fixed point
-    for (int i = threadIdx.x; i < (int)(sizeof(JpegHuffDev) / 4); i += SYNC_THREADS)
-        reinterpret_cast<unsigned *>(&tab)[i] = __ldg(reinterpret_cast<const unsigned *>(im.huff) + i);
-    if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
-    __syncthreads();
-    const int i = blockIdx.x * SYNC_THREADS + threadIdx.x;
-    if (i >= im.n_sub) return;
-    const unsigned *prev = im.exit_state[(round + 1) & 1];
-    unsigned *cur = im.exit_state[round & 1];
-    long long pos = (long long)i * SUBSEQ_BITS;
-    int q = 0, k = 0;
-    if (i > 0 && round > 0) {
-        const unsigned st = prev[i - 1];
-        pos += st & 31u;
-        q = (st >> 5) & 7u;
-        k = (int)(st >> 8);
-    }
-    const long long end_bit = min((long long)(i + 1) * SUBSEQ_BITS, im.nbits);
-    int blocks = 0;
-    const unsigned out = decode_subsequence<false>(im, tab, &tab.look[0][0], zz, pos, end_bit, q, k, 0, &blocks);
-    if (round > 0 && out != prev[i] ) atomicOr(im.changed + 1, 1);   // [1] collects this round's changes
-    cur[i] = out;
-    im.sub_blocks[i] = blocks;
-}
-
-// one CTA per image: publishes the round's change flag ([0] <- [1], [1] <- 0); with do_scan, turns the block counts into
-// exclusive prefix sums (sub_blocks[i] = number of the block sub-sequence i starts in)
-__global__ void __launch_bounds__(1024) jpeg_sync_epilogue_kernel(const JpegImageDev *__restrict__ imgs, int do_scan) {
-    const JpegImageDev &im = imgs[blockIdx.x];
-    if (im.gpu_entropy != 2) return;
-    if (!do_scan) {
-        if (threadIdx.x == 0) { im.changed[0] = im.changed[1]; im.changed[1] = 0; }
-        return;
-    }
+// exclusive prefix sums of a[0..n) in place by one CTA of 1024 threads; returns the total to every thread
+__device__ __forceinline__ int block_exclusive_scan_1024(int *a, int n) {
     __shared__ int warp_sums[33];
     __shared__ int carry_s;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int base = 0; base < im.n_sub; base += 1024) {
+    for (int base = 0; base < n; base += 1024) {
         const int i = base + threadIdx.x;
-        const int v = i < im.n_sub ? im.sub_blocks[i] : 0;
+        const int v = i < n ? a[i] : 0;
         int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -739,36 +637,329 @@ __global__ void __launch_bounds__(1024) jpeg_sync_epilogue_kernel(const JpegImag
         }
         __syncthreads();
         const int carry = carry_s;
-        if (i < im.n_sub) im.sub_blocks[i] = carry + warp_sums[warp] + incl - v;
+        if (i < n) a[i] = carry + warp_sums[warp] + incl - v;
         __syncthreads();
         if (threadIdx.x == 0) carry_s = carry + warp_sums[32];
         __syncthreads();
     }
+    return carry_s;
 }
 
-// the write pass: every sub-sequence from its exact start state; `final` = index of the exit-state buffer of the last round
-__global__ void __launch_bounds__(SYNC_THREADS) jpeg_write_kernel(const JpegImageDev *__restrict__ imgs, int final) {
+// -- step 0: byte unstuffing on the device.  What jdhuff.c's fill_bit_buffer does with an FF: further FFs are fill bytes, a 00
+// after them makes ONE data byte FF, anything else is a marker and ends the data.  Per byte, with its two neighbours:
+//   dropped: a 00 that follows an FF (stuffing), an FF that is followed by an FF (fill);  marker: an FF followed by neither.
+constexpr int UNSTUFF_THREADS = 256;
+constexpr int UNSTUFF_CHUNK = UNSTUFF_THREADS * 16;
+
+// the 16 bytes at [g, g+16) of a raw segment of n bytes (g % 16 == 0, g < n): bit j of *drop / *mark classifies byte g + j
+__device__ __forceinline__ uint4 unstuff_classify(const uint8_t *__restrict__ raw, int n, int g, unsigned *drop, unsigned *mark) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(raw + g));        // the arena is padded: bytes past n are ignored below
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+    unsigned prev = g > 0 ? __ldg(raw + g - 1) : 0u;
+    const unsigned after = g + 16 < n ? __ldg(raw + g + 16) : 1u;
+    unsigned d = 0, m = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const unsigned b = (w[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+        unsigned nx = j < 15 ? (w[(j + 1) >> 2] >> (((j + 1) & 3) * 8)) & 0xFFu : after;
+        if (g + j + 1 >= n) nx = 1u;                                         // an FF that ends the buffer counts as a marker
+        if (g + j < n) {
+            if ((b == 0u && prev == 0xFFu) || (b == 0xFFu && nx == 0xFFu)) d |= 1u << j;
+            else if (b == 0xFFu && nx != 0u) m |= 1u << j;
+        }
+        prev = b;
+    }
+    *drop = d;
+    *mark = m;
+    return v;
+}
+
+// grid (chunks covering [0, raw_len], B): non-data bytes per chunk, and the first marker (changed[2] = raw_len - position, 0 = none)
+__global__ void __launch_bounds__(UNSTUFF_THREADS) jpeg_unstuff_count_kernel(const JpegImageDev *__restrict__ imgs) {
+    const JpegImageDev &im = imgs[blockIdx.y];
+    const int n = im.raw_len;
+    if (im.gpu_entropy != 2 || (long long)blockIdx.x * UNSTUFF_CHUNK > n) return;
+    const int g = blockIdx.x * UNSTUFF_CHUNK + threadIdx.x * 16;
+    unsigned drop = 0, mark = 0;
+    if (g < n) unstuff_classify(im.raw, n, g, &drop, &mark);
+    int cnt = __popc(drop);
+    int slack = mark ? n - (g + __ffs(mark) - 1) : 0;                        // larger = earlier
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        slack = max(slack, __shfl_xor_sync(0xffffffffu, slack, o));
+    }
+    __shared__ int s_cnt[UNSTUFF_THREADS / 32], s_slack[UNSTUFF_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) { s_cnt[threadIdx.x >> 5] = cnt; s_slack[threadIdx.x >> 5] = slack; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < UNSTUFF_THREADS / 32; ++w) { cnt += s_cnt[w]; slack = max(slack, s_slack[w]); }
+        im.chunk_drop[blockIdx.x] = cnt;
+        if (slack) atomicMax(im.changed + 2, slack);
+    }
+}
+
+// one CTA per image: chunk counts -> non-data bytes before each chunk
+__global__ void __launch_bounds__(1024) jpeg_unstuff_scan_kernel(const JpegImageDev *__restrict__ imgs) {
+    const JpegImageDev &im = imgs[blockIdx.x];
+    if (im.gpu_entropy != 2) return;
+    block_exclusive_scan_1024(im.chunk_drop, im.raw_len / UNSTUFF_CHUNK + 1);
+}
+
+// the data bytes before the first marker, compacted; the thread that owns the end position publishes nbits / n_sub and pads
+__global__ void __launch_bounds__(UNSTUFF_THREADS) jpeg_unstuff_write_kernel(JpegImageDev *__restrict__ imgs) {
+    JpegImageDev &im = imgs[blockIdx.y];
+    const int n = im.raw_len;
+    if (im.gpu_entropy != 2) return;
+    const int end = n - im.changed[2];                                       // first marker, or raw_len
+    if ((long long)blockIdx.x * UNSTUFF_CHUNK > end) return;
+    const int g = blockIdx.x * UNSTUFF_CHUNK + threadIdx.x * 16;
+    unsigned drop = 0, mark = 0;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (g < n) v = unstuff_classify(im.raw, n, g, &drop, &mark);
+    const int cnt = __popc(drop);
+    int incl = cnt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += nb;
+    }
+    __shared__ int s_w[UNSTUFF_THREADS / 32];
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    int before = im.chunk_drop[blockIdx.x] + incl - cnt;                     // non-data bytes before byte g
+    for (int w = 0; w < warp; ++w) before += s_w[w];
+    uint8_t *out = im.clean;
+    if (end >= g && end < g + 16) {
+        const int ulen = end - before - __popc(drop & ((1u << (end - g)) - 1u));
+        im.nbits = (long long)ulen * 8;
+        im.n_sub = (int)(((long long)ulen * 8 + SUBSEQ_BITS - 1) / SUBSEQ_BITS);
+        for (int j = 0; j < 32; ++j) out[ulen + j] = 0;                      // the decoders read a few words past the end
+    }
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+    int o = g - before;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (g + j < end && !((drop >> j) & 1u)) out[o++] = (uint8_t)(w[j >> 2] >> ((j & 3) * 8));
+    }
+}
+
+constexpr int SYNC_THREADS = 128;
+
+// exit state: bits past the sub-sequence end (< 32) | block-in-MCU q << 5 | coefficient position k << 8
+__device__ __forceinline__ unsigned pack_state(int over, int q, int k) { return (unsigned)over | ((unsigned)q << 5) | ((unsigned)k << 8); }
+
+// One Huffman symbol + its value bits from the left-aligned window `acc` (>= 32 valid bits): F.2.2.3 DECODE with the 10-bit
+// lookahead (codes beyond it: count of the left-aligned length boundaries the 16-bit prefix has passed) and F.2.2.1 RECEIVE +
+// EXTEND.  dc: DC table slot, else AC.  Returns the bits consumed; *s / *r: size and run, *val: the extended value.
+__device__ __forceinline__ int huff_symbol(const JpegHuffDev &tab, const uint16_t *look, int slot, bool dc, unsigned long long &acc, int *s_out,
+                                           int *r_out, int *val_out) {
+    const unsigned top16 = (unsigned)(acc >> 48);
+    const unsigned e = look[slot + (top16 >> (16 - HUFF_LOOKAHEAD))];
+    int len = (int)(e >> 8), sym = (int)(e & 0xFF);
+    if (!e) {
+        const int t = slot >> HUFF_LOOKAHEAD;
+        len = HUFF_LOOKAHEAD + 1;
+#pragma unroll
+        for (int l = HUFF_LOOKAHEAD + 1; l <= 16; ++l) len += top16 >= tab.maxleft[t][l] ? 1 : 0;
+        if (len > 16) { len = 16; sym = 0; }
+        else sym = tab.vals[t][tab.valptr[t][len] + (int)(top16 >> (16 - len)) - tab.mincode[t][len]];
+    }
+    acc <<= len;
+    const int s = dc ? sym : (sym & 15);
+    int val = 0;
+    if (s) {
+        const int v = (int)(acc >> (64 - s));
+        acc <<= s;
+        val = v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+    }
+    *s_out = s;
+    *r_out = dc ? 0 : (sym >> 4);
+    *val_out = val;
+    return len + s;
+}
+
+// Decodes from bit `pos` in state (q, k) until the position reaches `end_bit`, without storing anything.  Returns the exit
+// state; *blocks = blocks finished.
+__device__ __forceinline__ unsigned decode_subsequence(const JpegImageDev &im, const JpegHuffDev &tab, const uint16_t *look, long long pos,
+                                                       long long end_bit, int q, int k, int *blocks) {
+    const int HV = im.H * im.V, per_mcu = HV + 2;
+    const int ds[3] = {im.td[0] << HUFF_LOOKAHEAD, im.td[1] << HUFF_LOOKAHEAD, im.td[2] << HUFF_LOOKAHEAD};
+    const int as[3] = {(2 + im.ta[0]) << HUFF_LOOKAHEAD, (2 + im.ta[1]) << HUFF_LOOKAHEAD, (2 + im.ta[2]) << HUFF_LOOKAHEAD};
+    // bit window over the (clean) stream: 64-bit accumulator, left-aligned; aligned big-endian words
+    const unsigned *wp = reinterpret_cast<const unsigned *>(im.stream) + (pos >> 5);
+    unsigned long long acc = ((unsigned long long)__byte_perm(wp[0], 0, 0x0123) << 32) | __byte_perm(wp[1], 0, 0x0123);
+    unsigned wnext = wp[2];                               // loaded one refill ahead of its use (the arena is padded past the end)
+    wp += 3;
+    int cnt = 64 - (int)(pos & 31);
+    acc <<= (int)(pos & 31);
+    int comp = q < HV ? 0 : q - HV + 1;
+    int dslot = ds[comp], aslot = as[comp];
+    int nblocks = 0;
+    while (pos < end_bit) {
+        if (cnt <= 32) {
+            acc |= (unsigned long long)__byte_perm(wnext, 0, 0x0123) << (32 - cnt);
+            cnt += 32;
+            wnext = *wp++;
+        }
+        const bool dc = k == 0;
+        int s, r, val;
+        const int used = huff_symbol(tab, look, dc ? dslot : aslot, dc, acc, &s, &r, &val);
+        cnt -= used;
+        pos += used;
+        k = dc ? 1 : (s ? k + r + 1 : (r == 15 ? k + 16 : 64));
+        if (k >= 64) {
+            k = 0;
+            ++nblocks;
+            if (++q == per_mcu) q = 0;
+            comp = q < HV ? 0 : q - HV + 1;
+            dslot = ds[comp];
+            aslot = as[comp];
+        }
+    }
+    *blocks = nblocks;
+    return pack_state((int)(pos - end_bit), q, k);
+}
+
+// grid (ceil(max n_sub / 128), B).  round 0: guessed start states (position = first bit, q = k = 0); round > 0: the exit state
+// the left neighbour holds now, and only if it differs from the state this sub-sequence was last decoded from.
+__global__ void __launch_bounds__(SYNC_THREADS) jpeg_sync_kernel(const JpegImageDev *__restrict__ imgs, int round) {
     __shared__ JpegHuffDev tab;
+    const JpegImageDev &im = imgs[blockIdx.y];
+    if (im.gpu_entropy != 2 || blockIdx.x * SYNC_THREADS >= im.n_sub) return;
+    if (round > 1 && *im.changed == 0) return;          // this image's states are already the fixed point
+    const int i = blockIdx.x * SYNC_THREADS + threadIdx.x;
+    unsigned st = 0;
+    bool work = i < im.n_sub;
+    if (work && round > 0) {
+        st = i > 0 ? *reinterpret_cast<volatile unsigned *>(im.exit_state + i - 1) : 0u;
+        work = st != im.used_state[i];
+    }
+    if (!__syncthreads_or(work)) return;                 // nothing moved on this CTA's left: skip the table load too
+    for (int t = threadIdx.x; t < (int)(sizeof(JpegHuffDev) / 4); t += SYNC_THREADS)
+        reinterpret_cast<unsigned *>(&tab)[t] = __ldg(reinterpret_cast<const unsigned *>(im.huff) + t);
+    __syncthreads();
+    if (!work) return;
+    const long long pos = (long long)i * SUBSEQ_BITS + (st & 31u);
+    const long long end_bit = min((long long)(i + 1) * SUBSEQ_BITS, im.nbits);
+    int blocks = 0;
+    const unsigned out = decode_subsequence(im, tab, &tab.look[0][0], pos, end_bit, (int)((st >> 5) & 7u), (int)(st >> 8), &blocks);
+    im.used_state[i] = st;
+    if (round == 0 || out != im.exit_state[i]) {
+        im.exit_state[i] = out;
+        if (round > 0) atomicOr(im.changed + 1, 1);      // [1] collects this round's changes
+    }
+    im.sub_blocks[i] = blocks;
+}
+
+// one CTA per image: publishes the round's change flag ([0] <- [1], [1] <- 0); with do_scan, turns the block counts into
+// exclusive prefix sums (sub_blocks[i] = number of the block sub-sequence i starts in)
+__global__ void __launch_bounds__(1024) jpeg_sync_epilogue_kernel(const JpegImageDev *__restrict__ imgs, int do_scan) {
+    const JpegImageDev &im = imgs[blockIdx.x];
+    if (im.gpu_entropy != 2) return;
+    if (!do_scan) {
+        if (threadIdx.x == 0) { im.changed[0] = im.changed[1]; im.changed[1] = 0; }
+        return;
+    }
+    const int total = block_exclusive_scan_1024(im.sub_blocks, im.n_sub);
+    if (threadIdx.x == 0) im.changed[3] = total;          // blocks the stream really holds (the IDCT zeroes the rest)
+}
+
+// the write pass: every sub-sequence from its exact start state.  A block that straddles sub-sequences is written piecewise:
+// each decoder owns the scan positions [k at its start, k at its end) — zeros included — so the pieces are disjoint and
+// together cover the block; whole blocks leave as one 128-byte warp store (stage_flush).
+__global__ void __launch_bounds__(SYNC_THREADS) jpeg_write_kernel(const JpegImageDev *__restrict__ imgs) {
+    __shared__ JpegHuffDev tab;
+    __shared__ unsigned stage[SYNC_THREADS * STAGE_PITCH];
     __shared__ uint8_t zz[64];
     const JpegImageDev &im = imgs[blockIdx.y];
     if (im.gpu_entropy != 2 || blockIdx.x * SYNC_THREADS >= im.n_sub) return;
-    for (int i = threadIdx.x; i < (int)(sizeof(JpegHuffDev) / 4); i += SYNC_THREADS)
-        reinterpret_cast<unsigned *>(&tab)[i] = __ldg(reinterpret_cast<const unsigned *>(im.huff) + i);
     if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
+    for (int t = threadIdx.x; t < (int)(sizeof(JpegHuffDev) / 4); t += SYNC_THREADS)
+        reinterpret_cast<unsigned *>(&tab)[t] = __ldg(reinterpret_cast<const unsigned *>(im.huff) + t);
+    for (int t = threadIdx.x; t < SYNC_THREADS * STAGE_PITCH; t += SYNC_THREADS) stage[t] = 0u;
     __syncthreads();
+    const uint16_t *look = &tab.look[0][0];
+    const int lane = threadIdx.x & 31;
+    unsigned *stage_warp = stage + (threadIdx.x & ~31) * STAGE_PITCH;
+    int16_t *my_row = reinterpret_cast<int16_t *>(stage + threadIdx.x * STAGE_PITCH);
     const int i = blockIdx.x * SYNC_THREADS + threadIdx.x;
-    if (i >= im.n_sub) return;
+    const bool live = i < im.n_sub;
+    const int HV = im.H * im.V, per_mcu = HV + 2;
+    const int total_blocks = min(im.mcux * im.mcuy * per_mcu, im.changed[3]);
+    const int ds0 = im.td[0] << HUFF_LOOKAHEAD, ds1 = im.td[1] << HUFF_LOOKAHEAD, ds2 = im.td[2] << HUFF_LOOKAHEAD;
+    const int as0 = (2 + im.ta[0]) << HUFF_LOOKAHEAD, as1 = (2 + im.ta[1]) << HUFF_LOOKAHEAD, as2 = (2 + im.ta[2]) << HUFF_LOOKAHEAD;
     long long pos = (long long)i * SUBSEQ_BITS;
     int q = 0, k = 0;
-    if (i > 0) {
-        const unsigned st = im.exit_state[final][i - 1];
+    if (live && i > 0) {
+        const unsigned st = im.exit_state[i - 1];
         pos += st & 31u;
         q = (st >> 5) & 7u;
         k = (int)(st >> 8);
     }
-    const long long end_bit = min((long long)(i + 1) * SUBSEQ_BITS, im.nbits);
-    int blocks = 0;
-    decode_subsequence<true>(im, tab, &tab.look[0][0], zz, pos, end_bit, q, k, im.sub_blocks[i], &blocks);
+    const long long end_bit = live ? min((long long)(i + 1) * SUBSEQ_BITS, im.nbits) : 0;
+    int n = live ? im.sub_blocks[i] : 0;                  // number (scan order) of the block the start lies in
+    int kfirst = k;                                       // first scan position of the current block this thread owns
+    int dslot = q < HV ? ds0 : (q == HV ? ds1 : ds2), aslot = q < HV ? as0 : (q == HV ? as1 : as2);
+    const unsigned *wp = reinterpret_cast<const unsigned *>(im.stream) + (live ? (pos >> 5) : 0);
+    unsigned long long acc = ((unsigned long long)__byte_perm(wp[0], 0, 0x0123) << 32) | __byte_perm(wp[1], 0, 0x0123);
+    unsigned wnext = wp[2];                               // loaded one refill ahead of its use
+    wp += 3;
+    int cnt = 64 - (int)(pos & 31);
+    acc <<= (int)(pos & 31);
+    bool active = live && pos < end_bit;
+    while (__any_sync(0xffffffffu, active)) {
+        bool done = false;
+        if (active) {
+            if (cnt <= 32) {
+                acc |= (unsigned long long)__byte_perm(wnext, 0, 0x0123) << (32 - cnt);
+                cnt += 32;
+                wnext = *wp++;
+            }
+            const bool dc = k == 0;
+            int s, r, val;
+            const int used = huff_symbol(tab, look, dc ? dslot : aslot, dc, acc, &s, &r, &val);
+            cnt -= used;
+            pos += used;
+            const int kk = dc ? 0 : k + r;
+            if ((dc || s) && kk < 64) my_row[dc ? 0 : zz[kk]] = (int16_t)val;   // DC: the difference (jpeg_dc_kernel integrates)
+            k = dc ? 1 : (s ? kk + 1 : (r == 15 ? k + 16 : 64));
+            done = k >= 64;
+            active = pos < end_bit;
+        }
+        unsigned fm = __ballot_sync(0xffffffffu, done);
+        if (fm) {
+            __syncwarp();
+            do {
+                const int src = __ffs(fm) - 1;
+                fm &= fm - 1;
+                const int ns = __shfl_sync(0xffffffffu, n, src);
+                const int kf = __shfl_sync(0xffffffffu, kfirst, src);
+                stage_flush(stage_warp, src, lane, im.coef + (size_t)ns * 64, kf, 64, ns < total_blocks);
+            } while (fm);
+            __syncwarp();
+        }
+        if (done) {                                                          // next block of the scan
+            k = 0;
+            kfirst = 0;
+            ++n;
+            if (++q == per_mcu) q = 0;
+            dslot = q < HV ? ds0 : (q == HV ? ds1 : ds2);
+            aslot = q < HV ? as0 : (q == HV ? as1 : as2);
+        }
+    }
+    // the block each sub-sequence ends in: positions [kfirst, k) are this thread's, the successor continues at k
+    unsigned fm = __ballot_sync(0xffffffffu, live && k > kfirst);
+    __syncwarp();
+    while (fm) {
+        const int src = __ffs(fm) - 1;
+        fm &= fm - 1;
+        const int ns = __shfl_sync(0xffffffffu, n, src);
+        const int kf = __shfl_sync(0xffffffffu, kfirst, src);
+        const int ke = __shfl_sync(0xffffffffu, min(k, 64), src);
+        stage_flush(stage_warp, src, lane, im.coef + (size_t)ns * 64, kf, ke, ns < total_blocks);
+    }
 }
 
 // DC prediction (T.81 F.2.1.3.1: DIFF is relative to the previous block OF THE SAME COMPONENT in scan order; no restart markers
@@ -777,11 +968,9 @@ __global__ void __launch_bounds__(1024) jpeg_dc_kernel(const JpegImageDev *__res
     const JpegImageDev &im = imgs[blockIdx.y];
     if (im.gpu_entropy != 2) return;
     const int c = blockIdx.x;
-    const int H = im.H, V = im.V, HV = H * V, mcux = im.mcux;
+    const int HV = im.H * im.V, per_mcu = HV + 2;
     const int per = c == 0 ? HV : 1;                       // blocks of this component per MCU
     const int total = im.mcux * im.mcuy * per;
-    int16_t *base = im.coef + (c == 0 ? 0 : ((size_t)im.nblk[0] + (c == 2 ? (size_t)im.nblk[1] : 0)) * 64);
-    const int bw = im.pw[c] >> 3;
     __shared__ int warp_sums[33];
     __shared__ int carry_s;
     if (threadIdx.x == 0) carry_s = 0;
@@ -793,8 +982,7 @@ __global__ void __launch_bounds__(1024) jpeg_dc_kernel(const JpegImageDev *__res
         int v = 0;
         if (n < total) {
             const int mcu = n / per, sub = n - mcu * per;
-            const int my = mcu / mcux, mx = mcu - my * mcux;
-            blk = c == 0 ? base + ((size_t)(my * V + sub / H) * bw + (size_t)(mx * H + (sub & (H - 1)))) * 64 : base + ((size_t)my * bw + mx) * 64;
+            blk = im.coef + ((size_t)mcu * per_mcu + (c == 0 ? sub : HV + c - 1)) * 64;
             v = blk[0];
         }
         int incl = v;
@@ -839,14 +1027,20 @@ __global__ void __launch_bounds__(IDCT_BLOCKS * 8) jpeg_idct_kernel(const JpegIm
     if (live) {
         if (bi >= im.nblk[0]) { bi -= im.nblk[0]; c = 1; }
         if (c == 1 && bi >= im.nblk[1]) { bi -= im.nblk[1]; c = 2; }
-        const int16_t *in = im.coef + (size_t)gb * 64 + k;    // column k of the block
+        // the arena is in scan order: plane position (c, yb, xb) -> block number n
+        const int bw_c = im.pw[c] >> 3, yb = bi / bw_c, xb = bi - yb * bw_c, HV = im.H * im.V;
+        const int n = c == 0 ? ((yb / im.V) * im.mcux + xb / im.H) * (HV + 2) + (yb % im.V) * im.H + xb % im.H
+                             : (yb * im.mcux + xb) * (HV + 2) + HV + c - 1;
+        const bool held = im.gpu_entropy != 2 || n < im.changed[3];   // a truncated stream holds fewer blocks: the rest is zero
+        const int16_t *in = im.coef + (size_t)n * 64 + k;             // column k of the block
         const uint16_t *q = im.qt[c] + k;
         int v[8], o[8];
         bool ac0 = true;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            v[r] = (int)in[8 * r] * (int)q[8 * r];            // DEQUANTIZE
-            if (r) ac0 = ac0 && in[8 * r] == 0;
+            const int cf = held ? (int)in[8 * r] : 0;
+            v[r] = cf * (int)q[8 * r];                        // DEQUANTIZE
+            if (r) ac0 = ac0 && cf == 0;
         }
         if (ac0) {   // jidctint.c's shortcut (identical to the general path for an all-zero AC column)
             const int dc = v[0] << JPASS1_BITS;
@@ -971,11 +1165,6 @@ __global__ void __launch_bounds__(128) jpeg_color_kernel(const JpegImageDev *__r
     }
 }
 
-// zero-fill of the coefficient arena (the Huffman kernel writes non-zero coefficients only): 128-bit streaming stores
-__global__ void __launch_bounds__(256) jpeg_zero_kernel(uint4 *__restrict__ p, size_t n16) {
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) __stcs(p + i, z);
-}
 
 }  // namespace fd
 
@@ -1037,9 +1226,9 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
         if (errs[i]) return fail(FD_ERR_INVALID, "fd_decode_jpeg_batch: image " + std::to_string(i) + ": " + errs[i]);
     t_parse = now();
     // layout: coefficient arena (device; pinned mirror for host-decoded images), plane arena, frame arena, stream / aux arenas
-    std::vector<size_t> coef_off(B), plane_off(B), frame_off(B), stream_off(B), aux_off(B), ustage_off(B), sync_off(B);
-    size_t coef_total = 0, plane_total = 0, frame_total = 0, stream_total = 0, aux_total = 0, host_coef_total = 0, ustage_total = 0, sync_total = 0;
-    int max_blocks = 0, max_h = 0, max_w = 0, max_iv = 0, max_sub = 0, n_rst = 0, n_sync = 0;
+    std::vector<size_t> coef_off(B), plane_off(B), frame_off(B), stream_off(B), aux_off(B), raw_off(B), sync_off(B);
+    size_t coef_total = 0, plane_total = 0, frame_total = 0, stream_total = 0, aux_total = 0, host_coef_total = 0, raw_total = 0, sync_total = 0;
+    int max_blocks = 0, max_h = 0, max_w = 0, max_iv = 0, max_sub = 0, max_chunks = 0, n_rst = 0, n_sync = 0;
     for (int i = 0; i < B; ++i) {
         const JpegHeader &j = hdr[i];
         const size_t nblk = j.blocks[0] + j.blocks[1] + j.blocks[2];
@@ -1063,14 +1252,17 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
         } else if (mode[i] == 2) {
             ++n_sync;
             stream_off[i] = stream_total;
-            stream_total += (j.scan_len + 32 + 15) & ~(size_t)15;
-            ustage_off[i] = ustage_total;
-            ustage_total += (j.scan_len + 32 + 15) & ~(size_t)15;
+            stream_total += (j.scan_len + 64 + 15) & ~(size_t)15;
+            raw_off[i] = raw_total;
+            raw_total += (j.scan_len + 32 + 15) & ~(size_t)15;
             aux_off[i] = aux_total;
             aux_total += (sizeof(JpegHuffDev) + 15) & ~(size_t)15;
             const size_t nsub_cap = (j.scan_len * 8 + SUBSEQ_BITS - 1) / SUBSEQ_BITS + 1;
+            const size_t nchunks = j.scan_len / UNSTUFF_CHUNK + 1;
             sync_off[i] = sync_total;
-            sync_total += (nsub_cap * 3 + 4) * sizeof(int);         // exit states x 2, block counts (+1)
+            sync_total += (nsub_cap * 3 + nchunks + 4) * sizeof(int);   // exit states, start states, block counts; chunk counts
+            max_sub = std::max<int>(max_sub, (int)nsub_cap - 1);
+            max_chunks = std::max<int>(max_chunks, (int)nchunks);
         } else {
             host_coef_total += nblk * 64;
         }
@@ -1085,42 +1277,29 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
     FD_TRY(ctx->jpeg_stream.reserve(stream_total + 64));
     FD_TRY(ctx->jpeg_aux.reserve(aux_total + 64));
     FD_TRY(ctx->jpeg_aux_host.reserve(aux_total + 64));
-    FD_TRY(ctx->jpeg_ustage_host.reserve(ustage_total + 64));
+    FD_TRY(ctx->jpeg_raw.reserve(raw_total + 64));
     FD_TRY(ctx->jpeg_sync.reserve(sync_total + 64));
-    FD_TRY(ctx->jpeg_flags.reserve(sizeof(int) * 2 * (size_t)B));
-    FD_TRY(ctx->jpeg_flags_host.reserve(sizeof(int) * 2 * (size_t)B));
+    FD_TRY(ctx->jpeg_flags.reserve(sizeof(int) * 4 * (size_t)B));
+    FD_TRY(ctx->jpeg_flags_host.reserve(sizeof(int) * 4 * (size_t)B));
     const double t_layout = now();
     FD_CUDA(cudaEventSynchronize(ctx->ev[3]));   // the previous call's H2D copies have left the pinned staging buffers
     t_wait = now();
     int64_t h2d = 0;
-    std::vector<size_t> ulen(B, 0);
-    // 1a. device paths: the streams go up compressed (mode 2: with the stuffed zero bytes removed on the way, one image per thread)
+    // 1a. device paths: the entropy-coded segments go up as they are
     if (n_gpu) {
-        // the decoders write non-zero coefficients only (blocks are 128 bytes: the arena is a whole number of uint4)
-        jpeg_zero_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->jpeg_coef.as<uint4>(), coef_total * sizeof(int16_t) / 16);
-        FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_zero_kernel");
         unsigned char *aux = ctx->jpeg_aux_host.as<unsigned char>();
-        uint8_t *ustage = ctx->jpeg_ustage_host.as<uint8_t>();
-        if (n_sync)
-            parallel_images(n_sync, [&](int i) {
-                if (mode[i] == 2) ulen[i] = unstuff_scan(hdr[i].scan, hdr[i].scan_len, ustage + ustage_off[i]);
-            });
         // (one copy queue: alternating the copies over two streams was measured 2x SLOWER, 5.0 vs 2.4 ms for 64 x 1.26 MB)
         for (int i = 0; i < B; ++i) {
             if (!mode[i]) continue;
             fill_huff_dev(hdr[i], reinterpret_cast<JpegHuffDev *>(aux + aux_off[i]));
-            if (mode[i] == 1) {
-                memcpy(aux + aux_off[i] + sizeof(JpegHuffDev), ivs[i].data(), ivs[i].size() * sizeof(uint32_t));
-                FD_CUDA(cudaMemcpyAsync(ctx->jpeg_stream.as<uint8_t>() + stream_off[i], hdr[i].scan, hdr[i].scan_len, cudaMemcpyHostToDevice, ctx->stream));
-                h2d += (int64_t)hdr[i].scan_len;
-            } else {
-                FD_CUDA(cudaMemcpyAsync(ctx->jpeg_stream.as<uint8_t>() + stream_off[i], ustage + ustage_off[i], ulen[i] + 16, cudaMemcpyHostToDevice, ctx->stream));
-                h2d += (int64_t)ulen[i] + 16;
-            }
+            if (mode[i] == 1) memcpy(aux + aux_off[i] + sizeof(JpegHuffDev), ivs[i].data(), ivs[i].size() * sizeof(uint32_t));
+            uint8_t *dst = mode[i] == 1 ? ctx->jpeg_stream.as<uint8_t>() + stream_off[i] : ctx->jpeg_raw.as<uint8_t>() + raw_off[i];
+            if (hdr[i].scan_len) FD_CUDA(cudaMemcpyAsync(dst, hdr[i].scan, hdr[i].scan_len, cudaMemcpyHostToDevice, ctx->stream));
+            h2d += (int64_t)hdr[i].scan_len;
         }
         FD_CUDA(cudaMemcpyAsync(ctx->jpeg_aux.p, aux, aux_total, cudaMemcpyHostToDevice, ctx->stream));
         h2d += (int64_t)aux_total;
-        if (n_sync) FD_CUDA(cudaMemsetAsync(ctx->jpeg_flags.p, 0, sizeof(int) * 2 * (size_t)B, ctx->stream));
+        if (n_sync) FD_CUDA(cudaMemsetAsync(ctx->jpeg_flags.p, 0, sizeof(int) * 4 * (size_t)B, ctx->stream));
     }
     // 1b. host path: entropy decoding on the host, images are independent, one per worker thread
     std::vector<size_t> host_off(B, 0);
@@ -1181,15 +1360,18 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
             d.n_intervals = (int)(ivs[i].size() / 2);
             d.iv = reinterpret_cast<const uint32_t *>(ctx->jpeg_aux.as<unsigned char>() + aux_off[i] + sizeof(JpegHuffDev));
         } else if (mode[i] == 2) {
-            d.nbits = (long long)ulen[i] * 8;
-            d.n_sub = (int)((d.nbits + SUBSEQ_BITS - 1) / SUBSEQ_BITS);
+            d.raw = ctx->jpeg_raw.as<uint8_t>() + raw_off[i];
+            d.clean = ctx->jpeg_stream.as<uint8_t>() + stream_off[i];
+            d.raw_len = (int)j.scan_len;
+            d.nbits = 0;                                            // both set by jpeg_unstuff_write_kernel
+            d.n_sub = 0;
             const size_t cap = (j.scan_len * 8 + SUBSEQ_BITS - 1) / SUBSEQ_BITS + 1;
             unsigned *sy = reinterpret_cast<unsigned *>(ctx->jpeg_sync.as<unsigned char>() + sync_off[i]);
-            d.exit_state[0] = sy;
-            d.exit_state[1] = sy + cap;
+            d.exit_state = sy;
+            d.used_state = sy + cap;
             d.sub_blocks = reinterpret_cast<int *>(sy + 2 * cap);
-            d.changed = ctx->jpeg_flags.as<int>() + 2 * i;
-            max_sub = std::max(max_sub, d.n_sub);
+            d.chunk_drop = reinterpret_cast<int *>(sy + 3 * cap);
+            d.changed = ctx->jpeg_flags.as<int>() + 4 * i;
         }
         frames_out[i].data = d.bgr;
         frames_out[i].height = j.h;
@@ -1210,31 +1392,44 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
         jpeg_huffman_kernel<<<g0, HUFF_THREADS, 0, ctx->stream>>>(ddesc);
         FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_huffman_kernel");
     }
-    // 3b. streams without restart markers: self-synchronising rounds until a round changes no exit state, then count -> scan -> write
+    // 3b. streams without restart markers: unstuff on the device, then self-synchronising rounds until one changes no exit state
+    //     (rounds are enqueued in groups — a round with nothing to do costs a few microseconds — and the flags read once per
+    //     group), then count -> scan -> write -> DC prefix
     ctx->jpeg_last_rounds = 0;
+    if (n_sync) {
+        dim3 gu(max_chunks, B);
+        jpeg_unstuff_count_kernel<<<gu, UNSTUFF_THREADS, 0, ctx->stream>>>(ddesc);
+        FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_unstuff_count_kernel");
+        jpeg_unstuff_scan_kernel<<<B, 1024, 0, ctx->stream>>>(ddesc);
+        FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_unstuff_scan_kernel");
+        jpeg_unstuff_write_kernel<<<gu, UNSTUFF_THREADS, 0, ctx->stream>>>(ctx->jpeg_desc.as<JpegImageDev>());
+        FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_unstuff_write_kernel");
+    }
     if (n_sync && max_sub > 0) {
         dim3 gs((max_sub + SYNC_THREADS - 1) / SYNC_THREADS, B);
         jpeg_sync_kernel<<<gs, SYNC_THREADS, 0, ctx->stream>>>(ddesc, 0);
         FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_sync_kernel");
         int round = 0;
         int *flags = ctx->jpeg_flags_host.as<int>();
-        for (;;) {
-            ++round;
-            jpeg_sync_kernel<<<gs, SYNC_THREADS, 0, ctx->stream>>>(ddesc, round);
-            FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_sync_kernel");
-            jpeg_sync_epilogue_kernel<<<B, 1024, 0, ctx->stream>>>(ddesc, 0);
-            FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_sync_epilogue_kernel");
-            FD_CUDA(cudaMemcpyAsync(flags, ctx->jpeg_flags.p, sizeof(int) * 2 * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+        for (int group = 6;; group = 4) {
+            for (int r = 0; r < group; ++r) {
+                ++round;
+                jpeg_sync_kernel<<<gs, SYNC_THREADS, 0, ctx->stream>>>(ddesc, round);
+                FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_sync_kernel");
+                jpeg_sync_epilogue_kernel<<<B, 32, 0, ctx->stream>>>(ddesc, 0);
+                FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_sync_epilogue_kernel");
+            }
+            FD_CUDA(cudaMemcpyAsync(flags, ctx->jpeg_flags.p, sizeof(int) * 4 * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
             FD_CUDA(cudaStreamSynchronize(ctx->stream));
             bool any = false;
-            for (int i = 0; i < B; ++i) any = any || (mode[i] == 2 && flags[2 * i] != 0);
+            for (int i = 0; i < B; ++i) any = any || (mode[i] == 2 && flags[4 * i] != 0);
             if (!any) break;
-            FD_REQUIRE(round <= max_sub + 2, "fd_decode_jpeg_batch: the sub-sequence states did not converge (corrupt stream?)");
+            FD_REQUIRE(round <= max_sub + 8, "fd_decode_jpeg_batch: the sub-sequence states did not converge (corrupt stream?)");
         }
         ctx->jpeg_last_rounds = round;
         jpeg_sync_epilogue_kernel<<<B, 1024, 0, ctx->stream>>>(ddesc, 1);
         FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_sync_epilogue_kernel");
-        jpeg_write_kernel<<<gs, SYNC_THREADS, 0, ctx->stream>>>(ddesc, round & 1);
+        jpeg_write_kernel<<<gs, SYNC_THREADS, 0, ctx->stream>>>(ddesc);
         FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_write_kernel");
         jpeg_dc_kernel<<<dim3(3, B), 1024, 0, ctx->stream>>>(ddesc);
         FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_dc_kernel");

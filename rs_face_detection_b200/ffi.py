@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfd_b200.so")
+LIB_PATH = os.environ.get("FD_B200_LIB") or os.path.join(_HERE, "libfd_b200.so")   # FD_B200_LIB: A/B a differently built library
 
 FD_MAX_STRIDES = 8
 FD_MAX_ANCHORS = 4

@@ -12,7 +12,7 @@ from rs_face_detection_b200.utils import synth
 ctx = Context(0)
 frames = [synth.make_frame(1080, 1920, 2000 + i) for i in range(64)]
 out = {}
-for rst in [0, 4, 16, 120, 480]:
+for rst in [int(x) for x in os.environ.get("RSTS", "0,4,16,120,480").split(",")]:
     pj = [pinned_like(np.asarray(cv2.imencode(".jpg", f, [cv2.IMWRITE_JPEG_QUALITY, 90] + ([cv2.IMWRITE_JPEG_RST_INTERVAL, rst] if rst else []))[1], np.uint8).ravel()) for f in frames]
     st = [p.array for p in pj]
     for _ in range(2):
@@ -28,4 +28,4 @@ for rst in [0, 4, 16, 120, 480]:
     ctx.profile(False)
     out[rst] = dict(wall_ms=wall * 1e3, mb=sum(s.size for s in st) / 1e6, kernels={k: v[1] / v[0] for k, v in prof.items()}, stats=ctx.jpeg_last_stats())
     print(rst, out[rst], flush=True)
-json.dump(out, open("gpurun_out/jpeg_profile.json", "w"), indent=1)
+json.dump(out, open(os.environ.get("OUT", "gpurun_out/jpeg_profile.json"), "w"), indent=1)
