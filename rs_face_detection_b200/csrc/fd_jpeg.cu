@@ -1023,14 +1023,13 @@ __global__ void __launch_bounds__(IDCT_BLOCKS * 8) jpeg_idct_kernel(const JpegIm
     const int gb = blockIdx.x * IDCT_BLOCKS + lb;
     const int total = im.nblk[0] + im.nblk[1] + im.nblk[2];
     const bool live = gb < total;
-    int c = 0, bi = gb;
+    // the arena is in scan order (the CTA reads 32 consecutive blocks = 4 KB): block n -> component c, block (yb, xb) of its plane
+    const int n = gb, HV = im.H * im.V;
+    const int mcu = n / (HV + 2), qb = n - mcu * (HV + 2);
+    const int my = mcu / im.mcux, mx = mcu - my * im.mcux;
+    const int c = qb < HV ? 0 : qb - HV + 1;
+    const int yb = c == 0 ? my * im.V + qb / im.H : my, xb = c == 0 ? mx * im.H + qb % im.H : mx;
     if (live) {
-        if (bi >= im.nblk[0]) { bi -= im.nblk[0]; c = 1; }
-        if (c == 1 && bi >= im.nblk[1]) { bi -= im.nblk[1]; c = 2; }
-        // the arena is in scan order: plane position (c, yb, xb) -> block number n
-        const int bw_c = im.pw[c] >> 3, yb = bi / bw_c, xb = bi - yb * bw_c, HV = im.H * im.V;
-        const int n = c == 0 ? ((yb / im.V) * im.mcux + xb / im.H) * (HV + 2) + (yb % im.V) * im.H + xb % im.H
-                             : (yb * im.mcux + xb) * (HV + 2) + HV + c - 1;
         const bool held = im.gpu_entropy != 2 || n < im.changed[3];   // a truncated stream holds fewer blocks: the rest is zero
         const int16_t *in = im.coef + (size_t)n * 64 + k;             // column k of the block
         const uint16_t *q = im.qt[c] + k;
@@ -1058,9 +1057,7 @@ __global__ void __launch_bounds__(IDCT_BLOCKS * 8) jpeg_idct_kernel(const JpegIm
 #pragma unroll
     for (int x = 0; x < 8; ++x) v[x] = ws[lb][8 * k + x];     // row k
     jpeg_idct_1d(v, JCONST_BITS + JPASS1_BITS + 3, o);
-    const int bw = im.pw[c] >> 3;
-    const int by = bi / bw, bx = bi - by * bw;
-    uint8_t *dst = im.plane[c] + (size_t)(by * 8 + k) * im.pw[c] + bx * 8;
+    uint8_t *dst = im.plane[c] + (size_t)(yb * 8 + k) * im.pw[c] + xb * 8;
     uint2 out;
     out.x = jpeg_range_limit(o[0]) | (jpeg_range_limit(o[1]) << 8) | (jpeg_range_limit(o[2]) << 16) | (jpeg_range_limit(o[3]) << 24);
     out.y = jpeg_range_limit(o[4]) | (jpeg_range_limit(o[5]) << 8) | (jpeg_range_limit(o[6]) << 16) | (jpeg_range_limit(o[7]) << 24);
