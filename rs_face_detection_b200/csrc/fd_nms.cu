@@ -683,11 +683,40 @@ struct RoundsArgs {
     int *tile_counts;
     unsigned *ballots;
     int *keep_ranks;
-    int *out_state;         // [1] = total kept
+    int *out_state;         // [0] = this path owns the problem, [1] = total kept
     IouParams iou;
+    const float4 *sbox;     // brute mode (mid path: no grid): boxes in rank order, a box without a usable list rescans every earlier box
+    int brute;
+    int mode;               // brute mode: 0 nms.rs / 1 cpu_nms.rs comparison for the full IEEE test
+    const int *status;      // brute mode: [0] NaN score seen, [2] != 0 -> some box is not "fast ok": full IEEE test
+    int *final_keep;        // brute mode: kept SOURCE indices in rank order (keys[rank] low word) and {count, NaN flag}, written here
+    const u64 *final_keys;  //             instead of keep_ranks + map_keep_kernel
+    int *final_num;
+    long long *dbg;         // FD_NMS_DBG: globaltimer stamps of block 0 (slots 5..7)
 };
 
+__device__ __forceinline__ void mid_stamp(long long *dbg, int slot) {
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        dbg[slot] = t;
+    }
+}
+
 constexpr int ROUND_SWEEPS = 8;
+
+// brute-mode stand-in for for_each_predecessor: every earlier box that suppresses box r
+template <class F>
+__device__ __forceinline__ void for_each_earlier(int r, const float4 *__restrict__ sbox, const IouParams &P, bool fast, int mode, F &&visit) {
+    const float4 bi = __ldcg(sbox + r);
+    const float ai = box_area(bi);
+    for (int j = 0; j < r; ++j) {
+        const float4 bj = __ldcg(sbox + j);
+        const bool s = fast ? iou_suppresses_exact(bj, box_area(bj), bi, ai, P)
+                            : (mode == 0 ? iou_suppresses_full<0>(bj, bi, P.thr) : iou_suppresses_full<1>(bj, bi, P.thr));
+        if (s && !visit(j)) return;
+    }
+}
 
 // decides box r if possible; idx(e) yields its e-th listed predecessor
 template <class IdxFn>
@@ -706,11 +735,9 @@ __device__ __forceinline__ int try_decide_listed(int cnt, IdxFn idx, const unsig
     return any_kept ? 2 : (all_sup ? 1 : 0);
 }
 
-__global__ void __launch_bounds__(NT, 1) nms_rounds_kernel(RoundsArgs a) {
-    extern __shared__ int sadj[];  // [ADJ_SMEM][NT]: head of the predecessor list of each thread's first box, kept across sweeps
-    __shared__ int red[32];
-    const GridCfg c = *a.cfg;
-    if (!c.use) return;  // uniform over the grid: the peel kernel handles this problem
+// sadj: [ADJ_SMEM][NT] ints of shared memory (head of the predecessor list of each thread's first box, kept across sweeps)
+__device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridCfg &c, int *sadj, int *red) {
+    const bool bfast = a.brute && a.iou.fast && __ldcg(&a.status[2]) == 0;
     cg::grid_group grid = cg::this_grid();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x;
@@ -718,10 +745,11 @@ __global__ void __launch_bounds__(NT, 1) nms_rounds_kernel(RoundsArgs a) {
     volatile unsigned char *state = a.state;
     int cnt0 = 0;
     if (gtid < a.N) {
-        cnt0 = a.adj_cnt[gtid];
+        cnt0 = __ldcg(&a.adj_cnt[gtid]);   // (ld.cg throughout: in the mid path the lists were written earlier in this same kernel)
+        if (cnt0 > ADJ_CAP) cnt0 = -1;                 // (mid path: the counter kept running past the list's capacity)
         const int4 *mine4 = reinterpret_cast<const int4 *>(a.adj + (size_t)gtid * ADJ_CAP);
         for (int e = 0; e < min(cnt0, ADJ_SMEM); e += 4) {
-            const int4 p = __ldg(mine4 + (e >> 2));
+            const int4 p = __ldcg(mine4 + (e >> 2));
             sadj[(e + 0) * NT + tid] = p.x;
             sadj[(e + 1) * NT + tid] = p.y;
             sadj[(e + 2) * NT + tid] = p.z;
@@ -737,16 +765,18 @@ __global__ void __launch_bounds__(NT, 1) nms_rounds_kernel(RoundsArgs a) {
                 int d;
                 if (cnt0 >= 0) {
                     const int *mine = a.adj + (size_t)gtid * ADJ_CAP;
-                    d = try_decide_listed(cnt0, [&](int e) { return e < ADJ_SMEM ? sadj[e * NT + tid] : __ldg(mine + e); }, a.state);
+                    d = try_decide_listed(cnt0, [&](int e) { return e < ADJ_SMEM ? sadj[e * NT + tid] : __ldcg(mine + e); }, a.state);
                 }
                 else {
                     bool any_kept = false, all_sup = true;
-                    for_each_predecessor(a.pos_of_rank[gtid], a.keys, c, a.cell_start, a.cell_end, a.cbox, a.carea, a.iou, [&](int rj) {
+                    auto visit = [&](int rj) {
                         const unsigned sj = ld_state(a.state + rj);
                         if (sj == 1u) { any_kept = true; return false; }
                         if (sj == 0u) all_sup = false;
                         return true;
-                    });
+                    };
+                    if (a.brute) for_each_earlier(gtid, a.sbox, a.iou, bfast, a.mode, visit);
+                    else for_each_predecessor(a.pos_of_rank[gtid], a.keys, c, a.cell_start, a.cell_end, a.cbox, a.carea, a.iou, visit);
                     d = any_kept ? 2 : (all_sup ? 1 : 0);
                 }
                 if (d) { state[gtid] = (unsigned char)d; first_done = true; }
@@ -754,19 +784,21 @@ __global__ void __launch_bounds__(NT, 1) nms_rounds_kernel(RoundsArgs a) {
             }
             for (int r = gtid + gstride; r < a.N; r += gstride) {  // only when N exceeds the resident thread count
                 if (state[r] != 0) continue;
-                const int cnt = a.adj_cnt[r];
+                const int cnt = __ldcg(&a.adj_cnt[r]);
                 int d;
-                if (cnt >= 0) {
+                if (cnt >= 0 && cnt <= ADJ_CAP) {
                     const int *mine = a.adj + (size_t)r * ADJ_CAP;
-                    d = try_decide_listed(cnt, [&](int e) { return __ldg(mine + e); }, a.state);
+                    d = try_decide_listed(cnt, [&](int e) { return __ldcg(mine + e); }, a.state);
                 } else {
                     bool any_kept = false, all_sup = true;
-                    for_each_predecessor(a.pos_of_rank[r], a.keys, c, a.cell_start, a.cell_end, a.cbox, a.carea, a.iou, [&](int rj) {
+                    auto visit = [&](int rj) {
                         const unsigned sj = ld_state(a.state + rj);
                         if (sj == 1u) { any_kept = true; return false; }
                         if (sj == 0u) all_sup = false;
                         return true;
-                    });
+                    };
+                    if (a.brute) for_each_earlier(r, a.sbox, a.iou, bfast, a.mode, visit);
+                    else for_each_predecessor(a.pos_of_rank[r], a.keys, c, a.cell_start, a.cell_end, a.cbox, a.carea, a.iou, visit);
                     d = any_kept ? 2 : (all_sup ? 1 : 0);
                 }
                 if (d) state[r] = (unsigned char)d;
@@ -785,6 +817,7 @@ __global__ void __launch_bounds__(NT, 1) nms_rounds_kernel(RoundsArgs a) {
         }
         if (left == 0) break;
     }
+    mid_stamp(a.dbg, 5);
     // ordered output of the kept ranks
     const int ntiles = (a.N + NT - 1) / NT;
     for (int t = blockIdx.x; t < ntiles; t += G) {
@@ -809,14 +842,165 @@ __global__ void __launch_bounds__(NT, 1) nms_rounds_kernel(RoundsArgs a) {
             if (w < warp) wpre += __popc(bw);
         }
         const unsigned mine = __shfl_sync(0xffffffffu, myb, warp);
-        if ((mine >> lane) & 1u) a.keep_ranks[offset + wpre + __popc(mine & ((1u << lane) - 1u))] = t * NT + tid;
+        if ((mine >> lane) & 1u) {
+            const int pos = offset + wpre + __popc(mine & ((1u << lane) - 1u));
+            if (a.final_keep) a.final_keep[pos] = (int)(unsigned)__ldcg(&a.final_keys[t * NT + tid]);
+            else a.keep_ranks[pos] = t * NT + tid;
+        }
     }
     if (blockIdx.x == 0) {
         int part = 0;
         for (int q = tid; q < ntiles; q += NT) part += __ldcg(&a.tile_counts[q]);
         const int total = block_sum(part, red);
-        if (tid == 0) a.out_state[1] = total;
+        if (tid == 0) {
+            a.out_state[1] = total;
+            if (a.final_num) { a.final_num[0] = total; a.final_num[1] = __ldcg(&a.status[0]); }
+        }
     }
+    mid_stamp(a.dbg, 6);
+}
+
+__global__ void __launch_bounds__(NT, 1) nms_rounds_kernel(RoundsArgs a) {
+    extern __shared__ int sadj[];
+    __shared__ int red[32];
+    const GridCfg c = *a.cfg;
+    if (!c.use) return;  // uniform over the grid: the peel kernel handles this problem
+    nms_rounds_body(a, c, sadj, red);
+}
+
+// ---- mid path (one problem of a few thousand boxes) ------------------------------------------------------------------
+// Between the single-CTA path (one SM's latency chain: 229 us at 4 096 boxes) and the spatial path (~25 stream operations of
+// fixed cost, built for 10^5 boxes) a problem of a few thousand boxes is small enough for brute force over ALL SMs, and short
+// enough that launches dominate: separate kernels for these phases measured 103 us at 4 096 boxes, of which ~10 us were
+// work.  So the whole problem is ONE cooperative kernel, phases separated by grid-wide barriers, no memset before it:
+//   0  clear the status block, ranks, list counters and decision states;
+//   1  rank sort: keys (score desc | index) are unique, so rank = number of smaller keys; (row tile x key slice) items count
+//      partial ranks, then every box is scattered to its rank (keys and boxes);
+//   2  predecessor lists by brute force: (row tile x column tile) items over the lower triangle, N^2/2 exact IoU tests
+//      (8.4 M at 4 096 boxes);
+//   3  the spatial path's decision sweeps over those lists (nms_rounds_body; a box with more predecessors than a list holds
+//      rescans every earlier box) and its ordered output, written straight as source indices.
+constexpr int MID_CAP = 12288;    // measured against the spatial path: 107 vs 196 us at 8 192 boxes, 178 vs 200 at 12 288, 263 vs 212 at 16 384
+constexpr int MID_CW = 64;        // column tile of phase 2
+
+struct MidArgs {
+    const float *dets;
+    int n, stride, presorted, mode;
+    int slices, per_slice;
+    u64 *sorted;
+    float4 *sbox;
+    int *rank;
+    int *st;                // status block (nms_big_impl's slots), followed by everything that must start at zero
+    int zero_ints;
+    RoundsArgs ra;
+};
+
+__global__ void __launch_bounds__(NT, 1) nms_mid_kernel(MidArgs m) {
+    extern __shared__ __align__(16) int dyn[];      // phase 1: key tile; phase 2: column boxes; phase 3: sadj
+    __shared__ int red[32];
+    cg::grid_group grid = cg::this_grid();
+    const int tid = threadIdx.x, G = gridDim.x, gtid = blockIdx.x * NT + tid, gstride = G * NT;
+    const int n = m.n;
+    mid_stamp(m.ra.dbg, 0);
+    for (int i = gtid; i < m.zero_ints; i += gstride) m.st[i] = 0;
+    __threadfence();
+    grid.sync();
+    mid_stamp(m.ra.dbg, 1);
+    bool nan_seen = false;
+    auto key_of = [&](int j) -> u64 {
+        if (m.presorted) return (u64)(unsigned)j;
+        const float sc = __ldg(m.dets + (size_t)j * m.stride + 4);
+        nan_seen |= (sc != sc);
+        return ((u64)desc_key(sc) << 32) | (unsigned)j;
+    };
+    const int rtiles = (n + NT - 1) / NT;
+    if (!m.presorted) {
+        u64 *tile = reinterpret_cast<u64 *>(dyn);
+        for (int it = blockIdx.x; it < rtiles * m.slices; it += G) {
+            const int rt = it / m.slices, sl = it - rt * m.slices;
+            const int i = rt * NT + tid;
+            const u64 mine = i < n ? key_of(i) : ~0ull;
+            const int c0 = sl * m.per_slice, c1 = min(n, c0 + m.per_slice);
+            int cnt = 0;
+            for (int base = c0; base < c1; base += NT) {
+                __syncthreads();
+                tile[tid] = base + tid < c1 ? key_of(base + tid) : ~0ull;          // padding: never smaller
+                __syncthreads();
+                const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(tile);
+                const int pairs = (min(NT, c1 - base) + 1) >> 1;
+#pragma unroll 4
+                for (int j = 0; j < pairs; ++j) {                                  // warp-uniform (broadcast) 128-bit reads
+                    const ulonglong2 q = k2[j];
+                    cnt += (q.x < mine) ? 1 : 0;
+                    cnt += (q.y < mine) ? 1 : 0;
+                }
+            }
+            if (i < n && cnt) atomicAdd(&m.rank[i], cnt);
+        }
+        __threadfence();
+        grid.sync();
+    }
+    mid_stamp(m.ra.dbg, 2);
+    bool ok = true;
+    for (int i = gtid; i < n; i += gstride) {
+        const u64 key = key_of(i);
+        const int r = m.presorted ? i : __ldcg(&m.rank[i]);
+        m.sorted[r] = key;
+        const float *p = m.dets + (size_t)i * m.stride;
+        const float4 bx = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+        m.sbox[r] = bx;
+        ok &= box_is_fast_ok(bx);
+    }
+    if (nan_seen) atomicExch(&m.st[0], 1);
+    if (!ok) atomicExch(&m.st[2], 1);               // not "fast": the full IEEE overlap test from here on
+    __threadfence();
+    grid.sync();
+    mid_stamp(m.ra.dbg, 3);
+    {
+        const bool fast = m.ra.iou.fast && __ldcg(&m.st[2]) == 0;
+        const IouParams P = m.ra.iou;
+        float4 *cb = reinterpret_cast<float4 *>(dyn);
+        float *ca = reinterpret_cast<float *>(cb + MID_CW);
+        // items = (row tile, column tile) pairs with at least one (row, earlier column): row tile rt has ceil((last row) / CW) of them
+        int total_items = 0;
+        for (int rt = 0; rt < rtiles; ++rt) total_items += (min(n, (rt + 1) * NT) - 1 + MID_CW - 1) / MID_CW;
+        for (int it = blockIdx.x; it < total_items; it += G) {
+            int rt = 0, ct = it;
+            for (;; ++rt) {
+                const int here = (min(n, (rt + 1) * NT) - 1 + MID_CW - 1) / MID_CW;
+                if (ct < here) break;
+                ct -= here;
+            }
+            const int j0 = ct * MID_CW, r = rt * NT + tid;
+            __syncthreads();
+            if (tid < MID_CW && j0 + tid < n) {
+                const float4 b = __ldcg(m.sbox + j0 + tid);
+                cb[tid] = b;
+                ca[tid] = box_area(b);
+            }
+            __syncthreads();
+            if (r >= n) continue;
+            const float4 bi = __ldcg(m.sbox + r);
+            const float ai = box_area(bi);
+            const int lim = min(min(MID_CW, n - j0), r - j0);                      // earlier boxes only
+            u64 hits = 0;                                                          // no memory operation inside the test loop
+            for (int jj = 0; jj < lim; ++jj) {
+                const bool s = fast ? iou_suppresses_exact(cb[jj], ca[jj], bi, ai, P)
+                                    : (m.mode == 0 ? iou_suppresses_full<0>(cb[jj], bi, P.thr) : iou_suppresses_full<1>(cb[jj], bi, P.thr));
+                hits |= (u64)(s ? 1 : 0) << jj;
+            }
+            if (hits) {                                                            // items of a row run concurrently: list order is arbitrary
+                int pos = atomicAdd(const_cast<int *>(m.ra.adj_cnt) + r, __popcll(hits));
+                int *mine = const_cast<int *>(m.ra.adj) + (size_t)r * ADJ_CAP;
+                for (; hits && pos < ADJ_CAP; hits &= hits - 1) mine[pos++] = j0 + __ffsll((long long)hits) - 1;
+            }
+        }
+    }
+    __threadfence();
+    grid.sync();
+    mid_stamp(m.ra.dbg, 4);
+    const GridCfg c = *m.ra.cfg;
+    nms_rounds_body(m.ra, c, dyn, red);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
@@ -985,7 +1169,7 @@ static int nms_big_impl(fd_ctx *ctx, const u64 *keys_in, const int *key_bytes, i
         FD_LAUNCH_CHECK(ctx);
         adjacency_kernel<<<gb, 256, 0, ctx->stream>>>(csorted, K, cfg, cell_start, cell_end, cbox, carea, iou, adj, adj_cnt);
         FD_LAUNCH_CHECK(ctx);
-        RoundsArgs ra;
+        RoundsArgs ra{};
         ra.N = K;
         ra.keys = csorted;
         ra.cfg = cfg;
@@ -1003,6 +1187,10 @@ static int nms_big_impl(fd_ctx *ctx, const u64 *keys_in, const int *key_bytes, i
         ra.keep_ranks = keep_ranks;
         ra.out_state = st + 3;
         ra.iou = iou;
+        ra.sbox = sbox;
+        ra.brute = 0;
+        ra.mode = mode;
+        ra.status = st;
         void *rargs[] = {&ra};
         int per_sm_r = 0;
         const size_t smem_r = sizeof(int) * (size_t)ADJ_SMEM * NT;
@@ -1041,6 +1229,79 @@ static int nms_big_impl(fd_ctx *ctx, const u64 *keys_in, const int *key_bytes, i
     return FD_OK;
 }
 
+// One problem of SINGLE_PROBLEM_CROSSOVER < K <= MID_CAP boxes: a single cooperative launch (nms_mid_kernel).
+static int nms_mid_impl(fd_ctx *ctx, const float *boxes, int K, int stride, const IouParams &iou, int mode, bool presorted, int32_t *keep_dev,
+                        int32_t *num_keep_dev) {
+    const int ntiles = (K + NT - 1) / NT;
+    FD_TRY(ctx->nms_ws[1].reserve(sizeof(u64) * (size_t)K));
+    FD_TRY(ctx->nms_ws[3].reserve(sizeof(float4) * (size_t)K));
+    FD_TRY(ctx->nms_ws[5].reserve(sizeof(int) * (size_t)ntiles * 33 + 64));
+    const size_t zero_ints = 32 + (size_t)K * 2 + ((size_t)K + 3) / 4;     // status block, list counters, ranks, decision states
+    FD_TRY(ctx->nms_ws[6].reserve(sizeof(int) * zero_ints + 64));
+    FD_TRY(ctx->nms_ws_sp[3].reserve(sizeof(int) * (size_t)K * ADJ_CAP));
+    int *st = ctx->nms_ws[6].as<int>();
+    int *adj_cnt = st + 32, *rank = adj_cnt + K;
+    MidArgs m{};
+    m.dets = boxes;
+    m.n = K;
+    m.stride = stride;
+    m.presorted = presorted ? 1 : 0;
+    m.mode = mode;
+    m.sorted = ctx->nms_ws[1].as<u64>();
+    m.sbox = ctx->nms_ws[3].as<float4>();
+    m.rank = rank;
+    m.st = st;
+    m.zero_ints = (int)zero_ints;
+    RoundsArgs &ra = m.ra;
+    ra.N = K;
+    ra.cfg = reinterpret_cast<GridCfg *>(st + 16);
+    ra.adj = ctx->nms_ws_sp[3].as<int>();
+    ra.adj_cnt = adj_cnt;
+    ra.state = reinterpret_cast<unsigned char *>(rank + K);
+    ra.counters = st + 13;
+    ra.tile_counts = ctx->nms_ws[5].as<int>();
+    ra.ballots = reinterpret_cast<unsigned *>(ra.tile_counts + ntiles);
+    ra.keep_ranks = nullptr;
+    ra.out_state = st + 3;
+    ra.iou = iou;
+    ra.sbox = m.sbox;
+    ra.brute = 1;
+    ra.mode = mode;
+    ra.status = st;
+    ra.final_keep = keep_dev;
+    ra.final_keys = m.sorted;
+    ra.final_num = num_keep_dev;
+    static int per_sm = 0;                                                 // one device type per process
+    const size_t smem = sizeof(int) * (size_t)ADJ_SMEM * NT;
+    if (!per_sm) {
+        FD_CUDA(cudaFuncSetAttribute(nms_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nms_mid_kernel, NT, smem));
+        if (per_sm < 1) return fail(FD_ERR_CUDA, "nms_mid_kernel does not fit on an SM");
+    }
+    const int grid = ctx->num_sms * per_sm;
+    m.slices = std::max(1, std::min((2 * grid + ntiles - 1) / ntiles, (K + 127) / 128));
+    m.per_slice = (((K + m.slices - 1) / m.slices) + 1) & ~1;
+    m.slices = (K + m.per_slice - 1) / m.per_slice;
+    static const bool dbg_on = getenv("FD_NMS_DBG") != nullptr;             // phase timeline of block 0 on stderr
+    static long long *dbg_dev = nullptr;
+    if (dbg_on && !dbg_dev) FD_CUDA(cudaMalloc(&dbg_dev, sizeof(long long) * 8));
+    ra.dbg = dbg_on ? dbg_dev : nullptr;
+    void *args[] = {&m};
+    FD_CUDA(cudaLaunchCooperativeKernel((const void *)nms_mid_kernel, dim3(grid), dim3(NT), args, smem, ctx->stream));
+    FD_LAUNCH_CHECK_NAMED(ctx, "nms_mid_kernel");
+    if (dbg_on) {
+        long long h[8];
+        int sth[8];
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaMemcpy(sth, st, sizeof(sth), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[nms mid dbg] K=%d grid=%d slices=%d: zero %.1f  rank %.1f  scatter %.1f  lists %.1f  sweeps %.1f (epochs %d)  output %.1f us\n", K, grid,
+                m.slices, (h[1] - h[0]) * 1e-3, (h[2] - h[1]) * 1e-3, (h[3] - h[2]) * 1e-3, (h[4] - h[3]) * 1e-3, (h[5] - h[4]) * 1e-3, sth[6],
+                (h[6] - h[5]) * 1e-3);
+    }
+    return FD_OK;
+}
+
 int nms_big_device(fd_ctx *ctx, const float *dets_dev, int K, int stride, float thr, int mode, bool presorted,
                    int32_t *keep_dev, int32_t *num_keep_dev) {
     static const int bytes[4] = {4, 5, 6, 7};  // score bytes only: the sort is stable, ties keep index order
@@ -1061,15 +1322,18 @@ int nms_last_stats(fd_ctx *ctx, int32_t out[8]) {
 
 // Generic device NMS on a (K, stride) row-major array with the score in column 4 (ignored if presorted).
 // keep_dev (K) and num_keep_dev (2 ints: [0] count, [1] NaN flag) are device buffers.
-constexpr int SINGLE_PROBLEM_CROSSOVER = 2560;
+constexpr int SINGLE_PROBLEM_CROSSOVER = 1024;   // = TINY_CAP: beyond it the all-SM mid path is faster (61 vs 68 us at 1 100 boxes)
 int nms_device(fd_ctx *ctx, const float *dets_dev, int K, int stride, float thr, int mode, bool presorted,
                int32_t *keep_dev, int32_t *num_keep_dev) {
+    // ONE problem: a single SM (the barrier-light tiny path) up to 1 024 boxes, one cooperative all-SM kernel up to MID_CAP, the
+    // multi-kernel spatial path beyond (measured: profiles/r2_nms_sizes.json); batched callers keep one CTA per image up to SMALL_CAP
+    static const int single_cross = getenv("FD_NMS_CROSS") ? atoi(getenv("FD_NMS_CROSS")) : SINGLE_PROBLEM_CROSSOVER;
+    static const int mid_cap = getenv("FD_NMS_MID_CAP") ? atoi(getenv("FD_NMS_MID_CAP")) : MID_CAP;   // 0: A/B without the mid path
+    if (K > std::min(SMALL_CAP, single_cross) && K <= mid_cap)
+        return nms_mid_impl(ctx, dets_dev, K, stride, make_iou_params(thr, mode), mode, presorted, keep_dev, num_keep_dev);
     FD_TRY(ctx->nms_ws[7].reserve(sizeof(int) * 8));
     int *status = ctx->nms_ws[7].as<int>();
     FD_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * 8, ctx->stream));
-    // ONE problem: a single SM is the faster home up to a few thousand boxes, the multi-kernel path beyond (measured
-    // crossover, profiles/r1_nms_sizes.json); batched callers keep one CTA per image up to SMALL_CAP
-    static const int single_cross = getenv("FD_NMS_CROSS") ? atoi(getenv("FD_NMS_CROSS")) : SINGLE_PROBLEM_CROSSOVER;
     if (K <= std::min(SMALL_CAP, single_cross)) {
         SmallArgs a{};
         a.keys = nullptr;

@@ -49,6 +49,26 @@ def test_big_path_sizes(ctx, oracle, n):
     np.testing.assert_array_equal(ctx.nms(dets, 0.4), oracle.nms(dets, 0.4))
 
 
+@pytest.mark.parametrize("n", [1025, 2561, 4096, 8192, 12287, 12288, 12289])
+def test_mid_path_sizes(ctx, oracle, n):
+    """A single problem of a few thousand boxes: rank sort + brute-force predecessor lists over all SMs (fd_nms.cu, mid path)."""
+    dets = _random_dets(n, 31 + n, canvas=1200, side=(8, 90), score_levels=500)       # ties: the rank sort must be stable
+    for thr in (0.4, 0.3):
+        np.testing.assert_array_equal(ctx.nms(dets, thr), oracle.nms(dets, thr))
+    np.testing.assert_array_equal(ctx.cpu_nms(dets, 0.4), oracle.cpu_nms(dets, 0.4))
+
+
+def test_mid_path_crowded_clusters_overflow_the_lists(ctx, oracle):
+    """300 jittered candidates per face: most boxes have more predecessors than a list holds (96) and rescan every earlier box."""
+    dets = synth.make_crowd_boxes(6000, seed=9, n_faces=20)
+    got, exp = ctx.nms(dets, 0.4), oracle.nms(dets, 0.4)
+    np.testing.assert_array_equal(got, exp)
+    n = 5000                                                   # chain: box i overlaps only i-1 -> worst-case decision depth
+    x = np.arange(n, dtype=np.float32) * 6
+    chain = np.stack([x, np.zeros(n, np.float32), x + 10, np.full(n, 10, np.float32), np.linspace(0.99, 0.01, n, dtype=np.float32)], 1)
+    np.testing.assert_array_equal(ctx.nms(chain, 0.2), oracle.nms(chain, 0.2))
+
+
 def test_dense_crowd_c3(ctx, oracle):
     """BASELINE config 3: ~100k candidates, 5000 faces x 20 jittered boxes, 1% duplicated scores."""
     dets = synth.make_crowd_boxes(100000, seed=42)
@@ -163,3 +183,22 @@ def test_property_random_small(ctx, oracle):
         np.testing.assert_array_equal(ctx.nms(dets, thr), oracle.nms(dets, thr))
 
     prop()
+
+
+def test_single_cta_and_spatial_paths_behind_the_switches():
+    """FD_NMS_CROSS=4096 FD_NMS_MID_CAP=0: the single-CTA general path (what the fused detect kernel runs for crowded images)
+    and the spatial path at the sizes the mid path normally takes — same keep lists."""
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import numpy as np\n"
+            "from rs_face_detection_b200 import Context\n"
+            "from oracle import oracle as O\n"
+            "from test_gpu_nms import _random_dets\n"
+            "O.build(); c = Context(0)\n"
+            "for n in (1025, 2048, 4096, 4097, 6000):\n"
+            "    d = _random_dets(n, 5 + n, canvas=1200, side=(8, 90), score_levels=300)\n"
+            "    np.testing.assert_array_equal(c.nms(d, 0.4), O.nms(d, 0.4))\n"
+            "    np.testing.assert_array_equal(c.cpu_nms(d, 0.3), O.cpu_nms(d, 0.3))\n"
+            "print('ok')\n" % (ROOT, os.path.join(ROOT, "tests")))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, FD_NMS_CROSS="4096", FD_NMS_MID_CAP="0"), capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-1500:]
