@@ -14,8 +14,10 @@
 //
 //   K <= 1024 : barrier-light single-CTA path (fd_nms_tiny.cuh: register bitonic sort, warp-resolved mini-heads of 32);
 //               the batched pipeline runs the same code inside the fused detect kernel (fd_detect_fused.cu).
-//   K <= 4096 : one CTA does sort + peel out of shared memory.
-//   K  > 4096 : LSD radix sort (own kernels) + spatially binned exact NMS (predecessor lists + decision sweeps in one
+//   K <= 4096 : one CTA does sort + greedy out of shared memory — per image of a batch (fused detect kernel, nms_batch_*).
+//   ONE problem of 1024 < K <= 12288 boxes (fd_nms / fd_nms_device): nms_mid_kernel, a single cooperative launch over all SMs —
+//               rank sort, brute-force predecessor lists, the decision sweeps below (72 us at 4 096 boxes, was 178).
+//   beyond    : LSD radix sort (own kernels) + spatially binned exact NMS (predecessor lists + decision sweeps in one
 //               cooperative kernel), or the cooperative multi-CTA peel for degenerate inputs.
 #include <cooperative_groups.h>
 #include <algorithm>
