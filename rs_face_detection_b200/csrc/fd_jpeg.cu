@@ -8,13 +8,18 @@
 //            device as they are and `jpeg_huffman_kernel` decodes one restart interval per thread (Huffman lookup tables in
 //            shared memory, coefficients written straight into the device coefficient blocks) — the 1.3 MB stream of a 1080p
 //            frame is all that crosses PCIe;
-//          * streams WITHOUT restart markers (what most encoders emit by default) have no parallelism to offer: the Huffman
-//            pass runs on the host, one image per worker thread, into pinned int16 coefficient blocks that are then copied;
+//          * streams WITHOUT restart markers (what most encoders emit by default) are copied as they are too, unstuffed on the
+//            device (jpeg_unstuff_*_kernel) and decoded by self-synchronising sub-sequences: jpeg_sync_kernel rounds to the
+//            fixed point of the chain of decoder states, then jpeg_write_kernel + jpeg_dc_kernel (see the section below);
+//          * a host Huffman decoder (one image per worker thread, pinned coefficient blocks, copied) remains for streams with
+//            more than two DC / AC tables or an inconsistent marker sequence, and behind FD_JPEG_HOST_HUFFMAN /
+//            FD_JPEG_NO_SELFSYNC for A/B runs;
+//          both device decoders assemble blocks in shared memory and write them out whole, in SCAN order (stage_flush);
 //   device `jpeg_idct_kernel`: dequantisation + libjpeg's jpeg_idct_islow (jidctint.c: 13-bit constants, PASS1_BITS 2, the
 //          range-limit table with its wrap-around), 8 threads per block;
 //          `jpeg_color_kernel`: chroma upsampling (jdsample.c h2v1 / h2v2 "fancy" triangle filters with jdmainct.c's replicated
 //          context rows; plain replication when downsampled_width <= 2, as jinit_upsampler selects) + YCbCr -> BGR with
-//          jdcolor.c's 16-bit fixed-point constants, 4 pixels per thread, 12-byte packed stores.
+//          jdcolor.c's 16-bit fixed-point constants, 8 pixels per thread sharing the filter's column sums.
 // Every integer operation follows libjpeg-turbo's decompressor with the defaults OpenCV leaves in place (JDCT_ISLOW,
 // do_fancy_upsampling), so the frames are bit-identical to cv2.imdecode (tests/test_gpu_jpeg.py, golden vectors from cv2 4.13).
 // Scope: SOF0 / SOF1 8-bit, one interleaved 3-component scan, 4:4:4 / 4:2:2 / 4:2:0, DRI/RSTn.  Progressive, arithmetic,
