@@ -783,7 +783,7 @@ def run_ours(args):
                                       "work SURVEY 8(d) names; the spatial path evaluates far fewer" % len(times)}
         try:
             st = ctx.nms_last_stats()
-            nms_extra["nms_100k_path"] = {"spatial": int(st[0]), "kept": int(st[1]), "decision_epochs": int(st[2]), "grid": [int(st[3]), int(st[4])]}
+            nms_extra["nms_100k_path"] = {"spatial": st["spatial"], "kept": st["kept"], "decision_epochs": st["epochs"], "grid": list(st["grid"])}
         except Exception:
             pass
         # the reference's own CUDA NMS (src/nms_kernel.cu, never built by the reference) recompiled for sm_100a from the
