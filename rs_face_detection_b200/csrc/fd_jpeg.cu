@@ -372,6 +372,13 @@ struct JpegImageDev {
     unsigned *used_state;      // [n_sub] the start state its last decode began from
     int *sub_blocks;           // [n_sub + 1] blocks completed inside each sub-sequence -> (after the scan) first block of each
     int *changed;              // [0] the last finished round changed some exit state, [1] collects the running round, [2] raw_len - first marker
+    // ... of a stream WITH restart markers (rst_sync = its restart interval in MCUs, else 0): the markers are dropped by the
+    // unstuff kernels and become known-state boundaries inside the flat chain of sub-sequences
+    int rst_sync, iv_cap;
+    int *n_iv;                 // [1] restart intervals found (device-written)
+    int *iv_start;             // [iv_cap + 2] first CLEAN byte of each interval; [n_iv] = end of the data
+    int *chunk_rst;            // [chunks] restart markers per chunk -> (after the scan) before each chunk
+    int *seg_dc;               // [3][iv_cap + 1] un-reset DC prefix (mod 2^16) at the last block of each interval, per component
     uint8_t *plane[3];         // component planes, pw x ph
     uint8_t *bgr;              // output frame
     int pw[3], ph[3];
@@ -656,26 +663,32 @@ __device__ __forceinline__ int block_exclusive_scan_1024(int *a, int n) {
 constexpr int UNSTUFF_THREADS = 256;
 constexpr int UNSTUFF_CHUNK = UNSTUFF_THREADS * 16;
 
-// the 16 bytes at [g, g+16) of a raw segment of n bytes (g % 16 == 0, g < n): bit j of *drop / *mark classifies byte g + j
-__device__ __forceinline__ uint4 unstuff_classify(const uint8_t *__restrict__ raw, int n, int g, unsigned *drop, unsigned *mark) {
+// the 16 bytes at [g, g+16) of a raw segment of n bytes (g % 16 == 0, g < n): bit j of *drop / *mark / *rst classifies byte g + j.
+// rst_ok (the stream is decoded with its restart markers as boundaries): FF D0..D7 is dropped, both bytes, and flagged in *rst.
+__device__ __forceinline__ uint4 unstuff_classify(const uint8_t *__restrict__ raw, int n, int g, bool rst_ok, unsigned *drop, unsigned *mark,
+                                                  unsigned *rst) {
     const uint4 v = __ldg(reinterpret_cast<const uint4 *>(raw + g));        // the arena is padded: bytes past n are ignored below
     const unsigned w[4] = {v.x, v.y, v.z, v.w};
     unsigned prev = g > 0 ? __ldg(raw + g - 1) : 0u;
     const unsigned after = g + 16 < n ? __ldg(raw + g + 16) : 1u;
-    unsigned d = 0, m = 0;
+    unsigned d = 0, m = 0, rs = 0;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const unsigned b = (w[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
         unsigned nx = j < 15 ? (w[(j + 1) >> 2] >> (((j + 1) & 3) * 8)) & 0xFFu : after;
         if (g + j + 1 >= n) nx = 1u;                                         // an FF that ends the buffer counts as a marker
         if (g + j < n) {
-            if ((b == 0u && prev == 0xFFu) || (b == 0xFFu && nx == 0xFFu)) d |= 1u << j;
+            const bool rst_here = rst_ok && b == 0xFFu && (nx & 0xF8u) == 0xD0u;
+            const bool rst_tail = rst_ok && prev == 0xFFu && (b & 0xF8u) == 0xD0u;
+            if ((b == 0u && prev == 0xFFu) || (b == 0xFFu && nx == 0xFFu) || rst_here || rst_tail) d |= 1u << j;
             else if (b == 0xFFu && nx != 0u) m |= 1u << j;
+            if (rst_here) rs |= 1u << j;
         }
         prev = b;
     }
     *drop = d;
     *mark = m;
+    *rst = rs;
     return v;
 }
 
@@ -685,21 +698,23 @@ __global__ void __launch_bounds__(UNSTUFF_THREADS) jpeg_unstuff_count_kernel(con
     const int n = im.raw_len;
     if (im.gpu_entropy != 2 || (long long)blockIdx.x * UNSTUFF_CHUNK > n) return;
     const int g = blockIdx.x * UNSTUFF_CHUNK + threadIdx.x * 16;
-    unsigned drop = 0, mark = 0;
-    if (g < n) unstuff_classify(im.raw, n, g, &drop, &mark);
-    int cnt = __popc(drop);
+    unsigned drop = 0, mark = 0, rst = 0;
+    if (g < n) unstuff_classify(im.raw, n, g, im.rst_sync != 0, &drop, &mark, &rst);
+    int cnt = __popc(drop), nr = __popc(rst);
     int slack = mark ? n - (g + __ffs(mark) - 1) : 0;                        // larger = earlier
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        nr += __shfl_xor_sync(0xffffffffu, nr, o);
         slack = max(slack, __shfl_xor_sync(0xffffffffu, slack, o));
     }
-    __shared__ int s_cnt[UNSTUFF_THREADS / 32], s_slack[UNSTUFF_THREADS / 32];
-    if ((threadIdx.x & 31) == 0) { s_cnt[threadIdx.x >> 5] = cnt; s_slack[threadIdx.x >> 5] = slack; }
+    __shared__ int s_cnt[UNSTUFF_THREADS / 32], s_nr[UNSTUFF_THREADS / 32], s_slack[UNSTUFF_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) { s_cnt[threadIdx.x >> 5] = cnt; s_nr[threadIdx.x >> 5] = nr; s_slack[threadIdx.x >> 5] = slack; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < UNSTUFF_THREADS / 32; ++w) { cnt += s_cnt[w]; slack = max(slack, s_slack[w]); }
+        for (int w = 1; w < UNSTUFF_THREADS / 32; ++w) { cnt += s_cnt[w]; nr += s_nr[w]; slack = max(slack, s_slack[w]); }
         im.chunk_drop[blockIdx.x] = cnt;
+        if (im.rst_sync) im.chunk_rst[blockIdx.x] = nr;
         if (slack) atomicMax(im.changed + 2, slack);
     }
 }
@@ -709,6 +724,7 @@ __global__ void __launch_bounds__(1024) jpeg_unstuff_scan_kernel(const JpegImage
     const JpegImageDev &im = imgs[blockIdx.x];
     if (im.gpu_entropy != 2) return;
     block_exclusive_scan_1024(im.chunk_drop, im.raw_len / UNSTUFF_CHUNK + 1);
+    if (im.rst_sync) block_exclusive_scan_1024(im.chunk_rst, im.raw_len / UNSTUFF_CHUNK + 1);
 }
 
 // the data bytes before the first marker, compacted; the thread that owns the end position publishes nbits / n_sub and pads
@@ -716,41 +732,57 @@ __global__ void __launch_bounds__(UNSTUFF_THREADS) jpeg_unstuff_write_kernel(Jpe
     JpegImageDev &im = imgs[blockIdx.y];
     const int n = im.raw_len;
     if (im.gpu_entropy != 2) return;
-    const int end = n - im.changed[2];                                       // first marker, or raw_len
+    const int end = n - im.changed[2];                                       // first marker (not RSTn when those are boundaries), or raw_len
     if ((long long)blockIdx.x * UNSTUFF_CHUNK > end) return;
     const int g = blockIdx.x * UNSTUFF_CHUNK + threadIdx.x * 16;
-    unsigned drop = 0, mark = 0;
+    const bool rst_ok = im.rst_sync != 0;
+    unsigned drop = 0, mark = 0, rst = 0;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (g < n) v = unstuff_classify(im.raw, n, g, &drop, &mark);
-    const int cnt = __popc(drop);
-    int incl = cnt;
+    if (g < n) v = unstuff_classify(im.raw, n, g, rst_ok, &drop, &mark, &rst);
+    const int cnt = __popc(drop), nr = __popc(rst);
+    int incl = cnt, incl_r = nr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int nb = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += nb;
+        const int nb = __shfl_up_sync(0xffffffffu, incl, o), nbr = __shfl_up_sync(0xffffffffu, incl_r, o);
+        if (lane >= o) { incl += nb; incl_r += nbr; }
     }
-    __shared__ int s_w[UNSTUFF_THREADS / 32];
-    if (lane == 31) s_w[warp] = incl;
+    __shared__ int s_w[UNSTUFF_THREADS / 32], s_r[UNSTUFF_THREADS / 32];
+    if (lane == 31) { s_w[warp] = incl; s_r[warp] = incl_r; }
     __syncthreads();
     int before = im.chunk_drop[blockIdx.x] + incl - cnt;                     // non-data bytes before byte g
-    for (int w = 0; w < warp; ++w) before += s_w[w];
+    int rbefore = rst_ok ? im.chunk_rst[blockIdx.x] + incl_r - nr : 0;       // restart markers before byte g
+    for (int w = 0; w < warp; ++w) { before += s_w[w]; rbefore += s_r[w]; }
     uint8_t *out = im.clean;
     if (end >= g && end < g + 16) {
-        const int ulen = end - before - __popc(drop & ((1u << (end - g)) - 1u));
+        const unsigned below = (1u << (end - g)) - 1u;
+        const int ulen = end - before - __popc(drop & below);
         im.nbits = (long long)ulen * 8;
         im.n_sub = (int)(((long long)ulen * 8 + SUBSEQ_BITS - 1) / SUBSEQ_BITS);
         for (int j = 0; j < 32; ++j) out[ulen + j] = 0;                      // the decoders read a few words past the end
+        if (rst_ok) {
+            const int niv = min(rbefore + __popc(rst & below) + 1, im.iv_cap);
+            *im.n_iv = niv;
+            im.iv_start[0] = 0;
+            im.iv_start[niv] = ulen;
+        }
     }
     const unsigned w[4] = {v.x, v.y, v.z, v.w};
     int o = g - before;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        if (g + j < end && !((drop >> j) & 1u)) out[o++] = (uint8_t)(w[j >> 2] >> ((j & 3) * 8));
+        if (g + j < end) {
+            if ((rst >> j) & 1u) {                                           // interval rbefore + 1 starts where this marker was
+                ++rbefore;
+                if (rbefore < im.iv_cap) im.iv_start[rbefore] = o;
+            }
+            if (!((drop >> j) & 1u)) out[o++] = (uint8_t)(w[j >> 2] >> ((j & 3) * 8));
+        }
     }
 }
 
 constexpr int SYNC_THREADS = 128;
+constexpr int RST_SYNC_MIN_MCUS = 32;   // restart intervals from this many MCUs take the self-synchronising decoder (FD_JPEG_RST_SYNC_MIN)
 
 // exit state: bits past the sub-sequence end (< 32) | block-in-MCU q << 5 | coefficient position k << 8
 __device__ __forceinline__ unsigned pack_state(int over, int q, int k) { return (unsigned)over | ((unsigned)q << 5) | ((unsigned)k << 8); }
@@ -785,8 +817,27 @@ __device__ __forceinline__ int huff_symbol(const JpegHuffDev &tab, const uint16_
     return len + s;
 }
 
+// Restart intervals as boundaries of the self-synchronising chain (streams decoded with rst_sync): the interval that starts at
+// clean byte iv_start[t] begins in a KNOWN decoder state (first block of an MCU, byte-aligned) whatever came before.  A decoder
+// takes the boundary when it has overshot it, or when it stands at the end of an MCU with less than a byte to go (the padding
+// bits; a whole MCU needs more).  first index t with iv_start[t] * 8 > pos:
+__device__ __forceinline__ int rst_next_boundary(const JpegImageDev &im, long long pos) {
+    const int n_iv = __ldcg(im.n_iv), byte = (int)(pos >> 3);
+    int lo = 1, hi = n_iv + 1;                           // answer in [1, n_iv + 1]
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldcg(im.iv_start + mid) > byte) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
+__device__ __forceinline__ long long rst_boundary_bit(const JpegImageDev &im, int t) {
+    return t <= __ldcg(im.n_iv) ? (long long)__ldcg(im.iv_start + t) * 8 : 0x7fffffffffffffffll;
+}
+
 // Decodes from bit `pos` in state (q, k) until the position reaches `end_bit`, without storing anything.  Returns the exit
 // state; *blocks = blocks finished.
+template <bool RST>
 __device__ __forceinline__ unsigned decode_subsequence(const JpegImageDev &im, const JpegHuffDev &tab, const uint16_t *look, long long pos,
                                                        long long end_bit, int q, int k, int *blocks) {
     const int HV = im.H * im.V, per_mcu = HV + 2;
@@ -802,7 +853,27 @@ __device__ __forceinline__ unsigned decode_subsequence(const JpegImageDev &im, c
     int comp = q < HV ? 0 : q - HV + 1;
     int dslot = ds[comp], aslot = as[comp];
     int nblocks = 0;
+    int t = 0;
+    long long bnd = 0x7fffffffffffffffll;
+    if (RST) {
+        t = rst_next_boundary(im, pos);
+        bnd = rst_boundary_bit(im, t);
+    }
     while (pos < end_bit) {
+        if (RST && (pos >= bnd || ((k | q) == 0 && bnd - pos < 8))) {      // the next interval starts here, in the known state
+            pos = bnd;
+            q = k = 0;
+            dslot = ds[0];
+            aslot = as[0];
+            wp = reinterpret_cast<const unsigned *>(im.stream) + (pos >> 5);   // (byte-aligned)
+            acc = ((unsigned long long)__byte_perm(wp[0], 0, 0x0123) << 32) | __byte_perm(wp[1], 0, 0x0123);
+            wnext = wp[2];
+            wp += 3;
+            cnt = 64 - (int)(pos & 31);
+            acc <<= (int)(pos & 31);
+            bnd = rst_boundary_bit(im, ++t);
+            continue;
+        }
         if (cnt <= 32) {
             acc |= (unsigned long long)__byte_perm(wnext, 0, 0x0123) << (32 - cnt);
             cnt += 32;
@@ -829,10 +900,11 @@ __device__ __forceinline__ unsigned decode_subsequence(const JpegImageDev &im, c
 
 // grid (ceil(max n_sub / 128), B).  round 0: guessed start states (position = first bit, q = k = 0); round > 0: the exit state
 // the left neighbour holds now, and only if it differs from the state this sub-sequence was last decoded from.
+template <bool RST>
 __global__ void __launch_bounds__(SYNC_THREADS) jpeg_sync_kernel(const JpegImageDev *__restrict__ imgs, int round) {
     __shared__ JpegHuffDev tab;
     const JpegImageDev &im = imgs[blockIdx.y];
-    if (im.gpu_entropy != 2 || blockIdx.x * SYNC_THREADS >= im.n_sub) return;
+    if (im.gpu_entropy != 2 || (im.rst_sync != 0) != RST || blockIdx.x * SYNC_THREADS >= im.n_sub) return;
     if (round > 1 && *im.changed == 0) return;          // this image's states are already the fixed point
     const int i = blockIdx.x * SYNC_THREADS + threadIdx.x;
     unsigned st = 0;
@@ -849,7 +921,7 @@ __global__ void __launch_bounds__(SYNC_THREADS) jpeg_sync_kernel(const JpegImage
     const long long pos = (long long)i * SUBSEQ_BITS + (st & 31u);
     const long long end_bit = min((long long)(i + 1) * SUBSEQ_BITS, im.nbits);
     int blocks = 0;
-    const unsigned out = decode_subsequence(im, tab, &tab.look[0][0], pos, end_bit, (int)((st >> 5) & 7u), (int)(st >> 8), &blocks);
+    const unsigned out = decode_subsequence<RST>(im, tab, &tab.look[0][0], pos, end_bit, (int)((st >> 5) & 7u), (int)(st >> 8), &blocks);
     im.used_state[i] = st;
     if (round == 0 || out != im.exit_state[i]) {
         im.exit_state[i] = out;
@@ -874,12 +946,13 @@ __global__ void __launch_bounds__(1024) jpeg_sync_epilogue_kernel(const JpegImag
 // the write pass: every sub-sequence from its exact start state.  A block that straddles sub-sequences is written piecewise:
 // each decoder owns the scan positions [k at its start, k at its end) — zeros included — so the pieces are disjoint and
 // together cover the block; whole blocks leave as one 128-byte warp store (stage_flush).
+template <bool RST>
 __global__ void __launch_bounds__(SYNC_THREADS) jpeg_write_kernel(const JpegImageDev *__restrict__ imgs) {
     __shared__ JpegHuffDev tab;
     __shared__ unsigned stage[SYNC_THREADS * STAGE_PITCH];
     __shared__ uint8_t zz[64];
     const JpegImageDev &im = imgs[blockIdx.y];
-    if (im.gpu_entropy != 2 || blockIdx.x * SYNC_THREADS >= im.n_sub) return;
+    if (im.gpu_entropy != 2 || (im.rst_sync != 0) != RST || blockIdx.x * SYNC_THREADS >= im.n_sub) return;
     if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
     for (int t = threadIdx.x; t < (int)(sizeof(JpegHuffDev) / 4); t += SYNC_THREADS)
         reinterpret_cast<unsigned *>(&tab)[t] = __ldg(reinterpret_cast<const unsigned *>(im.huff) + t);
@@ -892,7 +965,7 @@ __global__ void __launch_bounds__(SYNC_THREADS) jpeg_write_kernel(const JpegImag
     const int i = blockIdx.x * SYNC_THREADS + threadIdx.x;
     const bool live = i < im.n_sub;
     const int HV = im.H * im.V, per_mcu = HV + 2;
-    const int total_blocks = min(im.mcux * im.mcuy * per_mcu, im.changed[3]);
+    const int total_blocks = RST ? im.mcux * im.mcuy * per_mcu : min(im.mcux * im.mcuy * per_mcu, im.changed[3]);
     const int ds0 = im.td[0] << HUFF_LOOKAHEAD, ds1 = im.td[1] << HUFF_LOOKAHEAD, ds2 = im.td[2] << HUFF_LOOKAHEAD;
     const int as0 = (2 + im.ta[0]) << HUFF_LOOKAHEAD, as1 = (2 + im.ta[1]) << HUFF_LOOKAHEAD, as2 = (2 + im.ta[2]) << HUFF_LOOKAHEAD;
     long long pos = (long long)i * SUBSEQ_BITS;
@@ -914,9 +987,34 @@ __global__ void __launch_bounds__(SYNC_THREADS) jpeg_write_kernel(const JpegImag
     int cnt = 64 - (int)(pos & 31);
     acc <<= (int)(pos & 31);
     bool active = live && pos < end_bit;
+    int t = 0;                                            // RST: next restart boundary (see decode_subsequence)
+    long long bnd = 0x7fffffffffffffffll;
+    if (RST && live) {
+        t = rst_next_boundary(im, pos);
+        bnd = rst_boundary_bit(im, t);
+    }
     while (__any_sync(0xffffffffu, active)) {
         bool done = false;
-        if (active) {
+        if (RST && active && (pos >= bnd || ((k | q) == 0 && bnd - pos < 8))) {
+            // interval t starts here: block t * restart * (blocks per MCU), known state.  (A block left unfinished can only come
+            // from a corrupt stream: its staged coefficients are dropped.)
+            if (k != 0 || kfirst != 0)
+                for (int wi = 0; wi < 32; ++wi) reinterpret_cast<unsigned *>(my_row)[wi] = 0u;
+            pos = bnd;
+            q = k = 0;
+            kfirst = 0;
+            n = t * im.rst_sync * per_mcu;
+            dslot = ds0;
+            aslot = as0;
+            wp = reinterpret_cast<const unsigned *>(im.stream) + (pos >> 5);
+            acc = ((unsigned long long)__byte_perm(wp[0], 0, 0x0123) << 32) | __byte_perm(wp[1], 0, 0x0123);
+            wnext = wp[2];
+            wp += 3;
+            cnt = 64 - (int)(pos & 31);
+            acc <<= (int)(pos & 31);
+            bnd = rst_boundary_bit(im, ++t);
+            active = pos < end_bit;
+        } else if (active) {
             if (cnt <= 32) {
                 acc |= (unsigned long long)__byte_perm(wnext, 0, 0x0123) << (32 - cnt);
                 cnt += 32;
@@ -1011,7 +1109,15 @@ __global__ void __launch_bounds__(1024) jpeg_dc_kernel(const JpegImageDev *__res
         }
         __syncthreads();
         const int carry = carry_s;
-        if (blk) blk[0] = (int16_t)(carry + warp_sums[warp] + incl);
+        if (blk) {
+            const int p = carry + warp_sums[warp] + incl;
+            blk[0] = (int16_t)p;
+            if (im.rst_sync) {   // restart intervals reset the predictors: the IDCT subtracts the prefix at the previous interval's last block
+                const int mcu = n / per, sub = n - mcu * per;
+                if (sub == per - 1 && ((mcu + 1) % im.rst_sync == 0 || mcu == im.mcux * im.mcuy - 1))
+                    im.seg_dc[c * (im.iv_cap + 1) + mcu / im.rst_sync] = p;
+            }
+        }
         __syncthreads();
         if (threadIdx.x == 0) carry_s = carry + warp_sums[32];
         __syncthreads();
@@ -1035,14 +1141,20 @@ __global__ void __launch_bounds__(IDCT_BLOCKS * 8) jpeg_idct_kernel(const JpegIm
     const int c = qb < HV ? 0 : qb - HV + 1;
     const int yb = c == 0 ? my * im.V + qb / im.H : my, xb = c == 0 ? mx * im.H + qb % im.H : mx;
     if (live) {
-        const bool held = im.gpu_entropy != 2 || n < im.changed[3];   // a truncated stream holds fewer blocks: the rest is zero
+        const bool held = im.gpu_entropy != 2 || im.rst_sync != 0 || n < im.changed[3];   // a truncated stream holds fewer blocks: the rest is zero
+        int dc_base = 0;                                      // (rst_sync: the arena was cleared instead)
+        if (im.gpu_entropy == 2 && im.rst_sync != 0 && k == 0) {
+            const int seg = mcu / im.rst_sync;
+            if (seg > 0) dc_base = im.seg_dc[c * (im.iv_cap + 1) + seg - 1];
+        }
         const int16_t *in = im.coef + (size_t)n * 64 + k;             // column k of the block
         const uint16_t *q = im.qt[c] + k;
         int v[8], o[8];
         bool ac0 = true;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            const int cf = held ? (int)in[8 * r] : 0;
+            int cf = held ? (int)in[8 * r] : 0;
+            if (r == 0 && k == 0) cf = (int)(int16_t)(cf - dc_base);   // modular: both are un-reset prefixes mod 2^16
             v[r] = cf * (int)q[8 * r];                        // DEQUANTIZE
             if (r) ac0 = ac0 && cf == 0;
         }
@@ -1168,6 +1280,17 @@ __global__ void __launch_bounds__(128) jpeg_color_kernel(const JpegImageDev *__r
 }
 
 
+// grid (x, B): clears the coefficient blocks of the images decoded with their restart markers as boundaries (a missing interval
+// would leave a hole of stale coefficients): 128-bit streaming stores
+__global__ void __launch_bounds__(256) jpeg_zero_rst_kernel(const JpegImageDev *__restrict__ imgs) {
+    const JpegImageDev &im = imgs[blockIdx.y];
+    if (im.gpu_entropy != 2 || im.rst_sync == 0) return;
+    const size_t n16 = ((size_t)im.nblk[0] + im.nblk[1] + im.nblk[2]) * 8;       // a block is 128 bytes
+    uint4 *p = reinterpret_cast<uint4 *>(im.coef);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) __stcs(p + i, z);
+}
+
 }  // namespace fd
 
 using namespace fd;
@@ -1215,13 +1338,18 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
     std::vector<const char *> errs((size_t)B, nullptr);
     std::vector<std::vector<uint32_t>> ivs((size_t)B);
     std::vector<char> mode((size_t)B, 0);
+    std::vector<int> rst_iv((size_t)B, 0);          // mode 2 on a stream WITH restart markers: its restart interval (MCUs)
+    static const int rst_sync_min = getenv("FD_JPEG_RST_SYNC_MIN") ? atoi(getenv("FD_JPEG_RST_SYNC_MIN")) : RST_SYNC_MIN_MCUS;
     parallel_images(B, [&](int i) {
         errs[i] = parse_jpeg(jpegs[i], nbytes[i], &hdr[i]);
         if (errs[i]) return;
         const JpegHeader &j = hdr[i];
         bool ok = !no_gpu_entropy && j.scan_len < 0x7FFFFFF0ull;
         for (int c = 0; c < 3 && ok; ++c) ok = j.td[c] <= 1 && j.ta[c] <= 1;
-        if (ok && j.restart > 0) mode[i] = scan_restart_intervals(j, &ivs[i]) ? 1 : 0;
+        // long restart intervals (few threads for one-interval-per-thread decoding: 13.9 ms per 64 frames at one MCU row) take the
+        // self-synchronising decoder with the markers as boundaries; the device finds the markers, no host scan
+        if (ok && j.restart >= rst_sync_min && !no_selfsync) { mode[i] = 2; rst_iv[i] = j.restart; }
+        else if (ok && j.restart > 0) mode[i] = scan_restart_intervals(j, &ivs[i]) ? 1 : 0;
         else if (ok && !no_selfsync) mode[i] = 2;
     });
     for (int i = 0; i < B; ++i)
@@ -1230,7 +1358,7 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
     // layout: coefficient arena (device; pinned mirror for host-decoded images), plane arena, frame arena, stream / aux arenas
     std::vector<size_t> coef_off(B), plane_off(B), frame_off(B), stream_off(B), aux_off(B), raw_off(B), sync_off(B);
     size_t coef_total = 0, plane_total = 0, frame_total = 0, stream_total = 0, aux_total = 0, host_coef_total = 0, raw_total = 0, sync_total = 0;
-    int max_blocks = 0, max_h = 0, max_w = 0, max_iv = 0, max_sub = 0, max_chunks = 0, n_rst = 0, n_sync = 0;
+    int max_blocks = 0, max_h = 0, max_w = 0, max_iv = 0, max_sub = 0, max_chunks = 0, n_rst = 0, n_sync = 0, n_rstsync = 0;
     for (int i = 0; i < B; ++i) {
         const JpegHeader &j = hdr[i];
         const size_t nblk = j.blocks[0] + j.blocks[1] + j.blocks[2];
@@ -1262,7 +1390,10 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
             const size_t nsub_cap = (j.scan_len * 8 + SUBSEQ_BITS - 1) / SUBSEQ_BITS + 1;
             const size_t nchunks = j.scan_len / UNSTUFF_CHUNK + 1;
             sync_off[i] = sync_total;
-            sync_total += (nsub_cap * 3 + nchunks + 4) * sizeof(int);   // exit states, start states, block counts; chunk counts
+            const size_t iv_cap = rst_iv[i] ? ((size_t)j.mcux * j.mcuy + rst_iv[i] - 1) / rst_iv[i] : 0;
+            // exit states, start states, block counts; chunk counts; (restart boundaries) interval starts, markers per chunk, DC segment ends
+            sync_total += (nsub_cap * 3 + nchunks + 4 + (rst_iv[i] ? (iv_cap + 2) + nchunks + 3 * (iv_cap + 1) + 4 : 0)) * sizeof(int);
+            n_rstsync += rst_iv[i] ? 1 : 0;
             max_sub = std::max<int>(max_sub, (int)nsub_cap - 1);
             max_chunks = std::max<int>(max_chunks, (int)nchunks);
         } else {
@@ -1373,6 +1504,16 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
             d.used_state = sy + cap;
             d.sub_blocks = reinterpret_cast<int *>(sy + 2 * cap);
             d.chunk_drop = reinterpret_cast<int *>(sy + 3 * cap);
+            if (rst_iv[i]) {
+                const size_t nchunks = j.scan_len / UNSTUFF_CHUNK + 1;
+                d.rst_sync = rst_iv[i];
+                d.iv_cap = (int)(((size_t)j.mcux * j.mcuy + rst_iv[i] - 1) / rst_iv[i]);
+                int *p = d.chunk_drop + nchunks;
+                d.n_iv = p;
+                d.iv_start = p + 4;
+                d.chunk_rst = d.iv_start + d.iv_cap + 2;
+                d.seg_dc = d.chunk_rst + nchunks;
+            }
             d.changed = ctx->jpeg_flags.as<int>() + 4 * i;
         }
         frames_out[i].data = d.bgr;
@@ -1409,15 +1550,24 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
     }
     if (n_sync && max_sub > 0) {
         dim3 gs((max_sub + SYNC_THREADS - 1) / SYNC_THREADS, B);
-        jpeg_sync_kernel<<<gs, SYNC_THREADS, 0, ctx->stream>>>(ddesc, 0);
-        FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_sync_kernel");
+        const bool plain = n_sync > n_rstsync, rsts = n_rstsync > 0;       // which builds of the decoders this batch needs
+        auto sync_round = [&](int r) -> int {
+            if (plain) jpeg_sync_kernel<false><<<gs, SYNC_THREADS, 0, ctx->stream>>>(ddesc, r);
+            if (rsts) jpeg_sync_kernel<true><<<gs, SYNC_THREADS, 0, ctx->stream>>>(ddesc, r);
+            FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_sync_kernel");
+            return FD_OK;
+        };
+        if (rsts) {
+            jpeg_zero_rst_kernel<<<dim3(32, B), 256, 0, ctx->stream>>>(ddesc);
+            FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_zero_rst_kernel");
+        }
+        FD_TRY(sync_round(0));
         int round = 0;
         int *flags = ctx->jpeg_flags_host.as<int>();
         for (int group = 6;; group = 4) {
             for (int r = 0; r < group; ++r) {
                 ++round;
-                jpeg_sync_kernel<<<gs, SYNC_THREADS, 0, ctx->stream>>>(ddesc, round);
-                FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_sync_kernel");
+                FD_TRY(sync_round(round));
                 jpeg_sync_epilogue_kernel<<<B, 32, 0, ctx->stream>>>(ddesc, 0);
                 FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_sync_epilogue_kernel");
             }
@@ -1431,7 +1581,8 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
         ctx->jpeg_last_rounds = round;
         jpeg_sync_epilogue_kernel<<<B, 1024, 0, ctx->stream>>>(ddesc, 1);
         FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_sync_epilogue_kernel");
-        jpeg_write_kernel<<<gs, SYNC_THREADS, 0, ctx->stream>>>(ddesc);
+        if (plain) jpeg_write_kernel<false><<<gs, SYNC_THREADS, 0, ctx->stream>>>(ddesc);
+        if (rsts) jpeg_write_kernel<true><<<gs, SYNC_THREADS, 0, ctx->stream>>>(ddesc);
         FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_write_kernel");
         jpeg_dc_kernel<<<dim3(3, B), 1024, 0, ctx->stream>>>(ddesc);
         FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_dc_kernel");

@@ -100,9 +100,9 @@ def test_pipeline_host_jpeg_equals_pipeline_on_decoded_frames(ctx, oracle):
 
 @pytest.mark.skipif(cv2 is None, reason="cv2 not importable (only to ENCODE the test streams)")
 def test_restart_marker_streams_are_huffman_decoded_on_the_device(ctx):
-    """Streams with DRI/RSTn take jpeg_huffman_kernel (one restart interval per thread), streams without take the
-    self-synchronising sub-sequence decoder; only compressed bytes cross PCIe.  Both in one batch, every frame bit-identical to
-    cv2.imdecode."""
+    """Streams with short restart intervals take jpeg_huffman_kernel (one interval per thread); streams without markers, or with
+    intervals of 32 MCUs and more, the self-synchronising sub-sequence decoder (restart markers as known-state boundaries); only
+    compressed bytes cross PCIe.  All in one batch, every frame bit-identical to cv2.imdecode."""
     import ctypes as C
     SS = [cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]
     cases = [(1080, 1920, 0, 16, 90), (1080, 1920, 0, 0, 90), (720, 1280, 1, 1, 75), (333, 517, 2, 7, 95), (2160, 3840, 0, 240, 85),
@@ -120,7 +120,7 @@ def test_restart_marker_streams_are_huffman_decoded_on_the_device(ctx):
     frames = ctx.decode_jpeg_batch(streams, n_threads=2)
     ctx.synchronize()
     st = ctx.jpeg_last_stats()
-    assert st["device_entropy_images"] == len(cases) and st["host_entropy_images"] == 0 and st["selfsync_images"] == 1
+    assert st["device_entropy_images"] == len(cases) and st["host_entropy_images"] == 0 and st["selfsync_images"] == 4
     assert st["h2d_bytes"] < sum(s.size for s in streams) + 1e6               # only compressed bytes (+ tables) cross PCIe
     for b, w_ in enumerate(want):
         row = np.empty((w_.shape[0], frames[b].pitch), np.uint8)
@@ -128,6 +128,52 @@ def test_restart_marker_streams_are_huffman_decoded_on_the_device(ctx):
         np.testing.assert_array_equal(row[:, :w_.shape[1] * 3].reshape(w_.shape), w_, err_msg="case %d %r" % (b, cases[b]))
     for s_, w_ in zip(streams[:3], want[:3]):                                  # and through the single-image call
         np.testing.assert_array_equal(ctx.imdecode(s_.tobytes()), w_)
+
+
+@pytest.mark.skipif(cv2 is None, reason="cv2 not importable (only to ENCODE the test streams)")
+def test_long_restart_intervals_take_the_selfsync_decoder(ctx):
+    """DRI of one MCU row and more: too few intervals for one thread each, so the markers become boundaries of the
+    self-synchronising chain (dropped by the device unstuffing, DC prediction segmented at them).  Bit-identical to cv2."""
+    import ctypes as C
+    SS = [cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]
+    cases = [(1080, 1920, 0, 120, 90), (1080, 1920, 0, 480, 90), (1080, 1920, 0, 32, 50), (720, 1280, 1, 80, 75), (333, 517, 2, 33, 95),
+             (2160, 3840, 0, 240, 85), (601, 799, 0, 100000, 100), (480, 640, 2, 64, 10), (1080, 1920, 0, 121, 97)]
+    streams, want = [], []
+    for i, (h, w, ss, rst, q) in enumerate(cases):
+        params = [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, SS[ss], cv2.IMWRITE_JPEG_RST_INTERVAL, rst]
+        img = synth.make_frame(h, w, 1300 + i) if i != 6 else np.random.default_rng(3).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        buf = np.asarray(cv2.imencode(".jpg", img, params)[1], np.uint8).ravel()
+        streams.append(buf)
+        want.append(cv2.imdecode(buf, cv2.IMREAD_UNCHANGED))
+    for group in (list(range(len(cases))), [0], [6, 1]):
+        frames = ctx.decode_jpeg_batch([streams[i] for i in group], n_threads=2)
+        ctx.synchronize()
+        st = ctx.jpeg_last_stats()
+        assert st["selfsync_images"] == len(group) and st["host_entropy_images"] == 0, st
+        for b, i in enumerate(group):
+            w_ = want[i]
+            row = np.empty((w_.shape[0], frames[b].pitch), np.uint8)
+            ctx.lib.fd_memcpy_d2h(ctx.handle, row.ctypes.data_as(C.c_void_p), C.c_void_p(frames[b].data), C.c_size_t(row.nbytes))
+            np.testing.assert_array_equal(row[:, :w_.shape[1] * 3].reshape(w_.shape), w_, err_msg="case %d %r" % (i, cases[i]))
+
+
+@pytest.mark.skipif(cv2 is None, reason="cv2 not importable (only to ENCODE the test streams)")
+def test_every_restart_interval_through_the_selfsync_decoder():
+    """FD_JPEG_RST_SYNC_MIN=1: also the short intervals (1, 2, 7, 16 MCUs: several boundaries inside one sub-sequence)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r); import numpy as np, cv2\n"
+            "from rs_face_detection_b200 import Context\n"
+            "from rs_face_detection_b200.utils import synth\n"
+            "c = Context(0)\n"
+            "SS = [cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]\n"
+            "for i, (h, w, ss, rst, q) in enumerate([(1080, 1920, 0, 1, 90), (720, 1280, 1, 2, 75), (333, 517, 2, 7, 95), (1080, 1920, 0, 16, 90), (64, 48, 0, 3, 60), (17, 33, 0, 2, 100)]):\n"
+            "    buf = np.asarray(cv2.imencode('.jpg', synth.make_frame(h, w, 1500 + i), [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, SS[ss], cv2.IMWRITE_JPEG_RST_INTERVAL, rst])[1], np.uint8).ravel()\n"
+            "    np.testing.assert_array_equal(c.imdecode(buf.tobytes()), cv2.imdecode(buf, cv2.IMREAD_UNCHANGED), err_msg=str((h, w, ss, rst, q)))\n"
+            "    assert c.jpeg_last_stats()['selfsync_images'] == 1\n"
+            "print('ok')\n" % (root,))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, FD_JPEG_RST_SYNC_MIN="1"), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-1500:]
 
 
 def test_corrupted_streams_fail_or_decode_but_never_wedge_the_context(ctx):
