@@ -4,11 +4,12 @@
 // Split of the work:
 //   entropy decoding (ITU-T T.81 Annex F.2.2).  An entropy-coded segment is a serial bit stream: every symbol's position
 //          depends on all earlier ones, and the only synchronisation points the format has are restart markers (DRI / RSTn).
-//          * streams WITH restart markers: the host only locates the markers (a byte scan); the compressed bytes go to the
+//          * streams WITH restart markers less than 32 MCUs apart: the host only locates the markers (a byte scan); the compressed bytes go to the
 //            device as they are and `jpeg_huffman_kernel` decodes one restart interval per thread (Huffman lookup tables in
 //            shared memory, coefficients written straight into the device coefficient blocks) — the 1.3 MB stream of a 1080p
 //            frame is all that crosses PCIe;
-//          * streams WITHOUT restart markers (what most encoders emit by default) are copied as they are too, unstuffed on the
+//          * streams WITHOUT restart markers (what most encoders emit by default) and streams with LONG restart intervals (too
+//            few intervals for one thread each; the markers become boundaries of the chain) are copied as they are too, unstuffed on the
 //            device (jpeg_unstuff_*_kernel) and decoded by self-synchronising sub-sequences: jpeg_sync_kernel rounds to the
 //            fixed point of the chain of decoder states, then jpeg_write_kernel + jpeg_dc_kernel (see the section below);
 //          * a host Huffman decoder (one image per worker thread, pinned coefficient blocks, copied) remains for streams with
