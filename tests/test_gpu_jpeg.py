@@ -171,6 +171,22 @@ def test_every_restart_interval_through_the_selfsync_decoder():
             "    buf = np.asarray(cv2.imencode('.jpg', synth.make_frame(h, w, 1500 + i), [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, SS[ss], cv2.IMWRITE_JPEG_RST_INTERVAL, rst])[1], np.uint8).ravel()\n"
             "    np.testing.assert_array_equal(c.imdecode(buf.tobytes()), cv2.imdecode(buf, cv2.IMREAD_UNCHANGED), err_msg=str((h, w, ss, rst, q)))\n"
             "    assert c.jpeg_last_stats()['selfsync_images'] == 1\n"
+            "    if i in (0, 2, 3):\n"                      # corrupt copies (bit flips, damaged / missing markers, truncation): return, never wedge
+            "        rng = np.random.default_rng(40 + i)\n"
+            "        for trial in range(8):\n"
+            "            bad = buf.copy(); start = len(bad) // 3\n"
+            "            if trial < 3:\n"
+            "                for pos in rng.integers(start, len(bad) - 2, 12): bad[pos] ^= np.uint8(1 << int(rng.integers(0, 8)))\n"
+            "            elif trial < 6:\n"
+            "                ff = np.flatnonzero((bad[start:-2] == 0xFF) & ((bad[start + 1:-1] & 0xF8) == 0xD0)) + start\n"
+            "                for pos in rng.choice(ff, min(3, len(ff)), replace=False): bad[pos + 1] = [0xD9, 0x00, 0xD0 | int(rng.integers(0, 8))][trial - 3]\n"
+            "            else:\n"
+            "                bad = bad[:int(rng.integers(start, len(bad) - 2))]\n"
+            "            try:\n"
+            "                assert c.imdecode(bad.tobytes()).shape == (h, w, 3)\n"
+            "            except Exception as e:\n"
+            "                assert type(e).__name__ == 'FdError', e\n"
+            "        np.testing.assert_array_equal(c.imdecode(buf.tobytes()), cv2.imdecode(buf, cv2.IMREAD_UNCHANGED))\n"
             "print('ok')\n" % (root,))
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, FD_JPEG_RST_SYNC_MIN="1"), capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-1500:]
