@@ -265,12 +265,13 @@ int fd_align_selected(fd_ctx *ctx, const fd_frame *frames, int B, uint8_t *crops
 int fd_jpeg_info(const uint8_t *jpeg, size_t nbytes, int *height, int *width, int *subsampling);
 /* Decodes B JPEG streams (host memory) into DEVICE-resident BGR frames, bit-identical to cv2.imdecode (libjpeg-turbo islow IDCT,
  * fancy upsampling, 16-bit colour tables).  The streams are copied to the device as they are and entropy-decoded there: one
- * restart interval per thread when a stream carries restart markers less than 32 MCUs apart (DRI / RSTn; the host locates them
- * with a byte scan, up to n_threads threads, 0 = hardware concurrency, one image per thread); otherwise — no markers, or long
- * intervals — unstuffed on the device and decoded by self-synchronising sub-sequences, restart markers serving as known-state
+ * restart interval per thread when a stream carries restart markers less than 32 MCUs apart (DRI / RSTn; the device locates
+ * them); otherwise — no markers, or long intervals — unstuffed on the device and decoded by self-synchronising sub-sequences,
+ * restart markers serving as known-state
  * boundaries (exact: the rounds run to their fixed point; the call synchronises the ctx stream once per group of rounds, so
  * the count fd_jpeg_last_stats reports is a multiple of the group size).  Only a stream with more than
- * two DC / AC tables or an inconsistent marker sequence is Huffman-decoded on the host.  Dequantisation + IDCT and
+ * two DC / AC tables is Huffman-decoded on the host.  The host parses headers and tables only (up to n_threads threads, 0 =
+ * hardware concurrency, one image per thread).  Dequantisation + IDCT and
  * upsampling + colour conversion are CUDA kernels on the ctx stream.  frames_out[i] = {device pointer owned by the ctx and valid
  * until the next call, h, w, pitch = align16(3w)}: feed it to fd_preprocess_batch / fd_align_detections directly. */
 int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, const size_t *nbytes, int B, int n_threads, fd_frame *frames_out);

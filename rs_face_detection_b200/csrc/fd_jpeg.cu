@@ -4,7 +4,7 @@
 // Split of the work:
 //   entropy decoding (ITU-T T.81 Annex F.2.2).  An entropy-coded segment is a serial bit stream: every symbol's position
 //          depends on all earlier ones, and the only synchronisation points the format has are restart markers (DRI / RSTn).
-//          * streams WITH restart markers less than 32 MCUs apart: the host only locates the markers (a byte scan); the compressed bytes go to the
+//          * streams WITH restart markers less than 32 MCUs apart: the device locates the markers (jpeg_iv_write_kernel); the compressed bytes go to the
 //            device as they are and `jpeg_huffman_kernel` decodes one restart interval per thread (Huffman lookup tables in
 //            shared memory, coefficients written straight into the device coefficient blocks) — the 1.3 MB stream of a 1080p
 //            frame is all that crosses PCIe;
@@ -361,6 +361,8 @@ struct JpegImageDev {
     int td[3], ta[3];
     const uint8_t *stream;     // entropy-coded segment (gpu_entropy 1: as received; 2: with the stuffed zero bytes removed, device-made)
     const uint32_t *iv;        // [n_intervals][2]: first byte / end (exclusive) of each restart interval's data, offsets into stream
+    int scan_rst;              // gpu_entropy 1: the device locates the markers (jpeg_unstuff_count / scan + jpeg_iv_write_kernel fill iv
+    uint32_t *iv_dev;          //   and *n_iv; n_intervals is then the EXPECTED count = the table's capacity)
     const JpegHuffDev *huff;
     // gpu_entropy == 2: self-synchronising decode of a stream WITHOUT restart markers (sub-sequences of SUBSEQ_BITS bits)
     const uint8_t *raw;        // the segment as received (FF 00 stuffing, EOI at the end); raw_len bytes
@@ -469,7 +471,8 @@ __global__ void __launch_bounds__(HUFF_THREADS) jpeg_huffman_kernel(const JpegIm
     __shared__ unsigned stage[HUFF_THREADS * STAGE_PITCH];
     __shared__ uint8_t zz[64];
     const JpegImageDev &im = imgs[blockIdx.y];
-    if (im.gpu_entropy != 1 || blockIdx.x * HUFF_THREADS >= im.n_intervals) return;   // uniform over the CTA
+    const int n_intervals = im.scan_rst ? min(im.n_intervals, *im.n_iv) : im.n_intervals;
+    if (im.gpu_entropy != 1 || blockIdx.x * HUFF_THREADS >= n_intervals) return;   // uniform over the CTA
     if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
     for (int i = threadIdx.x; i < (int)(sizeof(JpegHuffDev) / 4); i += HUFF_THREADS)
         reinterpret_cast<unsigned *>(&tab)[i] = __ldg(reinterpret_cast<const unsigned *>(im.huff) + i);
@@ -480,7 +483,7 @@ __global__ void __launch_bounds__(HUFF_THREADS) jpeg_huffman_kernel(const JpegIm
     int16_t *my_row = reinterpret_cast<int16_t *>(stage + threadIdx.x * STAGE_PITCH);
     const uint16_t *look = &tab.look[0][0];
     const int iv = blockIdx.x * HUFF_THREADS + threadIdx.x;
-    const bool live = iv < im.n_intervals;
+    const bool live = iv < n_intervals;
     // The interval's bytes are consumed as ALIGNED 32-bit words, each loaded one refill ahead of its use (`wnext`), so the load's
     // latency (DRAM: the stream has just arrived over PCIe) overlaps the ~4 symbols decoded in between.  `lo`/`hi`: the first and
     // one-past-last byte address of the interval; bytes of a word outside [lo, hi) are ignored.
@@ -697,10 +700,11 @@ __device__ __forceinline__ uint4 unstuff_classify(const uint8_t *__restrict__ ra
 __global__ void __launch_bounds__(UNSTUFF_THREADS) jpeg_unstuff_count_kernel(const JpegImageDev *__restrict__ imgs) {
     const JpegImageDev &im = imgs[blockIdx.y];
     const int n = im.raw_len;
-    if (im.gpu_entropy != 2 || (long long)blockIdx.x * UNSTUFF_CHUNK > n) return;
+    if (!(im.gpu_entropy == 2 || im.scan_rst) || (long long)blockIdx.x * UNSTUFF_CHUNK > n) return;
     const int g = blockIdx.x * UNSTUFF_CHUNK + threadIdx.x * 16;
+    const bool rst_ok = im.rst_sync != 0 || im.scan_rst != 0;
     unsigned drop = 0, mark = 0, rst = 0;
-    if (g < n) unstuff_classify(im.raw, n, g, im.rst_sync != 0, &drop, &mark, &rst);
+    if (g < n) unstuff_classify(im.raw, n, g, rst_ok, &drop, &mark, &rst);
     int cnt = __popc(drop), nr = __popc(rst);
     int slack = mark ? n - (g + __ffs(mark) - 1) : 0;                        // larger = earlier
 #pragma unroll
@@ -715,7 +719,7 @@ __global__ void __launch_bounds__(UNSTUFF_THREADS) jpeg_unstuff_count_kernel(con
     if (threadIdx.x == 0) {
         for (int w = 1; w < UNSTUFF_THREADS / 32; ++w) { cnt += s_cnt[w]; nr += s_nr[w]; slack = max(slack, s_slack[w]); }
         im.chunk_drop[blockIdx.x] = cnt;
-        if (im.rst_sync) im.chunk_rst[blockIdx.x] = nr;
+        if (rst_ok) im.chunk_rst[blockIdx.x] = nr;
         if (slack) atomicMax(im.changed + 2, slack);
     }
 }
@@ -723,9 +727,9 @@ __global__ void __launch_bounds__(UNSTUFF_THREADS) jpeg_unstuff_count_kernel(con
 // one CTA per image: chunk counts -> non-data bytes before each chunk
 __global__ void __launch_bounds__(1024) jpeg_unstuff_scan_kernel(const JpegImageDev *__restrict__ imgs) {
     const JpegImageDev &im = imgs[blockIdx.x];
-    if (im.gpu_entropy != 2) return;
-    block_exclusive_scan_1024(im.chunk_drop, im.raw_len / UNSTUFF_CHUNK + 1);
-    if (im.rst_sync) block_exclusive_scan_1024(im.chunk_rst, im.raw_len / UNSTUFF_CHUNK + 1);
+    if (!(im.gpu_entropy == 2 || im.scan_rst)) return;
+    if (im.gpu_entropy == 2) block_exclusive_scan_1024(im.chunk_drop, im.raw_len / UNSTUFF_CHUNK + 1);
+    if (im.rst_sync || im.scan_rst) block_exclusive_scan_1024(im.chunk_rst, im.raw_len / UNSTUFF_CHUNK + 1);
 }
 
 // the data bytes before the first marker, compacted; the thread that owns the end position publishes nbits / n_sub and pads
@@ -778,6 +782,49 @@ __global__ void __launch_bounds__(UNSTUFF_THREADS) jpeg_unstuff_write_kernel(Jpe
                 if (rbefore < im.iv_cap) im.iv_start[rbefore] = o;
             }
             if (!((drop >> j) & 1u)) out[o++] = (uint8_t)(w[j >> 2] >> ((j & 3) * 8));
+        }
+    }
+}
+
+// One-interval-per-thread decoding (gpu_entropy 1, scan_rst): the restart-interval table from the same marker classification,
+// as RAW byte offsets {first data byte, end} — interval j+1 starts behind marker j, the last one ends at the first other marker.
+__global__ void __launch_bounds__(UNSTUFF_THREADS) jpeg_iv_write_kernel(const JpegImageDev *__restrict__ imgs) {
+    const JpegImageDev &im = imgs[blockIdx.y];
+    const int n = im.raw_len;
+    if (im.gpu_entropy != 1 || !im.scan_rst) return;
+    const int end = n - im.changed[2];
+    if ((long long)blockIdx.x * UNSTUFF_CHUNK > end) return;
+    const int g = blockIdx.x * UNSTUFF_CHUNK + threadIdx.x * 16;
+    unsigned drop = 0, mark = 0, rst = 0;
+    if (g < n) unstuff_classify(im.raw, n, g, true, &drop, &mark, &rst);
+    const int nr = __popc(rst);
+    int incl_r = nr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int nbr = __shfl_up_sync(0xffffffffu, incl_r, o);
+        if (lane >= o) incl_r += nbr;
+    }
+    __shared__ int s_r[UNSTUFF_THREADS / 32];
+    if (lane == 31) s_r[warp] = incl_r;
+    __syncthreads();
+    int rbefore = im.chunk_rst[blockIdx.x] + incl_r - nr;                    // restart markers before byte g
+    for (int w = 0; w < warp; ++w) rbefore += s_r[w];
+    const int cap = im.n_intervals;
+    if (end >= g && end < g + 16) {
+        const int niv = min(rbefore + __popc(rst & ((1u << (end - g)) - 1u)) + 1, cap);
+        *im.n_iv = niv;
+        im.iv_dev[0] = 0u;
+        im.iv_dev[2 * niv - 1] = (uint32_t)end;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (g + j < end && ((rst >> j) & 1u)) {
+            if (rbefore + 1 < cap) {
+                im.iv_dev[2 * rbefore + 1] = (uint32_t)(g + j);              // interval rbefore ends at the marker ...
+                im.iv_dev[2 * rbefore + 2] = (uint32_t)(g + j + 2);          // ... and the next one starts behind it
+            }
+            ++rbefore;
         }
     }
 }
@@ -1142,7 +1189,8 @@ __global__ void __launch_bounds__(IDCT_BLOCKS * 8) jpeg_idct_kernel(const JpegIm
     const int c = qb < HV ? 0 : qb - HV + 1;
     const int yb = c == 0 ? my * im.V + qb / im.H : my, xb = c == 0 ? mx * im.H + qb % im.H : mx;
     if (live) {
-        const bool held = im.gpu_entropy != 2 || im.rst_sync != 0 || n < im.changed[3];   // a truncated stream holds fewer blocks: the rest is zero
+        bool held = im.gpu_entropy != 2 || im.rst_sync != 0 || n < im.changed[3];   // a truncated stream holds fewer blocks: the rest is zero
+        if (im.gpu_entropy == 1 && im.scan_rst && mcu / im.restart >= *im.n_iv) held = false;   // ... or fewer restart intervals
         int dc_base = 0;                                      // (rst_sync: the arena was cleared instead)
         if (im.gpu_entropy == 2 && im.rst_sync != 0 && k == 0) {
             const int seg = mcu / im.rst_sync;
@@ -1341,6 +1389,7 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
     std::vector<char> mode((size_t)B, 0);
     std::vector<int> rst_iv((size_t)B, 0);          // mode 2 on a stream WITH restart markers: its restart interval (MCUs)
     static const int rst_sync_min = getenv("FD_JPEG_RST_SYNC_MIN") ? atoi(getenv("FD_JPEG_RST_SYNC_MIN")) : RST_SYNC_MIN_MCUS;
+    static const bool host_marker_scan = getenv("FD_JPEG_HOST_MARKER_SCAN") != nullptr;   // A/B switch: round-2 behaviour (memchr scan, host fallback)
     parallel_images(B, [&](int i) {
         errs[i] = parse_jpeg(jpegs[i], nbytes[i], &hdr[i]);
         if (errs[i]) return;
@@ -1350,7 +1399,7 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
         // long restart intervals (few threads for one-interval-per-thread decoding: 13.9 ms per 64 frames at one MCU row) take the
         // self-synchronising decoder with the markers as boundaries; the device finds the markers, no host scan
         if (ok && j.restart >= rst_sync_min && !no_selfsync) { mode[i] = 2; rst_iv[i] = j.restart; }
-        else if (ok && j.restart > 0) mode[i] = scan_restart_intervals(j, &ivs[i]) ? 1 : 0;
+        else if (ok && j.restart > 0) mode[i] = host_marker_scan ? (scan_restart_intervals(j, &ivs[i]) ? 1 : 0) : 1;
         else if (ok && !no_selfsync) mode[i] = 2;
     });
     for (int i = 0; i < B; ++i)
@@ -1359,7 +1408,7 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
     // layout: coefficient arena (device; pinned mirror for host-decoded images), plane arena, frame arena, stream / aux arenas
     std::vector<size_t> coef_off(B), plane_off(B), frame_off(B), stream_off(B), aux_off(B), raw_off(B), sync_off(B);
     size_t coef_total = 0, plane_total = 0, frame_total = 0, stream_total = 0, aux_total = 0, host_coef_total = 0, raw_total = 0, sync_total = 0;
-    int max_blocks = 0, max_h = 0, max_w = 0, max_iv = 0, max_sub = 0, max_chunks = 0, n_rst = 0, n_sync = 0, n_rstsync = 0;
+    int max_blocks = 0, max_h = 0, max_w = 0, max_iv = 0, max_sub = 0, max_chunks = 0, n_rst = 0, n_sync = 0, n_rstsync = 0, n_scan = 0;
     for (int i = 0; i < B; ++i) {
         const JpegHeader &j = hdr[i];
         const size_t nblk = j.blocks[0] + j.blocks[1] + j.blocks[2];
@@ -1379,7 +1428,15 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
             stream_total += (j.scan_len + 15) & ~(size_t)15;
             aux_off[i] = aux_total;
             aux_total += ((sizeof(JpegHuffDev) + ivs[i].size() * sizeof(uint32_t)) + 15) & ~(size_t)15;
-            max_iv = std::max<int>(max_iv, (int)(ivs[i].size() / 2));
+            const size_t want = ((size_t)j.mcux * j.mcuy + j.restart - 1) / j.restart;
+            max_iv = std::max<int>(max_iv, host_marker_scan ? (int)(ivs[i].size() / 2) : (int)want);
+            if (!host_marker_scan) {                   // device marker scan: markers per chunk, flags' neighbours, the interval table
+                const size_t nchunks = j.scan_len / UNSTUFF_CHUNK + 1;
+                sync_off[i] = sync_total;
+                sync_total += (2 * nchunks + 4 + 2 * want + 4) * sizeof(int);
+                max_chunks = std::max<int>(max_chunks, (int)nchunks);
+                ++n_scan;
+            }
         } else if (mode[i] == 2) {
             ++n_sync;
             stream_off[i] = stream_total;
@@ -1433,7 +1490,7 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
         }
         FD_CUDA(cudaMemcpyAsync(ctx->jpeg_aux.p, aux, aux_total, cudaMemcpyHostToDevice, ctx->stream));
         h2d += (int64_t)aux_total;
-        if (n_sync) FD_CUDA(cudaMemsetAsync(ctx->jpeg_flags.p, 0, sizeof(int) * 4 * (size_t)B, ctx->stream));
+        if (n_sync || n_scan) FD_CUDA(cudaMemsetAsync(ctx->jpeg_flags.p, 0, sizeof(int) * 4 * (size_t)B, ctx->stream));
     }
     // 1b. host path: entropy decoding on the host, images are independent, one per worker thread
     std::vector<size_t> host_off(B, 0);
@@ -1490,9 +1547,22 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
             d.stream = ctx->jpeg_stream.as<uint8_t>() + stream_off[i];
             d.huff = reinterpret_cast<const JpegHuffDev *>(ctx->jpeg_aux.as<unsigned char>() + aux_off[i]);
         }
-        if (mode[i] == 1) {
+        if (mode[i] == 1 && host_marker_scan) {
             d.n_intervals = (int)(ivs[i].size() / 2);
             d.iv = reinterpret_cast<const uint32_t *>(ctx->jpeg_aux.as<unsigned char>() + aux_off[i] + sizeof(JpegHuffDev));
+        } else if (mode[i] == 1) {
+            const size_t nchunks = j.scan_len / UNSTUFF_CHUNK + 1;
+            int *p = reinterpret_cast<int *>(ctx->jpeg_sync.as<unsigned char>() + sync_off[i]);
+            d.scan_rst = 1;
+            d.raw = d.stream;
+            d.raw_len = (int)j.scan_len;
+            d.n_intervals = (int)(((size_t)j.mcux * j.mcuy + j.restart - 1) / j.restart);
+            d.chunk_drop = p;
+            d.chunk_rst = p + nchunks;
+            d.n_iv = d.chunk_rst + nchunks;
+            d.iv_dev = reinterpret_cast<uint32_t *>(d.n_iv + 4);
+            d.iv = d.iv_dev;
+            d.changed = ctx->jpeg_flags.as<int>() + 4 * i;
         } else if (mode[i] == 2) {
             d.raw = ctx->jpeg_raw.as<uint8_t>() + raw_off[i];
             d.clean = ctx->jpeg_stream.as<uint8_t>() + stream_off[i];
@@ -1530,7 +1600,19 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
     ctx->jpeg_last_selfsync = n_sync;
     ctx->jpeg_last_B = B;
     const JpegImageDev *ddesc = ctx->jpeg_desc.as<JpegImageDev>();
-    // 3a. entropy decoding on the device, streams with restart markers: one restart interval per thread
+    // 3a. entropy decoding on the device, streams with (short) restart intervals: the device locates the markers, then one
+    //     restart interval per thread
+    if (n_sync || n_scan) {
+        dim3 gu(max_chunks, B);
+        jpeg_unstuff_count_kernel<<<gu, UNSTUFF_THREADS, 0, ctx->stream>>>(ddesc);
+        FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_unstuff_count_kernel");
+        jpeg_unstuff_scan_kernel<<<B, 1024, 0, ctx->stream>>>(ddesc);
+        FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_unstuff_scan_kernel");
+        if (n_scan) {
+            jpeg_iv_write_kernel<<<gu, UNSTUFF_THREADS, 0, ctx->stream>>>(ddesc);
+            FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_iv_write_kernel");
+        }
+    }
     if (n_rst) {
         dim3 g0((max_iv + HUFF_THREADS - 1) / HUFF_THREADS, B);
         jpeg_huffman_kernel<<<g0, HUFF_THREADS, 0, ctx->stream>>>(ddesc);
@@ -1542,10 +1624,6 @@ FD_EXPORT int fd_decode_jpeg_batch(fd_ctx *ctx, const uint8_t *const *jpegs, con
     ctx->jpeg_last_rounds = 0;
     if (n_sync) {
         dim3 gu(max_chunks, B);
-        jpeg_unstuff_count_kernel<<<gu, UNSTUFF_THREADS, 0, ctx->stream>>>(ddesc);
-        FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_unstuff_count_kernel");
-        jpeg_unstuff_scan_kernel<<<B, 1024, 0, ctx->stream>>>(ddesc);
-        FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_unstuff_scan_kernel");
         jpeg_unstuff_write_kernel<<<gu, UNSTUFF_THREADS, 0, ctx->stream>>>(ctx->jpeg_desc.as<JpegImageDev>());
         FD_LAUNCH_CHECK_NAMED(ctx, "jpeg_unstuff_write_kernel");
     }
