@@ -161,6 +161,20 @@ __device__ __forceinline__ unsigned blend24(unsigned lo0, unsigned hi0, unsigned
     return ob | (og << 8) | (orr << 16);
 }
 
+// blend24 for the fixed-size kernel: ay6 = ay << 6, so each channel's sum lands in byte 2 of its word ((S + 512) << 6 < 2^24) and
+// two byte permutes assemble the pixel instead of three shifts and two merges.
+__device__ __forceinline__ unsigned blend24_scaled(unsigned lo0, unsigned hi0, unsigned lo1, unsigned hi1, int ax, int ay6) {
+    const unsigned wx = (unsigned)(32 - ax) | ((unsigned)ax << 8);
+    const int wy0 = 2048 - ay6, wy1 = ay6;
+    const int hb0 = (int)__dp4a(__byte_perm(lo0, hi0, 0x7730), wx, 0u), hb1 = (int)__dp4a(__byte_perm(lo1, hi1, 0x7730), wx, 0u);
+    const int hg0 = (int)__dp4a(__byte_perm(lo0, hi0, 0x7741), wx, 0u), hg1 = (int)__dp4a(__byte_perm(lo1, hi1, 0x7741), wx, 0u);
+    const int hr0 = (int)__dp4a(__byte_perm(lo0, hi0, 0x7752), wx, 0u), hr1 = (int)__dp4a(__byte_perm(lo1, hi1, 0x7752), wx, 0u);
+    const unsigned sb = (unsigned)(hb0 * wy0 + hb1 * wy1 + 32768);
+    const unsigned sg = (unsigned)(hg0 * wy0 + hg1 * wy1 + 32768);
+    const unsigned sr = (unsigned)(hr0 * wy0 + hr1 * wy1 + 32768);
+    return __byte_perm(__byte_perm(sb, sg, 0x7762), sr, 0x7610);   // b | g << 8 | r << 16, byte 3 = 0
+}
+
 // One output pixel with per-tap BORDER_CONSTANT(0) tests; X, Y are the 5-bit sub-pixel fixed-point source coordinates.
 __device__ __forceinline__ unsigned border_tap_blend(const uint8_t *data, int w, int h, int pitch, const uint8_t *lo_lim,
                                                      const uint8_t *hi_lim, int X, int Y) {
@@ -356,9 +370,11 @@ __global__ void __launch_bounds__(WARP_THREADS, 4) warp_kernel(WarpArgs a) {
 #else
 #define WARP_LD(p) __ldg(p)
 #endif
+// pack_sel: the byte permute that cuts this lane's word out of (its pixel, the next lane's pixel): lanes 0..2 of a quad store
+// bytes 0-3, 4-7, 8-11 of the quad's 12.
 template <int CW, int N>
 __device__ __forceinline__ void fixed_rounds_interior(const uint8_t *__restrict__ data, unsigned pitch, int2 d, const int2 *__restrict__ xy,
-                                                      unsigned *__restrict__ outw, bool store) {
+                                                      unsigned *__restrict__ outw, bool store, unsigned pack_sel) {
     uint2 q[N][4];
     unsigned off[N];
     int axy[N];
@@ -366,7 +382,7 @@ __device__ __forceinline__ void fixed_rounds_interior(const uint8_t *__restrict_
     for (int u = 0; u < N; ++u) {
         const int2 r0 = xy[2 * u];
         const int X = (int)((unsigned)r0.x + (unsigned)d.x) >> 5, Y = (int)((unsigned)r0.y + (unsigned)d.y) >> 5;
-        axy[u] = (X & 31) | ((Y & 31) << 8);
+        axy[u] = (X & 31) | ((Y & 31) << 14);   // ax | ay << 6 << 8
         off[u] = (unsigned)(Y >> 5) * pitch + (unsigned)(X >> 5) * 3u;
         const uint2 *r0p = reinterpret_cast<const uint2 *>(data + (off[u] & ~7u));
         const uint2 *r1p = reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(r0p) + pitch);   // pitch % 8 == 0
@@ -380,11 +396,10 @@ __device__ __forceinline__ void fixed_rounds_interior(const uint8_t *__restrict_
         const unsigned sft = (off[u] & 3u) * 8;
         const unsigned a0 = up ? q[u][0].y : q[u][0].x, b0 = up ? q[u][1].x : q[u][0].y, c0 = up ? q[u][1].y : q[u][1].x;
         const unsigned a1 = up ? q[u][2].y : q[u][2].x, b1 = up ? q[u][3].x : q[u][2].y, c1 = up ? q[u][3].y : q[u][3].x;
-        const unsigned v = blend24(__funnelshift_r(a0, b0, sft), __funnelshift_r(b0, c0, sft), __funnelshift_r(a1, b1, sft),
-                                   __funnelshift_r(b1, c1, sft), axy[u] & 31, axy[u] >> 8);
+        const unsigned v = blend24_scaled(__funnelshift_r(a0, b0, sft), __funnelshift_r(b0, c0, sft), __funnelshift_r(a1, b1, sft),
+                                          __funnelshift_r(b1, c1, sft), axy[u] & 31, axy[u] >> 8);
         const unsigned nv = __shfl_down_sync(0xffffffffu, v, 1);
-        const unsigned word = __funnelshift_r(__byte_perm(v, nv, 0x4210), nv >> 8, 8 * (threadIdx.x & 3u));
-        if (store) outw[u * (2 * CW * 3 / 4)] = word;
+        if (store) outw[u * (2 * CW * 3 / 4)] = __byte_perm(v, nv, pack_sel);
     }
 }
 
@@ -460,12 +475,13 @@ __global__ void __launch_bounds__(2 * CW) warp_fixed_kernel(WarpArgs a) {
         if (tid == 0 && y0 == 0 && a.mode_out) a.mode_out[f] = 1;
         const int2 *xy = &xy0[par][r];
         if (interior) {
+            const unsigned pack_sel = (tid & 3) == 0 ? 0x4210u : ((tid & 3) == 1 ? 0x5421u : 0x6542u);
             int u = 0;
 #pragma unroll 1
             for (; u + UN <= ROUNDS; u += UN)
-                fixed_rounds_interior<CW, UN>(data, (unsigned)pitch, d, xy + 2 * u, outw + u * (T * 3 / 4), store);
+                fixed_rounds_interior<CW, UN>(data, (unsigned)pitch, d, xy + 2 * u, outw + u * (T * 3 / 4), store, pack_sel);
             constexpr int REM = ROUNDS % UN;
-            if (REM) fixed_rounds_interior<CW, REM ? REM : 1>(data, (unsigned)pitch, d, xy + 2 * (ROUNDS - REM), outw + (ROUNDS - REM) * (T * 3 / 4), store);
+            if (REM) fixed_rounds_interior<CW, REM ? REM : 1>(data, (unsigned)pitch, d, xy + 2 * (ROUNDS - REM), outw + (ROUNDS - REM) * (T * 3 / 4), store, pack_sel);
         } else {
             const uint8_t *lo_lim = data, *hi_lim = data + (size_t)(fh - 1) * pitch + (size_t)fw * 3;  // end of valid pixel bytes
             for (int u = 0; u < ROUNDS; ++u) {

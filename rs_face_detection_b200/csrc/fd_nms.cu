@@ -350,14 +350,13 @@ __device__ __forceinline__ int block_sum(int v, int *red) {
     return t;
 }
 
+// The peel itself: every CTA of a cooperative grid calls it (nms_peel_kernel, and nms_big_kernel when the spatial path does not apply).
 template <int MODE>
-__global__ void __launch_bounds__(NT, 1) nms_peel_kernel(PeelArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void nms_peel_body(const PeelArgs &a, unsigned char *smem_raw) {
     PeelSmem &sm = *reinterpret_cast<PeelSmem *>(smem_raw);
     cg::grid_group grid = cg::this_grid();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x;
-    if (__ldcg(&a.status[3]) != 0) return;  // uniform over the grid: the spatial path owns this problem
     const bool fast = a.iou.fast && (__ldcg(&a.status[2]) == 0);
     float4 *kbox = reinterpret_cast<float4 *>(sm.mask);
     float *karea = reinterpret_cast<float *>(kbox + HEAD);
@@ -464,6 +463,13 @@ __global__ void __launch_bounds__(NT, 1) nms_peel_kernel(PeelArgs a) {
     if (blockIdx.x == 0 && tid == 0) a.state[1] = nk_total;
 }
 
+template <int MODE>
+__global__ void __launch_bounds__(NT, 1) nms_peel_kernel(PeelArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (__ldcg(&a.status[3]) != 0) return;  // uniform over the grid: the spatial path owns this problem
+    nms_peel_body<MODE>(a, smem_raw);
+}
+
 // ============================================================================================================
 // Spatial big path: exact greedy NMS with work proportional to the number of OVERLAPPING pairs.
 //
@@ -541,15 +547,15 @@ __global__ void grid_stats_kernel(const float4 *__restrict__ sbox, int N, unsign
     }
 }
 
-__global__ void grid_setup_kernel(const unsigned *gs, int N, IouParams P, GridCfg *cfg, int *st) {
+__device__ __forceinline__ GridCfg grid_setup(const unsigned *gs, int N, const IouParams &P, int not_fast) {
     GridCfg c;
-    c.minx = ord2f(gs[0]);
-    c.miny = ord2f(gs[1]);
-    const float maxx = ord2f(gs[2]), maxy = ord2f(gs[3]), maxd = ord2f(gs[4]);
+    c.minx = ord2f(__ldcg(gs + 0));
+    c.miny = ord2f(__ldcg(gs + 1));
+    const float maxx = ord2f(__ldcg(gs + 2)), maxy = ord2f(__ldcg(gs + 3)), maxd = ord2f(__ldcg(gs + 4));
     c.use = 0;
     c.gx = c.gy = 1;
     c.cs = 1.0f;
-    if (P.fast && st[2] == 0 && isfinite(maxd) && isfinite(maxx) && isfinite(maxy) && isfinite(c.minx) && isfinite(c.miny)) {
+    if (P.fast && not_fast == 0 && isfinite(maxd) && isfinite(maxx) && isfinite(maxy) && isfinite(c.minx) && isfinite(c.miny)) {
         const float t = fminf(fmaxf(P.thr, 0.0f), 1.0f);
         // centre-distance bound per axis, with a 1% + 0.05 px margin for the separately rounded f32 operations
         double cs = (double)maxd * (1.0 - (double)t) * 1.01 + 0.05;
@@ -567,6 +573,10 @@ __global__ void grid_setup_kernel(const unsigned *gs, int N, IouParams P, GridCf
             cs *= 1.5;
         }
     }
+    return c;
+}
+__global__ void grid_setup_kernel(const unsigned *gs, int N, IouParams P, GridCfg *cfg, int *st) {
+    const GridCfg c = grid_setup(gs, N, P, st[2]);
     *cfg = c;
     st[3] = c.use;
 }
@@ -645,14 +655,10 @@ __device__ __forceinline__ void for_each_predecessor(int k, const u64 *__restric
     }
 }
 
-__global__ void __launch_bounds__(256) adjacency_kernel(const u64 *__restrict__ keys, int N, const GridCfg *cfg,
-                                                        const int *__restrict__ cell_start, const int *__restrict__ cell_end,
-                                                        const float4 *__restrict__ cbox, const float *__restrict__ carea, IouParams P,
-                                                        int *__restrict__ adj, int *__restrict__ adj_cnt) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= N) return;
-    const GridCfg c = *cfg;
-    if (!c.use) return;
+// predecessor list of cell-ordered box k
+__device__ __forceinline__ void adjacency_of(int k, const u64 *__restrict__ keys, const GridCfg &c, const int *__restrict__ cell_start,
+                                             const int *__restrict__ cell_end, const float4 *__restrict__ cbox, const float *__restrict__ carea,
+                                             const IouParams &P, int *__restrict__ adj, int *__restrict__ adj_cnt) {
     const int rank = (int)(unsigned)keys[k];
     int cnt = 0;
     int *mine = adj + (size_t)rank * ADJ_CAP;
@@ -662,6 +668,17 @@ __global__ void __launch_bounds__(256) adjacency_kernel(const u64 *__restrict__ 
         return true;
     });
     adj_cnt[rank] = cnt <= ADJ_CAP ? cnt : -1;  // -1: too many predecessors to list, rescan the neighbourhood instead
+}
+
+__global__ void __launch_bounds__(256) adjacency_kernel(const u64 *__restrict__ keys, int N, const GridCfg *cfg,
+                                                        const int *__restrict__ cell_start, const int *__restrict__ cell_end,
+                                                        const float4 *__restrict__ cbox, const float *__restrict__ carea, IouParams P,
+                                                        int *__restrict__ adj, int *__restrict__ adj_cnt) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    const GridCfg c = *cfg;
+    if (!c.use) return;
+    adjacency_of(k, keys, c, cell_start, cell_end, cbox, carea, P, adj, adj_cnt);
 }
 
 // L2 (cache-global) byte load the compiler may neither cache nor drop: other CTAs update the states concurrently
@@ -695,6 +712,7 @@ struct RoundsArgs {
     const u64 *final_keys;  //             instead of keep_ranks + map_keep_kernel
     int *final_num;
     long long *dbg;         // FD_NMS_DBG: globaltimer stamps of block 0 (slots 5..7)
+    int adj_smem;           // list entries per box cached in shared memory across sweeps (<= ADJ_SMEM; sadj holds adj_smem x NT ints)
 };
 
 __device__ __forceinline__ void mid_stamp(long long *dbg, int slot) {
@@ -750,7 +768,7 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
         cnt0 = __ldcg(&a.adj_cnt[gtid]);   // (ld.cg throughout: in the mid path the lists were written earlier in this same kernel)
         if (cnt0 > ADJ_CAP) cnt0 = -1;                 // (mid path: the counter kept running past the list's capacity)
         const int4 *mine4 = reinterpret_cast<const int4 *>(a.adj + (size_t)gtid * ADJ_CAP);
-        for (int e = 0; e < min(cnt0, ADJ_SMEM); e += 4) {
+        for (int e = 0; e < min(cnt0, a.adj_smem); e += 4) {
             const int4 p = __ldcg(mine4 + (e >> 2));
             sadj[(e + 0) * NT + tid] = p.x;
             sadj[(e + 1) * NT + tid] = p.y;
@@ -767,7 +785,7 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
                 int d;
                 if (cnt0 >= 0) {
                     const int *mine = a.adj + (size_t)gtid * ADJ_CAP;
-                    d = try_decide_listed(cnt0, [&](int e) { return e < ADJ_SMEM ? sadj[e * NT + tid] : __ldcg(mine + e); }, a.state);
+                    d = try_decide_listed(cnt0, [&](int e) { return e < a.adj_smem ? sadj[e * NT + tid] : __ldcg(mine + e); }, a.state);
                 }
                 else {
                     bool any_kept = false, all_sup = true;
@@ -1005,6 +1023,402 @@ __global__ void __launch_bounds__(NT, 1) nms_mid_kernel(MidArgs m) {
     nms_rounds_body(m.ra, c, dyn, red);
 }
 
+// ---- big path in one launch -------------------------------------------------------------------------------------------
+// The spatial path used to be ~25 stream operations (two radix sorts of one kernel per 8-bit pass, nine small kernels, six
+// memsets): at 100 000 boxes two thirds of its 332 us were launch gaps and latency-bound 25-CTA radix passes.  nms_big_kernel
+// runs the same algorithm as ONE cooperative kernel, phases separated by grid-wide barriers:
+//   0  keys (score desc | index), NaN flag, the OR / NAND of all score keys (which key bits differ at all), first digit histogram;
+//   1  LSD radix sort, 9-bit digits over the differing bits only (scores in [0.02, 1) differ in 26 bits: 3 passes), every SM busy:
+//      tiles of 1024 keys, per-(digit, tile) counts -> row scans -> stable scatter that also counts the next pass's digits;
+//   2  boxes in rank order + grid statistics;  3  grid geometry (every CTA, identically), cell keys;  4  cell sort (same code);
+//   5  cell bounds + cell-ordered boxes;  6  predecessor lists;  7  decision sweeps + ordered output (nms_rounds_body).
+// When the grid does not apply (irregular boxes, degenerate thresholds, too crowded) the same launch runs the peel instead.
+constexpr int CS_BITS = 9;
+constexpr int CS_D = 1 << CS_BITS;
+constexpr size_t CS_SMEM = sizeof(int) * (size_t)(2 + NWARPS) * CS_D;
+
+struct BigArgs {
+    const float *dets;
+    int n, stride, presorted, mode;
+    u64 *ka, *kb;           // score keys (ping-pong)
+    u64 *cka, *ckb;         // cell keys (ping-pong)
+    int *hist;              // [2][CS_D][ntiles] digit counts per tile, then [CS_D] digit totals
+    float4 *sbox;           // boxes in rank order
+    int *st;                // status block (zero at launch): nms_big_impl's slots, [22] NAND / [23] OR of the score keys
+    int *cell_start, *cell_end;
+    float4 *cbox;
+    float *carea;
+    int *pos_of_rank;
+    RoundsArgs ra;          // keys / final_keys are set on the device (they depend on the number of passes)
+    PeelArgs pa;
+    int *keep_dev, *num_keep_dev;
+    int lists_map;          // experiment switch: how phase 6 hands boxes to threads
+    long long *dbg;         // FD_NMS_DBG: globaltimer stamps of block 0
+};
+
+__device__ __forceinline__ void big_stamp(long long *dbg, int slot) {
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        dbg[slot] = t;
+    }
+}
+
+// digit counts of the tiles this CTA owns, written (not added) to hist[d * ntiles + t]; key(e) yields element e's key
+template <class KeyFn>
+__device__ __forceinline__ void cs_tile_hist(KeyFn key, int n, int shift, int *__restrict__ hist, int ntiles, int *sh) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        __syncthreads();
+        for (int d = tid; d < CS_D; d += NT) sh[d] = 0;
+        __syncthreads();
+        const int e = t * NT + tid;
+        const int d = e < n ? (int)((key(e) >> shift) & (u64)(CS_D - 1)) : CS_D;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (d < CS_D && lane == __ffs(peers) - 1) atomicAdd(&sh[d], __popc(peers));
+        __syncthreads();
+        for (int dd = tid; dd < CS_D; dd += NT) hist[(size_t)dd * ntiles + t] = sh[dd];
+    }
+}
+
+// exclusive scan of every digit's counts along the tiles (one warp per digit row), digit totals to tot[]; zeroes `zero` (the
+// histogram the scatter that follows accumulates into)
+__device__ __forceinline__ void cs_row_scan(int *__restrict__ hist, int *__restrict__ tot, int ntiles, int *__restrict__ zero) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gw = blockIdx.x * NWARPS + warp, nw = gridDim.x * NWARPS;
+    for (int d = gw; d < CS_D; d += nw) {
+        int *row = hist + (size_t)d * ntiles;
+        int carry = 0;
+        for (int base = 0; base < ntiles; base += 128) {   // four chunks' loads in flight together
+            int v4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = base + u * 32 + lane;
+                v4[u] = i < ntiles ? __ldcg(row + i) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = base + u * 32 + lane;
+                int incl = v4[u];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += nb;
+                }
+                if (i < ntiles) row[i] = carry + incl - v4[u];
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
+        if (lane == 0) tot[d] = carry;
+    }
+    if (zero) {
+        const size_t total = (size_t)CS_D * ntiles;
+        for (size_t i = (size_t)blockIdx.x * NT + tid; i < total; i += (size_t)gridDim.x * NT) zero[i] = 0;
+    }
+}
+
+// stable scatter of one pass: position = digit base + tile base + (warp, lane) order inside the tile
+__device__ __forceinline__ void cs_scatter(const u64 *__restrict__ in, u64 *__restrict__ out, int n, int shift, const int *__restrict__ hist_cur,
+                                           const int *__restrict__ tot, int *__restrict__ hist_next, int next_shift, int ntiles, int *sh, int *red) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int *dbase = sh, *tbase = sh + CS_D, *wcount = sh + 2 * CS_D;
+    __syncthreads();
+    {
+        const int v = tid < CS_D ? __ldcg(tot + tid) : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        if (lane == 31) red[warp] = incl;
+        __syncthreads();
+        int wb = 0;
+        for (int w = 0; w < warp; ++w) wb += red[w];
+        if (tid < CS_D) dbase[tid] = wb + incl - v;
+    }
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        __syncthreads();
+        for (int i = tid; i < NWARPS * CS_D; i += NT) wcount[i] = 0;
+        if (tid < CS_D) tbase[tid] = __ldcg(hist_cur + (size_t)tid * ntiles + t);
+        __syncthreads();
+        const int e = t * NT + tid;
+        const bool valid = e < n;
+        const u64 key = valid ? __ldcg(in + e) : 0ull;
+        const int d = valid ? (int)((key >> shift) & (u64)(CS_D - 1)) : CS_D;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        if (valid && lane == __ffs(peers) - 1) wcount[warp * CS_D + d] = __popc(peers);
+        __syncthreads();
+        for (int dd = tid; dd < CS_D; dd += NT) {
+            int run = 0;
+#pragma unroll 8
+            for (int w = 0; w < NWARPS; ++w) {
+                const int c = wcount[w * CS_D + dd];
+                wcount[w * CS_D + dd] = run;
+                run += c;
+            }
+        }
+        __syncthreads();
+        int slot = -1;
+        if (valid) {
+            const int pos = dbase[d] + tbase[d] + wcount[warp * CS_D + d] + rank;
+            out[pos] = key;
+            if (hist_next) slot = (int)((key >> next_shift) & (u64)(CS_D - 1)) * ntiles + pos / NT;
+        }
+        if (hist_next) {   // warp-aggregated: neighbouring keys often share the next digit and the destination tile
+            const unsigned p2 = __match_any_sync(0xffffffffu, slot);
+            if (slot >= 0 && lane == __ffs(p2) - 1) atomicAdd(&hist_next[slot], __popc(p2));
+        }
+    }
+}
+
+// LSD passes over key bits [lo_bit, lo_bit + nbits); hist buffer 0 holds the first pass's counts.  Returns the array that ends
+// up sorted (uniform over the grid).  Every CTA must call it.
+__device__ __forceinline__ u64 *cs_sort(u64 *a, u64 *b, int n, int lo_bit, int nbits, int *hist, int ntiles, int *sh, int *red) {
+    cg::grid_group grid = cg::this_grid();
+    const size_t hsz = (size_t)CS_D * ntiles;
+    int *tot = hist + 2 * hsz;
+    const int npass = (nbits + CS_BITS - 1) / CS_BITS;
+    u64 *in = a, *out = b;
+    for (int p = 0; p < npass; ++p) {
+        int *hcur = hist + (size_t)(p & 1) * hsz, *hnext = hist + (size_t)((p + 1) & 1) * hsz;
+        const bool more = p + 1 < npass;
+        cs_row_scan(hcur, tot, ntiles, more ? hnext : nullptr);
+        __threadfence();
+        grid.sync();
+        cs_scatter(in, out, n, lo_bit + CS_BITS * p, hcur, tot, more ? hnext : nullptr, lo_bit + CS_BITS * (p + 1), ntiles, sh, red);
+        __threadfence();
+        grid.sync();
+        u64 *tmp = in;
+        in = out;
+        out = tmp;
+    }
+    return in;
+}
+
+__global__ void __launch_bounds__(NT, 1) nms_big_kernel(BigArgs m) {
+    extern __shared__ __align__(16) int dyn[];
+    __shared__ int red[32];
+    __shared__ GridCfg scfg;
+    cg::grid_group grid = cg::this_grid();
+    const int tid = threadIdx.x, lane = tid & 31, G = gridDim.x, gtid = blockIdx.x * NT + tid, gstride = G * NT;
+    const int n = m.n, ntiles = (n + NT - 1) / NT;
+    unsigned *gs = reinterpret_cast<unsigned *>(m.st + 8);
+    big_stamp(m.dbg, 0);
+    // ---- 0. keys, flags, first digit histogram; arrays that must start at zero ----
+    {
+        unsigned acc_or = 0, acc_nand = 0;
+        bool nan_seen = false;
+        if (m.presorted) {
+            for (int i = gtid; i < n; i += gstride) m.ka[i] = (u64)(unsigned)i;
+        } else {
+            for (int t = blockIdx.x; t < ntiles; t += G) {
+                __syncthreads();
+                for (int d = tid; d < CS_D; d += NT) dyn[d] = 0;
+                __syncthreads();
+                const int e = t * NT + tid;
+                int d = CS_D;
+                if (e < n) {
+                    const float sc = __ldg(m.dets + (size_t)e * m.stride + 4);
+                    nan_seen |= (sc != sc);
+                    const unsigned k32 = desc_key(sc);
+                    m.ka[e] = ((u64)k32 << 32) | (unsigned)e;
+                    acc_or |= k32;
+                    acc_nand |= ~k32;
+                    d = (int)(k32 & (unsigned)(CS_D - 1));
+                }
+                const unsigned peers = __match_any_sync(0xffffffffu, d);
+                if (d < CS_D && lane == __ffs(peers) - 1) atomicAdd(&dyn[d], __popc(peers));
+                __syncthreads();
+                for (int dd = tid; dd < CS_D; dd += NT) m.hist[(size_t)dd * ntiles + t] = dyn[dd];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                acc_or |= __shfl_xor_sync(0xffffffffu, acc_or, o);
+                acc_nand |= __shfl_xor_sync(0xffffffffu, acc_nand, o);
+            }
+            __syncthreads();
+            unsigned *ured = reinterpret_cast<unsigned *>(dyn);   // one pair of atomics per CTA, not per warp
+            if (lane == 0) { ured[tid >> 5] = acc_or; ured[32 + (tid >> 5)] = acc_nand; }
+            __syncthreads();
+            if (tid < 32) {
+                acc_or = ured[tid];
+                acc_nand = ured[32 + tid];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    acc_or |= __shfl_xor_sync(0xffffffffu, acc_or, o);
+                    acc_nand |= __shfl_xor_sync(0xffffffffu, acc_nand, o);
+                }
+                if (tid == 0 && (acc_or | acc_nand)) {
+                    atomicOr(reinterpret_cast<unsigned *>(m.st) + 22, acc_nand);
+                    atomicOr(reinterpret_cast<unsigned *>(m.st) + 23, acc_or);
+                }
+            }
+            if (__syncthreads_or(nan_seen) && tid == 0) atomicExch(&m.st[0], 1);
+        }
+        unsigned *state4 = reinterpret_cast<unsigned *>(m.ra.state);
+        for (int i = gtid; i < (n + 3) / 4; i += gstride) state4[i] = 0u;
+        if (gtid < 2) gs[gtid] = 0xFFFFFFFFu;   // min cx / min cy (ordered-uint encoding); the maxima start at the memset's zero
+    }
+    __threadfence();
+    grid.sync();
+    big_stamp(m.dbg, 1);
+    // ---- 1. sort by score key (bits above the highest differing one are the same for every key) ----
+    u64 *sorted = m.ka;
+    if (!m.presorted) {
+        const unsigned diff = (~__ldcg(reinterpret_cast<unsigned *>(m.st) + 22)) ^ __ldcg(reinterpret_cast<unsigned *>(m.st) + 23);
+        const int nbits = diff ? 32 - __clz(diff) : 0;
+        sorted = cs_sort(m.ka, m.kb, n, 32, nbits, m.hist, ntiles, dyn, red);
+    }
+    big_stamp(m.dbg, 2);
+    // ---- 2. boxes in rank order, regularity flag, grid statistics ----
+    {
+        unsigned mincx = 0xFFFFFFFFu, mincy = 0xFFFFFFFFu, maxcx = 0, maxcy = 0, maxd = 0;
+        bool ok = true;
+        for (int r = gtid; r < n; r += gstride) {
+            const int idx = (int)(unsigned)__ldcg(sorted + r);
+            const float *p = m.dets + (size_t)idx * m.stride;
+            const float4 b = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+            m.sbox[r] = b;
+            ok &= box_is_fast_ok(b);
+            const unsigned cx = f2ord(box_cx(b)), cy = f2ord(box_cy(b));
+            mincx = min(mincx, cx); maxcx = max(maxcx, cx);
+            mincy = min(mincy, cy); maxcy = max(maxcy, cy);
+            const float w = __fadd_rn(__fsub_rn(b.z, b.x), 1.0f), h = __fadd_rn(__fsub_rn(b.w, b.y), 1.0f);
+            maxd = max(maxd, f2ord(fmaxf(fabsf(w), fabsf(h))));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mincx = min(mincx, __shfl_xor_sync(0xffffffffu, mincx, o));
+            mincy = min(mincy, __shfl_xor_sync(0xffffffffu, mincy, o));
+            maxcx = max(maxcx, __shfl_xor_sync(0xffffffffu, maxcx, o));
+            maxcy = max(maxcy, __shfl_xor_sync(0xffffffffu, maxcy, o));
+            maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
+        }
+        unsigned *ured = reinterpret_cast<unsigned *>(dyn);   // one set of atomics per CTA
+        __syncthreads();
+        if (lane == 0) {
+            const int w = tid >> 5;
+            ured[w] = mincx; ured[32 + w] = mincy; ured[64 + w] = maxcx; ured[96 + w] = maxcy; ured[128 + w] = maxd;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            mincx = ured[tid]; mincy = ured[32 + tid]; maxcx = ured[64 + tid]; maxcy = ured[96 + tid]; maxd = ured[128 + tid];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mincx = min(mincx, __shfl_xor_sync(0xffffffffu, mincx, o));
+                mincy = min(mincy, __shfl_xor_sync(0xffffffffu, mincy, o));
+                maxcx = max(maxcx, __shfl_xor_sync(0xffffffffu, maxcx, o));
+                maxcy = max(maxcy, __shfl_xor_sync(0xffffffffu, maxcy, o));
+                maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
+            }
+            if (tid == 0 && mincx != 0xFFFFFFFFu) {   // (a CTA without boxes has nothing to report)
+                atomicMin(&gs[0], mincx);
+                atomicMin(&gs[1], mincy);
+                atomicMax(&gs[2], maxcx);
+                atomicMax(&gs[3], maxcy);
+                atomicMax(&gs[4], maxd);
+            }
+        }
+        if (__syncthreads_or(!ok) && tid == 0) atomicExch(&m.st[2], 1);
+    }
+    __threadfence();
+    grid.sync();
+    big_stamp(m.dbg, 3);
+    // ---- 3. grid geometry: every CTA derives the same one ----
+    if (tid == 0) {
+        scfg = grid_setup(gs, n, m.ra.iou, __ldcg(&m.st[2]));
+        if (blockIdx.x == 0) {
+            *const_cast<GridCfg *>(m.ra.cfg) = scfg;
+            m.st[3] = scfg.use;
+        }
+    }
+    __syncthreads();
+    const GridCfg c = scfg;
+    if (!c.use) {   // uniform over the grid: the peel owns this problem; its kept ranks become source indices afterwards
+        if (m.mode == 0) nms_peel_body<0>(m.pa, reinterpret_cast<unsigned char *>(dyn));
+        else nms_peel_body<1>(m.pa, reinterpret_cast<unsigned char *>(dyn));
+        __threadfence();
+        grid.sync();
+        const int total = __ldcg(&m.pa.state[1]);
+        for (int k = gtid; k < total; k += gstride) m.keep_dev[k] = (int)(unsigned)__ldcg(sorted + __ldcg(&m.pa.keep_ranks[k]));
+        if (gtid == 0) {
+            m.num_keep_dev[0] = total;
+            m.num_keep_dev[1] = __ldcg(&m.st[0]);
+        }
+        return;
+    }
+    const int ncells = c.gx * c.gy;
+    const int cbits = ncells > 1 ? 32 - __clz(ncells - 1) : 0;
+    {
+        for (int r = gtid; r < n; r += gstride) {
+            const float4 b = m.sbox[r];
+            const int ix = cell_coord(box_cx(b), c.minx, c.cs, c.gx), iy = cell_coord(box_cy(b), c.miny, c.cs, c.gy);
+            m.cka[r] = ((u64)(unsigned)(iy * c.gx + ix) << 32) | (unsigned)r;
+        }
+        for (int i = gtid; i < ncells; i += gstride) {
+            m.cell_start[i] = 0;
+            m.cell_end[i] = 0;
+        }
+        __syncthreads();   // this CTA's tiles of cka were written by this CTA (same grid-stride ownership): block-level visibility
+        if (cbits > 0) cs_tile_hist([&](int e) { return __ldcg(m.cka + e); }, n, 32, m.hist, ntiles, dyn);   // (ld.cg: cka is rewritten by the passes, no stale L1 line later)
+    }
+    __threadfence();
+    grid.sync();
+    big_stamp(m.dbg, 4);
+    // ---- 4. stable sort by cell: members of a cell stay in rank order ----
+    const u64 *csorted = cs_sort(m.cka, m.ckb, n, 32, cbits, m.hist, ntiles, dyn, red);
+    big_stamp(m.dbg, 5);
+    // ---- 5. cell bounds, cell-ordered boxes ----
+    for (int k = gtid; k < n; k += gstride) {
+        const u64 key = __ldcg(csorted + k);
+        const int cell = (int)(key >> 32), rank = (int)(unsigned)key;
+        if (k == 0 || (int)(__ldcg(csorted + k - 1) >> 32) != cell) m.cell_start[cell] = k;
+        if (k == n - 1 || (int)(__ldcg(csorted + k + 1) >> 32) != cell) m.cell_end[cell] = k + 1;
+        const float4 b = m.sbox[rank];
+        m.cbox[k] = b;
+        m.carea[k] = box_area(b);
+        m.pos_of_rank[rank] = k;
+    }
+    __threadfence();
+    grid.sync();
+    big_stamp(m.dbg, 6);
+    // ---- 6. predecessor lists: contiguous cell-ordered chunks, every SM takes part ----
+    if (m.lists_map == 1) {          // tiles of 256 boxes dealt round-robin to the CTAs (what a 256-thread launch gives)
+        const int nt256 = (n + 255) / 256;
+        for (int t = blockIdx.x + G * (tid >> 8); t < nt256; t += G * (NT >> 8)) {
+            const int k = t * 256 + (tid & 255);
+            if (k < n) adjacency_of(k, csorted, c, m.cell_start, m.cell_end, m.cbox, m.carea, m.ra.iou, const_cast<int *>(m.ra.adj), const_cast<int *>(m.ra.adj_cnt));
+        }
+    } else if (m.lists_map == 2) {   // warps take 32 boxes at a time from a ticket
+        int *ticket = m.st + 24;
+        for (;;) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(ticket, 32);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= n) break;
+            const int k = base + lane;
+            if (k < n) adjacency_of(k, csorted, c, m.cell_start, m.cell_end, m.cbox, m.carea, m.ra.iou, const_cast<int *>(m.ra.adj), const_cast<int *>(m.ra.adj_cnt));
+        }
+    } else {
+        const int per = (n + G - 1) / G;
+        const int k1 = min(n, (int)(blockIdx.x + 1) * per);
+        for (int k = blockIdx.x * per + tid; k < k1; k += NT)
+            adjacency_of(k, csorted, c, m.cell_start, m.cell_end, m.cbox, m.carea, m.ra.iou, const_cast<int *>(m.ra.adj), const_cast<int *>(m.ra.adj_cnt));
+    }
+    __threadfence();
+    grid.sync();
+    big_stamp(m.dbg, 7);
+    // ---- 7. decision sweeps + ordered output as source indices ----
+    RoundsArgs ra = m.ra;
+    ra.keys = csorted;
+    ra.final_keys = sorted;
+    ra.dbg = m.dbg ? m.dbg + 4 : nullptr;   // its stamps 5 / 6 land in slots 9 / 10
+    nms_rounds_body(ra, c, dyn, red);
+    big_stamp(m.dbg, 8);
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------
 // Decision boundary of the exact division-free test (see iou_suppresses_exact).
 IouParams make_iou_params(float thr, int mode) {
@@ -1193,6 +1607,7 @@ static int nms_big_impl(fd_ctx *ctx, const u64 *keys_in, const int *key_bytes, i
         ra.brute = 0;
         ra.mode = mode;
         ra.status = st;
+        ra.adj_smem = ADJ_SMEM;
         void *rargs[] = {&ra};
         int per_sm_r = 0;
         const size_t smem_r = sizeof(int) * (size_t)ADJ_SMEM * NT;
@@ -1270,6 +1685,7 @@ static int nms_mid_impl(fd_ctx *ctx, const float *boxes, int K, int stride, cons
     ra.brute = 1;
     ra.mode = mode;
     ra.status = st;
+    ra.adj_smem = ADJ_SMEM;
     ra.final_keep = keep_dev;
     ra.final_keys = m.sorted;
     ra.final_num = num_keep_dev;
@@ -1304,10 +1720,123 @@ static int nms_mid_impl(fd_ctx *ctx, const float *boxes, int K, int stride, cons
     return FD_OK;
 }
 
+// The big path as ONE cooperative launch (nms_big_kernel); num_keep_dev receives {count, NaN flag}.
+static int nms_big_one_launch(fd_ctx *ctx, const float *boxes, int K, int stride, float thr, int mode, bool presorted, int32_t *keep_dev,
+                              int32_t *num_keep_dev) {
+    const int ntiles = (K + NT - 1) / NT;
+    FD_TRY(ctx->nms_ws[0].reserve(sizeof(u64) * (size_t)K));
+    FD_TRY(ctx->nms_ws[1].reserve(sizeof(u64) * (size_t)K));
+    FD_TRY(ctx->nms_ws[2].reserve(sizeof(int) * ((size_t)2 * CS_D * ntiles + CS_D)));
+    FD_TRY(ctx->nms_ws[3].reserve(sizeof(float4) * (size_t)K));
+    FD_TRY(ctx->nms_ws[4].reserve(sizeof(int) * (size_t)K * 3));
+    FD_TRY(ctx->nms_ws[5].reserve(sizeof(float4) * HEAD + sizeof(int) * (size_t)ntiles * 33 + 64));
+    FD_TRY(ctx->nms_ws[6].reserve(sizeof(int) * 32));
+    FD_TRY(ctx->nms_ws_sp[0].reserve(sizeof(u64) * (size_t)K * 2));
+    FD_TRY(ctx->nms_ws_sp[1].reserve(sizeof(int) * (size_t)(GRID_MAX_CELLS + 1) * 2));
+    FD_TRY(ctx->nms_ws_sp[2].reserve((sizeof(float4) + sizeof(float) + sizeof(int) * 2) * (size_t)K + (size_t)K + 16));
+    FD_TRY(ctx->nms_ws_sp[3].reserve(sizeof(int) * (size_t)K * ADJ_CAP));
+    int *st = ctx->nms_ws[6].as<int>();
+    FD_CUDA(cudaMemsetAsync(st, 0, sizeof(int) * 32, ctx->stream));
+    const IouParams iou = make_iou_params(thr, mode);
+    BigArgs m{};
+    m.dets = boxes;
+    m.n = K;
+    m.stride = stride;
+    m.presorted = presorted ? 1 : 0;
+    m.mode = mode;
+    m.ka = ctx->nms_ws[0].as<u64>();
+    m.kb = ctx->nms_ws[1].as<u64>();
+    m.cka = ctx->nms_ws_sp[0].as<u64>();
+    m.ckb = m.cka + K;
+    m.hist = ctx->nms_ws[2].as<int>();
+    m.sbox = ctx->nms_ws[3].as<float4>();
+    m.st = st;
+    m.cell_start = ctx->nms_ws_sp[1].as<int>();
+    m.cell_end = m.cell_start + (GRID_MAX_CELLS + 1);
+    m.cbox = ctx->nms_ws_sp[2].as<float4>();
+    m.carea = reinterpret_cast<float *>(m.cbox + K);
+    m.pos_of_rank = reinterpret_cast<int *>(m.carea + K);
+    int *adj_cnt = m.pos_of_rank + K;
+    float4 *ks = ctx->nms_ws[5].as<float4>();
+    int *tile_counts = reinterpret_cast<int *>(ks + HEAD);
+    unsigned *ballots = reinterpret_cast<unsigned *>(tile_counts + ntiles);
+    int *stream_a = ctx->nms_ws[4].as<int>(), *stream_b = stream_a + K, *keep_ranks = stream_b + K;
+    RoundsArgs &ra = m.ra;
+    ra.N = K;
+    ra.cfg = reinterpret_cast<GridCfg *>(st + 16);
+    ra.cell_start = m.cell_start;
+    ra.cell_end = m.cell_end;
+    ra.cbox = m.cbox;
+    ra.carea = m.carea;
+    ra.pos_of_rank = m.pos_of_rank;
+    ra.adj = ctx->nms_ws_sp[3].as<int>();
+    ra.adj_cnt = adj_cnt;
+    ra.state = reinterpret_cast<unsigned char *>(adj_cnt + K);
+    ra.counters = st + 13;
+    ra.tile_counts = tile_counts;
+    ra.ballots = ballots;
+    ra.keep_ranks = nullptr;
+    ra.out_state = st + 3;
+    ra.iou = iou;
+    ra.sbox = m.sbox;
+    ra.brute = 0;
+    ra.mode = mode;
+    ra.status = st;
+    static const int adj_smem = getenv("FD_NMS_ADJ_SMEM") ? std::max(4, std::min(ADJ_SMEM, atoi(getenv("FD_NMS_ADJ_SMEM")) & ~3)) : ADJ_SMEM;
+    ra.adj_smem = adj_smem;
+    static const int lists_map = getenv("FD_NMS_LISTS_MAP") ? atoi(getenv("FD_NMS_LISTS_MAP")) : 0;
+    m.lists_map = lists_map;
+    ra.final_keep = keep_dev;
+    ra.final_num = num_keep_dev;
+    PeelArgs &pa = m.pa;
+    pa.sbox = m.sbox;
+    pa.N = K;
+    pa.stream_a = stream_a;
+    pa.stream_b = stream_b;
+    pa.keep_ranks = keep_ranks;
+    pa.state = st + 3;
+    pa.ks = ks;
+    pa.tile_counts = tile_counts;
+    pa.ballots = ballots;
+    pa.status = st;
+    pa.iou = iou;
+    m.keep_dev = keep_dev;
+    m.num_keep_dev = num_keep_dev;
+    static int per_sm = 0;                                                 // one device type per process
+    const size_t smem = std::max(std::max(sizeof(int) * (size_t)adj_smem * NT, sizeof(PeelSmem)), CS_SMEM);
+    if (!per_sm) {
+        FD_CUDA(cudaFuncSetAttribute(nms_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nms_big_kernel, NT, smem));
+        if (per_sm < 1) return fail(FD_ERR_CUDA, "nms_big_kernel does not fit on an SM");
+    }
+    static const bool dbg_on = getenv("FD_NMS_DBG") != nullptr;             // phase timeline of block 0 on stderr
+    static long long *dbg_dev = nullptr;
+    if (dbg_on && !dbg_dev) FD_CUDA(cudaMalloc(&dbg_dev, sizeof(long long) * 16));
+    m.dbg = dbg_on ? dbg_dev : nullptr;
+    void *args[] = {&m};
+    FD_CUDA(cudaLaunchCooperativeKernel((const void *)nms_big_kernel, dim3(ctx->num_sms * per_sm), dim3(NT), args, smem, ctx->stream));
+    FD_LAUNCH_CHECK_NAMED(ctx, "nms_big_kernel");
+    if (dbg_on) {
+        long long h[16];
+        int sth[32];
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaMemcpy(sth, st, sizeof(sth), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[nms big dbg] K=%d grid=%d spatial=%d: keys %.1f  sort %.1f  boxes %.1f  cells %.1f  cell sort %.1f  bounds %.1f  lists %.1f  sweeps %.1f  output %.1f (epochs %d) us, total %.1f\n",
+                K, ctx->num_sms * per_sm, sth[3], (h[1] - h[0]) * 1e-3, (h[2] - h[1]) * 1e-3, (h[3] - h[2]) * 1e-3, (h[4] - h[3]) * 1e-3,
+                (h[5] - h[4]) * 1e-3, (h[6] - h[5]) * 1e-3, (h[7] - h[6]) * 1e-3, (h[9] - h[7]) * 1e-3, (h[8] - h[9]) * 1e-3, sth[6], (h[8] - h[0]) * 1e-3);
+    }
+    return FD_OK;
+}
+
 int nms_big_device(fd_ctx *ctx, const float *dets_dev, int K, int stride, float thr, int mode, bool presorted,
                    int32_t *keep_dev, int32_t *num_keep_dev) {
+    static const bool multi = getenv("FD_NMS_MULTI_KERNEL") != nullptr && getenv("FD_NMS_MULTI_KERNEL")[0] == '1';   // A/B: the round-1 launch sequence
+    if (!multi) return nms_big_one_launch(ctx, dets_dev, K, stride, thr, mode, presorted, keep_dev, num_keep_dev);
     static const int bytes[4] = {4, 5, 6, 7};  // score bytes only: the sort is stable, ties keep index order
-    return nms_big_impl(ctx, nullptr, bytes, 4, dets_dev, K, stride, thr, mode, presorted, false, keep_dev, num_keep_dev);
+    FD_TRY(nms_big_impl(ctx, nullptr, bytes, 4, dets_dev, K, stride, thr, mode, presorted, false, keep_dev, num_keep_dev));
+    FD_CUDA(cudaMemcpyAsync(num_keep_dev + 1, ctx->nms_ws[6].as<int>(), sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    return FD_OK;
 }
 
 // Statistics of the last big-path NMS: [0] spatial path used, [1] kept, [2] decision epochs, [3] grid w, [4] grid h,
@@ -1365,9 +1894,7 @@ int nms_device(fd_ctx *ctx, const float *dets_dev, int K, int stride, float thr,
         FD_CUDA(cudaMemcpyAsync(num_keep_dev + 1, status, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
         return FD_OK;
     }
-    FD_TRY(nms_big_device(ctx, dets_dev, K, stride, thr, mode, presorted, keep_dev, num_keep_dev));
-    FD_CUDA(cudaMemcpyAsync(num_keep_dev + 1, ctx->nms_ws[6].as<int>(), sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
-    return FD_OK;
+    return nms_big_device(ctx, dets_dev, K, stride, thr, mode, presorted, keep_dev, num_keep_dev);   // writes {count, NaN flag}
 }
 
 // argsort_descending on the device: order_dev (n), flag_dev (1 int: NaN flag)

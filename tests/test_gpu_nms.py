@@ -202,3 +202,44 @@ def test_single_cta_and_spatial_paths_behind_the_switches():
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, FD_NMS_CROSS="4096", FD_NMS_MID_CAP="0"), capture_output=True, text=True,
                          timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-1500:]
+
+
+def test_one_launch_big_path_behind_the_switch():
+    """FD_NMS_MID_CAP=0 sends every problem above 1 024 boxes through nms_big_kernel (the spatial path as one cooperative launch):
+    its sort (0-4 digit passes, several tiles per CTA), the peel fallback for irregular boxes / one-cell grids, the `_nms`
+    (presorted) contract, cpu_nms's comparison, the NaN flag — and the same keep lists as the multi-kernel launch sequence."""
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import numpy as np\n"
+            "from rs_face_detection_b200 import Context, FdError\n"
+            "from rs_face_detection_b200.utils import synth\n"
+            "from oracle import oracle as O\n"
+            "from test_gpu_nms import _random_dets\n"
+            "O.build(); c = Context(0)\n"
+            "for n in (1025, 5000, 13000, 40000):\n"
+            "    d = _random_dets(n, 5 + n, canvas=1500, side=(8, 90), score_levels=300)\n"
+            "    np.testing.assert_array_equal(c.nms(d, 0.4), O.nms(d, 0.4))\n"
+            "    np.testing.assert_array_equal(c.cpu_nms(d, 0.3), O.cpu_nms(d, 0.3))\n"
+            "d = synth.make_crowd_boxes(200000, seed=4, n_faces=10000)\n"          # more tiles than CTAs
+            "np.testing.assert_array_equal(c.nms(d, 0.4), O.nms(d, 0.4))\n"
+            "d = _random_dets(6000, 78, canvas=900); d[::13, 2] = d[::13, 0] - 1.0\n"   # zero-width boxes: not 'fast' -> peel
+            "for thr in (0.4, -1.0, 1.5):\n"
+            "    np.testing.assert_array_equal(c.nms(d, thr), O.nms(d, thr))\n"
+            "same = np.tile(np.array([[10, 10, 50, 50, 0.5]], np.float32), (3000, 1))\n"   # no differing key bit, one grid cell
+            "assert c.nms(same, 0.4).tolist() == [0]\n"
+            "n = 5000; x = np.arange(n, dtype=np.float32) * 6\n"
+            "chain = np.stack([x, np.zeros(n, np.float32), x + 10, np.full(n, 10, np.float32), np.linspace(0.99, 0.01, n, dtype=np.float32)], 1)\n"
+            "np.testing.assert_array_equal(c.nms(chain, 0.2), O.nms(chain, 0.2))\n"
+            "d = _random_dets(30000, 3, canvas=2000); order = O.argsort_descending(d[:, 4]); srt = np.ascontiguousarray(d[order])\n"
+            "np.testing.assert_array_equal(c.nms_sorted(srt, 0.4), O.nms_sorted(srt, 0.4))\n"
+            "d = _random_dets(9000, 2); d[5, 4] = np.nan\n"
+            "try:\n"
+            "    c.nms(d, 0.4); raise SystemExit('NaN score not reported')\n"
+            "except FdError:\n"
+            "    pass\n"
+            "d = _random_dets(9000, 2)\n"
+            "np.testing.assert_array_equal(c.nms(d, 0.4), O.nms(d, 0.4))\n"          # the flag of the failed call does not stick
+            "print('ok')\n" % (ROOT, os.path.join(ROOT, "tests")))
+    for extra in ({}, {"FD_NMS_MULTI_KERNEL": "1"}):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, FD_NMS_MID_CAP="0", **extra), capture_output=True, text=True,
+                             timeout=900)
+        assert out.returncode == 0 and "ok" in out.stdout, (extra, out.stderr[-1500:])
