@@ -484,6 +484,8 @@ __global__ void __launch_bounds__(NT, 1) nms_peel_kernel(PeelArgs a) {
 // ============================================================================================================
 constexpr int ADJ_CAP = 96;      // listed predecessors per box (global memory)
 constexpr int ADJ_SMEM = 32;     // of which the first are cached in shared memory across sweeps
+constexpr int ADJ_SEG = 64;      // one-launch path: a box's list is three segments of this capacity, one per neighbourhood row (three tasks)
+constexpr int ADJ_ROW3 = 3 * ADJ_SEG;   // ... so its row is 192 ints (the own-row segment of a box in a dense spot overflowed 32 and fell back to rescans)
 constexpr int GRID_MAX_CELLS = 65535;
 constexpr int GRID_MAX_DIM = 4096;
 
@@ -612,13 +614,13 @@ template <class F>
 __device__ __forceinline__ void for_each_predecessor(int k, const u64 *__restrict__ keys, const GridCfg &c,
                                                      const int *__restrict__ cell_start, const int *__restrict__ cell_end,
                                                      const float4 *__restrict__ cbox, const float *__restrict__ carea,
-                                                     const IouParams &P, F &&visit) {
+                                                     const IouParams &P, F &&visit, int dy0 = -1, int dy1 = 1) {
     const u64 key = keys[k];
     const int cell = (int)(key >> 32), rank = (int)(unsigned)key;
     const int iy = cell / c.gx, ix = cell - iy * c.gx;
     const float4 bi = cbox[k];
     const float ai = carea[k];
-    for (int dy = -1; dy <= 1; ++dy) {
+    for (int dy = dy0; dy <= dy1; ++dy) {
         const int y = iy + dy;
         if (y < 0 || y >= c.gy) continue;
         for (int dx = -1; dx <= 1; ++dx) {
@@ -667,7 +669,23 @@ __device__ __forceinline__ void adjacency_of(int k, const u64 *__restrict__ keys
         ++cnt;
         return true;
     });
-    adj_cnt[rank] = cnt <= ADJ_CAP ? cnt : -1;  // -1: too many predecessors to list, rescan the neighbourhood instead
+    adj_cnt[rank] = cnt;   // may exceed ADJ_CAP: the first ADJ_CAP are listed
+}
+
+// one neighbourhood row (dy = -1, 0, 1) of cell-ordered box k: segment dy + 1 of its list and of its counters (no atomics: three
+// tasks per box triple the parallelism of this latency-bound phase)
+__device__ __forceinline__ void adjacency_row(int k, int dy, const u64 *__restrict__ keys, const GridCfg &c, const int *__restrict__ cell_start,
+                                              const int *__restrict__ cell_end, const float4 *__restrict__ cbox, const float *__restrict__ carea,
+                                              const IouParams &P, int *__restrict__ adj, int *__restrict__ cnt3) {
+    const int rank = (int)(unsigned)keys[k];
+    int cnt = 0;
+    int *mine = adj + (size_t)rank * ADJ_ROW3 + (dy + 1) * ADJ_SEG;
+    for_each_predecessor(k, keys, c, cell_start, cell_end, cbox, carea, P, [&](int rj) {
+        if (cnt < ADJ_SEG) mine[cnt] = rj;
+        ++cnt;
+        return true;
+    }, dy, dy);
+    cnt3[rank * 3 + dy + 1] = cnt;   // may exceed ADJ_SEG: the first ADJ_SEG are listed
 }
 
 __global__ void __launch_bounds__(256) adjacency_kernel(const u64 *__restrict__ keys, int N, const GridCfg *cfg,
@@ -713,6 +731,8 @@ struct RoundsArgs {
     int *final_num;
     long long *dbg;         // FD_NMS_DBG: globaltimer stamps of block 0 (slots 5..7)
     int adj_smem;           // list entries per box cached in shared memory across sweeps (<= ADJ_SMEM; sadj holds adj_smem x NT ints)
+    int seg3;               // lists are three ADJ_SEG segments with adj_cnt[3 * box + segment] entries each (adjacency_row)
+    int adj_stride;         // ints per box in adj (ADJ_CAP, or ADJ_ROW3 with seg3)
 };
 
 __device__ __forceinline__ void mid_stamp(long long *dbg, int slot) {
@@ -755,7 +775,35 @@ __device__ __forceinline__ int try_decide_listed(int cnt, IdxFn idx, const unsig
     return any_kept ? 2 : (all_sup ? 1 : 0);
 }
 
-// sadj: [ADJ_SMEM][NT] ints of shared memory (head of the predecessor list of each thread's first box, kept across sweeps)
+// The same decision over a box's PENDING predecessors, compacted in place: a suppressed predecessor is final and leaves the list, so
+// every sweep polls only what is still undecided (the first visit polls the whole list, later ones a handful).  get(e) / put(e, v)
+// access the e-th pending entry.  Returns 0 undecided / 1 kept / 2 suppressed and updates `pend`.
+template <class GetFn, class PutFn>
+__device__ __forceinline__ int decide_pending(int &pend, GetFn get, PutFn put, const unsigned char *state) {
+    int w = 0;
+    for (int e = 0; e < pend; e += 8) {
+        int id[8];
+        unsigned sj[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) id[u] = (e + u < pend) ? get(e + u) : -1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sj[u] = id[u] >= 0 ? ld_state(state + id[u]) : 2u;   // loads in flight together
+        bool kept = false;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) kept |= (sj[u] == 1u);
+        if (kept) return 2;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (sj[u] == 0u) {   // w <= e + u: never overwrites an entry that has not been read
+                put(w, id[u]);
+                ++w;
+            }
+    }
+    pend = w;
+    return w == 0 ? 1 : 0;
+}
+
+// sadj: [adj_smem][NT] ints of shared memory (head of the pending-predecessor list of each thread's first box, kept across sweeps)
 __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridCfg &c, int *sadj, int *red) {
     const bool bfast = a.brute && a.iou.fast && __ldcg(&a.status[2]) == 0;
     cg::grid_group grid = cg::this_grid();
@@ -763,63 +811,123 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
     const int G = gridDim.x;
     const int gtid = blockIdx.x * NT + tid, gstride = G * NT;
     volatile unsigned char *state = a.state;
-    int cnt0 = 0;
-    if (gtid < a.N) {
-        cnt0 = __ldcg(&a.adj_cnt[gtid]);   // (ld.cg throughout: in the mid path the lists were written earlier in this same kernel)
-        if (cnt0 > ADJ_CAP) cnt0 = -1;                 // (mid path: the counter kept running past the list's capacity)
-        const int4 *mine4 = reinterpret_cast<const int4 *>(a.adj + (size_t)gtid * ADJ_CAP);
-        for (int e = 0; e < min(cnt0, a.adj_smem); e += 4) {
-            const int4 p = __ldcg(mine4 + (e >> 2));
-            sadj[(e + 0) * NT + tid] = p.x;
-            sadj[(e + 1) * NT + tid] = p.y;
-            sadj[(e + 2) * NT + tid] = p.z;
-            sadj[(e + 3) * NT + tid] = p.w;
+    // ---- prologue: every box's list becomes one compact run of PENDING predecessors (only the listed ones; `overflow` says
+    //      there are more) — the resident box of this thread keeps the head of its run in shared memory and the count in a
+    //      register, the others (N beyond the resident threads) keep both in global memory: adj_cnt[first counter] = count |
+    //      overflow << 30, or -1 once the box has fallen back to rescanning its neighbourhood.
+    const int cstep = a.seg3 ? 3 : 1;
+    int *const acnt = const_cast<int *>(a.adj_cnt);
+    int *const mine0 = const_cast<int *>(a.adj) + (size_t)min(gtid, max(a.N - 1, 0)) * a.adj_stride;   // this thread's resident box
+    auto get0 = [&](int e) { return e < a.adj_smem ? sadj[e * NT + tid] : __ldcg(mine0 + e); };
+    auto put0 = [&](int e, int v) {
+        if (e < a.adj_smem) sadj[e * NT + tid] = v;
+        else mine0[e] = v;
+    };
+    int pend = 0;
+    bool overflow = false, rescan = false;
+    for (int r = gtid; r < a.N; r += gstride) {
+        int *row = const_cast<int *>(a.adj) + (size_t)r * a.adj_stride;
+        const int4 *row4 = reinterpret_cast<const int4 *>(row);
+        const bool res = r == gtid;
+        int total = 0;
+        bool ov = false;
+        if (a.seg3) {   // gather the three row segments (typical segment: a few entries, so the three first loads overlap)
+            int cs[3];
+            int4 first[3];
+#pragma unroll
+            for (int sg = 0; sg < 3; ++sg) {
+                const int cr = __ldcg(&acnt[r * 3 + sg]);
+                ov |= cr > ADJ_SEG;
+                cs[sg] = min(cr, ADJ_SEG);
+                first[sg] = make_int4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int sg = 0; sg < 3; ++sg)
+                if (cs[sg] > 0) first[sg] = __ldcg(row4 + sg * (ADJ_SEG / 4));
+            int w = 0;
+            auto put = [&](int v) {   // w <= the position being read: the gather never overwrites what it has not read
+                if (res) put0(w, v);
+                else row[w] = v;
+                ++w;
+            };
+#pragma unroll
+            for (int sg = 0; sg < 3; ++sg) {
+                for (int i = 0; i < cs[sg]; i += 4) {
+                    const int4 q = i == 0 ? first[sg] : __ldcg(row4 + sg * (ADJ_SEG / 4) + (i >> 2));
+                    put(q.x);
+                    if (i + 1 < cs[sg]) put(q.y);
+                    if (i + 2 < cs[sg]) put(q.z);
+                    if (i + 3 < cs[sg]) put(q.w);
+                }
+            }
+            total = w;
+        } else {
+            const int cr = __ldcg(&acnt[r]);   // (ld.cg throughout: in the mid path the lists were written earlier in this same kernel)
+            ov = cr > ADJ_CAP;                  // (mid path: the counter kept running past the list's capacity)
+            total = min(cr, ADJ_CAP);
+            if (res)
+                for (int e = 0; e < min(total, a.adj_smem); e += 4) {
+                    const int4 q = __ldcg(row4 + (e >> 2));
+                    sadj[(e + 0) * NT + tid] = q.x;
+                    sadj[(e + 1) * NT + tid] = q.y;
+                    sadj[(e + 2) * NT + tid] = q.z;
+                    sadj[(e + 3) * NT + tid] = q.w;
+                }
         }
+        if (res) { pend = total; overflow = ov; }
+        else acnt[r * cstep] = total | (ov ? (1 << 30) : 0);
     }
+    // A box whose listed predecessors are all suppressed but which has more than the list holds rescans its neighbourhood from
+    // then on (exact, slow, rare: by then one of so many predecessors has almost always been kept).
+    auto decide_rescan = [&](int r) {
+        bool any_kept = false, all_sup = true;
+        auto visit = [&](int rj) {
+            const unsigned sj = ld_state(a.state + rj);
+            if (sj == 1u) { any_kept = true; return false; }
+            if (sj == 0u) all_sup = false;
+            return true;
+        };
+        if (a.brute) for_each_earlier(r, a.sbox, a.iou, bfast, a.mode, visit);
+        else for_each_predecessor(a.pos_of_rank[r], a.keys, c, a.cell_start, a.cell_end, a.cbox, a.carea, a.iou, visit);
+        return any_kept ? 2 : (all_sup ? 1 : 0);
+    };
     bool first_done = gtid >= a.N;
     for (int epoch = 0;; ++epoch) {
         int undecided = 0;
         for (int sweep = 0; sweep < ROUND_SWEEPS; ++sweep) {
             undecided = 0;
+            const bool nothing_yet = epoch == 0 && sweep == 0;   // no box is decided yet: polling would read zeros
             if (!first_done) {
                 int d;
-                if (cnt0 >= 0) {
-                    const int *mine = a.adj + (size_t)gtid * ADJ_CAP;
-                    d = try_decide_listed(cnt0, [&](int e) { return e < a.adj_smem ? sadj[e * NT + tid] : __ldcg(mine + e); }, a.state);
-                }
+                if (rescan) d = decide_rescan(gtid);
                 else {
-                    bool any_kept = false, all_sup = true;
-                    auto visit = [&](int rj) {
-                        const unsigned sj = ld_state(a.state + rj);
-                        if (sj == 1u) { any_kept = true; return false; }
-                        if (sj == 0u) all_sup = false;
-                        return true;
-                    };
-                    if (a.brute) for_each_earlier(gtid, a.sbox, a.iou, bfast, a.mode, visit);
-                    else for_each_predecessor(a.pos_of_rank[gtid], a.keys, c, a.cell_start, a.cell_end, a.cbox, a.carea, a.iou, visit);
-                    d = any_kept ? 2 : (all_sup ? 1 : 0);
+                    d = pend == 0 ? 1 : (nothing_yet ? 0 : decide_pending(pend, get0, put0, a.state));
+                    if (d == 1 && overflow) {
+                        d = 0;
+                        rescan = true;
+                        atomicAdd(&a.out_state[4], 1);   // statistics: boxes that had to rescan
+                    }
                 }
                 if (d) { state[gtid] = (unsigned char)d; first_done = true; }
                 else ++undecided;
             }
             for (int r = gtid + gstride; r < a.N; r += gstride) {  // only when N exceeds the resident thread count
                 if (state[r] != 0) continue;
-                const int cnt = __ldcg(&a.adj_cnt[r]);
+                const int v = __ldcg(&acnt[r * cstep]);
                 int d;
-                if (cnt >= 0 && cnt <= ADJ_CAP) {
-                    const int *mine = a.adj + (size_t)r * ADJ_CAP;
-                    d = try_decide_listed(cnt, [&](int e) { return __ldcg(mine + e); }, a.state);
-                } else {
-                    bool any_kept = false, all_sup = true;
-                    auto visit = [&](int rj) {
-                        const unsigned sj = ld_state(a.state + rj);
-                        if (sj == 1u) { any_kept = true; return false; }
-                        if (sj == 0u) all_sup = false;
-                        return true;
-                    };
-                    if (a.brute) for_each_earlier(r, a.sbox, a.iou, bfast, a.mode, visit);
-                    else for_each_predecessor(a.pos_of_rank[r], a.keys, c, a.cell_start, a.cell_end, a.cbox, a.carea, a.iou, visit);
-                    d = any_kept ? 2 : (all_sup ? 1 : 0);
+                if (v < 0) d = decide_rescan(r);
+                else {
+                    int pn = v & 0x3fffffff;
+                    const bool ov = (v >> 30) & 1;
+                    int *row = const_cast<int *>(a.adj) + (size_t)r * a.adj_stride;
+                    d = pn == 0 ? 1 : (nothing_yet ? 0 : decide_pending(pn, [&](int e) { return __ldcg(row + e); }, [&](int e, int x) { row[e] = x; }, a.state));
+                    if (d == 1 && ov) {
+                        d = 0;
+                        acnt[r * cstep] = -1;
+                        atomicAdd(&a.out_state[4], 1);
+                    } else if (d == 0 && !nothing_yet) {
+                        acnt[r * cstep] = pn | (ov ? (1 << 30) : 0);
+                    }
                 }
                 if (d) state[r] = (unsigned char)d;
                 else ++undecided;
@@ -1052,7 +1160,6 @@ struct BigArgs {
     RoundsArgs ra;          // keys / final_keys are set on the device (they depend on the number of passes)
     PeelArgs pa;
     int *keep_dev, *num_keep_dev;
-    int lists_map;          // experiment switch: how phase 6 hands boxes to threads
     long long *dbg;         // FD_NMS_DBG: globaltimer stamps of block 0
 };
 
@@ -1385,27 +1492,21 @@ __global__ void __launch_bounds__(NT, 1) nms_big_kernel(BigArgs m) {
     grid.sync();
     big_stamp(m.dbg, 6);
     // ---- 6. predecessor lists: contiguous cell-ordered chunks, every SM takes part ----
-    if (m.lists_map == 1) {          // tiles of 256 boxes dealt round-robin to the CTAs (what a 256-thread launch gives)
-        const int nt256 = (n + 255) / 256;
-        for (int t = blockIdx.x + G * (tid >> 8); t < nt256; t += G * (NT >> 8)) {
-            const int k = t * 256 + (tid & 255);
-            if (k < n) adjacency_of(k, csorted, c, m.cell_start, m.cell_end, m.cbox, m.carea, m.ra.iou, const_cast<int *>(m.ra.adj), const_cast<int *>(m.ra.adj_cnt));
-        }
-    } else if (m.lists_map == 2) {   // warps take 32 boxes at a time from a ticket
+    {   // (box, neighbourhood row) tasks, row-major so a warp's lanes are consecutive cell-ordered boxes on the same row; warps take
+        // 32 tasks at a time from a ticket (rows and cells differ in cost)
         int *ticket = m.st + 24;
+        const long long tasks = 3ll * n;
         for (;;) {
             int base = 0;
             if (lane == 0) base = atomicAdd(ticket, 32);
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= n) break;
-            const int k = base + lane;
-            if (k < n) adjacency_of(k, csorted, c, m.cell_start, m.cell_end, m.cbox, m.carea, m.ra.iou, const_cast<int *>(m.ra.adj), const_cast<int *>(m.ra.adj_cnt));
+            if (base >= tasks) break;
+            const int q = base + lane;
+            if (q < tasks) {
+                const int row = q / n, k = q - row * n;
+                adjacency_row(k, row - 1, csorted, c, m.cell_start, m.cell_end, m.cbox, m.carea, m.ra.iou, const_cast<int *>(m.ra.adj), const_cast<int *>(m.ra.adj_cnt));
+            }
         }
-    } else {
-        const int per = (n + G - 1) / G;
-        const int k1 = min(n, (int)(blockIdx.x + 1) * per);
-        for (int k = blockIdx.x * per + tid; k < k1; k += NT)
-            adjacency_of(k, csorted, c, m.cell_start, m.cell_end, m.cbox, m.carea, m.ra.iou, const_cast<int *>(m.ra.adj), const_cast<int *>(m.ra.adj_cnt));
     }
     __threadfence();
     grid.sync();
@@ -1608,6 +1709,8 @@ static int nms_big_impl(fd_ctx *ctx, const u64 *keys_in, const int *key_bytes, i
         ra.mode = mode;
         ra.status = st;
         ra.adj_smem = ADJ_SMEM;
+        ra.seg3 = 0;
+        ra.adj_stride = ADJ_CAP;
         void *rargs[] = {&ra};
         int per_sm_r = 0;
         const size_t smem_r = sizeof(int) * (size_t)ADJ_SMEM * NT;
@@ -1686,6 +1789,8 @@ static int nms_mid_impl(fd_ctx *ctx, const float *boxes, int K, int stride, cons
     ra.mode = mode;
     ra.status = st;
     ra.adj_smem = ADJ_SMEM;
+    ra.seg3 = 0;
+    ra.adj_stride = ADJ_CAP;
     ra.final_keep = keep_dev;
     ra.final_keys = m.sorted;
     ra.final_num = num_keep_dev;
@@ -1733,8 +1838,8 @@ static int nms_big_one_launch(fd_ctx *ctx, const float *boxes, int K, int stride
     FD_TRY(ctx->nms_ws[6].reserve(sizeof(int) * 32));
     FD_TRY(ctx->nms_ws_sp[0].reserve(sizeof(u64) * (size_t)K * 2));
     FD_TRY(ctx->nms_ws_sp[1].reserve(sizeof(int) * (size_t)(GRID_MAX_CELLS + 1) * 2));
-    FD_TRY(ctx->nms_ws_sp[2].reserve((sizeof(float4) + sizeof(float) + sizeof(int) * 2) * (size_t)K + (size_t)K + 16));
-    FD_TRY(ctx->nms_ws_sp[3].reserve(sizeof(int) * (size_t)K * ADJ_CAP));
+    FD_TRY(ctx->nms_ws_sp[2].reserve((sizeof(float4) + sizeof(float) + sizeof(int) * 4) * (size_t)K + (size_t)K + 16));   // cbox, carea, pos, 3 counters, state
+    FD_TRY(ctx->nms_ws_sp[3].reserve(sizeof(int) * (size_t)K * ADJ_ROW3));
     int *st = ctx->nms_ws[6].as<int>();
     FD_CUDA(cudaMemsetAsync(st, 0, sizeof(int) * 32, ctx->stream));
     const IouParams iou = make_iou_params(thr, mode);
@@ -1771,7 +1876,7 @@ static int nms_big_one_launch(fd_ctx *ctx, const float *boxes, int K, int stride
     ra.pos_of_rank = m.pos_of_rank;
     ra.adj = ctx->nms_ws_sp[3].as<int>();
     ra.adj_cnt = adj_cnt;
-    ra.state = reinterpret_cast<unsigned char *>(adj_cnt + K);
+    ra.state = reinterpret_cast<unsigned char *>(adj_cnt + (size_t)3 * K);
     ra.counters = st + 13;
     ra.tile_counts = tile_counts;
     ra.ballots = ballots;
@@ -1784,8 +1889,8 @@ static int nms_big_one_launch(fd_ctx *ctx, const float *boxes, int K, int stride
     ra.status = st;
     static const int adj_smem = getenv("FD_NMS_ADJ_SMEM") ? std::max(4, std::min(ADJ_SMEM, atoi(getenv("FD_NMS_ADJ_SMEM")) & ~3)) : ADJ_SMEM;
     ra.adj_smem = adj_smem;
-    static const int lists_map = getenv("FD_NMS_LISTS_MAP") ? atoi(getenv("FD_NMS_LISTS_MAP")) : 0;
-    m.lists_map = lists_map;
+    ra.seg3 = 1;
+    ra.adj_stride = ADJ_ROW3;
     ra.final_keep = keep_dev;
     ra.final_num = num_keep_dev;
     PeelArgs &pa = m.pa;
@@ -1822,9 +1927,9 @@ static int nms_big_one_launch(fd_ctx *ctx, const float *boxes, int K, int stride
         cudaStreamSynchronize(ctx->stream);
         cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
         cudaMemcpy(sth, st, sizeof(sth), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[nms big dbg] K=%d grid=%d spatial=%d: keys %.1f  sort %.1f  boxes %.1f  cells %.1f  cell sort %.1f  bounds %.1f  lists %.1f  sweeps %.1f  output %.1f (epochs %d) us, total %.1f\n",
+        fprintf(stderr, "[nms big dbg] K=%d grid=%d spatial=%d: keys %.1f  sort %.1f  boxes %.1f  cells %.1f  cell sort %.1f  bounds %.1f  lists %.1f  sweeps %.1f  output %.1f (epochs %d, rescanning boxes %d) us, total %.1f\n",
                 K, ctx->num_sms * per_sm, sth[3], (h[1] - h[0]) * 1e-3, (h[2] - h[1]) * 1e-3, (h[3] - h[2]) * 1e-3, (h[4] - h[3]) * 1e-3,
-                (h[5] - h[4]) * 1e-3, (h[6] - h[5]) * 1e-3, (h[7] - h[6]) * 1e-3, (h[9] - h[7]) * 1e-3, (h[8] - h[9]) * 1e-3, sth[6], (h[8] - h[0]) * 1e-3);
+                (h[5] - h[4]) * 1e-3, (h[6] - h[5]) * 1e-3, (h[7] - h[6]) * 1e-3, (h[9] - h[7]) * 1e-3, (h[8] - h[9]) * 1e-3, sth[6], sth[7], (h[8] - h[0]) * 1e-3);
     }
     return FD_OK;
 }
