@@ -549,11 +549,11 @@ __global__ void grid_stats_kernel(const float4 *__restrict__ sbox, int N, unsign
     }
 }
 
-__device__ __forceinline__ GridCfg grid_setup(const unsigned *gs, int N, const IouParams &P, int not_fast) {
+__device__ __forceinline__ GridCfg grid_setup(unsigned g0, unsigned g1, unsigned g2, unsigned g3, unsigned g4, int N, const IouParams &P, int not_fast) {
     GridCfg c;
-    c.minx = ord2f(__ldcg(gs + 0));
-    c.miny = ord2f(__ldcg(gs + 1));
-    const float maxx = ord2f(__ldcg(gs + 2)), maxy = ord2f(__ldcg(gs + 3)), maxd = ord2f(__ldcg(gs + 4));
+    c.minx = ord2f(g0);
+    c.miny = ord2f(g1);
+    const float maxx = ord2f(g2), maxy = ord2f(g3), maxd = ord2f(g4);
     c.use = 0;
     c.gx = c.gy = 1;
     c.cs = 1.0f;
@@ -578,7 +578,7 @@ __device__ __forceinline__ GridCfg grid_setup(const unsigned *gs, int N, const I
     return c;
 }
 __global__ void grid_setup_kernel(const unsigned *gs, int N, IouParams P, GridCfg *cfg, int *st) {
-    const GridCfg c = grid_setup(gs, N, P, st[2]);
+    const GridCfg c = grid_setup(gs[0], gs[1], gs[2], gs[3], gs[4], N, P, st[2]);
     *cfg = c;
     st[3] = c.use;
 }
@@ -1313,21 +1313,33 @@ __global__ void __launch_bounds__(NT, 1) nms_big_kernel(BigArgs m) {
     const int n = m.n, ntiles = (n + NT - 1) / NT;
     unsigned *gs = reinterpret_cast<unsigned *>(m.st + 8);
     big_stamp(m.dbg, 0);
-    // ---- 0. keys, flags, first digit histogram; arrays that must start at zero ----
+    // ---- 0. keys, flags, first digit histogram, grid statistics (order-independent, so taken here where the rows are read
+    //         anyway); arrays that must start at zero ----
     {
         unsigned acc_or = 0, acc_nand = 0;
-        bool nan_seen = false;
-        if (m.presorted) {
-            for (int i = gtid; i < n; i += gstride) m.ka[i] = (u64)(unsigned)i;
-        } else {
-            for (int t = blockIdx.x; t < ntiles; t += G) {
+        unsigned mincx = 0xFFFFFFFFu, mincy = 0xFFFFFFFFu, maxcx = 0, maxcy = 0, maxd = 0;
+        bool nan_seen = false, ok = true;
+        for (int t = blockIdx.x; t < ntiles; t += G) {
+            if (!m.presorted) {
                 __syncthreads();
                 for (int d = tid; d < CS_D; d += NT) dyn[d] = 0;
                 __syncthreads();
-                const int e = t * NT + tid;
-                int d = CS_D;
-                if (e < n) {
-                    const float sc = __ldg(m.dets + (size_t)e * m.stride + 4);
+            }
+            const int e = t * NT + tid;
+            int d = CS_D;
+            if (e < n) {
+                const float *p = m.dets + (size_t)e * m.stride;
+                const float4 b = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+                ok &= box_is_fast_ok(b);
+                const unsigned cx = f2ord(box_cx(b)), cy = f2ord(box_cy(b));
+                mincx = min(mincx, cx); maxcx = max(maxcx, cx);
+                mincy = min(mincy, cy); maxcy = max(maxcy, cy);
+                const float w = __fadd_rn(__fsub_rn(b.z, b.x), 1.0f), h = __fadd_rn(__fsub_rn(b.w, b.y), 1.0f);
+                maxd = max(maxd, f2ord(fmaxf(fabsf(w), fabsf(h))));
+                if (m.presorted) {
+                    m.ka[e] = (u64)(unsigned)e;
+                } else {
+                    const float sc = __ldg(p + 4);
                     nan_seen |= (sc != sc);
                     const unsigned k32 = desc_key(sc);
                     m.ka[e] = ((u64)k32 << 32) | (unsigned)e;
@@ -1335,42 +1347,78 @@ __global__ void __launch_bounds__(NT, 1) nms_big_kernel(BigArgs m) {
                     acc_nand |= ~k32;
                     d = (int)(k32 & (unsigned)(CS_D - 1));
                 }
+            }
+            if (!m.presorted) {
                 const unsigned peers = __match_any_sync(0xffffffffu, d);
                 if (d < CS_D && lane == __ffs(peers) - 1) atomicAdd(&dyn[d], __popc(peers));
                 __syncthreads();
                 for (int dd = tid; dd < CS_D; dd += NT) m.hist[(size_t)dd * ntiles + t] = dyn[dd];
             }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc_or |= __shfl_xor_sync(0xffffffffu, acc_or, o);
+            acc_nand |= __shfl_xor_sync(0xffffffffu, acc_nand, o);
+            mincx = min(mincx, __shfl_xor_sync(0xffffffffu, mincx, o));
+            mincy = min(mincy, __shfl_xor_sync(0xffffffffu, mincy, o));
+            maxcx = max(maxcx, __shfl_xor_sync(0xffffffffu, maxcx, o));
+            maxcy = max(maxcy, __shfl_xor_sync(0xffffffffu, maxcy, o));
+            maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
+        }
+        __syncthreads();
+        unsigned *ured = reinterpret_cast<unsigned *>(dyn);   // one set of atomics per CTA, not per warp
+        if (lane == 0) {
+            const int w = tid >> 5;
+            ured[w] = acc_or; ured[32 + w] = acc_nand;
+            ured[64 + w] = mincx; ured[96 + w] = mincy; ured[128 + w] = maxcx; ured[160 + w] = maxcy; ured[192 + w] = maxd;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            acc_or = ured[tid]; acc_nand = ured[32 + tid];
+            mincx = ured[64 + tid]; mincy = ured[96 + tid]; maxcx = ured[128 + tid]; maxcy = ured[160 + tid]; maxd = ured[192 + tid];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 acc_or |= __shfl_xor_sync(0xffffffffu, acc_or, o);
                 acc_nand |= __shfl_xor_sync(0xffffffffu, acc_nand, o);
+                mincx = min(mincx, __shfl_xor_sync(0xffffffffu, mincx, o));
+                mincy = min(mincy, __shfl_xor_sync(0xffffffffu, mincy, o));
+                maxcx = max(maxcx, __shfl_xor_sync(0xffffffffu, maxcx, o));
+                maxcy = max(maxcy, __shfl_xor_sync(0xffffffffu, maxcy, o));
+                maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
             }
-            __syncthreads();
-            unsigned *ured = reinterpret_cast<unsigned *>(dyn);   // one pair of atomics per CTA, not per warp
-            if (lane == 0) { ured[tid >> 5] = acc_or; ured[32 + (tid >> 5)] = acc_nand; }
-            __syncthreads();
-            if (tid < 32) {
-                acc_or = ured[tid];
-                acc_nand = ured[32 + tid];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    acc_or |= __shfl_xor_sync(0xffffffffu, acc_or, o);
-                    acc_nand |= __shfl_xor_sync(0xffffffffu, acc_nand, o);
-                }
-                if (tid == 0 && (acc_or | acc_nand)) {
+            if (tid == 0) {
+                if (acc_or | acc_nand) {
                     atomicOr(reinterpret_cast<unsigned *>(m.st) + 22, acc_nand);
                     atomicOr(reinterpret_cast<unsigned *>(m.st) + 23, acc_or);
                 }
+                if (mincx != 0xFFFFFFFFu) {   // (a CTA without boxes has nothing to report)
+                    // min cx / min cy are kept complemented so that the memset's zero is their identity as well
+                    atomicMax(&gs[0], ~mincx);
+                    atomicMax(&gs[1], ~mincy);
+                    atomicMax(&gs[2], maxcx);
+                    atomicMax(&gs[3], maxcy);
+                    atomicMax(&gs[4], maxd);
+                }
             }
-            if (__syncthreads_or(nan_seen) && tid == 0) atomicExch(&m.st[0], 1);
         }
+        if (__syncthreads_or(nan_seen) && tid == 0) atomicExch(&m.st[0], 1);
+        if (__syncthreads_or(!ok) && tid == 0) atomicExch(&m.st[2], 1);
         unsigned *state4 = reinterpret_cast<unsigned *>(m.ra.state);
         for (int i = gtid; i < (n + 3) / 4; i += gstride) state4[i] = 0u;
-        if (gtid < 2) gs[gtid] = 0xFFFFFFFFu;   // min cx / min cy (ordered-uint encoding); the maxima start at the memset's zero
     }
     __threadfence();
     grid.sync();
     big_stamp(m.dbg, 1);
+    // ---- grid geometry: every CTA derives the same one ----
+    if (tid == 0) {
+        scfg = grid_setup(~__ldcg(gs + 0), ~__ldcg(gs + 1), __ldcg(gs + 2), __ldcg(gs + 3), __ldcg(gs + 4), n, m.ra.iou, __ldcg(&m.st[2]));
+        if (blockIdx.x == 0) {
+            *const_cast<GridCfg *>(m.ra.cfg) = scfg;
+            m.st[3] = scfg.use;
+        }
+    }
+    __syncthreads();
+    const GridCfg c = scfg;
     // ---- 1. sort by score key (bits above the highest differing one are the same for every key) ----
     u64 *sorted = m.ka;
     if (!m.presorted) {
@@ -1379,70 +1427,33 @@ __global__ void __launch_bounds__(NT, 1) nms_big_kernel(BigArgs m) {
         sorted = cs_sort(m.ka, m.kb, n, 32, nbits, m.hist, ntiles, dyn, red);
     }
     big_stamp(m.dbg, 2);
-    // ---- 2. boxes in rank order, regularity flag, grid statistics ----
-    {
-        unsigned mincx = 0xFFFFFFFFu, mincy = 0xFFFFFFFFu, maxcx = 0, maxcy = 0, maxd = 0;
-        bool ok = true;
-        for (int r = gtid; r < n; r += gstride) {
+    // ---- 2. boxes in rank order, cell keys (cell | rank) and their first digit histogram ----
+    const int ncells = c.gx * c.gy;
+    const int cbits = ncells > 1 ? 32 - __clz(ncells - 1) : 0;
+    for (int t = blockIdx.x; t < ntiles; t += G) {
+        const int r = t * NT + tid;
+        if (r < n) {
             const int idx = (int)(unsigned)__ldcg(sorted + r);
             const float *p = m.dets + (size_t)idx * m.stride;
             const float4 b = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
             m.sbox[r] = b;
-            ok &= box_is_fast_ok(b);
-            const unsigned cx = f2ord(box_cx(b)), cy = f2ord(box_cy(b));
-            mincx = min(mincx, cx); maxcx = max(maxcx, cx);
-            mincy = min(mincy, cy); maxcy = max(maxcy, cy);
-            const float w = __fadd_rn(__fsub_rn(b.z, b.x), 1.0f), h = __fadd_rn(__fsub_rn(b.w, b.y), 1.0f);
-            maxd = max(maxd, f2ord(fmaxf(fabsf(w), fabsf(h))));
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mincx = min(mincx, __shfl_xor_sync(0xffffffffu, mincx, o));
-            mincy = min(mincy, __shfl_xor_sync(0xffffffffu, mincy, o));
-            maxcx = max(maxcx, __shfl_xor_sync(0xffffffffu, maxcx, o));
-            maxcy = max(maxcy, __shfl_xor_sync(0xffffffffu, maxcy, o));
-            maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
-        }
-        unsigned *ured = reinterpret_cast<unsigned *>(dyn);   // one set of atomics per CTA
-        __syncthreads();
-        if (lane == 0) {
-            const int w = tid >> 5;
-            ured[w] = mincx; ured[32 + w] = mincy; ured[64 + w] = maxcx; ured[96 + w] = maxcy; ured[128 + w] = maxd;
-        }
-        __syncthreads();
-        if (tid < 32) {
-            mincx = ured[tid]; mincy = ured[32 + tid]; maxcx = ured[64 + tid]; maxcy = ured[96 + tid]; maxd = ured[128 + tid];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                mincx = min(mincx, __shfl_xor_sync(0xffffffffu, mincx, o));
-                mincy = min(mincy, __shfl_xor_sync(0xffffffffu, mincy, o));
-                maxcx = max(maxcx, __shfl_xor_sync(0xffffffffu, maxcx, o));
-                maxcy = max(maxcy, __shfl_xor_sync(0xffffffffu, maxcy, o));
-                maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
-            }
-            if (tid == 0 && mincx != 0xFFFFFFFFu) {   // (a CTA without boxes has nothing to report)
-                atomicMin(&gs[0], mincx);
-                atomicMin(&gs[1], mincy);
-                atomicMax(&gs[2], maxcx);
-                atomicMax(&gs[3], maxcy);
-                atomicMax(&gs[4], maxd);
+            if (c.use) {
+                const int ix = cell_coord(box_cx(b), c.minx, c.cs, c.gx), iy = cell_coord(box_cy(b), c.miny, c.cs, c.gy);
+                m.cka[r] = ((u64)(unsigned)(iy * c.gx + ix) << 32) | (unsigned)r;
             }
         }
-        if (__syncthreads_or(!ok) && tid == 0) atomicExch(&m.st[2], 1);
+    }
+    if (c.use) {
+        for (int i = gtid; i < ncells; i += gstride) {
+            m.cell_start[i] = 0;
+            m.cell_end[i] = 0;
+        }
+        __syncthreads();   // this CTA's tiles of cka were written by this CTA (same tiles, same threads)
+        if (cbits > 0) cs_tile_hist([&](int e) { return __ldcg(m.cka + e); }, n, 32, m.hist, ntiles, dyn);   // (ld.cg: cka is rewritten by the passes, no stale L1 line later)
     }
     __threadfence();
     grid.sync();
     big_stamp(m.dbg, 3);
-    // ---- 3. grid geometry: every CTA derives the same one ----
-    if (tid == 0) {
-        scfg = grid_setup(gs, n, m.ra.iou, __ldcg(&m.st[2]));
-        if (blockIdx.x == 0) {
-            *const_cast<GridCfg *>(m.ra.cfg) = scfg;
-            m.st[3] = scfg.use;
-        }
-    }
-    __syncthreads();
-    const GridCfg c = scfg;
     if (!c.use) {   // uniform over the grid: the peel owns this problem; its kept ranks become source indices afterwards
         if (m.mode == 0) nms_peel_body<0>(m.pa, reinterpret_cast<unsigned char *>(dyn));
         else nms_peel_body<1>(m.pa, reinterpret_cast<unsigned char *>(dyn));
@@ -1456,23 +1467,6 @@ __global__ void __launch_bounds__(NT, 1) nms_big_kernel(BigArgs m) {
         }
         return;
     }
-    const int ncells = c.gx * c.gy;
-    const int cbits = ncells > 1 ? 32 - __clz(ncells - 1) : 0;
-    {
-        for (int r = gtid; r < n; r += gstride) {
-            const float4 b = m.sbox[r];
-            const int ix = cell_coord(box_cx(b), c.minx, c.cs, c.gx), iy = cell_coord(box_cy(b), c.miny, c.cs, c.gy);
-            m.cka[r] = ((u64)(unsigned)(iy * c.gx + ix) << 32) | (unsigned)r;
-        }
-        for (int i = gtid; i < ncells; i += gstride) {
-            m.cell_start[i] = 0;
-            m.cell_end[i] = 0;
-        }
-        __syncthreads();   // this CTA's tiles of cka were written by this CTA (same grid-stride ownership): block-level visibility
-        if (cbits > 0) cs_tile_hist([&](int e) { return __ldcg(m.cka + e); }, n, 32, m.hist, ntiles, dyn);   // (ld.cg: cka is rewritten by the passes, no stale L1 line later)
-    }
-    __threadfence();
-    grid.sync();
     big_stamp(m.dbg, 4);
     // ---- 4. stable sort by cell: members of a cell stay in rank order ----
     const u64 *csorted = cs_sort(m.cka, m.ckb, n, 32, cbits, m.hist, ntiles, dyn, red);
@@ -1493,7 +1487,9 @@ __global__ void __launch_bounds__(NT, 1) nms_big_kernel(BigArgs m) {
     big_stamp(m.dbg, 6);
     // ---- 6. predecessor lists: contiguous cell-ordered chunks, every SM takes part ----
     {   // (box, neighbourhood row) tasks, row-major so a warp's lanes are consecutive cell-ordered boxes on the same row; warps take
-        // 32 tasks at a time from a ticket (rows and cells differ in cost)
+        // 32 tasks at a time from a ticket (rows and cells differ in cost).  Measured at 100 000 boxes: one box per thread in
+        // contiguous chunks 145 us, 256-box tiles dealt round-robin 124, whole boxes from a ticket 119, these row tasks 82;
+        // one warp per (non-empty cell, row) — lanes walking the same candidate cells — 151 (few, uneven tasks).
         int *ticket = m.st + 24;
         const long long tasks = 3ll * n;
         for (;;) {
@@ -1927,8 +1923,8 @@ static int nms_big_one_launch(fd_ctx *ctx, const float *boxes, int K, int stride
         cudaStreamSynchronize(ctx->stream);
         cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
         cudaMemcpy(sth, st, sizeof(sth), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[nms big dbg] K=%d grid=%d spatial=%d: keys %.1f  sort %.1f  boxes %.1f  cells %.1f  cell sort %.1f  bounds %.1f  lists %.1f  sweeps %.1f  output %.1f (epochs %d, rescanning boxes %d) us, total %.1f\n",
-                K, ctx->num_sms * per_sm, sth[3], (h[1] - h[0]) * 1e-3, (h[2] - h[1]) * 1e-3, (h[3] - h[2]) * 1e-3, (h[4] - h[3]) * 1e-3,
+        fprintf(stderr, "[nms big dbg] K=%d grid=%d spatial=%d: keys+stats %.1f  sort %.1f  boxes+cells %.1f  cell sort %.1f  bounds %.1f  lists %.1f  sweeps %.1f  output %.1f (epochs %d, rescanning boxes %d) us, total %.1f\n",
+                K, ctx->num_sms * per_sm, sth[3], (h[1] - h[0]) * 1e-3, (h[2] - h[1]) * 1e-3, (h[3] - h[2]) * 1e-3,
                 (h[5] - h[4]) * 1e-3, (h[6] - h[5]) * 1e-3, (h[7] - h[6]) * 1e-3, (h[9] - h[7]) * 1e-3, (h[8] - h[9]) * 1e-3, sth[6], sth[7], (h[8] - h[0]) * 1e-3);
     }
     return FD_OK;
