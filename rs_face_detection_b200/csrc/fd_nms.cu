@@ -688,6 +688,66 @@ __device__ __forceinline__ void adjacency_row(int k, int dy, const u64 *__restri
     cnt3[rank * 3 + dy + 1] = cnt;   // may exceed ADJ_SEG: the first ADJ_SEG are listed
 }
 
+// ---- the same two for the one-launch path, which never sorts the boxes globally: boxes are addressed by their position k in
+// cell order, members of a cell are ordered by their FULL key (score desc | source index — the order a stable descending sort
+// gives), "earlier-ranked" is a key comparison, and the cell of a box is recomputed from its centre.  visit(j) gets a position.
+template <class F>
+__device__ __forceinline__ void for_each_predecessor_k(int k, const u64 *__restrict__ ckey, const GridCfg &c,
+                                                       const int *__restrict__ cell_start, const int *__restrict__ cell_end,
+                                                       const float4 *__restrict__ cbox, const float *__restrict__ carea,
+                                                       const IouParams &P, F &&visit, int dy0 = -1, int dy1 = 1) {
+    const u64 key = ckey[k];
+    const float4 bi = cbox[k];
+    const float ai = carea[k];
+    const int ix = cell_coord(box_cx(bi), c.minx, c.cs, c.gx), iy = cell_coord(box_cy(bi), c.miny, c.cs, c.gy);
+    for (int dy = dy0; dy <= dy1; ++dy) {
+        const int y = iy + dy;
+        if (y < 0 || y >= c.gy) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int x = ix + dx;
+            if (x < 0 || x >= c.gx) continue;
+            const int c2 = y * c.gx + x;
+            const int e = cell_end[c2];
+            int j = cell_start[c2];
+            for (; j + 3 < e; j += 4) {   // members are in key order: 4 candidates per step so their loads are in flight together
+                u64 kj[4];
+                float4 bj[4];
+                float aj[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    kj[u] = ckey[j + u];
+                    bj[u] = cbox[j + u];
+                    aj[u] = carea[j + u];
+                }
+                if (kj[0] >= key) break;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (kj[u] < key && iou_suppresses_exact(bj[u], aj[u], bi, ai, P))
+                        if (!visit(j + u)) return;
+                if (kj[3] >= key) { j = e; break; }
+            }
+            for (; j < e; ++j) {
+                if (ckey[j] >= key) break;
+                if (iou_suppresses_exact(cbox[j], carea[j], bi, ai, P))
+                    if (!visit(j)) return;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void adjacency_row_k(int k, int dy, const u64 *__restrict__ ckey, const GridCfg &c, const int *__restrict__ cell_start,
+                                                const int *__restrict__ cell_end, const float4 *__restrict__ cbox, const float *__restrict__ carea,
+                                                const IouParams &P, int *__restrict__ adj, int *__restrict__ cnt3) {
+    int cnt = 0;
+    int *mine = adj + (size_t)k * ADJ_ROW3 + (dy + 1) * ADJ_SEG;
+    for_each_predecessor_k(k, ckey, c, cell_start, cell_end, cbox, carea, P, [&](int j) {
+        if (cnt < ADJ_SEG) mine[cnt] = j;
+        ++cnt;
+        return true;
+    }, dy, dy);
+    cnt3[k * 3 + dy + 1] = cnt;   // may exceed ADJ_SEG: the first ADJ_SEG are listed
+}
+
 __global__ void __launch_bounds__(256) adjacency_kernel(const u64 *__restrict__ keys, int N, const GridCfg *cfg,
                                                         const int *__restrict__ cell_start, const int *__restrict__ cell_end,
                                                         const float4 *__restrict__ cbox, const float *__restrict__ carea, IouParams P,
@@ -733,6 +793,8 @@ struct RoundsArgs {
     int adj_smem;           // list entries per box cached in shared memory across sweeps (<= ADJ_SMEM; sadj holds adj_smem x NT ints)
     int seg3;               // lists are three ADJ_SEG segments with adj_cnt[3 * box + segment] entries each (adjacency_row)
     int adj_stride;         // ints per box in adj (ADJ_CAP, or ADJ_ROW3 with seg3)
+    int kspace;             // boxes are cell-order positions, keys = full (score | index) keys: for_each_predecessor_k
+    u64 *kept_keys;         // kspace: the kept boxes' keys (in position order) go here instead of final_keep; [1] of out_state = count
 };
 
 __device__ __forceinline__ void mid_stamp(long long *dbg, int slot) {
@@ -743,7 +805,7 @@ __device__ __forceinline__ void mid_stamp(long long *dbg, int slot) {
     }
 }
 
-constexpr int ROUND_SWEEPS = 8;
+constexpr int ROUND_SWEEPS = 24;   // sweeps of a warp between two grid-wide checks
 
 // brute-mode stand-in for for_each_predecessor: every earlier box that suppresses box r
 template <class F>
@@ -888,6 +950,7 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
             return true;
         };
         if (a.brute) for_each_earlier(r, a.sbox, a.iou, bfast, a.mode, visit);
+        else if (a.kspace) for_each_predecessor_k(r, a.keys, c, a.cell_start, a.cell_end, a.cbox, a.carea, a.iou, visit);
         else for_each_predecessor(a.pos_of_rank[r], a.keys, c, a.cell_start, a.cell_end, a.cbox, a.carea, a.iou, visit);
         return any_kept ? 2 : (all_sup ? 1 : 0);
     };
@@ -932,7 +995,10 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
                 if (d) state[r] = (unsigned char)d;
                 else ++undecided;
             }
-            if (__syncthreads_count(undecided) == 0) break;  // this CTA is finished
+            // Warps sweep at their own pace — no CTA barrier in here, so a warp with short lists advances one dependency link per
+            // L2 round trip instead of per (barrier + slowest thread of the CTA).  Measured at 100 000 boxes: CTA-wide sweeps 46 us,
+            // the same with two immediate re-polls per sweep 61 us (more polling, same pace), warp-paced sweeps: see DESIGN 4.3.
+            if (__all_sync(0xffffffffu, undecided == 0)) break;  // this warp is finished
         }
         int tot = block_sum(undecided, red);
         if (tid == 0 && tot) atomicAdd(&a.counters[epoch % 3], tot);
@@ -946,6 +1012,21 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
         if (left == 0) break;
     }
     mid_stamp(a.dbg, 5);
+    if (a.kept_keys) {   // the caller orders the kept keys itself: any order will do here, one atomic per warp
+        for (int r = gtid; r < a.N; r += gstride) {
+            const bool flag = state[r] == 1;
+            const unsigned bal = __ballot_sync(__activemask(), flag);
+            if (flag) {
+                const int leader = __ffs(bal) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(&a.out_state[1], __popc(bal));
+                base = __shfl_sync(bal, base, leader);
+                a.kept_keys[base + __popc(bal & ((1u << lane) - 1u))] = __ldcg(&a.final_keys[r]);
+            }
+        }
+        mid_stamp(a.dbg, 6);
+        return;
+    }
     // ordered output of the kept ranks
     const int ntiles = (a.N + NT - 1) / NT;
     for (int t = blockIdx.x; t < ntiles; t += G) {
@@ -972,7 +1053,8 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
         const unsigned mine = __shfl_sync(0xffffffffu, myb, warp);
         if ((mine >> lane) & 1u) {
             const int pos = offset + wpre + __popc(mine & ((1u << lane) - 1u));
-            if (a.final_keep) a.final_keep[pos] = (int)(unsigned)__ldcg(&a.final_keys[t * NT + tid]);
+            if (a.kept_keys) a.kept_keys[pos] = __ldcg(&a.final_keys[t * NT + tid]);
+            else if (a.final_keep) a.final_keep[pos] = (int)(unsigned)__ldcg(&a.final_keys[t * NT + tid]);
             else a.keep_ranks[pos] = t * NT + tid;
         }
     }
@@ -1148,16 +1230,20 @@ constexpr size_t CS_SMEM = sizeof(int) * (size_t)(2 + NWARPS) * CS_D;
 struct BigArgs {
     const float *dets;
     int n, stride, presorted, mode;
-    u64 *ka, *kb;           // score keys (ping-pong)
-    u64 *cka, *ckb;         // cell keys (ping-pong)
-    int *hist;              // [2][CS_D][ntiles] digit counts per tile, then [CS_D] digit totals
-    float4 *sbox;           // boxes in rank order
-    int *st;                // status block (zero at launch): nms_big_impl's slots, [22] NAND / [23] OR of the score keys
-    int *cell_start, *cell_end;
+    u64 *key_e;             // keys (score desc | source index) by source index; the fallback's sort ping-pongs it with tmp_key
+    u64 *tmp_key;           // keys in cell order, arrival order inside a cell
+    u64 *ckey;              // keys in cell order, key order inside a cell (final)
+    u64 *kept_keys;         // keys of the kept boxes
+    int *cell_e, *slot_e;   // cell and arrival slot of source box e
+    int *tmp_cell;          // cell of tmp position k
+    int *kept_rank;         // rank of a kept key among the kept keys (zero at its first use)
+    int *hist;              // fallback / many kept boxes: [2][CS_D][ntiles] digit counts per tile, then [CS_D] digit totals
+    float4 *sbox;           // fallback: boxes in rank order
+    int *st;                // status block (zero at launch): nms_big_impl's slots, [22] NAND / [23] OR of the score keys, [24] ticket
+    int *cell_cnt, *cell_start, *cell_end;
     float4 *cbox;
     float *carea;
-    int *pos_of_rank;
-    RoundsArgs ra;          // keys / final_keys are set on the device (they depend on the number of passes)
+    RoundsArgs ra;
     PeelArgs pa;
     int *keep_dev, *num_keep_dev;
     long long *dbg;         // FD_NMS_DBG: globaltimer stamps of block 0
@@ -1304,55 +1390,40 @@ __device__ __forceinline__ u64 *cs_sort(u64 *a, u64 *b, int n, int lo_bit, int n
     return in;
 }
 
+constexpr int KEPT_RANK_CAP = 16384;   // kept keys ordered by all-pairs counting up to here (6 357 at 100 000 boxes), by the radix passes beyond
+
 __global__ void __launch_bounds__(NT, 1) nms_big_kernel(BigArgs m) {
     extern __shared__ __align__(16) int dyn[];
     __shared__ int red[32];
     __shared__ GridCfg scfg;
     cg::grid_group grid = cg::this_grid();
-    const int tid = threadIdx.x, lane = tid & 31, G = gridDim.x, gtid = blockIdx.x * NT + tid, gstride = G * NT;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = gridDim.x, gtid = blockIdx.x * NT + tid, gstride = G * NT;
     const int n = m.n, ntiles = (n + NT - 1) / NT;
     unsigned *gs = reinterpret_cast<unsigned *>(m.st + 8);
     big_stamp(m.dbg, 0);
-    // ---- 0. keys, flags, first digit histogram, grid statistics (order-independent, so taken here where the rows are read
-    //         anyway); arrays that must start at zero ----
+    // ---- 0. keys, flags, grid statistics; arrays that must start at zero ----
     {
         unsigned acc_or = 0, acc_nand = 0;
         unsigned mincx = 0xFFFFFFFFu, mincy = 0xFFFFFFFFu, maxcx = 0, maxcy = 0, maxd = 0;
         bool nan_seen = false, ok = true;
-        for (int t = blockIdx.x; t < ntiles; t += G) {
-            if (!m.presorted) {
-                __syncthreads();
-                for (int d = tid; d < CS_D; d += NT) dyn[d] = 0;
-                __syncthreads();
-            }
-            const int e = t * NT + tid;
-            int d = CS_D;
-            if (e < n) {
-                const float *p = m.dets + (size_t)e * m.stride;
-                const float4 b = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
-                ok &= box_is_fast_ok(b);
-                const unsigned cx = f2ord(box_cx(b)), cy = f2ord(box_cy(b));
-                mincx = min(mincx, cx); maxcx = max(maxcx, cx);
-                mincy = min(mincy, cy); maxcy = max(maxcy, cy);
-                const float w = __fadd_rn(__fsub_rn(b.z, b.x), 1.0f), h = __fadd_rn(__fsub_rn(b.w, b.y), 1.0f);
-                maxd = max(maxd, f2ord(fmaxf(fabsf(w), fabsf(h))));
-                if (m.presorted) {
-                    m.ka[e] = (u64)(unsigned)e;
-                } else {
-                    const float sc = __ldg(p + 4);
-                    nan_seen |= (sc != sc);
-                    const unsigned k32 = desc_key(sc);
-                    m.ka[e] = ((u64)k32 << 32) | (unsigned)e;
-                    acc_or |= k32;
-                    acc_nand |= ~k32;
-                    d = (int)(k32 & (unsigned)(CS_D - 1));
-                }
-            }
-            if (!m.presorted) {
-                const unsigned peers = __match_any_sync(0xffffffffu, d);
-                if (d < CS_D && lane == __ffs(peers) - 1) atomicAdd(&dyn[d], __popc(peers));
-                __syncthreads();
-                for (int dd = tid; dd < CS_D; dd += NT) m.hist[(size_t)dd * ntiles + t] = dyn[dd];
+        for (int e = gtid; e < n; e += gstride) {
+            const float *p = m.dets + (size_t)e * m.stride;
+            const float4 b = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+            ok &= box_is_fast_ok(b);
+            const unsigned cx = f2ord(box_cx(b)), cy = f2ord(box_cy(b));
+            mincx = min(mincx, cx); maxcx = max(maxcx, cx);
+            mincy = min(mincy, cy); maxcy = max(maxcy, cy);
+            const float w = __fadd_rn(__fsub_rn(b.z, b.x), 1.0f), h = __fadd_rn(__fsub_rn(b.w, b.y), 1.0f);
+            maxd = max(maxd, f2ord(fmaxf(fabsf(w), fabsf(h))));
+            if (m.presorted) {
+                m.key_e[e] = (u64)(unsigned)e;
+            } else {
+                const float sc = __ldg(p + 4);
+                nan_seen |= (sc != sc);
+                const unsigned k32 = desc_key(sc);
+                m.key_e[e] = ((u64)k32 << 32) | (unsigned)e;
+                acc_or |= k32;
+                acc_nand |= ~k32;
             }
         }
 #pragma unroll
@@ -1365,12 +1436,10 @@ __global__ void __launch_bounds__(NT, 1) nms_big_kernel(BigArgs m) {
             maxcy = max(maxcy, __shfl_xor_sync(0xffffffffu, maxcy, o));
             maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
         }
-        __syncthreads();
         unsigned *ured = reinterpret_cast<unsigned *>(dyn);   // one set of atomics per CTA, not per warp
         if (lane == 0) {
-            const int w = tid >> 5;
-            ured[w] = acc_or; ured[32 + w] = acc_nand;
-            ured[64 + w] = mincx; ured[96 + w] = mincy; ured[128 + w] = maxcx; ured[160 + w] = maxcy; ured[192 + w] = maxd;
+            ured[warp] = acc_or; ured[32 + warp] = acc_nand;
+            ured[64 + warp] = mincx; ured[96 + warp] = mincy; ured[128 + warp] = maxcx; ured[160 + warp] = maxcy; ured[192 + warp] = maxd;
         }
         __syncthreads();
         if (tid < 32) {
@@ -1405,6 +1474,8 @@ __global__ void __launch_bounds__(NT, 1) nms_big_kernel(BigArgs m) {
         if (__syncthreads_or(!ok) && tid == 0) atomicExch(&m.st[2], 1);
         unsigned *state4 = reinterpret_cast<unsigned *>(m.ra.state);
         for (int i = gtid; i < (n + 3) / 4; i += gstride) state4[i] = 0u;
+        for (int i = gtid; i <= GRID_MAX_CELLS; i += gstride) m.cell_cnt[i] = 0;
+        for (int i = gtid; i < n; i += gstride) m.kept_rank[i] = 0;
     }
     __threadfence();
     grid.sync();
@@ -1419,42 +1490,26 @@ __global__ void __launch_bounds__(NT, 1) nms_big_kernel(BigArgs m) {
     }
     __syncthreads();
     const GridCfg c = scfg;
-    // ---- 1. sort by score key (bits above the highest differing one are the same for every key) ----
-    u64 *sorted = m.ka;
-    if (!m.presorted) {
-        const unsigned diff = (~__ldcg(reinterpret_cast<unsigned *>(m.st) + 22)) ^ __ldcg(reinterpret_cast<unsigned *>(m.st) + 23);
-        const int nbits = diff ? 32 - __clz(diff) : 0;
-        sorted = cs_sort(m.ka, m.kb, n, 32, nbits, m.hist, ntiles, dyn, red);
-    }
-    big_stamp(m.dbg, 2);
-    // ---- 2. boxes in rank order, cell keys (cell | rank) and their first digit histogram ----
-    const int ncells = c.gx * c.gy;
-    const int cbits = ncells > 1 ? 32 - __clz(ncells - 1) : 0;
-    for (int t = blockIdx.x; t < ntiles; t += G) {
-        const int r = t * NT + tid;
-        if (r < n) {
+    if (!c.use) {
+        // ---- the grid does not apply (irregular boxes, degenerate threshold, too crowded; uniform over the launch): global sort by
+        //      key (LSD radix over the differing score bits; the keys are in index order, so ties stay stable), boxes in rank order,
+        //      the peel, and its kept ranks become source indices ----
+        u64 *sorted = m.key_e;
+        if (!m.presorted) {
+            const unsigned diff = (~__ldcg(reinterpret_cast<unsigned *>(m.st) + 22)) ^ __ldcg(reinterpret_cast<unsigned *>(m.st) + 23);
+            const int nbits = diff ? 32 - __clz(diff) : 0;
+            if (nbits > 0) cs_tile_hist([&](int e) { return __ldcg(m.key_e + e); }, n, 32, m.hist, ntiles, dyn);
+            __threadfence();
+            grid.sync();
+            sorted = cs_sort(m.key_e, m.tmp_key, n, 32, nbits, m.hist, ntiles, dyn, red);
+        }
+        for (int r = gtid; r < n; r += gstride) {
             const int idx = (int)(unsigned)__ldcg(sorted + r);
             const float *p = m.dets + (size_t)idx * m.stride;
-            const float4 b = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
-            m.sbox[r] = b;
-            if (c.use) {
-                const int ix = cell_coord(box_cx(b), c.minx, c.cs, c.gx), iy = cell_coord(box_cy(b), c.miny, c.cs, c.gy);
-                m.cka[r] = ((u64)(unsigned)(iy * c.gx + ix) << 32) | (unsigned)r;
-            }
+            m.sbox[r] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
         }
-    }
-    if (c.use) {
-        for (int i = gtid; i < ncells; i += gstride) {
-            m.cell_start[i] = 0;
-            m.cell_end[i] = 0;
-        }
-        __syncthreads();   // this CTA's tiles of cka were written by this CTA (same tiles, same threads)
-        if (cbits > 0) cs_tile_hist([&](int e) { return __ldcg(m.cka + e); }, n, 32, m.hist, ntiles, dyn);   // (ld.cg: cka is rewritten by the passes, no stale L1 line later)
-    }
-    __threadfence();
-    grid.sync();
-    big_stamp(m.dbg, 3);
-    if (!c.use) {   // uniform over the grid: the peel owns this problem; its kept ranks become source indices afterwards
+        __threadfence();
+        grid.sync();
         if (m.mode == 0) nms_peel_body<0>(m.pa, reinterpret_cast<unsigned char *>(dyn));
         else nms_peel_body<1>(m.pa, reinterpret_cast<unsigned char *>(dyn));
         __threadfence();
@@ -1467,25 +1522,83 @@ __global__ void __launch_bounds__(NT, 1) nms_big_kernel(BigArgs m) {
         }
         return;
     }
-    big_stamp(m.dbg, 4);
-    // ---- 4. stable sort by cell: members of a cell stay in rank order ----
-    const u64 *csorted = cs_sort(m.cka, m.ckb, n, 32, cbits, m.hist, ntiles, dyn, red);
-    big_stamp(m.dbg, 5);
-    // ---- 5. cell bounds, cell-ordered boxes ----
-    for (int k = gtid; k < n; k += gstride) {
-        const u64 key = __ldcg(csorted + k);
-        const int cell = (int)(key >> 32), rank = (int)(unsigned)key;
-        if (k == 0 || (int)(__ldcg(csorted + k - 1) >> 32) != cell) m.cell_start[cell] = k;
-        if (k == n - 1 || (int)(__ldcg(csorted + k + 1) >> 32) != cell) m.cell_end[cell] = k + 1;
-        const float4 b = m.sbox[rank];
-        m.cbox[k] = b;
-        m.carea[k] = box_area(b);
-        m.pos_of_rank[rank] = k;
+    const int ncells = c.gx * c.gy;
+    // ---- 1. cell of every box and its arrival slot there (no global sort: only the members of a cell get ordered) ----
+    for (int e = gtid; e < n; e += gstride) {
+        const float *p = m.dets + (size_t)e * m.stride;
+        const float4 b = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+        const int cell = cell_coord(box_cy(b), c.miny, c.cs, c.gy) * c.gx + cell_coord(box_cx(b), c.minx, c.cs, c.gx);
+        m.cell_e[e] = cell;
+        m.slot_e[e] = atomicAdd(&m.cell_cnt[cell], 1);
     }
     __threadfence();
     grid.sync();
-    big_stamp(m.dbg, 6);
-    // ---- 6. predecessor lists: contiguous cell-ordered chunks, every SM takes part ----
+    big_stamp(m.dbg, 2);
+    // ---- 2. cell bounds: exclusive scan of the counts; every CTA sums what precedes its chunk of cells and scans the chunk ----
+    {
+        const int per = (ncells + G - 1) / G;   // <= 443 cells per CTA
+        const int c0 = min(ncells, (int)blockIdx.x * per), c1 = min(ncells, c0 + per);
+        int part = 0;
+        for (int i = tid; i < c0; i += NT) part += __ldcg(&m.cell_cnt[i]);
+        int before = block_sum(part, red);
+        for (int base = c0; base < c1; base += NT) {   // (one round on a 148-SM part: at most 443 cells per CTA)
+            const int i = base + tid;
+            const int v = i < c1 ? __ldcg(&m.cell_cnt[i]) : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += nb;
+            }
+            __syncthreads();
+            if (lane == 31) red[warp] = incl;
+            __syncthreads();
+            int wb = 0;
+            for (int w = 0; w < warp; ++w) wb += red[w];
+            if (i < c1) {
+                const int start = before + wb + incl - v;
+                m.cell_start[i] = start;
+                m.cell_end[i] = start + v;
+            }
+            for (int w = 0; w < NWARPS; ++w) before += red[w];
+        }
+    }
+    __threadfence();
+    grid.sync();
+    big_stamp(m.dbg, 3);
+    // ---- 3. keys to cell order (arrival order inside a cell) ----
+    for (int e = gtid; e < n; e += gstride) {
+        const int cell = m.cell_e[e];                       // (written by this very thread in phase 1)
+        const int k = __ldcg(&m.cell_start[cell]) + m.slot_e[e];
+        m.tmp_key[k] = m.key_e[e];
+        m.tmp_cell[k] = cell;
+    }
+    __threadfence();
+    grid.sync();
+    big_stamp(m.dbg, 4);
+    // ---- 4. key order inside every cell (position = number of smaller keys among the cell's members), cell-ordered boxes ----
+    for (int k = gtid; k < n; k += gstride) {
+        const int cell = __ldcg(&m.tmp_cell[k]);
+        const int cs = __ldcg(&m.cell_start[cell]), ce = __ldcg(&m.cell_end[cell]);
+        // (L1-cached loads: the threads of a cell read the same members, and no SM has read tmp_key through L1 before this phase)
+        const u64 mine = m.tmp_key[k];
+        int cnt = 0, j = cs;
+        for (; j + 3 < ce; j += 4) {
+            const u64 k0 = m.tmp_key[j], k1 = m.tmp_key[j + 1], k2 = m.tmp_key[j + 2], k3 = m.tmp_key[j + 3];
+            cnt += (k0 < mine) + (k1 < mine) + (k2 < mine) + (k3 < mine);
+        }
+        for (; j < ce; ++j) cnt += m.tmp_key[j] < mine;
+        const int pos = cs + cnt;
+        const float *p = m.dets + (size_t)(unsigned)mine * m.stride;
+        const float4 b = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+        m.ckey[pos] = mine;
+        m.cbox[pos] = b;
+        m.carea[pos] = box_area(b);
+    }
+    __threadfence();
+    grid.sync();
+    big_stamp(m.dbg, 5);
+    // ---- 5. predecessor lists ----
     {   // (box, neighbourhood row) tasks, row-major so a warp's lanes are consecutive cell-ordered boxes on the same row; warps take
         // 32 tasks at a time from a ticket (rows and cells differ in cost).  Measured at 100 000 boxes: one box per thread in
         // contiguous chunks 145 us, 256-box tiles dealt round-robin 124, whole boxes from a ticket 119, these row tasks 82;
@@ -1500,19 +1613,77 @@ __global__ void __launch_bounds__(NT, 1) nms_big_kernel(BigArgs m) {
             const int q = base + lane;
             if (q < tasks) {
                 const int row = q / n, k = q - row * n;
-                adjacency_row(k, row - 1, csorted, c, m.cell_start, m.cell_end, m.cbox, m.carea, m.ra.iou, const_cast<int *>(m.ra.adj), const_cast<int *>(m.ra.adj_cnt));
+                adjacency_row_k(k, row - 1, m.ckey, c, m.cell_start, m.cell_end, m.cbox, m.carea, m.ra.iou, const_cast<int *>(m.ra.adj), const_cast<int *>(m.ra.adj_cnt));
             }
         }
     }
     __threadfence();
     grid.sync();
-    big_stamp(m.dbg, 7);
-    // ---- 7. decision sweeps + ordered output as source indices ----
+    big_stamp(m.dbg, 6);
+    // ---- 6. decision sweeps; the kept boxes' keys come out in position order ----
     RoundsArgs ra = m.ra;
-    ra.keys = csorted;
-    ra.final_keys = sorted;
     ra.dbg = m.dbg ? m.dbg + 4 : nullptr;   // its stamps 5 / 6 land in slots 9 / 10
     nms_rounds_body(ra, c, dyn, red);
+    __threadfence();
+    grid.sync();
+    big_stamp(m.dbg, 7);
+    // ---- 7. the kept keys in key order = the reference's output order ----
+    const int M = __ldcg(&m.st[4]);
+    if (M <= KEPT_RANK_CAP) {   // rank = number of smaller kept keys: (row tile x key slice) items count partial ranks
+        const int rtiles = (M + NT - 1) / NT;
+        int slices = max(1, min((2 * G + max(rtiles, 1) - 1) / max(rtiles, 1), (M + 127) / 128));
+        const int per_slice = (((M + slices - 1) / slices) + 1) & ~1;
+        slices = per_slice > 0 ? (M + per_slice - 1) / per_slice : 0;
+        u64 *tile = reinterpret_cast<u64 *>(dyn);
+        for (int it = blockIdx.x; it < rtiles * slices; it += G) {
+            const int rt = it / slices, sl = it - rt * slices;
+            const int i = rt * NT + tid;
+            const u64 mine = i < M ? __ldcg(&m.kept_keys[i]) : ~0ull;
+            const int s0 = sl * per_slice, s1 = min(M, s0 + per_slice);
+            int cnt = 0;
+            for (int base = s0; base < s1; base += NT) {
+                __syncthreads();
+                tile[tid] = base + tid < s1 ? __ldcg(&m.kept_keys[base + tid]) : ~0ull;   // padding: never smaller
+                __syncthreads();
+                const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(tile);
+                const int pairs = (min(NT, s1 - base) + 1) >> 1;
+#pragma unroll 4
+                for (int j = 0; j < pairs; ++j) {   // warp-uniform (broadcast) 128-bit reads
+                    const ulonglong2 q = k2[j];
+                    cnt += (q.x < mine) ? 1 : 0;
+                    cnt += (q.y < mine) ? 1 : 0;
+                }
+            }
+            if (i < M && cnt) atomicAdd(&m.kept_rank[i], cnt);
+        }
+        __threadfence();
+        grid.sync();
+        for (int i = gtid; i < M; i += gstride) m.keep_dev[__ldcg(&m.kept_rank[i])] = (int)(unsigned)__ldcg(&m.kept_keys[i]);
+    } else {                    // very many kept boxes: LSD radix passes over the index bits, then the differing score bits
+        const int mt = (M + NT - 1) / NT;
+        const int ibits = n > 1 ? 32 - __clz(n - 1) : 0;
+        u64 *a = m.kept_keys, *b = m.tmp_key;
+        if (ibits > 0) {
+            cs_tile_hist([&](int e) { return __ldcg(a + e); }, M, 0, m.hist, mt, dyn);
+            __threadfence();
+            grid.sync();
+            u64 *r = cs_sort(a, b, M, 0, ibits, m.hist, mt, dyn, red);
+            if (r != a) { b = a; a = r; }
+        }
+        const unsigned diff = (~__ldcg(reinterpret_cast<unsigned *>(m.st) + 22)) ^ __ldcg(reinterpret_cast<unsigned *>(m.st) + 23);
+        const int nbits = (!m.presorted && diff) ? 32 - __clz(diff) : 0;
+        if (nbits > 0) {
+            cs_tile_hist([&](int e) { return __ldcg(a + e); }, M, 32, m.hist, mt, dyn);
+            __threadfence();
+            grid.sync();
+            a = cs_sort(a, b, M, 32, nbits, m.hist, mt, dyn, red);
+        }
+        for (int i = gtid; i < M; i += gstride) m.keep_dev[i] = (int)(unsigned)__ldcg(a + i);
+    }
+    if (gtid == 0) {
+        m.num_keep_dev[0] = M;
+        m.num_keep_dev[1] = __ldcg(&m.st[0]);
+    }
     big_stamp(m.dbg, 8);
 }
 
@@ -1707,6 +1878,8 @@ static int nms_big_impl(fd_ctx *ctx, const u64 *keys_in, const int *key_bytes, i
         ra.adj_smem = ADJ_SMEM;
         ra.seg3 = 0;
         ra.adj_stride = ADJ_CAP;
+        ra.kspace = 0;
+        ra.kept_keys = nullptr;
         void *rargs[] = {&ra};
         int per_sm_r = 0;
         const size_t smem_r = sizeof(int) * (size_t)ADJ_SMEM * NT;
@@ -1787,6 +1960,8 @@ static int nms_mid_impl(fd_ctx *ctx, const float *boxes, int K, int stride, cons
     ra.adj_smem = ADJ_SMEM;
     ra.seg3 = 0;
     ra.adj_stride = ADJ_CAP;
+    ra.kspace = 0;
+    ra.kept_keys = nullptr;
     ra.final_keep = keep_dev;
     ra.final_keys = m.sorted;
     ra.final_num = num_keep_dev;
@@ -1833,8 +2008,8 @@ static int nms_big_one_launch(fd_ctx *ctx, const float *boxes, int K, int stride
     FD_TRY(ctx->nms_ws[5].reserve(sizeof(float4) * HEAD + sizeof(int) * (size_t)ntiles * 33 + 64));
     FD_TRY(ctx->nms_ws[6].reserve(sizeof(int) * 32));
     FD_TRY(ctx->nms_ws_sp[0].reserve(sizeof(u64) * (size_t)K * 2));
-    FD_TRY(ctx->nms_ws_sp[1].reserve(sizeof(int) * (size_t)(GRID_MAX_CELLS + 1) * 2));
-    FD_TRY(ctx->nms_ws_sp[2].reserve((sizeof(float4) + sizeof(float) + sizeof(int) * 4) * (size_t)K + (size_t)K + 16));   // cbox, carea, pos, 3 counters, state
+    FD_TRY(ctx->nms_ws_sp[1].reserve(sizeof(int) * (size_t)(GRID_MAX_CELLS + 1) * 3));                                       // cell counts, starts, ends
+    FD_TRY(ctx->nms_ws_sp[2].reserve((sizeof(float4) + sizeof(float) + sizeof(int) * 4) * (size_t)K + (size_t)K + 16));   // cbox, carea, tmp cell, 3 counters, state
     FD_TRY(ctx->nms_ws_sp[3].reserve(sizeof(int) * (size_t)K * ADJ_ROW3));
     int *st = ctx->nms_ws[6].as<int>();
     FD_CUDA(cudaMemsetAsync(st, 0, sizeof(int) * 32, ctx->stream));
@@ -1845,31 +2020,36 @@ static int nms_big_one_launch(fd_ctx *ctx, const float *boxes, int K, int stride
     m.stride = stride;
     m.presorted = presorted ? 1 : 0;
     m.mode = mode;
-    m.ka = ctx->nms_ws[0].as<u64>();
-    m.kb = ctx->nms_ws[1].as<u64>();
-    m.cka = ctx->nms_ws_sp[0].as<u64>();
-    m.ckb = m.cka + K;
+    m.key_e = ctx->nms_ws[0].as<u64>();
+    m.tmp_key = ctx->nms_ws[1].as<u64>();
+    m.ckey = ctx->nms_ws_sp[0].as<u64>();
+    m.kept_keys = m.ckey + K;
     m.hist = ctx->nms_ws[2].as<int>();
     m.sbox = ctx->nms_ws[3].as<float4>();
     m.st = st;
-    m.cell_start = ctx->nms_ws_sp[1].as<int>();
+    m.cell_cnt = ctx->nms_ws_sp[1].as<int>();
+    m.cell_start = m.cell_cnt + (GRID_MAX_CELLS + 1);
     m.cell_end = m.cell_start + (GRID_MAX_CELLS + 1);
     m.cbox = ctx->nms_ws_sp[2].as<float4>();
     m.carea = reinterpret_cast<float *>(m.cbox + K);
-    m.pos_of_rank = reinterpret_cast<int *>(m.carea + K);
-    int *adj_cnt = m.pos_of_rank + K;
+    m.tmp_cell = reinterpret_cast<int *>(m.carea + K);
+    int *adj_cnt = m.tmp_cell + K;
     float4 *ks = ctx->nms_ws[5].as<float4>();
     int *tile_counts = reinterpret_cast<int *>(ks + HEAD);
     unsigned *ballots = reinterpret_cast<unsigned *>(tile_counts + ntiles);
     int *stream_a = ctx->nms_ws[4].as<int>(), *stream_b = stream_a + K, *keep_ranks = stream_b + K;
+    m.cell_e = stream_a;        // (the peel's streams and kept ranks: the grid path and the peel exclude each other)
+    m.slot_e = stream_b;
+    m.kept_rank = keep_ranks;
     RoundsArgs &ra = m.ra;
     ra.N = K;
+    ra.keys = m.ckey;
     ra.cfg = reinterpret_cast<GridCfg *>(st + 16);
     ra.cell_start = m.cell_start;
     ra.cell_end = m.cell_end;
     ra.cbox = m.cbox;
     ra.carea = m.carea;
-    ra.pos_of_rank = m.pos_of_rank;
+    ra.pos_of_rank = nullptr;
     ra.adj = ctx->nms_ws_sp[3].as<int>();
     ra.adj_cnt = adj_cnt;
     ra.state = reinterpret_cast<unsigned char *>(adj_cnt + (size_t)3 * K);
@@ -1887,8 +2067,11 @@ static int nms_big_one_launch(fd_ctx *ctx, const float *boxes, int K, int stride
     ra.adj_smem = adj_smem;
     ra.seg3 = 1;
     ra.adj_stride = ADJ_ROW3;
-    ra.final_keep = keep_dev;
-    ra.final_num = num_keep_dev;
+    ra.kspace = 1;
+    ra.kept_keys = m.kept_keys;
+    ra.final_keep = nullptr;
+    ra.final_keys = m.ckey;
+    ra.final_num = nullptr;
     PeelArgs &pa = m.pa;
     pa.sbox = m.sbox;
     pa.N = K;
@@ -1923,9 +2106,10 @@ static int nms_big_one_launch(fd_ctx *ctx, const float *boxes, int K, int stride
         cudaStreamSynchronize(ctx->stream);
         cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
         cudaMemcpy(sth, st, sizeof(sth), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[nms big dbg] K=%d grid=%d spatial=%d: keys+stats %.1f  sort %.1f  boxes+cells %.1f  cell sort %.1f  bounds %.1f  lists %.1f  sweeps %.1f  output %.1f (epochs %d, rescanning boxes %d) us, total %.1f\n",
-                K, ctx->num_sms * per_sm, sth[3], (h[1] - h[0]) * 1e-3, (h[2] - h[1]) * 1e-3, (h[3] - h[2]) * 1e-3,
-                (h[5] - h[4]) * 1e-3, (h[6] - h[5]) * 1e-3, (h[7] - h[6]) * 1e-3, (h[9] - h[7]) * 1e-3, (h[8] - h[9]) * 1e-3, sth[6], sth[7], (h[8] - h[0]) * 1e-3);
+        fprintf(stderr, "[nms big dbg] K=%d grid=%d spatial=%d: keys+stats %.1f  cells %.1f  scan %.1f  scatter %.1f  order %.1f  lists %.1f  sweeps %.1f  output %.1f  kept order %.1f (epochs %d, rescanning boxes %d) us, total %.1f\n",
+                K, ctx->num_sms * per_sm, sth[3], (h[1] - h[0]) * 1e-3, (h[2] - h[1]) * 1e-3, (h[3] - h[2]) * 1e-3, (h[4] - h[3]) * 1e-3,
+                (h[5] - h[4]) * 1e-3, (h[6] - h[5]) * 1e-3, (h[9] - h[6]) * 1e-3, (h[7] - h[9]) * 1e-3, (h[8] - h[7]) * 1e-3, sth[6], sth[7],
+                (h[8] - h[0]) * 1e-3);
     }
     return FD_OK;
 }
