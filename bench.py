@@ -780,7 +780,7 @@ def run_ours(args):
         nms_extra = {"nms_100k_us": med, "nms_100k_kept": int(len(keep)), "nms_100k_p10_us": float(np.percentile(times, 10)),
                      "nms_100k_p90_us": float(np.percentile(times, 90)), "nms_100k_samples": len(times),
                      "nms_100k_pairs_evaluated": pairs, "nms_100k_gpairs_per_s": pairs / (med * 1e-6) / 1e9,
-                     "nms_100k_note": "device-resident dets, sort included, IoU 0.4; median of %d launches after 10 warm-up; pairs = the IoU "
+                     "nms_100k_note": "device-resident dets, score ordering included, IoU 0.4; median of %d launches after 10 warm-up; pairs = the IoU "
                                       "evaluations of the reference's greedy loop (sum over kept boxes of the boxes still alive), the algorithmic "
                                       "work SURVEY 8(d) names; the spatial path evaluates far fewer" % len(times)}
         try:

@@ -17,8 +17,10 @@
 //   K <= 4096 : one CTA does sort + greedy out of shared memory — per image of a batch (fused detect kernel, nms_batch_*).
 //   ONE problem of 1024 < K <= 12288 boxes (fd_nms / fd_nms_device): nms_mid_kernel, a single cooperative launch over all SMs —
 //               rank sort, brute-force predecessor lists, the decision sweeps below (72 us at 4 096 boxes, was 178).
-//   beyond    : LSD radix sort (own kernels) + spatially binned exact NMS (predecessor lists + decision sweeps in one
-//               cooperative kernel), or the cooperative multi-CTA peel for degenerate inputs.
+//   beyond    : nms_big_kernel, ONE cooperative launch: spatially binned exact NMS without a global sort (boxes binned by cell,
+//               ordered inside cells only, predecessor lists + decision sweeps over cell-order positions, kept keys ordered at
+//               the end), or — same launch — a radix sort + the cooperative multi-CTA peel for degenerate inputs.  The round-1
+//               sequence of one kernel per step stays behind FD_NMS_MULTI_KERNEL=1 (A/B reference).
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
@@ -484,8 +486,11 @@ __global__ void __launch_bounds__(NT, 1) nms_peel_kernel(PeelArgs a) {
 // ============================================================================================================
 constexpr int ADJ_CAP = 96;      // listed predecessors per box (global memory)
 constexpr int ADJ_SMEM = 32;     // of which the first are cached in shared memory across sweeps
-constexpr int ADJ_SEG = 64;      // one-launch path: a box's list is three segments of this capacity, one per neighbourhood row (three tasks)
-constexpr int ADJ_ROW3 = 3 * ADJ_SEG;   // ... so its row is 192 ints (the own-row segment of a box in a dense spot overflowed 32 and fell back to rescans)
+constexpr int ADJ_SEG = 64;      // one-launch path: a box's list is three segments of this capacity, one per neighbourhood row (three tasks):
+constexpr int ADJ_ROW3 = 3 * ADJ_SEG;   // the first suppressing predecessors of every row.  When all listed ones end up suppressed and there were
+                                        // more, the list is refilled (exact; ~40 us each, so the capacity is chosen to make refills rare: at
+                                        // 100 000 crowd boxes 16 per row -> 207 boxes overflow and the sweeps take 796 us, 32 -> 5 refills, 77 us,
+                                        // 64 -> none, 34 us)
 constexpr int GRID_MAX_CELLS = 65535;
 constexpr int GRID_MAX_DIM = 4096;
 
@@ -743,9 +748,9 @@ __device__ __forceinline__ void adjacency_row_k(int k, int dy, const u64 *__rest
     for_each_predecessor_k(k, ckey, c, cell_start, cell_end, cbox, carea, P, [&](int j) {
         if (cnt < ADJ_SEG) mine[cnt] = j;
         ++cnt;
-        return true;
+        return cnt <= ADJ_SEG;   // one past the capacity is all the sweeps need to know: stop enumerating
     }, dy, dy);
-    cnt3[k * 3 + dy + 1] = cnt;   // may exceed ADJ_SEG: the first ADJ_SEG are listed
+    cnt3[k * 3 + dy + 1] = cnt;   // ADJ_SEG + 1: more than the segment lists
 }
 
 __global__ void __launch_bounds__(256) adjacency_kernel(const u64 *__restrict__ keys, int N, const GridCfg *cfg,
@@ -876,7 +881,7 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
     // ---- prologue: every box's list becomes one compact run of PENDING predecessors (only the listed ones; `overflow` says
     //      there are more) — the resident box of this thread keeps the head of its run in shared memory and the count in a
     //      register, the others (N beyond the resident threads) keep both in global memory: adj_cnt[first counter] = count |
-    //      overflow << 30, or -1 once the box has fallen back to rescanning its neighbourhood.
+    //      overflow << 30.
     const int cstep = a.seg3 ? 3 : 1;
     int *const acnt = const_cast<int *>(a.adj_cnt);
     int *const mine0 = const_cast<int *>(a.adj) + (size_t)min(gtid, max(a.N - 1, 0)) * a.adj_stride;   // this thread's resident box
@@ -886,7 +891,7 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
         else mine0[e] = v;
     };
     int pend = 0;
-    bool overflow = false, rescan = false;
+    bool overflow = false;
     for (int r = gtid; r < a.N; r += gstride) {
         int *row = const_cast<int *>(a.adj) + (size_t)r * a.adj_stride;
         const int4 *row4 = reinterpret_cast<const int4 *>(row);
@@ -894,18 +899,14 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
         int total = 0;
         bool ov = false;
         if (a.seg3) {   // gather the three row segments (typical segment: a few entries, so the three first loads overlap)
+            static_assert(ADJ_SEG % 16 == 0, "the gather below loads a segment four 128-bit words at a time");
             int cs[3];
-            int4 first[3];
 #pragma unroll
             for (int sg = 0; sg < 3; ++sg) {
                 const int cr = __ldcg(&acnt[r * 3 + sg]);
                 ov |= cr > ADJ_SEG;
                 cs[sg] = min(cr, ADJ_SEG);
-                first[sg] = make_int4(0, 0, 0, 0);
             }
-#pragma unroll
-            for (int sg = 0; sg < 3; ++sg)
-                if (cs[sg] > 0) first[sg] = __ldcg(row4 + sg * (ADJ_SEG / 4));
             int w = 0;
             auto put = [&](int v) {   // w <= the position being read: the gather never overwrites what it has not read
                 if (res) put0(w, v);
@@ -914,12 +915,19 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
             };
 #pragma unroll
             for (int sg = 0; sg < 3; ++sg) {
-                for (int i = 0; i < cs[sg]; i += 4) {
-                    const int4 q = i == 0 ? first[sg] : __ldcg(row4 + sg * (ADJ_SEG / 4) + (i >> 2));
-                    put(q.x);
-                    if (i + 1 < cs[sg]) put(q.y);
-                    if (i + 2 < cs[sg]) put(q.z);
-                    if (i + 3 < cs[sg]) put(q.w);
+                for (int g = 0; g * 16 < cs[sg]; ++g) {
+                    int4 q[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)   // in flight together
+                        q[u] = 16 * g + 4 * u < cs[sg] ? __ldcg(row4 + sg * (ADJ_SEG / 4) + 4 * g + u) : make_int4(0, 0, 0, 0);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = 16 * g + 4 * u;
+                        if (i < cs[sg]) put(q[u].x);
+                        if (i + 1 < cs[sg]) put(q[u].y);
+                        if (i + 2 < cs[sg]) put(q[u].z);
+                        if (i + 3 < cs[sg]) put(q[u].w);
+                    }
                 }
             }
             total = w;
@@ -939,20 +947,31 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
         if (res) { pend = total; overflow = ov; }
         else acnt[r * cstep] = total | (ov ? (1 << 30) : 0);
     }
-    // A box whose listed predecessors are all suppressed but which has more than the list holds rescans its neighbourhood from
-    // then on (exact, slow, rare: by then one of so many predecessors has almost always been kept).
-    auto decide_rescan = [&](int r) {
-        bool any_kept = false, all_sup = true;
-        auto visit = [&](int rj) {
-            const unsigned sj = ld_state(a.state + rj);
+    // A box whose listed predecessors are all suppressed but which has more than the list holds REFILLS its list: it walks its
+    // neighbourhood once more, is suppressed if it meets a kept predecessor, and lists the next undecided ones (the suppressed
+    // ones, among them everything it has listed before, are final and skipped).  Exact, and rare: by then one of so many
+    // predecessors has almost always been kept.  Returns the decision; pn / ov become the new list length and overflow flag.
+    auto refill = [&](int r, auto put, int &pn, bool &ov) -> int {
+        bool any_kept = false, more = false;
+        int w = 0;
+        auto visit = [&](int j) {
+            const unsigned sj = ld_state(a.state + j);
             if (sj == 1u) { any_kept = true; return false; }
-            if (sj == 0u) all_sup = false;
+            if (sj == 0u) {
+                if (w >= a.adj_stride) { more = true; return false; }
+                put(w, j);
+                ++w;
+            }
             return true;
         };
         if (a.brute) for_each_earlier(r, a.sbox, a.iou, bfast, a.mode, visit);
         else if (a.kspace) for_each_predecessor_k(r, a.keys, c, a.cell_start, a.cell_end, a.cbox, a.carea, a.iou, visit);
         else for_each_predecessor(a.pos_of_rank[r], a.keys, c, a.cell_start, a.cell_end, a.cbox, a.carea, a.iou, visit);
-        return any_kept ? 2 : (all_sup ? 1 : 0);
+        atomicAdd(&a.out_state[4], 1);   // statistics: list refills
+        if (any_kept) return 2;
+        pn = w;
+        ov = more;
+        return w == 0 ? 1 : 0;
     };
     bool first_done = gtid >= a.N;
     for (int epoch = 0;; ++epoch) {
@@ -961,37 +980,21 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
             undecided = 0;
             const bool nothing_yet = epoch == 0 && sweep == 0;   // no box is decided yet: polling would read zeros
             if (!first_done) {
-                int d;
-                if (rescan) d = decide_rescan(gtid);
-                else {
-                    d = pend == 0 ? 1 : (nothing_yet ? 0 : decide_pending(pend, get0, put0, a.state));
-                    if (d == 1 && overflow) {
-                        d = 0;
-                        rescan = true;
-                        atomicAdd(&a.out_state[4], 1);   // statistics: boxes that had to rescan
-                    }
-                }
+                int d = pend == 0 ? 1 : (nothing_yet ? 0 : decide_pending(pend, get0, put0, a.state));
+                if (d == 1 && overflow) d = refill(gtid, put0, pend, overflow);
                 if (d) { state[gtid] = (unsigned char)d; first_done = true; }
                 else ++undecided;
             }
             for (int r = gtid + gstride; r < a.N; r += gstride) {  // only when N exceeds the resident thread count
                 if (state[r] != 0) continue;
                 const int v = __ldcg(&acnt[r * cstep]);
-                int d;
-                if (v < 0) d = decide_rescan(r);
-                else {
-                    int pn = v & 0x3fffffff;
-                    const bool ov = (v >> 30) & 1;
-                    int *row = const_cast<int *>(a.adj) + (size_t)r * a.adj_stride;
-                    d = pn == 0 ? 1 : (nothing_yet ? 0 : decide_pending(pn, [&](int e) { return __ldcg(row + e); }, [&](int e, int x) { row[e] = x; }, a.state));
-                    if (d == 1 && ov) {
-                        d = 0;
-                        acnt[r * cstep] = -1;
-                        atomicAdd(&a.out_state[4], 1);
-                    } else if (d == 0 && !nothing_yet) {
-                        acnt[r * cstep] = pn | (ov ? (1 << 30) : 0);
-                    }
-                }
+                int pn = v & 0x3fffffff;
+                bool ov = (v >> 30) & 1;
+                int *row = const_cast<int *>(a.adj) + (size_t)r * a.adj_stride;
+                auto putr = [&](int e, int x) { row[e] = x; };
+                int d = pn == 0 ? 1 : (nothing_yet ? 0 : decide_pending(pn, [&](int e) { return __ldcg(row + e); }, putr, a.state));
+                if (d == 1 && ov) d = refill(r, putr, pn, ov);
+                if (d == 0 && !nothing_yet) acnt[r * cstep] = pn | (ov ? (1 << 30) : 0);
                 if (d) state[r] = (unsigned char)d;
                 else ++undecided;
             }
@@ -1215,14 +1218,18 @@ __global__ void __launch_bounds__(NT, 1) nms_mid_kernel(MidArgs m) {
 
 // ---- big path in one launch -------------------------------------------------------------------------------------------
 // The spatial path used to be ~25 stream operations (two radix sorts of one kernel per 8-bit pass, nine small kernels, six
-// memsets): at 100 000 boxes two thirds of its 332 us were launch gaps and latency-bound 25-CTA radix passes.  nms_big_kernel
-// runs the same algorithm as ONE cooperative kernel, phases separated by grid-wide barriers:
-//   0  keys (score desc | index), NaN flag, the OR / NAND of all score keys (which key bits differ at all), first digit histogram;
-//   1  LSD radix sort, 9-bit digits over the differing bits only (scores in [0.02, 1) differ in 26 bits: 3 passes), every SM busy:
-//      tiles of 1024 keys, per-(digit, tile) counts -> row scans -> stable scatter that also counts the next pass's digits;
-//   2  boxes in rank order + grid statistics;  3  grid geometry (every CTA, identically), cell keys;  4  cell sort (same code);
-//   5  cell bounds + cell-ordered boxes;  6  predecessor lists;  7  decision sweeps + ordered output (nms_rounds_body).
-// When the grid does not apply (irregular boxes, degenerate thresholds, too crowded) the same launch runs the peel instead.
+// memsets): at 100 000 boxes two thirds of its 332 us were launch gaps and latency-bound 25-CTA radix passes.  nms_big_kernel is
+// ONE cooperative kernel, phases separated by grid-wide barriers, and it never sorts the boxes globally:
+//   0  keys (score desc | index) by source index, NaN / regularity flags, grid statistics, the OR / NAND of all score keys;
+//   1  grid geometry (every CTA, identically); cell of every box and its arrival slot there (atomicAdd);
+//   2  cell bounds: scan of the counts;   3  keys to cell order;
+//   4  key order inside every cell by counting smaller members; cell-ordered boxes and areas;
+//   5  predecessor lists over cell-order positions ("earlier-ranked" = a key comparison);
+//   6  decision sweeps (nms_rounds_body) -> the kept boxes' keys, unordered;
+//   7  the kept keys ordered by all-pairs counting (radix passes when there are very many) = the reference's output order.
+// When the grid does not apply (irregular boxes, degenerate thresholds, too crowded) the same launch sorts globally with the
+// cooperative LSD radix sort below (9-bit digits over the differing key bits, tiles of 1024 keys, per-(digit, tile) counts ->
+// row scans -> stable scatter that also counts the next pass's digits) and runs the peel.
 constexpr int CS_BITS = 9;
 constexpr int CS_D = 1 << CS_BITS;
 constexpr size_t CS_SMEM = sizeof(int) * (size_t)(2 + NWARPS) * CS_D;
@@ -2106,7 +2113,7 @@ static int nms_big_one_launch(fd_ctx *ctx, const float *boxes, int K, int stride
         cudaStreamSynchronize(ctx->stream);
         cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
         cudaMemcpy(sth, st, sizeof(sth), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[nms big dbg] K=%d grid=%d spatial=%d: keys+stats %.1f  cells %.1f  scan %.1f  scatter %.1f  order %.1f  lists %.1f  sweeps %.1f  output %.1f  kept order %.1f (epochs %d, rescanning boxes %d) us, total %.1f\n",
+        fprintf(stderr, "[nms big dbg] K=%d grid=%d spatial=%d: keys+stats %.1f  cells %.1f  scan %.1f  scatter %.1f  order %.1f  lists %.1f  sweeps %.1f  output %.1f  kept order %.1f (epochs %d, list refills %d) us, total %.1f\n",
                 K, ctx->num_sms * per_sm, sth[3], (h[1] - h[0]) * 1e-3, (h[2] - h[1]) * 1e-3, (h[3] - h[2]) * 1e-3, (h[4] - h[3]) * 1e-3,
                 (h[5] - h[4]) * 1e-3, (h[6] - h[5]) * 1e-3, (h[9] - h[6]) * 1e-3, (h[7] - h[9]) * 1e-3, (h[8] - h[7]) * 1e-3, sth[6], sth[7],
                 (h[8] - h[0]) * 1e-3);

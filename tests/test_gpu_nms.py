@@ -221,6 +221,9 @@ def test_one_launch_big_path_behind_the_switch():
             "    np.testing.assert_array_equal(c.cpu_nms(d, 0.3), O.cpu_nms(d, 0.3))\n"
             "d = synth.make_crowd_boxes(200000, seed=4, n_faces=10000)\n"          # more tiles than CTAs
             "np.testing.assert_array_equal(c.nms(d, 0.4), O.nms(d, 0.4))\n"
+            "d = synth.make_crowd_boxes(30000, seed=9, n_faces=100)\n"           # 300 candidates per face: every list overflows
+            "np.testing.assert_array_equal(c.nms(d, 0.4), O.nms(d, 0.4))\n"
+            "np.testing.assert_array_equal(c.cpu_nms(d, 0.5), O.cpu_nms(d, 0.5))\n"
             "d = _random_dets(6000, 78, canvas=900); d[::13, 2] = d[::13, 0] - 1.0\n"   # zero-width boxes: not 'fast' -> peel
             "for thr in (0.4, -1.0, 1.5):\n"
             "    np.testing.assert_array_equal(c.nms(d, thr), O.nms(d, thr))\n"
