@@ -15,7 +15,7 @@
 //   K <= 1024 : barrier-light single-CTA path (fd_nms_tiny.cuh: register bitonic sort, warp-resolved mini-heads of 32);
 //               the batched pipeline runs the same code inside the fused detect kernel (fd_detect_fused.cu).
 //   K <= 4096 : one CTA does sort + greedy out of shared memory — per image of a batch (fused detect kernel, nms_batch_*).
-//   ONE problem of 1024 < K <= 12288 boxes (fd_nms / fd_nms_device): nms_mid_kernel, a single cooperative launch over all SMs —
+//   ONE problem of 1024 < K <= 8192 boxes (fd_nms / fd_nms_device): nms_mid_kernel, a single cooperative launch over all SMs —
 //               rank sort, brute-force predecessor lists, the decision sweeps below (72 us at 4 096 boxes, was 178).
 //   beyond    : nms_big_kernel, ONE cooperative launch: spatially binned exact NMS without a global sort (boxes binned by cell,
 //               ordered inside cells only, predecessor lists + decision sweeps over cell-order positions, kept keys ordered at
@@ -1093,7 +1093,8 @@ __global__ void __launch_bounds__(NT, 1) nms_rounds_kernel(RoundsArgs a) {
 //      (8.4 M at 4 096 boxes);
 //   3  the spatial path's decision sweeps over those lists (nms_rounds_body; a box with more predecessors than a list holds
 //      rescans every earlier box) and its ordered output, written straight as source indices.
-constexpr int MID_CAP = 12288;    // measured against the spatial path: 107 vs 196 us at 8 192 boxes, 178 vs 200 at 12 288, 263 vs 212 at 16 384
+constexpr int MID_CAP = 8192;     // measured against nms_big_kernel (host timer): 65.6 vs 83.6 us at 4 096 boxes, 82.0 vs 89.4 at 6 000, 94.3 vs 95.6 at
+                                  // 8 192, 166.8 vs 96.0 at 12 288 (against the round-1 launch sequence the crossover was 12 288)
 constexpr int MID_CW = 64;        // column tile of phase 2
 
 struct MidArgs {
