@@ -982,7 +982,11 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
             if (!first_done) {
                 int d = pend == 0 ? 1 : (nothing_yet ? 0 : decide_pending(pend, get0, put0, a.state));
                 if (d == 1 && overflow) d = refill(gtid, put0, pend, overflow);
-                if (d) { state[gtid] = (unsigned char)d; first_done = true; }
+                if (d) {
+                    state[gtid] = (unsigned char)d;
+                    first_done = true;
+                    if (d == 1 && a.kept_keys) a.kept_keys[atomicAdd(&a.out_state[1], 1)] = __ldcg(&a.final_keys[gtid]);   // (the caller orders them)
+                }
                 else ++undecided;
             }
             for (int r = gtid + gstride; r < a.N; r += gstride) {  // only when N exceeds the resident thread count
@@ -995,8 +999,10 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
                 int d = pn == 0 ? 1 : (nothing_yet ? 0 : decide_pending(pn, [&](int e) { return __ldcg(row + e); }, putr, a.state));
                 if (d == 1 && ov) d = refill(r, putr, pn, ov);
                 if (d == 0 && !nothing_yet) acnt[r * cstep] = pn | (ov ? (1 << 30) : 0);
-                if (d) state[r] = (unsigned char)d;
-                else ++undecided;
+                if (d) {
+                    state[r] = (unsigned char)d;
+                    if (d == 1 && a.kept_keys) a.kept_keys[atomicAdd(&a.out_state[1], 1)] = __ldcg(&a.final_keys[r]);
+                } else ++undecided;
             }
             // Warps sweep at their own pace — no CTA barrier in here, so a warp with short lists advances one dependency link per
             // L2 round trip instead of per (barrier + slowest thread of the CTA).  Measured at 100 000 boxes: CTA-wide sweeps 46 us,
@@ -1015,18 +1021,7 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
         if (left == 0) break;
     }
     mid_stamp(a.dbg, 5);
-    if (a.kept_keys) {   // the caller orders the kept keys itself: any order will do here, one atomic per warp
-        for (int r = gtid; r < a.N; r += gstride) {
-            const bool flag = state[r] == 1;
-            const unsigned bal = __ballot_sync(__activemask(), flag);
-            if (flag) {
-                const int leader = __ffs(bal) - 1;
-                int base = 0;
-                if (lane == leader) base = atomicAdd(&a.out_state[1], __popc(bal));
-                base = __shfl_sync(bal, base, leader);
-                a.kept_keys[base + __popc(bal & ((1u << lane) - 1u))] = __ldcg(&a.final_keys[r]);
-            }
-        }
+    if (a.kept_keys) {   // every kept box appended its key when it was decided; the epoch's last grid-wide barrier published them
         mid_stamp(a.dbg, 6);
         return;
     }
@@ -1631,15 +1626,13 @@ __global__ void __launch_bounds__(NT, 1) nms_big_kernel(BigArgs m) {
     // ---- 6. decision sweeps; the kept boxes' keys come out in position order ----
     RoundsArgs ra = m.ra;
     ra.dbg = m.dbg ? m.dbg + 4 : nullptr;   // its stamps 5 / 6 land in slots 9 / 10
-    nms_rounds_body(ra, c, dyn, red);
-    __threadfence();
-    grid.sync();
+    nms_rounds_body(ra, c, dyn, red);   // (ends behind the grid-wide barrier of its last epoch: kept keys and their count are visible)
     big_stamp(m.dbg, 7);
     // ---- 7. the kept keys in key order = the reference's output order ----
     const int M = __ldcg(&m.st[4]);
     if (M <= KEPT_RANK_CAP) {   // rank = number of smaller kept keys: (row tile x key slice) items count partial ranks
         const int rtiles = (M + NT - 1) / NT;
-        int slices = max(1, min((2 * G + max(rtiles, 1) - 1) / max(rtiles, 1), (M + 127) / 128));
+        int slices = max(1, min(G / max(rtiles, 1), (M + 127) / 128));   // one item per CTA where possible
         const int per_slice = (((M + slices - 1) / slices) + 1) & ~1;
         slices = per_slice > 0 ? (M + per_slice - 1) / per_slice : 0;
         u64 *tile = reinterpret_cast<u64 *>(dyn);
