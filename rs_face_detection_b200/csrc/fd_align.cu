@@ -604,8 +604,9 @@ int warp_launch(fd_ctx *ctx, const FrameDev *frames_dev, const int32_t *frame_id
         // 14-row items (8 per face, 7 rounds per thread as 4 + 3): small enough that the last items of a launch leave
         // no long tail (28 rows: +10 % time), large enough to amortise the per-item setup (8 rows: same time, 4: +8 %).
         // 4 rounds in flight per thread (72 registers, 4 CTAs/SM); 2, 3 measure the same, 7 (104 registers) is 35 % slower.
-        constexpr int IR = 14;
-        void (*kern)(WarpArgs) = warp_fixed_kernel<112, 112, IR, 4>;
+        static const int ir_env = getenv("FD_WARP_IR") ? atoi(getenv("FD_WARP_IR")) : 14;   // A/B: 16-row items (7 per face, 8 rounds as 4 + 4): 82.0 vs 78.8 us on C2
+        const int IR = ir_env == 16 ? 16 : 14;
+        void (*kern)(WarpArgs) = IR == 16 ? warp_fixed_kernel<112, 112, 16, 4> : warp_fixed_kernel<112, 112, 14, 4>;
         static int per_sm_fixed = 0;
         if (!per_sm_fixed) FD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fixed, kern, 224, 0));
         const long long items = (long long)F_cap * (112 / IR);
