@@ -810,6 +810,15 @@ __device__ __forceinline__ void mid_stamp(long long *dbg, int slot) {
     }
 }
 
+// FD_NMS_DBG: the latest time any CTA passes a point (slot of the globaltimer stamps)
+__device__ __forceinline__ void max_stamp(long long *dbg, int slot) {
+    if (dbg && threadIdx.x == 0) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMax(reinterpret_cast<unsigned long long *>(dbg) + slot, (unsigned long long)t);
+    }
+}
+
 constexpr int ROUND_SWEEPS = 24;   // sweeps of a warp between two grid-wide checks
 
 // brute-mode stand-in for for_each_predecessor: every earlier box that suppresses box r
@@ -892,7 +901,49 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
     };
     int pend = 0;
     bool overflow = false;
-    for (int r = gtid; r < a.N; r += gstride) {
+    // Resident box, segmented lists: the segments are consumed LAZILY, up to 8 entries of each at a time (six 128-bit loads in
+    // flight together), whenever the pending list runs empty.  Loading every list completely up front cost 15 us at 100 000
+    // boxes — as long as the longest list took — although a box with a long list is almost always suppressed by one of its
+    // first entries.  At most 24 entries are pending, so the list lives in shared memory and never touches the row again
+    // (whose segments still hold what has not been loaded).  segc / segd: listed / loaded entries per segment, 8 bits each.
+    unsigned segc = 0, segd = 0;
+    auto load_more = [&]() -> bool {
+        const int4 *row4 = reinterpret_cast<const int4 *>(mine0);
+        int4 q[3][2];
+        int rem[3];
+#pragma unroll
+        for (int sg = 0; sg < 3; ++sg) {
+            const int cnt = (segc >> (8 * sg)) & 255, dn = (segd >> (8 * sg)) & 255;
+            rem[sg] = min(cnt - dn, 8);
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                q[sg][u] = 4 * u < rem[sg] ? __ldcg(row4 + sg * (ADJ_SEG / 4) + (dn >> 2) + u) : make_int4(0, 0, 0, 0);
+        }
+        bool any = false;
+#pragma unroll
+        for (int sg = 0; sg < 3; ++sg) {
+            const int rm = rem[sg];
+            if (rm <= 0) continue;
+            any = true;
+            const int v[8] = {q[sg][0].x, q[sg][0].y, q[sg][0].z, q[sg][0].w, q[sg][1].x, q[sg][1].y, q[sg][1].z, q[sg][1].w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < rm) sadj[(pend++) * NT + tid] = v[i];
+            segd += (unsigned)rm << (8 * sg);
+        }
+        return any;
+    };
+    const bool lazy = a.seg3 && a.adj_smem >= 24;
+    if (lazy && gtid < a.N) {
+#pragma unroll
+        for (int sg = 0; sg < 3; ++sg) {
+            const int cr = __ldcg(&acnt[gtid * 3 + sg]);
+            overflow |= cr > ADJ_SEG;
+            segc |= (unsigned)min(cr, ADJ_SEG) << (8 * sg);
+        }
+        load_more();
+    }
+    for (int r = gtid + (lazy ? gstride : 0); r < a.N; r += gstride) {
         int *row = const_cast<int *>(a.adj) + (size_t)r * a.adj_stride;
         const int4 *row4 = reinterpret_cast<const int4 *>(row);
         const bool res = r == gtid;
@@ -973,6 +1024,8 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
         ov = more;
         return w == 0 ? 1 : 0;
     };
+    __syncthreads();
+    max_stamp(a.dbg, 7);    // (slot 11 of the one-launch kernel's timeline: every CTA has loaded its lists)
     bool first_done = gtid >= a.N;
     for (int epoch = 0;; ++epoch) {
         int undecided = 0;
@@ -981,7 +1034,8 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
             const bool nothing_yet = epoch == 0 && sweep == 0;   // no box is decided yet: polling would read zeros
             if (!first_done) {
                 int d = pend == 0 ? 1 : (nothing_yet ? 0 : decide_pending(pend, get0, put0, a.state));
-                if (d == 1 && overflow) d = refill(gtid, put0, pend, overflow);
+                if (d == 1 && lazy && load_more()) d = 0;   // the listed predecessors seen so far are all suppressed: on to the next ones
+                else if (d == 1 && overflow) d = refill(gtid, put0, pend, overflow);
                 if (d) {
                     state[gtid] = (unsigned char)d;
                     first_done = true;
@@ -1010,6 +1064,7 @@ __device__ __forceinline__ void nms_rounds_body(const RoundsArgs &a, const GridC
             if (__all_sync(0xffffffffu, undecided == 0)) break;  // this warp is finished
         }
         int tot = block_sum(undecided, red);
+        if (epoch == 0) max_stamp(a.dbg, 8);   // (slot 12: the last CTA leaves the sweeps of the first epoch)
         if (tid == 0 && tot) atomicAdd(&a.counters[epoch % 3], tot);
         __threadfence();
         grid.sync();
@@ -1979,7 +2034,7 @@ static int nms_mid_impl(fd_ctx *ctx, const float *boxes, int K, int stride, cons
     m.slices = (K + m.per_slice - 1) / m.per_slice;
     static const bool dbg_on = getenv("FD_NMS_DBG") != nullptr;             // phase timeline of block 0 on stderr
     static long long *dbg_dev = nullptr;
-    if (dbg_on && !dbg_dev) FD_CUDA(cudaMalloc(&dbg_dev, sizeof(long long) * 8));
+    if (dbg_on && !dbg_dev) FD_CUDA(cudaMalloc(&dbg_dev, sizeof(long long) * 16));
     ra.dbg = dbg_on ? dbg_dev : nullptr;
     void *args[] = {&m};
     FD_CUDA(cudaLaunchCooperativeKernel((const void *)nms_mid_kernel, dim3(grid), dim3(NT), args, smem, ctx->stream));
@@ -2107,9 +2162,9 @@ static int nms_big_one_launch(fd_ctx *ctx, const float *boxes, int K, int stride
         cudaStreamSynchronize(ctx->stream);
         cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
         cudaMemcpy(sth, st, sizeof(sth), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[nms big dbg] K=%d grid=%d spatial=%d: keys+stats %.1f  cells %.1f  scan %.1f  scatter %.1f  order %.1f  lists %.1f  sweeps %.1f  output %.1f  kept order %.1f (epochs %d, list refills %d) us, total %.1f\n",
+        fprintf(stderr, "[nms big dbg] K=%d grid=%d spatial=%d: keys+stats %.1f  cells %.1f  scan %.1f  scatter %.1f  order %.1f  lists %.1f  sweeps %.1f (lists loaded by %.1f, first epoch's sweeps until %.1f)  kept order %.1f (epochs %d, list refills %d) us, total %.1f\n",
                 K, ctx->num_sms * per_sm, sth[3], (h[1] - h[0]) * 1e-3, (h[2] - h[1]) * 1e-3, (h[3] - h[2]) * 1e-3, (h[4] - h[3]) * 1e-3,
-                (h[5] - h[4]) * 1e-3, (h[6] - h[5]) * 1e-3, (h[9] - h[6]) * 1e-3, (h[7] - h[9]) * 1e-3, (h[8] - h[7]) * 1e-3, sth[6], sth[7],
+                (h[5] - h[4]) * 1e-3, (h[6] - h[5]) * 1e-3, (h[9] - h[6]) * 1e-3, (h[11] - h[6]) * 1e-3, (h[12] - h[6]) * 1e-3, (h[8] - h[7]) * 1e-3, sth[6], sth[7],
                 (h[8] - h[0]) * 1e-3);
     }
     return FD_OK;
