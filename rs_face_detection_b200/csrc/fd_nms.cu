@@ -677,23 +677,7 @@ __device__ __forceinline__ void adjacency_of(int k, const u64 *__restrict__ keys
     adj_cnt[rank] = cnt;   // may exceed ADJ_CAP: the first ADJ_CAP are listed
 }
 
-// one neighbourhood row (dy = -1, 0, 1) of cell-ordered box k: segment dy + 1 of its list and of its counters (no atomics: three
-// tasks per box triple the parallelism of this latency-bound phase)
-__device__ __forceinline__ void adjacency_row(int k, int dy, const u64 *__restrict__ keys, const GridCfg &c, const int *__restrict__ cell_start,
-                                              const int *__restrict__ cell_end, const float4 *__restrict__ cbox, const float *__restrict__ carea,
-                                              const IouParams &P, int *__restrict__ adj, int *__restrict__ cnt3) {
-    const int rank = (int)(unsigned)keys[k];
-    int cnt = 0;
-    int *mine = adj + (size_t)rank * ADJ_ROW3 + (dy + 1) * ADJ_SEG;
-    for_each_predecessor(k, keys, c, cell_start, cell_end, cbox, carea, P, [&](int rj) {
-        if (cnt < ADJ_SEG) mine[cnt] = rj;
-        ++cnt;
-        return true;
-    }, dy, dy);
-    cnt3[rank * 3 + dy + 1] = cnt;   // may exceed ADJ_SEG: the first ADJ_SEG are listed
-}
-
-// ---- the same two for the one-launch path, which never sorts the boxes globally: boxes are addressed by their position k in
+// ---- the one-launch path never sorts the boxes globally: boxes are addressed by their position k in
 // cell order, members of a cell are ordered by their FULL key (score desc | source index — the order a stable descending sort
 // gives), "earlier-ranked" is a key comparison, and the cell of a box is recomputed from its centre.  visit(j) gets a position.
 template <class F>
@@ -834,24 +818,7 @@ __device__ __forceinline__ void for_each_earlier(int r, const float4 *__restrict
     }
 }
 
-// decides box r if possible; idx(e) yields its e-th listed predecessor
-template <class IdxFn>
-__device__ __forceinline__ int try_decide_listed(int cnt, IdxFn idx, const unsigned char *state) {
-    bool any_kept = false, all_sup = true;
-    for (int e = 0; e < cnt; e += 8) {
-        unsigned sj[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) sj[u] = (e + u < cnt) ? ld_state(state + idx(e + u)) : 2u;  // loads in flight together
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            any_kept |= (sj[u] == 1u);
-            all_sup &= (sj[u] == 2u);
-        }
-    }
-    return any_kept ? 2 : (all_sup ? 1 : 0);
-}
-
-// The same decision over a box's PENDING predecessors, compacted in place: a suppressed predecessor is final and leaves the list, so
+// Decides a box from its PENDING predecessors, compacted in place: a suppressed predecessor is final and leaves the list, so
 // every sweep polls only what is still undecided (the first visit polls the whole list, later ones a handful).  get(e) / put(e, v)
 // access the e-th pending entry.  Returns 0 undecided / 1 kept / 2 suppressed and updates `pend`.
 template <class GetFn, class PutFn>
