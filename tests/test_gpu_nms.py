@@ -77,6 +77,18 @@ def test_dense_crowd_c3(ctx, oracle):
     assert 3000 < len(got) < 30000
 
 
+def test_many_kept_boxes(ctx, oracle):
+    """Sparse boxes: almost everything is kept (> 16 384), so the one-launch path orders its kept keys with the radix passes
+    (index bits, then score bits) instead of all-pairs counting; quantised scores make the index tie-break matter."""
+    dets = _random_dets(40000, 123, canvas=9000, side=(8, 60), score_levels=500)
+    got, exp = ctx.nms(dets, 0.4), oracle.nms(dets, 0.4)
+    assert len(exp) > 20000
+    np.testing.assert_array_equal(got, exp)
+    order = oracle.argsort_descending(dets[:, 4])
+    srt = np.ascontiguousarray(dets[order])
+    np.testing.assert_array_equal(ctx.nms_sorted(srt, 0.4), oracle.nms_sorted(srt, 0.4))
+
+
 @pytest.mark.parametrize("n,levels", [(500, 10), (3000, 50), (20000, 100)])
 def test_ties_and_quantised_boxes(ctx, oracle, n, levels):
     dets = _random_dets(n, 11 + n, canvas=400, quant=4.0, score_levels=levels)
