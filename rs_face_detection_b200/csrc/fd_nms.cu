@@ -771,7 +771,7 @@ struct RoundsArgs {
     int *keep_ranks;
     int *out_state;         // [0] = this path owns the problem, [1] = total kept
     IouParams iou;
-    const float4 *sbox;     // brute mode (mid path: no grid): boxes in rank order, a box without a usable list rescans every earlier box
+    const float4 *sbox;     // brute mode (mid path: no grid): boxes in rank order; a box that exhausts an overflowed list refills it from every earlier box
     int brute;
     int mode;               // brute mode: 0 nms.rs / 1 cpu_nms.rs comparison for the full IEEE test
     const int *status;      // brute mode: [0] NaN score seen, [2] != 0 -> some box is not "fast ok": full IEEE test
@@ -1109,7 +1109,7 @@ __global__ void __launch_bounds__(NT, 1) nms_rounds_kernel(RoundsArgs a) {
 //   2  predecessor lists by brute force: (row tile x column tile) items over the lower triangle, N^2/2 exact IoU tests
 //      (8.4 M at 4 096 boxes);
 //   3  the spatial path's decision sweeps over those lists (nms_rounds_body; a box with more predecessors than a list holds
-//      rescans every earlier box) and its ordered output, written straight as source indices.
+//      refills it from every earlier box once the listed ones are all suppressed) and its ordered output, written straight as source indices.
 constexpr int MID_CAP = 8192;     // measured against nms_big_kernel (host timer): 65.6 vs 83.6 us at 4 096 boxes, 82.0 vs 89.4 at 6 000, 94.3 vs 95.6 at
                                   // 8 192, 166.8 vs 96.0 at 12 288 (against the round-1 launch sequence the crossover was 12 288)
 constexpr int MID_CW = 64;        // column tile of phase 2
