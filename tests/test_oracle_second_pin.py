@@ -1,0 +1,114 @@
+"""A second, independent pin for the oracle's Rust-only arithmetic (the reference holds no expected values for these
+rows and there is no Rust toolchain here): plain numpy float32 restatements written from the Rust sources — array expressions
+in the order the reference evaluates them, every operation rounded to f32 — against the C oracle on random inputs with ties,
+degenerate boxes and thresholds on both sides of the decision.  CPU only."""
+import numpy as np
+import pytest
+
+F = np.float32
+
+
+def np_nms(dets, thr):
+    """processing/nms.rs:3-65, statement by statement (stable descending sort, `ovr <= thresh` survives)."""
+    dets = np.asarray(dets, F)
+    scores = dets[:, 4]
+    # sort_by(|a, b| scores[b].partial_cmp(&scores[a])) is a stable sort by descending score
+    order = sorted(range(len(dets)), key=lambda i: -float(scores[i])) if not np.isnan(scores).any() else None
+    assert order is not None
+    order = np.array(order, np.int64)
+    keep = []
+    with np.errstate(divide="ignore", invalid="ignore"):
+        while len(order):
+            i = order[0]
+            keep.append(int(i))
+            rest = order[1:]
+            xx1 = np.maximum(dets[i, 0], dets[rest, 0])
+            yy1 = np.maximum(dets[i, 1], dets[rest, 1])
+            xx2 = np.minimum(dets[i, 2], dets[rest, 2])
+            yy2 = np.minimum(dets[i, 3], dets[rest, 3])
+            w = np.maximum(F(0), (xx2 - xx1 + F(1)).astype(F))
+            h = np.maximum(F(0), (yy2 - yy1 + F(1)).astype(F))
+            inter = (w * h).astype(F)
+            area_i = F((dets[i, 2] - dets[i, 0] + F(1)) * (dets[i, 3] - dets[i, 1] + F(1)))
+            area_o = ((dets[rest, 2] - dets[rest, 0] + F(1)) * (dets[rest, 3] - dets[rest, 1] + F(1))).astype(F)
+            ovr = (inter / ((area_i + area_o).astype(F) - inter).astype(F)).astype(F)
+            order = rest[ovr <= F(thr)]          # NaN <= thr is false: the box is removed (nms.rs:58)
+    return np.array(keep, np.int64)
+
+
+def _dets(n, seed, canvas=300.0, levels=None, degenerate=False):
+    rng = np.random.default_rng(seed)
+    s = rng.uniform(6, 90, n)
+    x, y = rng.uniform(0, canvas, n), rng.uniform(0, canvas, n)
+    sc = rng.uniform(0.02, 1, n)
+    if levels:
+        sc = np.round(sc * levels) / levels
+    d = np.stack([x, y, x + s, y + s * rng.uniform(0.7, 1.3, n), sc], 1).astype(F)
+    d[:, :4] = np.round(d[:, :4] / 2) * 2          # quantised: overlaps land exactly on simple thresholds
+    if degenerate:
+        d[::7, 2] = d[::7, 0] - 1.0                # zero width: area 0, 0/0 = NaN overlap
+        d[::11, 3] = d[::11, 1] - 5.0              # negative height
+    return d
+
+
+@pytest.mark.parametrize("seed,n,levels,deg", [(1, 300, None, False), (2, 800, 20, False), (3, 500, 5, True), (4, 1, None, False), (5, 64, 3, True)])
+def test_nms_against_numpy_restatement(oracle, seed, n, levels, deg):
+    d = _dets(n, seed, levels=levels, degenerate=deg)
+    for thr in (0.4, 0.25, 0.5, 0.0, 1.0):
+        np.testing.assert_array_equal(oracle.nms(d, thr), np_nms(d, thr))
+
+
+def test_argsort_is_the_stable_descending_order(oracle):
+    rng = np.random.default_rng(9)
+    s = (np.round(rng.uniform(-1, 1, 5000) * 50) / 50).astype(F)     # many ties, both signs, zeros of both signs
+    s[::13] = F(-0.0)
+    s[1::13] = F(0.0)
+    np.testing.assert_array_equal(oracle.argsort_descending(s), np.argsort(-s.astype(np.float64), kind="stable"))
+
+
+def test_clip_and_landmark_pred_against_numpy(oracle):
+    """bbox_transform.rs:27-68 (clip_boxes / clip_points: min then max), :123-160 (landmark_pred: d * size + centre)."""
+    rng = np.random.default_rng(11)
+    n = 400
+    x1, y1 = rng.uniform(-50, 600, n), rng.uniform(-50, 600, n)
+    boxes = np.stack([x1, y1, x1 + rng.uniform(1, 300, n), y1 + rng.uniform(1, 300, n)], 1).astype(F)
+    got = oracle.clip_boxes(boxes.copy(), (480, 640))
+    exp = boxes.copy()
+    exp[:, 0::2] = np.maximum(np.minimum(exp[:, 0::2], F(639)), F(0))
+    exp[:, 1::2] = np.maximum(np.minimum(exp[:, 1::2], F(479)), F(0))
+    np.testing.assert_array_equal(got, exp)
+    pts = rng.uniform(-100, 800, (n, 10)).astype(F)
+    got = oracle.clip_points(pts.copy(), (480, 640))
+    exp = pts.copy()
+    exp[:, 0::2] = np.maximum(np.minimum(exp[:, 0::2], F(639)), F(0))
+    exp[:, 1::2] = np.maximum(np.minimum(exp[:, 1::2], F(479)), F(0))
+    np.testing.assert_array_equal(got, exp)
+    deltas = rng.normal(0, 0.4, (n, 10)).astype(F)
+    w = (boxes[:, 2] - boxes[:, 0] + F(1)).astype(F)
+    h = (boxes[:, 3] - boxes[:, 1] + F(1)).astype(F)
+    cx = (boxes[:, 0] + (F(0.5) * (w - F(1)).astype(F)).astype(F)).astype(F)
+    cy = (boxes[:, 1] + (F(0.5) * (h - F(1)).astype(F)).astype(F)).astype(F)
+    exp = np.empty((n, 10), F)
+    for k in range(5):
+        exp[:, 2 * k] = ((deltas[:, 2 * k] * w).astype(F) + cx).astype(F)
+        exp[:, 2 * k + 1] = ((deltas[:, 2 * k + 1] * h).astype(F) + cy).astype(F)
+    np.testing.assert_array_equal(oracle.landmark_pred(boxes, deltas), exp)
+
+
+def test_nonlinear_pred_against_numpy(oracle):
+    """bbox_transform.rs:90-121: centre/size form, exp of the size deltas (libm expf vs numpy: 1e-6 relative)."""
+    rng = np.random.default_rng(12)
+    n = 400
+    x1, y1 = rng.uniform(0, 600, n), rng.uniform(0, 600, n)
+    boxes = np.stack([x1, y1, x1 + rng.uniform(1, 300, n), y1 + rng.uniform(1, 300, n)], 1).astype(F)
+    d = np.concatenate([rng.normal(0, 0.3, (n, 2)), rng.normal(0, 0.2, (n, 2))], 1).astype(F)
+    w = (boxes[:, 2] - boxes[:, 0] + F(1)).astype(F)
+    h = (boxes[:, 3] - boxes[:, 1] + F(1)).astype(F)
+    cx = (boxes[:, 0] + (F(0.5) * (w - F(1)))).astype(F)
+    cy = (boxes[:, 1] + (F(0.5) * (h - F(1)))).astype(F)
+    pcx = ((d[:, 0] * w).astype(F) + cx).astype(F)
+    pcy = ((d[:, 1] * h).astype(F) + cy).astype(F)
+    pw = (np.exp(d[:, 2]).astype(F) * w).astype(F)
+    ph = (np.exp(d[:, 3]).astype(F) * h).astype(F)
+    exp = np.stack([pcx - F(0.5) * (pw - F(1)), pcy - F(0.5) * (ph - F(1)), pcx + F(0.5) * (pw - F(1)), pcy + F(0.5) * (ph - F(1))], 1).astype(F)
+    np.testing.assert_allclose(oracle.nonlinear_pred(boxes, d), exp, rtol=2e-6, atol=1e-4)
