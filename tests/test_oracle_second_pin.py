@@ -112,3 +112,66 @@ def test_nonlinear_pred_against_numpy(oracle):
     ph = (np.exp(d[:, 3]).astype(F) * h).astype(F)
     exp = np.stack([pcx - F(0.5) * (pw - F(1)), pcy - F(0.5) * (ph - F(1)), pcx + F(0.5) * (pw - F(1)), pcy + F(0.5) * (ph - F(1))], 1).astype(F)
     np.testing.assert_allclose(oracle.nonlinear_pred(boxes, d), exp, rtol=2e-6, atol=1e-4)
+
+
+def np_forward_postprocess(heads, base_anchors, strides, conf_thr, iou_thr, det_scale, image_hw=(640, 640)):
+    """RetinaFaceDetection::_forward after the CNN + _postprocess (face_detection.rs:319-493, bbox_pred :516-549, landmark_pred
+    :551-570, rcnn/anchors.rs:3-21) in numpy float32: EVERY anchor is decoded and clipped, then `>= confidence_threshold`
+    selects, the strides are stacked 32|16|8, sorted by descending score (stable), NMS, rows gathered, `/= det_scale`."""
+    props, scs, lmks = [], [], []
+    for s, stride in enumerate(strides):
+        scores, deltas, ldeltas = (np.asarray(heads[3 * s + k], F) for k in range(3))   # (C,H,W)
+        base = np.asarray(base_anchors[s], F)
+        A = base.shape[0]
+        H, W = deltas.shape[1:]
+        # anchors(): all_anchors[ih, iw, k] = base[k] + (iw*stride, ih*stride, iw*stride, ih*stride)
+        sw = (np.arange(W) * stride).astype(F)[None, :, None]
+        sh = (np.arange(H) * stride).astype(F)[:, None, None]
+        an = np.empty((H, W, A, 4), F)
+        an[..., 0] = base[None, None, :, 0] + sw
+        an[..., 1] = base[None, None, :, 1] + sh
+        an[..., 2] = base[None, None, :, 2] + sw
+        an[..., 3] = base[None, None, :, 3] + sh
+        an = an.reshape(-1, 4)
+        sc = scores[A:].transpose(1, 2, 0).reshape(-1)                     # fg channels, (H,W,A) order
+        d = deltas.transpose(1, 2, 0).reshape(-1, 4)                       # bbox_stds = 1
+        w = (an[:, 2] - an[:, 0] + F(1)).astype(F)
+        h = (an[:, 3] - an[:, 1] + F(1)).astype(F)
+        cx = (an[:, 0] + F(0.5) * (w - F(1))).astype(F)
+        cy = (an[:, 1] + F(0.5) * (h - F(1))).astype(F)
+        pcx = ((d[:, 0] * w).astype(F) + cx).astype(F)
+        pcy = ((d[:, 1] * h).astype(F) + cy).astype(F)
+        pw = (np.exp(d[:, 2]).astype(F) * w).astype(F)
+        ph = (np.exp(d[:, 3]).astype(F) * h).astype(F)
+        box = np.stack([pcx - F(0.5) * (pw - F(1)), pcy - F(0.5) * (ph - F(1)), pcx + F(0.5) * (pw - F(1)), pcy + F(0.5) * (ph - F(1))], 1).astype(F)
+        box[:, 0::2] = np.maximum(np.minimum(box[:, 0::2], F(image_hw[1] - 1)), F(0))
+        box[:, 1::2] = np.maximum(np.minimum(box[:, 1::2], F(image_hw[0] - 1)), F(0))
+        ld = ldeltas.transpose(1, 2, 0).reshape(-1, 5, 2)                  # landmark_std = 1
+        lm = np.empty_like(ld)
+        lm[:, :, 0] = ((ld[:, :, 0] * w[:, None]).astype(F) + cx[:, None]).astype(F)
+        lm[:, :, 1] = ((ld[:, :, 1] * h[:, None]).astype(F) + cy[:, None]).astype(F)
+        sel = np.nonzero(sc >= F(conf_thr))[0]
+        props.append(box[sel]); scs.append(sc[sel]); lmks.append(lm[sel])
+    box, sc, lm = np.concatenate(props), np.concatenate(scs), np.concatenate(lmks)
+    if len(box) == 0:
+        return np.zeros((0, 5), F), np.zeros((0, 5, 2), F), 0
+    order = np.argsort(-sc.astype(np.float64), kind="stable")
+    pre = np.concatenate([box[order], sc[order, None]], 1).astype(F)
+    keep = np_nms(pre, iou_thr)
+    det = pre[keep].copy()
+    det[:, :4] = (det[:, :4] / F(det_scale)).astype(F)
+    return det, (lm[order][keep] / F(det_scale)).astype(F), len(box)
+
+
+@pytest.mark.parametrize("seed,faces,thr,scale", [(21, 12, 0.7, 1.0), (22, 30, 0.5, 0.3333333), (23, 0, 0.7, 0.5), (24, 6, 0.02, 0.59259259)])
+def test_forward_postprocess_against_numpy(oracle, seed, faces, thr, scale):
+    from rs_face_detection_b200.utils import synth
+    heads, _ = synth.make_heads(1, seed=seed, n_faces=faces)
+    heads1 = [h[0] for h in heads]
+    cfg = oracle.make_det_cfg(conf_thr=thr, iou_thr=0.4)
+    det, lmk, K = oracle.detect_post(cfg, heads1, scale)
+    edet, elmk, eK = np_forward_postprocess(heads1, synth.BASE_ANCHORS, synth.STRIDES, thr, 0.4, scale)
+    assert K == eK and det.shape == edet.shape
+    np.testing.assert_array_equal(det[:, 4], edet[:, 4])                 # same boxes picked, same order
+    np.testing.assert_allclose(det[:, :4], edet[:, :4], rtol=2e-6, atol=1e-4)   # expf vs numpy exp
+    np.testing.assert_array_equal(lmk, elmk)                             # no transcendental on this path: bit-exact
