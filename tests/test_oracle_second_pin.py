@@ -175,3 +175,22 @@ def test_forward_postprocess_against_numpy(oracle, seed, faces, thr, scale):
     np.testing.assert_array_equal(det[:, 4], edet[:, 4])                 # same boxes picked, same order
     np.testing.assert_allclose(det[:, :4], edet[:, :4], rtol=2e-6, atol=1e-4)   # expf vs numpy exp
     np.testing.assert_array_equal(lmk, elmk)                             # no transcendental on this path: bit-exact
+
+
+def test_letterbox_geometry_against_numpy(oracle):
+    """_preprocess geometry (face_detection.rs:140-153) in f32 with Rust's truncating `as i32`, over 3 000 random frame sizes
+    (incl. aspect ratios on both sides of the model's, where the f32 quotient decides the branch)."""
+    rng = np.random.default_rng(31)
+    sizes = [(1080, 1920), (2160, 3840), (640, 640), (641, 640), (640, 641), (1, 1), (7, 5000), (5000, 7)]
+    sizes += [(int(h), int(w)) for h, w in zip(rng.integers(1, 5000, 3000), rng.integers(1, 5000, 3000))]
+    for h, w in sizes:
+        im_ratio = F(h) / F(w)
+        model_ratio = F(640) / F(640)
+        if im_ratio > model_ratio:
+            nh = 640
+            nw = int(F(nh) / im_ratio)          # (new_height as f32 / im_ratio) as i32: truncation toward zero
+        else:
+            nw = 640
+            nh = int(F(nw) * im_ratio)
+        ds = F(nh) / F(h)
+        assert oracle.letterbox_geometry(h, w) == (nw, nh, ds), (h, w)
