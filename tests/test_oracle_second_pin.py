@@ -194,3 +194,60 @@ def test_letterbox_geometry_against_numpy(oracle):
             nh = int(F(nw) * im_ratio)
         ds = F(nh) / F(h)
         assert oracle.letterbox_geometry(h, w) == (nw, nh, ds), (h, w)
+
+
+def py_face_selection(img_hw, fb, has_kps, enroll, prm):
+    """FaceSelection::call (face_selection.rs:72-189) and get_biggest_area_face (:28-53) in f32, returning row indices."""
+    H, W = F(img_hw[0]), F(img_hw[1])
+    ml, mr, me, mn = (F(x) for x in prm)
+    if enroll:
+        best, bi = F(0), -1
+        if has_kps:
+            for i, b in enumerate(fb):
+                a = F(F(b[2] - b[0]) * F(b[3] - b[1]))
+                if a > best:
+                    best, bi = a, i
+        return bi, bi
+    mcl, mcr = F(ml * W), F(mr * W)
+    edge = min(F(50.0), F(me * W))
+    x_cen = F(W / F(2))
+    valid = []
+    for i, b in enumerate(fb):
+        area = F(F(b[2] - b[0]) * F(b[2] - b[0]))                         # (:115) the width, squared
+        cw, ch = F(F(b[0] + b[2]) / F(2)), F(F(b[1] + b[3]) / F(2))
+        if cw >= edge and cw <= F(W - edge) and ch >= edge and ch <= F(H - edge) and F(area / F(H * W)) >= mn:
+            valid.append(i)
+    center = [i for i in valid if -mcl <= F(F(F(fb[i][0] + fb[i][2]) / F(2)) - x_cen) <= mcr]
+    if not center:
+        center = valid if valid else list(range(len(fb)))
+    out, mx = -1, F(0)
+    for i in center:
+        t = F(F(fb[i][2] - fb[i][0]) + F(fb[i][3] - fb[i][1]))
+        if t > mx:
+            mx, out = t, i
+    if out < 0:
+        return -1, -1
+    ki = -1
+    if has_kps:
+        o = fb[out]
+        for i, b in enumerate(fb):
+            if abs(F(o[0] - b[0])) <= 2 and abs(F(o[1] - b[1])) <= 2 and abs(F(o[2] - b[2])) <= 2 and abs(F(o[3] - b[3])) <= 2:
+                ki = i
+                break
+    return out, ki
+
+
+def test_face_selection_against_python_restatement(oracle):
+    rng = np.random.default_rng(41)
+    prm = (0.3, 0.3, 0.1, 0.0075)
+    for trial in range(400):
+        H, W = int(rng.integers(200, 2200)), int(rng.integers(200, 3900))
+        n = int(rng.integers(0, 9))
+        x1, y1 = rng.uniform(-20, W, n), rng.uniform(-20, H, n)
+        fb = np.stack([x1, y1, x1 + rng.uniform(2, W / 2, n), y1 + rng.uniform(2, H / 2, n), rng.uniform(0, 1, n)], 1).astype(F).reshape(-1, 5)
+        if n >= 2 and trial % 3 == 0:
+            fb[1, :4] = fb[0, :4] + rng.uniform(-2.5, 2.5, 4).astype(F)     # a near-duplicate: the 2 px key-point match (:160-176)
+        for has_kps in (True, False):
+            for enroll in (False, True):
+                got = oracle.face_selection((H, W), fb, np.zeros((n, 5, 2), F) if has_kps else None, is_enroll=enroll, params=prm)
+                assert got == py_face_selection((H, W), fb, has_kps, enroll, prm), (trial, H, W, has_kps, enroll, fb)
