@@ -251,3 +251,16 @@ def test_face_selection_against_python_restatement(oracle):
             for enroll in (False, True):
                 got = oracle.face_selection((H, W), fb, np.zeros((n, 5, 2), F) if has_kps else None, is_enroll=enroll, params=prm)
                 assert got == py_face_selection((H, W), fb, has_kps, enroll, prm), (trial, H, W, has_kps, enroll, fb)
+
+
+def test_model_preprocessors_against_cv2_numpy(oracle):
+    """The three post-align preprocessors (face_extraction.rs:38-75, face_quality.rs:52-100, face_quality_assessment.rs): cv::resize
+    INTER_LINEAR -> BGR2RGB -> (pixel as f32 - mean) * mul -> CHW, restated with this container's cv2 + numpy f32."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(51)
+    for name, (mean, mul) in oracle.MODEL_NORMS.items():
+        for (h, w), out in (((112, 112), (112, 112)), ((112, 112), (224, 224)), ((97, 131), (112, 112)), ((300, 280), (128, 96))):
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            rgb = cv2.cvtColor(cv2.resize(img, out, interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2RGB).astype(F)
+            exp = ((rgb - np.asarray(mean, F)).astype(F) * np.asarray(mul, F)).astype(F).transpose(2, 0, 1)
+            np.testing.assert_array_equal(oracle.model_preprocess(img, out, mean, mul), exp, err_msg="%s %s -> %s" % (name, (h, w), out))
