@@ -264,3 +264,15 @@ def test_model_preprocessors_against_cv2_numpy(oracle):
             rgb = cv2.cvtColor(cv2.resize(img, out, interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2RGB).astype(F)
             exp = ((rgb - np.asarray(mean, F)).astype(F) * np.asarray(mul, F)).astype(F).transpose(2, 0, 1)
             np.testing.assert_array_equal(oracle.model_preprocess(img, out, mean, mul), exp, err_msg="%s %s -> %s" % (name, (h, w), out))
+
+
+def test_to_tensor_against_numpy(oracle):
+    """face_detection.rs:222-229: im_tensor[0, i, y, x] = (pixel[2 - i] as f32 / pixel_scale - pixel_means[2 - i]) / pixel_stds[2 - i]
+    — BGR -> RGB planes, two f32 divisions, with the reference's identity constants and with non-trivial ones."""
+    rng = np.random.default_rng(61)
+    img = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    for scale, means, stds in ((1.0, (0, 0, 0), (1, 1, 1)), (255.0, (0.406, 0.456, 0.485), (0.225, 0.224, 0.229)), (1.7, (12.5, 0.0, 99.0), (3.0, 0.1, 7.0))):
+        exp = np.empty((1, 3, 37, 53), F)
+        for i in range(3):
+            exp[0, i] = (((img[:, :, 2 - i].astype(F) / F(scale)).astype(F) - F(means[2 - i])).astype(F) / F(stds[2 - i])).astype(F)
+        np.testing.assert_array_equal(oracle.to_tensor(img, scale, means, stds), exp)
