@@ -13,8 +13,12 @@
  * Parity pin status (see DESIGN.md "Oracle"):
  *   - The reference's own tests hold NO expected values (every #[test] only println!s), and the Rust
  *     crate cannot be compiled here (no cargo/rustc).  The Rust-side functions are therefore restated
- *     line by line and pinned only on the reference's test INPUTS with hand-derived answers
- *     (tests/test_oracle_known_answers.py)  ->  "parity unpinned by reference tests" for those.
+ *     line by line and pinned on the reference's test INPUTS with hand-derived answers
+ *     (tests/test_oracle_known_answers.py) and, independently, against numpy / Python float32
+ *     restatements written from the Rust sources (tests/test_oracle_second_pin.py: nms, argsort,
+ *     clip, bbox / landmark pred, the whole post-CNN half of _forward + _postprocess, the letterbox
+ *     geometry, the tensor normalisation, FaceSelection, the model preprocessors)  ->  still
+ *     "parity unpinned by reference tests" for those: no output of the reference itself exists.
  *   - The three OpenCV calls (resize, estimateAffinePartial2D, warpAffine; opencv crate 0.92.0,
  *     Cargo.lock:1175) are restated from OpenCV's published algorithms and PINNED against this
  *     container's cv2 4.13.0 (tests/test_oracle_vs_cv2.py + committed fixtures in tests/golden/).
