@@ -276,3 +276,33 @@ def test_to_tensor_against_numpy(oracle):
         for i in range(3):
             exp[0, i] = (((img[:, :, 2 - i].astype(F) / F(scale)).astype(F) - F(means[2 - i])).astype(F) / F(stds[2 - i])).astype(F)
         np.testing.assert_array_equal(oracle.to_tensor(img, scale, means, stds), exp)
+
+
+def np_cpu_nms(dets, thr):
+    """rcnn/cpu_nms.rs:10-55: every kept box marks EVERY box (earlier ones and itself included) with `ovr >= thresh`; a NaN overlap
+    (zero-area boxes) marks nothing.  (The reference sorts with sort_unstable_by: distinct scores here, so the order is defined.)"""
+    dets = np.asarray(dets, F)
+    x1, y1, x2, y2, sc = (dets[:, k] for k in range(5))
+    areas = ((x2 - x1 + F(1)).astype(F) * (y2 - y1 + F(1)).astype(F)).astype(F)
+    order = np.argsort(-sc.astype(np.float64), kind="stable")
+    sup = np.zeros(len(dets), bool)
+    keep = []
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for i in order:
+            if sup[i]:
+                continue
+            keep.append(int(i))
+            w = np.maximum((np.minimum(x2[i], x2) - np.maximum(x1[i], x1) + F(1)).astype(F), F(0))
+            h = np.maximum((np.minimum(y2[i], y2) - np.maximum(y1[i], y1) + F(1)).astype(F), F(0))
+            inter = (w * h).astype(F)
+            ovr = (inter / ((areas[i] + areas).astype(F) - inter).astype(F)).astype(F)
+            sup |= ovr >= F(thr)
+    return np.array(keep, np.int64)
+
+
+@pytest.mark.parametrize("seed,n,deg", [(71, 400, False), (72, 700, True), (73, 1, False)])
+def test_cpu_nms_against_numpy_restatement(oracle, seed, n, deg):
+    d = _dets(n, seed, degenerate=deg)
+    assert len(np.unique(d[:, 4])) == n
+    for thr in (0.3, 0.4, 0.5, 1.0):
+        np.testing.assert_array_equal(oracle.cpu_nms(d, thr), np_cpu_nms(d, thr))
